@@ -1,0 +1,201 @@
+"""Host-side operator objects over the C ABI: activation views, conv layers (forward, data-gradient,
+weight-gradient launches and their packed-weight images).  Pure plumbing: every arithmetic op is a
+kernel of libcausalgen_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+
+def round16(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+class View:
+    """Channel slice [c0, c0+C) of an NHWC tensor (N,H,W,ld) -- or of a per-sample vector (N,ld)
+    when ``bcast`` (spatially constant parents).  ``C`` is the padded channel count (multiple of 8)."""
+    __slots__ = ("t", "c0", "C", "logical", "bcast")
+
+    def __init__(self, t: torch.Tensor, C: Optional[int] = None, c0: int = 0, logical: Optional[int] = None,
+                 bcast: bool = False):
+        self.t = t
+        self.c0 = c0
+        self.C = t.shape[-1] - c0 if C is None else C
+        self.logical = self.C if logical is None else logical
+        self.bcast = bcast
+
+    @property
+    def ld(self) -> int:
+        return self.t.shape[-1]
+
+    @property
+    def ptr(self) -> int:
+        return self.t.data_ptr() + self.c0 * self.t.element_size()
+
+    @property
+    def rows(self) -> int:
+        return self.t.numel() // self.t.shape[-1]
+
+    def slice(self, c0: int, C: int, logical: Optional[int] = None) -> "View":
+        return View(self.t, C, self.c0 + c0, logical, self.bcast)
+
+
+def new_act(N, H, W, C, device, dtype=torch.bfloat16, logical=None) -> View:
+    """zero-initialised NHWC buffer; padded channels stay zero/finite for the tensor-core K loop"""
+    Cp = round16(C)
+    return View(torch.zeros(N, H, W, Cp, device=device, dtype=dtype), Cp, 0, C if logical is None else logical)
+
+
+@dataclass
+class SegSpec:
+    out: View
+    c0: int                 # first output channel of the conv this segment takes
+    add: Optional[View] = None
+    mul: Optional[View] = None
+    mul_act: int = L.ACT_NONE
+
+
+class PackTable:
+    """All weight-packing descriptors of a model; one kernel launch repacks every conv."""
+
+    def __init__(self, device):
+        self.device = device
+        self.descs: List[L.PackDesc] = []
+        self.keep = []
+        self._dev = None
+
+    def add(self, desc: L.PackDesc):
+        self.descs.append(desc)
+        self._dev = None
+
+    def launch(self, stream):
+        if not self.descs:
+            return
+        if self._dev is None:
+            arr = (L.PackDesc * len(self.descs))(*self.descs)
+            raw = bytes(arr)
+            self._dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
+        L.check(L.load().cg_pack_weights(self._dev.data_ptr(), len(self.descs), stream), "cg_pack_weights")
+
+
+class ConvLayer:
+    """One nn.Conv2d of the reference (weight OIHW fp32 master) as tcgen05 launches.
+
+    src_logical: logical channel count of each K-concatenated source (torch.cat order).
+    taps: k*k, or 1 for a 3x3 conv evaluated on a 1x1 image (only the centre tap touches data).
+    """
+
+    def __init__(self, table: PackTable, weight: torch.Tensor, bias: Optional[torch.Tensor],
+                 src_logical: Sequence[int], act: int, centre_only: bool = False,
+                 grad_srcs: Optional[Sequence[bool]] = None):
+        lib = L.load()
+        self.weight, self.bias = weight, bias
+        self.cout_l, self.cin_l, self.k = weight.shape[0], weight.shape[1], weight.shape[2]
+        assert sum(src_logical) == self.cin_l, (src_logical, self.cin_l)
+        self.src_logical = list(src_logical)
+        self.src_pad = [round16(c) for c in src_logical]
+        self.src_off = [sum(src_logical[:i]) for i in range(len(src_logical))]
+        self.cout_pad = round16(self.cout_l)
+        self.act = act
+        self.taps = 1 if (centre_only or self.k == 1) else self.k * self.k
+        self.ksize = 1 if self.taps == 1 else self.k
+        dev = weight.device
+        kt = self.taps * sum(self.src_pad) // 16
+        self.nc = lib.cg_conv_nchunk(kt, self.cout_pad)
+        nbytes = lib.cg_packed_weight_bytes(kt, self.cout_pad)
+        if self.nc <= 0 or nbytes <= 0:
+            raise RuntimeError(f"conv K={kt * 16} does not fit a resident weight slab")
+        self.wpack = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        d = L.PackDesc()
+        d.w, d.out = weight.data_ptr(), self.wpack.data_ptr()
+        d.cout_l, d.cin_l, d.k = self.cout_l, self.cin_l, self.k
+        d.transpose, d.taps, d.n_pad, d.nc, d.n_off, d.n_log = 0, self.taps, self.cout_pad, self.nc, 0, self.cout_l
+        d.nsrc = len(src_logical)
+        for i in range(d.nsrc):
+            d.src_c[i], d.src_log[i], d.src_off[i] = self.src_pad[i], self.src_logical[i], self.src_off[i]
+        table.add(d)
+        # data-gradient packs (one per source that needs a gradient): K side = dY channels
+        self.wpack_bwd: List[Optional[torch.Tensor]] = []
+        grad_srcs = [True] * len(src_logical) if grad_srcs is None else list(grad_srcs)
+        ktb = self.taps * self.cout_pad // 16
+        for i, need in enumerate(grad_srcs):
+            if not need:
+                self.wpack_bwd.append(None)
+                continue
+            ncb = lib.cg_conv_nchunk(ktb, self.src_pad[i])
+            nb = lib.cg_packed_weight_bytes(ktb, self.src_pad[i])
+            buf = torch.zeros(nb, dtype=torch.uint8, device=dev)
+            b = L.PackDesc()
+            b.w, b.out = weight.data_ptr(), buf.data_ptr()
+            b.cout_l, b.cin_l, b.k = self.cout_l, self.cin_l, self.k
+            b.transpose, b.taps, b.n_pad, b.nc = 1, self.taps, self.src_pad[i], ncb
+            b.n_off, b.n_log, b.nsrc = self.src_off[i], self.src_logical[i], 1
+            b.src_c[0], b.src_log[0], b.src_off[0] = self.cout_pad, self.cout_l, 0
+            table.add(b)
+            self.wpack_bwd.append(buf)
+
+    # ------------------------------------------------------------------ launches
+    @staticmethod
+    def _fill_srcs(arr, srcs: Sequence[View]):
+        for i, s in enumerate(srcs):
+            arr[i].ptr, arr[i].C, arr[i].ld, arr[i].bcast = s.ptr, s.C, s.ld, int(s.bcast)
+
+    @staticmethod
+    def _fill_segs(a, segs: Sequence[SegSpec]):
+        a.nseg = len(segs)
+        for i, sg in enumerate(segs):
+            s = a.seg[i]
+            s.ptr, s.c0, s.cn, s.ld = sg.out.ptr, sg.c0, sg.out.C, sg.out.ld
+            s.dtype = L.F32 if sg.out.t.dtype == torch.float32 else L.BF16
+            s.add = sg.add.ptr if sg.add is not None else None
+            s.add_ld = sg.add.ld if sg.add is not None else 0
+            s.mul = sg.mul.ptr if sg.mul is not None else None
+            s.mul_ld = sg.mul.ld if sg.mul is not None else 0
+            s.mul_act = sg.mul_act
+
+    def forward(self, srcs: Sequence[View], segs: Sequence[SegSpec], N, H, W) -> L.Launch:
+        assert [s.C for s in srcs] == self.src_pad, ([s.C for s in srcs], self.src_pad)
+        a = L.ConvArgs()
+        a.N, a.H, a.W, a.ksize, a.act = N, H, W, self.ksize, self.act
+        a.nsrc, a.cout = len(srcs), self.cout_pad
+        self._fill_srcs(a.src, srcs)
+        self._fill_segs(a, segs)
+        a.wpack = self.wpack.data_ptr()
+        if self.bias is not None:
+            a.bias, a.bias_n = self.bias.data_ptr(), self.cout_l
+        ln = L.Launch("cg_conv2d", C.byref(a))
+        ln.keep = (a, srcs, segs)
+        return ln
+
+    def dgrad(self, i: int, dy: View, seg: SegSpec, N, H, W) -> L.Launch:
+        """dX_i = conv^T(dY) [* act'(x_i)] [+ add]  for source i"""
+        assert dy.C == self.cout_pad and seg.out.C == self.src_pad[i]
+        a = L.ConvArgs()
+        a.N, a.H, a.W, a.ksize, a.act = N, H, W, self.ksize, L.ACT_NONE
+        a.nsrc, a.cout = 1, self.src_pad[i]
+        self._fill_srcs(a.src, [dy])
+        self._fill_segs(a, [seg])
+        a.wpack = self.wpack_bwd[i].data_ptr()
+        ln = L.Launch("cg_conv2d", C.byref(a))
+        ln.keep = (a, dy, seg)
+        return ln
+
+    def wgrad(self, srcs: Sequence[View], dy: View, dw: torch.Tensor, db: Optional[torch.Tensor], N, H, W) -> L.Launch:
+        a = L.WgradArgs()
+        a.N, a.H, a.W, a.ksize, a.act = N, H, W, self.k, self.act
+        a.nsrc = len(srcs)
+        self._fill_srcs(a.src, srcs)
+        a.dy, a.dy_c, a.dy_ld = dy.ptr, dy.C, dy.ld
+        a.dw = dw.data_ptr()
+        a.dbias = db.data_ptr() if db is not None else None
+        a.cout_l, a.cin_l, a.taps = self.cout_l, self.cin_l, self.taps
+        for i in range(len(srcs)):
+            a.src_log[i], a.src_off[i] = self.src_logical[i], self.src_off[i]
+        ln = L.Launch("cg_conv2d_wgrad", C.byref(a))
+        ln.keep = (a, srcs, dy, dw, db)
+        return ln

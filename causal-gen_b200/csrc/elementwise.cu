@@ -1,0 +1,371 @@
+// Resampling, latent sample+KL (forward/backward), mediator mixture and counterfactual combine.
+#include "cg_common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ avg-pool / nearest upsample
+__global__ void avgpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C8, int d,
+                                   int x_ld, int y_ld, int Po) {
+  const int Ho = H / d, Wo = W / d;
+  long long total = (long long)N * Po * Po * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c8 = (int)(i % C8);
+    long long p = i / C8;
+    int wo = (int)(p % Po), ho = (int)((p / Po) % Po), n = (int)(p / ((long long)Po * Po));
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (ho < Ho && wo < Wo) {
+      for (int a = 0; a < d; ++a)
+        for (int b = 0; b < d; ++b) {
+          float f[8];
+          cg_unpack8(__ldg(reinterpret_cast<const uint4*>(
+                         x + ((long long)(n * H + ho * d + a) * W + wo * d + b) * x_ld + c8 * 8)), f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] += f[k];
+        }
+      const float inv = 1.0f / (d * d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] *= inv;
+    }
+    *reinterpret_cast<uint4*>(y + p * y_ld + c8 * 8) = cg_pack8(acc);
+  }
+}
+
+__global__ void avgpool_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int N, int H, int W, int C8,
+                                   int d, int dy_ld, int dx_ld, int Po, int accumulate) {
+  long long total = (long long)N * H * W * C8;
+  const float inv = 1.0f / (d * d);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c8 = (int)(i % C8);
+    long long p = i / C8;
+    int w = (int)(p % W), h = (int)((p / W) % H), n = (int)(p / ((long long)W * H));
+    float f[8];
+    cg_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + ((long long)(n * Po + h / d) * Po + w / d) * dy_ld + c8 * 8)), f);
+    bf16* o = dx + p * dx_ld + c8 * 8;
+    float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (accumulate) cg_unpack8(*reinterpret_cast<const uint4*>(o), g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] += f[k] * inv;
+    *reinterpret_cast<uint4*>(o) = cg_pack8(g);
+  }
+}
+
+__global__ void upsample_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ bias, bf16* __restrict__ y,
+                                    int N, int Hi, int Ho, int C, int x_ld, int y_ld) {
+  const int C8 = (C + 7) / 8;
+  long long total = (long long)N * Ho * Ho * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c8 = (int)(i % C8);
+    long long p = i / C8;
+    int w = (int)(p % Ho), h = (int)((p / Ho) % Ho), n = (int)(p / ((long long)Ho * Ho));
+    int hs = (h * Hi) / Ho, ws = (w * Hi) / Ho;
+    float f[8];
+    cg_unpack8(__ldg(reinterpret_cast<const uint4*>(x + ((long long)(n * Hi + hs) * Hi + ws) * x_ld + c8 * 8)), f);
+    if (bias != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        int c = c8 * 8 + k;
+        if (c < C) f[k] += __ldg(bias + ((long long)c * Ho + h) * Ho + w);
+      }
+    }
+    *reinterpret_cast<uint4*>(y + p * y_ld + c8 * 8) = cg_pack8(f);
+  }
+}
+
+__global__ void upsample_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int N, int Hi, int Ho, int C8,
+                                    int dy_ld, int dx_ld, int accumulate) {
+  long long total = (long long)N * Hi * Hi * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c8 = (int)(i % C8);
+    long long p = i / C8;
+    int w = (int)(p % Hi), h = (int)((p / Hi) % Hi), n = (int)(p / ((long long)Hi * Hi));
+    // destination rows/cols whose nearest source is (h, w): floor(ho*Hi/Ho) == h
+    int h0 = (h * Ho + Hi - 1) / Hi, h1 = ((h + 1) * Ho + Hi - 1) / Hi;
+    int w0 = (w * Ho + Hi - 1) / Hi, w1 = ((w + 1) * Ho + Hi - 1) / Hi;
+    float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bf16* o = dx + p * dx_ld + c8 * 8;
+    if (accumulate) cg_unpack8(*reinterpret_cast<const uint4*>(o), g);
+    for (int a = h0; a < h1; ++a)
+      for (int b = w0; b < w1; ++b) {
+        float f[8];
+        cg_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + ((long long)(n * Ho + a) * Ho + b) * dy_ld + c8 * 8)), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] += f[k];
+      }
+    *reinterpret_cast<uint4*>(o) = cg_pack8(g);
+  }
+}
+
+// dbias[c,h,w] += sum_n dy[n,h,w,c]
+__global__ void upsample_dbias_kernel(const bf16* __restrict__ dy, float* __restrict__ dbias, int N, int Ho, int C,
+                                      int dy_ld) {
+  long long total = (long long)Ho * Ho * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long p = i / C;  // h*Ho + w
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += __bfloat162float(dy[((long long)n * Ho * Ho + p) * dy_ld + c]);
+    dbias[(long long)c * Ho * Ho + p] += s;
+  }
+}
+
+// ------------------------------------------------------------------ Philox4x32-10 -> N(0,1)
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t idx) {
+  uint32_t c0 = (uint32_t)idx, c1 = (uint32_t)(idx >> 32), c2 = 0x243F6A88u, c3 = 0x85A308D3u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  float u1 = ((float)c0 + 0.5f) * 2.3283064365386963e-10f;
+  float u2 = ((float)c1 + 0.5f) * 2.3283064365386963e-10f;
+  return sqrtf(-2.0f * __logf(u1)) * __cosf(6.283185307179586f * u2);
+}
+
+// ------------------------------------------------------------------ latent block forward
+// One block = up to 64 pixels of one image x zdim(16) channels.  eps / z_f32 are NCHW (reference
+// layout), q / p / z_bf16 are NHWC, so the tile goes through shared memory to keep both coalesced.
+constexpr int kLatPix = 64;
+__global__ void __launch_bounds__(256) latent_fwd_kernel(const cg_latent_args a) {
+  __shared__ float s_eps[16][kLatPix + 1];
+  __shared__ float s_z[16][kLatPix + 1];
+  __shared__ float s_red[8];
+  const int n = blockIdx.y;
+  const int hw0 = blockIdx.x * kLatPix;
+  const int npx = min(kLatPix, a.HW - hw0);
+  const int zd = a.zdim;  // 16
+  const int tid = threadIdx.x;
+  if (a.mode != 2) {
+    for (int e = tid; e < zd * kLatPix; e += 256) {
+      int c = e / kLatPix, px = e - c * kLatPix;
+      float v = 0.f;
+      if (px < npx) {
+        long long gi = ((long long)n * zd + c) * a.HW + hw0 + px;
+        v = a.eps != nullptr ? a.eps[gi] : philox_normal(a.seed, a.offset + (uint64_t)gi);
+        if (a.eps_out != nullptr) a.eps_out[gi] = v;
+      }
+      s_eps[c][px] = v;
+    }
+  }
+  __syncthreads();
+  float kl_acc = 0.f;
+  for (int e = tid; e < zd * kLatPix; e += 256) {
+    int px = e / zd, c = e - px * zd;
+    if (px >= npx) continue;
+    long long pix = (long long)n * a.HW + hw0 + px;
+    float p_loc = a.p[pix * a.p_ld + c], p_ls = a.p[pix * a.p_ld + zd + c] + a.log_t;
+    float z;
+    if (a.mode == 0) {
+      float q_loc = a.q[pix * a.q_ld + c], q_ls = a.q[pix * a.q_ld + zd + c] + a.log_t;
+      z = q_loc + __expf(q_ls) * s_eps[c][px];
+      // src/vae.py:14-25 (same term order)
+      float eq = __expf(q_ls), ep = __expf(p_ls), dm = q_loc - p_loc;
+      kl_acc += -0.5f + p_ls - q_ls + 0.5f * (eq * eq + dm * dm) / (ep * ep);
+    } else if (a.mode == 1) {
+      z = p_loc + __expf(p_ls) * s_eps[c][px];
+    } else {
+      z = p_loc;
+    }
+    reinterpret_cast<bf16*>(a.z_bf16)[pix * a.z_ld + c] = __float2bfloat16(z);
+    s_z[c][px] = z;
+  }
+  if (a.kl_out != nullptr && a.mode == 0) {
+    kl_acc = cg_warp_sum(kl_acc);
+    if ((tid & 31) == 0) s_red[tid >> 5] = kl_acc;
+  }
+  __syncthreads();
+  if (a.kl_out != nullptr && a.mode == 0 && tid == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += s_red[i];
+    atomicAdd(a.kl_out + n, s);
+  }
+  if (a.z_f32 != nullptr) {
+    for (int e = tid; e < zd * kLatPix; e += 256) {
+      int c = e / kLatPix, px = e - c * kLatPix;
+      if (px < npx) a.z_f32[((long long)n * zd + c) * a.HW + hw0 + px] = s_z[c][px];
+    }
+  }
+}
+
+// gradients of g_kl*KL + <dz,z> wrt (q_loc,q_ls) and (p_loc,p_ls), written bf16 as channels [0,2*zd)
+__global__ void __launch_bounds__(256) latent_bwd_kernel(const cg_latent_bwd_args a) {
+  __shared__ float s_eps[16][kLatPix + 1];
+  const int n = blockIdx.y;
+  const int hw0 = blockIdx.x * kLatPix;
+  const int npx = min(kLatPix, a.HW - hw0);
+  const int zd = a.zdim;
+  const int tid = threadIdx.x;
+  if (a.mode != 2) {
+    for (int e = tid; e < zd * kLatPix; e += 256) {
+      int c = e / kLatPix, px = e - c * kLatPix;
+      float v = 0.f;
+      if (px < npx) {
+        long long gi = ((long long)n * zd + c) * a.HW + hw0 + px;
+        v = a.eps != nullptr ? a.eps[gi] : philox_normal(a.seed, a.offset + (uint64_t)gi);
+      }
+      s_eps[c][px] = v;
+    }
+  }
+  __syncthreads();
+  bf16* dq = reinterpret_cast<bf16*>(a.dq);
+  bf16* dp = reinterpret_cast<bf16*>(a.dp);
+  for (int e = tid; e < zd * kLatPix; e += 256) {
+    int px = e / zd, c = e - px * zd;
+    if (px >= npx) continue;
+    long long pix = (long long)n * a.HW + hw0 + px;
+    float dz = a.dz != nullptr ? __bfloat162float(reinterpret_cast<const bf16*>(a.dz)[pix * a.dz_ld + c]) : 0.f;
+    float p_loc = a.p[pix * a.p_ld + c], p_ls = a.p[pix * a.p_ld + zd + c];
+    float g_ploc, g_pls;
+    if (a.mode == 0) {
+      float q_loc = a.q[pix * a.q_ld + c], q_ls = a.q[pix * a.q_ld + zd + c];
+      float eq = __expf(q_ls), ivp = __expf(-2.0f * p_ls), dm = q_loc - p_loc;
+      float g_qloc = a.g_kl * dm * ivp + dz;
+      float g_qls = a.g_kl * (eq * eq * ivp - 1.0f) + dz * eq * s_eps[c][px];
+      g_ploc = -a.g_kl * dm * ivp;
+      g_pls = a.g_kl * (1.0f - (eq * eq + dm * dm) * ivp);
+      dq[pix * a.dq_ld + c] = __float2bfloat16(g_qloc);
+      dq[pix * a.dq_ld + zd + c] = __float2bfloat16(g_qls);
+    } else if (a.mode == 1) {
+      g_ploc = dz;
+      g_pls = dz * __expf(p_ls) * s_eps[c][px];
+    } else {
+      g_ploc = dz;
+      g_pls = 0.f;
+    }
+    dp[pix * a.dp_ld + c] = __float2bfloat16(g_ploc);
+    dp[pix * a.dp_ld + zd + c] = __float2bfloat16(g_pls);
+  }
+}
+
+__global__ void latent_mix_kernel(const float* __restrict__ z, const float* __restrict__ q_loc,
+                                  const float* __restrict__ q_ls, const float* __restrict__ p_loc,
+                                  const float* __restrict__ p_ls, float* __restrict__ out, long long n, float alpha,
+                                  float t, int has_t) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    // src/vae.py:487-513
+    float qs = __expf(q_ls[i]);
+    float u = (z[i] - q_loc[i]) / qs;
+    float pv = __expf(p_ls[i]);
+    pv *= pv;
+    float r_loc = alpha * q_loc[i] + (1.0f - alpha) * p_loc[i];
+    float r_sc = sqrtf(alpha * alpha * qs * qs + (1.0f - alpha) * (1.0f - alpha) * pv);
+    if (has_t) r_sc *= t;
+    out[i] = r_loc + r_sc * u;
+  }
+}
+
+__global__ void cf_combine_kernel(const float* __restrict__ x, const float* __restrict__ rec_loc,
+                                  const float* __restrict__ rec_scale, const float* __restrict__ cf_loc,
+                                  const float* __restrict__ cf_scale, float* __restrict__ cf_x, float* __restrict__ sum,
+                                  float* __restrict__ sum2, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    // src/pgm/dscm.py:55-56
+    float u = (x[i] - rec_loc[i]) / fmaxf(rec_scale[i], 1e-12f);
+    float v = fminf(fmaxf(cf_loc[i] + cf_scale[i] * u, -1.0f), 1.0f);
+    cf_x[i] = v;
+    if (sum != nullptr) sum[i] += v;      // src/pgm/dscm.py:59
+    if (sum2 != nullptr) sum2[i] += v * v;  // src/pgm/dscm.py:61
+  }
+}
+
+inline int grid_for(long long work, int threads) {
+  long long b = (work + threads - 1) / threads;
+  if (b > 148LL * 16) b = 148LL * 16;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+extern "C" int cg_avgpool_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, int32_t d,
+                              int32_t x_ld, int32_t y_ld, int32_t pad_to, void* stream) {
+  CG_ARCH_GUARD();
+  CG_REQUIRE(d >= 1 && H % d == 0 && W % d == 0 && H == W, "cg_avgpool_fwd: H=%d W=%d d=%d", H, W, d);
+  CG_REQUIRE(C % 8 == 0 && x_ld % 8 == 0 && y_ld % 8 == 0, "cg_avgpool_fwd: C/ld multiples of 8");
+  const int Po = pad_to > 0 ? pad_to : H / d;
+  CG_REQUIRE(Po >= H / d, "cg_avgpool_fwd: pad_to %d < %d", Po, H / d);
+  avgpool_fwd_kernel<<<grid_for((long long)N * Po * Po * (C / 8), 256), 256, 0, cg_stream(stream)>>>(
+      reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), N, H, W, C / 8, d, x_ld, y_ld, Po);
+  CG_LAUNCH_CHECK("cg_avgpool_fwd");
+  return CG_OK;
+}
+
+extern "C" int cg_avgpool_bwd(const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t C, int32_t d,
+                              int32_t dy_ld, int32_t dx_ld, int32_t pad_to, int32_t accumulate, void* stream) {
+  CG_ARCH_GUARD();
+  CG_REQUIRE(d >= 1 && H % d == 0 && W % d == 0 && H == W, "cg_avgpool_bwd: H=%d W=%d d=%d", H, W, d);
+  CG_REQUIRE(C % 8 == 0 && dy_ld % 8 == 0 && dx_ld % 8 == 0, "cg_avgpool_bwd: C/ld multiples of 8");
+  const int Po = pad_to > 0 ? pad_to : H / d;
+  avgpool_bwd_kernel<<<grid_for((long long)N * H * W * (C / 8), 256), 256, 0, cg_stream(stream)>>>(
+      reinterpret_cast<const bf16*>(dy), reinterpret_cast<bf16*>(dx), N, H, W, C / 8, d, dy_ld, dx_ld, Po, accumulate);
+  CG_LAUNCH_CHECK("cg_avgpool_bwd");
+  return CG_OK;
+}
+
+extern "C" int cg_upsample_fwd(const void* x, const float* bias, void* y, int32_t N, int32_t Hi, int32_t Ho, int32_t C,
+                               int32_t x_ld, int32_t y_ld, void* stream) {
+  CG_ARCH_GUARD();
+  CG_REQUIRE(Ho >= Hi && x_ld % 8 == 0 && y_ld % 8 == 0, "cg_upsample_fwd: Hi=%d Ho=%d", Hi, Ho);
+  upsample_fwd_kernel<<<grid_for((long long)N * Ho * Ho * ((C + 7) / 8), 256), 256, 0, cg_stream(stream)>>>(
+      reinterpret_cast<const bf16*>(x), bias, reinterpret_cast<bf16*>(y), N, Hi, Ho, C, x_ld, y_ld);
+  CG_LAUNCH_CHECK("cg_upsample_fwd");
+  return CG_OK;
+}
+
+extern "C" int cg_upsample_bwd(const void* dy, void* dx, float* dbias, int32_t N, int32_t Hi, int32_t Ho, int32_t C,
+                               int32_t dy_ld, int32_t dx_ld, int32_t accumulate, void* stream) {
+  CG_ARCH_GUARD();
+  CG_REQUIRE(Ho >= Hi && dy_ld % 8 == 0 && dx_ld % 8 == 0, "cg_upsample_bwd: Hi=%d Ho=%d", Hi, Ho);
+  if (dx != nullptr) {
+    upsample_bwd_kernel<<<grid_for((long long)N * Hi * Hi * ((C + 7) / 8), 256), 256, 0, cg_stream(stream)>>>(
+        reinterpret_cast<const bf16*>(dy), reinterpret_cast<bf16*>(dx), N, Hi, Ho, (C + 7) / 8, dy_ld, dx_ld, accumulate);
+    CG_LAUNCH_CHECK("cg_upsample_bwd");
+  }
+  if (dbias != nullptr) {
+    upsample_dbias_kernel<<<grid_for((long long)Ho * Ho * C, 256), 256, 0, cg_stream(stream)>>>(
+        reinterpret_cast<const bf16*>(dy), dbias, N, Ho, C, dy_ld);
+    CG_LAUNCH_CHECK("cg_upsample_bwd(dbias)");
+  }
+  return CG_OK;
+}
+
+extern "C" int cg_latent_fwd(const cg_latent_args* a, void* stream) {
+  CG_ARCH_GUARD();
+  CG_REQUIRE(a != nullptr && a->zdim == 16, "cg_latent_fwd: zdim must be 16");
+  CG_REQUIRE(a->p != nullptr && a->z_bf16 != nullptr && (a->mode != 0 || a->q != nullptr), "cg_latent_fwd: null operand");
+  dim3 grid(cg_ceil_div(a->HW, kLatPix), a->N);
+  latent_fwd_kernel<<<grid, 256, 0, cg_stream(stream)>>>(*a);
+  CG_LAUNCH_CHECK("cg_latent_fwd");
+  return CG_OK;
+}
+
+extern "C" int cg_latent_bwd(const cg_latent_bwd_args* a, void* stream) {
+  CG_ARCH_GUARD();
+  CG_REQUIRE(a != nullptr && a->zdim == 16, "cg_latent_bwd: zdim must be 16");
+  CG_REQUIRE(a->p != nullptr && a->dp != nullptr && (a->mode != 0 || (a->q != nullptr && a->dq != nullptr)),
+             "cg_latent_bwd: null operand");
+  dim3 grid(cg_ceil_div(a->HW, kLatPix), a->N);
+  latent_bwd_kernel<<<grid, 256, 0, cg_stream(stream)>>>(*a);
+  CG_LAUNCH_CHECK("cg_latent_bwd");
+  return CG_OK;
+}
+
+extern "C" int cg_latent_mix(const float* z, const float* q_loc, const float* q_ls, const float* p_loc,
+                             const float* p_ls, float* out, int64_t n, float alpha, float t, int32_t has_t,
+                             void* stream) {
+  CG_ARCH_GUARD();
+  latent_mix_kernel<<<grid_for(n, 256), 256, 0, cg_stream(stream)>>>(z, q_loc, q_ls, p_loc, p_ls, out, n, alpha, t, has_t);
+  CG_LAUNCH_CHECK("cg_latent_mix");
+  return CG_OK;
+}
+
+extern "C" int cg_cf_combine(const float* x, const float* rec_loc, const float* rec_scale, const float* cf_loc,
+                             const float* cf_scale, float* cf_x, float* sum, float* sum2, int64_t n, void* stream) {
+  CG_ARCH_GUARD();
+  cf_combine_kernel<<<grid_for(n, 256), 256, 0, cg_stream(stream)>>>(x, rec_loc, rec_scale, cf_loc, cf_scale, cf_x, sum,
+                                                                     sum2, n);
+  CG_LAUNCH_CHECK("cg_cf_combine");
+  return CG_OK;
+}

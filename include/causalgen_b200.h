@@ -1,0 +1,287 @@
+/* causalgen_b200 -- C ABI of the B200 (sm_100a) HVAE causal-mechanism engine.
+ *
+ * The reference (biomedia-mira/causal-gen) has no FFI: its boundary for this path is the
+ * Python nn.Module surface of src/vae.py / src/dmol.py / src/pgm/dscm.py.  This header is
+ * the C boundary UNDER that surface: every arithmetic op the path executes is one of the
+ * entry points below.  Each entry cites the reference lines whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller (PyTorch) owns every buffer, the library
+ *     never allocates, frees or synchronises device memory (CUDA-graph capturable);
+ *   - every launch goes on the `stream` argument (a cudaStream_t passed as void*);
+ *   - return 0 on success, a negative cg_status otherwise; cg_last_error() gives the text;
+ *   - activations are NHWC bf16 with a channel pitch `ld` (elements) so channel slices of a
+ *     wider buffer are valid operands; channel counts handed to the tensor-core kernels are
+ *     multiples of 16 (zero padded); latent statistics / KL / likelihood math is fp32;
+ *   - sm_100a only: any other device returns CG_ERR_ARCH.  There is no CPU fallback.
+ */
+#ifndef CAUSALGEN_B200_H
+#define CAUSALGEN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  CG_OK = 0,
+  CG_ERR_ARG = -1,     /* bad shape / alignment / enum */
+  CG_ERR_ARCH = -2,    /* device is not sm_100 */
+  CG_ERR_CUDA = -3,    /* CUDA runtime error (text in cg_last_error) */
+  CG_ERR_UNSUPPORTED = -4
+} cg_status;
+
+enum { CG_ACT_NONE = 0, CG_ACT_RELU = 1, CG_ACT_GELU = 2 };   /* nn.ReLU / nn.GELU(erf), src/vae.py:50,58 */
+enum { CG_BF16 = 0, CG_F32 = 1 };
+
+int cg_version(void);
+const char* cg_last_error(void);
+/* number of SMs of the current device, 0 if it is not sm_100 */
+int cg_device_sms(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Convolution (implicit GEMM on tcgen05, fp32 accumulation in TMEM)
+ *   replaces nn.Conv2d forward/backward in Block / DecoderBlock: src/vae.py:49-84,165-170
+ * ------------------------------------------------------------------------------------- */
+#define CG_MAX_SRC 3
+#define CG_MAX_SEG 4
+
+typedef struct {
+  const void* ptr;  /* bf16, (N,H,W,ld) -- or (N,ld) when bcast!=0 (spatially constant parents) */
+  int32_t C;        /* channels taken from this source, multiple of 16 */
+  int32_t ld;       /* channel pitch in elements */
+  int32_t bcast;    /* 1: per-sample vector broadcast over H,W (zero outside the image) */
+  int32_t _pad;
+} cg_src;
+
+typedef struct {
+  void* ptr;        /* destination of output channels [c0, c0+cn) */
+  const void* add;  /* optional bf16 tensor added after everything else (residual / accumulate) */
+  const void* mul;  /* optional bf16 pre-activation tensor x: result *= act'(x)  (backward) */
+  int32_t c0, cn;   /* c0 multiple of 16, cn multiple of 8 */
+  int32_t ld, add_ld, mul_ld;
+  int32_t dtype;    /* CG_BF16 or CG_F32 */
+  int32_t mul_act;  /* activation whose derivative is applied with `mul` */
+  int32_t _pad;
+} cg_seg;
+
+typedef struct {
+  int32_t N, H, W;     /* stride 1, "same" padding: output spatial == input spatial */
+  int32_t ksize;       /* 1 or 3 */
+  int32_t act;         /* activation applied to the (concatenated) input on load */
+  int32_t nsrc, nseg;
+  int32_t cout;        /* output channels incl. zero padding, multiple of 16 */
+  cg_src src[CG_MAX_SRC];   /* K-concatenated inputs: torch.cat([...], dim=1) without the copy */
+  cg_seg seg[CG_MAX_SEG];   /* channel-split outputs (loc | logscale | features ...) */
+  const void* wpack;   /* weights packed by cg_pack_weights for exactly this (src list, cout) */
+  const float* bias;   /* fp32 [bias_n] or NULL */
+  int32_t bias_n;      /* valid bias entries (logical output channels); the rest is 0 */
+  int32_t _pad;
+} cg_conv_args;
+
+/* y = conv(act(cat(src))) + bias, split/added per segment.  Also the data-gradient pass when
+ * given transposed+flipped packed weights and seg.mul = saved pre-activation. */
+int cg_conv2d(const cg_conv_args* a, void* stream);
+
+/* GEMM-N chunk (output channels per CTA) the conv kernel uses for this problem size; the packed
+ * weight image is laid out per chunk, so cg_pack_desc.nc must carry this value */
+int32_t cg_conv_nchunk(int32_t ktot16, int32_t cout);
+/* bytes of the packed-weight image for a conv with `ktot16` K-blocks of 16 (= taps * sum(C)/16) */
+int64_t cg_packed_weight_bytes(int32_t ktot16, int32_t cout);
+
+typedef struct {
+  const float* w;      /* fp32 OIHW master weight (Cout_l, Cin_l, k, k) -- reference layout */
+  void* out;           /* bf16 packed image */
+  int32_t cout_l, cin_l, k;   /* logical dims of w */
+  int32_t transpose;   /* 0: forward pack; 1: data-gradient pack (swap O/I, flip taps) */
+  int32_t taps;        /* taps packed: k*k, or 1 = centre tap only (3x3 conv on a 1x1 image) */
+  int32_t n_pad;       /* GEMM-N (padded output channels of this pass), multiple of 16 */
+  int32_t nc;          /* cg_conv_nchunk(ktot16, n_pad) */
+  int32_t n_off;       /* forward: 0.  transpose: first logical input channel of the source */
+  int32_t n_log;       /* logical channels valid on the N side (others are zero) */
+  int32_t nsrc;        /* K side: sources in concat order */
+  int32_t src_c[CG_MAX_SRC];      /* padded channels per source (multiple of 16) */
+  int32_t src_log[CG_MAX_SRC];    /* logical channels per source */
+  int32_t src_off[CG_MAX_SRC];    /* first logical channel of the source on the K side */
+} cg_pack_desc;
+
+/* pack `n` weight tensors in one launch; `descs_dev` is a device copy of the descriptors */
+int cg_pack_weights(const cg_pack_desc* descs_dev, int32_t n, void* stream);
+
+typedef struct {
+  int32_t N, H, W, ksize, act;
+  int32_t nsrc;
+  cg_src src[CG_MAX_SRC];  /* forward inputs (activation re-applied on load) */
+  const void* dy;          /* bf16 (N,H,W,dy_ld) gradient of the conv output */
+  int32_t dy_c, dy_ld;     /* padded channels (multiple of 16), pitch */
+  float* dw;               /* fp32 OIHW gradient, ACCUMULATED into (atomics) */
+  float* dbias;            /* fp32 [cout_l] accumulated, or NULL */
+  int32_t cout_l, cin_l;   /* logical dims of dw */
+  int32_t src_log[CG_MAX_SRC], src_off[CG_MAX_SRC];
+  int32_t taps;            /* k*k or 1 (centre tap only) */
+} cg_wgrad_args;
+
+/* dW += sum_pixels dy (x) act(cat(src)) shifted per tap; dbias += sum_pixels dy */
+int cg_conv2d_wgrad(const cg_wgrad_args* a, void* stream);
+
+/* 7x7 stem, fp32 NCHW image in -> bf16 NHWC out (src/vae.py:104-110,126) and its weight grad */
+int cg_stem_fwd(const float* x, const float* w, const float* b, void* y, int32_t N, int32_t Cin,
+                int32_t R, int32_t Cout, int32_t y_ld, void* stream);
+int cg_stem_wgrad(const float* x, const void* dy, float* dw, float* db, int32_t N, int32_t Cin,
+                  int32_t R, int32_t Cout, int32_t dy_ld, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Resampling: F.avg_pool2d (src/vae.py:79-83), F.interpolate nearest + learned bias
+ * (src/vae.py:251-262), F.pad odd resolutions (src/vae.py:130-132); NHWC bf16
+ * ------------------------------------------------------------------------------------- */
+int cg_avgpool_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, int32_t d,
+                   int32_t x_ld, int32_t y_ld, int32_t pad_to, void* stream);
+/* dx (+)= avgpool^T(dy); accumulate!=0 adds into dx */
+int cg_avgpool_bwd(const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t C, int32_t d,
+                   int32_t dy_ld, int32_t dx_ld, int32_t pad_to, int32_t accumulate, void* stream);
+/* y[n,h,w,c] = bias[c,h,w] + x[n,h/s,w/s,c]; bias fp32 (C,Ho,Wo) reference layout or NULL.
+ * Ho need not be a multiple of Hi (7 -> 8 style): source index floor(h*Hi/Ho). */
+int cg_upsample_fwd(const void* x, const float* bias, void* y, int32_t N, int32_t Hi, int32_t Ho,
+                    int32_t C, int32_t x_ld, int32_t y_ld, void* stream);
+/* dx (+)= sum over replicas of dy; dbias += sum over batch of dy (fp32, may be NULL) */
+int cg_upsample_bwd(const void* dy, void* dx, float* dbias, int32_t N, int32_t Hi, int32_t Ho,
+                    int32_t C, int32_t dy_ld, int32_t dx_ld, int32_t accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Latent blocks: sample_gaussian + gaussian_kl fused (src/vae.py:14-30,268-269)
+ *   q,p: fp32 NHWC (npix, 32) = [loc(16) | logscale(16)]; eps fp32 NCHW (N,16,H,W) (reference
+ *   layout, drawn by the caller) or NULL -> in-kernel Philox(seed, block offset).
+ *   z_bf16: (npix, z_ld) conv operand; z_f32: NCHW (N,16,H,W) fp32 or NULL (abduct output);
+ *   kl_out: fp32 [N] += sum over (16,H,W) of the block's KL.
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* q; const float* p; int32_t q_ld, p_ld;
+  const float* eps; uint64_t seed; uint64_t offset;
+  float log_t;            /* log temperature added to both logscales (0 when t is None) */
+  void* z_bf16; int32_t z_ld;
+  float* z_f32;
+  float* eps_out;         /* optional: NCHW eps actually used (needed by backward in Philox mode) */
+  float* kl_out;          /* [N] accumulated, or NULL */
+  int32_t N, HW, zdim;
+  int32_t mode;           /* 0: z~q, KL(q||p)   1: z~p (prior sample)   2: z=p_loc (deterministic) */
+} cg_latent_args;
+int cg_latent_fwd(const cg_latent_args* a, void* stream);
+
+/* gradients of  sum_n g_kl * kl[n]  +  <dz, z>  w.r.t. q and p statistics, written as bf16
+ * into the conv-output-gradient buffers dq (npix,dq_ld) and dp (npix,dp_ld) channels [0,32) */
+typedef struct {
+  const float* q; const float* p; int32_t q_ld, p_ld;
+  const float* eps;           /* NCHW eps used in forward, or NULL -> regenerate Philox(seed, offset) */
+  uint64_t seed; uint64_t offset;
+  const void* dz; int32_t dz_ld;   /* bf16 gradient wrt z (npix, dz_ld) or NULL */
+  float g_kl;                 /* d loss / d kl[n]  (= beta / (B * C*H*W)) */
+  void* dq; int32_t dq_ld; void* dp; int32_t dp_ld;
+  int32_t N, HW, zdim, mode;
+} cg_latent_bwd_args;
+int cg_latent_bwd(const cg_latent_bwd_args* a, void* stream);
+
+/* mediator mixture r = alpha q + (1-alpha) p of HVAE.abduct (src/vae.py:485-513); all fp32 NCHW */
+int cg_latent_mix(const float* z, const float* q_loc, const float* q_ls, const float* p_loc,
+                  const float* p_ls, float* out, int64_t n, float alpha, float t, int32_t has_t,
+                  void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Likelihoods
+ * ------------------------------------------------------------------------------------- */
+/* DGaussNet (src/vae.py:322-422): 1x1 heads fused with the discretised-Gaussian NLL.
+ * h bf16 (npix, h_ld) with Cw channels; x fp32 NCHW (N,C,H,W); w_* fp32 (C,Cw); C in {1,3}. */
+typedef struct {
+  const void* h; int32_t h_ld, Cw;
+  const float* x;
+  const float *w_loc, *b_loc, *w_ls, *b_ls, *w_co, *b_co;   /* w_co/b_co NULL when C==1 */
+  int32_t N, HW, C;
+  float* nll;        /* fwd: [N] accumulated: -mean over (C,H,W) of log-prob */
+  float g;           /* bwd: d loss / d nll[n]  (= 1/B) */
+  void* dh; int32_t dh_ld;                  /* bwd: bf16 (npix, dh_ld) written */
+  float *dw_loc, *db_loc, *dw_ls, *db_ls, *dw_co, *db_co;   /* bwd: accumulated */
+} cg_dgauss_args;
+int cg_dgauss_nll_fwd(const cg_dgauss_args* a, void* stream);
+int cg_dgauss_nll_bwd(const cg_dgauss_args* a, void* stream);
+/* likelihood.sample(h, return_loc=True): x = clamp(loc), scale = exp(logscale) as fp32 NCHW;
+ * eps!=NULL -> x = clamp(loc + exp(logscale + log_t) * eps) (intended return_loc=False semantics) */
+int cg_dgauss_sample(const cg_dgauss_args* a, float* x_out, float* scale_out, const float* eps,
+                     float log_t, void* stream);
+
+/* DmolNet (src/dmol.py:24-245): 1x1 conv to 100 channels fused with the mixture loss.
+ * w (100,Cw) b (100) fp32; x fp32 NCHW (N,3,H,W). */
+typedef struct {
+  const void* h; int32_t h_ld, Cw;
+  const float* x; const float* w; const float* b;
+  int32_t N, HW;
+  float* nll;   /* fwd [N] accumulated */
+  float g; void* dh; int32_t dh_ld; float* dw; float* db;   /* bwd */
+} cg_dmol_args;
+int cg_dmol_loss_fwd(const cg_dmol_args* a, void* stream);
+int cg_dmol_loss_bwd(const cg_dmol_args* a, void* stream);
+/* mode 0 soft mean, 1 hard (argmax) mean, 2 sample (u_gumbel (N,H,W,10), u_logistic (N,H,W,3)
+ * uniform(1e-5,1-1e-5) drawn by caller); outputs fp32 NCHW x (clamped) and scale */
+int cg_dmol_predict(const cg_dmol_args* a, int32_t mode, const float* u_gumbel,
+                    const float* u_logistic, float log_t, float* x_out, float* scale_out,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * DSCM counterfactual combine (src/pgm/dscm.py:55-72), fp32 NCHW
+ *   u = (x-rec_loc)/max(rec_scale,1e-12); cf = clamp(cf_loc + cf_scale*u, -1, 1)
+ *   sum/sum2 (optional) accumulate particles.
+ * ------------------------------------------------------------------------------------- */
+int cg_cf_combine(const float* x, const float* rec_loc, const float* rec_scale, const float* cf_loc,
+                  const float* cf_scale, float* cf_x, float* sum, float* sum2, int64_t n,
+                  void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Layout glue (src/trainer.py:16-21, src/pgm/dscm.py:121-132)
+ * ------------------------------------------------------------------------------------- */
+/* uint8 (N,C,H,W) -> fp32 NCHW (x-127.5)/127.5 */
+int cg_normalise_u8(const uint8_t* x8, float* x, int64_t n, void* stream);
+/* parents (N,ctx,R,R) fp32 [sampled at pixel (0,0)] or (N,ctx) -> bf16 (N,ld) zero padded;
+ * channels >= drop_from multiplied by drop_scale (conditioning dropout, src/vae.py:244-247) */
+int cg_parents_pack(const float* pa, int64_t sample_stride, int64_t chan_stride, void* out,
+                    int32_t N, int32_t ctx, int32_t ld, int32_t drop_from, float drop_scale,
+                    void* stream);
+int cg_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t N, int32_t C, int32_t HW, int32_t ld,
+                             void* stream);
+int cg_nhwc_bf16_to_nchw_f32(const void* x, float* y, int32_t N, int32_t C, int32_t HW, int32_t ld,
+                             void* stream);
+/* fp32 NHWC statistics slice [c0,c0+C) (+add) -> fp32 NCHW (abduct's q_loc/q_logscale dict entries) */
+int cg_stats_to_nchw(const float* src, int32_t ld, int32_t c0, float add, float* dst, int32_t N, int32_t C,
+                     int32_t HW, void* stream);
+/* y[n, :] = v[:] for every pixel (decoder initial state bias[1].repeat, src/vae.py:232) */
+int cg_fill_rows(const float* v, void* y, int64_t rows, int32_t C, int32_t ld, void* stream);
+/* dv[c] += sum_rows dy[row,c] (fp32 accumulate): bias gradients */
+int cg_colsum(const void* dy, float* dv, int64_t rows, int32_t C, int32_t ld, void* stream);
+/* y = a + b (bf16, same pitch rules) */
+int cg_add(const void* a, const void* b, void* y, int64_t rows, int32_t C, int32_t a_ld, int32_t b_ld,
+           int32_t y_ld, void* stream);
+
+/* elbo = mean(nll) + beta*mean(kl)/npix_dims  (src/vae.py:451-458); out[3] = {elbo,nll,kl} */
+int cg_elbo_finalize(const float* nll, const float* kl, float* out, int32_t N, float kl_scale,
+                     float beta, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Optimiser tail on flat fp32 buffers (src/trainer.py:66-87, src/train_setup.py:42-53,
+ * src/utils.py:169-220): global-norm clip, NaN/skip test, AdamW, EMA -- no host sync.
+ * ------------------------------------------------------------------------------------- */
+int cg_sumsq(const float* g, float* out /* [1] accumulated */, int64_t n, void* stream);
+/* Device-side step bookkeeping so the whole training step is CUDA-graph replayable:
+ *   state[4] (int32): {adam step t, ema update calls, skipped updates, skip flag of this step}
+ *   dyn[6]   (fp32) : {lr, 1-b1^t, 1-b2^t, ema decay, grad scale*clip coefficient, grad norm}
+ * gsumsq = sum of squares of the (all-reduced, still unscaled) flat gradient; grad_scale = 1/world.
+ * Skips (flag=1, counters untouched) when the norm >= grad_skip or nll/kl in loss_terms[3] is NaN. */
+int cg_optim_advance(int32_t* state, float* dyn, const float* gsumsq, const float* loss_terms,
+                     float base_lr, int32_t warmup, float beta1, float beta2, float grad_clip,
+                     float grad_skip, float grad_scale, float ema_beta, int32_t ema_after, void* stream);
+/* p,m,v,ema updated in place from g using state/dyn written by cg_optim_advance; ema may be NULL */
+int cg_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, int64_t n,
+                      const int32_t* state, const float* dyn, float beta1, float beta2, float eps,
+                      float wd, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAUSALGEN_B200_H */

@@ -1,0 +1,499 @@
+"""Kernel-level numerics on a real B200: every C-ABI op against a plain PyTorch fp32 reference of the
+same op (TF32 off) on identical, bf16-representable inputs.  Tolerances: bf16 outputs are compared at
+bf16 resolution (rel 1e-2 of the tensor scale), fp32 outputs at 2e-3."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _setup():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from causalgen_b200 import _lib
+    _lib.load()
+    yield
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def nhwc_bf16(x_nchw, pad_to=None):
+    """(N,C,H,W) fp32 -> zero padded NHWC bf16 buffer"""
+    from causalgen_b200.ops import round16
+    N, Cc, H, W = x_nchw.shape
+    Cp = pad_to or round16(Cc)
+    out = torch.zeros(N, H, W, Cp, device=DEV, dtype=torch.bfloat16)
+    out[..., :Cc] = x_nchw.permute(0, 2, 3, 1).to(torch.bfloat16)
+    return out
+
+
+def to_nchw(t_nhwc, C):
+    return t_nhwc[..., :C].permute(0, 3, 1, 2).float()
+
+
+def act_fn(a):
+    return {0: (lambda v: v), 1: F.relu, 2: F.gelu}[a]
+
+
+def assert_close(ours, ref, rel, what=""):
+    scale = ref.abs().max().item() + 1e-6
+    err = (ours - ref).abs().max().item()
+    assert err <= rel * scale, f"{what}: max err {err:.4g} vs scale {scale:.4g} (rel {err / scale:.3g} > {rel})"
+
+
+CONV_CASES = [
+    # N, H, W, src channels, bcast ctx, cout, k, act
+    (2, 16, 16, [32], 0, 16, 3, 1),
+    (3, 12, 12, [64], 0, 24, 3, 1),
+    (2, 24, 24, [48, 48], 4, 8, 3, 1),          # posterior-style cat[h, pa, x]
+    (2, 6, 6, [40], 0, 176, 3, 2),              # N > 128 columns, odd widths
+    (5, 1, 1, [128], 12, 544, 1, 2),            # res-1 1x1, Cout > 256 -> N chunks
+    (2, 32, 32, [16], 0, 4, 1, 2),              # tiny bottleneck
+    (1, 48, 48, [24], 0, 128, 3, 1),
+    (2, 8, 8, [16], 20, 64, 1, 0),              # z_proj-style cat[z, pa], no activation
+    (1, 7, 7, [32], 0, 16, 3, 0),               # odd resolution
+]
+
+
+def run_conv(N, H, W, chans, ctx, cout, k, act, seed=0):
+    from causalgen_b200 import _lib as L
+    from causalgen_b200.ops import ConvLayer, PackTable, SegSpec, View, new_act, round16
+    xs = [rnd(N, c, H, W, seed=seed + i) for i, c in enumerate(chans)]
+    views = [View(nhwc_bf16(x), round16(c), 0, c) for x, c in zip(xs, chans)]
+    logical = list(chans)
+    pa = None
+    if ctx:
+        pa = rnd(N, ctx, seed=seed + 9)
+        pat = torch.zeros(N, round16(ctx), device=DEV, dtype=torch.bfloat16)
+        pat[:, :ctx] = pa.to(torch.bfloat16)
+        views.insert(1, View(pat, round16(ctx), 0, ctx, bcast=True))
+        logical.insert(1, ctx)
+    cin = sum(logical)
+    w = rnd(cout, cin, k, k, scale=1.0 / math.sqrt(cin * k * k), seed=seed + 20)
+    b = rnd(cout, scale=0.1, seed=seed + 21)
+    table = PackTable(DEV)
+    layer = ConvLayer(table, w, b, logical, act)
+    table.launch(stream())
+    out = new_act(N, H, W, cout, DEV)
+    layer.forward(views, [SegSpec(out, 0)], N, H, W)(stream())
+    torch.cuda.synchronize()
+    # reference on the same bf16-rounded operands
+    parts = [to_nchw(v.t, c) for v, c in zip([v for v in views if not v.bcast], chans)]
+    if ctx:
+        parts.insert(1, pat[:, :ctx].float()[:, :, None, None].expand(N, ctx, H, W))
+    xin = act_fn(act)(torch.cat(parts, 1))
+    ref = F.conv2d(xin, w.to(torch.bfloat16).float(), b, padding=k // 2)
+    return layer, views, out, ref, w, b
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_forward(case):
+    N, H, W, chans, ctx, cout, k, act = case
+    layer, views, out, ref, w, b = run_conv(*case)
+    assert_close(to_nchw(out.t, cout), ref, 1e-2, f"conv fwd {case}")
+    # padded output channels must be exactly zero
+    if out.t.shape[-1] > cout:
+        assert out.t[..., cout:].abs().max().item() == 0.0
+
+
+def test_conv_segments_add_and_fp32_split():
+    from causalgen_b200.ops import SegSpec, View, new_act
+    N, H, W = 2, 12, 12
+    layer, views, out, ref, w, b = run_conv(N, H, W, [32], 0, 32 + 48, 3, 1, seed=3)
+    stats = View(torch.zeros(N, H, W, 32, device=DEV, dtype=torch.float32), 32)
+    feat = new_act(N, H, W, 48, DEV)
+    hsum = new_act(N, H, W, 48, DEV)
+    h = View(nhwc_bf16(rnd(N, 48, H, W, seed=77)), 48)
+    layer.forward(views, [SegSpec(stats, 0), SegSpec(feat, 32), SegSpec(hsum, 32, add=h)], N, H, W)(stream())
+    torch.cuda.synchronize()
+    assert_close(stats.t.permute(0, 3, 1, 2), ref[:, :32], 2e-3, "fp32 stats split")
+    assert_close(to_nchw(feat.t, 48), ref[:, 32:], 1e-2, "feature split")
+    assert_close(to_nchw(hsum.t, 48), ref[:, 32:] + to_nchw(h.t, 48), 1e-2, "residual add")
+
+
+@pytest.mark.parametrize("case", [(2, 16, 16, [32], 0, 16, 3, 1), (2, 24, 24, [48, 48], 4, 8, 3, 2),
+                                  (3, 6, 6, [40], 0, 176, 3, 2), (2, 8, 8, [16], 20, 64, 1, 0),
+                                  (4, 1, 1, [128], 0, 64, 1, 2), (1, 48, 48, [24], 0, 128, 3, 1)])
+def test_conv_dgrad_and_wgrad(case):
+    from causalgen_b200.ops import SegSpec, View, new_act, round16
+    N, H, W, chans, ctx, cout, k, act = case
+    layer, views, out, ref, w, b = run_conv(*case, seed=5)
+    dy_nchw = rnd(N, cout, H, W, seed=31)
+    dy = View(nhwc_bf16(dy_nchw), round16(cout), 0, cout)
+    # autograd reference on the bf16-rounded operands
+    data_views = [v for v in views if not v.bcast]
+    xs = [to_nchw(v.t, c).requires_grad_(True) for v, c in zip(data_views, chans)]
+    parts = list(xs)
+    if ctx:
+        pav = [v for v in views if v.bcast][0]
+        parts.insert(1, pav.t[:, :ctx].float()[:, :, None, None].expand(N, ctx, H, W))
+    wq = w.to(torch.bfloat16).float().requires_grad_(True)
+    bq = b.clone().requires_grad_(True)
+    y = F.conv2d(act_fn(act)(torch.cat(parts, 1)), wq, bq, padding=k // 2)
+    y.backward(to_nchw(dy.t, cout))
+    # data gradients, per source, with act'(x) fused and an accumulate-add
+    for i, v in enumerate(views):
+        if v.bcast:
+            continue
+        j = data_views.index(v)
+        dx = new_act(N, H, W, chans[j], DEV)
+        prev = View(nhwc_bf16(rnd(N, chans[j], H, W, seed=40 + j)), round16(chans[j]))
+        layer.dgrad(i, dy, SegSpec(dx, 0, add=prev, mul=v, mul_act=act), N, H, W)(stream())
+        torch.cuda.synchronize()
+        assert_close(to_nchw(dx.t, chans[j]), xs[j].grad + to_nchw(prev.t, chans[j]), 1.5e-2, f"dgrad src{i} {case}")
+    # weight / bias gradients (accumulated into existing values)
+    dw = torch.full_like(w, 0.5)
+    db = torch.full_like(b, -0.25)
+    layer.wgrad(views, dy, dw, db, N, H, W)(stream())
+    torch.cuda.synchronize()
+    assert_close(dw - 0.5, wq.grad, 1e-2, f"wgrad {case}")
+    assert_close(db + 0.25, bq.grad, 1e-2, f"bias grad {case}")
+
+
+def test_conv_centre_tap_on_1x1_image():
+    from causalgen_b200.ops import ConvLayer, PackTable, SegSpec, View, new_act
+    N, Cin, Cout = 6, 64, 48
+    x = rnd(N, Cin, 1, 1, seed=1)
+    w = rnd(Cout, Cin, 3, 3, scale=0.05, seed=2)
+    b = rnd(Cout, scale=0.1, seed=3)
+    table = PackTable(DEV)
+    layer = ConvLayer(table, w, b, [Cin], 2, centre_only=True)
+    table.launch(stream())
+    xv = View(nhwc_bf16(x), Cin)
+    out = new_act(N, 1, 1, Cout, DEV)
+    layer.forward([xv], [SegSpec(out, 0)], N, 1, 1)(stream())
+    dy = View(nhwc_bf16(rnd(N, Cout, 1, 1, seed=4)), Cout)
+    dw = torch.zeros_like(w)
+    layer.wgrad([xv], dy, dw, None, N, 1, 1)(stream())
+    torch.cuda.synchronize()
+    xq = to_nchw(xv.t, Cin)
+    wq = w.to(torch.bfloat16).float().requires_grad_(True)
+    ref = F.conv2d(F.gelu(xq), wq, b, padding=1)
+    assert_close(to_nchw(out.t, Cout), ref, 1e-2, "centre tap fwd")
+    ref.backward(to_nchw(dy.t, Cout))
+    assert_close(dw, wq.grad, 1e-2, "centre tap wgrad")
+    assert dw[:, :, 0, 0].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("cin,R,cout", [(1, 32, 16), (3, 32, 16), (1, 48, 32)])
+def test_stem(cin, R, cout):
+    from causalgen_b200 import _lib as L
+    lib = L.load()
+    N = 2
+    x = rnd(N, cin, R, R, seed=1)
+    w = rnd(cout, cin, 7, 7, scale=0.1, seed=2)
+    b = rnd(cout, scale=0.1, seed=3)
+    y = torch.zeros(N, R, R, cout, device=DEV, dtype=torch.bfloat16)
+    L.check(lib.cg_stem_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), N, cin, R, cout, cout, stream()))
+    wr = w.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    ref = F.conv2d(x, wr, br, padding=3)
+    torch.cuda.synchronize()
+    assert_close(to_nchw(y, cout), ref, 1e-2, "stem fwd")
+    dy = nhwc_bf16(rnd(N, cout, R, R, seed=4), cout)
+    dw, db = torch.zeros_like(w), torch.zeros_like(b)
+    L.check(lib.cg_stem_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), N, cin, R, cout, cout, stream()))
+    ref.backward(to_nchw(dy, cout))
+    torch.cuda.synchronize()
+    assert_close(dw, wr.grad, 2e-3, "stem wgrad")
+    assert_close(db, br.grad, 2e-3, "stem bias grad")
+
+
+def test_pool_and_upsample():
+    from causalgen_b200 import _lib as L
+    lib = L.load()
+    N, C, H = 2, 32, 24
+    x = rnd(N, C, H, H, seed=1)
+    xb = nhwc_bf16(x)
+    for d in (2, 4, 6):
+        y = torch.zeros(N, H // d, H // d, C, device=DEV, dtype=torch.bfloat16)
+        L.check(lib.cg_avgpool_fwd(xb.data_ptr(), y.data_ptr(), N, H, H, C, d, C, C, 0, stream()))
+        assert_close(to_nchw(y, C), F.avg_pool2d(to_nchw(xb, C), d, d), 1e-2, f"pool {d}")
+        dy = nhwc_bf16(rnd(N, C, H // d, H // d, seed=2))
+        dx = torch.zeros_like(xb)
+        L.check(lib.cg_avgpool_bwd(dy.data_ptr(), dx.data_ptr(), N, H, H, C, d, C, C, 0, 0, stream()))
+        xr = to_nchw(xb, C).requires_grad_(True)
+        F.avg_pool2d(xr, d, d).backward(to_nchw(dy, C))
+        assert_close(to_nchw(dx, C), xr.grad, 1e-2, f"pool bwd {d}")
+    # odd resolution: 14 -> 7 padded to 8 (src/vae.py:130-132)
+    x14 = nhwc_bf16(rnd(N, C, 14, 14, seed=3))
+    y8 = torch.ones(N, 8, 8, C, device=DEV, dtype=torch.bfloat16)
+    L.check(lib.cg_avgpool_fwd(x14.data_ptr(), y8.data_ptr(), N, 14, 14, C, 2, C, C, 8, stream()))
+    assert_close(to_nchw(y8, C), F.pad(F.avg_pool2d(to_nchw(x14, C), 2, 2), [0, 1, 0, 1]), 1e-2, "pool+pad")
+    # nearest upsample + learned bias, integer and 7->8 style factors
+    for hi, ho in ((6, 12), (1, 4), (7, 8), (8, 14)):
+        xs = nhwc_bf16(rnd(N, C, hi, hi, seed=4))
+        bias = rnd(1, C, ho, ho, seed=5)
+        y = torch.zeros(N, ho, ho, C, device=DEV, dtype=torch.bfloat16)
+        L.check(lib.cg_upsample_fwd(xs.data_ptr(), bias.data_ptr(), y.data_ptr(), N, hi, ho, C, C, C, stream()))
+        xr = to_nchw(xs, C).requires_grad_(True)
+        br = bias.clone().requires_grad_(True)
+        ref = br + F.interpolate(xr, scale_factor=ho / hi)
+        assert_close(to_nchw(y, C), ref, 1e-2, f"upsample {hi}->{ho}")
+        dy = nhwc_bf16(rnd(N, C, ho, ho, seed=6))
+        dx = torch.zeros_like(xs)
+        dbias = torch.zeros_like(bias)
+        L.check(lib.cg_upsample_bwd(dy.data_ptr(), dx.data_ptr(), dbias.data_ptr(), N, hi, ho, C, C, C, 0, stream()))
+        ref.backward(to_nchw(dy, C))
+        assert_close(to_nchw(dx, C), xr.grad, 1e-2, f"upsample bwd {hi}->{ho}")
+        assert_close(dbias, br.grad, 2e-3, f"upsample dbias {hi}->{ho}")
+
+
+def test_latent_forward_backward():
+    import ctypes as C
+    from causalgen_b200 import _lib as L
+    lib = L.load()
+    N, H, zd = 3, 12, 16
+    HW = H * H
+    q = rnd(N, HW, 32, seed=1, scale=0.7).contiguous()
+    p = rnd(N, HW, 32, seed=2, scale=0.7).contiguous()
+    eps = rnd(N, zd, H, H, seed=3)
+    z16 = torch.zeros(N, HW, 16, device=DEV, dtype=torch.bfloat16)
+    z32 = torch.zeros(N, zd, H, H, device=DEV)
+    kl = torch.zeros(N, device=DEV)
+    a = L.LatentArgs()
+    a.q, a.p, a.q_ld, a.p_ld, a.eps = q.data_ptr(), p.data_ptr(), 32, 32, eps.data_ptr()
+    a.log_t, a.z_bf16, a.z_ld, a.z_f32, a.kl_out = math.log(0.9), z16.data_ptr(), 16, z32.data_ptr(), kl.data_ptr()
+    a.N, a.HW, a.zdim, a.mode = N, HW, zd, 0
+    L.check(lib.cg_latent_fwd(C.byref(a), stream()))
+    qn = q.view(N, H, H, 32).permute(0, 3, 1, 2)
+    pn = p.view(N, H, H, 32).permute(0, 3, 1, 2)
+    ql, qs, pl, ps = qn[:, :16], qn[:, 16:] + math.log(0.9), pn[:, :16], pn[:, 16:] + math.log(0.9)
+    zr = ql + qs.exp() * eps
+    klr = (-0.5 + ps - qs + 0.5 * (qs.exp() ** 2 + (ql - pl) ** 2) / ps.exp() ** 2).sum(dim=(1, 2, 3))
+    torch.cuda.synchronize()
+    assert_close(z32, zr, 1e-5, "z fp32")
+    assert_close(z16.view(N, H, H, 16).permute(0, 3, 1, 2).float(), zr, 1e-2, "z bf16")
+    assert_close(kl, klr, 1e-4, "kl")
+    # backward (t = None)
+    dz = rnd(N, HW, 16, seed=4).to(torch.bfloat16).contiguous()
+    dq = torch.zeros(N, HW, 32, device=DEV, dtype=torch.bfloat16)
+    dp = torch.zeros(N, HW, 48, device=DEV, dtype=torch.bfloat16)
+    b = L.LatentBwdArgs()
+    b.q, b.p, b.q_ld, b.p_ld, b.eps = q.data_ptr(), p.data_ptr(), 32, 32, eps.data_ptr()
+    b.dz, b.dz_ld, b.g_kl = dz.data_ptr(), 16, 0.37
+    b.dq, b.dq_ld, b.dp, b.dp_ld = dq.data_ptr(), 32, dp.data_ptr(), 48
+    b.N, b.HW, b.zdim, b.mode = N, HW, zd, 0
+    L.check(lib.cg_latent_bwd(C.byref(b), stream()))
+    qr = q.clone().requires_grad_(True)
+    pr = p.clone().requires_grad_(True)
+    qn = qr.view(N, H, H, 32).permute(0, 3, 1, 2)
+    pn = pr.view(N, H, H, 32).permute(0, 3, 1, 2)
+    ql, qs, pl, ps = qn[:, :16], qn[:, 16:], pn[:, :16], pn[:, 16:]
+    z = ql + qs.exp() * eps
+    klv = (-0.5 + ps - qs + 0.5 * (qs.exp() ** 2 + (ql - pl) ** 2) / ps.exp() ** 2).sum()
+    loss = 0.37 * klv + (z * dz.view(N, H, H, 16).permute(0, 3, 1, 2).float()).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    assert_close(dq.float(), qr.grad, 1e-2, "dq")
+    assert_close(dp[..., :32].float(), pr.grad, 1e-2, "dp")
+
+
+@pytest.mark.parametrize("Cc,Cw", [(1, 32), (3, 16)])
+def test_dgauss_forward_backward_sample(Cc, Cw):
+    import ctypes as C
+    from causalgen_b200 import _lib as L
+    lib = L.load()
+    N, R = 2, 20
+    HW = R * R
+    h = nhwc_bf16(rnd(N, Cw, R, R, seed=1))
+    x8 = torch.randint(0, 256, (N, Cc, R, R), generator=torch.Generator().manual_seed(2))
+    x8[torch.rand(N, Cc, R, R, generator=torch.Generator().manual_seed(3)) < 0.4] = 0
+    x8[torch.rand(N, Cc, R, R, generator=torch.Generator().manual_seed(4)) < 0.05] = 255
+    x = ((x8.float() - 127.5) / 127.5).to(DEV)
+    ws = [rnd(Cc, Cw, seed=10 + i, scale=0.3) for i in range(3)]
+    bs = [rnd(Cc, seed=20 + i, scale=0.3) for i in range(3)]
+    bs[1] = bs[1] - 2.0
+    nll = torch.zeros(N, device=DEV)
+    a = L.DGaussArgs()
+    a.h, a.h_ld, a.Cw, a.x = h.data_ptr(), Cw, Cw, x.data_ptr()
+    a.w_loc, a.b_loc, a.w_ls, a.b_ls = ws[0].data_ptr(), bs[0].data_ptr(), ws[1].data_ptr(), bs[1].data_ptr()
+    if Cc == 3:
+        a.w_co, a.b_co = ws[2].data_ptr(), bs[2].data_ptr()
+    a.N, a.HW, a.C, a.nll = N, HW, Cc, nll.data_ptr()
+    L.check(lib.cg_dgauss_nll_fwd(C.byref(a), stream()))
+
+    def ref_nll(hh, w, b):
+        loc = F.conv2d(hh, w[0][:, :, None, None], b[0])
+        ls = F.conv2d(hh, w[1][:, :, None, None], b[1]).clamp(min=-9)
+        if Cc == 3:
+            co = torch.tanh(F.conv2d(hh, w[2][:, :, None, None], b[2]))
+            loc = torch.stack([loc[:, 0], loc[:, 1] + co[:, 0] * x[:, 0],
+                               loc[:, 2] + co[:, 1] * x[:, 0] + co[:, 2] * x[:, 1]], 1)
+        cdf = lambda v: 0.5 * (1 + torch.tanh(math.sqrt(2 / math.pi) * (v + 0.044715 * v ** 3)))
+        inv = torch.exp(-ls)
+        hi, lo = cdf(inv * (x - loc + 1 / 255)), cdf(inv * (x - loc - 1 / 255))
+        lp = torch.where(x < -0.999, hi.clamp(min=1e-12).log(),
+                         torch.where(x > 0.999, (1 - lo).clamp(min=1e-12).log(), (hi - lo).clamp(min=1e-12).log()))
+        return -lp.mean(dim=(1, 2, 3))
+
+    hr = to_nchw(h, Cw).requires_grad_(True)
+    wr = [w.clone().requires_grad_(True) for w in ws]
+    br = [b.clone().requires_grad_(True) for b in bs]
+    ref = ref_nll(hr, wr, br)
+    torch.cuda.synchronize()
+    assert_close(nll, ref, 2e-4, "dgauss nll")
+    # backward
+    dh = torch.zeros_like(h)
+    dws = [torch.zeros_like(w) for w in ws]
+    dbs = [torch.zeros_like(b) for b in bs]
+    a.g, a.dh, a.dh_ld = 0.5, dh.data_ptr(), Cw
+    a.dw_loc, a.db_loc, a.dw_ls, a.db_ls = dws[0].data_ptr(), dbs[0].data_ptr(), dws[1].data_ptr(), dbs[1].data_ptr()
+    if Cc == 3:
+        a.dw_co, a.db_co = dws[2].data_ptr(), dbs[2].data_ptr()
+    L.check(lib.cg_dgauss_nll_bwd(C.byref(a), stream()))
+    (0.5 * ref.sum()).backward()
+    torch.cuda.synchronize()
+    assert_close(to_nchw(dh, Cw), hr.grad, 1e-2, "dgauss dh")
+    for i in range(3 if Cc == 3 else 2):
+        assert_close(dws[i], wr[i].grad, 2e-3, f"dgauss dw{i}")
+        assert_close(dbs[i], br[i].grad, 2e-3, f"dgauss db{i}")
+    # sample (return_loc=True)
+    xo, so = torch.zeros_like(x), torch.zeros_like(x)
+    L.check(lib.cg_dgauss_sample(C.byref(a), xo.data_ptr(), so.data_ptr(), None, 0.0, stream()))
+    hh = to_nchw(h, Cw)
+    loc = F.conv2d(hh, ws[0][:, :, None, None], bs[0])
+    ls = F.conv2d(hh, ws[1][:, :, None, None], bs[1]).clamp(min=-9)
+    if Cc == 3:
+        co = torch.tanh(F.conv2d(hh, ws[2][:, :, None, None], bs[2]))
+        r = loc[:, 0].clamp(-1, 1)
+        g = (loc[:, 1] + co[:, 0] * r).clamp(-1, 1)
+        bl = (loc[:, 2] + co[:, 1] * r + co[:, 2] * g).clamp(-1, 1)
+        loc = torch.stack([r, g, bl], 1)
+    torch.cuda.synchronize()
+    assert_close(xo, loc.clamp(-1, 1), 1e-4, "dgauss sample loc")
+    assert_close(so, ls.exp(), 1e-4, "dgauss sample scale")
+
+
+def test_dmol_against_oracle_functions():
+    """DMoL kernels vs the CPU oracle's restatement of src/dmol.py on the same head outputs."""
+    import ctypes as C
+    import hvae_oracle as O
+    from causalgen_b200 import _lib as L
+    lib = L.load()
+    N, R, Cw = 2, 12, 16
+    HW = R * R
+    h = nhwc_bf16(rnd(N, Cw, R, R, seed=1))
+    x8 = torch.randint(0, 256, (N, 3, R, R), generator=torch.Generator().manual_seed(2))
+    x8[torch.rand(N, 3, R, R, generator=torch.Generator().manual_seed(3)) < 0.3] = 0
+    x8[torch.rand(N, 3, R, R, generator=torch.Generator().manual_seed(4)) < 0.1] = 255
+    x = ((x8.float() - 127.5) / 127.5).to(DEV)
+    w = rnd(100, Cw, seed=5, scale=0.5)
+    b = rnd(100, seed=6, scale=0.5)
+    nll = torch.zeros(N, device=DEV)
+    a = L.DmolArgs()
+    a.h, a.h_ld, a.Cw, a.x, a.w, a.b = h.data_ptr(), Cw, Cw, x.data_ptr(), w.data_ptr(), b.data_ptr()
+    a.N, a.HW, a.nll = N, HW, nll.data_ptr()
+    L.check(lib.cg_dmol_loss_fwd(C.byref(a), stream()))
+    hc = to_nchw(h, Cw).cpu().requires_grad_(True)
+    wc = w.cpu().clone().requires_grad_(True)
+    bc = b.cpu().clone().requires_grad_(True)
+    l = F.conv2d(hc, wc[:, :, None, None], bc).permute(0, 2, 3, 1)
+    ref = O.dmol_loss(x.cpu().permute(0, 2, 3, 1), l)
+    torch.cuda.synchronize()
+    assert_close(nll.cpu(), ref.detach(), 2e-4, "dmol loss")
+    dh = torch.zeros_like(h)
+    dw, db = torch.zeros_like(w), torch.zeros_like(b)
+    a.g, a.dh, a.dh_ld, a.dw, a.db = 0.5, dh.data_ptr(), Cw, dw.data_ptr(), db.data_ptr()
+    L.check(lib.cg_dmol_loss_bwd(C.byref(a), stream()))
+    (0.5 * ref.sum()).backward()
+    torch.cuda.synchronize()
+    assert_close(to_nchw(dh, Cw).cpu(), hc.grad, 1e-2, "dmol dh")
+    assert_close(dw.cpu(), wc.grad, 2e-3, "dmol dw")
+    assert_close(db.cpu(), bc.grad, 2e-3, "dmol db")
+    # predictions
+    xo, so = torch.zeros_like(x), torch.zeros_like(x)
+    for mode, mask in ((0, "soft"), (1, "hard")):
+        L.check(lib.cg_dmol_predict(C.byref(a), mode, None, None, 0.0, xo.data_ptr(), so.data_ptr(), stream()))
+        m, s = O.dmol_mean(l.detach(), mask=mask)
+        torch.cuda.synchronize()
+        assert_close(xo.cpu(), m.permute(0, 3, 1, 2), 1e-4, f"dmol mean {mask}")
+        assert_close(so.cpu(), s.permute(0, 3, 1, 2), 1e-4, f"dmol scale {mask}")
+    ug = torch.rand(N, R, R, 10, generator=torch.Generator().manual_seed(7)).clamp(1e-5, 1 - 1e-5)
+    ul = torch.rand(N, R, R, 3, generator=torch.Generator().manual_seed(8)).clamp(1e-5, 1 - 1e-5)
+    ugd, uld = ug.to(DEV), ul.to(DEV)
+    L.check(lib.cg_dmol_predict(C.byref(a), 2, ugd.data_ptr(), uld.data_ptr(), math.log(0.7), xo.data_ptr(),
+                                so.data_ptr(), stream()))
+    sx, ss = O.dmol_sample(l.detach(), O.NoiseTape([ug, ul]), t=0.7)
+    torch.cuda.synchronize()
+    # argmax ties aside, identical uniforms give identical component picks
+    frac = ((xo.cpu() - sx.permute(0, 3, 1, 2)).abs() < 1e-3).float().mean().item()
+    assert frac > 0.995, frac
+
+
+def test_mix_cf_and_layout_glue():
+    from causalgen_b200 import _lib as L
+    lib = L.load()
+    n = 5000
+    z, ql, qs, pl, ps = (rnd(n, seed=i, scale=0.5) for i in range(5))
+    out = torch.zeros(n, device=DEV)
+    L.check(lib.cg_latent_mix(z.data_ptr(), ql.data_ptr(), qs.data_ptr(), pl.data_ptr(), ps.data_ptr(), out.data_ptr(),
+                              n, 0.65, 0.8, 1, stream()))
+    u = (z - ql) / qs.exp()
+    ref = 0.65 * ql + 0.35 * pl + (0.65 ** 2 * qs.exp() ** 2 + 0.35 ** 2 * ps.exp() ** 2).sqrt() * 0.8 * u
+    assert_close(out, ref, 1e-5, "latent mix")
+    x, rl, cl = (rnd(n, seed=10 + i, scale=0.5) for i in range(3))
+    rs, cs = rnd(n, seed=20).abs() + 0.01, rnd(n, seed=21).abs() + 0.01
+    cf = torch.zeros(n, device=DEV)
+    s1, s2 = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    for _ in range(2):
+        L.check(lib.cg_cf_combine(x.data_ptr(), rl.data_ptr(), rs.data_ptr(), cl.data_ptr(), cs.data_ptr(),
+                                  cf.data_ptr(), s1.data_ptr(), s2.data_ptr(), n, stream()))
+    ref = (cl + cs * (x - rl) / rs.clamp(min=1e-12)).clamp(-1, 1)
+    assert_close(cf, ref, 1e-6, "cf combine")
+    assert_close(s1, 2 * ref, 1e-6, "cf sum")
+    assert_close(s2, 2 * ref ** 2, 1e-6, "cf sum2")
+    # layout glue round trip
+    t = rnd(2, 20, 9, 9, seed=30)
+    nh = torch.zeros(2, 81, 32, device=DEV, dtype=torch.bfloat16)
+    L.check(lib.cg_nchw_f32_to_nhwc_bf16(t.data_ptr(), nh.data_ptr(), 2, 20, 81, 32, stream()))
+    back = torch.zeros_like(t)
+    L.check(lib.cg_nhwc_bf16_to_nchw_f32(nh.data_ptr(), back.data_ptr(), 2, 20, 81, 32, stream()))
+    assert_close(back, t.to(torch.bfloat16).float(), 1e-6, "layout round trip")
+    assert nh[..., 20:].abs().max().item() == 0
+
+
+def test_optimizer_tail_matches_torch_adamw():
+    from causalgen_b200 import _lib as L
+    lib = L.load()
+    n = 10007
+    p0 = rnd(n, seed=1)
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref_p], lr=1e-3, weight_decay=0.05, betas=(0.9, 0.9))
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda it: 1.0 if it > 100 else it / 100)
+    p = p0.clone()
+    m, v, ema = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV), p0.clone()
+    state = torch.zeros(4, dtype=torch.int32, device=DEV)
+    dyn = torch.zeros(6, device=DEV)
+    ss = torch.zeros(1, device=DEV)
+    for it in range(5):
+        g = rnd(n, seed=100 + it, scale={2: 30.0, 1: 4.0}.get(it, 1.0))
+        ref_p.grad = g.clone()
+        gn = torch.nn.utils.clip_grad_norm_([ref_p], 350.0)
+        if gn < 500:
+            opt.step()
+            sched.step()
+        ss.zero_()
+        L.check(lib.cg_sumsq(g.data_ptr(), ss.data_ptr(), n, stream()))
+        L.check(lib.cg_optim_advance(state.data_ptr(), dyn.data_ptr(), ss.data_ptr(), None, 1e-3, 100, 0.9, 0.9, 350.0,
+                                     500.0, 1.0, 0.999, 100, stream()))
+        L.check(lib.cg_adamw_ema_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), ema.data_ptr(), n,
+                                      state.data_ptr(), dyn.data_ptr(), 0.9, 0.9, 1e-8, 0.05, stream()))
+        torch.cuda.synchronize()
+        assert abs(dyn[5].item() - gn.item()) <= 1e-3 * gn.item()
+    assert_close(p, ref_p.detach(), 1e-5, "adamw params")
+    assert state[2].item() == 1 and state[0].item() == 4  # the 30x gradient step was skipped
+    assert_close(ema, p, 1e-6, "ema copies params during its first 100 calls")
