@@ -1,0 +1,618 @@
+"""Launch-program builder for the HVAE hot path.
+
+For a given (model, batch size, mode) the engine allocates every activation / gradient buffer once and
+records the exact sequence of C-ABI kernel launches of the pass (`Program`).  Running a pass is then a
+flat loop over pre-built argument structs -- no per-step allocation, CUDA-graph capturable.
+
+Reference semantics implemented here (citations relative to /root/reference):
+  encoder           src/vae.py:125-134        decoder loop      src/vae.py:222-301
+  Block             src/vae.py:73-84          ELBO reduction    src/vae.py:439-458
+  abduct / mixture  src/vae.py:466-516        forward_latents   src/vae.py:518-522
+Backward passes are hand-derived (there is no autograd under this package).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+from .model import Block, DmolNet
+from .ops import ConvLayer, PackTable, SegSpec, View, new_act, round16
+
+
+class PyOp:
+    """a recorded torch-side glue op (layout copies only; never arithmetic on the path)"""
+
+    def __init__(self, fn, name="pyop"):
+        self.fn, self.name = fn, name
+
+    def __call__(self, stream):
+        self.fn()
+
+
+class Program:
+    def __init__(self, name):
+        self.name = name
+        self.launches: List = []
+        self.keep: List = []
+        self.n_kernels = 0
+
+    def add(self, ln):
+        self.launches.append(ln)
+        if isinstance(ln, L.Launch):
+            self.n_kernels += 2 if (ln.name == "cg_conv2d_wgrad" and ln.keep[0].dbias) else 1
+        return ln
+
+    def call(self, name, *args):
+        return self.add(L.Launch(name, *args))
+
+    def run(self, stream=None):
+        s = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        for ln in self.launches:
+            ln(s)
+
+
+class BlockLayers:
+    """ConvLayers of one reference Block"""
+
+    def __init__(self, eng: "Engine", mod: Block, src_logical: Sequence[int], res: int, grad_srcs=None):
+        self.mod = mod
+        self.act = L.ACT_RELU if mod.light else L.ACT_GELU
+        centre = (res == 1 and mod.ksize == 3)
+        convs = mod.convs
+        self.layers: List[ConvLayer] = []
+        for i, c in enumerate(convs):
+            srcs = list(src_logical) if i == 0 else [c.weight.shape[1]]
+            self.layers.append(ConvLayer(eng.table, c.weight, c.bias, srcs, self.act,
+                                         centre_only=centre and c.weight.shape[2] == 3,
+                                         grad_srcs=(grad_srcs if i == 0 else None)))
+        self.proj = None
+        if hasattr(mod, "width_proj"):
+            self.proj = ConvLayer(eng.table, mod.width_proj.weight, mod.width_proj.bias, list(src_logical), L.ACT_NONE)
+        self.params = [(c.weight, c.bias) for c in convs]
+
+
+class Rec:
+    """attribute bag of tensors a forward pass saves for its backward"""
+    pass
+
+
+class Engine:
+    def __init__(self, model, args):
+        L.load()
+        self.model = model
+        self.args = args
+        p0 = next(model.parameters())
+        if p0.device.type != "cuda":
+            raise RuntimeError("causalgen_b200 runs on a CUDA sm_100 device only (no CPU fallback); move the model "
+                               "to cuda first")
+        self.device = p0.device
+        with torch.cuda.device(self.device):
+            if L.load().cg_device_sms() <= 0:
+                raise RuntimeError("causalgen_b200: device is not sm_100 (B200); there is no fallback path")
+        self.table = PackTable(self.device)
+        self.zd = args.z_dim
+        self.ctx = args.context_dim
+        self.ctx_pad = round16(self.ctx)
+        self.cond_prior = bool(args.cond_prior)
+        self.q_corr = bool(args.q_correction)
+        self.C = args.input_channels
+        self.R = args.input_res
+        self.light = args.vr == "light"
+        enc, dec = model.encoder, model.decoder
+        self.enc_layers = [BlockLayers(self, b, [st.cin], st.res_in) for b, st in zip(enc.blocks, enc.plan)]
+        self.dec_layers = []
+        for blk, st in zip(dec.blocks, dec.plan):
+            d = Rec()
+            d.st = st
+            psrc = [st.cin] + ([self.ctx] if self.cond_prior else [])
+            d.prior = BlockLayers(self, blk.prior, psrc, st.res, grad_srcs=[True] + [False] * (len(psrc) - 1))
+            d.post = None
+            if st.stochastic:
+                d.post = BlockLayers(self, blk.posterior, [st.cin, self.ctx, st.cin], st.res,
+                                     grad_srcs=[True, False, True])
+            d.z_proj = ConvLayer(self.table, blk.z_proj.weight, blk.z_proj.bias, [self.zd, self.ctx], L.ACT_NONE,
+                                 grad_srcs=[True, False])
+            d.zfp = None
+            if not self.q_corr:
+                d.zfp = ConvLayer(self.table, blk.z_feat_proj.weight, blk.z_feat_proj.bias, [self.zd, st.cin],
+                                  L.ACT_NONE)
+            d.conv = BlockLayers(self, blk.conv, [st.cin], st.res)
+            self.dec_layers.append(d)
+        self.dmol = isinstance(model.likelihood, DmolNet)
+        # flat gradient bucket with per-parameter views (the one buffer DDP all-reduces)
+        self.params = [p for p in model.parameters()]
+        n = sum(p.numel() for p in self.params)
+        self.flat_grad = torch.zeros(n, device=self.device, dtype=torch.float32)
+        self.grad_of: Dict[int, torch.Tensor] = {}
+        off = 0
+        for p in self.params:
+            self.grad_of[id(p)] = self.flat_grad[off: off + p.numel()].view_as(p)
+            off += p.numel()
+        self.signature = self.param_signature(model)
+        self.programs: Dict = {}
+
+    @staticmethod
+    def param_signature(model):
+        return tuple(p.data_ptr() for p in model.parameters())
+
+    def g(self, p: Optional[torch.Tensor]):
+        return None if p is None else self.grad_of[id(p)]
+
+    def pack_weights(self, stream=None):
+        s = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        self.table.launch(s)
+
+    # ================================================================== forward emission
+    def _block_fwd(self, prog: Program, bl: BlockLayers, srcs: List[View], N, H, W, final_segs=None) -> Rec:
+        """reference Block.forward (src/vae.py:73-84) without the pooling"""
+        r = Rec()
+        r.bl, r.srcs, r.N, r.H, r.W = bl, srcs, N, H, W
+        r.mids = []
+        cur = srcs
+        for layer in bl.layers[:-1]:
+            mid = new_act(N, H, W, layer.cout_l, self.device)
+            prog.add(layer.forward(cur, [SegSpec(mid, 0)], N, H, W))
+            r.mids.append(mid)
+            cur = [mid]
+        last = bl.layers[-1]
+        r.proj_out = None
+        if final_segs is None:
+            skip = None
+            if bl.mod.residual:
+                if bl.proj is not None:
+                    r.proj_out = new_act(N, H, W, bl.proj.cout_l, self.device)
+                    prog.add(bl.proj.forward(srcs, [SegSpec(r.proj_out, 0)], N, H, W))
+                    skip = r.proj_out
+                else:
+                    skip = srcs[0]
+            r.y = new_act(N, H, W, last.cout_l, self.device)
+            final_segs = [SegSpec(r.y, 0, add=skip)]
+        prog.add(last.forward(cur, final_segs, N, H, W))
+        return r
+
+    def _encoder_fwd(self, prog: Program, x: torch.Tensor, N) -> Rec:
+        enc = self.model.encoder
+        e = Rec()
+        e.x = x
+        R = self.R
+        w0 = self.args.widths[0]
+        e.stem_out = new_act(N, R, R, w0, self.device)
+        prog.call("cg_stem_fwd", x.data_ptr(), enc.stem.weight.data_ptr(), enc.stem.bias.data_ptr(),
+                  e.stem_out.ptr, N, self.C, R, w0, e.stem_out.ld)
+        prog.keep.append(x)
+        cur = e.stem_out
+        e.blocks = []
+        e.acts: Dict[int, View] = {}
+        e.owner: Dict[int, int] = {}
+        for i, (bl, st) in enumerate(zip(self.enc_layers, enc.plan)):
+            r = self._block_fwd(prog, bl, [cur], N, st.res_in, st.res_in)
+            r.st = st
+            if st.down:
+                r.out = new_act(N, st.res_out, st.res_out, st.cout, self.device)
+                prog.call("cg_avgpool_fwd", r.y.ptr, r.out.ptr, N, st.res_in, st.res_in, r.y.C, st.down, r.y.ld,
+                          r.out.ld, st.res_out)
+            else:
+                r.out = r.y
+            e.blocks.append(r)
+            e.acts[st.res_out] = r.out
+            e.owner[st.res_out] = i
+            cur = r.out
+        return e
+
+    def _decoder_fwd(self, prog: Program, N, pa: View, pa_sto: View, acts: Optional[Dict[int, View]],
+                     given: Optional[Sequence[bool]] = None, want_z: bool = False, want_stats: bool = False,
+                     explicit_eps: bool = True, kl_rows: Optional[torch.Tensor] = None) -> Rec:
+        """reference Decoder.forward (src/vae.py:222-301).  `given[i]` marks stochastic block i whose latent is
+        supplied by the caller (forward_latents); other stochastic blocks sample q (acts given) or p."""
+        dec = self.model.decoder
+        zd = self.zd
+        D = Rec()
+        D.blocks = []
+        D.latent_args = []
+        D.eps = []
+        D.z_in = {}
+        D.z_out = {}
+        D.stats_out = {}
+        bias_of = {r: p for (r, _), p in zip(dec.bias_res, dec.bias)}
+        w1 = dec.plan[0].cin
+        h = new_act(N, 1, 1, w1, self.device)
+        prog.call("cg_fill_rows", bias_of[1].data_ptr(), h.ptr, N, w1, h.ld)
+        zs = h  # h = z = bias[1].repeat (src/vae.py:232)
+        cur_res = 1
+        ksto = 0
+        for d in self.dec_layers:
+            st = d.st
+            r = Rec()
+            r.d, r.st = d, st
+            res = st.res
+            r.up = None
+            if cur_res < res:  # src/vae.py:251-262 (the z stream reuses the same bias b)
+                b = bias_of.get(res)
+                bptr = b.data_ptr() if b is not None else None
+                r.up = (cur_res, h, zs, b)
+                h_up = new_act(N, res, res, st.cin, self.device)
+                prog.call("cg_upsample_fwd", h.ptr, bptr, h_up.ptr, N, cur_res, res, st.cin, h.ld, h_up.ld)
+                if not self.q_corr:
+                    if zs is h:
+                        zs_up = h_up
+                    else:
+                        zs_up = new_act(N, res, res, st.cin, self.device)
+                        prog.call("cg_upsample_fwd", zs.ptr, bptr, zs_up.ptr, N, cur_res, res, st.cin, zs.ld, zs_up.ld)
+                    zs = zs_up
+                h = h_up
+                cur_res = res
+            r.h_in, r.zs_in = h, zs
+            # ---- prior (src/vae.py:172-183)
+            p_src = [h if self.q_corr else zs] + ([pa_sto] if self.cond_prior else [])
+            r.pstat = View(torch.zeros(N, res, res, 2 * zd, device=self.device, dtype=torch.float32), 2 * zd)
+            r.pfeat = new_act(N, res, res, st.cin, self.device)
+            r.h2 = new_act(N, res, res, st.cin, self.device)
+            r.prior = self._block_fwd(prog, d.prior, p_src, N, res, res,
+                                      final_segs=[SegSpec(r.pstat, 0), SegSpec(r.pfeat, 2 * zd),
+                                                  SegSpec(r.h2, 2 * zd, add=h)])
+            # ---- posterior + latent (src/vae.py:265-291)
+            r.z = new_act(N, res, res, zd, self.device)
+            r.post = None
+            r.mode = 2
+            r.eps = None
+            r.qstat = None
+            la = None
+            if st.stochastic:
+                is_given = bool(given[ksto]) if given is not None and ksto < len(given) else False
+                if acts is not None:
+                    r.qstat = View(torch.zeros(N, res, res, 2 * zd, device=self.device, dtype=torch.float32), 2 * zd)
+                    r.post = self._block_fwd(prog, d.post, [h, pa, acts[res]], N, res, res,
+                                             final_segs=[SegSpec(r.qstat, 0)])
+                    r.mode = 0
+                elif is_given:
+                    zin = torch.zeros(N, zd, res, res, device=self.device, dtype=torch.float32)
+                    D.z_in[ksto] = zin
+                    prog.call("cg_nchw_f32_to_nhwc_bf16", zin.data_ptr(), r.z.ptr, N, zd, res * res, r.z.ld)
+                    r.mode = 3
+                else:
+                    r.mode = 1
+                if r.mode in (0, 1):
+                    la = L.LatentArgs()
+                    la.p, la.p_ld = r.pstat.ptr, r.pstat.ld
+                    if r.mode == 0:
+                        la.q, la.q_ld = r.qstat.ptr, r.qstat.ld
+                    if explicit_eps:
+                        r.eps = torch.zeros(N, zd, res, res, device=self.device, dtype=torch.float32)
+                        la.eps = r.eps.data_ptr()
+                    D.eps.append(r.eps)
+                    la.offset = ksto << 40
+                    la.z_bf16, la.z_ld = r.z.ptr, r.z.ld
+                    if want_z:
+                        zo = torch.zeros(N, zd, res, res, device=self.device, dtype=torch.float32)
+                        D.z_out[ksto] = zo
+                        la.z_f32 = zo.data_ptr()
+                    if kl_rows is not None and r.mode == 0:
+                        la.kl_out = kl_rows[ksto].data_ptr()
+                    la.N, la.HW, la.zdim, la.mode = N, res * res, zd, r.mode
+                    if want_stats:
+                        D.stats_out[ksto] = (r.qstat, r.pstat)
+                ksto += 1
+            else:
+                la = L.LatentArgs()
+                la.p, la.p_ld = r.pstat.ptr, r.pstat.ld
+                la.z_bf16, la.z_ld = r.z.ptr, r.z.ld
+                la.N, la.HW, la.zdim, la.mode = N, res * res, zd, 2
+            if la is not None:
+                prog.add(L.Launch("cg_latent_fwd", C.byref(la))).keep = (la, r)
+                D.latent_args.append(la)
+            # ---- merge (src/vae.py:292-300)
+            r.h3 = new_act(N, res, res, st.cin, self.device)
+            prog.add(d.z_proj.forward([r.z, pa], [SegSpec(r.h3, 0, add=r.h2)], N, res, res))
+            r.conv = self._block_fwd(prog, d.conv, [r.h3], N, res, res)
+            h = r.conv.y
+            r.zs_out = None
+            if d.zfp is not None and st.idx + 1 < len(self.dec_layers):
+                r.zs_out = new_act(N, res, res, st.cout, self.device)
+                prog.add(d.zfp.forward([r.z, r.pfeat], [SegSpec(r.zs_out, 0)], N, res, res))
+                zs = r.zs_out
+            D.blocks.append(r)
+        D.h = h
+        D.nsto = ksto
+        return D
+
+    # ================================================================== backward emission
+    def _block_bwd(self, prog: Program, r: Rec, dy: View, dsrc: List[Optional[SegSpec]]):
+        """Backward of _block_fwd.  dy: gradient wrt the last conv's full output (padded channels).
+        dsrc[i]: where/how the first conv's data gradient for source i lands (None = not needed);
+        mul/mul_act are filled in here.  Weight/bias gradients accumulate into the flat bucket."""
+        bl = r.bl
+        N, H, W = r.N, r.H, r.W
+        ins = [r.srcs] + [[m] for m in r.mids]
+        cur_dy = dy
+        for li in range(len(bl.layers) - 1, -1, -1):
+            layer = bl.layers[li]
+            srcs = ins[li]
+            prog.add(layer.wgrad(srcs, cur_dy, self.g(layer.weight), self.g(layer.bias), N, H, W))
+            if li > 0:
+                dmid = new_act(N, H, W, layer.src_logical[0], self.device)
+                prog.add(layer.dgrad(0, cur_dy, SegSpec(dmid, 0, mul=srcs[0], mul_act=bl.act), N, H, W))
+                cur_dy = dmid
+            else:
+                for i, sg in enumerate(dsrc):
+                    if sg is None:
+                        continue
+                    sg.mul, sg.mul_act = srcs[i], bl.act
+                    prog.add(layer.dgrad(i, cur_dy, sg, N, H, W))
+
+    def _res_block_bwd(self, prog: Program, r: Rec, dout: View, extra: Optional[View] = None) -> View:
+        """Backward of a residual Block (encoder block / decoder `conv`), incl. pooling.
+        Returns d(input).  `extra` is one more gradient contribution to the block input."""
+        bl = r.bl
+        N, H, W = r.N, r.H, r.W
+        st = getattr(r, "st", None)
+        dy = dout
+        if st is not None and getattr(st, "down", None):
+            dy = new_act(N, H, W, r.y.logical, self.device)
+            prog.call("cg_avgpool_bwd", dout.ptr, dy.ptr, N, H, W, dy.C, st.down, dout.ld, dy.ld, st.res_out, 0)
+        x = r.srcs[0]
+        dx = new_act(N, H, W, x.logical, self.device)
+        if bl.proj is not None:
+            skip = new_act(N, H, W, x.logical, self.device)
+            prog.add(bl.proj.wgrad(r.srcs, dy, self.g(bl.proj.weight), self.g(bl.proj.bias), N, H, W))
+            prog.add(bl.proj.dgrad(0, dy, SegSpec(skip, 0, add=extra), N, H, W))
+        elif extra is not None:
+            skip = new_act(N, H, W, x.logical, self.device)
+            prog.call("cg_add", dy.ptr, extra.ptr, skip.ptr, N * H * W, skip.C, dy.ld, extra.ld, skip.ld)
+        else:
+            skip = dy
+        self._block_bwd(prog, r, dy, [SegSpec(dx, 0, add=skip)])
+        return dx
+
+    def _decoder_bwd(self, prog: Program, D: Rec, dh_final: View, N, g_kl: float, acts_grad: Dict[int, View],
+                     explicit_eps: bool):
+        dec = self.model.decoder
+        zd = self.zd
+        bias_param = {r: p for (r, _), p in zip(dec.bias_res, dec.bias)}
+        dh_out, dzs_out = dh_final, None
+        D.latent_bwd_args = []
+        for r in reversed(D.blocks):
+            d, st = r.d, r.st
+            res = st.res
+            # conv block
+            dh3 = self._res_block_bwd(prog, r.conv, dh_out)
+            # gradient of the prior's last conv output: [dp stats (2*zd) | d p_feat (cin)]
+            DP = new_act(N, res, res, 2 * zd + st.cin, self.device)
+            dz = new_act(N, res, res, zd, self.device)
+            dz_written = False
+            dpf = DP.slice(2 * zd, round16(st.cin), st.cin)
+            if r.zs_out is not None:
+                prog.add(d.zfp.wgrad([r.z, r.pfeat], dzs_out, self.g(d.zfp.weight), self.g(d.zfp.bias), N, res, res))
+                prog.add(d.zfp.dgrad(0, dzs_out, SegSpec(dz, 0), N, res, res))
+                dz_written = True
+                prog.add(d.zfp.dgrad(1, dzs_out, SegSpec(dpf, 0, add=dh3), N, res, res))
+            else:
+                w = st.cin
+                prog.add(PyOp(lambda a=DP.t, b=dh3.t, w=w, o=2 * zd: a[..., o:o + w].copy_(b[..., :w]), "copy_dpfeat"))
+            # z_proj (no activation on its input)
+            prog.add(d.z_proj.wgrad([r.z, r.pa], dh3, self.g(d.z_proj.weight), self.g(d.z_proj.bias), N, res, res))
+            prog.add(d.z_proj.dgrad(0, dh3, SegSpec(dz, 0, add=dz if dz_written else None), N, res, res))
+            # latent
+            lb = L.LatentBwdArgs()
+            lb.p, lb.p_ld = r.pstat.ptr, r.pstat.ld
+            dq = None
+            if r.mode == 0:
+                dq = new_act(N, res, res, 2 * zd, self.device)
+                lb.q, lb.q_ld = r.qstat.ptr, r.qstat.ld
+                lb.dq, lb.dq_ld = dq.ptr, dq.ld
+                if explicit_eps:
+                    lb.eps = r.eps.data_ptr()
+                lb.offset = r.ksto << 40
+            lb.dz, lb.dz_ld, lb.g_kl = dz.ptr, dz.ld, g_kl
+            lb.dp, lb.dp_ld = DP.ptr, DP.ld
+            lb.N, lb.HW, lb.zdim, lb.mode = N, res * res, zd, r.mode
+            prog.add(L.Launch("cg_latent_bwd", C.byref(lb))).keep = (lb, dz, DP, dq)
+            D.latent_bwd_args.append(lb)
+            # posterior: d h_in = dh3 (+ posterior path), d acts[res] accumulates over blocks
+            if r.post is not None:
+                dh_in = new_act(N, res, res, st.cin, self.device)
+                if res in acts_grad:
+                    da = acts_grad[res]
+                    seg_a = SegSpec(da, 0, add=da)
+                else:
+                    da = acts_grad[res] = new_act(N, res, res, st.cin, self.device)
+                    seg_a = SegSpec(da, 0)
+                self._block_bwd(prog, r.post, dq, [SegSpec(dh_in, 0, add=dh3), None, seg_a])
+            else:
+                dh_in = dh3
+            # prior
+            if self.q_corr:
+                if dh_in is dh3:  # keep dh3 intact for clarity: accumulate into a fresh buffer
+                    tmp = new_act(N, res, res, st.cin, self.device)
+                    self._block_bwd(prog, r.prior, DP, [SegSpec(tmp, 0, add=dh_in)] + [None] * (len(r.prior.srcs) - 1))
+                    dh_in = tmp
+                else:
+                    self._block_bwd(prog, r.prior, DP, [SegSpec(dh_in, 0, add=dh_in)] + [None] * (len(r.prior.srcs) - 1))
+                dzs_in = None
+            else:
+                dzs_in = new_act(N, res, res, st.cin, self.device)
+                self._block_bwd(prog, r.prior, DP, [SegSpec(dzs_in, 0)] + [None] * (len(r.prior.srcs) - 1))
+            # upsample
+            if r.up is not None:
+                src_res, h_prev, zs_prev, b = r.up
+                dbias = self.g(b).data_ptr() if b is not None else None
+                dh_prev = new_act(N, src_res, src_res, st.cin, self.device)
+                prog.call("cg_upsample_bwd", dh_in.ptr, dh_prev.ptr, dbias, N, src_res, res, st.cin, dh_in.ld,
+                          dh_prev.ld, 0)
+                dzs_prev = None
+                if dzs_in is not None:
+                    if zs_prev is h_prev:  # first block: h and z are the same tensor
+                        prog.call("cg_upsample_bwd", dzs_in.ptr, dh_prev.ptr, dbias, N, src_res, res, st.cin,
+                                  dzs_in.ld, dh_prev.ld, 1)
+                    else:
+                        dzs_prev = new_act(N, src_res, src_res, st.cin, self.device)
+                        prog.call("cg_upsample_bwd", dzs_in.ptr, dzs_prev.ptr, dbias, N, src_res, res, st.cin,
+                                  dzs_in.ld, dzs_prev.ld, 0)
+                dh_out, dzs_out = dh_prev, dzs_prev
+            else:
+                dh_out, dzs_out = dh_in, dzs_in
+        # initial state h = z = bias[1] (src/vae.py:232)
+        g1 = self.g(bias_param[1])
+        w1 = dec.plan[0].cin
+        prog.call("cg_colsum", dh_out.ptr, g1.data_ptr(), N, w1, dh_out.ld)
+        if dzs_out is not None:
+            prog.call("cg_colsum", dzs_out.ptr, g1.data_ptr(), N, w1, dzs_out.ld)
+
+    def _encoder_bwd(self, prog: Program, e: Rec, acts_grad: Dict[int, View], N):
+        enc = self.model.encoder
+        din_next: Optional[View] = None
+        for i in range(len(e.blocks) - 1, -1, -1):
+            r = e.blocks[i]
+            own = acts_grad.get(r.st.res_out) if e.owner.get(r.st.res_out) == i else None
+            if din_next is None and own is None:
+                continue  # nothing downstream of this block reaches the loss
+            if din_next is None:
+                dout, extra = own, None
+            else:
+                dout, extra = din_next, own
+            if extra is not None:
+                # d(out) = d(next block input) + d(acts[res]); fold the sum into one tensor first
+                s = new_act(N, r.st.res_out, r.st.res_out, r.out.logical, self.device)
+                prog.call("cg_add", dout.ptr, extra.ptr, s.ptr, N * r.st.res_out * r.st.res_out, s.C, dout.ld,
+                          extra.ld, s.ld)
+                dout = s
+            din_next = self._res_block_bwd(prog, r, dout)
+        if din_next is not None:
+            prog.call("cg_stem_wgrad", e.x.data_ptr(), din_next.ptr, self.g(enc.stem.weight).data_ptr(),
+                      self.g(enc.stem.bias).data_ptr(), N, self.C, self.R, self.args.widths[0], din_next.ld)
+
+    # ================================================================== likelihood
+    def _lik_args(self, h: View, x: Optional[torch.Tensor], N):
+        lik = self.model.likelihood
+        HW = self.R * self.R
+        if self.dmol:
+            a = L.DmolArgs()
+            a.h, a.h_ld, a.Cw = h.ptr, h.ld, self.args.widths[0]
+            a.x = x.data_ptr() if x is not None else None
+            a.w, a.b = lik.conv.weight.data_ptr(), lik.conv.bias.data_ptr()
+            a.N, a.HW = N, HW
+            return a
+        a = L.DGaussArgs()
+        a.h, a.h_ld, a.Cw = h.ptr, h.ld, self.args.widths[0]
+        a.x = x.data_ptr() if x is not None else None
+        a.w_loc, a.b_loc = lik.x_loc.weight.data_ptr(), lik.x_loc.bias.data_ptr()
+        a.w_ls, a.b_ls = lik.x_logscale.weight.data_ptr(), lik.x_logscale.bias.data_ptr()
+        if self.C == 3:
+            a.w_co, a.b_co = lik.channel_coeffs.weight.data_ptr(), lik.channel_coeffs.bias.data_ptr()
+        a.N, a.HW, a.C = N, HW, self.C
+        return a
+
+    # ================================================================== programs
+    def _inputs(self, prog: Program, N, with_x=True, n_pa=1):
+        io = Rec()
+        if with_x:
+            io.x = torch.zeros(N, self.C, self.R, self.R, device=self.device, dtype=torch.float32)
+        io.pa_in = [torch.zeros(N, self.ctx, device=self.device, dtype=torch.float32) for _ in range(n_pa)]
+        io.pa = []
+        io.pa_sto = []
+        io.drop_launch = []
+        for t in io.pa_in:
+            v = View(torch.zeros(N, self.ctx_pad, device=self.device, dtype=torch.bfloat16), self.ctx_pad, 0, self.ctx,
+                     bcast=True)
+            prog.call("cg_parents_pack", t.data_ptr(), self.ctx, 1, v.ptr, N, self.ctx, self.ctx_pad, self.ctx, 1.0)
+            io.pa.append(v)
+            if self.model.decoder.is_drop_cond:  # src/vae.py:244-247: channels 2: scaled by p_sto
+                vs = View(torch.zeros_like(v.t), self.ctx_pad, 0, self.ctx, bcast=True)
+                ln = prog.call("cg_parents_pack", t.data_ptr(), self.ctx, 1, vs.ptr, N, self.ctx, self.ctx_pad, 2, 1.0)
+                io.drop_launch.append(ln)
+                io.pa_sto.append(vs)
+            else:
+                io.pa_sto.append(v)
+        return io
+
+    def build_elbo(self, N: int, train: bool, explicit_eps: bool) -> Program:
+        """HVAE.forward (src/vae.py:439-458) and, when `train`, its full backward"""
+        prog = Program(f"elbo(N={N},train={train})")
+        io = self._inputs(prog, N)
+        prog.io = io
+        nsto = sum(1 for d in self.dec_layers if d.st.stochastic)
+        prog.kl_rows = torch.zeros(max(nsto, 1), N, device=self.device, dtype=torch.float32)
+        prog.nll = torch.zeros(N, device=self.device, dtype=torch.float32)
+        prog.out3 = torch.zeros(3, device=self.device, dtype=torch.float32)
+        prog.zero = [prog.kl_rows, prog.nll]
+        e = self._encoder_fwd(prog, io.x, N)
+        D = self._decoder_fwd(prog, N, io.pa[0], io.pa_sto[0], e.acts, explicit_eps=explicit_eps,
+                              kl_rows=prog.kl_rows)
+        k = 0
+        for r in D.blocks:
+            r.pa = io.pa[0]
+            r.ksto = k
+            if r.st.stochastic:
+                k += 1
+        prog.D, prog.e = D, e
+        prog.eps = D.eps
+        la = self._lik_args(D.h, io.x, N)
+        la.nll = prog.nll.data_ptr()
+        prog.lik = la
+        prog.add(L.Launch("cg_dmol_loss_fwd" if self.dmol else "cg_dgauss_nll_fwd", C.byref(la)))
+        npix = float(self.C * self.R * self.R)
+        prog.fin = prog.call("cg_elbo_finalize", prog.nll.data_ptr(), prog.kl_rows.data_ptr(), prog.out3.data_ptr(),
+                             N, max(nsto, 1), 1.0 / npix, 1.0)
+        prog.n_fwd = len(prog.launches)
+        if train:
+            prog.beta_users = []
+            lik = self.model.likelihood
+            dh = new_act(N, self.R, self.R, self.args.widths[0], self.device)
+            lb = self._lik_args(D.h, io.x, N)
+            lb.g = 1.0 / N
+            lb.dh, lb.dh_ld = dh.ptr, dh.ld
+            if self.dmol:
+                lb.dw, lb.db = self.g(lik.conv.weight).data_ptr(), self.g(lik.conv.bias).data_ptr()
+                prog.add(L.Launch("cg_dmol_loss_bwd", C.byref(lb))).keep = (lb, dh)
+            else:
+                lb.dw_loc, lb.db_loc = self.g(lik.x_loc.weight).data_ptr(), self.g(lik.x_loc.bias).data_ptr()
+                lb.dw_ls, lb.db_ls = self.g(lik.x_logscale.weight).data_ptr(), self.g(lik.x_logscale.bias).data_ptr()
+                if self.C == 3:
+                    lb.dw_co = self.g(lik.channel_coeffs.weight).data_ptr()
+                    lb.db_co = self.g(lik.channel_coeffs.bias).data_ptr()
+                prog.add(L.Launch("cg_dgauss_nll_bwd", C.byref(lb))).keep = (lb, dh)
+            acts_grad: Dict[int, View] = {}
+            self._decoder_bwd(prog, D, dh, N, 1.0 / (N * npix), acts_grad, explicit_eps)
+            self._encoder_bwd(prog, e, acts_grad, N)
+            prog.npix = npix
+        return prog
+
+    def set_beta(self, prog: Program, beta: float, N: int):
+        args = list(prog.fin.args)
+        args[-1] = C.c_float(beta)
+        prog.fin.args = tuple(args)
+        if hasattr(prog.D, "latent_bwd_args"):
+            for lb in prog.D.latent_bwd_args:
+                lb.g_kl = beta / (N * prog.npix)
+
+    def build_decode(self, N: int, kind: str, given: Optional[Sequence[bool]] = None, n_pa: int = 1,
+                     want_stats: bool = False) -> Program:
+        """kind: 'abduct' (encoder + posterior pass returning z), 'latents' (forward_latents / sample)"""
+        prog = Program(f"{kind}(N={N})")
+        if kind == "abduct":
+            io = self._inputs(prog, N)
+            e = self._encoder_fwd(prog, io.x, N)
+            prog.D = self._decoder_fwd(prog, N, io.pa[0], io.pa_sto[0], e.acts, want_z=True, want_stats=want_stats)
+            prog.io = io
+            return prog
+        io = self._inputs(prog, N, with_x=False, n_pa=n_pa)
+        prog.io = io
+        prog.Ds, prog.x_out, prog.scale_out, prog.lik_args = [], [], [], []
+        for j in range(n_pa):
+            D = self._decoder_fwd(prog, N, io.pa[j], io.pa_sto[j], None, given=given, want_stats=want_stats)
+            xo = torch.zeros(N, self.C, self.R, self.R, device=self.device, dtype=torch.float32)
+            so = torch.zeros_like(xo)
+            la = self._lik_args(D.h, None, N)
+            if self.dmol:
+                prog.add(L.Launch("cg_dmol_predict", C.byref(la), 0, None, None, C.c_float(0.0), xo.data_ptr(),
+                                  so.data_ptr()))
+            else:
+                prog.add(L.Launch("cg_dgauss_sample", C.byref(la), xo.data_ptr(), so.data_ptr(), None, C.c_float(0.0)))
+            prog.Ds.append(D)
+            prog.x_out.append(xo)
+            prog.scale_out.append(so)
+            prog.lik_args.append(la)
+        return prog
