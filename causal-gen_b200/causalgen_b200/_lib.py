@@ -121,7 +121,8 @@ _SIGNATURES = {
     "cg_fill_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "cg_colsum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "cg_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_int32] * 4 + [C.c_void_p]),
-    "cg_elbo_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_void_p]),
+    "cg_elbo_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float,
+                                   C.c_void_p]),
     "cg_sumsq": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "cg_optim_advance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32] +
                          [C.c_float] * 6 + [C.c_int32, C.c_void_p]),
@@ -166,7 +167,7 @@ class Launch:
 
     def __init__(self, name, *args):
         self.fn = getattr(load(), name)
-        self.args = args
+        self.args = tuple(args)
         self.name = name
         self.keep = None
 

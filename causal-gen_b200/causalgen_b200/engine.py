@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -21,6 +22,11 @@ import torch
 from . import _lib as L
 from .model import Block, DmolNet
 from .ops import ConvLayer, PackTable, SegSpec, View, new_act, round16
+
+
+# CAUSALGEN_B200_TRACE_ONLY=1 lets the launch programs be *built* (buffers + argument structs) on a host
+# without a GPU so their structure can be unit-tested; nothing is executed and outputs stay zero.
+TRACE_ONLY = os.environ.get("CAUSALGEN_B200_TRACE_ONLY", "0") == "1"
 
 
 class PyOp:
@@ -50,6 +56,8 @@ class Program:
         return self.add(L.Launch(name, *args))
 
     def run(self, stream=None):
+        if TRACE_ONLY:  # program construction check on a box without a GPU: nothing is computed
+            return
         s = torch.cuda.current_stream().cuda_stream if stream is None else stream
         for ln in self.launches:
             ln(s)
@@ -86,13 +94,14 @@ class Engine:
         self.model = model
         self.args = args
         p0 = next(model.parameters())
-        if p0.device.type != "cuda":
+        if p0.device.type != "cuda" and not TRACE_ONLY:
             raise RuntimeError("causalgen_b200 runs on a CUDA sm_100 device only (no CPU fallback); move the model "
                                "to cuda first")
         self.device = p0.device
-        with torch.cuda.device(self.device):
-            if L.load().cg_device_sms() <= 0:
-                raise RuntimeError("causalgen_b200: device is not sm_100 (B200); there is no fallback path")
+        if not TRACE_ONLY:
+            with torch.cuda.device(self.device):
+                if L.load().cg_device_sms() <= 0:
+                    raise RuntimeError("causalgen_b200: device is not sm_100 (B200); there is no fallback path")
         self.table = PackTable(self.device)
         self.zd = args.z_dim
         self.ctx = args.context_dim
@@ -143,6 +152,8 @@ class Engine:
         return None if p is None else self.grad_of[id(p)]
 
     def pack_weights(self, stream=None):
+        if TRACE_ONLY:
+            return
         s = torch.cuda.current_stream().cuda_stream if stream is None else stream
         self.table.launch(s)
 

@@ -1,0 +1,314 @@
+"""Drop-in surface of the reference's image mechanism: ``HVAE`` (src/vae.py:425-522), its likelihood heads
+and the DSCM abduction -> action -> prediction lines (src/pgm/dscm.py:47-72,121-132).
+
+Same constructor (an ``args`` bag built by the reference's own ``hps.py``), same state_dict keys, same
+methods and return types.  Differences are documented fences, not silent changes:
+  * runs only on an sm_100 CUDA device through libcausalgen_b200.so (no CPU/eager fallback);
+  * activations are bf16 with fp32 accumulation / fp32 latent + likelihood math (reference: fp32/TF32);
+  * ``forward`` accepts an optional ``eps`` list (one (B,16,r,r) tensor per stochastic block, reference RNG
+    order) so tests can feed identical noise; without it noise comes from an in-kernel Philox stream;
+  * gradients flow into the parameters for ``forward`` (the training path).  Gradients through
+    ``abduct``/``forward_latents`` (counterfactual fine-tuning) are not implemented yet.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib as L
+from .engine import Engine, TRACE_ONLY
+from .model import Decoder, DGaussNet, DmolNet, Encoder
+
+
+def _stream() -> int:
+    return 0 if TRACE_ONLY else torch.cuda.current_stream().cuda_stream
+
+
+def _pa_vector(parents: Tensor) -> Tensor:
+    """(B,ctx,R,R) spatially-constant parents (src/trainer.py:20, src/pgm/dscm.py:129-131) or (B,ctx)"""
+    if parents.dim() == 4:
+        return parents[:, :, 0, 0]
+    return parents
+
+
+class _ElboFn(torch.autograd.Function):
+    """One autograd node for the whole hand-written forward+backward."""
+
+    @staticmethod
+    def forward(ctx, model, x, parents, beta, eps, *params):
+        out3 = model._run_elbo(x, parents, beta, eps, train=True)
+        ctx.model = model
+        ctx.nparams = len(params)
+        return out3[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        eng = ctx.model._engine_or_none()
+        flat = eng.flat_grad * g  # one op; views of the copy are safe for autograd to keep
+        grads, off = [], 0
+        for p in eng.params:
+            grads.append(flat[off: off + p.numel()].view_as(p) if p.requires_grad else None)
+            off += p.numel()
+        return (None, None, None, None, None) + tuple(grads)
+
+
+class HVAE(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        args.vr = "light" if "ukbb" in args.hps else None  # src/vae.py:428 (hidden state on args, kept)
+        self.encoder = Encoder(args)
+        self.decoder = Decoder(args)
+        if args.x_like.split("_")[1] == "dgauss":
+            self.likelihood = DGaussNet(args)
+        elif args.x_like.split("_")[1] == "dmol":
+            self.likelihood = DmolNet(args)
+        else:
+            raise NotImplementedError(f"{args.x_like} not implemented.")
+        self.cond_prior = args.cond_prior
+        self.free_bits = args.kl_free_bits
+        keys = ("hps", "enc_arch", "dec_arch", "widths", "bottleneck", "z_dim", "z_max_res", "bias_max_res",
+                "input_channels", "input_res", "context_dim", "cond_prior", "q_correction", "x_like", "std_init",
+                "kl_free_bits", "vr")
+        self._hp = {k: getattr(args, k) for k in keys}
+        self.__dict__["_engine"] = None
+        self.__dict__["_noise_calls"] = 0
+
+    # ------------------------------------------------------------------ engine plumbing
+    def __getstate__(self):  # copy.deepcopy (EMA, src/utils.py:125) must not drag device programs along
+        st = self.__dict__.copy()
+        st["_engine"] = None
+        return st
+
+    def _engine_or_none(self) -> Optional[Engine]:
+        return self.__dict__.get("_engine")
+
+    def engine(self) -> Engine:
+        eng = self.__dict__.get("_engine")
+        if eng is None or eng.signature != Engine.param_signature(self):
+            from types import SimpleNamespace
+            eng = Engine(self, SimpleNamespace(**self._hp))
+            self.__dict__["_engine"] = eng
+        return eng
+
+    def _seed(self) -> int:
+        self.__dict__["_noise_calls"] = self.__dict__.get("_noise_calls", 0) + 1
+        return (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._noise_calls * 0xD1B54A32D192ED03) % (1 << 64)
+
+    def _program(self, key, build):
+        eng = self.engine()
+        if key not in eng.programs:
+            if eng.device.type == "cuda":
+                with torch.cuda.device(eng.device):
+                    eng.programs[key] = build()
+            else:
+                eng.programs[key] = build()
+        return eng.programs[key]
+
+    def _load_parents(self, prog, io, plist: Sequence[Tensor], training_drop: Optional[Tuple[float, float]] = None):
+        for buf, pa in zip(io.pa_in, plist):
+            buf.copy_(_pa_vector(pa).to(torch.float32))
+        for ln in io.drop_launch:
+            scale = 1.0 if training_drop is None else float(training_drop[0])
+            a = list(ln.args)
+            a[-1] = C.c_float(scale)
+            ln.args = tuple(a)
+
+    def _set_noise(self, D, eps: Optional[Sequence[Tensor]], log_t: float, bwd=None):
+        seed = self._seed()
+        k = 0
+        for la in D.latent_args:
+            la.log_t = log_t
+            if la.mode in (0, 1):
+                la.seed = seed
+        if eps is not None:
+            bufs = [b for b in D.eps if b is not None]
+            assert len(eps) >= len(bufs), f"need {len(bufs)} eps tensors, got {len(eps)}"
+            for b, e in zip(bufs, eps):
+                b.copy_(e)
+        if bwd is not None:
+            for lb in bwd:
+                lb.seed = seed
+        return seed
+
+    # ------------------------------------------------------------------ ELBO
+    def drop_cond(self) -> Tuple[int, int]:
+        """conditioning dropout draw, CPU RNG like the reference (src/vae.py:310-319)"""
+        opt = int(torch.distributions.Categorical(1 / 3 * torch.ones(3)).sample())
+        return [(0, 1), (1, 0), (1, 1)][opt]
+
+    def _run_elbo(self, x: Tensor, parents: Tensor, beta, eps, train: bool) -> Tensor:
+        if self.free_bits > 0:
+            raise NotImplementedError("kl_free_bits > 0 (src/vae.py:443-449) is not on the hot path (default 0)")
+        eng = self.engine()
+        N = x.shape[0]
+        explicit = eps is not None
+        prog = self._program(("elbo", N, train, explicit), lambda: eng.build_elbo(N, train, explicit))
+        prog.io.x.copy_(x)
+        drop = None
+        if self.training and self.cond_prior and self.decoder.is_drop_cond:
+            drop = self.drop_cond()
+        self._load_parents(prog, prog.io, [parents], drop)
+        self._set_noise(prog.D, eps, 0.0, getattr(prog.D, "latent_bwd_args", None))
+        eng.set_beta(prog, float(beta), N) if train else self._set_beta_fwd(prog, float(beta))
+        for t in prog.zero:
+            t.zero_()
+        if train:
+            eng.flat_grad.zero_()
+        eng.pack_weights()
+        prog.run()
+        return prog.out3
+
+    @staticmethod
+    def _set_beta_fwd(prog, beta):
+        a = list(prog.fin.args)
+        a[-1] = C.c_float(beta)
+        prog.fin.args = tuple(a)
+
+    def forward(self, x: Tensor, parents: Tensor, beta: float = 1, eps: Optional[Sequence[Tensor]] = None
+                ) -> Dict[str, Tensor]:
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if need_grad:
+            params = list(self.parameters())
+            elbo = _ElboFn.apply(self, x, parents, beta, eps, *params)
+            out3 = self.engine().programs[("elbo", x.shape[0], True, eps is not None)].out3
+        else:
+            out3 = self._run_elbo(x, parents, beta, eps, train=False)
+            elbo = out3[0].clone()
+        return dict(elbo=elbo, nll=out3[1].clone(), kl=out3[2].clone())
+
+    def block_kl(self) -> Tensor:
+        """(B, n_stochastic) per-block KL sums of the last forward() -- parity tests / TensorBoard"""
+        eng = self.engine()
+        progs = [p for k, p in eng.programs.items() if k[0] == "elbo"]
+        return progs[-1].kl_rows.t().clone()
+
+    # ------------------------------------------------------------------ inference surface
+    @torch.no_grad()
+    def abduct(self, x: Tensor, parents: Tensor, cf_parents: Optional[Tensor] = None, alpha: float = 0.5,
+               t: Optional[float] = None, eps: Optional[Sequence[Tensor]] = None):
+        eng = self.engine()
+        N = x.shape[0]
+        prog = self._program(("abduct", N, self.cond_prior),
+                             lambda: eng.build_decode(N, "abduct", want_stats=self.cond_prior))
+        prog.io.x.copy_(x)
+        self._load_parents(prog, prog.io, [parents])
+        log_t = math.log(t) if t is not None else 0.0
+        n_eps = len([b for b in prog.D.eps if b is not None])
+        self._set_noise(prog.D, eps[:n_eps] if eps is not None else self._host_eps(prog.D), log_t)
+        eng.pack_weights()
+        prog.run()
+        zs = [prog.D.z_out[k].clone() for k in sorted(prog.D.z_out)]
+        if not self.cond_prior:
+            return zs
+        lib = L.load()
+        s = _stream()
+        q_stats = []
+        for k in sorted(prog.D.z_out):
+            qstat, _ = prog.D.stats_out[k]
+            q_stats.append({"z": zs[k], "q_loc": self._stat_nchw(qstat, 0, 0.0), "q_logscale": self._stat_nchw(qstat, 16, log_t)})
+        if cf_parents is None:
+            return q_stats
+        # second decoder pass: prior only under the counterfactual parents (src/vae.py:480-482)
+        pprog = self._program(("prior_stats", N), lambda: eng.build_decode(N, "latents", given=None, want_stats=True))
+        self._load_parents(pprog, pprog.io, [cf_parents])
+        D = pprog.Ds[0]
+        self._set_noise(D, eps[n_eps:] if eps is not None else self._host_eps(D), log_t)
+        pprog.run()
+        out = []
+        for k, qs in enumerate(q_stats):
+            _, pstat = D.stats_out[k]
+            p_loc, p_ls = self._stat_nchw(pstat, 0, 0.0), self._stat_nchw(pstat, 16, log_t)
+            z = torch.empty_like(qs["z"])
+            L.check(lib.cg_latent_mix(qs["z"].data_ptr(), qs["q_loc"].data_ptr(), qs["q_logscale"].data_ptr(),
+                                      p_loc.data_ptr(), p_ls.data_ptr(), z.data_ptr(), z.numel(), float(alpha),
+                                      float(t) if t is not None else 1.0, int(t is not None), s), "cg_latent_mix")
+            out.append(z)
+        return out
+
+    def _stat_nchw(self, stat, c0: int, add: float) -> Tensor:
+        N, H, W, _ = stat.t.shape
+        out = torch.empty(N, 16, H, W, device=stat.t.device, dtype=torch.float32)
+        L.check(L.load().cg_stats_to_nchw(stat.ptr, stat.ld, c0, float(add), out.data_ptr(), N, 16, H * W,
+                                          _stream()), "cg_stats_to_nchw")
+        return out
+
+    def _host_eps(self, D):
+        """explicit-eps programs without caller noise: draw with torch's device RNG like the reference
+        (randn_like, src/vae.py:30)"""
+        return [torch.randn_like(b) for b in D.eps if b is not None]
+
+    @torch.no_grad()
+    def _decode(self, latents: Sequence[Optional[Tensor]], plist: Sequence[Tensor], t: Optional[float],
+                eps: Optional[Sequence[Tensor]]):
+        eng = self.engine()
+        N = plist[0].shape[0]
+        nsto = sum(1 for d in eng.dec_layers if d.st.stochastic)
+        given = tuple(i < len(latents) and latents[i] is not None for i in range(nsto))
+        prog = self._program(("latents", N, given, len(plist)),
+                             lambda: eng.build_decode(N, "latents", given=given, n_pa=len(plist)))
+        self._load_parents(prog, prog.io, plist)
+        log_t = math.log(t) if t is not None else 0.0
+        ofs = 0
+        for D in prog.Ds:
+            for k, buf in D.z_in.items():
+                buf.copy_(latents[k])
+            n_eps = len([b for b in D.eps if b is not None])
+            self._set_noise(D, eps[ofs: ofs + n_eps] if eps is not None else self._host_eps(D), log_t)
+            ofs += n_eps
+        eng.pack_weights()
+        prog.run()
+        return prog
+
+    def forward_latents(self, latents: List[Tensor], parents: Tensor, t: Optional[float] = None,
+                        eps: Optional[Sequence[Tensor]] = None) -> Tuple[Tensor, Tensor]:
+        latents = [z["z"] if isinstance(z, dict) else z for z in latents]
+        prog = self._decode(latents, [parents], t, eps)
+        return prog.x_out[0].clone(), prog.scale_out[0].clone()
+
+    def sample(self, parents: Tensor, return_loc: bool = True, t: Optional[float] = None,
+               eps: Optional[Sequence[Tensor]] = None) -> Tuple[Tensor, Tensor]:
+        if not return_loc:
+            raise NotImplementedError("return_loc=False hits a reference bug (t passed as x, src/vae.py:419 vs "
+                                      ":352); use return_loc=True as every reference caller does")
+        prog = self._decode([], [parents], t, eps)
+        return prog.x_out[0].clone(), prog.scale_out[0].clone()
+
+
+# ---------------------------------------------------------------------------------------------
+# DSCM hot lines (src/pgm/dscm.py)
+# ---------------------------------------------------------------------------------------------
+def vae_preprocess(args, pa: Dict[str, Tensor]) -> Tensor:
+    """src/pgm/dscm.py:121-132 without the (B,ctx,R,R) materialisation: returns (B, ctx) on the GPU;
+    every entry point of ``HVAE`` accepts either form."""
+    cols = [pa[k] if pa[k].dim() > 1 else pa[k][..., None] for k in args.parents_x]
+    return torch.cat(cols, dim=1).cuda().float()
+
+
+@torch.no_grad()
+def counterfactual(vae: HVAE, x: Tensor, pa: Tensor, cf_pa: Tensor, t_abduct: float = 1.0, particles: int = 1,
+                   eps: Optional[Sequence[Sequence[Tensor]]] = None):
+    """abduct -> forward_latents(cf_pa) & forward_latents(pa) (one 2-parent-set pass) -> combine
+    (src/pgm/dscm.py:47-72).  Returns (cf_x, var_cf_x or None)."""
+    lib = L.load()
+    n = x.numel()
+    acc = torch.zeros_like(x) if particles > 1 else None
+    acc2 = torch.zeros_like(x) if particles > 1 else None
+    cf_x = torch.empty_like(x)
+    for i in range(particles):
+        zs = vae.abduct(x, pa, t=t_abduct, eps=None if eps is None else eps[i])
+        zs = [z["z"] if isinstance(z, dict) else z for z in zs]
+        prog = vae._decode(zs, [cf_pa, pa], None, None)
+        s = _stream()
+        L.check(lib.cg_cf_combine(x.data_ptr(), prog.x_out[1].data_ptr(), prog.scale_out[1].data_ptr(),
+                                  prog.x_out[0].data_ptr(), prog.scale_out[0].data_ptr(), cf_x.data_ptr(),
+                                  acc.data_ptr() if acc is not None else None,
+                                  acc2.data_ptr() if acc2 is not None else None, n, s), "cg_cf_combine")
+    if particles > 1:
+        mean = acc / particles
+        var = (acc2 - acc ** 2 / particles) / particles  # src/pgm/dscm.py:68
+        return mean, var
+    return cf_x, None

@@ -163,11 +163,11 @@ __global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ 
 }
 
 __global__ void elbo_finalize_kernel(const float* __restrict__ nll, const float* __restrict__ kl, float* __restrict__ out,
-                                     int N, float kl_scale, float beta) {
+                                     int N, int nblk, float kl_scale, float beta) {
   float a = 0.f, b = 0.f;
   for (int i = threadIdx.x; i < N; i += 32) {
     a += nll[i];
-    b += kl[i];
+    for (int j = 0; j < nblk; ++j) b += kl[(long long)j * N + i];
   }
   a = cg_warp_sum(a);
   b = cg_warp_sum(b);
@@ -267,10 +267,10 @@ extern "C" int cg_add(const void* a, const void* b, void* y, int64_t rows, int32
   return CG_OK;
 }
 
-extern "C" int cg_elbo_finalize(const float* nll, const float* kl, float* out, int32_t N, float kl_scale, float beta,
-                                void* stream) {
+extern "C" int cg_elbo_finalize(const float* nll, const float* kl, float* out, int32_t N, int32_t nblk, float kl_scale,
+                                float beta, void* stream) {
   CG_ARCH_GUARD();
-  elbo_finalize_kernel<<<1, 32, 0, cg_stream(stream)>>>(nll, kl, out, N, kl_scale, beta);
+  elbo_finalize_kernel<<<1, 32, 0, cg_stream(stream)>>>(nll, kl, out, N, nblk, kl_scale, beta);
   CG_LAUNCH_CHECK("cg_elbo_finalize");
   return CG_OK;
 }

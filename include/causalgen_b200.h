@@ -259,9 +259,10 @@ int cg_colsum(const void* dy, float* dv, int64_t rows, int32_t C, int32_t ld, vo
 int cg_add(const void* a, const void* b, void* y, int64_t rows, int32_t C, int32_t a_ld, int32_t b_ld,
            int32_t y_ld, void* stream);
 
-/* elbo = mean(nll) + beta*mean(kl)/npix_dims  (src/vae.py:451-458); out[3] = {elbo,nll,kl} */
-int cg_elbo_finalize(const float* nll, const float* kl, float* out, int32_t N, float kl_scale,
-                     float beta, void* stream);
+/* kl rows (nblk, N): per-block per-sample KL sums.  kl_pp[n] = kl_scale * sum_blk kl[blk][n];
+ * elbo = mean(nll) + beta*mean(kl_pp)  (src/vae.py:451-458); out[3] = {elbo,nll,kl} */
+int cg_elbo_finalize(const float* nll, const float* kl, float* out, int32_t N, int32_t nblk,
+                     float kl_scale, float beta, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Optimiser tail on flat fp32 buffers (src/trainer.py:66-87, src/train_setup.py:42-53,
