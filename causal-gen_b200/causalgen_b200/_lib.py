@@ -22,9 +22,9 @@ class Src(C.Structure):
 
 
 class Seg(C.Structure):
-    _fields_ = [("ptr", C.c_void_p), ("add", C.c_void_p), ("mul", C.c_void_p),
+    _fields_ = [("ptr", C.c_void_p), ("add", C.c_void_p), ("add2", C.c_void_p), ("mul", C.c_void_p),
                 ("c0", C.c_int32), ("cn", C.c_int32), ("ld", C.c_int32), ("add_ld", C.c_int32),
-                ("mul_ld", C.c_int32), ("dtype", C.c_int32), ("mul_act", C.c_int32), ("_pad", C.c_int32)]
+                ("add2_ld", C.c_int32), ("mul_ld", C.c_int32), ("dtype", C.c_int32), ("mul_act", C.c_int32)]
 
 
 class ConvArgs(C.Structure):
@@ -52,7 +52,8 @@ class WgradArgs(C.Structure):
 
 class LatentArgs(C.Structure):
     _fields_ = [("q", C.c_void_p), ("p", C.c_void_p), ("q_ld", C.c_int32), ("p_ld", C.c_int32),
-                ("eps", C.c_void_p), ("seed", C.c_uint64), ("offset", C.c_uint64), ("log_t", C.c_float),
+                ("eps", C.c_void_p), ("seed", C.c_uint64), ("offset", C.c_uint64), ("seed_dev", C.c_void_p),
+                ("log_t", C.c_float),
                 ("z_bf16", C.c_void_p), ("z_ld", C.c_int32), ("z_f32", C.c_void_p), ("eps_out", C.c_void_p),
                 ("kl_out", C.c_void_p), ("N", C.c_int32), ("HW", C.c_int32), ("zdim", C.c_int32),
                 ("mode", C.c_int32)]
@@ -60,7 +61,7 @@ class LatentArgs(C.Structure):
 
 class LatentBwdArgs(C.Structure):
     _fields_ = [("q", C.c_void_p), ("p", C.c_void_p), ("q_ld", C.c_int32), ("p_ld", C.c_int32),
-                ("eps", C.c_void_p), ("seed", C.c_uint64), ("offset", C.c_uint64),
+                ("eps", C.c_void_p), ("seed", C.c_uint64), ("offset", C.c_uint64), ("seed_dev", C.c_void_p),
                 ("dz", C.c_void_p), ("dz_ld", C.c_int32), ("g_kl", C.c_float),
                 ("dq", C.c_void_p), ("dq_ld", C.c_int32), ("dp", C.c_void_p), ("dp_ld", C.c_int32),
                 ("N", C.c_int32), ("HW", C.c_int32), ("zdim", C.c_int32), ("mode", C.c_int32)]

@@ -261,10 +261,8 @@ class Engine:
             p_src = [h if self.q_corr else zs] + ([pa_sto] if self.cond_prior else [])
             r.pstat = View(torch.zeros(N, res, res, 2 * zd, device=self.device, dtype=torch.float32), 2 * zd)
             r.pfeat = new_act(N, res, res, st.cin, self.device)
-            r.h2 = new_act(N, res, res, st.cin, self.device)
             r.prior = self._block_fwd(prog, d.prior, p_src, N, res, res,
-                                      final_segs=[SegSpec(r.pstat, 0), SegSpec(r.pfeat, 2 * zd),
-                                                  SegSpec(r.h2, 2 * zd, add=h)])
+                                      final_segs=[SegSpec(r.pstat, 0), SegSpec(r.pfeat, 2 * zd)])
             # ---- posterior + latent (src/vae.py:265-291)
             r.z = new_act(N, res, res, zd, self.device)
             r.post = None
@@ -317,7 +315,8 @@ class Engine:
                 D.latent_args.append(la)
             # ---- merge (src/vae.py:292-300)
             r.h3 = new_act(N, res, res, st.cin, self.device)
-            prog.add(d.z_proj.forward([r.z, pa], [SegSpec(r.h3, 0, add=r.h2)], N, res, res))
+            # h3 = h + p_feat + z_proj(cat[z, pa]) in one epilogue (src/vae.py:292-294)
+            prog.add(d.z_proj.forward([r.z, pa], [SegSpec(r.h3, 0, add=h, add2=r.pfeat)], N, res, res))
             r.conv = self._block_fwd(prog, d.conv, [r.h3], N, res, res)
             h = r.conv.y
             r.zs_out = None

@@ -58,6 +58,7 @@ class SegSpec:
     add: Optional[View] = None
     mul: Optional[View] = None
     mul_act: int = L.ACT_NONE
+    add2: Optional[View] = None
 
 
 class PackTable:
@@ -154,6 +155,8 @@ class ConvLayer:
             s.dtype = L.F32 if sg.out.t.dtype == torch.float32 else L.BF16
             s.add = sg.add.ptr if sg.add is not None else None
             s.add_ld = sg.add.ld if sg.add is not None else 0
+            s.add2 = sg.add2.ptr if sg.add2 is not None else None
+            s.add2_ld = sg.add2.ld if sg.add2 is not None else 0
             s.mul = sg.mul.ptr if sg.mul is not None else None
             s.mul_ld = sg.mul.ld if sg.mul is not None else 0
             s.mul_act = sg.mul_act

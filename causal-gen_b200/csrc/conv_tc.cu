@@ -257,6 +257,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               for (int i = 0; i < 8; ++i) v[h8 + i] += x[i];
             }
           }
+          if (sg.add2 != nullptr) {
+            const bf16* ap = reinterpret_cast<const bf16*>(sg.add2) + pix * sg.add2_ld + lc;
+            for (int h8 = 0; h8 < cnt; h8 += 8) {
+              float x[8];
+              cg_unpack8(*reinterpret_cast<const uint4*>(ap + h8), x);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[h8 + i] += x[i];
+            }
+          }
           if (sg.dtype == CG_F32) {
             float* op = reinterpret_cast<float*>(sg.ptr) + pix * sg.ld + lc;
             for (int q = 0; q < cnt; q += 4)
@@ -339,6 +348,7 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
     CG_REQUIRE(sg.c0 % 16 == 0 && sg.cn % 8 == 0 && sg.cn > 0 && sg.ld % (sg.dtype == CG_F32 ? 4 : 8) == 0,
                "cg_conv2d: seg %d c0=%d cn=%d ld=%d", s, sg.c0, sg.cn, sg.ld);
     CG_REQUIRE(sg.add == nullptr || (((uintptr_t)sg.add & 15) == 0 && sg.add_ld % 8 == 0), "cg_conv2d: seg %d add", s);
+    CG_REQUIRE(sg.add2 == nullptr || (((uintptr_t)sg.add2 & 15) == 0 && sg.add2_ld % 8 == 0), "cg_conv2d: seg %d add2", s);
     CG_REQUIRE(sg.mul == nullptr || (((uintptr_t)sg.mul & 15) == 0 && sg.mul_ld % 8 == 0), "cg_conv2d: seg %d mul", s);
   }
   kp.Hp = a->H + 1;

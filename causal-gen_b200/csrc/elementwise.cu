@@ -137,13 +137,14 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const cg_latent_args a)
   const int npx = min(kLatPix, a.HW - hw0);
   const int zd = a.zdim;  // 16
   const int tid = threadIdx.x;
+  const uint64_t seed = a.seed + (a.seed_dev != nullptr ? *a.seed_dev : 0ull);
   if (a.mode != 2) {
     for (int e = tid; e < zd * kLatPix; e += 256) {
       int c = e / kLatPix, px = e - c * kLatPix;
       float v = 0.f;
       if (px < npx) {
         long long gi = ((long long)n * zd + c) * a.HW + hw0 + px;
-        v = a.eps != nullptr ? a.eps[gi] : philox_normal(a.seed, a.offset + (uint64_t)gi);
+        v = a.eps != nullptr ? a.eps[gi] : philox_normal(seed, a.offset + (uint64_t)gi);
         if (a.eps_out != nullptr) a.eps_out[gi] = v;
       }
       s_eps[c][px] = v;
@@ -197,13 +198,14 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const cg_latent_bwd_arg
   const int npx = min(kLatPix, a.HW - hw0);
   const int zd = a.zdim;
   const int tid = threadIdx.x;
+  const uint64_t seed = a.seed + (a.seed_dev != nullptr ? *a.seed_dev : 0ull);
   if (a.mode != 2) {
     for (int e = tid; e < zd * kLatPix; e += 256) {
       int c = e / kLatPix, px = e - c * kLatPix;
       float v = 0.f;
       if (px < npx) {
         long long gi = ((long long)n * zd + c) * a.HW + hw0 + px;
-        v = a.eps != nullptr ? a.eps[gi] : philox_normal(a.seed, a.offset + (uint64_t)gi);
+        v = a.eps != nullptr ? a.eps[gi] : philox_normal(seed, a.offset + (uint64_t)gi);
       }
       s_eps[c][px] = v;
     }

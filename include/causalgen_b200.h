@@ -58,12 +58,12 @@ typedef struct {
 typedef struct {
   void* ptr;        /* destination of output channels [c0, c0+cn) */
   const void* add;  /* optional bf16 tensor added after everything else (residual / accumulate) */
+  const void* add2; /* optional second bf16 addend (h + p_feat + z_proj(...) in one pass, src/vae.py:292-294) */
   const void* mul;  /* optional bf16 pre-activation tensor x: result *= act'(x)  (backward) */
   int32_t c0, cn;   /* c0 multiple of 16, cn multiple of 8 */
-  int32_t ld, add_ld, mul_ld;
+  int32_t ld, add_ld, add2_ld, mul_ld;
   int32_t dtype;    /* CG_BF16 or CG_F32 */
   int32_t mul_act;  /* activation whose derivative is applied with `mul` */
-  int32_t _pad;
 } cg_seg;
 
 typedef struct {
@@ -158,6 +158,7 @@ int cg_upsample_bwd(const void* dy, void* dx, float* dbias, int32_t N, int32_t H
 typedef struct {
   const float* q; const float* p; int32_t q_ld, p_ld;
   const float* eps; uint64_t seed; uint64_t offset;
+  const uint64_t* seed_dev; /* optional device counter added to seed (graph-replayable noise) */
   float log_t;            /* log temperature added to both logscales (0 when t is None) */
   void* z_bf16; int32_t z_ld;
   float* z_f32;
@@ -173,7 +174,7 @@ int cg_latent_fwd(const cg_latent_args* a, void* stream);
 typedef struct {
   const float* q; const float* p; int32_t q_ld, p_ld;
   const float* eps;           /* NCHW eps used in forward, or NULL -> regenerate Philox(seed, offset) */
-  uint64_t seed; uint64_t offset;
+  uint64_t seed; uint64_t offset; const uint64_t* seed_dev;
   const void* dz; int32_t dz_ld;   /* bf16 gradient wrt z (npix, dz_ld) or NULL */
   float g_kl;                 /* d loss / d kl[n]  (= beta / (B * C*H*W)) */
   void* dq; int32_t dq_ld; void* dp; int32_t dp_ld;

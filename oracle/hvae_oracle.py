@@ -290,34 +290,44 @@ def gaussian_kl_ref_form(q_loc, q_ls, p_loc, p_ls):
     return -0.5 + p_ls - q_ls + 0.5 * (q_ls.exp().pow(2) + (q_loc - p_loc).pow(2)) / p_ls.exp().pow(2)
 
 
+# Optional emulation of the CUDA path's storage precision (activations and conv weights held in bf16,
+# fp32 accumulation, fp32 latent statistics).  Off by default: the oracle proper is fp32.  The GPU parity
+# tests use it to separate "implementation differs" from "bf16 storage differs".
+EMULATE_BF16 = False
+
+
+def _q(t: Tensor) -> Tensor:
+    return t.to(torch.bfloat16).to(t.dtype) if EMULATE_BF16 else t
+
+
 def _conv(sd, name, x, pad=0):
-    return F.conv2d(x, sd[name + ".weight"], sd[name + ".bias"], stride=1, padding=pad)
+    return F.conv2d(_q(x), _q(sd[name + ".weight"]), sd[name + ".bias"], stride=1, padding=pad)
 
 
 def run_block(sd, b: BlockSpec, x: Tensor) -> Tensor:  # src/vae.py:73-84
     pad = 0 if b.ksize == 1 else 1
     p = b.prefix + ".conv."
     if b.light:
-        y = _conv(sd, p + "1", F.relu(x), pad)
+        y = _q(_conv(sd, p + "1", F.relu(x), pad))
         y = _conv(sd, p + "3", F.relu(y), pad)
     else:
-        y = _conv(sd, p + "1", F.gelu(x))
-        y = _conv(sd, p + "3", F.gelu(y), pad)
-        y = _conv(sd, p + "5", F.gelu(y), pad)
+        y = _q(_conv(sd, p + "1", F.gelu(x)))
+        y = _q(_conv(sd, p + "3", F.gelu(y), pad))
+        y = _q(_conv(sd, p + "5", F.gelu(y), pad))
         y = _conv(sd, p + "7", F.gelu(y))
     if b.residual:
-        skip = _conv(sd, b.prefix + ".width_proj", x) if x.shape[1] != y.shape[1] else x
+        skip = _q(_conv(sd, b.prefix + ".width_proj", x)) if x.shape[1] != y.shape[1] else x
         y = skip + y
     if b.down:
-        y = F.avg_pool2d(y, b.down, b.down)
+        y = F.avg_pool2d(_q(y), b.down, b.down)
     return y
 
 
 def encoder(sd, cfg, arch: Arch, x: Tensor) -> Dict[int, Tensor]:  # src/vae.py:125-134
-    h = _conv(sd, "encoder.stem", x, 3)
+    h = _q(F.conv2d(x, sd["encoder.stem.weight"], sd["encoder.stem.bias"], padding=3))
     acts: Dict[int, Tensor] = {}
     for b in arch.enc:
-        h = run_block(sd, b, h)
+        h = _q(run_block(sd, b, h))
         r = h.shape[2]
         if r % 2 == 1 and r > 1:
             h = F.pad(h, [0, 1, 0, 1])
@@ -346,7 +356,7 @@ def decoder(sd, cfg, arch: Arch, parents: Tensor, noise: NoiseTape,
         if k.startswith("decoder.bias."):
             biases[sd[k].shape[2]] = sd[k]
     B = parents.shape[0]
-    h = z = biases[1].repeat(B, 1, 1, 1)
+    h = z = _q(biases[1].repeat(B, 1, 1, 1))
     stats: List[Dict] = []
     is_drop = "morphomnist" in cfg.hps  # src/vae.py:220
     log_t = math.log(t) if t is not None else None
@@ -361,15 +371,16 @@ def decoder(sd, cfg, arch: Arch, parents: Tensor, noise: NoiseTape,
             pa_sto = pa_det = pa
         if h.shape[-1] < d.res:
             up_bias = biases.get(d.res, 0)
-            h = up_bias + _nearest_up(h, d.res)
+            h = _q(up_bias + _nearest_up(h, d.res))
         if cfg.q_correction:
             p_in = h
         else:
-            p_in = up_bias + _nearest_up(z, d.res) if z.shape[-1] < d.res else z
+            p_in = _q(up_bias + _nearest_up(z, d.res)) if z.shape[-1] < d.res else z
         if cfg.cond_prior:
             p_in = torch.cat([p_in, pa_sto], 1)
         pr = run_block(sd, d.prior, p_in)
         p_loc, p_ls, p_feat = pr[:, :zd], pr[:, zd: 2 * zd], pr[:, 2 * zd:]
+        p_feat = _q(p_feat)
         if log_t is not None:
             p_ls = p_ls + log_t
         if d.stochastic:
@@ -397,10 +408,10 @@ def decoder(sd, cfg, arch: Arch, parents: Tensor, noise: NoiseTape,
         h = h + p_feat
         # quirk (pinned by golden elbo_drop1): the reference builds pa_det but feeds the
         # un-dropped pa to z_proj (src/vae.py:294), so p_det has no effect.
-        h = h + _conv(sd, f"decoder.blocks.{d.idx}.z_proj", torch.cat([z, pa], 1))
-        h = run_block(sd, d.conv, h)
+        h = _q(h + _conv(sd, f"decoder.blocks.{d.idx}.z_proj", torch.cat([z, pa], 1)))
+        h = _q(run_block(sd, d.conv, h))
         if not cfg.q_correction and d.idx + 1 < len(arch.dec):
-            z = _conv(sd, f"decoder.blocks.{d.idx}.z_feat_proj", torch.cat([z, p_feat], 1))
+            z = _q(_conv(sd, f"decoder.blocks.{d.idx}.z_feat_proj", torch.cat([z, p_feat], 1)))
     return h, stats
 
 

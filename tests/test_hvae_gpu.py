@@ -1,13 +1,21 @@
 """Model-level parity on a real B200: the CUDA path (through the HVAE surface -> C ABI) against the CPU
 oracle on the same seeded weights, inputs and eps.
 
-Stated tolerances (bf16 activations / fp32 accumulation vs an fp32 oracle; the reference's own
-fp32 <-> bf16-autocast drift is 1e-4..3.3e-3 on these scalars):
-    elbo / nll / kl          rel 1e-2
-    per-block KL sums        rel 3e-2 of the block scale (+ 2e-3 * total)
-    gradients                per-parameter-tensor rel-L2 <= 8e-2 for tensors carrying signal, global rel-L2 <= 3e-2
-    abducted z               rel-L2 <= 2e-2
-    rec / cf pixels          abs <= 2/255 on >= 99.5% of pixels, max <= 8/255
+The CUDA path stores activations in bf16 (fp32 accumulation, fp32 latent statistics / KL / likelihood);
+the oracle -- like the reference -- is fp32.  With the all-paths-active seeded weights used here the
+40-block residual stream amplifies any 2^-9 storage perturbation to ~1e-2 on pixels, so each case also
+runs the oracle with the same bf16 storage points emulated (``hvae_oracle.EMULATE_BF16``) and states the
+tolerance against that measured, inherent drift:
+
+    elbo / nll / kl        rel <= 5e-3 vs the fp32 oracle
+    per-block KL sums      |d| <= 3e-2*|ref| + 2e-3*sum|ref| per block, rel-L2 over blocks <= 5e-3
+    gradients              global rel-L2 <= max(1.5e-2, 2 * drift); per tensor (norm > 1% of the largest)
+                           rel-L2 <= max(5e-2, 2 * drift_tensor + 2e-2)   (activation gradients are also
+                           stored in bf16, which the forward-only emulation does not include)
+    abducted z             rel-L2 <= max(5e-3, 2 * drift)
+    rec / cf / sampled px  mean |d| <= max(1/255, 1.5 * drift_mean), p99 |d| <= max(2/255, 1.5 * drift_p99)
+
+where drift = the same statistic of (bf16-storage oracle - fp32 oracle).
 """
 import numpy as np
 import pytest
@@ -45,42 +53,88 @@ def rel_l2(a, b):
     return float((a - b).norm() / (b.norm() + 1e-12))
 
 
+def oracle_elbo(cfg, sd, x, pa_full, emulate):
+    O.EMULATE_BF16 = emulate
+    try:
+        sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        tape = O.NoiseTape(seed=101)
+        out = O.hvae_forward(sdr, cfg, x, pa_full, tape, beta=cfg.beta, detail=True)
+        out["elbo"].backward()
+    finally:
+        O.EMULATE_BF16 = False
+    return out, sdr, tape
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_elbo_kl_and_gradients(name):
     cfg, sd, model, x, pa, _ = build(name)
     pa_full = O.expand_parents(pa, cfg.input_res)
-    for p in sd.values():
-        p.requires_grad_(True)
-    tape = O.NoiseTape(seed=101)
-    ref = O.hvae_forward(sd, cfg, x, pa_full, tape, beta=cfg.beta, detail=True)
-    ref["elbo"].backward()
+    ref, sd32, tape = oracle_elbo(cfg, sd, x, pa_full, False)
+    emu, sd16, _ = oracle_elbo(cfg, sd, x, pa_full, True)
     eps = [e.to(DEV) for e in tape.drawn]
     model.zero_grad()
     out = model(x.to(DEV), pa_full.to(DEV), beta=cfg.beta, eps=eps)
     out["elbo"].backward()
     torch.cuda.synchronize()
     for k in ("elbo", "nll", "kl"):
-        np.testing.assert_allclose(out[k].item(), ref[k].item(), rtol=1e-2, err_msg=f"{name} {k}")
+        np.testing.assert_allclose(out[k].item(), ref[k].item(), rtol=5e-3, err_msg=f"{name} {k}")
     bk, rk = model.block_kl().cpu(), ref["block_kl"].detach()
-    tol = 3e-2 * rk.abs() + 2e-3 * rk.sum(1, keepdim=True).abs() + 1e-3
+    tol = 3e-2 * rk.abs() + 2e-3 * rk.abs().sum(1, keepdim=True) + 1e-3
     assert bool(((bk - rk).abs() <= tol).all()), f"{name} block KL: {(bk - rk).abs().max()} vs {rk.abs().max()}"
-    # gradients
-    num = den = 0.0
-    worst = (0.0, "")
+    assert rel_l2(bk, rk) <= 5e-3, f"{name} block KL rel-L2 {rel_l2(bk, rk):.4g}"
+    # gradients vs fp32, bounded by the measured bf16-storage drift of the algorithm itself
     named = dict(model.named_parameters())
-    gmax = max(float(p.grad.norm()) for p in sd.values() if p.grad is not None)
-    for k, p in sd.items():
+    num = den = dnum = 0.0
+    gmax = max(float(p.grad.norm()) for p in sd32.values() if p.grad is not None)
+    bad = []
+    for k, p in sd32.items():
         if p.grad is None:
             continue
-        g = named[k].grad.cpu()
+        g, g16 = named[k].grad.cpu(), sd16[k].grad
         num += float((g - p.grad).pow(2).sum())
+        dnum += float((g16 - p.grad).pow(2).sum())
         den += float(p.grad.pow(2).sum())
         if float(p.grad.norm()) > 1e-2 * gmax:
-            r = rel_l2(g, p.grad)
-            if r > worst[0]:
-                worst = (r, k)
-    assert (num / den) ** 0.5 <= 3e-2, f"{name} global grad rel-L2 {(num / den) ** 0.5:.4f}"
-    assert worst[0] <= 8e-2, f"{name} worst param grad rel-L2 {worst}"
+            r, drift = rel_l2(g, p.grad), rel_l2(g16, p.grad)
+            if r > max(5e-2, 2 * drift + 2e-2):
+                bad.append((k, round(r, 4), round(drift, 4)))
+    glob, gdrift = (num / den) ** 0.5, (dnum / den) ** 0.5
+    assert glob <= max(1.5e-2, 2 * gdrift), f"{name} global grad rel-L2 {glob:.4f} (drift {gdrift:.4f})"
+    assert not bad, f"{name} per-tensor grad outliers (name, rel, drift): {bad[:8]}"
+
+
+def px_stats(a, b):
+    d = (a - b).abs().flatten()
+    return float(d.mean()), float(torch.quantile(d[:: max(1, d.numel() // 200000)], 0.99))
+
+
+def assert_pixels(ours, ref, emu, what):
+    m, p99 = px_stats(ours, ref)
+    dm, dp99 = px_stats(emu, ref)
+    assert m <= max(1 / 255, 1.5 * dm), f"{what}: mean |d| {m:.5f} vs bf16 drift {dm:.5f}"
+    assert p99 <= max(2 / 255, 1.5 * dp99), f"{what}: p99 |d| {p99:.5f} vs bf16 drift {dp99:.5f}"
+
+
+def oracle_cf(cfg, sd, x, pa_full, cf_full, emulate):
+    O.EMULATE_BF16 = emulate
+    try:
+        with torch.no_grad():
+            r = {}
+            r["tape"] = O.NoiseTape(seed=202)
+            zs = O.hvae_abduct(sd, cfg, x, pa_full, r["tape"], t=0.9)
+            r["zs"] = [z["z"] for z in zs] if cfg.cond_prior else zs
+            cf_loc, cf_scale = O.hvae_forward_latents(sd, cfg, r["zs"], cf_full)
+            r["rec_loc"], r["rec_scale"] = O.hvae_forward_latents(sd, cfg, r["zs"], pa_full)
+            u = (x - r["rec_loc"]) / r["rec_scale"].clamp(min=1e-12)
+            r["cf"] = torch.clamp(cf_loc + cf_scale * u, -1, 1)
+            r["tape2"] = O.NoiseTape(seed=303)
+            half = r["zs"][: len(r["zs"]) // 2]
+            r["partial"], _ = O.hvae_forward_latents(sd, cfg, half, pa_full, r["tape2"], t=0.7)
+            r["tape3"] = O.NoiseTape(seed=505)
+            r["sample"], r["sample_scale"] = O.hvae_sample(sd, cfg, pa_full, r["tape3"], t=0.5)
+    finally:
+        O.EMULATE_BF16 = False
+    return r
 
 
 @pytest.mark.parametrize("name", list(CASES))
@@ -89,46 +143,45 @@ def test_abduct_forward_latents_counterfactual(name):
     cfg, sd, model, x, pa, cf = build(name)
     R = cfg.input_res
     pa_full, cf_full = O.expand_parents(pa, R), O.expand_parents(cf, R)
-    with torch.no_grad():
-        tape = O.NoiseTape(seed=202)
-        zs_ref = O.hvae_abduct(sd, cfg, x, pa_full, tape, t=0.9)
-        zs_ref = [z["z"] for z in zs_ref] if cfg.cond_prior else zs_ref
-        cf_loc, cf_scale = O.hvae_forward_latents(sd, cfg, zs_ref, cf_full)
-        rec_loc, rec_scale = O.hvae_forward_latents(sd, cfg, zs_ref, pa_full)
-        u = (x - rec_loc) / rec_scale.clamp(min=1e-12)
-        cf_ref = torch.clamp(cf_loc + cf_scale * u, -1, 1)
-    eps = [e.to(DEV) for e in tape.drawn]
+    ref = oracle_cf(cfg, sd, x, pa_full, cf_full, False)
+    emu = oracle_cf(cfg, sd, x, pa_full, cf_full, True)
+    eps = [e.to(DEV) for e in ref["tape"].drawn]
     xd, pad, cfd = x.to(DEV), pa.to(DEV), cf_full.to(DEV)  # (B,ctx) and (B,ctx,R,R) forms both accepted
     zs = model.abduct(xd, pad, t=0.9, eps=eps)
     zs = [z["z"] for z in zs] if cfg.cond_prior else zs
-    assert len(zs) == len(zs_ref)
-    for i, (a, b) in enumerate(zip(zs, zs_ref)):
+    assert len(zs) == len(ref["zs"])
+    for i, (a, b, e) in enumerate(zip(zs, ref["zs"], emu["zs"])):
         assert a.shape == b.shape
-        assert rel_l2(a.cpu(), b) <= 2e-2, f"{name} z[{i}] rel-L2 {rel_l2(a.cpu(), b):.4f}"
+        assert rel_l2(a.cpu(), b) <= max(5e-3, 2 * rel_l2(e, b)), f"{name} z[{i}] rel-L2 {rel_l2(a.cpu(), b):.4f}"
     loc, scale = model.forward_latents(zs, pad)
-    d = (loc.cpu() - rec_loc).abs()
-    assert float((d <= 2 / 255).float().mean()) >= 0.995 and float(d.max()) <= 8 / 255, (name, float(d.max()))
-    assert rel_l2(scale.cpu(), rec_scale) <= 3e-2
+    assert_pixels(loc.cpu(), ref["rec_loc"], emu["rec_loc"], f"{name} rec loc")
+    assert rel_l2(scale.cpu(), ref["rec_scale"]) <= max(5e-3, 2 * rel_l2(emu["rec_scale"], ref["rec_scale"]))
     cf_x, var = counterfactual(model, xd, pad, cfd, t_abduct=0.9, eps=[eps])
     assert var is None
-    d = (cf_x.cpu() - cf_ref).abs()
-    # u = (x-loc)/scale amplifies loc error by cf_scale/rec_scale ~ 1: same pixel tolerance, looser tail
-    assert float((d <= 2 / 255).float().mean()) >= 0.99 and float(d.max()) <= 16 / 255, (name, float(d.max()), float((d <= 2 / 255).float().mean()))
+    assert_pixels(cf_x.cpu(), ref["cf"], emu["cf"], f"{name} cf_x")
     # partially given latents + temperature: the rest is sampled from the prior with the given eps
-    half = zs_ref[: len(zs_ref) // 2]
-    with torch.no_grad():
-        tape2 = O.NoiseTape(seed=303)
-        pl_ref, _ = O.hvae_forward_latents(sd, cfg, half, pa_full, tape2, t=0.7)
-    pl, _ = model.forward_latents([z.to(DEV) for z in half], pad, t=0.7, eps=[e.to(DEV) for e in tape2.drawn])
-    d = (pl.cpu() - pl_ref).abs()
-    assert float((d <= 2 / 255).float().mean()) >= 0.99, (name, float(d.max()))
+    half = ref["zs"][: len(ref["zs"]) // 2]
+    pl, _ = model.forward_latents([z.to(DEV) for z in half], pad, t=0.7, eps=[e.to(DEV) for e in ref["tape2"].drawn])
+    assert_pixels(pl.cpu(), ref["partial"], emu["partial"], f"{name} partial latents")
     # unconditional sample
+    sx, ss = model.sample(pad, t=0.5, eps=[e.to(DEV) for e in ref["tape3"].drawn])
+    assert_pixels(sx.cpu(), ref["sample"], emu["sample"], f"{name} sample")
+    assert rel_l2(ss.cpu(), ref["sample_scale"]) <= max(5e-3, 2 * rel_l2(emu["sample_scale"], ref["sample_scale"]))
+
+
+def test_counterfactual_particles():
+    from causalgen_b200 import counterfactual
+    cfg, sd, model, x, pa, cf = build("tiny_ukbb")
+    R = cfg.input_res
+    pa_full, cf_full = O.expand_parents(pa, R), O.expand_parents(cf, R)
     with torch.no_grad():
-        tape3 = O.NoiseTape(seed=505)
-        sx_ref, ss_ref = O.hvae_sample(sd, cfg, pa_full, tape3, t=0.5)
-    sx, ss = model.sample(pad, t=0.5, eps=[e.to(DEV) for e in tape3.drawn])
-    d = (sx.cpu() - sx_ref).abs()
-    assert float((d <= 2 / 255).float().mean()) >= 0.99, (name, float(d.max()))
+        tape = O.NoiseTape(seed=77)
+        mref, vref = O.counterfactual(sd, cfg, x, pa_full, cf_full, tape, t_abduct=1.0, particles=3)
+    n = len(tape.drawn) // 3
+    eps = [[e.to(DEV) for e in tape.drawn[i * n:(i + 1) * n]] for i in range(3)]
+    m, v = counterfactual(model, x.to(DEV), pa.to(DEV), cf.to(DEV), t_abduct=1.0, particles=3, eps=eps)
+    assert float((m.cpu() - mref).abs().mean()) <= 2 / 255
+    assert float((v.cpu() - vref).abs().mean()) <= 1e-3 + 0.1 * float(vref.abs().mean())
 
 
 def test_mediator_mixture_abduction():
@@ -141,7 +194,7 @@ def test_mediator_mixture_abduction():
     out = model.abduct(x.to(DEV), pa.to(DEV), cf_parents=cf.to(DEV), alpha=0.65, t=0.8,
                        eps=[e.to(DEV) for e in tape.drawn])
     for i, (a, b) in enumerate(zip(out, ref)):
-        assert rel_l2(a.cpu(), b) <= 3e-2, f"cf z[{i}] rel-L2 {rel_l2(a.cpu(), b):.4f}"
+        assert rel_l2(a.cpu(), b) <= 1e-2, f"cf z[{i}] rel-L2 {rel_l2(a.cpu(), b):.4f}"
 
 
 def test_dmol_likelihood_swap():
@@ -162,16 +215,20 @@ def test_dmol_likelihood_swap():
     out = model(x.to(DEV), pa.to(DEV), beta=1.0, eps=[e.to(DEV) for e in tape.drawn])
     out["elbo"].backward()
     for k in ("elbo", "nll", "kl"):
-        np.testing.assert_allclose(out[k].item(), ref[k].item(), rtol=1e-2, err_msg=k)
+        np.testing.assert_allclose(out[k].item(), ref[k].item(), rtol=5e-3, err_msg=k)
     g = dict(model.named_parameters())["likelihood.conv.weight"].grad.cpu()
     assert rel_l2(g, sd["likelihood.conv.weight"].grad) <= 5e-2
     with torch.no_grad():
         tape = O.NoiseTape(seed=202)
         zs = O.hvae_abduct(sd, cfg, x, pa_full, tape)
         loc_ref, scale_ref = O.hvae_forward_latents(sd, cfg, zs, pa_full)
+        O.EMULATE_BF16 = True
+        try:
+            loc_emu, _ = O.hvae_forward_latents(sd, cfg, zs, pa_full)
+        finally:
+            O.EMULATE_BF16 = False
     loc, scale = model.forward_latents([z.to(DEV) for z in zs], pa.to(DEV))
-    d = (loc.cpu() - loc_ref).abs()
-    assert float((d <= 2 / 255).float().mean()) >= 0.99, float(d.max())
+    assert_pixels(loc.cpu(), loc_ref, loc_emu, "dmol rec loc")
 
 
 def test_conditioning_dropout_and_philox_noise():
@@ -188,7 +245,7 @@ def test_conditioning_dropout_and_philox_noise():
         model.drop_cond = lambda d=d: d
         with torch.no_grad():
             got = model(x.to(DEV), pa.to(DEV), beta=1.0, eps=eps)["elbo"].item()
-        np.testing.assert_allclose(got, want, rtol=1e-2, err_msg=str(d))
+        np.testing.assert_allclose(got, want, rtol=5e-3, err_msg=str(d))
     # in-kernel Philox noise: finite, differs call to call, statistically close to the explicit-eps value
     model.eval()
     with torch.no_grad():
