@@ -11,9 +11,12 @@
 //               between images) so a 16x8-pixel tile has a constant row pitch for any H.
 //   B operand   packed weights for the CTA's Cout chunk, bulk-copied (cp.async.bulk) into shared
 //               memory once and kept resident while the persistent CTA walks its pixel tiles.
-//   D           fp32 in TMEM, double buffered (2 x Nc columns) so the epilogue of tile i overlaps the
-//               MMAs of tile i+1.  Epilogue: bias, channel-split segments, act'(x) multiply (backward),
-//               residual / accumulate add, bf16 or fp32 stores.
+//   D           fp32 in TMEM, double buffered (2 x Nc columns, Nc <= 64; wider outputs are split over
+//               blockIdx.y) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   epilogue    bias, channel-split segments, act'(x) multiply (backward), residual / accumulate adds,
+//               bf16 or fp32 stores.  The tensors the epilogue READS (residual, pre-activation) are staged by
+//               the loader warps with the same cp.async pipeline ("E stages"), two tiles ahead, so the
+//               epilogue never waits on a global load.
 //
 // Warp roles: 0-3 epilogue (TMEM lane quarters), 4 MMA issuer + TMEM owner, 5-12 loaders.
 #include "cg_common.cuh"
@@ -30,17 +33,31 @@ constexpr int kStages = 4;
 constexpr int kPlane3 = 2976;  // 18*10*16 = 2880, padded so the 4 planes of a stage hit distinct banks
 constexpr int kPlane1 = 2080;  // 128*16   = 2048, same padding rule
 constexpr int kStageBytes = 4 * kPlane3;
-constexpr int kHdrBytes = 1280;  // barriers (<=128B) | tmem slot | bias[256]
+constexpr int kHdrBytes = 1280;  // barriers (<=160B) | tmem slot | bias[256]
 constexpr int kSmemMax = 232448;  // 227 KB
 constexpr int kMaxChunks = 40;
+constexpr int kMaxNc = 64;        // GEMM-N per CTA
+constexpr int kEStages = 3;       // epilogue-operand ring depth (> loader queue lag of 2 tiles: no deadlock)
+constexpr int kESlots = 2;        // staged operands per tile
+// a staged operand tile is [128 pixel rows][Nc channels] bf16 with a 16-byte row pad (bank spread)
+__host__ __device__ constexpr int e_pitch(int nc) { return nc * 2 + 16; }
+__host__ __device__ constexpr int e_slot_bytes(int nc) { return 128 * e_pitch(nc); }
+__host__ __device__ constexpr int e_bytes(int nc) { return kEStages * kESlots * e_slot_bytes(nc); }
 
 struct Chunk {
   uint16_t src, c0, nc16, kbase;
 };
 
+struct EOp {           // one epilogue input staged through shared memory
+  const void* ptr;     // bf16 tensor
+  int ld, seg, kind;   // kind: 0 add, 1 add2, 2 mul
+};
+
 struct KParams {
   cg_conv_args a;
   Chunk chunk[kMaxChunks];
+  EOp eop[kESlots];
+  int nE, emode;
   int nchunks, ntaps, Nc, nN, ktot16;
   int tiles_x, ntiles, Hp, V;
   long long P;  // N*H*W
@@ -66,29 +83,17 @@ __device__ __forceinline__ TileGeom tile_geom(const KParams& P, int tile) {
   return g;
 }
 
-__device__ __forceinline__ uint4 load_act8(const KParams& P, const cg_src& s, long long elem_off, bool valid) {
-  uint4 u = make_uint4(0, 0, 0, 0);
-  if (valid) {
-    u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(s.ptr) + elem_off));
-    if (P.a.act != CG_ACT_NONE) {
-      float f[8];
-      cg_unpack8(u, f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = cg_act(f[i], P.a.act);
-      u = cg_pack8(f);
-    }
-  }
-  return u;
-}
-
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  // barrier map: [0..3] a_full, [4..7] a_empty, [8] b_full, [9,10] acc_full, [11,12] acc_empty
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 128);
+  // barrier map: [0..3] a_full, [4..7] a_empty, [8] b_full, [9,10] acc_full, [11,12] acc_empty,
+  //              [13..15] e_full, [16..18] e_empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 192);
   float* s_bias = reinterpret_cast<float*>(smem + 256);
   uint8_t* sA = smem + kHdrBytes;
-  uint8_t* sB = sA + kStages * kStageBytes;
+  uint8_t* sE = sA + kStages * kStageBytes;
+  uint8_t* sB = sE + (P.emode ? e_bytes(P.Nc) : 0);
+  const int epitch = e_pitch(P.Nc), eslot = e_slot_bytes(P.Nc);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunkN = blockIdx.y;
@@ -106,6 +111,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     mbar_init(BAR(10), 1);
     mbar_init(BAR(11), kEpiWarps);
     mbar_init(BAR(12), kEpiWarps);
+    for (int i = 0; i < kEStages; ++i) {
+      mbar_init(BAR(13 + i), kLoadWarps);
+      mbar_init(BAR(16 + i), kEpiWarps);
+    }
     mbar_fence_init();
   }
   if (warp == kMmaWarp) tmem_alloc(cg_smem_u32(tmem_slot), P.tmem_cols);
@@ -130,9 +139,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         bulk_g2s(cg_smem_u32(sB) + off, wsrc + off, n, BAR(8));
       }
       mbar_wait(BAR(8), 0);
-      const uint32_t sB_addr = cg_smem_u32(sB);
-      const uint32_t b_lbo = (uint32_t)Nc * 16u, b_step = (uint32_t)Nc * 32u;
+      // Descriptors are built once; per MMA only the 14-bit start-address fields advance (all offsets are
+      // multiples of 16 B), so the single issuing thread spends ~4 instructions per tcgen05.mma.
       const uint32_t a_sbo = k3 ? 160u : 128u;
+      const uint64_t a_desc0 = umma_desc(cg_smem_u32(sA), (uint32_t)plane, a_sbo);
+      const uint64_t b_desc0 = umma_desc(cg_smem_u32(sB), (uint32_t)Nc * 16u, 128u);
+      const uint32_t b_step16 = (uint32_t)Nc * 2u;        // (Nc*32 B per K-block) >> 4
+      const uint32_t plane2_16 = (uint32_t)(2 * plane) >> 4;
+      const uint32_t stage16 = (uint32_t)kStageBytes >> 4;
+      const uint32_t idesc = P.idesc;
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
         mbar_wait(BAR(11 + as), aphase ^ 1u);
@@ -143,15 +158,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const Chunk ch = P.chunk[c];
           mbar_wait(BAR(stage), phase);
           tc_fence_after();
-          const uint32_t a_base = cg_smem_u32(sA) + stage * kStageBytes;
+          uint64_t ad = a_desc0 + stage * stage16;
+          uint64_t bd = b_desc0 + (uint32_t)ch.kbase * b_step16;
           for (int j = 0; j < ch.nc16; ++j) {
-            for (int t = 0; t < P.ntaps; ++t) {
-              uint32_t toff = k3 ? (uint32_t)((t / 3) * 10 + (t % 3)) * 16u : 0u;
-              uint64_t ad = umma_desc(a_base + (uint32_t)(2 * j) * plane + toff, (uint32_t)plane, a_sbo);
-              uint64_t bd = umma_desc(sB_addr + (uint32_t)(ch.kbase + j * P.ntaps + t) * b_step, b_lbo, 128u);
-              tc_mma_bf16(d_tmem, ad, bd, P.idesc, accum);
+            if (k3) {
+#pragma unroll
+              for (int t = 0; t < 9; ++t) {
+                tc_mma_bf16(d_tmem, ad + (uint32_t)((t / 3) * 10 + (t % 3)), bd, idesc, accum);
+                accum = 1;
+                bd += b_step16;
+              }
+            } else {
+              tc_mma_bf16(d_tmem, ad, bd, idesc, accum);
               accum = 1;
+              bd += b_step16;
             }
+            ad += plane2_16;
           }
           tc_commit(BAR(4 + stage));  // frees the A stage once these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -162,50 +184,150 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
   } else if (warp >= kLoadWarp0) {
     // ------------------------------------------------------------------ A-tile loaders
+    // Each thread owns up to 3 fixed (pixel, channel-octet) slots of a stage.  Copies are cp.async
+    // (LDGSTS, zero-fill for padding) issued up to kStages-1 stages ahead, so global latency overlaps
+    // across stages instead of serialising per stage; the activation is applied in place afterwards by
+    // the thread that issued the copy (no cross-thread hazard), then the stage is published to the MMA.
     const int lt = threadIdx.x - kLoadWarp0 * 32;
-    uint32_t stage = 0, phase = 0;
     const int H = P.a.H, W = P.a.W, N = P.a.N;
+    const int npix = k3 ? 180 : 128;
+    const int c8 = lt & 3;
+    int pixj[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) pixj[j] = (lt + j * kLoadThreads) >> 2;
+    constexpr int D = kStages - 1;
+    uint32_t q_stage[kStages];
+    int q_nc8[kStages];
+    int q_es[kStages];  // E stage published together with this A stage, or -1
+    int q_head = 0, q_len = 0;
+    uint32_t stage = 0, phase = 0;
+    uint32_t es = 0, ephase = 0;
+    const int nE = P.nE;
+    const int ncE8 = Nc >> 3;  // channel octets per staged operand row
+    const int act = P.a.act;
+    auto finalize = [&](uint32_t st, int nc8, int e_st) {
+      if (act != CG_ACT_NONE && c8 < nc8) {
+        uint8_t* dst = sA + st * kStageBytes + c8 * plane;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          if (pixj[j] < npix) {
+            uint4* p = reinterpret_cast<uint4*>(dst + pixj[j] * 16);
+            float f[8];
+            cg_unpack8(*p, f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = cg_act(f[i], act);
+            *p = cg_pack8(f);
+          }
+        }
+      }
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(BAR(st));
+        if (e_st >= 0) mbar_arrive(BAR(13 + e_st));
+      }
+    };
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
       const TileGeom g = tile_geom(P, tile);
+      bool valid[3];
+      long long poff[3];
+      int nidx[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int pix = pixj[j];
+        if (k3) {
+          const int rr = pix / 10, cc = pix - rr * 10;
+          const int v = g.v0 - 1 + rr, w = g.w0 - 1 + cc;
+          const int n = v / P.Hp, h = v - n * P.Hp;
+          valid[j] = (pix < npix) && (v >= 0) && (w >= 0) && (w < W) && (n < N) && (h < H);
+          poff[j] = (long long)(n * H + h) * W + w;
+          nidx[j] = n;
+        } else {
+          const long long p = g.p0 + pix;
+          valid[j] = (pix < npix) && (p < P.P);
+          poff[j] = p;
+          nidx[j] = (int)(p / ((long long)H * W));
+        }
+      }
+      int e_now = -1;
+      if (nE > 0) {
+        // stage the tensors this tile's epilogue will read (residual / pre-activation rows of the
+        // 128 output pixels x Nc channels) into E stage `es`
+        mbar_wait(BAR(16 + es), ephase ^ 1u);
+        const int items = 128 * ncE8;
+        for (int k = 0; k < nE; ++k) {
+          const EOp& op = P.eop[k];
+          const cg_seg& sg = P.a.seg[op.seg];
+          const uint32_t dstE = cg_smem_u32(sE + (es * kESlots + k) * eslot);
+          for (int it = lt; it < items; it += kLoadThreads) {
+            const int row = it / ncE8, oc = it - row * ncE8;
+            const int lc = nchunkN * Nc + oc * 8 - sg.c0;  // channel inside the segment
+            bool ok;
+            long long px;
+            if (k3) {
+              const int v = g.v0 + (row >> 3), w = g.w0 + (row & 7);
+              const int n = v / P.Hp, h = v - n * P.Hp;
+              ok = (n < N) && (h < H) && (w < W);
+              px = (long long)(n * H + h) * W + w;
+            } else {
+              px = g.p0 + row;
+              ok = px < P.P;
+            }
+            if (ok && lc >= 0 && lc < sg.cn)
+              cp_async16(dstE + row * epitch + oc * 16, reinterpret_cast<const bf16*>(op.ptr) + px * op.ld + lc, 16u);
+          }
+        }
+        e_now = (int)es;
+        if (++es == kEStages) { es = 0; ephase ^= 1u; }
+      }
       for (int c = 0; c < P.nchunks; ++c) {
         const Chunk ch = P.chunk[c];
         const cg_src& s = P.a.src[ch.src];
         const int nc8 = ch.nc16 * 2;
-        const int sh = (nc8 == 4) ? 2 : 1;
         mbar_wait(BAR(4 + stage), phase ^ 1u);
-        uint8_t* dst = sA + stage * kStageBytes;
-        const int npix = k3 ? 180 : 128;
-        const int items = npix << sh;
-        for (int it = lt; it < items; it += kLoadThreads) {
-          const int c8 = it & (nc8 - 1);
-          const int pix = it >> sh;
-          bool valid;
-          long long off;
-          if (k3) {
-            const int rr = pix / 10, cc = pix - rr * 10;
-            const int v = g.v0 - 1 + rr, w = g.w0 - 1 + cc;
-            const int n = v / P.Hp, h = v - n * P.Hp;
-            valid = (v >= 0) && (w >= 0) && (w < W) && (n < N) && (h < H);
-            off = s.bcast ? (long long)n * s.ld : ((long long)(n * H + h) * W + w) * s.ld;
-          } else {
-            const long long p = g.p0 + pix;
-            valid = p < P.P;
-            off = s.bcast ? (p / ((long long)H * W)) * s.ld : p * s.ld;
+        if (c8 < nc8) {
+          const uint32_t dst = cg_smem_u32(sA + stage * kStageBytes + c8 * plane);
+          const bf16* base = reinterpret_cast<const bf16*>(s.ptr) + ch.c0 + c8 * 8;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            if (pixj[j] < npix) {
+              const bf16* src = valid[j] ? base + (s.bcast ? (long long)nidx[j] : poff[j]) * s.ld : base;
+              cp_async16(dst + pixj[j] * 16, src, valid[j] ? 16u : 0u);
+            }
           }
-          uint4 u = load_act8(P, s, off + ch.c0 + c8 * 8, valid);
-          *reinterpret_cast<uint4*>(dst + c8 * plane + pix * 16) = u;
         }
-        fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(stage));
+        cp_async_commit();
+        q_stage[(q_head + q_len) % kStages] = stage;
+        q_nc8[(q_head + q_len) % kStages] = nc8;
+        q_es[(q_head + q_len) % kStages] = (c == 0) ? e_now : -1;
+        ++q_len;
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        if (q_len == D) {
+          cp_async_wait<D - 1>();
+          finalize(q_stage[q_head], q_nc8[q_head], q_es[q_head]);
+          q_head = (q_head + 1) % kStages;
+          --q_len;
+        }
       }
+    }
+    cp_async_wait<0>();
+    while (q_len > 0) {
+      finalize(q_stage[q_head], q_nc8[q_head], q_es[q_head]);
+      q_head = (q_head + 1) % kStages;
+      --q_len;
     }
   } else {
     // ------------------------------------------------------------------ epilogue
-    uint32_t as = 0, aphase = 0;
+    uint32_t as = 0, aphase = 0, es = 0, ephase = 0;
     const int m = warp * 32 + lane;
     const int H = P.a.H, W = P.a.W, N = P.a.N;
+    const int nE = P.nE;
+    // staged-operand slot of (segment, kind) or -1 -> direct global load
+    auto slot_of = [&](int sgi, int kind) {
+      for (int k = 0; k < nE; ++k)
+        if (P.eop[k].seg == sgi && P.eop[k].kind == kind) return k;
+      return -1;
+    };
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
       const TileGeom g = tile_geom(P, tile);
       bool valid;
@@ -219,8 +341,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         pix = g.p0 + m;
         valid = pix < P.P;
       }
+      if (nE > 0) mbar_wait(BAR(13 + es), ephase);
       mbar_wait(BAR(9 + as), aphase);
       tc_fence_after();
+      const uint8_t* e_row = sE + (size_t)(es * kESlots) * eslot + (size_t)m * epitch;
       const uint32_t t_row = tmem_base + as * (uint32_t)Nc + ((uint32_t)(warp * 32) << 16);
       for (int col = 0; col < Nc; col += 16) {
         float acc[16];
@@ -239,29 +363,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = acc[i];
+          // operand fetch: staged tile row (shared memory) if the loaders brought it, else global
+          auto fetch = [&](int kind, const void* gptr, int gld, int h8) -> uint4 {
+            const int k = slot_of(sgi, kind);
+            if (k >= 0) return *reinterpret_cast<const uint4*>(e_row + (size_t)k * eslot + (col + h8) * 2);
+            return *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(gptr) + pix * gld + lc + h8);
+          };
           if (sg.mul != nullptr) {
-            const bf16* mp = reinterpret_cast<const bf16*>(sg.mul) + pix * sg.mul_ld + lc;
             for (int h8 = 0; h8 < cnt; h8 += 8) {
               float x[8];
-              cg_unpack8(__ldg(reinterpret_cast<const uint4*>(mp + h8)), x);
+              cg_unpack8(fetch(2, sg.mul, sg.mul_ld, h8), x);
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[h8 + i] *= cg_dact(x[i], sg.mul_act);
             }
           }
           if (sg.add != nullptr) {
-            const bf16* ap = reinterpret_cast<const bf16*>(sg.add) + pix * sg.add_ld + lc;
             for (int h8 = 0; h8 < cnt; h8 += 8) {
               float x[8];
-              cg_unpack8(*reinterpret_cast<const uint4*>(ap + h8), x);
+              cg_unpack8(fetch(0, sg.add, sg.add_ld, h8), x);
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[h8 + i] += x[i];
             }
           }
           if (sg.add2 != nullptr) {
-            const bf16* ap = reinterpret_cast<const bf16*>(sg.add2) + pix * sg.add2_ld + lc;
             for (int h8 = 0; h8 < cnt; h8 += 8) {
               float x[8];
-              cg_unpack8(*reinterpret_cast<const uint4*>(ap + h8), x);
+              cg_unpack8(fetch(1, sg.add2, sg.add2_ld, h8), x);
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[h8 + i] += x[i];
             }
@@ -278,8 +405,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(11 + as));
+      if (lane == 0) {
+        mbar_arrive(BAR(11 + as));
+        if (nE > 0) mbar_arrive(BAR(16 + es));
+      }
       if (++as == 2) { as = 0; aphase ^= 1u; }
+      if (nE > 0 && ++es == kEStages) { es = 0; ephase ^= 1u; }
     }
   }
   tc_fence_before();
@@ -290,22 +421,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   }
 }
 
-int pick_nc(int ktot16, int cout) {
-  const int budget = kSmemMax - kHdrBytes - kStages * kStageBytes;
-  int nc_max = (budget / (ktot16 * 32)) / 16 * 16;
-  if (nc_max > 256) nc_max = 256;
-  if (nc_max < 16) return 0;
-  int nN = (cout + nc_max - 1) / nc_max;
-  int nc = ((cout + nN - 1) / nN + 15) / 16 * 16;
-  return nc;
+// GEMM-N per CTA (<= 64, multiple of 16) such that the resident weight slab fits.  Prefer a size that also
+// leaves room for the epilogue-operand ring (*emode = 1); huge-K layers fall back to no ring.
+int pick_nc(int ktot16, int cout, int* emode) {
+  const int base = kSmemMax - kHdrBytes - kStages * kStageBytes;
+  for (int mode = 1; mode >= 0; --mode) {
+    for (int nc_max = kMaxNc; nc_max >= 16; nc_max -= 16) {
+      if (ktot16 * nc_max * 32 + (mode ? e_bytes(nc_max) : 0) > base) continue;
+      const int nN = (cout + nc_max - 1) / nc_max;
+      if (emode) *emode = mode;
+      return ((cout + nN - 1) / nN + 15) / 16 * 16;
+    }
+  }
+  return 0;
 }
 
 }  // namespace
 
-extern "C" int32_t cg_conv_nchunk(int32_t ktot16, int32_t cout) { return pick_nc(ktot16, cout); }
+extern "C" int32_t cg_conv_nchunk(int32_t ktot16, int32_t cout) { return pick_nc(ktot16, cout, nullptr); }
 
 extern "C" int64_t cg_packed_weight_bytes(int32_t ktot16, int32_t cout) {
-  int nc = pick_nc(ktot16, cout);
+  int nc = pick_nc(ktot16, cout, nullptr);
   if (nc <= 0) return -1;
   int nN = (cout + nc - 1) / nc;
   return (int64_t)nN * ktot16 * nc * 32;
@@ -338,7 +474,7 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
   }
   kp.nchunks = nchunks;
   kp.ktot16 = c16 * kp.ntaps;
-  kp.Nc = pick_nc(kp.ktot16, a->cout);
+  kp.Nc = pick_nc(kp.ktot16, a->cout, &kp.emode);
   CG_REQUIRE(kp.Nc >= 16, "cg_conv2d: K=%d too large for a resident weight slab", kp.ktot16 * 16);
   kp.nN = (a->cout + kp.Nc - 1) / kp.Nc;
   kp.slab_bytes = (uint32_t)kp.ktot16 * kp.Nc * 32u;
@@ -350,6 +486,16 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
     CG_REQUIRE(sg.add == nullptr || (((uintptr_t)sg.add & 15) == 0 && sg.add_ld % 8 == 0), "cg_conv2d: seg %d add", s);
     CG_REQUIRE(sg.add2 == nullptr || (((uintptr_t)sg.add2 & 15) == 0 && sg.add2_ld % 8 == 0), "cg_conv2d: seg %d add2", s);
     CG_REQUIRE(sg.mul == nullptr || (((uintptr_t)sg.mul & 15) == 0 && sg.mul_ld % 8 == 0), "cg_conv2d: seg %d mul", s);
+  }
+  kp.nE = 0;
+  if (kp.emode) {
+    for (int s = 0; s < a->nseg && kp.nE < kESlots; ++s) {
+      const cg_seg& sg = a->seg[s];
+      const void* ptrs[3] = {sg.add, sg.add2, sg.mul};
+      const int lds[3] = {sg.add_ld, sg.add2_ld, sg.mul_ld};
+      for (int kind = 0; kind < 3 && kp.nE < kESlots; ++kind)
+        if (ptrs[kind] != nullptr) kp.eop[kp.nE++] = EOp{ptrs[kind], lds[kind], s, kind};
+    }
   }
   kp.Hp = a->H + 1;
   kp.V = a->N * kp.Hp;
@@ -365,7 +511,7 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
   uint32_t cols = 32;
   while (cols < 2u * kp.Nc) cols <<= 1;
   kp.tmem_cols = cols;
-  const int smem_bytes = kHdrBytes + kStages * kStageBytes + (int)kp.slab_bytes;
+  const int smem_bytes = kHdrBytes + kStages * kStageBytes + (kp.emode ? e_bytes(kp.Nc) : 0) + (int)kp.slab_bytes;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);

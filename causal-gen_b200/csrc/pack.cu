@@ -122,29 +122,32 @@ __global__ void fill_rows_kernel(const float* __restrict__ v, bf16* __restrict__
   y[i] = __float2bfloat16(c < C ? v[c] : 0.0f);
 }
 
-// dv[c] += sum_rows dy[row][c]; block = 32 channel-octets x 8 row lanes
-__global__ void colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ dv, long long rows, int C, int ld) {
-  const int c8 = blockIdx.y * 32 + threadIdx.x;  // channel octet
+// dv[c] += sum_rows dy[row][c].  Threads walk (row, channel-octet) pairs in memory order (coalesced 16-byte
+// loads whatever C is); partial sums are combined per octet through shared memory, one atomicAdd per
+// channel per block.
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ dv, long long rows,
+                                                     int C, int ld) {
+  const int C8 = (C + 7) / 8;
+  const int rpb = 256 / C8;              // rows per block pass (threads beyond rpb*C8 idle)
+  const int oct = threadIdx.x % C8, rsub = threadIdx.x / C8;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (c8 * 8 < C) {
-    for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < rows; r += (long long)gridDim.x * blockDim.y) {
+  if (rsub < rpb) {
+    for (long long r = (long long)blockIdx.x * rpb + rsub; r < rows; r += (long long)gridDim.x * rpb) {
       float f[8];
-      cg_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + r * ld + c8 * 8)), f);
+      cg_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + r * ld + oct * 8)), f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] += f[i];
     }
   }
-  __shared__ float red[8][32][8];
+  __shared__ float red[256][9];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) red[threadIdx.y][threadIdx.x][i] = acc[i];
+  for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = acc[i];
   __syncthreads();
-  if (threadIdx.y == 0 && c8 * 8 < C) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float s = 0.f;
-      for (int j = 0; j < 8; ++j) s += red[j][threadIdx.x][i];
-      if (c8 * 8 + i < C) atomicAdd(dv + c8 * 8 + i, s);
-    }
+  if (threadIdx.x < C8 * 8) {
+    const int o = threadIdx.x / 8, i = threadIdx.x % 8;
+    float s = 0.f;
+    for (int j = 0; j < rpb; ++j) s += red[j * C8 + o][i];
+    if (o * 8 + i < C) atomicAdd(dv + o * 8 + i, s);
   }
 }
 
@@ -247,11 +250,12 @@ extern "C" int cg_fill_rows(const float* v, void* y, int64_t rows, int32_t C, in
 extern "C" int cg_colsum(const void* dy, float* dv, int64_t rows, int32_t C, int32_t ld, void* stream) {
   CG_ARCH_GUARD();
   CG_REQUIRE(ld % 8 == 0, "cg_colsum: ld=%d", ld);
-  int gx = (int)((rows + 63) / 64);
+  CG_REQUIRE(C <= 2048, "cg_colsum: C=%d too wide", C);
+  const int rpb = 256 / ((C + 7) / 8);
+  int gx = (int)((rows + (long long)rpb * 8 - 1) / ((long long)rpb * 8));
   if (gx > 148 * 4) gx = 148 * 4;
   if (gx < 1) gx = 1;
-  colsum_kernel<<<dim3(gx, cg_ceil_div(C, 256)), dim3(32, 8), 0, cg_stream(stream)>>>(
-      reinterpret_cast<const bf16*>(dy), dv, rows, C, ld);
+  colsum_kernel<<<gx, 256, 0, cg_stream(stream)>>>(reinterpret_cast<const bf16*>(dy), dv, rows, C, ld);
   CG_LAUNCH_CHECK("cg_colsum");
   return CG_OK;
 }

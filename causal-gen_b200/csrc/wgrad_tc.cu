@@ -9,6 +9,8 @@
 // The wide side (<=128 channels per CTA) sits on M, the narrow side (<=48 channels for 3x3, <=64 for 1x1)
 // on N.  Each persistent CTA accumulates over all of its pixel tiles in TMEM and flushes once with fp32
 // atomics straight into the OIHW gradient tensor.
+#include <cmath>
+
 #include "cg_common.cuh"
 
 namespace {
@@ -60,13 +62,16 @@ __device__ __forceinline__ Geom geom_of(const WParams& P, int tile) {
   return g;
 }
 
-// Stage one operand tile as channel-octet planes.  `with_halo`: 18x10 pixels around the tile (3x3 forward
-// input), else the tile's own 128 pixels in [16][8] order.
-__device__ __forceinline__ void stage_tile(const WParams& P, uint8_t* dst, int plane, const void* ptr, int ld, int bcast,
-                                           int act, int c0, int nc8, bool with_halo, const Geom& g, int lt) {
+// Issue the cp.async copies (zero-fill for padding / out-of-image pixels) of one operand tile as
+// channel-octet planes.  `with_halo`: 18x10 pixels around the tile (3x3 forward input), else the tile's own
+// 128 pixels in [16][8] order.
+__device__ __forceinline__ void stage_tile_async(const WParams& P, uint8_t* dst, int plane, const void* ptr, int ld,
+                                                 int bcast, int c0, int nc8, bool with_halo, const Geom& g, int lt) {
   const int H = P.a.H, W = P.a.W, N = P.a.N;
   const int npix = with_halo ? 180 : 128;
   const int items = npix * nc8;
+  const uint32_t dst_u = cg_smem_u32(dst);
+  const bf16* base = reinterpret_cast<const bf16*>(ptr) + c0;
   for (int it = lt; it < items; it += kLoadThreads) {
     const int c8 = it % nc8;
     const int pix = it / nc8;
@@ -84,18 +89,20 @@ __device__ __forceinline__ void stage_tile(const WParams& P, uint8_t* dst, int p
       valid = p < P.P;
       off = bcast ? (p / ((long long)H * W)) * ld : p * ld;
     }
-    uint4 u = make_uint4(0, 0, 0, 0);
-    if (valid) {
-      u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ptr) + off + c0 + c8 * 8));
-      if (act != CG_ACT_NONE) {
-        float f[8];
-        cg_unpack8(u, f);
+    cp_async16(dst_u + c8 * plane + pix * 16, valid ? base + off + c8 * 8 : base, valid ? 16u : 0u);
+  }
+}
+
+// in-place activation of the slots this thread copied (same index walk as stage_tile_async)
+__device__ __forceinline__ void act_tile_inplace(uint8_t* dst, int plane, int act, int nc8, bool with_halo, int lt) {
+  const int items = (with_halo ? 180 : 128) * nc8;
+  for (int it = lt; it < items; it += kLoadThreads) {
+    uint4* p = reinterpret_cast<uint4*>(dst + (it % nc8) * plane + (it / nc8) * 16);
+    float f[8];
+    cg_unpack8(*p, f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = cg_act(f[i], act);
-        u = cg_pack8(f);
-      }
-    }
-    *reinterpret_cast<uint4*>(dst + c8 * plane + pix * 16) = u;
+    for (int i = 0; i < 8; ++i) f[i] = cg_act(f[i], act);
+    *p = cg_pack8(f);
   }
 }
 
@@ -141,19 +148,26 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, Nq, 1, 1);
       const uint32_t pitchP = p_halo ? 160u : 128u, pitchQ = q_halo ? 160u : 128u;
+      // descriptors built once; per MMA only the start-address field advances (16-byte units)
+      const uint64_t p_desc0 = umma_desc(cg_smem_u32(stages), pitchP, (uint32_t)planeP);
+      const uint64_t q_desc0 = umma_desc(cg_smem_u32(stages) + q_off, pitchQ, (uint32_t)planeQ);
+      const uint32_t stage16 = (uint32_t)kStageBytes >> 4;
+      const uint32_t ksP = (2u * pitchP) >> 4, ksQ = (2u * pitchQ) >> 4;
       uint32_t stage = 0, phase = 0, accum_any = 0;
       for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
         mbar_wait(BAR(stage), phase);
         tc_fence_after();
-        const uint32_t sP = cg_smem_u32(stages) + stage * kStageBytes, sQ = sP + q_off;
+        const uint64_t pd = p_desc0 + stage * stage16, qd = q_desc0 + stage * stage16;
         for (int t = 0; t < P.ntaps; ++t) {
-          const uint32_t toff = P.halo ? (uint32_t)((t / 3) * 10 + (t % 3)) * 16u : 0u;
-          // the un-shifted operand of a 3x3 problem is staged without halo: start at its own pixel 0
-          const uint32_t offP = p_halo ? toff : 0u, offQ = q_halo ? toff : 0u;
+          // the un-shifted operand of a 3x3 problem is staged without halo: it starts at its own pixel 0
+          const uint32_t toff = P.halo ? (uint32_t)((t / 3) * 10 + (t % 3)) : 0u;
+          uint64_t ad = pd + (p_halo ? toff : 0u), bd = qd + (q_halo ? toff : 0u);
+          const uint32_t d = tmem_base + (uint32_t)(t * Nq);
+#pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
-            uint64_t ad = umma_desc(sP + offP + (uint32_t)ks * 2u * pitchP, pitchP, (uint32_t)planeP);
-            uint64_t bd = umma_desc(sQ + offQ + (uint32_t)ks * 2u * pitchQ, pitchQ, (uint32_t)planeQ);
-            tc_mma_bf16(tmem_base + (uint32_t)(t * Nq), ad, bd, idesc, accum_any | (uint32_t)(ks > 0));
+            tc_mma_bf16(d, ad, bd, idesc, accum_any | (uint32_t)(ks > 0));
+            ad += ksP;
+            bd += ksQ;
           }
         }
         accum_any = 1;
@@ -163,27 +177,51 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
       tc_commit(BAR(6));
     }
   } else if (warp >= kLoadWarp0) {
+    // loaders: cp.async copies issued kStages-1 tiles ahead; activation applied in place afterwards
     const int lt = threadIdx.x - kLoadWarp0 * 32;
+    constexpr int D = kStages - 1;
     uint32_t stage = 0, phase = 0;
+    uint32_t q_stage[kStages];
+    int q_head = 0, q_len = 0;
+    const cg_src& xs = P.a.src[p_is_x ? pc.src : qc.src];
+    auto finalize = [&](uint32_t st) {
+      if (P.a.act != CG_ACT_NONE) {
+        uint8_t* sP = stages + st * kStageBytes;
+        if (p_is_x) act_tile_inplace(sP, planeP, P.a.act, pc.nc / 8, p_halo, lt);
+        else act_tile_inplace(sP + q_off, planeQ, P.a.act, qc.nc / 8, q_halo, lt);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(st));
+    };
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
       const Geom g = geom_of(P, tile);
       mbar_wait(BAR(3 + stage), phase ^ 1u);
       uint8_t* sP = stages + stage * kStageBytes;
       uint8_t* sQ = sP + q_off;
-      // P operand
       if (p_is_x) {
-        const cg_src& s = P.a.src[pc.src];
-        stage_tile(P, sP, planeP, s.ptr, s.ld, s.bcast, P.a.act, pc.c0, pc.nc / 8, p_halo, g, lt);
-        stage_tile(P, sQ, planeQ, P.a.dy, P.a.dy_ld, 0, CG_ACT_NONE, qc.c0, qc.nc / 8, false, g, lt);
+        stage_tile_async(P, sP, planeP, xs.ptr, xs.ld, xs.bcast, pc.c0, pc.nc / 8, p_halo, g, lt);
+        stage_tile_async(P, sQ, planeQ, P.a.dy, P.a.dy_ld, 0, qc.c0, qc.nc / 8, false, g, lt);
       } else {
-        const cg_src& s = P.a.src[qc.src];
-        stage_tile(P, sP, planeP, P.a.dy, P.a.dy_ld, 0, CG_ACT_NONE, pc.c0, pc.nc / 8, false, g, lt);
-        stage_tile(P, sQ, planeQ, s.ptr, s.ld, s.bcast, P.a.act, qc.c0, qc.nc / 8, q_halo, g, lt);
+        stage_tile_async(P, sP, planeP, P.a.dy, P.a.dy_ld, 0, pc.c0, pc.nc / 8, false, g, lt);
+        stage_tile_async(P, sQ, planeQ, xs.ptr, xs.ld, xs.bcast, qc.c0, qc.nc / 8, q_halo, g, lt);
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(stage));
+      cp_async_commit();
+      q_stage[(q_head + q_len) % kStages] = stage;
+      ++q_len;
       if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      if (q_len == D) {
+        cp_async_wait<D - 1>();
+        finalize(q_stage[q_head]);
+        q_head = (q_head + 1) % kStages;
+        --q_len;
+      }
+    }
+    cp_async_wait<0>();
+    while (q_len > 0) {
+      finalize(q_stage[q_head]);
+      q_head = (q_head + 1) % kStages;
+      --q_len;
     }
   } else {
     // epilogue: lane m of TMEM = channel m of the P chunk
@@ -194,22 +232,33 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
     const WChunk& xc = p_is_x ? pc : qc;  // chunk that indexes input channels
     const int xs = xc.src;
     const int ncols = P.ntaps * Nq;
+    // Nq is a multiple of 16, so a 16-column chunk never straddles two taps: tap / channel bases hoisted
+    const bool row_ok = m < pc.nc;
+    const int x_m = xc.c0 + m, y_m = pc.c0 + m;
+    int t = 0, nq0 = 0;
     for (int col = 0; col < ncols; col += 16) {
       float acc[16];
       __syncwarp();
       tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)col, acc);
-      if (m >= pc.nc) continue;
+      const int tap = (kk == 9) ? (P.ntaps == 9 ? t : 4) : 0;
+      if (row_ok) {
+        if (p_is_x) {  // lane = input channel, columns = dY channels
+          const bool x_ok = x_m < P.a.src_log[xs];
+          float* base = P.a.dw + ((long long)(qc.c0 + nq0) * P.a.cin_l + (P.a.src_off[xs] + x_m)) * kk + tap;
+          const long long step = (long long)P.a.cin_l * kk;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int c = col + i;
-        const int t = c / Nq, nq = c - t * Nq;
-        const int xch = xc.c0 + (p_is_x ? m : nq);   // channel inside the X source
-        const int ych = (p_is_x ? qc.c0 + nq : pc.c0 + m);  // dY channel
-        if (xch >= P.a.src_log[xs] || ych >= P.a.cout_l) continue;
-        const int ci = P.a.src_off[xs] + xch;
-        const int tap = (kk == 9) ? (P.ntaps == 9 ? t : 4) : 0;
-        atomicAdd(P.a.dw + ((long long)ych * P.a.cin_l + ci) * kk + tap, acc[i]);
+          for (int i = 0; i < 16; ++i)
+            if (x_ok && qc.c0 + nq0 + i < P.a.cout_l) atomicAdd(base + i * step, acc[i]);
+        } else {  // lane = dY channel, columns = input channels
+          const bool y_ok = y_m < P.a.cout_l;
+          float* base = P.a.dw + ((long long)y_m * P.a.cin_l + (P.a.src_off[xs] + xc.c0 + nq0)) * kk + tap;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (y_ok && xc.c0 + nq0 + i < P.a.src_log[xs]) atomicAdd(base + i * kk, acc[i]);
+        }
       }
+      nq0 += 16;
+      if (nq0 >= Nq) { nq0 = 0; ++t; }
     }
   }
   tc_fence_before();
@@ -282,8 +331,15 @@ extern "C" int cg_conv2d_wgrad(const cg_wgrad_args* a, void* stream) {
     }
     attr_done = true;
   }
+  // CTAs along the pixel axis: every CTA ends with one fp32 atomic per accumulator element, so few pixel
+  // tiles spread over many CTAs is dominated by the flush.  Balance tile time against flush time:
+  //   T(gx) ~ ntiles/gx * t_tile + gx * A / R   ->  gx* = sqrt(t_tile * ntiles * R / A)
+  // (t_tile ~ 2 us, R ~ 1e5 atomics/us chip-wide, A = atomics per CTA; measured on B200, profiles/r1a)
   const int combos = kp.nP * kp.nQ;
-  int gx = cg_device_sms() / combos;
+  const double atoms = 128.0 * kp.ntaps * nmax;
+  int gx = (int)(sqrt(2.0 * kp.ntiles * 1.0e5 / atoms) + 0.5);
+  const int cap = cg_device_sms() / combos > 0 ? cg_device_sms() / combos : 1;
+  if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   if (gx > kp.ntiles) gx = kp.ntiles;
   wgrad_tc_kernel<<<dim3(gx, combos), kThreads, smem_bytes, cg_stream(stream)>>>(kp);
