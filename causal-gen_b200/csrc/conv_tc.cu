@@ -2,9 +2,8 @@
 // nn.Conv2d in Block / DecoderBlock (reference src/vae.py:49-84,165-170).
 //
 //   GEMM view   D[M=128 pixels][N=Cout chunk] += A[pixels][K] * B[Cout][K],  K = taps * Cin
-//   A operand   one halo tile of the NHWC bf16 input per K-chunk of 32 channels, staged by the loader
-//               warps (activation applied on the way in) as channel-octet planes
-//               [c8][18 rows][10 px][8 ch]; because 8 consecutive pixels of a plane row are one
+//   A operand   one halo tile of the NHWC bf16 input per K-chunk of 32 channels, staged as channel-octet
+//               planes [c8][18 rows][10 px][8 ch]; because 8 consecutive pixels of a plane row are one
 //               128-byte UMMA core matrix (SWIZZLE_NONE, K-major), every one of the 9 taps is just a
 //               different descriptor start address into the SAME tile -- im2col without copies.
 //   rows        the batch is viewed as one tall image of N*(H+1) "virtual rows" (one shared zero row
@@ -14,35 +13,52 @@
 //   D           fp32 in TMEM, double buffered (2 x Nc columns, Nc <= 64; wider outputs are split over
 //               blockIdx.y) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //   epilogue    bias, channel-split segments, act'(x) multiply (backward), residual / accumulate adds,
-//               bf16 or fp32 stores.  The tensors the epilogue READS (residual, pre-activation) are staged by
-//               the loader warps with the same cp.async pipeline ("E stages"), two tiles ahead, so the
-//               epilogue never waits on a global load.
+//               bf16 or fp32 stores.  The tensors the epilogue READS (residual, pre-activation) are staged
+//               through shared memory ("E stages") by the same producer pipeline, up to 3 tiles ahead.
 //
-// Warp roles: 0-3 epilogue (TMEM lane quarters), 4 MMA issuer + TMEM owner, 5-12 loaders.
+// Producer pipeline.  Measured on B200 (profiles/r1c): mbarrier arrivals are the scarce resource -- 256
+// per-thread arrivals per stage cost ~0.6 us -- so every hand-off here is ONE arrival:
+//   stage-owner warps  warp w owns ring stage w: it alone issues all cp.async (LDGSTS, zero-fill padding) of a
+//                      K-chunk, waits for its own copies (wait_group 0), applies the pre-activation in place,
+//                      fence.proxy.async, then one lane publishes the stage.  kStages warps work on kStages
+//                      different chunks concurrently, so global latency overlaps across warps.
+//   E-owner warps      same idea for the epilogue-operand ring (one warp per E stage)
+//   MMA warp           one thread issues tcgen05.mma; tcgen05.commit frees the stage / signals the epilogue
+//   epilogue warps     TMEM -> registers -> global
+//
+// Warp roles: 0-3 epilogue (TMEM lane quarters), 4 MMA issuer + TMEM owner, 5-10 A-stage owners,
+//             11-13 E-stage owners.
+#include <cstdlib>
+
 #include "cg_common.cuh"
 
 namespace {
 
 constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = 4;
-constexpr int kLoadWarp0 = 5;
-constexpr int kLoadWarps = 8;
-constexpr int kThreads = (kLoadWarp0 + kLoadWarps) * 32;  // 416
-constexpr int kLoadThreads = kLoadWarps * 32;
-constexpr int kStages = 4;
+constexpr int kStages = 6;
+constexpr int kOwnWarp0 = 5;                 // warps 5..10 own A stages 0..5
+constexpr int kEStages = 3;                  // epilogue-operand ring depth
+constexpr int kEWarp0 = kOwnWarp0 + kStages; // warps 11..13 own E stages 0..2
+constexpr int kThreads = (kEWarp0 + kEStages) * 32;  // 448
 constexpr int kPlane3 = 2976;  // 18*10*16 = 2880, padded so the 4 planes of a stage hit distinct banks
 constexpr int kPlane1 = 2080;  // 128*16   = 2048, same padding rule
 constexpr int kStageBytes = 4 * kPlane3;
-constexpr int kHdrBytes = 1280;  // barriers (<=160B) | tmem slot | bias[256]
+constexpr int kHdrBytes = 1408;   // barriers (<=256B) | tmem slot @256 | bias[256] @320
 constexpr int kSmemMax = 232448;  // 227 KB
 constexpr int kMaxChunks = 40;
 constexpr int kMaxNc = 64;        // GEMM-N per CTA
-constexpr int kEStages = 3;       // epilogue-operand ring depth (> loader queue lag of 2 tiles: no deadlock)
 constexpr int kESlots = 2;        // staged operands per tile
 // a staged operand tile is [128 pixel rows][Nc channels] bf16 with a 16-byte row pad (bank spread)
 __host__ __device__ constexpr int e_pitch(int nc) { return nc * 2 + 16; }
 __host__ __device__ constexpr int e_slot_bytes(int nc) { return 128 * e_pitch(nc); }
 __host__ __device__ constexpr int e_bytes(int nc) { return kEStages * kESlots * e_slot_bytes(nc); }
+
+// barrier indices
+constexpr int B_AFULL = 0, B_AEMPTY = kStages, B_BFULL = 2 * kStages,
+              B_ACCFULL = B_BFULL + 1, B_ACCEMPTY = B_ACCFULL + 2, B_EFULL = B_ACCEMPTY + 2,
+              B_EEMPTY = B_EFULL + kEStages, B_COUNT = B_EEMPTY + kEStages;
+static_assert(B_COUNT * 8 <= 256, "barrier block overflows the header");
 
 struct Chunk {
   uint16_t src, c0, nc16, kbase;
@@ -60,8 +76,10 @@ struct KParams {
   int nE, emode;
   int nchunks, ntaps, Nc, nN, ktot16;
   int tiles_x, ntiles, Hp, V;
-  long long P;  // N*H*W
+  uint32_t hp_magic;            // floor(2^32/(H+1))+1: exact n = v/(H+1) for v < 2^24, H < 256
+  long long P;                  // N*H*W
   uint32_t idesc, tmem_cols, slab_bytes;
+  int dbg;  // CG_DEBUG_SKIP bit mask (profiling experiments only): 1 no cp.async, 2 no act, 4 no mma, 8 no epilogue stores
 };
 
 struct TileGeom {
@@ -83,13 +101,32 @@ __device__ __forceinline__ TileGeom tile_geom(const KParams& P, int tile) {
   return g;
 }
 
+// warp-level wait: one lane polls the mbarrier, the warp re-converges behind it
+__device__ __forceinline__ void warp_wait(uint32_t bar, uint32_t parity, int lane) {
+  if (lane == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
+
+__device__ __forceinline__ uint4 act8(uint4 u, int act) {
+  if (act == CG_ACT_RELU) {
+    const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __hmax2(h[i], z);
+    return u;
+  }
+  float f[8];
+  cg_unpack8(u, f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = cg_gelu(f[i]);
+  return cg_pack8(f);
+}
+
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  // barrier map: [0..3] a_full, [4..7] a_empty, [8] b_full, [9,10] acc_full, [11,12] acc_empty,
-  //              [13..15] e_full, [16..18] e_empty
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 192);
-  float* s_bias = reinterpret_cast<float*>(smem + 256);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
+  float* s_bias = reinterpret_cast<float*>(smem + 320);
   uint8_t* sA = smem + kHdrBytes;
   uint8_t* sE = sA + kStages * kStageBytes;
   uint8_t* sB = sE + (P.emode ? e_bytes(P.Nc) : 0);
@@ -103,17 +140,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(BAR(i), kLoadWarps);
-      mbar_init(BAR(4 + i), 1);
+      mbar_init(BAR(B_AFULL + i), 1);
+      mbar_init(BAR(B_AEMPTY + i), 1);
     }
-    mbar_init(BAR(8), 1);
-    mbar_init(BAR(9), 1);
-    mbar_init(BAR(10), 1);
-    mbar_init(BAR(11), kEpiWarps);
-    mbar_init(BAR(12), kEpiWarps);
+    mbar_init(BAR(B_BFULL), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(BAR(B_ACCFULL + i), 1);
+      mbar_init(BAR(B_ACCEMPTY + i), kEpiWarps);
+    }
     for (int i = 0; i < kEStages; ++i) {
-      mbar_init(BAR(13 + i), kLoadWarps);
-      mbar_init(BAR(16 + i), kEpiWarps);
+      mbar_init(BAR(B_EFULL + i), 1);
+      mbar_init(BAR(B_EEMPTY + i), kEpiWarps);
     }
     mbar_fence_init();
   }
@@ -128,199 +165,165 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   const bool k3 = P.a.ksize == 3;
   const int plane = k3 ? kPlane3 : kPlane1;
+  const int npix = k3 ? 180 : 128;
+  const int H = P.a.H, W = P.a.W, N = P.a.N;
 
   if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(P.a.wpack) + (size_t)nchunkN * P.slab_bytes;
-      mbar_expect_tx(BAR(8), P.slab_bytes);
+      mbar_expect_tx(BAR(B_BFULL), P.slab_bytes);
       for (uint32_t off = 0; off < P.slab_bytes; off += 32768u) {
         uint32_t n = min(32768u, P.slab_bytes - off);
-        bulk_g2s(cg_smem_u32(sB) + off, wsrc + off, n, BAR(8));
+        bulk_g2s(cg_smem_u32(sB) + off, wsrc + off, n, BAR(B_BFULL));
       }
-      mbar_wait(BAR(8), 0);
-      // Descriptors are built once; per MMA only the 14-bit start-address fields advance (all offsets are
-      // multiples of 16 B), so the single issuing thread spends ~4 instructions per tcgen05.mma.
+      mbar_wait(BAR(B_BFULL), 0);
+      // Descriptors are built once; per MMA only the 14-bit start-address field (low word) advances
+      // (all offsets are multiples of 16 B): ~4 instructions per tcgen05.mma for the issuing thread.
       const uint32_t a_sbo = k3 ? 160u : 128u;
-      const uint64_t a_desc0 = umma_desc(cg_smem_u32(sA), (uint32_t)plane, a_sbo);
-      const uint64_t b_desc0 = umma_desc(cg_smem_u32(sB), (uint32_t)Nc * 16u, 128u);
-      const uint32_t b_step16 = (uint32_t)Nc * 2u;        // (Nc*32 B per K-block) >> 4
+      const uint64_t a_d = umma_desc(cg_smem_u32(sA), (uint32_t)plane, a_sbo);
+      const uint64_t b_d = umma_desc(cg_smem_u32(sB), (uint32_t)Nc * 16u, 128u);
+      const uint32_t a_hi = (uint32_t)(a_d >> 32), b_hi = (uint32_t)(b_d >> 32);
+      const uint32_t a_lo0 = (uint32_t)a_d, b_lo0 = (uint32_t)b_d;
+      auto D64 = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
+      const uint32_t b_step16 = (uint32_t)Nc * 2u;  // (Nc*32 B per K-block) >> 4
       const uint32_t plane2_16 = (uint32_t)(2 * plane) >> 4;
       const uint32_t stage16 = (uint32_t)kStageBytes >> 4;
       const uint32_t idesc = P.idesc;
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-        mbar_wait(BAR(11 + as), aphase ^ 1u);
+        mbar_wait(BAR(B_ACCEMPTY + as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * (uint32_t)Nc;
         uint32_t accum = 0;
         for (int c = 0; c < P.nchunks; ++c) {
           const Chunk ch = P.chunk[c];
-          mbar_wait(BAR(stage), phase);
+          mbar_wait(BAR(B_AFULL + stage), phase);
           tc_fence_after();
-          uint64_t ad = a_desc0 + stage * stage16;
-          uint64_t bd = b_desc0 + (uint32_t)ch.kbase * b_step16;
-          for (int j = 0; j < ch.nc16; ++j) {
+          uint32_t alo = a_lo0 + stage * stage16;
+          uint32_t blo = b_lo0 + (uint32_t)ch.kbase * b_step16;
+          for (int j = 0; j < ch.nc16 && !(P.dbg & 4); ++j) {
             if (k3) {
 #pragma unroll
               for (int t = 0; t < 9; ++t) {
-                tc_mma_bf16(d_tmem, ad + (uint32_t)((t / 3) * 10 + (t % 3)), bd, idesc, accum);
+                tc_mma_bf16(d_tmem, D64(a_hi, alo + (uint32_t)((t / 3) * 10 + (t % 3))), D64(b_hi, blo), idesc, accum);
                 accum = 1;
-                bd += b_step16;
+                blo += b_step16;
               }
             } else {
-              tc_mma_bf16(d_tmem, ad, bd, idesc, accum);
+              tc_mma_bf16(d_tmem, D64(a_hi, alo), D64(b_hi, blo), idesc, accum);
               accum = 1;
-              bd += b_step16;
+              blo += b_step16;
             }
-            ad += plane2_16;
+            alo += plane2_16;
           }
-          tc_commit(BAR(4 + stage));  // frees the A stage once these MMAs retire
+          tc_commit(BAR(B_AEMPTY + stage));  // frees the A stage once these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        tc_commit(BAR(9 + as));  // accumulator ready for the epilogue
+        tc_commit(BAR(B_ACCFULL + as));  // accumulator ready for the epilogue
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
-  } else if (warp >= kLoadWarp0) {
-    // ------------------------------------------------------------------ A-tile loaders
-    // Each thread owns up to 3 fixed (pixel, channel-octet) slots of a stage.  Copies are cp.async
-    // (LDGSTS, zero-fill for padding) issued up to kStages-1 stages ahead, so global latency overlaps
-    // across stages instead of serialising per stage; the activation is applied in place afterwards by
-    // the thread that issued the copy (no cross-thread hazard), then the stage is published to the MMA.
-    const int lt = threadIdx.x - kLoadWarp0 * 32;
-    const int H = P.a.H, W = P.a.W, N = P.a.N;
-    const int npix = k3 ? 180 : 128;
-    const int c8 = lt & 3;
-    int pixj[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) pixj[j] = (lt + j * kLoadThreads) >> 2;
-    constexpr int D = kStages - 1;
-    uint32_t q_stage[kStages];
-    int q_nc8[kStages];
-    int q_es[kStages];  // E stage published together with this A stage, or -1
-    int q_head = 0, q_len = 0;
-    uint32_t stage = 0, phase = 0;
-    uint32_t es = 0, ephase = 0;
+  } else if (warp >= kEWarp0) {
+    // ------------------------------------------------------------------ E-stage owner warps
+    // warp e stages the tensors the epilogue of tiles e, e+3, e+6 ... (of this CTA) will read: residual /
+    // pre-activation rows of the 128 output pixels x Nc channels
     const int nE = P.nE;
-    const int ncE8 = Nc >> 3;  // channel octets per staged operand row
-    const int act = P.a.act;
-    auto finalize = [&](uint32_t st, int nc8, int e_st) {
-      if (act != CG_ACT_NONE && c8 < nc8) {
-        uint8_t* dst = sA + st * kStageBytes + c8 * plane;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          if (pixj[j] < npix) {
-            uint4* p = reinterpret_cast<uint4*>(dst + pixj[j] * 16);
-            float f[8];
-            cg_unpack8(*p, f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = cg_act(f[i], act);
-            *p = cg_pack8(f);
-          }
-        }
-      }
-      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(BAR(st));
-        if (e_st >= 0) mbar_arrive(BAR(13 + e_st));
-      }
-    };
-    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-      const TileGeom g = tile_geom(P, tile);
-      bool valid[3];
-      long long poff[3];
-      int nidx[3];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const int pix = pixj[j];
-        if (k3) {
-          const int rr = pix / 10, cc = pix - rr * 10;
-          const int v = g.v0 - 1 + rr, w = g.w0 - 1 + cc;
-          const int n = v / P.Hp, h = v - n * P.Hp;
-          valid[j] = (pix < npix) && (v >= 0) && (w >= 0) && (w < W) && (n < N) && (h < H);
-          poff[j] = (long long)(n * H + h) * W + w;
-          nidx[j] = n;
-        } else {
-          const long long p = g.p0 + pix;
-          valid[j] = (pix < npix) && (p < P.P);
-          poff[j] = p;
-          nidx[j] = (int)(p / ((long long)H * W));
-        }
-      }
-      int e_now = -1;
-      if (nE > 0) {
-        // stage the tensors this tile's epilogue will read (residual / pre-activation rows of the
-        // 128 output pixels x Nc channels) into E stage `es`
-        mbar_wait(BAR(16 + es), ephase ^ 1u);
-        const int items = 128 * ncE8;
+    if (nE > 0) {
+      const int es = warp - kEWarp0;
+      const int ncE8 = Nc >> 3;  // channel octets per staged operand row
+      const int items = 128 * ncE8;
+      uint32_t ephase = 0;
+      int tseq = 0;
+      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++tseq) {
+        if (tseq % kEStages != es) continue;
+        const TileGeom g = tile_geom(P, tile);
+        warp_wait(BAR(B_EEMPTY + es), ephase ^ 1u, lane);
         for (int k = 0; k < nE; ++k) {
           const EOp& op = P.eop[k];
           const cg_seg& sg = P.a.seg[op.seg];
           const uint32_t dstE = cg_smem_u32(sE + (es * kESlots + k) * eslot);
-          for (int it = lt; it < items; it += kLoadThreads) {
-            const int row = it / ncE8, oc = it - row * ncE8;
+          for (int i = lane; i < items; i += 32) {
+            const int row = i / ncE8, oc = i - row * ncE8;
             const int lc = nchunkN * Nc + oc * 8 - sg.c0;  // channel inside the segment
             bool ok;
             long long px;
             if (k3) {
               const int v = g.v0 + (row >> 3), w = g.w0 + (row & 7);
-              const int n = v / P.Hp, h = v - n * P.Hp;
+              const int n = (int)__umulhi((uint32_t)v, P.hp_magic), h = v - n * P.Hp;
               ok = (n < N) && (h < H) && (w < W);
               px = (long long)(n * H + h) * W + w;
             } else {
               px = g.p0 + row;
               ok = px < P.P;
             }
-            if (ok && lc >= 0 && lc < sg.cn)
+            if (ok && lc >= 0 && lc < sg.cn && !(P.dbg & 1))
               cp_async16(dstE + row * epitch + oc * 16, reinterpret_cast<const bf16*>(op.ptr) + px * op.ld + lc, 16u);
           }
         }
-        e_now = (int)es;
-        if (++es == kEStages) { es = 0; ephase ^= 1u; }
-      }
-      for (int c = 0; c < P.nchunks; ++c) {
-        const Chunk ch = P.chunk[c];
-        const cg_src& s = P.a.src[ch.src];
-        const int nc8 = ch.nc16 * 2;
-        mbar_wait(BAR(4 + stage), phase ^ 1u);
-        if (c8 < nc8) {
-          const uint32_t dst = cg_smem_u32(sA + stage * kStageBytes + c8 * plane);
-          const bf16* base = reinterpret_cast<const bf16*>(s.ptr) + ch.c0 + c8 * 8;
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            if (pixj[j] < npix) {
-              const bf16* src = valid[j] ? base + (s.bcast ? (long long)nidx[j] : poff[j]) * s.ld : base;
-              cp_async16(dst + pixj[j] * 16, src, valid[j] ? 16u : 0u);
-            }
-          }
-        }
         cp_async_commit();
-        q_stage[(q_head + q_len) % kStages] = stage;
-        q_nc8[(q_head + q_len) % kStages] = nc8;
-        q_es[(q_head + q_len) % kStages] = (c == 0) ? e_now : -1;
-        ++q_len;
-        if (++stage == kStages) { stage = 0; phase ^= 1u; }
-        if (q_len == D) {
-          cp_async_wait<D - 1>();
-          finalize(q_stage[q_head], q_nc8[q_head], q_es[q_head]);
-          q_head = (q_head + 1) % kStages;
-          --q_len;
-        }
+        cp_async_wait<0>();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(B_EFULL + es));
+        ephase ^= 1u;
       }
     }
-    cp_async_wait<0>();
-    while (q_len > 0) {
-      finalize(q_stage[q_head], q_nc8[q_head], q_es[q_head]);
-      q_head = (q_head + 1) % kStages;
-      --q_len;
+  } else if (warp >= kOwnWarp0) {
+    // ------------------------------------------------------------------ A-stage owner warps
+    const int st = warp - kOwnWarp0;  // the ring stage this warp owns
+    const int act = P.a.act;
+    uint8_t* const sbase = sA + st * kStageBytes;
+    const uint32_t sbase_u = cg_smem_u32(sbase);
+    const int nslots = npix * 4;
+    uint32_t phase = 0;
+    const long long nwork = (long long)((P.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1) * P.nchunks;
+    for (long long gidx = st; gidx < nwork; gidx += kStages) {
+      const int tseq = (int)(gidx / P.nchunks);
+      const Chunk ch = P.chunk[(int)(gidx - (long long)tseq * P.nchunks)];
+      const TileGeom g = tile_geom(P, (int)blockIdx.x + tseq * (int)gridDim.x);
+      const cg_src& s = P.a.src[ch.src];
+      const int nc8 = ch.nc16 * 2;
+      const bf16* base = reinterpret_cast<const bf16*>(s.ptr) + ch.c0;
+      warp_wait(BAR(B_AEMPTY + st), phase ^ 1u, lane);
+      if (!(P.dbg & 1)) {
+        for (int sl = lane; sl < nslots; sl += 32) {
+          const int c8 = sl & 3, pix = sl >> 2;
+          if (c8 >= nc8) continue;
+          bool valid;
+          long long off;
+          if (k3) {
+            const int rr = pix / 10, cc = pix - rr * 10;
+            const int v = g.v0 - 1 + rr, w = g.w0 - 1 + cc;
+            const int n = (int)__umulhi((uint32_t)max(v, 0), P.hp_magic), h = v - n * P.Hp;
+            valid = (v >= 0) && (w >= 0) && (w < W) && (n < N) && (h < H);
+            off = s.bcast ? (long long)n * s.ld : ((long long)(n * H + h) * W + w) * s.ld;
+          } else {
+            const long long p = g.p0 + pix;
+            valid = p < P.P;
+            off = s.bcast ? (long long)((uint32_t)min(p, P.P - 1) / (uint32_t)(H * W)) * s.ld : p * s.ld;
+          }
+          cp_async16(sbase_u + c8 * plane + pix * 16, valid ? base + off + c8 * 8 : base, valid ? 16u : 0u);
+        }
+      }
+      cp_async_commit();
+      cp_async_wait<0>();  // this warp's copies only; the other owner warps keep their chunks in flight
+      if (act != CG_ACT_NONE && !(P.dbg & 2)) {
+        for (int sl = lane; sl < nslots; sl += 32) {
+          const int c8 = sl & 3;
+          if (c8 >= nc8) continue;
+          uint4* p = reinterpret_cast<uint4*>(sbase + c8 * plane + (sl >> 2) * 16);
+          *p = act8(*p, act);
+        }
+      }
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_AFULL + st));
+      phase ^= 1u;
     }
   } else {
     // ------------------------------------------------------------------ epilogue
     uint32_t as = 0, aphase = 0, es = 0, ephase = 0;
     const int m = warp * 32 + lane;
-    const int H = P.a.H, W = P.a.W, N = P.a.N;
     const int nE = P.nE;
     // staged-operand slot of (segment, kind) or -1 -> direct global load
     auto slot_of = [&](int sgi, int kind) {
@@ -334,15 +337,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       long long pix;
       if (k3) {
         const int v = g.v0 + (m >> 3), w = g.w0 + (m & 7);
-        const int n = v / P.Hp, h = v - n * P.Hp;
+        const int n = (int)__umulhi((uint32_t)v, P.hp_magic), h = v - n * P.Hp;
         valid = (n < N) && (h < H) && (w < W);
         pix = (long long)(n * H + h) * W + w;
       } else {
         pix = g.p0 + m;
         valid = pix < P.P;
       }
-      if (nE > 0) mbar_wait(BAR(13 + es), ephase);
-      mbar_wait(BAR(9 + as), aphase);
+      if (nE > 0) warp_wait(BAR(B_EFULL + es), ephase, lane);
+      warp_wait(BAR(B_ACCFULL + as), aphase, lane);
       tc_fence_after();
       const uint8_t* e_row = sE + (size_t)(es * kESlots) * eslot + (size_t)m * epitch;
       const uint32_t t_row = tmem_base + as * (uint32_t)Nc + ((uint32_t)(warp * 32) << 16);
@@ -354,7 +357,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (cg0 >= P.a.cout) continue;
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] += s_bias[col + i];
-        if (!valid) continue;
+        if (!valid || (P.dbg & 8)) continue;
         for (int sgi = 0; sgi < P.a.nseg; ++sgi) {
           const cg_seg& sg = P.a.seg[sgi];
           const int lc = cg0 - sg.c0;
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = acc[i];
-          // operand fetch: staged tile row (shared memory) if the loaders brought it, else global
+          // operand fetch: staged tile row (shared memory) if the producers brought it, else global
           auto fetch = [&](int kind, const void* gptr, int gld, int h8) -> uint4 {
             const int k = slot_of(sgi, kind);
             if (k >= 0) return *reinterpret_cast<const uint4*>(e_row + (size_t)k * eslot + (col + h8) * 2);
@@ -406,8 +409,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(BAR(11 + as));
-        if (nE > 0) mbar_arrive(BAR(16 + es));
+        mbar_arrive(BAR(B_ACCEMPTY + as));
+        if (nE > 0) mbar_arrive(BAR(B_EEMPTY + es));
       }
       if (++as == 2) { as = 0; aphase ^= 1u; }
       if (nE > 0 && ++es == kEStages) { es = 0; ephase ^= 1u; }
@@ -429,12 +432,15 @@ int pick_nc(int ktot16, int cout, int* emode) {
     for (int nc_max = kMaxNc; nc_max >= 16; nc_max -= 16) {
       if (ktot16 * nc_max * 32 + (mode ? e_bytes(nc_max) : 0) > base) continue;
       const int nN = (cout + nc_max - 1) / nc_max;
+      const int nc = ((cout + nN - 1) / nN + 15) / 16 * 16;
       if (emode) *emode = mode;
-      return ((cout + nN - 1) / nN + 15) / 16 * 16;
+      return nc;
     }
   }
   return 0;
 }
+
+uint32_t magic_of(long long d) { return (uint32_t)((1ull << 32) / (unsigned long long)d + 1ull); }
 
 }  // namespace
 
@@ -455,7 +461,10 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
   CG_REQUIRE(a->nseg >= 1 && a->nseg <= CG_MAX_SEG, "cg_conv2d: nseg %d", a->nseg);
   CG_REQUIRE(a->cout > 0 && a->cout % 16 == 0, "cg_conv2d: cout %d must be a positive multiple of 16", a->cout);
   CG_REQUIRE(a->N > 0 && a->H > 0 && a->W > 0, "cg_conv2d: empty tensor");
+  CG_REQUIRE((long long)a->N * (a->H + 1) < (1ll << 24) && (long long)a->N * a->H * a->W < (1ll << 31),
+             "cg_conv2d: tensor too large for 32-bit pixel arithmetic");
   CG_REQUIRE(a->wpack != nullptr && ((uintptr_t)a->wpack & 15) == 0, "cg_conv2d: wpack null or unaligned");
+  CG_REQUIRE(a->ksize == 1 || a->H < 256, "cg_conv2d: 3x3 path supports H < 256 (got %d)", a->H);
   KParams kp;
   kp.a = *a;
   kp.ntaps = a->ksize * a->ksize;
@@ -500,6 +509,7 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
   kp.Hp = a->H + 1;
   kp.V = a->N * kp.Hp;
   kp.P = (long long)a->N * a->H * a->W;
+  kp.hp_magic = magic_of(kp.Hp);
   if (a->ksize == 3) {
     kp.tiles_x = (a->W + 7) / 8;
     kp.ntiles = ((kp.V + 15) / 16) * kp.tiles_x;
@@ -521,6 +531,9 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
     }
     attr_done = true;
   }
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("CG_DEBUG_SKIP"); dbg = e ? atoi(e) : 0; }
+  kp.dbg = dbg;
   const int sms = cg_device_sms();
   int gx = sms / kp.nN;
   if (gx < 1) gx = 1;

@@ -143,8 +143,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy
 #pragma unroll
   for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = acc[i];
   __syncthreads();
-  if (threadIdx.x < C8 * 8) {
-    const int o = threadIdx.x / 8, i = threadIdx.x % 8;
+  for (int t = threadIdx.x; t < C8 * 8; t += 256) {  // C may exceed 256 channels
+    const int o = t / 8, i = t % 8;
     float s = 0.f;
     for (int j = 0; j < rpb; ++j) s += red[j * C8 + o][i];
     if (o * 8 + i < C) atomicAdd(dv + o * 8 + i, s);

@@ -163,6 +163,45 @@ def test_conv_dgrad_and_wgrad(case):
     assert_close(db + 0.25, bq.grad, 1e-2, f"bias grad {case}")
 
 
+@pytest.mark.parametrize("case", [(8, 96, 96, [16], 0, 64, 3, 1), (8, 96, 96, [64], 0, 16, 3, 1),
+                                  (16, 48, 48, [32], 0, 96, 3, 2), (32, 24, 24, [128, 128], 4, 32, 3, 1),
+                                  (8, 96, 96, [16], 4, 64, 1, 0), (4, 192, 192, [16], 0, 32, 3, 1)])
+def test_conv_many_tiles_per_cta(case):
+    """pipeline rings wrap many times: several tiles per persistent CTA, in-place accumulate, fused operands"""
+    from causalgen_b200.ops import SegSpec, View, new_act, round16
+    N, H, W, chans, ctx, cout, k, act = case
+    layer, views, out, ref, w, b = run_conv(*case, seed=11)
+    assert_close(to_nchw(out.t, cout), ref, 1e-2, f"fwd {case}")
+    # forward again with residual + second addend, accumulating IN PLACE into the first addend's buffer
+    acc = View(nhwc_bf16(rnd(N, cout, H, W, seed=50)), round16(cout))
+    acc0 = to_nchw(acc.t, cout).clone()
+    other = View(nhwc_bf16(rnd(N, cout, H, W, seed=51)), round16(cout))
+    layer.forward(views, [SegSpec(acc, 0, add=acc, add2=other)], N, H, W)(stream())
+    torch.cuda.synchronize()
+    assert_close(to_nchw(acc.t, cout), ref + acc0 + to_nchw(other.t, cout), 1e-2, f"fwd in-place add {case}")
+    # data gradient with act'(x) and in-place accumulate; weight gradient
+    dy = View(nhwc_bf16(rnd(N, cout, H, W, seed=52)), round16(cout), 0, cout)
+    data_views = [v for v in views if not v.bcast]
+    xs = [to_nchw(v.t, c).requires_grad_(True) for v, c in zip(data_views, chans)]
+    parts = list(xs)
+    if ctx:
+        pav = [v for v in views if v.bcast][0]
+        parts.insert(1, pav.t[:, :ctx].float()[:, :, None, None].expand(N, ctx, H, W))
+    wq = w.to(torch.bfloat16).float().requires_grad_(True)
+    y = F.conv2d(act_fn(act)(torch.cat(parts, 1)), wq, None, padding=k // 2)
+    y.backward(to_nchw(dy.t, cout))
+    i0 = views.index(data_views[0])
+    dx = View(nhwc_bf16(rnd(N, chans[0], H, W, seed=53)), round16(chans[0]))
+    dx0 = to_nchw(dx.t, chans[0]).clone()
+    layer.dgrad(i0, dy, SegSpec(dx, 0, add=dx, mul=data_views[0], mul_act=act), N, H, W)(stream())
+    torch.cuda.synchronize()
+    assert_close(to_nchw(dx.t, chans[0]), xs[0].grad + dx0, 1.5e-2, f"dgrad in-place {case}")
+    dw = torch.zeros_like(w)
+    layer.wgrad(views, dy, dw, None, N, H, W)(stream())
+    torch.cuda.synchronize()
+    assert_close(dw, wq.grad, 1e-2, f"wgrad {case}")
+
+
 def test_conv_centre_tap_on_1x1_image():
     from causalgen_b200.ops import ConvLayer, PackTable, SegSpec, View, new_act
     N, Cin, Cout = 6, 64, 48
@@ -464,6 +503,18 @@ def test_mix_cf_and_layout_glue():
     L.check(lib.cg_nhwc_bf16_to_nchw_f32(nh.data_ptr(), back.data_ptr(), 2, 20, 81, 32, stream()))
     assert_close(back, t.to(torch.bfloat16).float(), 1e-6, "layout round trip")
     assert nh[..., 20:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("rows,C", [(2, 288), (5000, 32), (777, 24), (36864, 16), (3, 544), (100, 8)])
+def test_colsum_bias_gradient(rows, C):
+    from causalgen_b200 import _lib as L
+    from causalgen_b200.ops import round16
+    ld = round16(C)
+    dy = torch.zeros(rows, ld, device=DEV, dtype=torch.bfloat16)
+    dy[:, :C] = rnd(rows, C, seed=3).to(torch.bfloat16)
+    out = torch.full((C,), 0.5, device=DEV)
+    L.check(L.load().cg_colsum(dy.data_ptr(), out.data_ptr(), rows, C, ld, stream()))
+    assert_close(out - 0.5, dy[:, :C].float().sum(0), 2e-3, f"colsum {rows}x{C}")
 
 
 def test_optimizer_tail_matches_torch_adamw():
