@@ -158,7 +158,7 @@ def conv_bytes(a):
     k = 0
     for i in range(a.nsrc):
         s = a.src[i]
-        b += (a.N if s.bcast else npix) * s.C * 2
+        b += npix * s.C * 2
         k += s.C
     for i in range(a.nseg):
         sg = a.seg[i]
@@ -174,8 +174,7 @@ def wgrad_bytes(a):
     npix = a.N * a.H * a.W
     b = npix * a.dy_c * 2
     for i in range(a.nsrc):
-        s = a.src[i]
-        b += (a.N if s.bcast else npix) * s.C * 2
+        b += npix * a.src[i].C * 2
     return b + a.cout_l * a.cin_l * a.ksize * a.ksize * 4
 
 

@@ -18,13 +18,13 @@ BF16, F32 = 0, 1
 
 
 class Src(C.Structure):
-    _fields_ = [("ptr", C.c_void_p), ("C", C.c_int32), ("ld", C.c_int32), ("bcast", C.c_int32), ("_pad", C.c_int32)]
+    _fields_ = [("ptr", C.c_void_p), ("ns", C.c_int64), ("C", C.c_int32), ("_pad", C.c_int32)]
 
 
 class Seg(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("add", C.c_void_p), ("add2", C.c_void_p), ("mul", C.c_void_p),
-                ("c0", C.c_int32), ("cn", C.c_int32), ("ld", C.c_int32), ("add_ld", C.c_int32),
-                ("add2_ld", C.c_int32), ("mul_ld", C.c_int32), ("dtype", C.c_int32), ("mul_act", C.c_int32)]
+                ("ns", C.c_int64), ("add_ns", C.c_int64), ("add2_ns", C.c_int64), ("mul_ns", C.c_int64),
+                ("c0", C.c_int32), ("cn", C.c_int32), ("dtype", C.c_int32), ("mul_act", C.c_int32)]
 
 
 class ConvArgs(C.Structure):
@@ -44,8 +44,8 @@ class PackDesc(C.Structure):
 
 class WgradArgs(C.Structure):
     _fields_ = [("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("ksize", C.c_int32), ("act", C.c_int32),
-                ("nsrc", C.c_int32), ("src", Src * CG_MAX_SRC), ("dy", C.c_void_p), ("dy_c", C.c_int32),
-                ("dy_ld", C.c_int32), ("dw", C.c_void_p), ("dbias", C.c_void_p), ("cout_l", C.c_int32),
+                ("nsrc", C.c_int32), ("src", Src * CG_MAX_SRC), ("dy", C.c_void_p), ("dy_ns", C.c_int64),
+                ("dy_c", C.c_int32), ("_pad", C.c_int32), ("dw", C.c_void_p), ("dbias", C.c_void_p), ("cout_l", C.c_int32),
                 ("cin_l", C.c_int32), ("src_log", C.c_int32 * CG_MAX_SRC), ("src_off", C.c_int32 * CG_MAX_SRC),
                 ("taps", C.c_int32)]
 
@@ -54,7 +54,7 @@ class LatentArgs(C.Structure):
     _fields_ = [("q", C.c_void_p), ("p", C.c_void_p), ("q_ld", C.c_int32), ("p_ld", C.c_int32),
                 ("eps", C.c_void_p), ("seed", C.c_uint64), ("offset", C.c_uint64), ("seed_dev", C.c_void_p),
                 ("log_t", C.c_float),
-                ("z_bf16", C.c_void_p), ("z_ld", C.c_int32), ("z_f32", C.c_void_p), ("eps_out", C.c_void_p),
+                ("z_bf16", C.c_void_p), ("z_ns", C.c_int64), ("z_f32", C.c_void_p), ("eps_out", C.c_void_p),
                 ("kl_out", C.c_void_p), ("N", C.c_int32), ("HW", C.c_int32), ("zdim", C.c_int32),
                 ("mode", C.c_int32)]
 
@@ -62,25 +62,25 @@ class LatentArgs(C.Structure):
 class LatentBwdArgs(C.Structure):
     _fields_ = [("q", C.c_void_p), ("p", C.c_void_p), ("q_ld", C.c_int32), ("p_ld", C.c_int32),
                 ("eps", C.c_void_p), ("seed", C.c_uint64), ("offset", C.c_uint64), ("seed_dev", C.c_void_p),
-                ("dz", C.c_void_p), ("dz_ld", C.c_int32), ("g_kl", C.c_float),
-                ("dq", C.c_void_p), ("dq_ld", C.c_int32), ("dp", C.c_void_p), ("dp_ld", C.c_int32),
+                ("dz", C.c_void_p), ("dz_ns", C.c_int64), ("g_kl", C.c_float),
+                ("dq", C.c_void_p), ("dq_ns", C.c_int64), ("dp", C.c_void_p), ("dp_ns", C.c_int64),
                 ("N", C.c_int32), ("HW", C.c_int32), ("zdim", C.c_int32), ("mode", C.c_int32)]
 
 
 class DGaussArgs(C.Structure):
-    _fields_ = [("h", C.c_void_p), ("h_ld", C.c_int32), ("Cw", C.c_int32), ("x", C.c_void_p),
+    _fields_ = [("h", C.c_void_p), ("h_ns", C.c_int64), ("Cw", C.c_int32), ("_pad0", C.c_int32), ("x", C.c_void_p),
                 ("w_loc", C.c_void_p), ("b_loc", C.c_void_p), ("w_ls", C.c_void_p), ("b_ls", C.c_void_p),
                 ("w_co", C.c_void_p), ("b_co", C.c_void_p),
                 ("N", C.c_int32), ("HW", C.c_int32), ("C", C.c_int32),
-                ("nll", C.c_void_p), ("g", C.c_float), ("dh", C.c_void_p), ("dh_ld", C.c_int32),
+                ("nll", C.c_void_p), ("g", C.c_float), ("dh", C.c_void_p), ("dh_ns", C.c_int64),
                 ("dw_loc", C.c_void_p), ("db_loc", C.c_void_p), ("dw_ls", C.c_void_p), ("db_ls", C.c_void_p),
                 ("dw_co", C.c_void_p), ("db_co", C.c_void_p)]
 
 
 class DmolArgs(C.Structure):
-    _fields_ = [("h", C.c_void_p), ("h_ld", C.c_int32), ("Cw", C.c_int32), ("x", C.c_void_p), ("w", C.c_void_p),
-                ("b", C.c_void_p), ("N", C.c_int32), ("HW", C.c_int32), ("nll", C.c_void_p), ("g", C.c_float),
-                ("dh", C.c_void_p), ("dh_ld", C.c_int32), ("dw", C.c_void_p), ("db", C.c_void_p)]
+    _fields_ = [("h", C.c_void_p), ("h_ns", C.c_int64), ("Cw", C.c_int32), ("_pad0", C.c_int32), ("x", C.c_void_p),
+                ("w", C.c_void_p), ("b", C.c_void_p), ("N", C.c_int32), ("HW", C.c_int32), ("nll", C.c_void_p),
+                ("g", C.c_float), ("dh", C.c_void_p), ("dh_ns", C.c_int64), ("dw", C.c_void_p), ("db", C.c_void_p)]
 
 
 _SIGNATURES = {
@@ -94,13 +94,15 @@ _SIGNATURES = {
     "cg_pack_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "cg_conv2d_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
     "cg_stem_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
-                              C.c_int32, C.c_int32, C.c_void_p]),
+                              C.c_int32, C.c_int64, C.c_void_p]),
     "cg_stem_wgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
-                                C.c_int32, C.c_int32, C.c_void_p]),
-    "cg_avgpool_fwd": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 8 + [C.c_void_p]),
-    "cg_avgpool_bwd": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 9 + [C.c_void_p]),
-    "cg_upsample_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
-    "cg_upsample_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p]),
+                                C.c_int32, C.c_int64, C.c_void_p]),
+    "cg_avgpool_fwd": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 5 + [C.c_int64] * 2 + [C.c_int32, C.c_void_p]),
+    "cg_avgpool_bwd": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 5 + [C.c_int64] * 2 + [C.c_int32] * 2 +
+                       [C.c_void_p]),
+    "cg_upsample_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 4 + [C.c_int64] * 2 + [C.c_void_p]),
+    "cg_upsample_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 4 + [C.c_int64] * 2 +
+                        [C.c_int32, C.c_void_p]),
     "cg_latent_fwd": (C.c_int, [C.POINTER(LatentArgs), C.c_void_p]),
     "cg_latent_bwd": (C.c_int, [C.POINTER(LatentBwdArgs), C.c_void_p]),
     "cg_latent_mix": (C.c_int, [C.c_void_p] * 6 + [C.c_int64, C.c_float, C.c_float, C.c_int32, C.c_void_p]),
@@ -113,15 +115,15 @@ _SIGNATURES = {
                                   C.c_void_p, C.c_void_p]),
     "cg_cf_combine": (C.c_int, [C.c_void_p] * 8 + [C.c_int64, C.c_void_p]),
     "cg_normalise_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
-    "cg_parents_pack": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
-                                  C.c_int32, C.c_float, C.c_void_p]),
-    "cg_nchw_f32_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p]),
-    "cg_nhwc_bf16_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p]),
+    "cg_parents_plane": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_int32, C.c_int64, C.c_int32, C.c_float, C.c_void_p]),
+    "cg_nchw_f32_to_planar": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 3 + [C.c_int64, C.c_void_p]),
+    "cg_planar_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 3 + [C.c_int64, C.c_void_p]),
     "cg_stats_to_nchw": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_void_p]),
-    "cg_fill_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
-    "cg_colsum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
-    "cg_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_int32] * 4 + [C.c_void_p]),
+    "cg_fill_planar": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]),
+    "cg_colsum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]),
+    "cg_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 3 + [C.c_int64] * 3 + [C.c_void_p]),
     "cg_elbo_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float,
                                    C.c_void_p]),
     "cg_sumsq": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

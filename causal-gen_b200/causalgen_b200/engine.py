@@ -193,7 +193,7 @@ class Engine:
         w0 = self.args.widths[0]
         e.stem_out = new_act(N, R, R, w0, self.device)
         prog.call("cg_stem_fwd", x.data_ptr(), enc.stem.weight.data_ptr(), enc.stem.bias.data_ptr(),
-                  e.stem_out.ptr, N, self.C, R, w0, e.stem_out.ld)
+                  e.stem_out.ptr, N, self.C, R, w0, e.stem_out.ns)
         prog.keep.append(x)
         cur = e.stem_out
         e.blocks = []
@@ -204,8 +204,8 @@ class Engine:
             r.st = st
             if st.down:
                 r.out = new_act(N, st.res_out, st.res_out, st.cout, self.device)
-                prog.call("cg_avgpool_fwd", r.y.ptr, r.out.ptr, N, st.res_in, st.res_in, r.y.C, st.down, r.y.ld,
-                          r.out.ld, st.res_out)
+                prog.call("cg_avgpool_fwd", r.y.ptr, r.out.ptr, N, st.res_in, st.res_in, r.y.C, st.down, r.y.ns,
+                          r.out.ns, st.res_out)
             else:
                 r.out = r.y
             e.blocks.append(r)
@@ -214,7 +214,7 @@ class Engine:
             cur = r.out
         return e
 
-    def _decoder_fwd(self, prog: Program, N, pa: View, pa_sto: View, acts: Optional[Dict[int, View]],
+    def _decoder_fwd(self, prog: Program, N, pa: Dict[int, View], pa_sto: Dict[int, View], acts: Optional[Dict[int, View]],
                      given: Optional[Sequence[bool]] = None, want_z: bool = False, want_stats: bool = False,
                      explicit_eps: bool = True, kl_rows: Optional[torch.Tensor] = None) -> Rec:
         """reference Decoder.forward (src/vae.py:222-301).  `given[i]` marks stochastic block i whose latent is
@@ -231,7 +231,7 @@ class Engine:
         bias_of = {r: p for (r, _), p in zip(dec.bias_res, dec.bias)}
         w1 = dec.plan[0].cin
         h = new_act(N, 1, 1, w1, self.device)
-        prog.call("cg_fill_rows", bias_of[1].data_ptr(), h.ptr, N, w1, h.ld)
+        prog.call("cg_fill_planar", bias_of[1].data_ptr(), h.ptr, N, 1, w1, h.ns)
         zs = h  # h = z = bias[1].repeat (src/vae.py:232)
         cur_res = 1
         ksto = 0
@@ -246,19 +246,19 @@ class Engine:
                 bptr = b.data_ptr() if b is not None else None
                 r.up = (cur_res, h, zs, b)
                 h_up = new_act(N, res, res, st.cin, self.device)
-                prog.call("cg_upsample_fwd", h.ptr, bptr, h_up.ptr, N, cur_res, res, st.cin, h.ld, h_up.ld)
+                prog.call("cg_upsample_fwd", h.ptr, bptr, h_up.ptr, N, cur_res, res, st.cin, h.ns, h_up.ns)
                 if not self.q_corr:
                     if zs is h:
                         zs_up = h_up
                     else:
                         zs_up = new_act(N, res, res, st.cin, self.device)
-                        prog.call("cg_upsample_fwd", zs.ptr, bptr, zs_up.ptr, N, cur_res, res, st.cin, zs.ld, zs_up.ld)
+                        prog.call("cg_upsample_fwd", zs.ptr, bptr, zs_up.ptr, N, cur_res, res, st.cin, zs.ns, zs_up.ns)
                     zs = zs_up
                 h = h_up
                 cur_res = res
             r.h_in, r.zs_in = h, zs
             # ---- prior (src/vae.py:172-183)
-            p_src = [h if self.q_corr else zs] + ([pa_sto] if self.cond_prior else [])
+            p_src = [h if self.q_corr else zs] + ([pa_sto[res]] if self.cond_prior else [])
             r.pstat = View(torch.zeros(N, res, res, 2 * zd, device=self.device, dtype=torch.float32), 2 * zd)
             r.pfeat = new_act(N, res, res, st.cin, self.device)
             r.prior = self._block_fwd(prog, d.prior, p_src, N, res, res,
@@ -274,27 +274,27 @@ class Engine:
                 is_given = bool(given[ksto]) if given is not None and ksto < len(given) else False
                 if acts is not None:
                     r.qstat = View(torch.zeros(N, res, res, 2 * zd, device=self.device, dtype=torch.float32), 2 * zd)
-                    r.post = self._block_fwd(prog, d.post, [h, pa, acts[res]], N, res, res,
+                    r.post = self._block_fwd(prog, d.post, [h, pa[res], acts[res]], N, res, res,
                                              final_segs=[SegSpec(r.qstat, 0)])
                     r.mode = 0
                 elif is_given:
                     zin = torch.zeros(N, zd, res, res, device=self.device, dtype=torch.float32)
                     D.z_in[ksto] = zin
-                    prog.call("cg_nchw_f32_to_nhwc_bf16", zin.data_ptr(), r.z.ptr, N, zd, res * res, r.z.ld)
+                    prog.call("cg_nchw_f32_to_planar", zin.data_ptr(), r.z.ptr, N, zd, res * res, r.z.ns)
                     r.mode = 3
                 else:
                     r.mode = 1
                 if r.mode in (0, 1):
                     la = L.LatentArgs()
-                    la.p, la.p_ld = r.pstat.ptr, r.pstat.ld
+                    la.p, la.p_ld = r.pstat.ptr, r.pstat.ns
                     if r.mode == 0:
-                        la.q, la.q_ld = r.qstat.ptr, r.qstat.ld
+                        la.q, la.q_ld = r.qstat.ptr, r.qstat.ns
                     if explicit_eps:
                         r.eps = torch.zeros(N, zd, res, res, device=self.device, dtype=torch.float32)
                         la.eps = r.eps.data_ptr()
                     D.eps.append(r.eps)
                     la.offset = ksto << 40
-                    la.z_bf16, la.z_ld = r.z.ptr, r.z.ld
+                    la.z_bf16, la.z_ns = r.z.ptr, r.z.ns
                     if want_z:
                         zo = torch.zeros(N, zd, res, res, device=self.device, dtype=torch.float32)
                         D.z_out[ksto] = zo
@@ -307,8 +307,8 @@ class Engine:
                 ksto += 1
             else:
                 la = L.LatentArgs()
-                la.p, la.p_ld = r.pstat.ptr, r.pstat.ld
-                la.z_bf16, la.z_ld = r.z.ptr, r.z.ld
+                la.p, la.p_ld = r.pstat.ptr, r.pstat.ns
+                la.z_bf16, la.z_ns = r.z.ptr, r.z.ns
                 la.N, la.HW, la.zdim, la.mode = N, res * res, zd, 2
             if la is not None:
                 prog.add(L.Launch("cg_latent_fwd", C.byref(la))).keep = (la, r)
@@ -316,7 +316,7 @@ class Engine:
             # ---- merge (src/vae.py:292-300)
             r.h3 = new_act(N, res, res, st.cin, self.device)
             # h3 = h + p_feat + z_proj(cat[z, pa]) in one epilogue (src/vae.py:292-294)
-            prog.add(d.z_proj.forward([r.z, pa], [SegSpec(r.h3, 0, add=h, add2=r.pfeat)], N, res, res))
+            prog.add(d.z_proj.forward([r.z, pa[res]], [SegSpec(r.h3, 0, add=h, add2=r.pfeat)], N, res, res))
             r.conv = self._block_fwd(prog, d.conv, [r.h3], N, res, res)
             h = r.conv.y
             r.zs_out = None
@@ -362,7 +362,7 @@ class Engine:
         dy = dout
         if st is not None and getattr(st, "down", None):
             dy = new_act(N, H, W, r.y.logical, self.device)
-            prog.call("cg_avgpool_bwd", dout.ptr, dy.ptr, N, H, W, dy.C, st.down, dout.ld, dy.ld, st.res_out, 0)
+            prog.call("cg_avgpool_bwd", dout.ptr, dy.ptr, N, H, W, dy.C, st.down, dout.ns, dy.ns, st.res_out, 0)
         x = r.srcs[0]
         dx = new_act(N, H, W, x.logical, self.device)
         if bl.proj is not None:
@@ -371,7 +371,7 @@ class Engine:
             prog.add(bl.proj.dgrad(0, dy, SegSpec(skip, 0, add=extra), N, H, W))
         elif extra is not None:
             skip = new_act(N, H, W, x.logical, self.device)
-            prog.call("cg_add", dy.ptr, extra.ptr, skip.ptr, N * H * W, skip.C, dy.ld, extra.ld, skip.ld)
+            prog.call("cg_add", dy.ptr, extra.ptr, skip.ptr, N, H * W, skip.C, dy.ns, extra.ns, skip.ns)
         else:
             skip = dy
         self._block_bwd(prog, r, dy, [SegSpec(dx, 0, add=skip)])
@@ -400,24 +400,24 @@ class Engine:
                 dz_written = True
                 prog.add(d.zfp.dgrad(1, dzs_out, SegSpec(dpf, 0, add=dh3), N, res, res))
             else:
-                w = st.cin
-                prog.add(PyOp(lambda a=DP.t, b=dh3.t, w=w, o=2 * zd: a[..., o:o + w].copy_(b[..., :w]), "copy_dpfeat"))
+                w8, o8 = round16(st.cin) // 8, (2 * zd) // 8
+                prog.add(PyOp(lambda a=DP.t, b=dh3.t, w8=w8, o8=o8: a[:, o8:o8 + w8].copy_(b[:, :w8]), "copy_dpfeat"))
             # z_proj (no activation on its input)
             prog.add(d.z_proj.wgrad([r.z, r.pa], dh3, self.g(d.z_proj.weight), self.g(d.z_proj.bias), N, res, res))
             prog.add(d.z_proj.dgrad(0, dh3, SegSpec(dz, 0, add=dz if dz_written else None), N, res, res))
             # latent
             lb = L.LatentBwdArgs()
-            lb.p, lb.p_ld = r.pstat.ptr, r.pstat.ld
+            lb.p, lb.p_ld = r.pstat.ptr, r.pstat.ns
             dq = None
             if r.mode == 0:
                 dq = new_act(N, res, res, 2 * zd, self.device)
-                lb.q, lb.q_ld = r.qstat.ptr, r.qstat.ld
-                lb.dq, lb.dq_ld = dq.ptr, dq.ld
+                lb.q, lb.q_ld = r.qstat.ptr, r.qstat.ns
+                lb.dq, lb.dq_ns = dq.ptr, dq.ns
                 if explicit_eps:
                     lb.eps = r.eps.data_ptr()
                 lb.offset = r.ksto << 40
-            lb.dz, lb.dz_ld, lb.g_kl = dz.ptr, dz.ld, g_kl
-            lb.dp, lb.dp_ld = DP.ptr, DP.ld
+            lb.dz, lb.dz_ns, lb.g_kl = dz.ptr, dz.ns, g_kl
+            lb.dp, lb.dp_ns = DP.ptr, DP.ns
             lb.N, lb.HW, lb.zdim, lb.mode = N, res * res, zd, r.mode
             prog.add(L.Launch("cg_latent_bwd", C.byref(lb))).keep = (lb, dz, DP, dq)
             D.latent_bwd_args.append(lb)
@@ -450,26 +450,26 @@ class Engine:
                 src_res, h_prev, zs_prev, b = r.up
                 dbias = self.g(b).data_ptr() if b is not None else None
                 dh_prev = new_act(N, src_res, src_res, st.cin, self.device)
-                prog.call("cg_upsample_bwd", dh_in.ptr, dh_prev.ptr, dbias, N, src_res, res, st.cin, dh_in.ld,
-                          dh_prev.ld, 0)
+                prog.call("cg_upsample_bwd", dh_in.ptr, dh_prev.ptr, dbias, N, src_res, res, st.cin, dh_in.ns,
+                          dh_prev.ns, 0)
                 dzs_prev = None
                 if dzs_in is not None:
                     if zs_prev is h_prev:  # first block: h and z are the same tensor
                         prog.call("cg_upsample_bwd", dzs_in.ptr, dh_prev.ptr, dbias, N, src_res, res, st.cin,
-                                  dzs_in.ld, dh_prev.ld, 1)
+                                  dzs_in.ns, dh_prev.ns, 1)
                     else:
                         dzs_prev = new_act(N, src_res, src_res, st.cin, self.device)
                         prog.call("cg_upsample_bwd", dzs_in.ptr, dzs_prev.ptr, dbias, N, src_res, res, st.cin,
-                                  dzs_in.ld, dzs_prev.ld, 0)
+                                  dzs_in.ns, dzs_prev.ns, 0)
                 dh_out, dzs_out = dh_prev, dzs_prev
             else:
                 dh_out, dzs_out = dh_in, dzs_in
         # initial state h = z = bias[1] (src/vae.py:232)
         g1 = self.g(bias_param[1])
         w1 = dec.plan[0].cin
-        prog.call("cg_colsum", dh_out.ptr, g1.data_ptr(), N, w1, dh_out.ld)
+        prog.call("cg_colsum", dh_out.ptr, g1.data_ptr(), N, 1, w1, dh_out.ns)
         if dzs_out is not None:
-            prog.call("cg_colsum", dzs_out.ptr, g1.data_ptr(), N, w1, dzs_out.ld)
+            prog.call("cg_colsum", dzs_out.ptr, g1.data_ptr(), N, 1, w1, dzs_out.ns)
 
     def _encoder_bwd(self, prog: Program, e: Rec, acts_grad: Dict[int, View], N):
         enc = self.model.encoder
@@ -486,13 +486,13 @@ class Engine:
             if extra is not None:
                 # d(out) = d(next block input) + d(acts[res]); fold the sum into one tensor first
                 s = new_act(N, r.st.res_out, r.st.res_out, r.out.logical, self.device)
-                prog.call("cg_add", dout.ptr, extra.ptr, s.ptr, N * r.st.res_out * r.st.res_out, s.C, dout.ld,
-                          extra.ld, s.ld)
+                prog.call("cg_add", dout.ptr, extra.ptr, s.ptr, N, r.st.res_out * r.st.res_out, s.C, dout.ns,
+                          extra.ns, s.ns)
                 dout = s
             din_next = self._res_block_bwd(prog, r, dout)
         if din_next is not None:
             prog.call("cg_stem_wgrad", e.x.data_ptr(), din_next.ptr, self.g(enc.stem.weight).data_ptr(),
-                      self.g(enc.stem.bias).data_ptr(), N, self.C, self.R, self.args.widths[0], din_next.ld)
+                      self.g(enc.stem.bias).data_ptr(), N, self.C, self.R, self.args.widths[0], din_next.ns)
 
     # ================================================================== likelihood
     def _lik_args(self, h: View, x: Optional[torch.Tensor], N):
@@ -500,13 +500,13 @@ class Engine:
         HW = self.R * self.R
         if self.dmol:
             a = L.DmolArgs()
-            a.h, a.h_ld, a.Cw = h.ptr, h.ld, self.args.widths[0]
+            a.h, a.h_ns, a.Cw = h.ptr, h.ns, self.args.widths[0]
             a.x = x.data_ptr() if x is not None else None
             a.w, a.b = lik.conv.weight.data_ptr(), lik.conv.bias.data_ptr()
             a.N, a.HW = N, HW
             return a
         a = L.DGaussArgs()
-        a.h, a.h_ld, a.Cw = h.ptr, h.ld, self.args.widths[0]
+        a.h, a.h_ns, a.Cw = h.ptr, h.ns, self.args.widths[0]
         a.x = x.data_ptr() if x is not None else None
         a.w_loc, a.b_loc = lik.x_loc.weight.data_ptr(), lik.x_loc.bias.data_ptr()
         a.w_ls, a.b_ls = lik.x_logscale.weight.data_ptr(), lik.x_logscale.bias.data_ptr()
@@ -517,25 +517,32 @@ class Engine:
 
     # ================================================================== programs
     def _inputs(self, prog: Program, N, with_x=True, n_pa=1):
+        """static input buffers.  Parents arrive as (N, ctx); they are materialised per decoder resolution as
+        spatially-constant planar tensors (= parents[..., :res, :res] of src/vae.py:241, in bf16)."""
         io = Rec()
         if with_x:
             io.x = torch.zeros(N, self.C, self.R, self.R, device=self.device, dtype=torch.float32)
         io.pa_in = [torch.zeros(N, self.ctx, device=self.device, dtype=torch.float32) for _ in range(n_pa)]
-        io.pa = []
-        io.pa_sto = []
-        io.drop_launch = []
+        io.pa, io.pa_sto, io.drop_launch = [], [], []
+        resolutions = sorted({d.st.res for d in self.dec_layers})
+        drop = self.model.decoder.is_drop_cond and self.cond_prior
         for t in io.pa_in:
-            v = View(torch.zeros(N, self.ctx_pad, device=self.device, dtype=torch.bfloat16), self.ctx_pad, 0, self.ctx,
-                     bcast=True)
-            prog.call("cg_parents_pack", t.data_ptr(), self.ctx, 1, v.ptr, N, self.ctx, self.ctx_pad, self.ctx, 1.0)
-            io.pa.append(v)
-            if self.model.decoder.is_drop_cond:  # src/vae.py:244-247: channels 2: scaled by p_sto
-                vs = View(torch.zeros_like(v.t), self.ctx_pad, 0, self.ctx, bcast=True)
-                ln = prog.call("cg_parents_pack", t.data_ptr(), self.ctx, 1, vs.ptr, N, self.ctx, self.ctx_pad, 2, 1.0)
-                io.drop_launch.append(ln)
-                io.pa_sto.append(vs)
-            else:
-                io.pa_sto.append(v)
+            planes, planes_sto = {}, {}
+            for res in resolutions:
+                v = new_act(N, res, res, self.ctx, self.device)
+                prog.call("cg_parents_plane", t.data_ptr(), self.ctx, 1, v.ptr, N, self.ctx, v.C, res * res, v.ns,
+                          self.ctx, 1.0)
+                planes[res] = v
+                if drop:  # src/vae.py:244-247: channels 2: scaled by p_sto on the stochastic (prior) path
+                    vs = new_act(N, res, res, self.ctx, self.device)
+                    ln = prog.call("cg_parents_plane", t.data_ptr(), self.ctx, 1, vs.ptr, N, self.ctx, vs.C, res * res,
+                                   vs.ns, 2, 1.0)
+                    io.drop_launch.append(ln)
+                    planes_sto[res] = vs
+                else:
+                    planes_sto[res] = v
+            io.pa.append(planes)
+            io.pa_sto.append(planes_sto)
         return io
 
     def build_elbo(self, N: int, train: bool, explicit_eps: bool) -> Program:
@@ -553,7 +560,7 @@ class Engine:
                               kl_rows=prog.kl_rows)
         k = 0
         for r in D.blocks:
-            r.pa = io.pa[0]
+            r.pa = io.pa[0][r.st.res]
             r.ksto = k
             if r.st.stochastic:
                 k += 1
@@ -573,7 +580,7 @@ class Engine:
             dh = new_act(N, self.R, self.R, self.args.widths[0], self.device)
             lb = self._lik_args(D.h, io.x, N)
             lb.g = 1.0 / N
-            lb.dh, lb.dh_ld = dh.ptr, dh.ld
+            lb.dh, lb.dh_ns = dh.ptr, dh.ns
             if self.dmol:
                 lb.dw, lb.db = self.g(lik.conv.weight).data_ptr(), self.g(lik.conv.bias).data_ptr()
                 prog.add(L.Launch("cg_dmol_loss_bwd", C.byref(lb))).keep = (lb, dh)

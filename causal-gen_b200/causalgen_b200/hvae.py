@@ -232,7 +232,7 @@ class HVAE(nn.Module):
     def _stat_nchw(self, stat, c0: int, add: float) -> Tensor:
         N, H, W, _ = stat.t.shape
         out = torch.empty(N, 16, H, W, device=stat.t.device, dtype=torch.float32)
-        L.check(L.load().cg_stats_to_nchw(stat.ptr, stat.ld, c0, float(add), out.data_ptr(), N, 16, H * W,
+        L.check(L.load().cg_stats_to_nchw(stat.ptr, stat.ns, c0, float(add), out.data_ptr(), N, 16, H * W,
                                           _stream()), "cg_stats_to_nchw")
         return out
 

@@ -17,38 +17,74 @@ def round16(c: int) -> int:
 
 
 class View:
-    """Channel slice [c0, c0+C) of an NHWC tensor (N,H,W,ld) -- or of a per-sample vector (N,ld)
-    when ``bcast`` (spatially constant parents).  ``C`` is the padded channel count (multiple of 8)."""
-    __slots__ = ("t", "c0", "C", "logical", "bcast")
+    """Channel slice [c0, c0+C) of an activation tensor.
 
-    def __init__(self, t: torch.Tensor, C: Optional[int] = None, c0: int = 0, logical: Optional[int] = None,
-                 bcast: bool = False):
+    bf16 activations are channel-octet planar: t has shape (N, Ctot/8, H, W, 8); element (n,c,h,w) lives at
+    n*ns + (c//8)*H*W*8 + (h*W+w)*8 + c%8.  A slice with c0 % 8 == 0 keeps the same sample stride ``ns`` and
+    only advances the base pointer, so it is a valid kernel operand without a copy.
+    fp32 statistics tensors keep a row layout (N, H, W, ld); for those ``ns`` is the row pitch."""
+    __slots__ = ("t", "c0", "C", "logical")
+
+    def __init__(self, t: torch.Tensor, C: Optional[int] = None, c0: int = 0, logical: Optional[int] = None):
         self.t = t
         self.c0 = c0
-        self.C = t.shape[-1] - c0 if C is None else C
+        full = t.shape[1] * 8 if self.planar_dtype(t) else t.shape[-1]
+        self.C = full - c0 if C is None else C
         self.logical = self.C if logical is None else logical
-        self.bcast = bcast
+        assert c0 % 8 == 0 and self.C % 8 == 0
+
+    @staticmethod
+    def planar_dtype(t) -> bool:
+        return t.dtype == torch.bfloat16
 
     @property
-    def ld(self) -> int:
-        return self.t.shape[-1]
+    def planar(self) -> bool:
+        return self.planar_dtype(self.t)
+
+    @property
+    def HW(self) -> int:
+        return self.t.shape[2] * self.t.shape[3] if self.planar else self.t.shape[1] * self.t.shape[2]
+
+    @property
+    def ns(self) -> int:
+        return self.t.stride(0) if self.planar else self.t.shape[-1]
 
     @property
     def ptr(self) -> int:
+        if self.planar:
+            return self.t.data_ptr() + (self.c0 // 8) * self.HW * 8 * 2
         return self.t.data_ptr() + self.c0 * self.t.element_size()
 
-    @property
-    def rows(self) -> int:
-        return self.t.numel() // self.t.shape[-1]
-
     def slice(self, c0: int, C: int, logical: Optional[int] = None) -> "View":
-        return View(self.t, C, self.c0 + c0, logical, self.bcast)
+        return View(self.t, C, self.c0 + c0, logical)
+
+    def nchw(self) -> torch.Tensor:
+        """(N, C, H, W) float copy of the logical channels (tests / debugging only)"""
+        if self.planar:
+            N, C8, H, W, _ = self.t.shape
+            full = self.t.permute(0, 1, 4, 2, 3).reshape(N, C8 * 8, H, W)
+        else:
+            full = self.t.permute(0, 3, 1, 2)
+        return full[:, self.c0: self.c0 + self.logical].float()
 
 
 def new_act(N, H, W, C, device, dtype=torch.bfloat16, logical=None) -> View:
-    """zero-initialised NHWC buffer; padded channels stay zero/finite for the tensor-core K loop"""
+    """zero-initialised planar buffer; padded channels stay zero for the tensor-core K loop"""
     Cp = round16(C)
-    return View(torch.zeros(N, H, W, Cp, device=device, dtype=dtype), Cp, 0, C if logical is None else logical)
+    if dtype == torch.bfloat16:
+        t = torch.zeros(N, Cp // 8, H, W, 8, device=device, dtype=dtype)
+    else:
+        t = torch.zeros(N, H, W, Cp, device=device, dtype=dtype)
+    return View(t, Cp, 0, C if logical is None else logical)
+
+
+def planar_from_nchw(x: torch.Tensor, pad_to: Optional[int] = None) -> torch.Tensor:
+    """(N,C,H,W) float -> zero padded planar bf16 tensor (tests / debugging only)"""
+    N, Cc, H, W = x.shape
+    Cp = pad_to or round16(Cc)
+    full = torch.zeros(N, Cp, H, W, device=x.device, dtype=torch.bfloat16)
+    full[:, :Cc] = x.to(torch.bfloat16)
+    return full.reshape(N, Cp // 8, 8, H, W).permute(0, 1, 3, 4, 2).contiguous()
 
 
 @dataclass
@@ -144,21 +180,21 @@ class ConvLayer:
     @staticmethod
     def _fill_srcs(arr, srcs: Sequence[View]):
         for i, s in enumerate(srcs):
-            arr[i].ptr, arr[i].C, arr[i].ld, arr[i].bcast = s.ptr, s.C, s.ld, int(s.bcast)
+            arr[i].ptr, arr[i].ns, arr[i].C = s.ptr, s.ns, s.C
 
     @staticmethod
     def _fill_segs(a, segs: Sequence[SegSpec]):
         a.nseg = len(segs)
         for i, sg in enumerate(segs):
             s = a.seg[i]
-            s.ptr, s.c0, s.cn, s.ld = sg.out.ptr, sg.c0, sg.out.C, sg.out.ld
+            s.ptr, s.c0, s.cn, s.ns = sg.out.ptr, sg.c0, sg.out.C, sg.out.ns
             s.dtype = L.F32 if sg.out.t.dtype == torch.float32 else L.BF16
             s.add = sg.add.ptr if sg.add is not None else None
-            s.add_ld = sg.add.ld if sg.add is not None else 0
+            s.add_ns = sg.add.ns if sg.add is not None else 0
             s.add2 = sg.add2.ptr if sg.add2 is not None else None
-            s.add2_ld = sg.add2.ld if sg.add2 is not None else 0
+            s.add2_ns = sg.add2.ns if sg.add2 is not None else 0
             s.mul = sg.mul.ptr if sg.mul is not None else None
-            s.mul_ld = sg.mul.ld if sg.mul is not None else 0
+            s.mul_ns = sg.mul.ns if sg.mul is not None else 0
             s.mul_act = sg.mul_act
 
     def forward(self, srcs: Sequence[View], segs: Sequence[SegSpec], N, H, W) -> L.Launch:
@@ -193,7 +229,7 @@ class ConvLayer:
         a.N, a.H, a.W, a.ksize, a.act = N, H, W, self.k, self.act
         a.nsrc = len(srcs)
         self._fill_srcs(a.src, srcs)
-        a.dy, a.dy_c, a.dy_ld = dy.ptr, dy.C, dy.ld
+        a.dy, a.dy_c, a.dy_ns = dy.ptr, dy.C, dy.ns
         a.dw = dw.data_ptr()
         a.dbias = db.data_ptr() if db is not None else None
         a.cout_l, a.cin_l, a.taps = self.cout_l, self.cin_l, self.taps

@@ -33,6 +33,10 @@ int cg_require_sm100();  // CG_OK or CG_ERR_ARCH
     }                                                                           \
   } while (0)
 
+// TMA tensor map (CUtensorMap, 128 B) over a planar bf16 view; see conv_tc.cu
+int cg_make_planar_map(void* map_out, const void* ptr, long long ns, int N, int H, int W, int C8, int flat, int box_w8,
+                       int box_h, int box_c8);
+
 static inline cudaStream_t cg_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int cg_ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

@@ -1,33 +1,33 @@
 // Implicit-GEMM convolution on tcgen05 (sm_100a): forward and data-gradient pass of every
 // nn.Conv2d in Block / DecoderBlock (reference src/vae.py:49-84,165-170).
 //
-//   GEMM view   D[M=128 pixels][N=Cout chunk] += A[pixels][K] * B[Cout][K],  K = taps * Cin
-//   A operand   one halo tile of the NHWC bf16 input per K-chunk of 32 channels, staged as channel-octet
-//               planes [c8][18 rows][10 px][8 ch]; because 8 consecutive pixels of a plane row are one
-//               128-byte UMMA core matrix (SWIZZLE_NONE, K-major), every one of the 9 taps is just a
-//               different descriptor start address into the SAME tile -- im2col without copies.
-//   rows        the batch is viewed as one tall image of N*(H+1) "virtual rows" (one shared zero row
-//               between images) so a 16x8-pixel tile has a constant row pitch for any H.
-//   B operand   packed weights for the CTA's Cout chunk, bulk-copied (cp.async.bulk) into shared
-//               memory once and kept resident while the persistent CTA walks its pixel tiles.
+//   layout      activations are bf16 "channel-octet planar": (N, C/8, H, W, 8).  One TMA box
+//               (8*10 elements x 18 rows x 4 octets) of that tensor lands in shared memory EXACTLY as the
+//               UMMA SWIZZLE_NONE K-major operand: channel-octet planes [c8][18 rows][10 px][8 ch] in which 8
+//               consecutive pixels of a row are one 128-byte core matrix.  Image borders are zero-filled by
+//               the TMA unit (out-of-bounds box coordinates), so "same" padding costs nothing.
+//   GEMM view   D[M=128 pixels (16x8 tile)][N=Cout chunk] += A[pixels][K] * B[Cout][K],  K = taps * Cin.
+//               Every one of the 9 taps is just a different descriptor start address (+(kh*10+kw)*16 B)
+//               into the SAME halo tile -- im2col without copies.
+//   B operand   packed weights for the CTA's Cout chunk, bulk-copied (cp.async.bulk) into shared memory once
+//               and kept resident while the persistent CTA walks its pixel tiles.
 //   D           fp32 in TMEM, double buffered (2 x Nc columns, Nc <= 64; wider outputs are split over
 //               blockIdx.y) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //   epilogue    bias, channel-split segments, act'(x) multiply (backward), residual / accumulate adds,
-//               bf16 or fp32 stores.  The tensors the epilogue READS (residual, pre-activation) are staged
-//               through shared memory ("E stages") by the same producer pipeline, up to 3 tiles ahead.
+//               bf16 (planar, 128-byte coalesced per octet) or fp32 (row) stores.  The tensors the epilogue
+//               READS (residual, pre-activation) are TMA-staged too ("E stages"), up to 3 tiles ahead.
 //
-// Producer pipeline.  Measured on B200 (profiles/r1c): mbarrier arrivals are the scarce resource -- 256
-// per-thread arrivals per stage cost ~0.6 us -- so every hand-off here is ONE arrival:
-//   stage-owner warps  warp w owns ring stage w: it alone issues all cp.async (LDGSTS, zero-fill padding) of a
-//                      K-chunk, waits for its own copies (wait_group 0), applies the pre-activation in place,
-//                      fence.proxy.async, then one lane publishes the stage.  kStages warps work on kStages
-//                      different chunks concurrently, so global latency overlaps across warps.
-//   E-owner warps      same idea for the epilogue-operand ring (one warp per E stage)
-//   MMA warp           one thread issues tcgen05.mma; tcgen05.commit frees the stage / signals the epilogue
-//   epilogue warps     TMEM -> registers -> global
+// Pipeline (every hand-off is one mbarrier arrival or a TMA transaction count -- measured on B200,
+// profiles/r1c: per-thread arrivals and per-slot address arithmetic, not memory, were the bottleneck):
+//   producer warp    one thread: wait stage free -> expect_tx -> cp.async.bulk.tensor (A chunk / E operands)
+//   transform warps  wait "landed", apply the pre-activation (ReLU/GELU) in place, fence.proxy.async, publish
+//                    (skipped entirely when the conv has no input activation: the MMA waits on "landed")
+//   MMA warp         one thread issues tcgen05.mma; tcgen05.commit frees the stage / signals the epilogue
+//   epilogue warps   TMEM -> registers -> global
 //
-// Warp roles: 0-3 epilogue (TMEM lane quarters), 4 MMA issuer + TMEM owner, 5-10 A-stage owners,
-//             11-13 E-stage owners.
+// Warp roles: 0-3 epilogue (TMEM lane quarters), 4 MMA issuer + TMEM owner, 5 TMA producer, 6-9 transform.
+#include <cuda.h>
+
 #include <cstdlib>
 
 #include "cg_common.cuh"
@@ -36,67 +36,71 @@ namespace {
 
 constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = 4;
+constexpr int kTmaWarp = 5;
+constexpr int kXfWarp0 = 6;
+constexpr int kXfWarps = 4;
+constexpr int kThreads = (kXfWarp0 + kXfWarps) * 32;  // 320
+constexpr int kXfThreads = kXfWarps * 32;
 constexpr int kStages = 6;
-constexpr int kOwnWarp0 = 5;                 // warps 5..10 own A stages 0..5
-constexpr int kEStages = 3;                  // epilogue-operand ring depth
-constexpr int kEWarp0 = kOwnWarp0 + kStages; // warps 11..13 own E stages 0..2
-constexpr int kThreads = (kEWarp0 + kEStages) * 32;  // 448
-constexpr int kPlane3 = 2976;  // 18*10*16 = 2880, padded so the 4 planes of a stage hit distinct banks
-constexpr int kPlane1 = 2080;  // 128*16   = 2048, same padding rule
-constexpr int kStageBytes = 4 * kPlane3;
+constexpr int kPlane3 = 2880;  // 18 rows * 10 px * 16 B
+constexpr int kPlane1 = 2048;  // 16 rows *  8 px * 16 B
+constexpr int kStageBytes = 4 * kPlane3;  // 11520 (multiple of 128: TMA destination alignment)
 constexpr int kHdrBytes = 1408;   // barriers (<=256B) | tmem slot @256 | bias[256] @320
 constexpr int kSmemMax = 232448;  // 227 KB
 constexpr int kMaxChunks = 40;
 constexpr int kMaxNc = 64;        // GEMM-N per CTA
+constexpr int kEStages = 3;       // epilogue-operand ring depth
 constexpr int kESlots = 2;        // staged operands per tile
-// a staged operand tile is [128 pixel rows][Nc channels] bf16 with a 16-byte row pad (bank spread)
-__host__ __device__ constexpr int e_pitch(int nc) { return nc * 2 + 16; }
-__host__ __device__ constexpr int e_slot_bytes(int nc) { return 128 * e_pitch(nc); }
+// a staged operand tile is [Nc/8 octets][16 rows][8 px][8 ch] bf16 = Nc/8 planes of 2048 B
+__host__ __device__ constexpr int e_slot_bytes(int nc) { return (nc / 8) * kPlane1; }
 __host__ __device__ constexpr int e_bytes(int nc) { return kEStages * kESlots * e_slot_bytes(nc); }
 
 // barrier indices
-constexpr int B_AFULL = 0, B_AEMPTY = kStages, B_BFULL = 2 * kStages,
+constexpr int B_LANDED = 0, B_AFULL = kStages, B_AEMPTY = 2 * kStages, B_BFULL = 3 * kStages,
               B_ACCFULL = B_BFULL + 1, B_ACCEMPTY = B_ACCFULL + 2, B_EFULL = B_ACCEMPTY + 2,
               B_EEMPTY = B_EFULL + kEStages, B_COUNT = B_EEMPTY + kEStages;
 static_assert(B_COUNT * 8 <= 256, "barrier block overflows the header");
 
 struct Chunk {
-  uint16_t src, c0, nc16, kbase;
+  uint16_t src, oct0, nc16, kbase;  // source index, first channel octet, K-blocks of 16 (1 or 2), first K-block
 };
 
-struct EOp {           // one epilogue input staged through shared memory
-  const void* ptr;     // bf16 tensor
-  int ld, seg, kind;   // kind: 0 add, 1 add2, 2 mul
+struct EOp {  // one epilogue input staged through shared memory
+  int seg, kind;  // kind: 0 add, 1 add2, 2 mul
+  int oct_off;    // (first output channel of the segment) / 8
 };
 
-struct KParams {
+struct alignas(64) KParams {
+  CUtensorMap src_map[CG_MAX_SRC];
+  CUtensorMap e_map[kESlots];
   cg_conv_args a;
   Chunk chunk[kMaxChunks];
   EOp eop[kESlots];
+  uint32_t src_bytes[CG_MAX_SRC];  // TMA transaction bytes of one A box per source
   int nE, emode;
   int nchunks, ntaps, Nc, nN, ktot16;
-  int tiles_x, ntiles, Hp, V;
-  uint32_t hp_magic;            // floor(2^32/(H+1))+1: exact n = v/(H+1) for v < 2^24, H < 256
-  long long P;                  // N*H*W
-  uint32_t idesc, tmem_cols, slab_bytes;
-  int dbg;  // CG_DEBUG_SKIP bit mask (profiling experiments only): 1 no cp.async, 2 no act, 4 no mma, 8 no epilogue stores
+  int flat;  // 1: H=W=1, samples are the GEMM rows (128 per tile)
+  int tiles_x, tiles_per_img, ntiles;
+  long long HW8;  // H*W*8: elements per channel-octet plane
+  uint32_t idesc, tmem_cols, slab_bytes, e_tx_bytes;
+  int dbg;  // CG_DEBUG_SKIP bit mask (profiling experiments only): 2 no act, 4 no mma, 8 no epilogue stores
 };
 
 struct TileGeom {
-  int v0, w0;       // 3x3: first virtual row / column of the tile
-  long long p0;     // 1x1: first flat pixel
+  int n, h0, w0;
 };
 
 __device__ __forceinline__ TileGeom tile_geom(const KParams& P, int tile) {
   TileGeom g;
-  if (P.a.ksize == 3) {
-    int tv = tile / P.tiles_x;
-    g.v0 = tv * 16;
-    g.w0 = (tile - tv * P.tiles_x) * 8;
-    g.p0 = 0;
+  if (P.flat) {
+    g.n = tile * 128;
+    g.h0 = g.w0 = 0;
   } else {
-    g.v0 = g.w0 = 0;
-    g.p0 = (long long)tile * 128;
+    g.n = tile / P.tiles_per_img;
+    const int r = tile - g.n * P.tiles_per_img;
+    const int ty = r / P.tiles_x;
+    g.h0 = ty * 16;
+    g.w0 = (r - ty * P.tiles_x) * 8;
   }
   return g;
 }
@@ -105,6 +109,25 @@ __device__ __forceinline__ TileGeom tile_geom(const KParams& P, int tile) {
 __device__ __forceinline__ void warp_wait(uint32_t bar, uint32_t parity, int lane) {
   if (lane == 0) mbar_wait(bar, parity);
   __syncwarp();
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::
+          "r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
+          "r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
 __device__ __forceinline__ uint4 act8(uint4 u, int act) {
@@ -130,17 +153,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   uint8_t* sA = smem + kHdrBytes;
   uint8_t* sE = sA + kStages * kStageBytes;
   uint8_t* sB = sE + (P.emode ? e_bytes(P.Nc) : 0);
-  const int epitch = e_pitch(P.Nc), eslot = e_slot_bytes(P.Nc);
+  const int eslot = e_slot_bytes(P.Nc);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunkN = blockIdx.y;
   const int Nc = P.Nc;
   const uint32_t bar0 = cg_smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
+  const int act = (P.dbg & 2) ? CG_ACT_NONE : P.a.act;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(BAR(B_AFULL + i), 1);
+      mbar_init(BAR(B_LANDED + i), 1);
+      mbar_init(BAR(B_AFULL + i), kXfWarps);
       mbar_init(BAR(B_AEMPTY + i), 1);
     }
     mbar_init(BAR(B_BFULL), 1);
@@ -165,7 +190,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   const bool k3 = P.a.ksize == 3;
   const int plane = k3 ? kPlane3 : kPlane1;
-  const int npix = k3 ? 180 : 128;
   const int H = P.a.H, W = P.a.W, N = P.a.N;
 
   if (warp == kMmaWarp) {
@@ -179,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
       mbar_wait(BAR(B_BFULL), 0);
       // Descriptors are built once; per MMA only the 14-bit start-address field (low word) advances
-      // (all offsets are multiples of 16 B): ~4 instructions per tcgen05.mma for the issuing thread.
+      // (all offsets are multiples of 16 B).
       const uint32_t a_sbo = k3 ? 160u : 128u;
       const uint64_t a_d = umma_desc(cg_smem_u32(sA), (uint32_t)plane, a_sbo);
       const uint64_t b_d = umma_desc(cg_smem_u32(sB), (uint32_t)Nc * 16u, 128u);
@@ -190,6 +214,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t plane2_16 = (uint32_t)(2 * plane) >> 4;
       const uint32_t stage16 = (uint32_t)kStageBytes >> 4;
       const uint32_t idesc = P.idesc;
+      const int ready0 = (act == CG_ACT_NONE) ? B_LANDED : B_AFULL;  // no activation: consume TMA data directly
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
         mbar_wait(BAR(B_ACCEMPTY + as), aphase ^ 1u);
@@ -198,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         uint32_t accum = 0;
         for (int c = 0; c < P.nchunks; ++c) {
           const Chunk ch = P.chunk[c];
-          mbar_wait(BAR(B_AFULL + stage), phase);
+          mbar_wait(BAR(ready0 + stage), phase);
           tc_fence_after();
           uint32_t alo = a_lo0 + stage * stage16;
           uint32_t blo = b_lo0 + (uint32_t)ch.kbase * b_step16;
@@ -224,101 +249,54 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
-  } else if (warp >= kEWarp0) {
-    // ------------------------------------------------------------------ E-stage owner warps
-    // warp e stages the tensors the epilogue of tiles e, e+3, e+6 ... (of this CTA) will read: residual /
-    // pre-activation rows of the 128 output pixels x Nc channels
-    const int nE = P.nE;
-    if (nE > 0) {
-      const int es = warp - kEWarp0;
-      const int ncE8 = Nc >> 3;  // channel octets per staged operand row
-      const int items = 128 * ncE8;
-      uint32_t ephase = 0;
-      int tseq = 0;
-      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++tseq) {
-        if (tseq % kEStages != es) continue;
+  } else if (warp == kTmaWarp) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int s = 0; s < P.a.nsrc; ++s) tma_prefetch_desc(&P.src_map[s]);
+      for (int k = 0; k < P.nE; ++k) tma_prefetch_desc(&P.e_map[k]);
+      uint32_t stage = 0, phase = 0, es = 0, ephase = 0;
+      const int halo = k3 ? 1 : 0;
+      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
         const TileGeom g = tile_geom(P, tile);
-        warp_wait(BAR(B_EEMPTY + es), ephase ^ 1u, lane);
-        for (int k = 0; k < nE; ++k) {
-          const EOp& op = P.eop[k];
-          const cg_seg& sg = P.a.seg[op.seg];
-          const uint32_t dstE = cg_smem_u32(sE + (es * kESlots + k) * eslot);
-          for (int i = lane; i < items; i += 32) {
-            const int row = i / ncE8, oc = i - row * ncE8;
-            const int lc = nchunkN * Nc + oc * 8 - sg.c0;  // channel inside the segment
-            bool ok;
-            long long px;
-            if (k3) {
-              const int v = g.v0 + (row >> 3), w = g.w0 + (row & 7);
-              const int n = (int)__umulhi((uint32_t)v, P.hp_magic), h = v - n * P.Hp;
-              ok = (n < N) && (h < H) && (w < W);
-              px = (long long)(n * H + h) * W + w;
-            } else {
-              px = g.p0 + row;
-              ok = px < P.P;
-            }
-            if (ok && lc >= 0 && lc < sg.cn && !(P.dbg & 1))
-              cp_async16(dstE + row * epitch + oc * 16, reinterpret_cast<const bf16*>(op.ptr) + px * op.ld + lc, 16u);
+        if (P.nE > 0) {
+          mbar_wait(BAR(B_EEMPTY + es), ephase ^ 1u);
+          mbar_expect_tx(BAR(B_EFULL + es), P.e_tx_bytes);
+          for (int k = 0; k < P.nE; ++k) {
+            const uint32_t dst = cg_smem_u32(sE + (es * kESlots + k) * eslot);
+            const int oct = nchunkN * (Nc >> 3) - P.eop[k].oct_off;  // may be out of range: zero-filled
+            if (P.flat) tma_load_3d(dst, &P.e_map[k], 0, g.n, oct, BAR(B_EFULL + es));
+            else tma_load_4d(dst, &P.e_map[k], g.w0 * 8, g.h0, oct, g.n, BAR(B_EFULL + es));
           }
+          if (++es == kEStages) { es = 0; ephase ^= 1u; }
         }
-        cp_async_commit();
-        cp_async_wait<0>();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(B_EFULL + es));
-        ephase ^= 1u;
+        for (int c = 0; c < P.nchunks; ++c) {
+          const Chunk ch = P.chunk[c];
+          mbar_wait(BAR(B_AEMPTY + stage), phase ^ 1u);
+          mbar_expect_tx(BAR(B_LANDED + stage), P.src_bytes[ch.src]);
+          const uint32_t dst = cg_smem_u32(sA + stage * kStageBytes);
+          if (P.flat) tma_load_3d(dst, &P.src_map[ch.src], 0, g.n, ch.oct0, BAR(B_LANDED + stage));
+          else tma_load_4d(dst, &P.src_map[ch.src], (g.w0 - halo) * 8, g.h0 - halo, ch.oct0, g.n, BAR(B_LANDED + stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
       }
     }
-  } else if (warp >= kOwnWarp0) {
-    // ------------------------------------------------------------------ A-stage owner warps
-    const int st = warp - kOwnWarp0;  // the ring stage this warp owns
-    const int act = P.a.act;
-    uint8_t* const sbase = sA + st * kStageBytes;
-    const uint32_t sbase_u = cg_smem_u32(sbase);
-    const int nslots = npix * 4;
-    uint32_t phase = 0;
-    const long long nwork = (long long)((P.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1) * P.nchunks;
-    for (long long gidx = st; gidx < nwork; gidx += kStages) {
-      const int tseq = (int)(gidx / P.nchunks);
-      const Chunk ch = P.chunk[(int)(gidx - (long long)tseq * P.nchunks)];
-      const TileGeom g = tile_geom(P, (int)blockIdx.x + tseq * (int)gridDim.x);
-      const cg_src& s = P.a.src[ch.src];
-      const int nc8 = ch.nc16 * 2;
-      const bf16* base = reinterpret_cast<const bf16*>(s.ptr) + ch.c0;
-      warp_wait(BAR(B_AEMPTY + st), phase ^ 1u, lane);
-      if (!(P.dbg & 1)) {
-        for (int sl = lane; sl < nslots; sl += 32) {
-          const int c8 = sl & 3, pix = sl >> 2;
-          if (c8 >= nc8) continue;
-          bool valid;
-          long long off;
-          if (k3) {
-            const int rr = pix / 10, cc = pix - rr * 10;
-            const int v = g.v0 - 1 + rr, w = g.w0 - 1 + cc;
-            const int n = (int)__umulhi((uint32_t)max(v, 0), P.hp_magic), h = v - n * P.Hp;
-            valid = (v >= 0) && (w >= 0) && (w < W) && (n < N) && (h < H);
-            off = s.bcast ? (long long)n * s.ld : ((long long)(n * H + h) * W + w) * s.ld;
-          } else {
-            const long long p = g.p0 + pix;
-            valid = p < P.P;
-            off = s.bcast ? (long long)((uint32_t)min(p, P.P - 1) / (uint32_t)(H * W)) * s.ld : p * s.ld;
-          }
-          cp_async16(sbase_u + c8 * plane + pix * 16, valid ? base + off + c8 * 8 : base, valid ? 16u : 0u);
+  } else if (warp >= kXfWarp0) {
+    // ------------------------------------------------------------------ transform warps
+    if (act != CG_ACT_NONE) {
+      const int xt = threadIdx.x - kXfWarp0 * 32;
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+        for (int c = 0; c < P.nchunks; ++c) {
+          const int n16 = (int)(P.src_bytes[P.chunk[c].src] >> 4);  // 16-byte slots the TMA box filled
+          warp_wait(BAR(B_LANDED + stage), phase, lane);
+          uint4* base = reinterpret_cast<uint4*>(sA + stage * kStageBytes);
+          for (int i = xt; i < n16; i += kXfThreads) base[i] = act8(base[i], act);
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_AFULL + stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
-      cp_async_commit();
-      cp_async_wait<0>();  // this warp's copies only; the other owner warps keep their chunks in flight
-      if (act != CG_ACT_NONE && !(P.dbg & 2)) {
-        for (int sl = lane; sl < nslots; sl += 32) {
-          const int c8 = sl & 3;
-          if (c8 >= nc8) continue;
-          uint4* p = reinterpret_cast<uint4*>(sbase + c8 * plane + (sl >> 2) * 16);
-          *p = act8(*p, act);
-        }
-      }
-      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(B_AFULL + st));
-      phase ^= 1u;
     }
   } else {
     // ------------------------------------------------------------------ epilogue
@@ -334,20 +312,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
       const TileGeom g = tile_geom(P, tile);
       bool valid;
-      long long pix;
-      if (k3) {
-        const int v = g.v0 + (m >> 3), w = g.w0 + (m & 7);
-        const int n = (int)__umulhi((uint32_t)v, P.hp_magic), h = v - n * P.Hp;
-        valid = (n < N) && (h < H) && (w < W);
-        pix = (long long)(n * H + h) * W + w;
+      int n;
+      long long hw;  // pixel index inside the image
+      if (P.flat) {
+        n = g.n + m;
+        hw = 0;
+        valid = n < N;
       } else {
-        pix = g.p0 + m;
-        valid = pix < P.P;
+        const int h = g.h0 + (m >> 3), w = g.w0 + (m & 7);
+        n = g.n;
+        hw = (long long)h * W + w;
+        valid = (h < H) && (w < W);
       }
       if (nE > 0) warp_wait(BAR(B_EFULL + es), ephase, lane);
       warp_wait(BAR(B_ACCFULL + as), aphase, lane);
       tc_fence_after();
-      const uint8_t* e_row = sE + (size_t)(es * kESlots) * eslot + (size_t)m * epitch;
+      const uint8_t* e_row = sE + (size_t)(es * kESlots) * eslot + (size_t)m * 16;
       const uint32_t t_row = tmem_base + as * (uint32_t)Nc + ((uint32_t)(warp * 32) << 16);
       for (int col = 0; col < Nc; col += 16) {
         float acc[16];
@@ -366,16 +346,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = acc[i];
-          // operand fetch: staged tile row (shared memory) if the producers brought it, else global
-          auto fetch = [&](int kind, const void* gptr, int gld, int h8) -> uint4 {
+          // operand fetch: staged octet plane (shared memory) if the producer brought it, else global
+          auto fetch = [&](int kind, const void* gptr, long long gns, int h8) -> uint4 {
             const int k = slot_of(sgi, kind);
-            if (k >= 0) return *reinterpret_cast<const uint4*>(e_row + (size_t)k * eslot + (col + h8) * 2);
-            return *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(gptr) + pix * gld + lc + h8);
+            if (k >= 0) return *reinterpret_cast<const uint4*>(e_row + (size_t)k * eslot + ((col + h8) >> 3) * kPlane1);
+            return *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(gptr) + n * gns +
+                                                   ((lc + h8) >> 3) * P.HW8 + hw * 8);
           };
           if (sg.mul != nullptr) {
             for (int h8 = 0; h8 < cnt; h8 += 8) {
               float x[8];
-              cg_unpack8(fetch(2, sg.mul, sg.mul_ld, h8), x);
+              cg_unpack8(fetch(2, sg.mul, sg.mul_ns, h8), x);
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[h8 + i] *= cg_dact(x[i], sg.mul_act);
             }
@@ -383,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           if (sg.add != nullptr) {
             for (int h8 = 0; h8 < cnt; h8 += 8) {
               float x[8];
-              cg_unpack8(fetch(0, sg.add, sg.add_ld, h8), x);
+              cg_unpack8(fetch(0, sg.add, sg.add_ns, h8), x);
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[h8 + i] += x[i];
             }
@@ -391,18 +372,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           if (sg.add2 != nullptr) {
             for (int h8 = 0; h8 < cnt; h8 += 8) {
               float x[8];
-              cg_unpack8(fetch(1, sg.add2, sg.add2_ld, h8), x);
+              cg_unpack8(fetch(1, sg.add2, sg.add2_ns, h8), x);
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[h8 + i] += x[i];
             }
           }
-          if (sg.dtype == CG_F32) {
-            float* op = reinterpret_cast<float*>(sg.ptr) + pix * sg.ld + lc;
+          if (sg.dtype == CG_F32) {  // fp32 statistics: row layout (pixel, channel), pitch ns
+            float* op = reinterpret_cast<float*>(sg.ptr) + ((long long)n * H * W + hw) * sg.ns + lc;
             for (int q = 0; q < cnt; q += 4)
               *reinterpret_cast<float4*>(op + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
-          } else {
-            bf16* op = reinterpret_cast<bf16*>(sg.ptr) + pix * sg.ld + lc;
-            for (int h8 = 0; h8 < cnt; h8 += 8) *reinterpret_cast<uint4*>(op + h8) = cg_pack8(v + h8);
+          } else {  // bf16 planar: 8 lanes of a tile row write one contiguous 128-byte line per octet
+            bf16* op = reinterpret_cast<bf16*>(sg.ptr) + n * sg.ns + (lc >> 3) * P.HW8 + hw * 8;
+            for (int h8 = 0; h8 < cnt; h8 += 8) *reinterpret_cast<uint4*>(op + (h8 >> 3) * P.HW8) = cg_pack8(v + h8);
           }
         }
       }
@@ -440,9 +421,59 @@ int pick_nc(int ktot16, int cout, int* emode) {
   return 0;
 }
 
-uint32_t magic_of(long long d) { return (uint32_t)((1ull << 32) / (unsigned long long)d + 1ull); }
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
 
 }  // namespace
+
+// Tensor map over a planar bf16 view (N, C8, H, W, 8) whose sample stride is `ns` elements.
+//   spatial: dims (W*8, H, C8, N), box (box_w8, box_h, box_c8, 1)
+//   flat (H=W=1): dims (8, N, C8), box (8, 128, box_c8)   -- samples are the GEMM rows
+int cg_make_planar_map(void* map_out, const void* ptr, long long ns, int N, int H, int W, int C8, int flat, int box_w8,
+                       int box_h, int box_c8) {
+  CUtensorMap* map = reinterpret_cast<CUtensorMap*>(map_out);
+  EncodeTiledFn enc = encode_fn();
+  if (enc == nullptr) {
+    cg_set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return CG_ERR_CUDA;
+  }
+  CUresult r;
+  const cuuint32_t ones[4] = {1, 1, 1, 1};
+  if (flat) {
+    const cuuint64_t dims[3] = {8, (cuuint64_t)N, (cuuint64_t)C8};
+    const cuuint64_t strides[2] = {(cuuint64_t)ns * 2, 16};
+    const cuuint32_t box[3] = {8, 128, (cuuint32_t)box_c8};
+    r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, ones,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)C8, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)ns * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)box_w8, (cuuint32_t)box_h, (cuuint32_t)box_c8, 1};
+    r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, ones,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) {
+    cg_set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p ns=%lld N=%d H=%d W=%d C8=%d flat=%d box=(%d,%d,%d)", (int)r,
+                 ptr, ns, N, H, W, C8, flat, box_w8, box_h, box_c8);
+    return CG_ERR_CUDA;
+  }
+  return CG_OK;
+}
 
 extern "C" int32_t cg_conv_nchunk(int32_t ktot16, int32_t cout) { return pick_nc(ktot16, cout, nullptr); }
 
@@ -461,23 +492,30 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
   CG_REQUIRE(a->nseg >= 1 && a->nseg <= CG_MAX_SEG, "cg_conv2d: nseg %d", a->nseg);
   CG_REQUIRE(a->cout > 0 && a->cout % 16 == 0, "cg_conv2d: cout %d must be a positive multiple of 16", a->cout);
   CG_REQUIRE(a->N > 0 && a->H > 0 && a->W > 0, "cg_conv2d: empty tensor");
-  CG_REQUIRE((long long)a->N * (a->H + 1) < (1ll << 24) && (long long)a->N * a->H * a->W < (1ll << 31),
-             "cg_conv2d: tensor too large for 32-bit pixel arithmetic");
   CG_REQUIRE(a->wpack != nullptr && ((uintptr_t)a->wpack & 15) == 0, "cg_conv2d: wpack null or unaligned");
-  CG_REQUIRE(a->ksize == 1 || a->H < 256, "cg_conv2d: 3x3 path supports H < 256 (got %d)", a->H);
+  const bool flat = (a->H == 1 && a->W == 1);
+  CG_REQUIRE(!(flat && a->ksize == 3), "cg_conv2d: a 3x3 conv on a 1x1 image must be passed as its centre tap (ksize=1)");
   KParams kp;
   kp.a = *a;
+  kp.flat = flat ? 1 : 0;
   kp.ntaps = a->ksize * a->ksize;
+  kp.HW8 = (long long)a->H * a->W * 8;
+  const int halo = a->ksize == 3 ? 2 : 0;
   int nchunks = 0, c16 = 0;
   for (int s = 0; s < a->nsrc; ++s) {
     const cg_src& src = a->src[s];
     CG_REQUIRE(src.ptr != nullptr && ((uintptr_t)src.ptr & 15) == 0, "cg_conv2d: src %d null/unaligned", s);
-    CG_REQUIRE(src.C > 0 && src.C % 16 == 0 && src.ld % 8 == 0 && src.ld >= src.C,
-               "cg_conv2d: src %d C=%d ld=%d (C multiple of 16, ld multiple of 8)", s, src.C, src.ld);
+    CG_REQUIRE(src.C > 0 && src.C % 16 == 0 && src.ns % 8 == 0, "cg_conv2d: src %d C=%d ns=%lld", s, src.C,
+               (long long)src.ns);
+    const int box_c8 = src.C / 8 < 4 ? src.C / 8 : 4;
+    int rc = cg_make_planar_map(&kp.src_map[s], src.ptr, src.ns, a->N, a->H, a->W, src.C / 8, kp.flat, (8 + halo) * 8,
+                                16 + halo, box_c8);
+    if (rc != CG_OK) return rc;
+    kp.src_bytes[s] = (uint32_t)box_c8 * (flat ? kPlane1 : (a->ksize == 3 ? kPlane3 : kPlane1));
     for (int c0 = 0; c0 < src.C; c0 += 32) {
       CG_REQUIRE(nchunks < kMaxChunks, "cg_conv2d: too many K chunks");
       int n16 = (src.C - c0 >= 32) ? 2 : 1;
-      kp.chunk[nchunks++] = Chunk{(uint16_t)s, (uint16_t)c0, (uint16_t)n16, (uint16_t)(c16 * kp.ntaps)};
+      kp.chunk[nchunks++] = Chunk{(uint16_t)s, (uint16_t)(c0 / 8), (uint16_t)n16, (uint16_t)(c16 * kp.ntaps)};
       c16 += n16;
     }
   }
@@ -490,32 +528,36 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
   for (int s = 0; s < a->nseg; ++s) {
     const cg_seg& sg = a->seg[s];
     CG_REQUIRE(sg.ptr != nullptr && ((uintptr_t)sg.ptr & 15) == 0, "cg_conv2d: seg %d null/unaligned", s);
-    CG_REQUIRE(sg.c0 % 16 == 0 && sg.cn % 8 == 0 && sg.cn > 0 && sg.ld % (sg.dtype == CG_F32 ? 4 : 8) == 0,
-               "cg_conv2d: seg %d c0=%d cn=%d ld=%d", s, sg.c0, sg.cn, sg.ld);
-    CG_REQUIRE(sg.add == nullptr || (((uintptr_t)sg.add & 15) == 0 && sg.add_ld % 8 == 0), "cg_conv2d: seg %d add", s);
-    CG_REQUIRE(sg.add2 == nullptr || (((uintptr_t)sg.add2 & 15) == 0 && sg.add2_ld % 8 == 0), "cg_conv2d: seg %d add2", s);
-    CG_REQUIRE(sg.mul == nullptr || (((uintptr_t)sg.mul & 15) == 0 && sg.mul_ld % 8 == 0), "cg_conv2d: seg %d mul", s);
+    CG_REQUIRE(sg.c0 % 16 == 0 && sg.cn % 8 == 0 && sg.cn > 0 && sg.ns % (sg.dtype == CG_F32 ? 4 : 8) == 0,
+               "cg_conv2d: seg %d c0=%d cn=%d ns=%lld", s, sg.c0, sg.cn, (long long)sg.ns);
+    CG_REQUIRE(sg.add == nullptr || (((uintptr_t)sg.add & 15) == 0 && sg.add_ns % 8 == 0), "cg_conv2d: seg %d add", s);
+    CG_REQUIRE(sg.add2 == nullptr || (((uintptr_t)sg.add2 & 15) == 0 && sg.add2_ns % 8 == 0), "cg_conv2d: seg %d add2", s);
+    CG_REQUIRE(sg.mul == nullptr || (((uintptr_t)sg.mul & 15) == 0 && sg.mul_ns % 8 == 0), "cg_conv2d: seg %d mul", s);
   }
   kp.nE = 0;
   if (kp.emode) {
     for (int s = 0; s < a->nseg && kp.nE < kESlots; ++s) {
       const cg_seg& sg = a->seg[s];
       const void* ptrs[3] = {sg.add, sg.add2, sg.mul};
-      const int lds[3] = {sg.add_ld, sg.add2_ld, sg.mul_ld};
-      for (int kind = 0; kind < 3 && kp.nE < kESlots; ++kind)
-        if (ptrs[kind] != nullptr) kp.eop[kp.nE++] = EOp{ptrs[kind], lds[kind], s, kind};
+      const long long nss[3] = {sg.add_ns, sg.add2_ns, sg.mul_ns};
+      for (int kind = 0; kind < 3 && kp.nE < kESlots; ++kind) {
+        if (ptrs[kind] == nullptr) continue;
+        int rc = cg_make_planar_map(&kp.e_map[kp.nE], ptrs[kind], nss[kind], a->N, a->H, a->W, sg.cn / 8, kp.flat, 64, 16,
+                                    kp.Nc / 8);
+        if (rc != CG_OK) return rc;
+        kp.eop[kp.nE++] = EOp{s, kind, sg.c0 / 8};
+      }
     }
   }
-  kp.Hp = a->H + 1;
-  kp.V = a->N * kp.Hp;
-  kp.P = (long long)a->N * a->H * a->W;
-  kp.hp_magic = magic_of(kp.Hp);
-  if (a->ksize == 3) {
-    kp.tiles_x = (a->W + 7) / 8;
-    kp.ntiles = ((kp.V + 15) / 16) * kp.tiles_x;
-  } else {
+  kp.e_tx_bytes = (uint32_t)(kp.nE * e_slot_bytes(kp.Nc));
+  if (flat) {
     kp.tiles_x = 1;
-    kp.ntiles = (int)((kp.P + 127) / 128);
+    kp.tiles_per_img = 1;
+    kp.ntiles = (a->N + 127) / 128;
+  } else {
+    kp.tiles_x = (a->W + 7) / 8;
+    kp.tiles_per_img = kp.tiles_x * ((a->H + 15) / 16);
+    kp.ntiles = a->N * kp.tiles_per_img;
   }
   kp.idesc = umma_idesc_bf16(128, kp.Nc, 0, 0);
   uint32_t cols = 32;
@@ -532,7 +574,10 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
     attr_done = true;
   }
   static int dbg = -1;
-  if (dbg < 0) { const char* e = getenv("CG_DEBUG_SKIP"); dbg = e ? atoi(e) : 0; }
+  if (dbg < 0) {
+    const char* e = getenv("CG_DEBUG_SKIP");
+    dbg = e ? atoi(e) : 0;
+  }
   kp.dbg = dbg;
   const int sms = cg_device_sms();
   int gx = sms / kp.nN;

@@ -3,22 +3,23 @@
 
 namespace {
 
+// All bf16 tensors here are channel-octet planar (N, C/8, H, W, 8): one thread handles one 16-byte octet of one
+// pixel, consecutive threads walk consecutive pixels of a plane -> fully coalesced.
 // ------------------------------------------------------------------ avg-pool / nearest upsample
 __global__ void avgpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C8, int d,
-                                   int x_ld, int y_ld, int Po) {
+                                   long long x_ns, long long y_ns, int Po) {
   const int Ho = H / d, Wo = W / d;
-  long long total = (long long)N * Po * Po * C8;
+  const long long total = (long long)N * C8 * Po * Po;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c8 = (int)(i % C8);
-    long long p = i / C8;
-    int wo = (int)(p % Po), ho = (int)((p / Po) % Po), n = (int)(p / ((long long)Po * Po));
+    const int wo = (int)(i % Po), ho = (int)((i / Po) % Po);
+    const int c8 = (int)((i / ((long long)Po * Po)) % C8), n = (int)(i / ((long long)Po * Po * C8));
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (ho < Ho && wo < Wo) {
+      const bf16* xp = x + n * x_ns + (long long)c8 * H * W * 8;
       for (int a = 0; a < d; ++a)
         for (int b = 0; b < d; ++b) {
           float f[8];
-          cg_unpack8(__ldg(reinterpret_cast<const uint4*>(
-                         x + ((long long)(n * H + ho * d + a) * W + wo * d + b) * x_ld + c8 * 8)), f);
+          cg_unpack8(__ldg(reinterpret_cast<const uint4*>(xp + ((long long)(ho * d + a) * W + wo * d + b) * 8)), f);
 #pragma unroll
           for (int k = 0; k < 8; ++k) acc[k] += f[k];
         }
@@ -26,21 +27,21 @@ __global__ void avgpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict_
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] *= inv;
     }
-    *reinterpret_cast<uint4*>(y + p * y_ld + c8 * 8) = cg_pack8(acc);
+    *reinterpret_cast<uint4*>(y + n * y_ns + ((long long)c8 * Po * Po + (long long)ho * Po + wo) * 8) = cg_pack8(acc);
   }
 }
 
 __global__ void avgpool_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int N, int H, int W, int C8,
-                                   int d, int dy_ld, int dx_ld, int Po, int accumulate) {
-  long long total = (long long)N * H * W * C8;
+                                   int d, long long dy_ns, long long dx_ns, int Po, int accumulate) {
+  const long long total = (long long)N * C8 * H * W;
   const float inv = 1.0f / (d * d);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c8 = (int)(i % C8);
-    long long p = i / C8;
-    int w = (int)(p % W), h = (int)((p / W) % H), n = (int)(p / ((long long)W * H));
+    const int w = (int)(i % W), h = (int)((i / W) % H);
+    const int c8 = (int)((i / ((long long)W * H)) % C8), n = (int)(i / ((long long)W * H * C8));
     float f[8];
-    cg_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + ((long long)(n * Po + h / d) * Po + w / d) * dy_ld + c8 * 8)), f);
-    bf16* o = dx + p * dx_ld + c8 * 8;
+    cg_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + n * dy_ns +
+                                                    ((long long)c8 * Po * Po + (long long)(h / d) * Po + w / d) * 8)), f);
+    bf16* o = dx + n * dx_ns + ((long long)c8 * H * W + (long long)h * W + w) * 8;
     float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (accumulate) cg_unpack8(*reinterpret_cast<const uint4*>(o), g);
 #pragma unroll
@@ -50,44 +51,43 @@ __global__ void avgpool_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict
 }
 
 __global__ void upsample_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ bias, bf16* __restrict__ y,
-                                    int N, int Hi, int Ho, int C, int x_ld, int y_ld) {
+                                    int N, int Hi, int Ho, int C, long long x_ns, long long y_ns) {
   const int C8 = (C + 7) / 8;
-  long long total = (long long)N * Ho * Ho * C8;
+  const long long total = (long long)N * C8 * Ho * Ho;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c8 = (int)(i % C8);
-    long long p = i / C8;
-    int w = (int)(p % Ho), h = (int)((p / Ho) % Ho), n = (int)(p / ((long long)Ho * Ho));
-    int hs = (h * Hi) / Ho, ws = (w * Hi) / Ho;
+    const int w = (int)(i % Ho), h = (int)((i / Ho) % Ho);
+    const int c8 = (int)((i / ((long long)Ho * Ho)) % C8), n = (int)(i / ((long long)Ho * Ho * C8));
+    const int hs = (h * Hi) / Ho, ws = (w * Hi) / Ho;
     float f[8];
-    cg_unpack8(__ldg(reinterpret_cast<const uint4*>(x + ((long long)(n * Hi + hs) * Hi + ws) * x_ld + c8 * 8)), f);
+    cg_unpack8(__ldg(reinterpret_cast<const uint4*>(x + n * x_ns + ((long long)c8 * Hi * Hi + (long long)hs * Hi + ws) * 8)), f);
     if (bias != nullptr) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        int c = c8 * 8 + k;
+        const int c = c8 * 8 + k;
         if (c < C) f[k] += __ldg(bias + ((long long)c * Ho + h) * Ho + w);
       }
     }
-    *reinterpret_cast<uint4*>(y + p * y_ld + c8 * 8) = cg_pack8(f);
+    *reinterpret_cast<uint4*>(y + n * y_ns + ((long long)c8 * Ho * Ho + (long long)h * Ho + w) * 8) = cg_pack8(f);
   }
 }
 
 __global__ void upsample_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int N, int Hi, int Ho, int C8,
-                                    int dy_ld, int dx_ld, int accumulate) {
-  long long total = (long long)N * Hi * Hi * C8;
+                                    long long dy_ns, long long dx_ns, int accumulate) {
+  const long long total = (long long)N * C8 * Hi * Hi;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c8 = (int)(i % C8);
-    long long p = i / C8;
-    int w = (int)(p % Hi), h = (int)((p / Hi) % Hi), n = (int)(p / ((long long)Hi * Hi));
+    const int w = (int)(i % Hi), h = (int)((i / Hi) % Hi);
+    const int c8 = (int)((i / ((long long)Hi * Hi)) % C8), n = (int)(i / ((long long)Hi * Hi * C8));
     // destination rows/cols whose nearest source is (h, w): floor(ho*Hi/Ho) == h
-    int h0 = (h * Ho + Hi - 1) / Hi, h1 = ((h + 1) * Ho + Hi - 1) / Hi;
-    int w0 = (w * Ho + Hi - 1) / Hi, w1 = ((w + 1) * Ho + Hi - 1) / Hi;
+    const int h0 = (h * Ho + Hi - 1) / Hi, h1 = ((h + 1) * Ho + Hi - 1) / Hi;
+    const int w0 = (w * Ho + Hi - 1) / Hi, w1 = ((w + 1) * Ho + Hi - 1) / Hi;
     float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    bf16* o = dx + p * dx_ld + c8 * 8;
+    bf16* o = dx + n * dx_ns + ((long long)c8 * Hi * Hi + (long long)h * Hi + w) * 8;
     if (accumulate) cg_unpack8(*reinterpret_cast<const uint4*>(o), g);
+    const bf16* dp = dy + n * dy_ns + (long long)c8 * Ho * Ho * 8;
     for (int a = h0; a < h1; ++a)
       for (int b = w0; b < w1; ++b) {
         float f[8];
-        cg_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + ((long long)(n * Ho + a) * Ho + b) * dy_ld + c8 * 8)), f);
+        cg_unpack8(__ldg(reinterpret_cast<const uint4*>(dp + ((long long)a * Ho + b) * 8)), f);
 #pragma unroll
         for (int k = 0; k < 8; ++k) g[k] += f[k];
       }
@@ -95,16 +95,24 @@ __global__ void upsample_bwd_kernel(const bf16* __restrict__ dy, bf16* __restric
   }
 }
 
-// dbias[c,h,w] += sum_n dy[n,h,w,c]
+// dbias[c,h,w] += sum_n dy[n,c,h,w]
 __global__ void upsample_dbias_kernel(const bf16* __restrict__ dy, float* __restrict__ dbias, int N, int Ho, int C,
-                                      int dy_ld) {
-  long long total = (long long)Ho * Ho * C;
+                                      long long dy_ns) {
+  const int C8 = (C + 7) / 8;
+  const long long total = (long long)C8 * Ho * Ho;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % C);
-    long long p = i / C;  // h*Ho + w
-    float s = 0.f;
-    for (int n = 0; n < N; ++n) s += __bfloat162float(dy[((long long)n * Ho * Ho + p) * dy_ld + c]);
-    dbias[(long long)c * Ho * Ho + p] += s;
+    const long long p = i % ((long long)Ho * Ho);
+    const int c8 = (int)(i / ((long long)Ho * Ho));
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int n = 0; n < N; ++n) {
+      float f[8];
+      cg_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + n * dy_ns + ((long long)c8 * Ho * Ho + p) * 8)), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s[k] += f[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (c8 * 8 + k < C) dbias[(long long)(c8 * 8 + k) * Ho * Ho + p] += s[k];
   }
 }
 
@@ -152,25 +160,32 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const cg_latent_args a)
   }
   __syncthreads();
   float kl_acc = 0.f;
-  for (int e = tid; e < zd * kLatPix; e += 256) {
-    int px = e / zd, c = e - px * zd;
+  bf16* zb = reinterpret_cast<bf16*>(a.z_bf16);
+  for (int e = tid; e < 2 * kLatPix; e += 256) {  // work item = (pixel, channel octet)
+    const int px = e >> 1, oc = e & 1;
     if (px >= npx) continue;
-    long long pix = (long long)n * a.HW + hw0 + px;
-    float p_loc = a.p[pix * a.p_ld + c], p_ls = a.p[pix * a.p_ld + zd + c] + a.log_t;
-    float z;
-    if (a.mode == 0) {
-      float q_loc = a.q[pix * a.q_ld + c], q_ls = a.q[pix * a.q_ld + zd + c] + a.log_t;
-      z = q_loc + __expf(q_ls) * s_eps[c][px];
-      // src/vae.py:14-25 (same term order)
-      float eq = __expf(q_ls), ep = __expf(p_ls), dm = q_loc - p_loc;
-      kl_acc += -0.5f + p_ls - q_ls + 0.5f * (eq * eq + dm * dm) / (ep * ep);
-    } else if (a.mode == 1) {
-      z = p_loc + __expf(p_ls) * s_eps[c][px];
-    } else {
-      z = p_loc;
+    const long long pix = (long long)n * a.HW + hw0 + px;
+    float zv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = oc * 8 + k;
+      const float p_loc = a.p[pix * a.p_ld + c], p_ls = a.p[pix * a.p_ld + zd + c] + a.log_t;
+      float z;
+      if (a.mode == 0) {
+        const float q_loc = a.q[pix * a.q_ld + c], q_ls = a.q[pix * a.q_ld + zd + c] + a.log_t;
+        z = q_loc + __expf(q_ls) * s_eps[c][px];
+        // src/vae.py:14-25 (same term order)
+        const float eq = __expf(q_ls), ep = __expf(p_ls), dm = q_loc - p_loc;
+        kl_acc += -0.5f + p_ls - q_ls + 0.5f * (eq * eq + dm * dm) / (ep * ep);
+      } else if (a.mode == 1) {
+        z = p_loc + __expf(p_ls) * s_eps[c][px];
+      } else {
+        z = p_loc;
+      }
+      zv[k] = z;
+      s_z[c][px] = z;
     }
-    reinterpret_cast<bf16*>(a.z_bf16)[pix * a.z_ld + c] = __float2bfloat16(z);
-    s_z[c][px] = z;
+    *reinterpret_cast<uint4*>(zb + n * a.z_ns + ((long long)oc * a.HW + hw0 + px) * 8) = cg_pack8(zv);
   }
   if (a.kl_out != nullptr && a.mode == 0) {
     kl_acc = cg_warp_sum(kl_acc);
@@ -213,31 +228,43 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const cg_latent_bwd_arg
   __syncthreads();
   bf16* dq = reinterpret_cast<bf16*>(a.dq);
   bf16* dp = reinterpret_cast<bf16*>(a.dp);
-  for (int e = tid; e < zd * kLatPix; e += 256) {
-    int px = e / zd, c = e - px * zd;
+  const bf16* dzp = reinterpret_cast<const bf16*>(a.dz);
+  for (int e = tid; e < 2 * kLatPix; e += 256) {  // work item = (pixel, channel octet)
+    const int px = e >> 1, oc = e & 1;
     if (px >= npx) continue;
-    long long pix = (long long)n * a.HW + hw0 + px;
-    float dz = a.dz != nullptr ? __bfloat162float(reinterpret_cast<const bf16*>(a.dz)[pix * a.dz_ld + c]) : 0.f;
-    float p_loc = a.p[pix * a.p_ld + c], p_ls = a.p[pix * a.p_ld + zd + c];
-    float g_ploc, g_pls;
-    if (a.mode == 0) {
-      float q_loc = a.q[pix * a.q_ld + c], q_ls = a.q[pix * a.q_ld + zd + c];
-      float eq = __expf(q_ls), ivp = __expf(-2.0f * p_ls), dm = q_loc - p_loc;
-      float g_qloc = a.g_kl * dm * ivp + dz;
-      float g_qls = a.g_kl * (eq * eq * ivp - 1.0f) + dz * eq * s_eps[c][px];
-      g_ploc = -a.g_kl * dm * ivp;
-      g_pls = a.g_kl * (1.0f - (eq * eq + dm * dm) * ivp);
-      dq[pix * a.dq_ld + c] = __float2bfloat16(g_qloc);
-      dq[pix * a.dq_ld + zd + c] = __float2bfloat16(g_qls);
-    } else if (a.mode == 1) {
-      g_ploc = dz;
-      g_pls = dz * __expf(p_ls) * s_eps[c][px];
-    } else {
-      g_ploc = dz;
-      g_pls = 0.f;
+    const long long hw = hw0 + px;
+    const long long pix = (long long)n * a.HW + hw;
+    float dz[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (dzp != nullptr) cg_unpack8(*reinterpret_cast<const uint4*>(dzp + n * a.dz_ns + ((long long)oc * a.HW + hw) * 8), dz);
+    float g_qloc[8], g_qls[8], g_ploc[8], g_pls[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = oc * 8 + k;
+      const float p_loc = a.p[pix * a.p_ld + c], p_ls = a.p[pix * a.p_ld + zd + c];
+      if (a.mode == 0) {
+        const float q_loc = a.q[pix * a.q_ld + c], q_ls = a.q[pix * a.q_ld + zd + c];
+        const float eq = __expf(q_ls), ivp = __expf(-2.0f * p_ls), dm = q_loc - p_loc;
+        g_qloc[k] = a.g_kl * dm * ivp + dz[k];
+        g_qls[k] = a.g_kl * (eq * eq * ivp - 1.0f) + dz[k] * eq * s_eps[c][px];
+        g_ploc[k] = -a.g_kl * dm * ivp;
+        g_pls[k] = a.g_kl * (1.0f - (eq * eq + dm * dm) * ivp);
+      } else if (a.mode == 1) {
+        g_ploc[k] = dz[k];
+        g_pls[k] = dz[k] * __expf(p_ls) * s_eps[c][px];
+      } else {
+        g_ploc[k] = dz[k];
+        g_pls[k] = 0.f;
+      }
     }
-    dp[pix * a.dp_ld + c] = __float2bfloat16(g_ploc);
-    dp[pix * a.dp_ld + zd + c] = __float2bfloat16(g_pls);
+    // channels [0,16) = loc -> octets 0,1 ; channels [16,32) = logscale -> octets 2,3
+    if (a.mode == 0) {
+      bf16* q0 = dq + n * a.dq_ns + hw * 8;
+      *reinterpret_cast<uint4*>(q0 + (long long)oc * a.HW * 8) = cg_pack8(g_qloc);
+      *reinterpret_cast<uint4*>(q0 + (long long)(2 + oc) * a.HW * 8) = cg_pack8(g_qls);
+    }
+    bf16* p0 = dp + n * a.dp_ns + hw * 8;
+    *reinterpret_cast<uint4*>(p0 + (long long)oc * a.HW * 8) = cg_pack8(g_ploc);
+    *reinterpret_cast<uint4*>(p0 + (long long)(2 + oc) * a.HW * 8) = cg_pack8(g_pls);
   }
 }
 
@@ -282,7 +309,7 @@ inline int grid_for(long long work, int threads) {
 }  // namespace
 
 extern "C" int cg_avgpool_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, int32_t d,
-                              int32_t x_ld, int32_t y_ld, int32_t pad_to, void* stream) {
+                              int64_t x_ld, int64_t y_ld, int32_t pad_to, void* stream) {
   CG_ARCH_GUARD();
   CG_REQUIRE(d >= 1 && H % d == 0 && W % d == 0 && H == W, "cg_avgpool_fwd: H=%d W=%d d=%d", H, W, d);
   CG_REQUIRE(C % 8 == 0 && x_ld % 8 == 0 && y_ld % 8 == 0, "cg_avgpool_fwd: C/ld multiples of 8");
@@ -295,7 +322,7 @@ extern "C" int cg_avgpool_fwd(const void* x, void* y, int32_t N, int32_t H, int3
 }
 
 extern "C" int cg_avgpool_bwd(const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t C, int32_t d,
-                              int32_t dy_ld, int32_t dx_ld, int32_t pad_to, int32_t accumulate, void* stream) {
+                              int64_t dy_ld, int64_t dx_ld, int32_t pad_to, int32_t accumulate, void* stream) {
   CG_ARCH_GUARD();
   CG_REQUIRE(d >= 1 && H % d == 0 && W % d == 0 && H == W, "cg_avgpool_bwd: H=%d W=%d d=%d", H, W, d);
   CG_REQUIRE(C % 8 == 0 && dy_ld % 8 == 0 && dx_ld % 8 == 0, "cg_avgpool_bwd: C/ld multiples of 8");
@@ -307,7 +334,7 @@ extern "C" int cg_avgpool_bwd(const void* dy, void* dx, int32_t N, int32_t H, in
 }
 
 extern "C" int cg_upsample_fwd(const void* x, const float* bias, void* y, int32_t N, int32_t Hi, int32_t Ho, int32_t C,
-                               int32_t x_ld, int32_t y_ld, void* stream) {
+                               int64_t x_ld, int64_t y_ld, void* stream) {
   CG_ARCH_GUARD();
   CG_REQUIRE(Ho >= Hi && x_ld % 8 == 0 && y_ld % 8 == 0, "cg_upsample_fwd: Hi=%d Ho=%d", Hi, Ho);
   upsample_fwd_kernel<<<grid_for((long long)N * Ho * Ho * ((C + 7) / 8), 256), 256, 0, cg_stream(stream)>>>(
@@ -317,7 +344,7 @@ extern "C" int cg_upsample_fwd(const void* x, const float* bias, void* y, int32_
 }
 
 extern "C" int cg_upsample_bwd(const void* dy, void* dx, float* dbias, int32_t N, int32_t Hi, int32_t Ho, int32_t C,
-                               int32_t dy_ld, int32_t dx_ld, int32_t accumulate, void* stream) {
+                               int64_t dy_ld, int64_t dx_ld, int32_t accumulate, void* stream) {
   CG_ARCH_GUARD();
   CG_REQUIRE(Ho >= Hi && dy_ld % 8 == 0 && dx_ld % 8 == 0, "cg_upsample_bwd: Hi=%d Ho=%d", Hi, Ho);
   if (dx != nullptr) {
@@ -326,7 +353,7 @@ extern "C" int cg_upsample_bwd(const void* dy, void* dx, float* dbias, int32_t N
     CG_LAUNCH_CHECK("cg_upsample_bwd");
   }
   if (dbias != nullptr) {
-    upsample_dbias_kernel<<<grid_for((long long)Ho * Ho * C, 256), 256, 0, cg_stream(stream)>>>(
+    upsample_dbias_kernel<<<grid_for((long long)Ho * Ho * ((C + 7) / 8), 256), 256, 0, cg_stream(stream)>>>(
         reinterpret_cast<const bf16*>(dy), dbias, N, Ho, C, dy_ld);
     CG_LAUNCH_CHECK("cg_upsample_bwd(dbias)");
   }

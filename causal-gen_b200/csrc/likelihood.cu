@@ -40,13 +40,13 @@ __device__ void load_heads(Heads& s, const cg_dgauss_args& a) {
 
 // per-pixel head evaluation: raw loc / raw logscale / raw coeff for C channels
 template <int C>
-__device__ __forceinline__ void eval_heads(const Heads& s, const bf16* hrow, int Cw, float* loc, float* ls, float* co,
-                                           bool rgb) {
+__device__ __forceinline__ void eval_heads(const Heads& s, const bf16* hrow, long long oct_stride, int Cw, float* loc,
+                                           float* ls, float* co, bool rgb) {
 #pragma unroll
   for (int c = 0; c < C; ++c) { loc[c] = s.b_loc[c]; ls[c] = s.b_ls[c]; co[c] = s.b_co[c]; }
   for (int k8 = 0; k8 < Cw; k8 += 8) {
     float h[8];
-    cg_unpack8(*reinterpret_cast<const uint4*>(hrow + k8), h);
+    cg_unpack8(*reinterpret_cast<const uint4*>(hrow + (k8 >> 3) * oct_stride), h);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
 #pragma unroll
@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(256) dgauss_fwd_kernel(const cg_dgauss_args a)
   if (hw < a.HW) {
     const long long pix = (long long)n * a.HW + hw;
     float loc[C], ls[C], co[C], x[C];
-    eval_heads<C>(s, reinterpret_cast<const bf16*>(a.h) + pix * a.h_ld, a.Cw, loc, ls, co, C == 3);
+    eval_heads<C>(s, reinterpret_cast<const bf16*>(a.h) + n * a.h_ns + (long long)hw * 8, (long long)a.HW * 8, a.Cw, loc,
+                  ls, co, C == 3);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       x[c] = a.x[((long long)n * C + c) * a.HW + hw];
@@ -135,10 +136,10 @@ __global__ void __launch_bounds__(256) dgauss_bwd_kernel(const cg_dgauss_args a)
   for (int c = 0; c < C; ++c) dloc[c] = dls[c] = dco[c] = 0.f;
   if (hw < a.HW) {
     const long long pix = (long long)n * a.HW + hw;
-    const bf16* hrow = reinterpret_cast<const bf16*>(a.h) + pix * a.h_ld;
+    const bf16* hrow = reinterpret_cast<const bf16*>(a.h) + n * a.h_ns + (long long)hw * 8;
     float loc[C], ls[C], co[C], x[C];
     bool live[C];
-    eval_heads<C>(s, hrow, a.Cw, loc, ls, co, C == 3);
+    eval_heads<C>(s, hrow, (long long)a.HW * 8, a.Cw, loc, ls, co, C == 3);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       x[c] = a.x[((long long)n * C + c) * a.HW + hw];
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(256) dgauss_bwd_kernel(const cg_dgauss_args a)
       dco[2] = dloc[2] * x[1] * (1.0f - tc[2] * tc[2]);
     }
     // dh = W_loc^T dloc + W_ls^T dls + W_co^T dco
-    bf16* drow = reinterpret_cast<bf16*>(a.dh) + pix * a.dh_ld;
+    bf16* drow = reinterpret_cast<bf16*>(a.dh) + n * a.dh_ns + (long long)hw * 8;
     for (int k8 = 0; k8 < a.Cw; k8 += 8) {
       float g[8];
 #pragma unroll
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(256) dgauss_bwd_kernel(const cg_dgauss_args a)
           v += s.w_loc[c][k8 + k] * dloc[c] + s.w_ls[c][k8 + k] * dls[c] + (C == 3 ? s.w_co[c][k8 + k] * dco[c] : 0.f);
         g[k] = v;
       }
-      *reinterpret_cast<uint4*>(drow + k8) = cg_pack8(g);
+      *reinterpret_cast<uint4*>(drow + (long long)(k8 >> 3) * a.HW * 8) = cg_pack8(g);
     }
   }
 #pragma unroll
@@ -192,8 +193,8 @@ __global__ void __launch_bounds__(256) dgauss_bwd_kernel(const cg_dgauss_args a)
   for (int t = threadIdx.x; t < nhead * per; t += blockDim.x) {
     int head = t / per, r = t - head * per, c = r / a.Cw, k = r - c * a.Cw;
     float acc = 0.f;
-    const bf16* hb = reinterpret_cast<const bf16*>(a.h) + ((long long)n * a.HW + blockIdx.x * blockDim.x) * a.h_ld + k;
-    for (int p = 0; p < npx; ++p) acc += s_d[p][head * C + c] * __bfloat162float(hb[(long long)p * a.h_ld]);
+    const bf16* hb = reinterpret_cast<const bf16*>(a.h) + n * a.h_ns + ((long long)(k >> 3) * a.HW + blockIdx.x * blockDim.x) * 8 + (k & 7);
+    for (int p = 0; p < npx; ++p) acc += s_d[p][head * C + c] * __bfloat162float(hb[(long long)p * 8]);
     float* dst = head == 0 ? a.dw_loc : (head == 1 ? a.dw_ls : a.dw_co);
     if (dst != nullptr) atomicAdd(dst + c * a.Cw + k, acc);
   }
@@ -217,7 +218,8 @@ __global__ void __launch_bounds__(256) dgauss_sample_kernel(const cg_dgauss_args
   if (hw >= a.HW) return;
   const long long pix = (long long)n * a.HW + hw;
   float loc[C], ls[C], co[C];
-  eval_heads<C>(s, reinterpret_cast<const bf16*>(a.h) + pix * a.h_ld, a.Cw, loc, ls, co, C == 3);
+  eval_heads<C>(s, reinterpret_cast<const bf16*>(a.h) + n * a.h_ns + (long long)hw * 8, (long long)a.HW * 8, a.Cw, loc, ls,
+                co, C == 3);
 #pragma unroll
   for (int c = 0; c < C; ++c) ls[c] = fmaxf(ls[c], -9.0f);
   if (C == 3) {  // src/vae.py:360-369 (inference branch: clamped predicted means feed the next sub-pixel)
@@ -337,7 +339,8 @@ __global__ void __launch_bounds__(256) dmol_fwd_kernel(const cg_dmol_args a) {
   const long long pix = (long long)n * a.HW + (live ? hw : 0);
 #pragma unroll
   for (int k8 = 0; k8 < CW; k8 += 8)
-    cg_unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.h) + pix * a.h_ld + k8), h + k8);
+    cg_unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.h) + n * a.h_ns +
+                                               ((long long)(k8 >> 3) * a.HW + (live ? hw : 0)) * 8), h + k8);
   for (int c = 0; c < 3; ++c) x[c] = a.x[((long long)n * 3 + c) * a.HW + (live ? hw : 0)];
   DmolLane L = dmol_heads<CW>(sw, sb, h, m);
   float c0 = tanhf(L.co_raw[0]), c1 = tanhf(L.co_raw[1]), c2 = tanhf(L.co_raw[2]);
@@ -380,7 +383,8 @@ __global__ void __launch_bounds__(256) dmol_bwd_kernel(const cg_dmol_args a) {
   const long long pix = (long long)n * a.HW + (live ? hw : 0);
 #pragma unroll
   for (int k8 = 0; k8 < CW; k8 += 8)
-    cg_unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.h) + pix * a.h_ld + k8), h + k8);
+    cg_unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.h) + n * a.h_ns +
+                                               ((long long)(k8 >> 3) * a.HW + (live ? hw : 0)) * 8), h + k8);
   for (int c = 0; c < 3; ++c) x[c] = a.x[((long long)n * 3 + c) * a.HW + (live ? hw : 0)];
   DmolLane L = dmol_heads<CW>(sw, sb, h, m);
   float tc[3] = {tanhf(L.co_raw[0]), tanhf(L.co_raw[1]), tanhf(L.co_raw[2])};
@@ -424,14 +428,14 @@ __global__ void __launch_bounds__(256) dmol_bwd_kernel(const cg_dmol_args a) {
     int c = (i - 1) / 3, w = (i - 1) % 3;
     return kMix + c * 3 * kMix + w * kMix + m;
   };
-  bf16* drow = reinterpret_cast<bf16*>(a.dh) + pix * a.dh_ld;
+  bf16* drow = reinterpret_cast<bf16*>(a.dh) + n * a.dh_ns + (long long)(live ? hw : 0) * 8;
 #pragma unroll
   for (int k = 0; k < CW; ++k) {
     float v = 0.f;
 #pragma unroll
     for (int i = 0; i < 10; ++i) v += d_out[i] * sw[oidx(i) * (CW + 1) + k];
     v = hw_sum(v);
-    if (lane16 == 0 && live) drow[k] = __float2bfloat16(v);
+    if (lane16 == 0 && live) drow[(long long)(k >> 3) * a.HW * 8 + (k & 7)] = __float2bfloat16(v);
   }
   if (act) {
 #pragma unroll
@@ -439,11 +443,11 @@ __global__ void __launch_bounds__(256) dmol_bwd_kernel(const cg_dmol_args a) {
   }
   __syncthreads();
   const int npx = min(kDmolPix, a.HW - (int)(blockIdx.x * kDmolPix));
-  const bf16* hb = reinterpret_cast<const bf16*>(a.h) + ((long long)n * a.HW + blockIdx.x * kDmolPix) * a.h_ld;
+  const bf16* hb = reinterpret_cast<const bf16*>(a.h) + n * a.h_ns + (long long)blockIdx.x * kDmolPix * 8;
   for (int tI = threadIdx.x; tI < 100 * CW; tI += blockDim.x) {
     int o = tI / CW, k = tI - o * CW;
     float acc = 0.f;
-    for (int p = 0; p < npx; ++p) acc += s_dl[p][o] * __bfloat162float(hb[(long long)p * a.h_ld + k]);
+    for (int p = 0; p < npx; ++p) acc += s_dl[p][o] * __bfloat162float(hb[((long long)(k >> 3) * a.HW + p) * 8 + (k & 7)]);
     atomicAdd(a.dw + tI, acc);
   }
   for (int o = threadIdx.x; o < 100; o += blockDim.x) {
@@ -471,7 +475,8 @@ __global__ void __launch_bounds__(256) dmol_predict_kernel(const cg_dmol_args a,
   const long long pix = (long long)n * a.HW + (live ? hw : 0);
 #pragma unroll
   for (int k8 = 0; k8 < CW; k8 += 8)
-    cg_unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.h) + pix * a.h_ld + k8), h + k8);
+    cg_unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.h) + n * a.h_ns +
+                                               ((long long)(k8 >> 3) * a.HW + (live ? hw : 0)) * 8), h + k8);
   DmolLane L = dmol_heads<CW>(sw, sb, h, m);
   float sel;
   if (mode == 0) {  // soft: softmax(logits)  src/dmol.py:170-172
@@ -525,7 +530,7 @@ __global__ void __launch_bounds__(256) dmol_predict_kernel(const cg_dmol_args a,
 
 #define DGAUSS_CHECK(a, name)                                                                       \
   CG_REQUIRE((a) != nullptr && ((a)->C == 1 || (a)->C == 3), name ": C must be 1 or 3");           \
-  CG_REQUIRE((a)->Cw % 8 == 0 && (a)->Cw <= kMaxCw && (a)->h_ld % 8 == 0, name ": Cw=%d h_ld=%d", (a)->Cw, (a)->h_ld)
+  CG_REQUIRE((a)->Cw % 8 == 0 && (a)->Cw <= kMaxCw && (a)->h_ns % 8 == 0, name ": Cw=%d", (a)->Cw)
 
 extern "C" int cg_dgauss_nll_fwd(const cg_dgauss_args* a, void* stream) {
   CG_ARCH_GUARD();
@@ -540,7 +545,7 @@ extern "C" int cg_dgauss_nll_fwd(const cg_dgauss_args* a, void* stream) {
 extern "C" int cg_dgauss_nll_bwd(const cg_dgauss_args* a, void* stream) {
   CG_ARCH_GUARD();
   DGAUSS_CHECK(a, "cg_dgauss_nll_bwd");
-  CG_REQUIRE(a->dh != nullptr && a->dh_ld % 8 == 0, "cg_dgauss_nll_bwd: dh");
+  CG_REQUIRE(a->dh != nullptr && a->dh_ns % 8 == 0, "cg_dgauss_nll_bwd: dh");
   dim3 grid(cg_ceil_div(a->HW, 256), a->N);
   if (a->C == 1) dgauss_bwd_kernel<1><<<grid, 256, 0, cg_stream(stream)>>>(*a);
   else dgauss_bwd_kernel<3><<<grid, 256, 0, cg_stream(stream)>>>(*a);
@@ -560,7 +565,7 @@ extern "C" int cg_dgauss_sample(const cg_dgauss_args* a, float* x_out, float* sc
 }
 
 #define DMOL_CHECK(a, name)                                                                                 \
-  CG_REQUIRE((a) != nullptr && ((a)->Cw == 16 || (a)->Cw == 32) && (a)->h_ld % 8 == 0, name ": Cw=%d must be 16 or 32", \
+  CG_REQUIRE((a) != nullptr && ((a)->Cw == 16 || (a)->Cw == 32) && (a)->h_ns % 8 == 0, name ": Cw=%d must be 16 or 32", \
              (a) ? (a)->Cw : -1)
 #define DMOL_LAUNCH(kern, a, ...)                                                            \
   do {                                                                                       \

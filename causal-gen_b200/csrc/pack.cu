@@ -59,44 +59,55 @@ __global__ void normalise_u8_kernel(const uint8_t* __restrict__ x8, float* __res
     x[i] = ((float)x8[i] - 127.5f) / 127.5f;
 }
 
-__global__ void parents_pack_kernel(const float* __restrict__ pa, long long sstride, long long cstride,
-                                    bf16* __restrict__ out, int N, int ctx, int ld, int drop_from, float drop_scale) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * ld) return;
-  int n = i / ld, c = i - n * ld;
-  float v = 0.0f;
-  if (c < ctx) {
-    v = pa[n * sstride + c * cstride];
-    if (c >= drop_from) v *= drop_scale;
+// spatially constant parents -> bf16 planar (N, C/8, HW, 8)
+__global__ void parents_plane_kernel(const float* __restrict__ pa, long long sstride, long long cstride,
+                                     bf16* __restrict__ out, int N, int ctx, int C8, int HW, long long ns, int drop_from,
+                                     float drop_scale) {
+  const long long total = (long long)N * C8 * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int hw = (int)(i % HW), c8 = (int)((i / HW) % C8), n = (int)(i / ((long long)HW * C8));
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = c8 * 8 + k;
+      float v = 0.f;
+      if (c < ctx) {
+        v = __ldg(pa + n * sstride + c * cstride);
+        if (c >= drop_from) v *= drop_scale;
+      }
+      f[k] = v;
+    }
+    *reinterpret_cast<uint4*>(out + n * ns + ((long long)c8 * HW + hw) * 8) = cg_pack8(f);
   }
-  out[i] = __float2bfloat16(v);
 }
 
-// NCHW fp32 <-> NHWC bf16 through a 32x32 shared-memory transpose
-__global__ void nchw2nhwc_kernel(const float* __restrict__ x, bf16* __restrict__ y, int C, int HW, int ld) {
-  __shared__ float t[32][33];
-  const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    int c = c0 + r, p = p0 + threadIdx.x;
-    t[r][threadIdx.x] = (c < C && p < HW) ? x[((long long)n * C + c) * HW + p] : 0.0f;
-  }
-  __syncthreads();
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    int p = p0 + r, c = c0 + threadIdx.x;
-    if (p < HW && c < ld) y[((long long)n * HW + p) * ld + c] = __float2bfloat16(c < C ? t[threadIdx.x][r] : 0.0f);
+// fp32 NCHW <-> bf16 planar: per (n, octet, pixel) gather/scatter 8 channels; reads/writes coalesced along pixels
+__global__ void nchw_to_planar_kernel(const float* __restrict__ x, bf16* __restrict__ y, int N, int C, int HW, long long ns) {
+  const int C8 = (C + 7) / 8;
+  const long long total = (long long)N * C8 * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int hw = (int)(i % HW), c8 = (int)((i / HW) % C8), n = (int)(i / ((long long)HW * C8));
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = c8 * 8 + k;
+      f[k] = c < C ? x[((long long)n * C + c) * HW + hw] : 0.f;
+    }
+    *reinterpret_cast<uint4*>(y + n * ns + ((long long)c8 * HW + hw) * 8) = cg_pack8(f);
   }
 }
-__global__ void nhwc2nchw_kernel(const bf16* __restrict__ x, float* __restrict__ y, int C, int HW, int ld) {
-  __shared__ float t[32][33];
-  const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    int p = p0 + r, c = c0 + threadIdx.x;
-    t[r][threadIdx.x] = (p < HW && c < C) ? __bfloat162float(x[((long long)n * HW + p) * ld + c]) : 0.0f;
-  }
-  __syncthreads();
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    int c = c0 + r, p = p0 + threadIdx.x;
-    if (c < C && p < HW) y[((long long)n * C + c) * HW + p] = t[threadIdx.x][r];
+__global__ void planar_to_nchw_kernel(const bf16* __restrict__ x, float* __restrict__ y, int N, int C, int HW, long long ns) {
+  const int C8 = (C + 7) / 8;
+  const long long total = (long long)N * C8 * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int hw = (int)(i % HW), c8 = (int)((i / HW) % C8), n = (int)(i / ((long long)HW * C8));
+    float f[8];
+    cg_unpack8(*reinterpret_cast<const uint4*>(x + n * ns + ((long long)c8 * HW + hw) * 8), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = c8 * 8 + k;
+      if (c < C) y[((long long)n * C + c) * HW + hw] = f[k];
+    }
   }
 }
 
@@ -115,54 +126,61 @@ __global__ void stats_to_nchw_kernel(const float* __restrict__ src, int ld, int 
   }
 }
 
-__global__ void fill_rows_kernel(const float* __restrict__ v, bf16* __restrict__ y, long long rows, int C, int ld) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * ld) return;
-  int c = (int)(i % ld);
-  y[i] = __float2bfloat16(c < C ? v[c] : 0.0f);
-}
-
-// dv[c] += sum_rows dy[row][c].  Threads walk (row, channel-octet) pairs in memory order (coalesced 16-byte
-// loads whatever C is); partial sums are combined per octet through shared memory, one atomicAdd per
-// channel per block.
-__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ dv, long long rows,
-                                                     int C, int ld) {
+__global__ void fill_planar_kernel(const float* __restrict__ v, bf16* __restrict__ y, int N, int HW, int C, long long ns) {
   const int C8 = (C + 7) / 8;
-  const int rpb = 256 / C8;              // rows per block pass (threads beyond rpb*C8 idle)
-  const int oct = threadIdx.x % C8, rsub = threadIdx.x / C8;
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (rsub < rpb) {
-    for (long long r = (long long)blockIdx.x * rpb + rsub; r < rows; r += (long long)gridDim.x * rpb) {
-      float f[8];
-      cg_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + r * ld + oct * 8)), f);
+  const long long total = (long long)N * C8 * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int hw = (int)(i % HW), c8 = (int)((i / HW) % C8), n = (int)(i / ((long long)HW * C8));
+    float f[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += f[i];
-    }
-  }
-  __shared__ float red[256][9];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = acc[i];
-  __syncthreads();
-  for (int t = threadIdx.x; t < C8 * 8; t += 256) {  // C may exceed 256 channels
-    const int o = t / 8, i = t % 8;
-    float s = 0.f;
-    for (int j = 0; j < rpb; ++j) s += red[j * C8 + o][i];
-    if (o * 8 + i < C) atomicAdd(dv + o * 8 + i, s);
+    for (int k = 0; k < 8; ++k) f[k] = (c8 * 8 + k < C) ? v[c8 * 8 + k] : 0.f;
+    *reinterpret_cast<uint4*>(y + n * ns + ((long long)c8 * HW + hw) * 8) = cg_pack8(f);
   }
 }
 
-__global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ y, long long rows,
-                           int C8, int a_ld, int b_ld, int y_ld) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * C8) return;
-  long long r = i / C8;
-  int c = (int)(i - r * C8) * 8;
-  float fa[8], fb[8];
-  cg_unpack8(*reinterpret_cast<const uint4*>(a + r * a_ld + c), fa);
-  cg_unpack8(*reinterpret_cast<const uint4*>(b + r * b_ld + c), fb);
+// dv[c] += sum over (n, pixel) of dy[n, c, pixel].  grid.y = channel octet; each block strides over the
+// (sample, pixel) positions of its octet plane with 16-byte loads, reduces through shared memory and issues
+// 8 atomics.
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ dv, int N, int HW,
+                                                     int C, long long ns) {
+  const int c8 = blockIdx.y;
+  const long long total = (long long)N * HW;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / HW), hw = (int)(i - (long long)n * HW);
+    float f[8];
+    cg_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + n * ns + ((long long)c8 * HW + hw) * 8)), f);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) fa[k] += fb[k];
-  *reinterpret_cast<uint4*>(y + r * y_ld + c) = cg_pack8(fa);
+    for (int k = 0; k < 8; ++k) acc[k] += f[k];
+  }
+  __shared__ float red[8][8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float s = cg_warp_sum(acc[k]);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8 && c8 * 8 + threadIdx.x < C) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    atomicAdd(dv + c8 * 8 + threadIdx.x, s);
+  }
+}
+
+__global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ y, int N, int HW,
+                           int C8, long long a_ns, long long b_ns, long long y_ns) {
+  const long long per = (long long)C8 * HW;
+  const long long total = (long long)N * per;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / per);
+    const long long r = (i - (long long)n * per) * 8;
+    float fa[8], fb[8];
+    cg_unpack8(*reinterpret_cast<const uint4*>(a + n * a_ns + r), fa);
+    cg_unpack8(*reinterpret_cast<const uint4*>(b + n * b_ns + r), fb);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) fa[k] += fb[k];
+    *reinterpret_cast<uint4*>(y + n * y_ns + r) = cg_pack8(fa);
+  }
 }
 
 __global__ void elbo_finalize_kernel(const float* __restrict__ nll, const float* __restrict__ kl, float* __restrict__ out,
@@ -202,31 +220,36 @@ extern "C" int cg_normalise_u8(const uint8_t* x8, float* x, int64_t n, void* str
   return CG_OK;
 }
 
-extern "C" int cg_parents_pack(const float* pa, int64_t sample_stride, int64_t chan_stride, void* out, int32_t N,
-                               int32_t ctx, int32_t ld, int32_t drop_from, float drop_scale, void* stream) {
+static inline int glue_grid(long long work) {
+  long long g = (work + 255) / 256;
+  if (g > 148LL * 16) g = 148LL * 16;
+  return g < 1 ? 1 : (int)g;
+}
+
+extern "C" int cg_parents_plane(const float* pa, int64_t sample_stride, int64_t chan_stride, void* out, int32_t N,
+                                int32_t ctx, int32_t C, int32_t HW, int64_t ns, int32_t drop_from, float drop_scale,
+                                void* stream) {
   CG_ARCH_GUARD();
-  CG_REQUIRE(ld % 16 == 0 && ld >= ctx, "cg_parents_pack: ld=%d ctx=%d", ld, ctx);
-  parents_pack_kernel<<<cg_ceil_div((int64_t)N * ld, 256), 256, 0, cg_stream(stream)>>>(
-      pa, sample_stride, chan_stride, reinterpret_cast<bf16*>(out), N, ctx, ld, drop_from, drop_scale);
-  CG_LAUNCH_CHECK("cg_parents_pack");
+  CG_REQUIRE(C % 8 == 0 && C >= ctx && ns % 8 == 0, "cg_parents_plane: C=%d ctx=%d", C, ctx);
+  parents_plane_kernel<<<glue_grid((long long)N * (C / 8) * HW), 256, 0, cg_stream(stream)>>>(
+      pa, sample_stride, chan_stride, reinterpret_cast<bf16*>(out), N, ctx, C / 8, HW, ns, drop_from, drop_scale);
+  CG_LAUNCH_CHECK("cg_parents_plane");
   return CG_OK;
 }
 
-extern "C" int cg_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t N, int32_t C, int32_t HW, int32_t ld,
-                                        void* stream) {
+extern "C" int cg_nchw_f32_to_planar(const float* x, void* y, int32_t N, int32_t C, int32_t HW, int64_t ns, void* stream) {
   CG_ARCH_GUARD();
-  dim3 grid(cg_ceil_div(HW, 32), cg_ceil_div(ld, 32), N);
-  nchw2nhwc_kernel<<<grid, dim3(32, 8), 0, cg_stream(stream)>>>(x, reinterpret_cast<bf16*>(y), C, HW, ld);
-  CG_LAUNCH_CHECK("cg_nchw_f32_to_nhwc_bf16");
+  nchw_to_planar_kernel<<<glue_grid((long long)N * ((C + 7) / 8) * HW), 256, 0, cg_stream(stream)>>>(
+      x, reinterpret_cast<bf16*>(y), N, C, HW, ns);
+  CG_LAUNCH_CHECK("cg_nchw_f32_to_planar");
   return CG_OK;
 }
 
-extern "C" int cg_nhwc_bf16_to_nchw_f32(const void* x, float* y, int32_t N, int32_t C, int32_t HW, int32_t ld,
-                                        void* stream) {
+extern "C" int cg_planar_to_nchw_f32(const void* x, float* y, int32_t N, int32_t C, int32_t HW, int64_t ns, void* stream) {
   CG_ARCH_GUARD();
-  dim3 grid(cg_ceil_div(HW, 32), cg_ceil_div(C, 32), N);
-  nhwc2nchw_kernel<<<grid, dim3(32, 8), 0, cg_stream(stream)>>>(reinterpret_cast<const bf16*>(x), y, C, HW, ld);
-  CG_LAUNCH_CHECK("cg_nhwc_bf16_to_nchw_f32");
+  planar_to_nchw_kernel<<<glue_grid((long long)N * ((C + 7) / 8) * HW), 256, 0, cg_stream(stream)>>>(
+      reinterpret_cast<const bf16*>(x), y, N, C, HW, ns);
+  CG_LAUNCH_CHECK("cg_planar_to_nchw_f32");
   return CG_OK;
 }
 
@@ -239,34 +262,34 @@ extern "C" int cg_stats_to_nchw(const float* src, int32_t ld, int32_t c0, float 
   return CG_OK;
 }
 
-extern "C" int cg_fill_rows(const float* v, void* y, int64_t rows, int32_t C, int32_t ld, void* stream) {
+extern "C" int cg_fill_planar(const float* v, void* y, int32_t N, int32_t HW, int32_t C, int64_t ns, void* stream) {
   CG_ARCH_GUARD();
-  fill_rows_kernel<<<cg_ceil_div(rows * ld, 256), 256, 0, cg_stream(stream)>>>(v, reinterpret_cast<bf16*>(y), rows, C,
-                                                                               ld);
-  CG_LAUNCH_CHECK("cg_fill_rows");
+  fill_planar_kernel<<<glue_grid((long long)N * ((C + 7) / 8) * HW), 256, 0, cg_stream(stream)>>>(
+      v, reinterpret_cast<bf16*>(y), N, HW, C, ns);
+  CG_LAUNCH_CHECK("cg_fill_planar");
   return CG_OK;
 }
 
-extern "C" int cg_colsum(const void* dy, float* dv, int64_t rows, int32_t C, int32_t ld, void* stream) {
+extern "C" int cg_colsum(const void* dy, float* dv, int32_t N, int32_t HW, int32_t C, int64_t ns, void* stream) {
   CG_ARCH_GUARD();
-  CG_REQUIRE(ld % 8 == 0, "cg_colsum: ld=%d", ld);
-  CG_REQUIRE(C <= 2048, "cg_colsum: C=%d too wide", C);
-  const int rpb = 256 / ((C + 7) / 8);
-  int gx = (int)((rows + (long long)rpb * 8 - 1) / ((long long)rpb * 8));
-  if (gx > 148 * 4) gx = 148 * 4;
+  CG_REQUIRE(ns % 8 == 0, "cg_colsum: ns");
+  const int C8 = (C + 7) / 8;
+  long long gx = ((long long)N * HW + 2047) / 2048;  // ~8 positions per thread
+  const long long cap = (148LL * 4 + C8 - 1) / C8;
+  if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
-  colsum_kernel<<<gx, 256, 0, cg_stream(stream)>>>(reinterpret_cast<const bf16*>(dy), dv, rows, C, ld);
+  colsum_kernel<<<dim3((int)gx, C8), 256, 0, cg_stream(stream)>>>(reinterpret_cast<const bf16*>(dy), dv, N, HW, C, ns);
   CG_LAUNCH_CHECK("cg_colsum");
   return CG_OK;
 }
 
-extern "C" int cg_add(const void* a, const void* b, void* y, int64_t rows, int32_t C, int32_t a_ld, int32_t b_ld,
-                      int32_t y_ld, void* stream) {
+extern "C" int cg_add(const void* a, const void* b, void* y, int32_t N, int32_t HW, int32_t C, int64_t a_ns, int64_t b_ns,
+                      int64_t y_ns, void* stream) {
   CG_ARCH_GUARD();
-  CG_REQUIRE(C % 8 == 0 && a_ld % 8 == 0 && b_ld % 8 == 0 && y_ld % 8 == 0, "cg_add: C/ld must be multiples of 8");
-  add_kernel<<<cg_ceil_div(rows * (C / 8), 256), 256, 0, cg_stream(stream)>>>(
-      reinterpret_cast<const bf16*>(a), reinterpret_cast<const bf16*>(b), reinterpret_cast<bf16*>(y), rows, C / 8, a_ld,
-      b_ld, y_ld);
+  CG_REQUIRE(C % 8 == 0, "cg_add: C must be a multiple of 8");
+  add_kernel<<<glue_grid((long long)N * (C / 8) * HW), 256, 0, cg_stream(stream)>>>(
+      reinterpret_cast<const bf16*>(a), reinterpret_cast<const bf16*>(b), reinterpret_cast<bf16*>(y), N, HW, C / 8, a_ns,
+      b_ns, y_ns);
   CG_LAUNCH_CHECK("cg_add");
   return CG_OK;
 }

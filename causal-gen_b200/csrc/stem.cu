@@ -12,7 +12,7 @@ constexpr int kMaxCout = 32;
 template <int CIN>
 __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                        const float* __restrict__ b, bf16* __restrict__ y, int R,
-                                                       int Cout, int y_ld) {
+                                                       int Cout, long long y_ns) {
   extern __shared__ float sm[];
   float* s_w = sm;                              // [tap][ci][co]
   float* s_x = sm + 49 * CIN * Cout;            // [ci][kHalo][kHalo]
@@ -43,8 +43,8 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__
       }
   const int h = h0 + ty, wq = w0 + tx;
   if (h < R && wq < R) {
-    bf16* o = y + ((long long)(n * R + h) * R + wq) * y_ld;
-    for (int c8 = 0; c8 < Cout; c8 += 8) *reinterpret_cast<uint4*>(o + c8) = cg_pack8(acc + c8);
+    bf16* o = y + n * y_ns + ((long long)h * R + wq) * 8;  // planar: one 16-byte octet per plane
+    for (int c8 = 0; c8 < Cout; c8 += 8) *reinterpret_cast<uint4*>(o + (long long)(c8 >> 3) * R * R * 8) = cg_pack8(acc + c8);
   }
 }
 
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__
 template <int CIN>
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dy,
                                                          float* __restrict__ dw, float* __restrict__ db, int N, int R,
-                                                         int Cout, int dy_ld) {
+                                                         int Cout, long long dy_ns) {
   __shared__ float s_dy[kT * kT][kMaxCout + 1];
   __shared__ float s_x[CIN * kHalo * kHalo];
   const int nout = Cout * (CIN * 49 + 1);  // + bias column
@@ -69,7 +69,9 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
     __syncthreads();
     for (int i = threadIdx.x; i < kT * kT * Cout; i += 256) {
       int co = i % Cout, p = i / Cout, hh = h0 + p / kT, ww = w0 + p % kT;
-      s_dy[p][co] = (hh < R && ww < R) ? __bfloat162float(dy[((long long)(n * R + hh) * R + ww) * dy_ld + co]) : 0.f;
+      s_dy[p][co] = (hh < R && ww < R)
+                        ? __bfloat162float(dy[n * dy_ns + ((long long)(co >> 3) * R * R + (long long)hh * R + ww) * 8 + (co & 7)])
+                        : 0.f;
     }
     for (int i = threadIdx.x; i < CIN * kHalo * kHalo; i += 256) {
       int cc = i % kHalo, rr = (i / kHalo) % kHalo, ci = i / (kHalo * kHalo);
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
 }  // namespace
 
 extern "C" int cg_stem_fwd(const float* x, const float* w, const float* b, void* y, int32_t N, int32_t Cin, int32_t R,
-                           int32_t Cout, int32_t y_ld, void* stream) {
+                           int32_t Cout, int64_t y_ld, void* stream) {
   CG_ARCH_GUARD();
   CG_REQUIRE((Cin == 1 || Cin == 3) && Cout % 8 == 0 && Cout <= kMaxCout && y_ld % 8 == 0,
              "cg_stem_fwd: Cin=%d Cout=%d", Cin, Cout);
@@ -126,7 +128,7 @@ extern "C" int cg_stem_fwd(const float* x, const float* w, const float* b, void*
 }
 
 extern "C" int cg_stem_wgrad(const float* x, const void* dy, float* dw, float* db, int32_t N, int32_t Cin, int32_t R,
-                             int32_t Cout, int32_t dy_ld, void* stream) {
+                             int32_t Cout, int64_t dy_ld, void* stream) {
   CG_ARCH_GUARD();
   CG_REQUIRE((Cin == 1 || Cin == 3) && Cout <= kMaxCout, "cg_stem_wgrad: Cin=%d Cout=%d", Cin, Cout);
   const int t1 = cg_ceil_div(R, kT);

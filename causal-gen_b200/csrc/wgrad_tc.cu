@@ -3,28 +3,34 @@
 //
 // GEMM view: the reduction (K) dimension is PIXELS, so both operands are "MN-major" (channels contiguous):
 //   D[M][N] (+)= A[M][pixels] * B[N][pixels]
-// One operand is a 128-pixel tile of dY, the other the halo tile of the (re-activated) forward input; the
-// halo tile is staged exactly like in conv_tc.cu, so the 9 taps are again 9 descriptor start offsets
-// into one shared-memory tile, and each tap accumulates into its own TMEM column range.
+// One operand is a 16x8-pixel tile of dY, the other the halo tile of the (re-activated) forward input.  Both are
+// TMA boxes of the planar bf16 layout (N, C/8, H, W, 8) and land in shared memory as channel-octet planes, so
+// -- exactly like conv_tc.cu -- the 9 taps are 9 descriptor start offsets into one halo tile, and each tap
+// accumulates into its own TMEM column range.  Out-of-image pixels are zero-filled by the TMA unit.
 // The wide side (<=128 channels per CTA) sits on M, the narrow side (<=48 channels for 3x3, <=64 for 1x1)
 // on N.  Each persistent CTA accumulates over all of its pixel tiles in TMEM and flushes once with fp32
 // atomics straight into the OIHW gradient tensor.
+//
+// Warp roles: 0-3 flush (TMEM lane quarters), 4 MMA issuer + TMEM owner, 5 TMA producer, 6-9 transform
+// (re-apply the forward pre-activation to the X tile in place).
+#include <cuda.h>
+
 #include <cmath>
 
 #include "cg_common.cuh"
 
 namespace {
 
-constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = 4;
-constexpr int kLoadWarp0 = 5;
-constexpr int kLoadWarps = 8;
-constexpr int kThreads = (kLoadWarp0 + kLoadWarps) * 32;
-constexpr int kLoadThreads = kLoadWarps * 32;
+constexpr int kTmaWarp = 5;
+constexpr int kXfWarp0 = 6;
+constexpr int kXfWarps = 4;
+constexpr int kThreads = (kXfWarp0 + kXfWarps) * 32;  // 320
+constexpr int kXfThreads = kXfWarps * 32;
 constexpr int kStages = 3;
-constexpr int kPlaneHalo = 2976;  // 18*10*16 padded (see conv_tc.cu)
-constexpr int kPlaneFlat = 2080;  // 16*8*16 padded
-constexpr int kStageBytes = 16 * kPlaneHalo + 8 * kPlaneFlat;  // 64256, covers both operand assignments
+constexpr int kPlaneHalo = 2880;  // 18*10*16
+constexpr int kPlaneFlat = 2048;  // 16*8*16
+constexpr int kStageBytes = 16 * kPlaneHalo + 8 * kPlaneFlat;  // 62464, covers both operand assignments
 constexpr int kHdrBytes = 256;
 constexpr int kMaxChunks = 24;
 
@@ -33,82 +39,70 @@ struct WChunk {
   int16_t c0, nc;
 };
 
-struct WParams {
+struct alignas(64) WParams {
+  CUtensorMap x_map[CG_MAX_SRC];
+  CUtensorMap dy_map;
   cg_wgrad_args a;
   WChunk pch[kMaxChunks], qch[kMaxChunks];
+  uint32_t x_bytes[CG_MAX_SRC], dy_bytes;  // TMA transaction bytes per box
   int nP, nQ;
-  int x_on_m, ntaps, halo;
-  int tiles_x, ntiles, Hp;
-  long long P;
+  int x_on_m, ntaps, halo, flat;
+  int tiles_x, tiles_per_img, ntiles;
   uint32_t tmem_cols;
 };
 
 struct Geom {
-  int v0, w0;
-  long long p0;
+  int n, h0, w0;
 };
 
 __device__ __forceinline__ Geom geom_of(const WParams& P, int tile) {
   Geom g;
-  if (P.halo) {
-    int tv = tile / P.tiles_x;
-    g.v0 = tv * 16;
-    g.w0 = (tile - tv * P.tiles_x) * 8;
-    g.p0 = 0;
+  if (P.flat) {
+    g.n = tile * 128;
+    g.h0 = g.w0 = 0;
   } else {
-    g.v0 = g.w0 = 0;
-    g.p0 = (long long)tile * 128;
+    g.n = tile / P.tiles_per_img;
+    const int r = tile - g.n * P.tiles_per_img;
+    const int ty = r / P.tiles_x;
+    g.h0 = ty * 16;
+    g.w0 = (r - ty * P.tiles_x) * 8;
   }
   return g;
 }
 
-// Issue the cp.async copies (zero-fill for padding / out-of-image pixels) of one operand tile as
-// channel-octet planes.  `with_halo`: 18x10 pixels around the tile (3x3 forward input), else the tile's own
-// 128 pixels in [16][8] order.
-__device__ __forceinline__ void stage_tile_async(const WParams& P, uint8_t* dst, int plane, const void* ptr, int ld,
-                                                 int bcast, int c0, int nc8, bool with_halo, const Geom& g, int lt) {
-  const int H = P.a.H, W = P.a.W, N = P.a.N;
-  const int npix = with_halo ? 180 : 128;
-  const int items = npix * nc8;
-  const uint32_t dst_u = cg_smem_u32(dst);
-  const bf16* base = reinterpret_cast<const bf16*>(ptr) + c0;
-  for (int it = lt; it < items; it += kLoadThreads) {
-    const int c8 = it % nc8;
-    const int pix = it / nc8;
-    bool valid;
-    long long off;
-    if (P.halo) {
-      int rr, cc;
-      if (with_halo) { rr = pix / 10; cc = pix - rr * 10; } else { rr = (pix >> 3) + 1; cc = (pix & 7) + 1; }
-      const int v = g.v0 - 1 + rr, w = g.w0 - 1 + cc;
-      const int n = v / P.Hp, h = v - n * P.Hp;
-      valid = (v >= 0) && (w >= 0) && (w < W) && (n < N) && (h < H);
-      off = bcast ? (long long)n * ld : ((long long)(n * H + h) * W + w) * ld;
-    } else {
-      const long long p = g.p0 + pix;
-      valid = p < P.P;
-      off = bcast ? (p / ((long long)H * W)) * ld : p * ld;
-    }
-    cp_async16(dst_u + c8 * plane + pix * 16, valid ? base + off + c8 * 8 : base, valid ? 16u : 0u);
-  }
+__device__ __forceinline__ void tma4(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::
+          "r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma3(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
+          "r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
 }
 
-// in-place activation of the slots this thread copied (same index walk as stage_tile_async)
-__device__ __forceinline__ void act_tile_inplace(uint8_t* dst, int plane, int act, int nc8, bool with_halo, int lt) {
-  const int items = (with_halo ? 180 : 128) * nc8;
-  for (int it = lt; it < items; it += kLoadThreads) {
-    uint4* p = reinterpret_cast<uint4*>(dst + (it % nc8) * plane + (it / nc8) * 16);
-    float f[8];
-    cg_unpack8(*p, f);
+__device__ __forceinline__ uint4 wact8(uint4 u, int act) {
+  if (act == CG_ACT_RELU) {
+    const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = cg_act(f[i], act);
-    *p = cg_pack8(f);
+    for (int i = 0; i < 4; ++i) h[i] = __hmax2(h[i], z);
+    return u;
   }
+  float f[8];
+  cg_unpack8(u, f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = cg_gelu(f[i]);
+  return cg_pack8(f);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_constant__ WParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0..2] full, [3..5] empty, [6] done
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0..2] landed, [3..5] full, [6..8] empty, [9] done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 128);
   uint8_t* stages = smem + kHdrBytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -124,21 +118,18 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   const int planeP = p_halo ? kPlaneHalo : kPlaneFlat;
   const int planeQ = q_halo ? kPlaneHalo : kPlaneFlat;
   const int q_off = 16 * planeP;  // Q tile sits after the 16 P planes of the stage
+  const int act = P.a.act;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(BAR(i), kLoadWarps);
-      mbar_init(BAR(3 + i), 1);
+      mbar_init(BAR(i), 1);
+      mbar_init(BAR(3 + i), kXfWarps);
+      mbar_init(BAR(6 + i), 1);
     }
-    mbar_init(BAR(6), 1);
+    mbar_init(BAR(9), 1);
     mbar_fence_init();
   }
   if (warp == kMmaWarp) tmem_alloc(cg_smem_u32(tmem_slot), P.tmem_cols);
-  // rows of A beyond the chunk's channels are never loaded: clear them once so no NaN bit patterns
-  // ever enter the tensor core (their D rows are discarded anyway)
-  for (int i = threadIdx.x; i < kStages * kStageBytes / 16; i += kThreads)
-    reinterpret_cast<uint4*>(stages)[i] = make_uint4(0, 0, 0, 0);
-  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -149,83 +140,82 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
       const uint32_t idesc = umma_idesc_bf16(128, Nq, 1, 1);
       const uint32_t pitchP = p_halo ? 160u : 128u, pitchQ = q_halo ? 160u : 128u;
       // descriptors built once; per MMA only the start-address field advances (16-byte units)
-      const uint64_t p_desc0 = umma_desc(cg_smem_u32(stages), pitchP, (uint32_t)planeP);
-      const uint64_t q_desc0 = umma_desc(cg_smem_u32(stages) + q_off, pitchQ, (uint32_t)planeQ);
+      const uint64_t p_d = umma_desc(cg_smem_u32(stages), pitchP, (uint32_t)planeP);
+      const uint64_t q_d = umma_desc(cg_smem_u32(stages) + q_off, pitchQ, (uint32_t)planeQ);
+      const uint32_t p_hi = (uint32_t)(p_d >> 32), q_hi = (uint32_t)(q_d >> 32);
+      const uint32_t p_lo0 = (uint32_t)p_d, q_lo0 = (uint32_t)q_d;
+      auto D64 = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
       const uint32_t stage16 = (uint32_t)kStageBytes >> 4;
       const uint32_t ksP = (2u * pitchP) >> 4, ksQ = (2u * pitchQ) >> 4;
+      const int ready0 = (act == CG_ACT_NONE) ? 0 : 3;
       uint32_t stage = 0, phase = 0, accum_any = 0;
       for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-        mbar_wait(BAR(stage), phase);
+        mbar_wait(BAR(ready0 + stage), phase);
         tc_fence_after();
-        const uint64_t pd = p_desc0 + stage * stage16, qd = q_desc0 + stage * stage16;
+        const uint32_t plo = p_lo0 + stage * stage16, qlo = q_lo0 + stage * stage16;
         for (int t = 0; t < P.ntaps; ++t) {
           // the un-shifted operand of a 3x3 problem is staged without halo: it starts at its own pixel 0
           const uint32_t toff = P.halo ? (uint32_t)((t / 3) * 10 + (t % 3)) : 0u;
-          uint64_t ad = pd + (p_halo ? toff : 0u), bd = qd + (q_halo ? toff : 0u);
+          uint32_t alo = plo + (p_halo ? toff : 0u), blo = qlo + (q_halo ? toff : 0u);
           const uint32_t d = tmem_base + (uint32_t)(t * Nq);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
-            tc_mma_bf16(d, ad, bd, idesc, accum_any | (uint32_t)(ks > 0));
-            ad += ksP;
-            bd += ksQ;
+            tc_mma_bf16(d, D64(p_hi, alo), D64(q_hi, blo), idesc, accum_any | (uint32_t)(ks > 0));
+            alo += ksP;
+            blo += ksQ;
           }
         }
         accum_any = 1;
-        tc_commit(BAR(3 + stage));
+        tc_commit(BAR(6 + stage));
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
-      tc_commit(BAR(6));
+      tc_commit(BAR(9));
     }
-  } else if (warp >= kLoadWarp0) {
-    // loaders: cp.async copies issued kStages-1 tiles ahead; activation applied in place afterwards
-    const int lt = threadIdx.x - kLoadWarp0 * 32;
-    constexpr int D = kStages - 1;
-    uint32_t stage = 0, phase = 0;
-    uint32_t q_stage[kStages];
-    int q_head = 0, q_len = 0;
-    const cg_src& xs = P.a.src[p_is_x ? pc.src : qc.src];
-    auto finalize = [&](uint32_t st) {
-      if (P.a.act != CG_ACT_NONE) {
-        uint8_t* sP = stages + st * kStageBytes;
-        if (p_is_x) act_tile_inplace(sP, planeP, P.a.act, pc.nc / 8, p_halo, lt);
-        else act_tile_inplace(sP + q_off, planeQ, P.a.act, qc.nc / 8, q_halo, lt);
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(st));
-    };
-    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-      const Geom g = geom_of(P, tile);
-      mbar_wait(BAR(3 + stage), phase ^ 1u);
-      uint8_t* sP = stages + stage * kStageBytes;
-      uint8_t* sQ = sP + q_off;
-      if (p_is_x) {
-        stage_tile_async(P, sP, planeP, xs.ptr, xs.ld, xs.bcast, pc.c0, pc.nc / 8, p_halo, g, lt);
-        stage_tile_async(P, sQ, planeQ, P.a.dy, P.a.dy_ld, 0, qc.c0, qc.nc / 8, false, g, lt);
-      } else {
-        stage_tile_async(P, sP, planeP, P.a.dy, P.a.dy_ld, 0, pc.c0, pc.nc / 8, false, g, lt);
-        stage_tile_async(P, sQ, planeQ, xs.ptr, xs.ld, xs.bcast, qc.c0, qc.nc / 8, q_halo, g, lt);
-      }
-      cp_async_commit();
-      q_stage[(q_head + q_len) % kStages] = stage;
-      ++q_len;
-      if (++stage == kStages) { stage = 0; phase ^= 1u; }
-      if (q_len == D) {
-        cp_async_wait<D - 1>();
-        finalize(q_stage[q_head]);
-        q_head = (q_head + 1) % kStages;
-        --q_len;
+  } else if (warp == kTmaWarp) {
+    if (lane == 0) {
+      const int xs_i = p_is_x ? pc.src : qc.src;
+      const CUtensorMap* xmap = &P.x_map[xs_i];
+      const uint32_t tx = P.x_bytes[xs_i] + P.dy_bytes;
+      const int x_oct = (p_is_x ? pc.c0 : qc.c0) >> 3, y_oct = (p_is_x ? qc.c0 : pc.c0) >> 3;
+      const uint32_t x_off = p_is_x ? 0u : (uint32_t)q_off, y_off = p_is_x ? (uint32_t)q_off : 0u;
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+        const Geom g = geom_of(P, tile);
+        mbar_wait(BAR(6 + stage), phase ^ 1u);
+        mbar_expect_tx(BAR(stage), tx);
+        const uint32_t sbase = cg_smem_u32(stages + stage * kStageBytes);
+        if (P.flat) {
+          tma3(sbase + x_off, xmap, 0, g.n, x_oct, BAR(stage));
+          tma3(sbase + y_off, &P.dy_map, 0, g.n, y_oct, BAR(stage));
+        } else {
+          tma4(sbase + x_off, xmap, (g.w0 - P.halo) * 8, g.h0 - P.halo, x_oct, g.n, BAR(stage));
+          tma4(sbase + y_off, &P.dy_map, g.w0 * 8, g.h0, y_oct, g.n, BAR(stage));
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
-    cp_async_wait<0>();
-    while (q_len > 0) {
-      finalize(q_stage[q_head]);
-      q_head = (q_head + 1) % kStages;
-      --q_len;
+  } else if (warp >= kXfWarp0) {
+    if (act != CG_ACT_NONE) {
+      const int xt = threadIdx.x - kXfWarp0 * 32;
+      const int xs_i = p_is_x ? pc.src : qc.src;
+      const int n16 = (int)(P.x_bytes[xs_i] >> 4);
+      const uint32_t x_off = p_is_x ? 0u : (uint32_t)q_off;
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+        if (lane == 0) mbar_wait(BAR(stage), phase);
+        __syncwarp();
+        uint4* base = reinterpret_cast<uint4*>(stages + stage * kStageBytes + x_off);
+        for (int i = xt; i < n16; i += kXfThreads) base[i] = wact8(base[i], act);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(3 + stage));
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
     }
   } else {
-    // epilogue: lane m of TMEM = channel m of the P chunk
-    mbar_wait(BAR(6), 0);
+    // flush: lane m of TMEM = channel m of the P chunk
+    if (lane == 0) mbar_wait(BAR(9), 0);
+    __syncwarp();
     tc_fence_after();
     const int m = warp * 32 + lane;
     const int kk = P.a.ksize * P.a.ksize;
@@ -275,17 +265,19 @@ extern "C" int cg_conv2d_wgrad(const cg_wgrad_args* a, void* stream) {
   CG_ARCH_GUARD();
   CG_REQUIRE(a != nullptr && (a->ksize == 1 || a->ksize == 3), "cg_conv2d_wgrad: ksize");
   CG_REQUIRE(a->nsrc >= 1 && a->nsrc <= CG_MAX_SRC, "cg_conv2d_wgrad: nsrc %d", a->nsrc);
-  CG_REQUIRE(a->dy != nullptr && ((uintptr_t)a->dy & 15) == 0 && a->dy_c % 16 == 0 && a->dy_ld % 8 == 0,
-             "cg_conv2d_wgrad: dy (c=%d ld=%d)", a->dy_c, a->dy_ld);
+  CG_REQUIRE(a->dy != nullptr && ((uintptr_t)a->dy & 15) == 0 && a->dy_c % 16 == 0 && a->dy_ns % 8 == 0,
+             "cg_conv2d_wgrad: dy (c=%d ns=%lld)", a->dy_c, (long long)a->dy_ns);
   CG_REQUIRE(a->taps == 1 || a->taps == a->ksize * a->ksize, "cg_conv2d_wgrad: taps %d", a->taps);
   WParams kp;
   kp.a = *a;
   kp.ntaps = a->taps;
   kp.halo = (a->ksize == 3 && a->taps == 9) ? 1 : 0;
+  kp.flat = (a->H == 1 && a->W == 1) ? 1 : 0;
+  CG_REQUIRE(!(kp.flat && kp.halo), "cg_conv2d_wgrad: 3x3 on a 1x1 image must use taps=1");
   int xtot = 0;
   for (int s = 0; s < a->nsrc; ++s) {
     CG_REQUIRE(a->src[s].ptr != nullptr && ((uintptr_t)a->src[s].ptr & 15) == 0 && a->src[s].C % 16 == 0 &&
-                   a->src[s].ld % 8 == 0,
+                   a->src[s].ns % 8 == 0,
                "cg_conv2d_wgrad: src %d", s);
     xtot += a->src[s].C;
   }
@@ -309,14 +301,31 @@ extern "C" int cg_conv2d_wgrad(const cg_wgrad_args* a, void* stream) {
     for (int s = 0; s < a->nsrc; ++s) ok = ok && split(kp.qch, kp.nQ, s, a->src[s].C, nmax);
   }
   CG_REQUIRE(ok, "cg_conv2d_wgrad: too many channel chunks");
-  kp.Hp = a->H + 1;
-  kp.P = (long long)a->N * a->H * a->W;
-  if (kp.halo) {
-    kp.tiles_x = (a->W + 7) / 8;
-    kp.ntiles = ((a->N * kp.Hp + 15) / 16) * kp.tiles_x;
+  // tensor maps: the X operand carries the halo for 3x3; box octet counts = chunk size of its role
+  const int x_box_oct = kp.x_on_m ? 16 : nmax / 8, y_box_oct = kp.x_on_m ? nmax / 8 : 16;
+  const int xw = kp.halo ? 80 : 64, xh = kp.halo ? 18 : 16;
+  const int xplane = kp.halo ? kPlaneHalo : kPlaneFlat;
+  for (int s = 0; s < a->nsrc; ++s) {
+    const int c8 = a->src[s].C / 8;
+    const int boct = c8 < x_box_oct ? c8 : x_box_oct;
+    int rc = cg_make_planar_map(&kp.x_map[s], a->src[s].ptr, a->src[s].ns, a->N, a->H, a->W, c8, kp.flat, xw, xh, boct);
+    if (rc != CG_OK) return rc;
+    kp.x_bytes[s] = (uint32_t)boct * xplane;
+  }
+  {
+    const int c8 = a->dy_c / 8;
+    const int boct = c8 < y_box_oct ? c8 : y_box_oct;
+    int rc = cg_make_planar_map(&kp.dy_map, a->dy, a->dy_ns, a->N, a->H, a->W, c8, kp.flat, 64, 16, boct);
+    if (rc != CG_OK) return rc;
+    kp.dy_bytes = (uint32_t)boct * kPlaneFlat;
+  }
+  if (kp.flat) {
+    kp.tiles_x = kp.tiles_per_img = 1;
+    kp.ntiles = (a->N + 127) / 128;
   } else {
-    kp.tiles_x = 1;
-    kp.ntiles = (int)((kp.P + 127) / 128);
+    kp.tiles_x = (a->W + 7) / 8;
+    kp.tiles_per_img = kp.tiles_x * ((a->H + 15) / 16);
+    kp.ntiles = a->N * kp.tiles_per_img;
   }
   uint32_t cols = 32;
   while (cols < (uint32_t)(kp.ntaps * nmax)) cols <<= 1;
@@ -345,7 +354,7 @@ extern "C" int cg_conv2d_wgrad(const cg_wgrad_args* a, void* stream) {
   wgrad_tc_kernel<<<dim3(gx, combos), kThreads, smem_bytes, cg_stream(stream)>>>(kp);
   CG_LAUNCH_CHECK("cg_conv2d_wgrad");
   if (a->dbias != nullptr) {
-    int rc = cg_colsum(a->dy, a->dbias, kp.P, a->cout_l, a->dy_ld, stream);
+    int rc = cg_colsum(a->dy, a->dbias, a->N, a->H * a->W, a->cout_l, a->dy_ns, stream);
     if (rc != CG_OK) return rc;
   }
   return CG_OK;

@@ -47,21 +47,25 @@ int cg_device_sms(void);
 #define CG_MAX_SRC 3
 #define CG_MAX_SEG 4
 
+/* Activation layout: bf16 "channel-octet planar" (N, C/8, H, W, 8) -- element (n,c,h,w) lives at
+ *   ptr + n*ns + (c/8)*H*W*8 + (h*W+w)*8 + c%8        (ns = sample stride in elements)
+ * so a channel slice [c0, c0+C) with c0 % 8 == 0 of a wider tensor is again a valid operand (same ns,
+ * ptr advanced by (c0/8)*H*W*8).  A TMA box of this layout is directly the tcgen05 shared-memory operand. */
 typedef struct {
-  const void* ptr;  /* bf16, (N,H,W,ld) -- or (N,ld) when bcast!=0 (spatially constant parents) */
-  int32_t C;        /* channels taken from this source, multiple of 16 */
-  int32_t ld;       /* channel pitch in elements */
-  int32_t bcast;    /* 1: per-sample vector broadcast over H,W (zero outside the image) */
+  const void* ptr;  /* first channel-octet plane of the view */
+  int64_t ns;       /* sample stride in elements (multiple of 8) */
+  int32_t C;        /* channels taken from this source, multiple of 16 (zero padded) */
   int32_t _pad;
 } cg_src;
 
 typedef struct {
-  void* ptr;        /* destination of output channels [c0, c0+cn) */
-  const void* add;  /* optional bf16 tensor added after everything else (residual / accumulate) */
-  const void* add2; /* optional second bf16 addend (h + p_feat + z_proj(...) in one pass, src/vae.py:292-294) */
-  const void* mul;  /* optional bf16 pre-activation tensor x: result *= act'(x)  (backward) */
+  void* ptr;        /* destination of output channels [c0, c0+cn): bf16 planar view, or fp32 rows */
+  const void* add;  /* optional bf16 planar tensor added after everything else (residual / accumulate) */
+  const void* add2; /* optional second addend (h + p_feat + z_proj(...) in one pass, src/vae.py:292-294) */
+  const void* mul;  /* optional bf16 planar pre-activation tensor x: result *= act'(x)  (backward) */
+  int64_t ns;       /* bf16: sample stride; CG_F32: row pitch of a (N*H*W, ns) fp32 row tensor */
+  int64_t add_ns, add2_ns, mul_ns;
   int32_t c0, cn;   /* c0 multiple of 16, cn multiple of 8 */
-  int32_t ld, add_ld, add2_ld, mul_ld;
   int32_t dtype;    /* CG_BF16 or CG_F32 */
   int32_t mul_act;  /* activation whose derivative is applied with `mul` */
 } cg_seg;
@@ -113,8 +117,9 @@ typedef struct {
   int32_t N, H, W, ksize, act;
   int32_t nsrc;
   cg_src src[CG_MAX_SRC];  /* forward inputs (activation re-applied on load) */
-  const void* dy;          /* bf16 (N,H,W,dy_ld) gradient of the conv output */
-  int32_t dy_c, dy_ld;     /* padded channels (multiple of 16), pitch */
+  const void* dy;          /* bf16 planar gradient of the conv output */
+  int64_t dy_ns;           /* its sample stride */
+  int32_t dy_c, _pad;      /* padded channels (multiple of 16) */
   float* dw;               /* fp32 OIHW gradient, ACCUMULATED into (atomics) */
   float* dbias;            /* fp32 [cout_l] accumulated, or NULL */
   int32_t cout_l, cin_l;   /* logical dims of dw */
@@ -125,34 +130,34 @@ typedef struct {
 /* dW += sum_pixels dy (x) act(cat(src)) shifted per tap; dbias += sum_pixels dy */
 int cg_conv2d_wgrad(const cg_wgrad_args* a, void* stream);
 
-/* 7x7 stem, fp32 NCHW image in -> bf16 NHWC out (src/vae.py:104-110,126) and its weight grad */
+/* 7x7 stem, fp32 NCHW image in -> bf16 planar out (src/vae.py:104-110,126) and its weight grad */
 int cg_stem_fwd(const float* x, const float* w, const float* b, void* y, int32_t N, int32_t Cin,
-                int32_t R, int32_t Cout, int32_t y_ld, void* stream);
+                int32_t R, int32_t Cout, int64_t y_ns, void* stream);
 int cg_stem_wgrad(const float* x, const void* dy, float* dw, float* db, int32_t N, int32_t Cin,
-                  int32_t R, int32_t Cout, int32_t dy_ld, void* stream);
+                  int32_t R, int32_t Cout, int64_t dy_ns, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Resampling: F.avg_pool2d (src/vae.py:79-83), F.interpolate nearest + learned bias
- * (src/vae.py:251-262), F.pad odd resolutions (src/vae.py:130-132); NHWC bf16
+ * (src/vae.py:251-262), F.pad odd resolutions (src/vae.py:130-132); bf16 planar, *_ns = sample strides
  * ------------------------------------------------------------------------------------- */
 int cg_avgpool_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, int32_t d,
-                   int32_t x_ld, int32_t y_ld, int32_t pad_to, void* stream);
+                   int64_t x_ns, int64_t y_ns, int32_t pad_to, void* stream);
 /* dx (+)= avgpool^T(dy); accumulate!=0 adds into dx */
 int cg_avgpool_bwd(const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t C, int32_t d,
-                   int32_t dy_ld, int32_t dx_ld, int32_t pad_to, int32_t accumulate, void* stream);
+                   int64_t dy_ns, int64_t dx_ns, int32_t pad_to, int32_t accumulate, void* stream);
 /* y[n,h,w,c] = bias[c,h,w] + x[n,h/s,w/s,c]; bias fp32 (C,Ho,Wo) reference layout or NULL.
  * Ho need not be a multiple of Hi (7 -> 8 style): source index floor(h*Hi/Ho). */
 int cg_upsample_fwd(const void* x, const float* bias, void* y, int32_t N, int32_t Hi, int32_t Ho,
-                    int32_t C, int32_t x_ld, int32_t y_ld, void* stream);
+                    int32_t C, int64_t x_ns, int64_t y_ns, void* stream);
 /* dx (+)= sum over replicas of dy; dbias += sum over batch of dy (fp32, may be NULL) */
 int cg_upsample_bwd(const void* dy, void* dx, float* dbias, int32_t N, int32_t Hi, int32_t Ho,
-                    int32_t C, int32_t dy_ld, int32_t dx_ld, int32_t accumulate, void* stream);
+                    int32_t C, int64_t dy_ns, int64_t dx_ns, int32_t accumulate, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Latent blocks: sample_gaussian + gaussian_kl fused (src/vae.py:14-30,268-269)
  *   q,p: fp32 NHWC (npix, 32) = [loc(16) | logscale(16)]; eps fp32 NCHW (N,16,H,W) (reference
  *   layout, drawn by the caller) or NULL -> in-kernel Philox(seed, block offset).
- *   z_bf16: (npix, z_ld) conv operand; z_f32: NCHW (N,16,H,W) fp32 or NULL (abduct output);
+ *   z_bf16: bf16 planar (N,2,H,W,8) conv operand with sample stride z_ns; z_f32: NCHW (N,16,H,W) fp32 or NULL (abduct output);
  *   kl_out: fp32 [N] += sum over (16,H,W) of the block's KL.
  * ------------------------------------------------------------------------------------- */
 typedef struct {
@@ -160,7 +165,7 @@ typedef struct {
   const float* eps; uint64_t seed; uint64_t offset;
   const uint64_t* seed_dev; /* optional device counter added to seed (graph-replayable noise) */
   float log_t;            /* log temperature added to both logscales (0 when t is None) */
-  void* z_bf16; int32_t z_ld;
+  void* z_bf16; int64_t z_ns;
   float* z_f32;
   float* eps_out;         /* optional: NCHW eps actually used (needed by backward in Philox mode) */
   float* kl_out;          /* [N] accumulated, or NULL */
@@ -170,14 +175,14 @@ typedef struct {
 int cg_latent_fwd(const cg_latent_args* a, void* stream);
 
 /* gradients of  sum_n g_kl * kl[n]  +  <dz, z>  w.r.t. q and p statistics, written as bf16
- * into the conv-output-gradient buffers dq (npix,dq_ld) and dp (npix,dp_ld) channels [0,32) */
+ * into channels [0,32) of the bf16 planar conv-output-gradient buffers dq / dp */
 typedef struct {
   const float* q; const float* p; int32_t q_ld, p_ld;
   const float* eps;           /* NCHW eps used in forward, or NULL -> regenerate Philox(seed, offset) */
   uint64_t seed; uint64_t offset; const uint64_t* seed_dev;
-  const void* dz; int32_t dz_ld;   /* bf16 gradient wrt z (npix, dz_ld) or NULL */
+  const void* dz; int64_t dz_ns;   /* bf16 planar gradient wrt z or NULL */
   float g_kl;                 /* d loss / d kl[n]  (= beta / (B * C*H*W)) */
-  void* dq; int32_t dq_ld; void* dp; int32_t dp_ld;
+  void* dq; int64_t dq_ns; void* dp; int64_t dp_ns;
   int32_t N, HW, zdim, mode;
 } cg_latent_bwd_args;
 int cg_latent_bwd(const cg_latent_bwd_args* a, void* stream);
@@ -191,15 +196,15 @@ int cg_latent_mix(const float* z, const float* q_loc, const float* q_ls, const f
  * Likelihoods
  * ------------------------------------------------------------------------------------- */
 /* DGaussNet (src/vae.py:322-422): 1x1 heads fused with the discretised-Gaussian NLL.
- * h bf16 (npix, h_ld) with Cw channels; x fp32 NCHW (N,C,H,W); w_* fp32 (C,Cw); C in {1,3}. */
+ * h bf16 planar with Cw channels, sample stride h_ns; x fp32 NCHW (N,C,H,W); w_* fp32 (C,Cw); C in {1,3}. */
 typedef struct {
-  const void* h; int32_t h_ld, Cw;
+  const void* h; int64_t h_ns; int32_t Cw, _pad0;
   const float* x;
   const float *w_loc, *b_loc, *w_ls, *b_ls, *w_co, *b_co;   /* w_co/b_co NULL when C==1 */
   int32_t N, HW, C;
   float* nll;        /* fwd: [N] accumulated: -mean over (C,H,W) of log-prob */
   float g;           /* bwd: d loss / d nll[n]  (= 1/B) */
-  void* dh; int32_t dh_ld;                  /* bwd: bf16 (npix, dh_ld) written */
+  void* dh; int64_t dh_ns;                  /* bwd: bf16 planar, written */
   float *dw_loc, *db_loc, *dw_ls, *db_ls, *dw_co, *db_co;   /* bwd: accumulated */
 } cg_dgauss_args;
 int cg_dgauss_nll_fwd(const cg_dgauss_args* a, void* stream);
@@ -212,11 +217,11 @@ int cg_dgauss_sample(const cg_dgauss_args* a, float* x_out, float* scale_out, co
 /* DmolNet (src/dmol.py:24-245): 1x1 conv to 100 channels fused with the mixture loss.
  * w (100,Cw) b (100) fp32; x fp32 NCHW (N,3,H,W). */
 typedef struct {
-  const void* h; int32_t h_ld, Cw;
+  const void* h; int64_t h_ns; int32_t Cw, _pad0;
   const float* x; const float* w; const float* b;
   int32_t N, HW;
   float* nll;   /* fwd [N] accumulated */
-  float g; void* dh; int32_t dh_ld; float* dw; float* db;   /* bwd */
+  float g; void* dh; int64_t dh_ns; float* dw; float* db;   /* bwd */
 } cg_dmol_args;
 int cg_dmol_loss_fwd(const cg_dmol_args* a, void* stream);
 int cg_dmol_loss_bwd(const cg_dmol_args* a, void* stream);
@@ -240,25 +245,27 @@ int cg_cf_combine(const float* x, const float* rec_loc, const float* rec_scale, 
  * ------------------------------------------------------------------------------------- */
 /* uint8 (N,C,H,W) -> fp32 NCHW (x-127.5)/127.5 */
 int cg_normalise_u8(const uint8_t* x8, float* x, int64_t n, void* stream);
-/* parents (N,ctx,R,R) fp32 [sampled at pixel (0,0)] or (N,ctx) -> bf16 (N,ld) zero padded;
- * channels >= drop_from multiplied by drop_scale (conditioning dropout, src/vae.py:244-247) */
-int cg_parents_pack(const float* pa, int64_t sample_stride, int64_t chan_stride, void* out,
-                    int32_t N, int32_t ctx, int32_t ld, int32_t drop_from, float drop_scale,
-                    void* stream);
-int cg_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t N, int32_t C, int32_t HW, int32_t ld,
-                             void* stream);
-int cg_nhwc_bf16_to_nchw_f32(const void* x, float* y, int32_t N, int32_t C, int32_t HW, int32_t ld,
-                             void* stream);
-/* fp32 NHWC statistics slice [c0,c0+C) (+add) -> fp32 NCHW (abduct's q_loc/q_logscale dict entries) */
+/* parents (N,ctx,R,R) fp32 [sampled at pixel (0,0)] or (N,ctx) -> bf16 planar (N, ctx16/8, H, W, 8), spatially
+ * constant, zero padded channels; channels >= drop_from multiplied by drop_scale (conditioning dropout,
+ * src/vae.py:244-247).  This is the materialised parents[..., :res, :res] of src/vae.py:241 at bf16. */
+int cg_parents_plane(const float* pa, int64_t sample_stride, int64_t chan_stride, void* out, int32_t N,
+                     int32_t ctx, int32_t C, int32_t HW, int64_t ns, int32_t drop_from, float drop_scale,
+                     void* stream);
+/* fp32 NCHW (N,C,H,W) <-> bf16 planar (latents in / out) */
+int cg_nchw_f32_to_planar(const float* x, void* y, int32_t N, int32_t C, int32_t HW, int64_t ns,
+                          void* stream);
+int cg_planar_to_nchw_f32(const void* x, float* y, int32_t N, int32_t C, int32_t HW, int64_t ns,
+                          void* stream);
+/* fp32 row statistics slice [c0,c0+C) (+add) -> fp32 NCHW (abduct's q_loc/q_logscale dict entries) */
 int cg_stats_to_nchw(const float* src, int32_t ld, int32_t c0, float add, float* dst, int32_t N, int32_t C,
                      int32_t HW, void* stream);
-/* y[n, :] = v[:] for every pixel (decoder initial state bias[1].repeat, src/vae.py:232) */
-int cg_fill_rows(const float* v, void* y, int64_t rows, int32_t C, int32_t ld, void* stream);
-/* dv[c] += sum_rows dy[row,c] (fp32 accumulate): bias gradients */
-int cg_colsum(const void* dy, float* dv, int64_t rows, int32_t C, int32_t ld, void* stream);
-/* y = a + b (bf16, same pitch rules) */
-int cg_add(const void* a, const void* b, void* y, int64_t rows, int32_t C, int32_t a_ld, int32_t b_ld,
-           int32_t y_ld, void* stream);
+/* y[n, c, :] = v[c] for every pixel (decoder initial state bias[1].repeat, src/vae.py:232) */
+int cg_fill_planar(const float* v, void* y, int32_t N, int32_t HW, int32_t C, int64_t ns, void* stream);
+/* dv[c] += sum_{n,pixels} dy[n,c,pixel] (fp32 accumulate): bias gradients */
+int cg_colsum(const void* dy, float* dv, int32_t N, int32_t HW, int32_t C, int64_t ns, void* stream);
+/* y = a + b (bf16 planar) */
+int cg_add(const void* a, const void* b, void* y, int32_t N, int32_t HW, int32_t C, int64_t a_ns, int64_t b_ns,
+           int64_t y_ns, void* stream);
 
 /* kl rows (nblk, N): per-block per-sample KL sums.  kl_pp[n] = kl_scale * sum_blk kl[blk][n];
  * elbo = mean(nll) + beta*mean(kl_pp)  (src/vae.py:451-458); out[3] = {elbo,nll,kl} */

@@ -31,17 +31,21 @@ def rnd(*shape, scale=1.0, seed=0):
 
 
 def nhwc_bf16(x_nchw, pad_to=None):
-    """(N,C,H,W) fp32 -> zero padded NHWC bf16 buffer"""
-    from causalgen_b200.ops import round16
-    N, Cc, H, W = x_nchw.shape
-    Cp = pad_to or round16(Cc)
-    out = torch.zeros(N, H, W, Cp, device=DEV, dtype=torch.bfloat16)
-    out[..., :Cc] = x_nchw.permute(0, 2, 3, 1).to(torch.bfloat16)
-    return out
+    """(N,C,H,W) fp32 -> zero padded channel-octet planar bf16 buffer (N, C/8, H, W, 8)"""
+    from causalgen_b200.ops import planar_from_nchw
+    return planar_from_nchw(x_nchw, pad_to)
 
 
-def to_nchw(t_nhwc, C):
-    return t_nhwc[..., :C].permute(0, 3, 1, 2).float()
+def to_nchw(t, C):
+    """planar bf16 (N,C8,H,W,8) or fp32 rows (N,H,W,C) -> (N,C,H,W) float"""
+    if t.dtype == torch.bfloat16:
+        N, C8, H, W, _ = t.shape
+        return t.permute(0, 1, 4, 2, 3).reshape(N, C8 * 8, H, W)[:, :C].float()
+    return t[..., :C].permute(0, 3, 1, 2).float()
+
+
+def ns_of(t):
+    return t.stride(0)
 
 
 def act_fn(a):
@@ -75,12 +79,12 @@ def run_conv(N, H, W, chans, ctx, cout, k, act, seed=0):
     views = [View(nhwc_bf16(x), round16(c), 0, c) for x, c in zip(xs, chans)]
     logical = list(chans)
     pa = None
-    if ctx:
+    if ctx:  # spatially constant parents, materialised (src/vae.py:241)
         pa = rnd(N, ctx, seed=seed + 9)
-        pat = torch.zeros(N, round16(ctx), device=DEV, dtype=torch.bfloat16)
-        pat[:, :ctx] = pa.to(torch.bfloat16)
-        views.insert(1, View(pat, round16(ctx), 0, ctx, bcast=True))
+        pat = nhwc_bf16(pa[:, :, None, None].expand(N, ctx, H, W))
+        views.insert(1, View(pat, round16(ctx), 0, ctx))
         logical.insert(1, ctx)
+        chans = list(chans)
     cin = sum(logical)
     w = rnd(cout, cin, k, k, scale=1.0 / math.sqrt(cin * k * k), seed=seed + 20)
     b = rnd(cout, scale=0.1, seed=seed + 21)
@@ -91,9 +95,7 @@ def run_conv(N, H, W, chans, ctx, cout, k, act, seed=0):
     layer.forward(views, [SegSpec(out, 0)], N, H, W)(stream())
     torch.cuda.synchronize()
     # reference on the same bf16-rounded operands
-    parts = [to_nchw(v.t, c) for v, c in zip([v for v in views if not v.bcast], chans)]
-    if ctx:
-        parts.insert(1, pat[:, :ctx].float()[:, :, None, None].expand(N, ctx, H, W))
+    parts = [to_nchw(v.t, c) for v, c in zip(views, logical)]
     xin = act_fn(act)(torch.cat(parts, 1))
     ref = F.conv2d(xin, w.to(torch.bfloat16).float(), b, padding=k // 2)
     return layer, views, out, ref, w, b
@@ -105,8 +107,8 @@ def test_conv_forward(case):
     layer, views, out, ref, w, b = run_conv(*case)
     assert_close(to_nchw(out.t, cout), ref, 1e-2, f"conv fwd {case}")
     # padded output channels must be exactly zero
-    if out.t.shape[-1] > cout:
-        assert out.t[..., cout:].abs().max().item() == 0.0
+    if out.t.shape[1] * 8 > cout:
+        assert to_nchw(out.t, out.t.shape[1] * 8)[:, cout:].abs().max().item() == 0.0
 
 
 def test_conv_segments_add_and_fp32_split():
@@ -134,19 +136,19 @@ def test_conv_dgrad_and_wgrad(case):
     dy_nchw = rnd(N, cout, H, W, seed=31)
     dy = View(nhwc_bf16(dy_nchw), round16(cout), 0, cout)
     # autograd reference on the bf16-rounded operands
-    data_views = [v for v in views if not v.bcast]
+    is_pa = [ctx and i == 1 for i in range(len(views))]
+    data_views = [v for v, p in zip(views, is_pa) if not p]
     xs = [to_nchw(v.t, c).requires_grad_(True) for v, c in zip(data_views, chans)]
     parts = list(xs)
     if ctx:
-        pav = [v for v in views if v.bcast][0]
-        parts.insert(1, pav.t[:, :ctx].float()[:, :, None, None].expand(N, ctx, H, W))
+        parts.insert(1, to_nchw(views[1].t, ctx))
     wq = w.to(torch.bfloat16).float().requires_grad_(True)
     bq = b.clone().requires_grad_(True)
     y = F.conv2d(act_fn(act)(torch.cat(parts, 1)), wq, bq, padding=k // 2)
     y.backward(to_nchw(dy.t, cout))
     # data gradients, per source, with act'(x) fused and an accumulate-add
     for i, v in enumerate(views):
-        if v.bcast:
+        if is_pa[i]:
             continue
         j = data_views.index(v)
         dx = new_act(N, H, W, chans[j], DEV)
@@ -181,12 +183,11 @@ def test_conv_many_tiles_per_cta(case):
     assert_close(to_nchw(acc.t, cout), ref + acc0 + to_nchw(other.t, cout), 1e-2, f"fwd in-place add {case}")
     # data gradient with act'(x) and in-place accumulate; weight gradient
     dy = View(nhwc_bf16(rnd(N, cout, H, W, seed=52)), round16(cout), 0, cout)
-    data_views = [v for v in views if not v.bcast]
+    data_views = [v for i, v in enumerate(views) if not (ctx and i == 1)]
     xs = [to_nchw(v.t, c).requires_grad_(True) for v, c in zip(data_views, chans)]
     parts = list(xs)
     if ctx:
-        pav = [v for v in views if v.bcast][0]
-        parts.insert(1, pav.t[:, :ctx].float()[:, :, None, None].expand(N, ctx, H, W))
+        parts.insert(1, to_nchw(views[1].t, ctx))
     wq = w.to(torch.bfloat16).float().requires_grad_(True)
     y = F.conv2d(act_fn(act)(torch.cat(parts, 1)), wq, None, padding=k // 2)
     y.backward(to_nchw(dy.t, cout))
@@ -235,8 +236,8 @@ def test_stem(cin, R, cout):
     x = rnd(N, cin, R, R, seed=1)
     w = rnd(cout, cin, 7, 7, scale=0.1, seed=2)
     b = rnd(cout, scale=0.1, seed=3)
-    y = torch.zeros(N, R, R, cout, device=DEV, dtype=torch.bfloat16)
-    L.check(lib.cg_stem_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), N, cin, R, cout, cout, stream()))
+    y = torch.zeros(N, cout // 8, R, R, 8, device=DEV, dtype=torch.bfloat16)
+    L.check(lib.cg_stem_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), N, cin, R, cout, ns_of(y), stream()))
     wr = w.clone().requires_grad_(True)
     br = b.clone().requires_grad_(True)
     ref = F.conv2d(x, wr, br, padding=3)
@@ -244,7 +245,7 @@ def test_stem(cin, R, cout):
     assert_close(to_nchw(y, cout), ref, 1e-2, "stem fwd")
     dy = nhwc_bf16(rnd(N, cout, R, R, seed=4), cout)
     dw, db = torch.zeros_like(w), torch.zeros_like(b)
-    L.check(lib.cg_stem_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), N, cin, R, cout, cout, stream()))
+    L.check(lib.cg_stem_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), N, cin, R, cout, ns_of(dy), stream()))
     ref.backward(to_nchw(dy, cout))
     torch.cuda.synchronize()
     assert_close(dw, wr.grad, 2e-3, "stem wgrad")
@@ -255,29 +256,33 @@ def test_pool_and_upsample():
     from causalgen_b200 import _lib as L
     lib = L.load()
     N, C, H = 2, 32, 24
+
+    def zeros(res):
+        return torch.zeros(N, C // 8, res, res, 8, device=DEV, dtype=torch.bfloat16)
+
     x = rnd(N, C, H, H, seed=1)
     xb = nhwc_bf16(x)
     for d in (2, 4, 6):
-        y = torch.zeros(N, H // d, H // d, C, device=DEV, dtype=torch.bfloat16)
-        L.check(lib.cg_avgpool_fwd(xb.data_ptr(), y.data_ptr(), N, H, H, C, d, C, C, 0, stream()))
+        y = zeros(H // d)
+        L.check(lib.cg_avgpool_fwd(xb.data_ptr(), y.data_ptr(), N, H, H, C, d, ns_of(xb), ns_of(y), 0, stream()))
         assert_close(to_nchw(y, C), F.avg_pool2d(to_nchw(xb, C), d, d), 1e-2, f"pool {d}")
         dy = nhwc_bf16(rnd(N, C, H // d, H // d, seed=2))
         dx = torch.zeros_like(xb)
-        L.check(lib.cg_avgpool_bwd(dy.data_ptr(), dx.data_ptr(), N, H, H, C, d, C, C, 0, 0, stream()))
+        L.check(lib.cg_avgpool_bwd(dy.data_ptr(), dx.data_ptr(), N, H, H, C, d, ns_of(dy), ns_of(dx), 0, 0, stream()))
         xr = to_nchw(xb, C).requires_grad_(True)
         F.avg_pool2d(xr, d, d).backward(to_nchw(dy, C))
         assert_close(to_nchw(dx, C), xr.grad, 1e-2, f"pool bwd {d}")
     # odd resolution: 14 -> 7 padded to 8 (src/vae.py:130-132)
     x14 = nhwc_bf16(rnd(N, C, 14, 14, seed=3))
-    y8 = torch.ones(N, 8, 8, C, device=DEV, dtype=torch.bfloat16)
-    L.check(lib.cg_avgpool_fwd(x14.data_ptr(), y8.data_ptr(), N, 14, 14, C, 2, C, C, 8, stream()))
+    y8 = torch.ones(N, C // 8, 8, 8, 8, device=DEV, dtype=torch.bfloat16)
+    L.check(lib.cg_avgpool_fwd(x14.data_ptr(), y8.data_ptr(), N, 14, 14, C, 2, ns_of(x14), ns_of(y8), 8, stream()))
     assert_close(to_nchw(y8, C), F.pad(F.avg_pool2d(to_nchw(x14, C), 2, 2), [0, 1, 0, 1]), 1e-2, "pool+pad")
     # nearest upsample + learned bias, integer and 7->8 style factors
     for hi, ho in ((6, 12), (1, 4), (7, 8), (8, 14)):
         xs = nhwc_bf16(rnd(N, C, hi, hi, seed=4))
         bias = rnd(1, C, ho, ho, seed=5)
-        y = torch.zeros(N, ho, ho, C, device=DEV, dtype=torch.bfloat16)
-        L.check(lib.cg_upsample_fwd(xs.data_ptr(), bias.data_ptr(), y.data_ptr(), N, hi, ho, C, C, C, stream()))
+        y = zeros(ho)
+        L.check(lib.cg_upsample_fwd(xs.data_ptr(), bias.data_ptr(), y.data_ptr(), N, hi, ho, C, ns_of(xs), ns_of(y), stream()))
         xr = to_nchw(xs, C).requires_grad_(True)
         br = bias.clone().requires_grad_(True)
         ref = br + F.interpolate(xr, scale_factor=ho / hi)
@@ -285,7 +290,8 @@ def test_pool_and_upsample():
         dy = nhwc_bf16(rnd(N, C, ho, ho, seed=6))
         dx = torch.zeros_like(xs)
         dbias = torch.zeros_like(bias)
-        L.check(lib.cg_upsample_bwd(dy.data_ptr(), dx.data_ptr(), dbias.data_ptr(), N, hi, ho, C, C, C, 0, stream()))
+        L.check(lib.cg_upsample_bwd(dy.data_ptr(), dx.data_ptr(), dbias.data_ptr(), N, hi, ho, C, ns_of(dy), ns_of(dx), 0,
+                                    stream()))
         ref.backward(to_nchw(dy, C))
         assert_close(to_nchw(dx, C), xr.grad, 1e-2, f"upsample bwd {hi}->{ho}")
         assert_close(dbias, br.grad, 2e-3, f"upsample dbias {hi}->{ho}")
@@ -300,12 +306,12 @@ def test_latent_forward_backward():
     q = rnd(N, HW, 32, seed=1, scale=0.7).contiguous()
     p = rnd(N, HW, 32, seed=2, scale=0.7).contiguous()
     eps = rnd(N, zd, H, H, seed=3)
-    z16 = torch.zeros(N, HW, 16, device=DEV, dtype=torch.bfloat16)
+    z16 = torch.zeros(N, 2, H, H, 8, device=DEV, dtype=torch.bfloat16)
     z32 = torch.zeros(N, zd, H, H, device=DEV)
     kl = torch.zeros(N, device=DEV)
     a = L.LatentArgs()
     a.q, a.p, a.q_ld, a.p_ld, a.eps = q.data_ptr(), p.data_ptr(), 32, 32, eps.data_ptr()
-    a.log_t, a.z_bf16, a.z_ld, a.z_f32, a.kl_out = math.log(0.9), z16.data_ptr(), 16, z32.data_ptr(), kl.data_ptr()
+    a.log_t, a.z_bf16, a.z_ns, a.z_f32, a.kl_out = math.log(0.9), z16.data_ptr(), ns_of(z16), z32.data_ptr(), kl.data_ptr()
     a.N, a.HW, a.zdim, a.mode = N, HW, zd, 0
     L.check(lib.cg_latent_fwd(C.byref(a), stream()))
     qn = q.view(N, H, H, 32).permute(0, 3, 1, 2)
@@ -315,16 +321,16 @@ def test_latent_forward_backward():
     klr = (-0.5 + ps - qs + 0.5 * (qs.exp() ** 2 + (ql - pl) ** 2) / ps.exp() ** 2).sum(dim=(1, 2, 3))
     torch.cuda.synchronize()
     assert_close(z32, zr, 1e-5, "z fp32")
-    assert_close(z16.view(N, H, H, 16).permute(0, 3, 1, 2).float(), zr, 1e-2, "z bf16")
+    assert_close(to_nchw(z16, 16), zr, 1e-2, "z bf16")
     assert_close(kl, klr, 1e-4, "kl")
     # backward (t = None)
-    dz = rnd(N, HW, 16, seed=4).to(torch.bfloat16).contiguous()
-    dq = torch.zeros(N, HW, 32, device=DEV, dtype=torch.bfloat16)
-    dp = torch.zeros(N, HW, 48, device=DEV, dtype=torch.bfloat16)
+    dz = nhwc_bf16(rnd(N, 16, H, H, seed=4))
+    dq = torch.zeros(N, 4, H, H, 8, device=DEV, dtype=torch.bfloat16)
+    dp = torch.zeros(N, 6, H, H, 8, device=DEV, dtype=torch.bfloat16)
     b = L.LatentBwdArgs()
     b.q, b.p, b.q_ld, b.p_ld, b.eps = q.data_ptr(), p.data_ptr(), 32, 32, eps.data_ptr()
-    b.dz, b.dz_ld, b.g_kl = dz.data_ptr(), 16, 0.37
-    b.dq, b.dq_ld, b.dp, b.dp_ld = dq.data_ptr(), 32, dp.data_ptr(), 48
+    b.dz, b.dz_ns, b.g_kl = dz.data_ptr(), ns_of(dz), 0.37
+    b.dq, b.dq_ns, b.dp, b.dp_ns = dq.data_ptr(), ns_of(dq), dp.data_ptr(), ns_of(dp)
     b.N, b.HW, b.zdim, b.mode = N, HW, zd, 0
     L.check(lib.cg_latent_bwd(C.byref(b), stream()))
     qr = q.clone().requires_grad_(True)
@@ -334,11 +340,11 @@ def test_latent_forward_backward():
     ql, qs, pl, ps = qn[:, :16], qn[:, 16:], pn[:, :16], pn[:, 16:]
     z = ql + qs.exp() * eps
     klv = (-0.5 + ps - qs + 0.5 * (qs.exp() ** 2 + (ql - pl) ** 2) / ps.exp() ** 2).sum()
-    loss = 0.37 * klv + (z * dz.view(N, H, H, 16).permute(0, 3, 1, 2).float()).sum()
+    loss = 0.37 * klv + (z * to_nchw(dz, 16)).sum()
     loss.backward()
     torch.cuda.synchronize()
-    assert_close(dq.float(), qr.grad, 1e-2, "dq")
-    assert_close(dp[..., :32].float(), pr.grad, 1e-2, "dp")
+    assert_close(to_nchw(dq, 32), qr.grad.view(N, H, H, 32).permute(0, 3, 1, 2), 1e-2, "dq")
+    assert_close(to_nchw(dp, 32), pr.grad.view(N, H, H, 32).permute(0, 3, 1, 2), 1e-2, "dp")
 
 
 @pytest.mark.parametrize("Cc,Cw", [(1, 32), (3, 16)])
@@ -358,7 +364,7 @@ def test_dgauss_forward_backward_sample(Cc, Cw):
     bs[1] = bs[1] - 2.0
     nll = torch.zeros(N, device=DEV)
     a = L.DGaussArgs()
-    a.h, a.h_ld, a.Cw, a.x = h.data_ptr(), Cw, Cw, x.data_ptr()
+    a.h, a.h_ns, a.Cw, a.x = h.data_ptr(), ns_of(h), Cw, x.data_ptr()
     a.w_loc, a.b_loc, a.w_ls, a.b_ls = ws[0].data_ptr(), bs[0].data_ptr(), ws[1].data_ptr(), bs[1].data_ptr()
     if Cc == 3:
         a.w_co, a.b_co = ws[2].data_ptr(), bs[2].data_ptr()
@@ -389,7 +395,7 @@ def test_dgauss_forward_backward_sample(Cc, Cw):
     dh = torch.zeros_like(h)
     dws = [torch.zeros_like(w) for w in ws]
     dbs = [torch.zeros_like(b) for b in bs]
-    a.g, a.dh, a.dh_ld = 0.5, dh.data_ptr(), Cw
+    a.g, a.dh, a.dh_ns = 0.5, dh.data_ptr(), ns_of(dh)
     a.dw_loc, a.db_loc, a.dw_ls, a.db_ls = dws[0].data_ptr(), dbs[0].data_ptr(), dws[1].data_ptr(), dbs[1].data_ptr()
     if Cc == 3:
         a.dw_co, a.db_co = dws[2].data_ptr(), dbs[2].data_ptr()
@@ -434,7 +440,7 @@ def test_dmol_against_oracle_functions():
     b = rnd(100, seed=6, scale=0.5)
     nll = torch.zeros(N, device=DEV)
     a = L.DmolArgs()
-    a.h, a.h_ld, a.Cw, a.x, a.w, a.b = h.data_ptr(), Cw, Cw, x.data_ptr(), w.data_ptr(), b.data_ptr()
+    a.h, a.h_ns, a.Cw, a.x, a.w, a.b = h.data_ptr(), ns_of(h), Cw, x.data_ptr(), w.data_ptr(), b.data_ptr()
     a.N, a.HW, a.nll = N, HW, nll.data_ptr()
     L.check(lib.cg_dmol_loss_fwd(C.byref(a), stream()))
     hc = to_nchw(h, Cw).cpu().requires_grad_(True)
@@ -446,7 +452,7 @@ def test_dmol_against_oracle_functions():
     assert_close(nll.cpu(), ref.detach(), 2e-4, "dmol loss")
     dh = torch.zeros_like(h)
     dw, db = torch.zeros_like(w), torch.zeros_like(b)
-    a.g, a.dh, a.dh_ld, a.dw, a.db = 0.5, dh.data_ptr(), Cw, dw.data_ptr(), db.data_ptr()
+    a.g, a.dh, a.dh_ns, a.dw, a.db = 0.5, dh.data_ptr(), ns_of(dh), dw.data_ptr(), db.data_ptr()
     L.check(lib.cg_dmol_loss_bwd(C.byref(a), stream()))
     (0.5 * ref.sum()).backward()
     torch.cuda.synchronize()
@@ -497,24 +503,28 @@ def test_mix_cf_and_layout_glue():
     assert_close(s2, 2 * ref ** 2, 1e-6, "cf sum2")
     # layout glue round trip
     t = rnd(2, 20, 9, 9, seed=30)
-    nh = torch.zeros(2, 81, 32, device=DEV, dtype=torch.bfloat16)
-    L.check(lib.cg_nchw_f32_to_nhwc_bf16(t.data_ptr(), nh.data_ptr(), 2, 20, 81, 32, stream()))
+    nh = torch.ones(2, 4, 9, 9, 8, device=DEV, dtype=torch.bfloat16)
+    L.check(lib.cg_nchw_f32_to_planar(t.data_ptr(), nh.data_ptr(), 2, 20, 81, ns_of(nh), stream()))
+    assert_close(to_nchw(nh, 20), t.to(torch.bfloat16).float(), 1e-6, "nchw -> planar")
+    assert to_nchw(nh, 24)[:, 20:].abs().max().item() == 0 and nh[:, 3].float().abs().max().item() == 1.0
     back = torch.zeros_like(t)
-    L.check(lib.cg_nhwc_bf16_to_nchw_f32(nh.data_ptr(), back.data_ptr(), 2, 20, 81, 32, stream()))
+    L.check(lib.cg_planar_to_nchw_f32(nh.data_ptr(), back.data_ptr(), 2, 20, 81, ns_of(nh), stream()))
     assert_close(back, t.to(torch.bfloat16).float(), 1e-6, "layout round trip")
-    assert nh[..., 20:].abs().max().item() == 0
+    pa = rnd(3, 12, seed=31)
+    pl = torch.zeros(3, 2, 5, 5, 8, device=DEV, dtype=torch.bfloat16)
+    L.check(lib.cg_parents_plane(pa.data_ptr(), 12, 1, pl.data_ptr(), 3, 12, 16, 25, ns_of(pl), 2, 0.0, stream()))
+    want = pa.clone()
+    want[:, 2:] = 0
+    assert_close(to_nchw(pl, 12), want.to(torch.bfloat16).float()[:, :, None, None].expand(3, 12, 5, 5), 1e-6, "parents plane")
 
 
-@pytest.mark.parametrize("rows,C", [(2, 288), (5000, 32), (777, 24), (36864, 16), (3, 544), (100, 8)])
-def test_colsum_bias_gradient(rows, C):
+@pytest.mark.parametrize("N,HW,C", [(2, 1, 288), (5, 1000, 32), (3, 259, 24), (4, 9216, 16), (3, 1, 544), (7, 13, 8)])
+def test_colsum_bias_gradient(N, HW, C):
     from causalgen_b200 import _lib as L
-    from causalgen_b200.ops import round16
-    ld = round16(C)
-    dy = torch.zeros(rows, ld, device=DEV, dtype=torch.bfloat16)
-    dy[:, :C] = rnd(rows, C, seed=3).to(torch.bfloat16)
+    dy = nhwc_bf16(rnd(N, C, HW, 1, seed=3))
     out = torch.full((C,), 0.5, device=DEV)
-    L.check(L.load().cg_colsum(dy.data_ptr(), out.data_ptr(), rows, C, ld, stream()))
-    assert_close(out - 0.5, dy[:, :C].float().sum(0), 2e-3, f"colsum {rows}x{C}")
+    L.check(L.load().cg_colsum(dy.data_ptr(), out.data_ptr(), N, HW, C, ns_of(dy), stream()))
+    assert_close(out - 0.5, to_nchw(dy, C).sum(dim=(0, 2, 3)), 2e-3, f"colsum {N}x{HW}x{C}")
 
 
 def test_optimizer_tail_matches_torch_adamw():

@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "causal-gen_b200
 import torch
 from bench import conv_bytes, wgrad_bytes
 from causalgen_b200 import _lib as L
-from causalgen_b200.ops import ConvLayer, PackTable, SegSpec, View, new_act, round16
+from causalgen_b200.ops import ConvLayer, PackTable, SegSpec, View, new_act, planar_from_nchw, round16
 DEV = "cuda"
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 only = sys.argv[2] if len(sys.argv) > 2 else None
@@ -47,13 +47,13 @@ for name, H, cins, cout, k, act, epi in CASES:
     g = torch.Generator().manual_seed(0)
     views = []
     for i, c in enumerate(cins):
-        t = torch.randn(N, H, H, round16(c), generator=g).to(DEV).to(torch.bfloat16)
+        t = planar_from_nchw(torch.randn(N, round16(c), H, H, generator=g).to(DEV))
         views.append(View(t, round16(c), 0, c))
     w = (torch.randn(cout, sum(cins), k, k, generator=g) * 0.05).to(DEV); b = torch.zeros(cout, device=DEV)
     table = PackTable(DEV); layer = ConvLayer(table, w, b, cins, act); table.launch(s())
     out = new_act(N, H, H, cout, DEV)
-    x1 = View(torch.randn(N, H, H, round16(cout), generator=g).to(DEV).to(torch.bfloat16), round16(cout))
-    x2 = View(torch.randn(N, H, H, round16(cout), generator=g).to(DEV).to(torch.bfloat16), round16(cout))
+    x1 = View(planar_from_nchw(torch.randn(N, round16(cout), H, H, generator=g).to(DEV)), round16(cout))
+    x2 = View(planar_from_nchw(torch.randn(N, round16(cout), H, H, generator=g).to(DEV)), round16(cout))
     seg = SegSpec(out, 0)
     if epi == "add": seg.add = x1
     if epi in ("mul", "muladd"): seg.mul, seg.mul_act = x1, 1
