@@ -16,6 +16,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib as L
+from . import dp
 from .engine import TRACE_ONLY
 from .hvae import HVAE, _stream
 
@@ -30,8 +31,7 @@ class Trainer:
         self.hp = dict(lr=lr, wd=wd, b1=betas[0], b2=betas[1], warmup=lr_warmup_steps, clip=grad_clip,
                        skip=grad_skip, ema=ema_rate, ema_after=ema_update_after)
         self.beta = float(beta)
-        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        self.rank = dist.get_rank() if self.world > 1 else 0
+        self.world, self.rank = dp.world_info()
         dev = next(model.parameters()).device
         self.device = dev
         # flatten parameters: AdamW / EMA run over one buffer; nn.Parameters become views of it
@@ -43,8 +43,7 @@ class Trainer:
             self.flat_p[off: off + p.numel()].copy_(p.data.reshape(-1))
             p.data = self.flat_p[off: off + p.numel()].view_as(p)
             off += p.numel()
-        if self.world > 1:
-            dist.broadcast(self.flat_p, src=0)  # identical initial weights on every rank
+        dp.broadcast_params_(self.flat_p)  # identical initial weights on every rank
         self.m = torch.zeros_like(self.flat_p)
         self.v = torch.zeros_like(self.flat_p)
         self.ema = self.flat_p.clone()
@@ -57,7 +56,7 @@ class Trainer:
         self.prog = model._program(("elbo", self.N, True, False), lambda: self.eng.build_elbo(self.N, True, False))
         self.eng.set_beta(self.prog, self.beta, self.N)
         # noise: Philox keyed by (seed + device step counter, rank-disjoint stream)
-        base = (noise_seed * 0x9E3779B97F4A7C15 + (self.rank << 48)) % (1 << 64)
+        base = dp.rank_noise_seed(noise_seed, self.rank)
         for la in self.prog.D.latent_args:
             la.seed, la.seed_dev = base, self.seed_ctr.data_ptr()
         for lb in self.prog.D.latent_bwd_args:
@@ -133,8 +132,7 @@ class Trainer:
             self.g_fb.replay()
         else:
             self._fwd_bwd()
-        if self.world > 1:
-            dist.all_reduce(self.eng.flat_grad)  # the one exchange step of the path (NCCL over NVLink)
+        dp.reduce_gradients_(self.eng.flat_grad)  # the one exchange step of the path (NCCL over NVLink)
         if self.g_opt is not None:
             self.g_opt.replay()
         else:

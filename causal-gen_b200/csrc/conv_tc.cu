@@ -25,7 +25,8 @@
 //   MMA warp         one thread issues tcgen05.mma; tcgen05.commit frees the stage / signals the epilogue
 //   epilogue warps   TMEM -> registers -> global
 //
-// Warp roles: 0-3 epilogue (TMEM lane quarters), 4 MMA issuer + TMEM owner, 5 TMA producer, 6-9 transform.
+// Warp roles: 0-7 epilogue (TMEM lane quarter = warp & 3, column half = warp >> 2), 8 MMA issuer + TMEM owner,
+//             9 TMA producer, 10-13 transform.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -34,12 +35,12 @@
 
 namespace {
 
-constexpr int kEpiWarps = 4;
-constexpr int kMmaWarp = 4;
-constexpr int kTmaWarp = 5;
-constexpr int kXfWarp0 = 6;
+constexpr int kEpiWarps = 8;  // two warps per TMEM lane quarter, each takes every other 16-column chunk
+constexpr int kMmaWarp = 8;
+constexpr int kTmaWarp = 9;
+constexpr int kXfWarp0 = 10;
 constexpr int kXfWarps = 4;
-constexpr int kThreads = (kXfWarp0 + kXfWarps) * 32;  // 320
+constexpr int kThreads = (kXfWarp0 + kXfWarps) * 32;  // 448
 constexpr int kXfThreads = kXfWarps * 32;
 constexpr int kStages = 6;
 constexpr int kPlane3 = 2880;  // 18 rows * 10 px * 16 B
@@ -300,15 +301,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
   } else {
     // ------------------------------------------------------------------ epilogue
+    // warp = quarter + 4*half: TMEM lanes [32*quarter, +32) (one pixel per lane); 16-column chunks with
+    // (chunk & 1) == half.  Per chunk: TMEM -> 16 fp32 -> (+bias) -> (*act'(x)) -> (+residuals) -> store.
     uint32_t as = 0, aphase = 0, es = 0, ephase = 0;
-    const int m = warp * 32 + lane;
+    const int quarter = warp & 3, half = warp >> 2;
+    const int m = quarter * 32 + lane;
     const int nE = P.nE;
-    // staged-operand slot of (segment, kind) or -1 -> direct global load
-    auto slot_of = [&](int sgi, int kind) {
-      for (int k = 0; k < nE; ++k)
-        if (P.eop[k].seg == sgi && P.eop[k].kind == kind) return k;
-      return -1;
-    };
+    const bool has_bias = P.a.bias != nullptr;
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
       const TileGeom g = tile_geom(P, tile);
       bool valid;
@@ -328,51 +327,59 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       warp_wait(BAR(B_ACCFULL + as), aphase, lane);
       tc_fence_after();
       const uint8_t* e_row = sE + (size_t)(es * kESlots) * eslot + (size_t)m * 16;
-      const uint32_t t_row = tmem_base + as * (uint32_t)Nc + ((uint32_t)(warp * 32) << 16);
-      for (int col = 0; col < Nc; col += 16) {
+      const uint32_t t_row = tmem_base + as * (uint32_t)Nc + ((uint32_t)(quarter * 32) << 16);
+      for (int col = half * 16; col < Nc; col += 32) {
         float acc[16];
         __syncwarp();  // .aligned TMEM load needs the whole warp converged
         tmem_ld16(t_row + (uint32_t)col, acc);
         const int cg0 = nchunkN * Nc + col;
-        if (cg0 >= P.a.cout) continue;
+        if (cg0 >= P.a.cout || !valid || (P.dbg & 8)) continue;
+        if (has_bias) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] += s_bias[col + i];
-        if (!valid || (P.dbg & 8)) continue;
+          for (int i = 0; i < 16; ++i) acc[i] += s_bias[col + i];
+        }
         for (int sgi = 0; sgi < P.a.nseg; ++sgi) {
           const cg_seg& sg = P.a.seg[sgi];
           const int lc = cg0 - sg.c0;
           if (lc < 0 || lc >= sg.cn) continue;
           const int cnt = min(16, sg.cn - lc);  // 8 or 16
+          // staged-operand slots of this segment (or -1 -> direct global load)
+          int k_add = -1, k_add2 = -1, k_mul = -1;
+          for (int k = 0; k < nE; ++k)
+            if (P.eop[k].seg == sgi) {
+              if (P.eop[k].kind == 0) k_add = k;
+              else if (P.eop[k].kind == 1) k_add2 = k;
+              else k_mul = k;
+            }
+          auto fetch = [&](int k, const void* gptr, long long gns, int h8, float* x) {
+            uint4 u;
+            if (k >= 0) u = *reinterpret_cast<const uint4*>(e_row + (size_t)k * eslot + ((col + h8) >> 3) * kPlane1);
+            else u = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(gptr) + n * gns +
+                                                     ((lc + h8) >> 3) * P.HW8 + hw * 8);
+            cg_unpack8(u, x);
+          };
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = acc[i];
-          // operand fetch: staged octet plane (shared memory) if the producer brought it, else global
-          auto fetch = [&](int kind, const void* gptr, long long gns, int h8) -> uint4 {
-            const int k = slot_of(sgi, kind);
-            if (k >= 0) return *reinterpret_cast<const uint4*>(e_row + (size_t)k * eslot + ((col + h8) >> 3) * kPlane1);
-            return *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(gptr) + n * gns +
-                                                   ((lc + h8) >> 3) * P.HW8 + hw * 8);
-          };
-          if (sg.mul != nullptr) {
-            for (int h8 = 0; h8 < cnt; h8 += 8) {
-              float x[8];
-              cg_unpack8(fetch(2, sg.mul, sg.mul_ns, h8), x);
+          for (int h8 = 0; h8 < cnt; h8 += 8) {
+            float x[8];
+            if (sg.mul != nullptr) {
+              fetch(k_mul, sg.mul, sg.mul_ns, h8, x);
+              if (sg.mul_act == CG_ACT_RELU) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[h8 + i] *= cg_dact(x[i], sg.mul_act);
+                for (int i = 0; i < 8; ++i) v[h8 + i] = x[i] > 0.f ? v[h8 + i] : 0.f;
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[h8 + i] *= cg_dact(x[i], sg.mul_act);
+              }
             }
-          }
-          if (sg.add != nullptr) {
-            for (int h8 = 0; h8 < cnt; h8 += 8) {
-              float x[8];
-              cg_unpack8(fetch(0, sg.add, sg.add_ns, h8), x);
+            if (sg.add != nullptr) {
+              fetch(k_add, sg.add, sg.add_ns, h8, x);
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[h8 + i] += x[i];
             }
-          }
-          if (sg.add2 != nullptr) {
-            for (int h8 = 0; h8 < cnt; h8 += 8) {
-              float x[8];
-              cg_unpack8(fetch(1, sg.add2, sg.add2_ns, h8), x);
+            if (sg.add2 != nullptr) {
+              fetch(k_add2, sg.add2, sg.add2_ns, h8, x);
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[h8 + i] += x[i];
             }

@@ -1,0 +1,150 @@
+"""Host-side logic that needs no GPU: architecture tables, state_dict compatibility, launch-program
+construction (trace-only), data-parallel helpers under gloo with world_size 2."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import hvae_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PRESETS = ["morphomnist", "cmnist", "ukbb192", "mimic192", "mimic224", "tiny_ukbb"]
+
+
+@pytest.mark.parametrize("name", PRESETS)
+def test_state_dict_keys_and_shapes_match_reference_layout(name):
+    from causalgen_b200 import HVAE
+    cfg = O.make_cfg(name)
+    model = HVAE(cfg)
+    ours = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert list(ours.items()) == list(O.param_shapes(cfg).items())
+    assert [b.res for b in model.decoder.blocks] == [d.res for d in O.build_arch(cfg).dec]
+    assert [b.stochastic for b in model.decoder.blocks] == [d.stochastic for d in O.build_arch(cfg).dec]
+
+
+@pytest.mark.parametrize("name", PRESETS)
+def test_arch_tables_agree_with_oracle(name):
+    from causalgen_b200.arch import decoder_plan, encoder_plan
+    from causalgen_b200.presets import make_args
+    a = make_args(name) if name != "tiny_ukbb" else make_args("tiny_ukbb")
+    ref = O.build_arch(O.make_cfg(name))
+    enc = encoder_plan(a)
+    assert [(s.cin, s.cmid, s.cout, s.down) for s in enc] == [(b.cin, b.cmid, b.cout, b.down) for b in ref.enc]
+    dec = decoder_plan(a)
+    assert [(s.res, s.cin, s.cout, s.stochastic, s.ksize) for s in dec] == \
+        [(d.res, d.cin, d.cout, d.stochastic, d.conv.ksize) for d in ref.dec]
+    # odd resolutions are zero padded up by one after pooling (src/vae.py:130-132)
+    if name == "mimic224":
+        assert [s.res_out for s in enc if s.down][-2] == 8
+
+
+def test_reference_init_scaling_rules():
+    from causalgen_b200 import HVAE
+    from causalgen_b200.presets import init_like_reference_main, make_args
+    torch.manual_seed(7)
+    m = init_like_reference_main(HVAE(make_args("tiny_ukbb")))
+    sd = m.state_dict()
+    assert float(sd["decoder.blocks.0.prior.conv.3.weight"].abs().max()) == 0.0  # src/vae.py:308
+    assert all(float(v.abs().max()) == 0.0 for k, v in sd.items() if k.endswith(".bias") and "decoder.bias" not in k)
+    assert float(sd["encoder.blocks.0.conv.1.weight"].abs().max()) > 0.0
+
+
+def test_trace_only_program_construction():
+    """builds the launch programs on CPU (nothing executes) and checks their structure"""
+    code = r'''
+import os, sys
+os.environ["CAUSALGEN_B200_TRACE_ONLY"] = "1"
+sys.path.insert(0, os.path.join(%r, "causal-gen_b200")); sys.path.insert(0, os.path.join(%r, "oracle"))
+import torch, hvae_oracle as O
+import causalgen_b200._lib as L
+from causalgen_b200 import HVAE
+class Fake:
+    def __init__(self, real): self.real = real
+    def __getattr__(self, n):
+        if n in ("cg_conv_nchunk", "cg_packed_weight_bytes", "cg_version", "cg_last_error"): return getattr(self.real, n)
+        return lambda *a: 0
+L._lib = Fake(L.load())
+for name, nsto, nconv_min in (("tiny_ukbb", 5, 60), ("tiny_morphomnist", 4, 80)):
+    cfg = O.make_cfg(name); m = HVAE(cfg)
+    x8, pa, cf = O.synthetic_batch(cfg, 2, 1); x = O.normalise_x(x8)
+    out = m(x, pa, beta=cfg.beta); out["elbo"].backward()
+    prog = m.engine().programs[("elbo", 2, True, False)]
+    names = [getattr(l, "name", "py") for l in prog.launches]
+    assert names.count("cg_latent_fwd") == len(O.build_arch(cfg).dec)
+    assert sum(n == "cg_conv2d" for n in names) >= nconv_min
+    assert names.count("cg_conv2d_wgrad") >= 20 and names.count("cg_stem_wgrad") == 1
+    assert prog.kl_rows.shape == (nsto, 2)
+    fwd = names[:prog.n_fwd]
+    assert "cg_conv2d_wgrad" not in fwd and fwd[-1] == "cg_elbo_finalize"
+    zs = m.abduct(x, pa, t=0.9)
+    assert len(zs) == nsto
+    print(name, len(names), prog.n_kernels)
+print("ok")
+''' % (ROOT, ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+def _dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "causal-gen_b200"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from causalgen_b200 import dp
+    import hvae_oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    cfg = O.make_cfg("tiny_ukbb")
+    sd = {k: v.clone().requires_grad_(True) for k, v in O.seeded_state_dict(cfg, 7).items()}
+    x8, pa, _ = O.synthetic_batch(cfg, 4, seed=3)
+    x, pa_full = O.normalise_x(x8), O.expand_parents(pa, cfg.input_res)
+    eps = O.NoiseTape(seed=5)
+    with torch.no_grad():
+        O.hvae_forward(sd, cfg, x, pa_full, eps)  # draw the global eps once (identical on both ranks)
+    lo, hi = dp.shard_batch(4, world, rank)
+    shard_eps = O.NoiseTape([e[lo:hi] for e in eps.drawn])
+    out = O.hvae_forward(sd, cfg, x[lo:hi], pa_full[lo:hi], shard_eps, beta=cfg.beta)
+    out["elbo"].backward()
+    flat = torch.cat([p.grad.reshape(-1) for p in sd.values() if p.grad is not None])
+    params = torch.cat([p.detach().reshape(-1) for p in sd.values()]) + (rank * 1.0)
+    dp.broadcast_params_(params)
+    scale = dp.reduce_gradients_(flat)
+    q.put((rank, (flat * scale).numpy(), params.numpy(), dp.rank_noise_seed(7, rank)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_equals_full_batch_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    g0, g1 = res[0][1], res[1][1]
+    np.testing.assert_array_equal(g0, g1)  # every rank holds the same reduced bucket
+    np.testing.assert_array_equal(res[0][2], res[1][2])  # broadcast made the parameters identical
+    assert res[0][3] != res[1][3]  # rank-disjoint noise streams
+    # single-process full batch
+    cfg = O.make_cfg("tiny_ukbb")
+    sd = {k: v.clone().requires_grad_(True) for k, v in O.seeded_state_dict(cfg, 7).items()}
+    x8, pa, _ = O.synthetic_batch(cfg, 4, seed=3)
+    out = O.hvae_forward(sd, cfg, O.normalise_x(x8), O.expand_parents(pa, cfg.input_res), O.NoiseTape(seed=5), beta=cfg.beta)
+    out["elbo"].backward()
+    full = torch.cat([p.grad.reshape(-1) for p in sd.values() if p.grad is not None]).numpy()
+    np.testing.assert_allclose(g0, full, rtol=2e-4, atol=1e-6)
+
+
+def test_shard_batch_rejects_ragged_split():
+    from causalgen_b200 import dp
+    assert dp.shard_batch(32, 4, 3) == (24, 32)
+    with pytest.raises(ValueError):
+        dp.shard_batch(30, 4, 0)
