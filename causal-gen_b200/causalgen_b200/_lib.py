@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcausalgen_b200.so")
+LIB_PATH = os.environ.get("CAUSALGEN_B200_LIB", os.path.join(_HERE, "libcausalgen_b200.so"))
 
 CG_MAX_SRC = 3
 CG_MAX_SEG = 4

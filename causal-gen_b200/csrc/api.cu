@@ -36,3 +36,7 @@ int cg_require_sm100() {
   }
   return CG_OK;
 }
+
+// debug builds (-DCG_TIMELINE): kernels of CTA (0,0) write %globaltimer marks into this device buffer
+unsigned long long* cg_tl_ptr = nullptr;
+extern "C" void cg_debug_timeline(unsigned long long* dev_buf) { cg_tl_ptr = dev_buf; }

@@ -40,8 +40,23 @@ int cg_make_planar_map(void* map_out, const void* ptr, long long ns, int N, int 
 static inline cudaStream_t cg_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int cg_ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// ---- optional in-kernel timeline (debug builds only: make EXTRA=-DCG_TIMELINE) ---------
+extern unsigned long long* cg_tl_ptr;  // device buffer set by cg_debug_timeline(), NULL otherwise (api.cu)
+
 // ---- device helpers ------------------------------------------------------------------
 #ifdef __CUDACC__
+#ifdef CG_TIMELINE
+__device__ __forceinline__ void cg_tl_mark(unsigned long long* tl, int k) {
+  if (tl != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    tl[k] = t;
+  }
+}
+#define CG_TL(tl, k) cg_tl_mark(tl, k)
+#else
+#define CG_TL(tl, k)
+#endif
 typedef __nv_bfloat16 bf16;
 
 __device__ __forceinline__ float cg_gelu(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }

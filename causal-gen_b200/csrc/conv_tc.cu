@@ -84,6 +84,7 @@ struct alignas(64) KParams {
   int tiles_x, tiles_per_img, ntiles;
   long long HW8;  // H*W*8: elements per channel-octet plane
   uint32_t idesc, tmem_cols, slab_bytes, e_tx_bytes;
+  unsigned long long* tl;  // debug timeline (CG_TIMELINE builds)
   int dbg;  // CG_DEBUG_SKIP bit mask (profiling experiments only): 2 no act, 4 no mma, 8 no epilogue stores
 };
 
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t bar0 = cg_smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   const int act = (P.dbg & 2) ? CG_ACT_NONE : P.a.act;
+  if (threadIdx.x == 0) CG_TL(P.tl, 32);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -189,6 +191,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) CG_TL(P.tl, 33);
   const bool k3 = P.a.ksize == 3;
   const int plane = k3 ? kPlane3 : kPlane1;
   const int H = P.a.H, W = P.a.W, N = P.a.N;
@@ -203,6 +206,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         bulk_g2s(cg_smem_u32(sB) + off, wsrc + off, n, BAR(B_BFULL));
       }
       mbar_wait(BAR(B_BFULL), 0);
+      CG_TL(P.tl, 34);
+      int tl_i = 0;
+      (void)tl_i;
       // Descriptors are built once; per MMA only the 14-bit start-address field (low word) advances
       // (all offsets are multiples of 16 B).
       const uint32_t a_sbo = k3 ? 160u : 128u;
@@ -226,6 +232,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const Chunk ch = P.chunk[c];
           mbar_wait(BAR(ready0 + stage), phase);
           tc_fence_after();
+          if (c == 0 && tl_i < 6) CG_TL(P.tl, 35 + 2 * tl_i);
           uint32_t alo = a_lo0 + stage * stage16;
           uint32_t blo = b_lo0 + (uint32_t)ch.kbase * b_step16;
           for (int j = 0; j < ch.nc16 && !(P.dbg & 4); ++j) {
@@ -247,6 +254,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         tc_commit(BAR(B_ACCFULL + as));  // accumulator ready for the epilogue
+        if (tl_i < 6) CG_TL(P.tl, 36 + 2 * tl_i);
+        ++tl_i;
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
@@ -304,6 +313,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // warp = quarter + 4*half: TMEM lanes [32*quarter, +32) (one pixel per lane); 16-column chunks with
     // (chunk & 1) == half.  Per chunk: TMEM -> 16 fp32 -> (+bias) -> (*act'(x)) -> (+residuals) -> store.
     uint32_t as = 0, aphase = 0, es = 0, ephase = 0;
+    int tl_i = 0;
+    (void)tl_i;
     const int quarter = warp & 3, half = warp >> 2;
     const int m = quarter * 32 + lane;
     const int nE = P.nE;
@@ -400,12 +411,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         mbar_arrive(BAR(B_ACCEMPTY + as));
         if (nE > 0) mbar_arrive(BAR(B_EEMPTY + es));
       }
+      if (threadIdx.x == 0 && tl_i < 8) CG_TL(P.tl, 50 + tl_i);
+      ++tl_i;
       if (++as == 2) { as = 0; aphase ^= 1u; }
       if (nE > 0 && ++es == kEStages) { es = 0; ephase ^= 1u; }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) CG_TL(P.tl, 60);
   if (warp == kMmaWarp) {
     __syncwarp();
     tmem_dealloc(tmem_base, P.tmem_cols);
@@ -586,6 +600,7 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
     dbg = e ? atoi(e) : 0;
   }
   kp.dbg = dbg;
+  kp.tl = cg_tl_ptr;
   const int sms = cg_device_sms();
   int gx = sms / kp.nN;
   if (gx < 1) gx = 1;

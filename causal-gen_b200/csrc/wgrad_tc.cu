@@ -49,6 +49,7 @@ struct alignas(64) WParams {
   int x_on_m, ntaps, halo, flat;
   int tiles_x, tiles_per_img, ntiles;
   uint32_t tmem_cols;
+  unsigned long long* tl;  // debug timeline (CG_TIMELINE builds)
 };
 
 struct Geom {
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = cg_smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
+  if (threadIdx.x == 0) CG_TL(P.tl, 1);
 
   const WChunk pc = P.pch[blockIdx.y / P.nQ];
   const WChunk qc = P.qch[blockIdx.y % P.nQ];
@@ -134,9 +136,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) CG_TL(P.tl, 0);
 
   if (warp == kMmaWarp) {
     if (lane == 0) {
+      int tl_i = 0;
+      (void)tl_i;
       const uint32_t idesc = umma_idesc_bf16(128, Nq, 1, 1);
       const uint32_t pitchP = p_halo ? 160u : 128u, pitchQ = q_halo ? 160u : 128u;
       // descriptors built once; per MMA only the start-address field advances (16-byte units)
@@ -152,6 +157,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
       for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
         mbar_wait(BAR(ready0 + stage), phase);
         tc_fence_after();
+        if (tl_i < 8) CG_TL(P.tl, 2 + 2 * tl_i);
         const uint32_t plo = p_lo0 + stage * stage16, qlo = q_lo0 + stage * stage16;
         for (int t = 0; t < P.ntaps; ++t) {
           // the un-shifted operand of a 3x3 problem is staged without halo: it starts at its own pixel 0
@@ -167,6 +173,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
         }
         accum_any = 1;
         tc_commit(BAR(6 + stage));
+        if (tl_i < 8) CG_TL(P.tl, 3 + 2 * tl_i);
+        ++tl_i;
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
       tc_commit(BAR(9));
@@ -217,6 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
     if (lane == 0) mbar_wait(BAR(9), 0);
     __syncwarp();
     tc_fence_after();
+    if (threadIdx.x == 0) CG_TL(P.tl, 20);
     const int m = warp * 32 + lane;
     const int kk = P.a.ksize * P.a.ksize;
     const WChunk& xc = p_is_x ? pc : qc;  // chunk that indexes input channels
@@ -250,9 +259,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
       nq0 += 16;
       if (nq0 >= Nq) { nq0 = 0; ++t; }
     }
+    if (threadIdx.x == 0) CG_TL(P.tl, 21);
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) CG_TL(P.tl, 22);
   if (warp == kMmaWarp) {
     __syncwarp();
     tmem_dealloc(tmem_base, P.tmem_cols);
@@ -270,6 +281,7 @@ extern "C" int cg_conv2d_wgrad(const cg_wgrad_args* a, void* stream) {
   CG_REQUIRE(a->taps == 1 || a->taps == a->ksize * a->ksize, "cg_conv2d_wgrad: taps %d", a->taps);
   WParams kp;
   kp.a = *a;
+  kp.tl = cg_tl_ptr;
   kp.ntaps = a->taps;
   kp.halo = (a->ksize == 3 && a->taps == 9) ? 1 : 0;
   kp.flat = (a->H == 1 && a->W == 1) ? 1 : 0;
