@@ -166,13 +166,14 @@ def check(rc: int, what: str = ""):
 
 class Launch:
     """One recorded kernel launch: a bound C function plus its (mutable) argument tuple."""
-    __slots__ = ("fn", "args", "name", "keep")
+    __slots__ = ("fn", "args", "name", "keep", "side")
 
     def __init__(self, name, *args):
         self.fn = getattr(load(), name)
         self.args = tuple(args)
         self.name = name
         self.keep = None
+        self.side = False  # True: nothing later in the program reads its result -> may run on a side stream
 
     def __call__(self, stream):
         rc = self.fn(*self.args, stream)

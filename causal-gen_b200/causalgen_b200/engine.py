@@ -27,10 +27,15 @@ from .ops import ConvLayer, PackTable, SegSpec, View, new_act, round16
 # CAUSALGEN_B200_TRACE_ONLY=1 lets the launch programs be *built* (buffers + argument structs) on a host
 # without a GPU so their structure can be unit-tested; nothing is executed and outputs stay zero.
 TRACE_ONLY = os.environ.get("CAUSALGEN_B200_TRACE_ONLY", "0") == "1"
+# Weight-gradient launches only feed the flat gradient bucket, so they are forked onto side streams (graph
+# branches under capture) and overlap the latency-bound data-gradient chain.  0 = everything on one stream.
+SIDE_STREAMS = int(os.environ.get("CAUSALGEN_B200_SIDE_STREAMS", "2"))
 
 
 class PyOp:
     """a recorded torch-side glue op (layout copies only; never arithmetic on the path)"""
+
+    side = False
 
     def __init__(self, fn, name="pyop"):
         self.fn, self.name = fn, name
@@ -45,11 +50,13 @@ class Program:
         self.launches: List = []
         self.keep: List = []
         self.n_kernels = 0
+        self.sides = None
 
     def add(self, ln):
         self.launches.append(ln)
         if isinstance(ln, L.Launch):
             self.n_kernels += 2 if (ln.name == "cg_conv2d_wgrad" and ln.keep[0].dbias) else 1
+            ln.side = ln.name == "cg_conv2d_wgrad"
         return ln
 
     def call(self, name, *args):
@@ -58,9 +65,32 @@ class Program:
     def run(self, stream=None):
         if TRACE_ONLY:  # program construction check on a box without a GPU: nothing is computed
             return
-        s = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        main = torch.cuda.current_stream()
+        s = main.cuda_stream if stream is None else stream
+        if SIDE_STREAMS <= 0 or s != main.cuda_stream:
+            for ln in self.launches:
+                ln(s)
+            return
+        if self.sides is None:
+            self.sides = [torch.cuda.Stream() for _ in range(SIDE_STREAMS)]
+        ev, seen, k = None, [None] * len(self.sides), 0
         for ln in self.launches:
-            ln(s)
+            if ln.side:
+                if ev is None:  # main advanced since the last fork point
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                j = k % len(self.sides)
+                k += 1
+                if seen[j] is not ev:
+                    self.sides[j].wait_event(ev)
+                    seen[j] = ev
+                ln(self.sides[j].cuda_stream)
+            else:
+                ln(s)
+                ev = None
+        if k:
+            for st in self.sides:
+                main.wait_stream(st)
 
 
 class BlockLayers:

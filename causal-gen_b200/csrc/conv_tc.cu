@@ -311,7 +311,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   } else {
     // ------------------------------------------------------------------ epilogue
     // warp = quarter + 4*half: TMEM lanes [32*quarter, +32) (one pixel per lane); 16-column chunks with
-    // (chunk & 1) == half.  Per chunk: TMEM -> 16 fp32 -> (+bias) -> (*act'(x)) -> (+residuals) -> store.
+    // (chunk & 1) == half, at most two per warp (Nc <= 64).  Which segment / staged operands a chunk maps to
+    // is the same for every tile, so it is resolved ONCE here (ChunkPlan); per tile the warp issues both TMEM
+    // loads, waits once, releases the accumulator and then does bias / act' / residual / store from registers.
     uint32_t as = 0, aphase = 0, es = 0, ephase = 0;
     int tl_i = 0;
     (void)tl_i;
@@ -319,6 +321,51 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int m = quarter * 32 + lane;
     const int nE = P.nE;
     const bool has_bias = P.a.bias != nullptr;
+    struct ChunkPlan {
+      int col, sgi, lc, cnt;        // sgi < 0: chunk has no destination (padding / beyond cout)
+      int k_add, k_add2, k_mul;     // -2 absent, -1 read from global memory, >= 0 staged E slot
+      int dtype, mul_act;
+      uint8_t* out;                 // bf16: ptr + (lc/8) planes; fp32: ptr + lc floats
+      long long ns;
+    } plan[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      ChunkPlan& pl = plan[j];
+      pl.col = half * 16 + 32 * j;
+      pl.sgi = -1;
+      pl.lc = pl.cnt = 0;
+      pl.k_add = pl.k_add2 = pl.k_mul = -2;
+      pl.dtype = CG_BF16;
+      pl.mul_act = CG_ACT_NONE;
+      pl.out = nullptr;
+      pl.ns = 0;
+      const int cg0 = nchunkN * Nc + pl.col;
+      if (pl.col >= Nc || cg0 >= P.a.cout || (P.dbg & 8)) continue;
+      for (int sgi = 0; sgi < P.a.nseg; ++sgi) {
+        const cg_seg& sg = P.a.seg[sgi];
+        const int lc = cg0 - sg.c0;
+        if (lc < 0 || lc >= sg.cn) continue;
+        pl.sgi = sgi;
+        pl.lc = lc;
+        pl.cnt = min(16, sg.cn - lc);
+        pl.dtype = sg.dtype;
+        pl.mul_act = sg.mul_act;
+        pl.ns = sg.ns;
+        pl.out = reinterpret_cast<uint8_t*>(sg.ptr) +
+                 (sg.dtype == CG_F32 ? (long long)lc * 4 : (long long)(lc >> 3) * P.HW8 * 2);
+        if (sg.add != nullptr) pl.k_add = -1;
+        if (sg.add2 != nullptr) pl.k_add2 = -1;
+        if (sg.mul != nullptr) pl.k_mul = -1;
+        for (int k = 0; k < nE; ++k)
+          if (P.eop[k].seg == sgi) {
+            if (P.eop[k].kind == 0) pl.k_add = k;
+            else if (P.eop[k].kind == 1) pl.k_add2 = k;
+            else pl.k_mul = k;
+          }
+        break;
+      }
+    }
+    const bool two = plan[1].col < Nc;
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
       const TileGeom g = tile_geom(P, tile);
       bool valid;
@@ -339,82 +386,81 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       tc_fence_after();
       const uint8_t* e_row = sE + (size_t)(es * kESlots) * eslot + (size_t)m * 16;
       const uint32_t t_row = tmem_base + as * (uint32_t)Nc + ((uint32_t)(quarter * 32) << 16);
-      for (int col = half * 16; col < Nc; col += 32) {
-        float acc[16];
-        __syncwarp();  // .aligned TMEM load needs the whole warp converged
-        tmem_ld16(t_row + (uint32_t)col, acc);
-        const int cg0 = nchunkN * Nc + col;
-        if (cg0 >= P.a.cout || !valid || (P.dbg & 8)) continue;
+      float acc[2][16];
+      __syncwarp();  // .aligned TMEM loads need the whole warp converged
+      tmem_ld16_nowait(t_row + (uint32_t)plan[0].col, acc[0]);
+      if (two) tmem_ld16_nowait(t_row + (uint32_t)plan[1].col, acc[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_ACCEMPTY + as));  // accumulator is in registers: MMA may reuse it
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const ChunkPlan& pl = plan[j];
+        if (pl.sgi < 0 || !valid) continue;
+        float* v = acc[j];
         if (has_bias) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) acc[i] += s_bias[col + i];
+          for (int q = 0; q < 16; q += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + pl.col + q);
+            v[q] += b4.x; v[q + 1] += b4.y; v[q + 2] += b4.z; v[q + 3] += b4.w;
+          }
         }
-        for (int sgi = 0; sgi < P.a.nseg; ++sgi) {
-          const cg_seg& sg = P.a.seg[sgi];
-          const int lc = cg0 - sg.c0;
-          if (lc < 0 || lc >= sg.cn) continue;
-          const int cnt = min(16, sg.cn - lc);  // 8 or 16
-          // staged-operand slots of this segment (or -1 -> direct global load)
-          int k_add = -1, k_add2 = -1, k_mul = -1;
-          for (int k = 0; k < nE; ++k)
-            if (P.eop[k].seg == sgi) {
-              if (P.eop[k].kind == 0) k_add = k;
-              else if (P.eop[k].kind == 1) k_add2 = k;
-              else k_mul = k;
-            }
-          auto fetch = [&](int k, const void* gptr, long long gns, int h8, float* x) {
-            uint4 u;
-            if (k >= 0) u = *reinterpret_cast<const uint4*>(e_row + (size_t)k * eslot + ((col + h8) >> 3) * kPlane1);
-            else u = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(gptr) + n * gns +
-                                                     ((lc + h8) >> 3) * P.HW8 + hw * 8);
-            cg_unpack8(u, x);
-          };
-          float v[16];
+        auto fetch = [&](int k, int kind, int h8, float* x) {
+          uint4 u;
+          if (k >= 0) {
+            u = *reinterpret_cast<const uint4*>(e_row + (size_t)k * eslot + ((pl.col + h8) >> 3) * kPlane1);
+          } else {
+            const cg_seg& sg = P.a.seg[pl.sgi];
+            const void* gp = kind == 0 ? sg.add : (kind == 1 ? sg.add2 : sg.mul);
+            const long long gns = kind == 0 ? sg.add_ns : (kind == 1 ? sg.add2_ns : sg.mul_ns);
+            u = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(gp) + n * gns +
+                                                ((pl.lc + h8) >> 3) * P.HW8 + hw * 8);
+          }
+          cg_unpack8(u, x);
+        };
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = acc[i];
-          for (int h8 = 0; h8 < cnt; h8 += 8) {
-            float x[8];
-            if (sg.mul != nullptr) {
-              fetch(k_mul, sg.mul, sg.mul_ns, h8, x);
-              if (sg.mul_act == CG_ACT_RELU) {
+        for (int h8 = 0; h8 < 16; h8 += 8) {
+          if (h8 >= pl.cnt) continue;
+          float x[8];
+          if (pl.k_mul != -2) {
+            fetch(pl.k_mul, 2, h8, x);
+            if (pl.mul_act == CG_ACT_RELU) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[h8 + i] = x[i] > 0.f ? v[h8 + i] : 0.f;
-              } else {
+              for (int i = 0; i < 8; ++i) v[h8 + i] = x[i] > 0.f ? v[h8 + i] : 0.f;
+            } else {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[h8 + i] *= cg_dact(x[i], sg.mul_act);
-              }
-            }
-            if (sg.add != nullptr) {
-              fetch(k_add, sg.add, sg.add_ns, h8, x);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[h8 + i] += x[i];
-            }
-            if (sg.add2 != nullptr) {
-              fetch(k_add2, sg.add2, sg.add2_ns, h8, x);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[h8 + i] += x[i];
+              for (int i = 0; i < 8; ++i) v[h8 + i] *= cg_dact(x[i], pl.mul_act);
             }
           }
-          if (sg.dtype == CG_F32) {  // fp32 statistics: row layout (pixel, channel), pitch ns
-            float* op = reinterpret_cast<float*>(sg.ptr) + ((long long)n * H * W + hw) * sg.ns + lc;
-            for (int q = 0; q < cnt; q += 4)
-              *reinterpret_cast<float4*>(op + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+          if (pl.k_add != -2) {
+            fetch(pl.k_add, 0, h8, x);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[h8 + i] += x[i];
+          }
+          if (pl.k_add2 != -2) {
+            fetch(pl.k_add2, 1, h8, x);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[h8 + i] += x[i];
+          }
+          if (pl.dtype == CG_F32) {  // fp32 statistics: row layout (pixel, channel), pitch ns
+            float* op = reinterpret_cast<float*>(pl.out) + ((long long)n * H * W + hw) * pl.ns + h8;
+            *reinterpret_cast<float4*>(op) = make_float4(v[h8], v[h8 + 1], v[h8 + 2], v[h8 + 3]);
+            *reinterpret_cast<float4*>(op + 4) = make_float4(v[h8 + 4], v[h8 + 5], v[h8 + 6], v[h8 + 7]);
           } else {  // bf16 planar: 8 lanes of a tile row write one contiguous 128-byte line per octet
-            bf16* op = reinterpret_cast<bf16*>(sg.ptr) + n * sg.ns + (lc >> 3) * P.HW8 + hw * 8;
-            for (int h8 = 0; h8 < cnt; h8 += 8) *reinterpret_cast<uint4*>(op + (h8 >> 3) * P.HW8) = cg_pack8(v + h8);
+            bf16* op = reinterpret_cast<bf16*>(pl.out) + n * pl.ns + (long long)(h8 >> 3) * P.HW8 + hw * 8;
+            *reinterpret_cast<uint4*>(op) = cg_pack8(v + h8);
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(BAR(B_ACCEMPTY + as));
-        if (nE > 0) mbar_arrive(BAR(B_EEMPTY + es));
+      if (nE > 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(B_EEMPTY + es));
+        if (++es == kEStages) { es = 0; ephase ^= 1u; }
       }
       if (threadIdx.x == 0 && tl_i < 8) CG_TL(P.tl, 50 + tl_i);
       ++tl_i;
       if (++as == 2) { as = 0; aphase ^= 1u; }
-      if (nE > 0 && ++es == kEStages) { es = 0; ephase ^= 1u; }
     }
   }
   tc_fence_before();

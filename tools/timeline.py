@@ -15,7 +15,7 @@ sys.argv, argv = sys.argv[:1], sys.argv[1:]
 import importlib.util
 spec = importlib.util.spec_from_file_location("mb", os.path.join(ROOT, "tools", "conv_microbench.py"))
 src = open(os.path.join(ROOT, "tools", "conv_microbench.py")).read().split("def s():")[0]
-ns = {}
+ns = {"__file__": os.path.join(ROOT, "tools", "conv_microbench.py")}
 exec(compile(src, "mb_cases", "exec"), ns)
 CASES = ns["CASES"]
 only = argv[0] if argv else None
