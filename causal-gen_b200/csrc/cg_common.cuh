@@ -37,6 +37,9 @@ int cg_require_sm100();  // CG_OK or CG_ERR_ARCH
 int cg_make_planar_map(void* map_out, const void* ptr, long long ns, int N, int H, int W, int C8, int flat, int box_w8,
                        int box_h, int box_c8);
 
+// mma.sync weight-gradient path for small-channel 3x3 problems (wgrad_mma.cu); *handled = 0 -> use tcgen05
+int cg_wgrad_mma_try(const cg_wgrad_args* a, void* stream, int* handled);
+
 static inline cudaStream_t cg_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int cg_ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

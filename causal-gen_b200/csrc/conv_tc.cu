@@ -600,6 +600,9 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
     CG_REQUIRE(sg.add == nullptr || (((uintptr_t)sg.add & 15) == 0 && sg.add_ns % 8 == 0), "cg_conv2d: seg %d add", s);
     CG_REQUIRE(sg.add2 == nullptr || (((uintptr_t)sg.add2 & 15) == 0 && sg.add2_ns % 8 == 0), "cg_conv2d: seg %d add2", s);
     CG_REQUIRE(sg.mul == nullptr || (((uintptr_t)sg.mul & 15) == 0 && sg.mul_ns % 8 == 0), "cg_conv2d: seg %d mul", s);
+    for (int t = 0; t < s; ++t)
+      CG_REQUIRE(sg.c0 >= a->seg[t].c0 + a->seg[t].cn || a->seg[t].c0 >= sg.c0 + sg.cn,
+                 "cg_conv2d: segments %d and %d overlap (output channel ranges must be disjoint)", t, s);
   }
   kp.nE = 0;
   if (kp.emode) {

@@ -1,0 +1,411 @@
+// Weight gradient of the 3x3 convolutions whose channel counts are too small to feed tcgen05 (sm_100a):
+//   dW[co][ci][kh][kw] += sum_pixels dY[p][co] * act(X)[p + (kh-1, kw-1)][ci],   dbias[co] += sum_pixels dY[p][co]
+//
+// Why not tcgen05 here (measured on B200, profiles/r1e_timeline.txt): the reduction dimension is PIXELS, so each
+// tcgen05.mma covers only K=16 pixels and re-reads a full M=128-row operand from shared memory although the
+// layers have 16..64 real channels; one 128-pixel tile costs 72 instructions x ~75 clk (shared-memory operand
+// rate ~60 B/clk) = 2.9 us against an HBM budget of 0.3 us.  Warp-level mma.sync (m16n8k16, bf16 -> fp32) has
+// M/N granularity 16/8, takes its operands from registers, and lets each warp keep the WIDE operand's
+// fragments in registers while it sweeps the three taps of one kernel row over the NARROW operand:
+//
+//   operands    both are TMA boxes of the planar bf16 layout (N, C/8, H, W, 8): the wide one as a 16x8-pixel
+//               tile, the narrow one as the 18x10 halo tile (borders zero-filled by the TMA unit).  A pixel's 8
+//               channels are 16 contiguous bytes = one ldmatrix row, so ldmatrix.trans with per-lane pixel
+//               addresses yields the (channel x pixel) fragments directly; a tap is an address offset.
+//   roles       M = dY channels (A fragments), N = X channels (B fragments), K = 16 pixels (two tile rows).
+//               SHIFT_A: dY is narrow -> dY carries the halo, tile partitions X positions.
+//               else   : X is narrow  -> X carries the halo, tile partitions dY positions.
+//   warps       6 compute warps = 3 kernel rows (kh) x 2 halves of the tile's pixel rows, + 1 TMA producer warp;
+//               accumulators (3 taps x MT x NT fragments, <= 96 fp32 registers) persist over all tiles of the CTA.
+//   activation  ReLU of the forward pre-activation is applied to the X fragments in registers.
+//   dbias       one extra mma of the (unshifted) dY fragment against a ones fragment -- no second pass over dY.
+//   flush       fragments -> fp32 shared-memory tile ordered [co][ci][tap] (= OIHW order) -> coalesced global
+//               red.add into the flat gradient bucket.
+// GELU layers and 1x1 / 1-pixel problems stay on the tcgen05 kernel of wgrad_tc.cu.
+#include <cuda.h>
+
+#include "cg_common.cuh"
+
+namespace {
+
+constexpr int kComputeWarps = 6;
+constexpr int kThreadsM = (kComputeWarps + 1) * 32;  // 224
+constexpr int kStagesM = 4;
+constexpr int kPlaneHalo = 2880;  // 18 rows * 10 px * 16 B
+constexpr int kPlaneFlat = 2048;  // 16 rows *  8 px * 16 B
+constexpr int kMaxChunksM = 32;
+constexpr int kHdrM = 128;
+
+struct MChunk {
+  int16_t src, c0, nc;  // chunk of the wide operand: X source index (or 0 for dY), first channel, channels
+};
+
+struct alignas(64) MParams {
+  CUtensorMap x_map[CG_MAX_SRC];
+  CUtensorMap dy_map;
+  cg_wgrad_args a;
+  MChunk chunk[kMaxChunksM];
+  uint32_t x_bytes[CG_MAX_SRC], dy_bytes;  // TMA transaction bytes of one box
+  int nchunks;
+  int tiles_x, tiles_per_img, ntiles;
+  int stage_bytes, wide_off;
+  unsigned long long* tl;  // debug timeline (CG_TIMELINE builds)
+};
+
+__device__ __forceinline__ void tma4m(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::
+          "r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint32_t relu2(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  v = __hmax2(v, __floats2bfloat162_rn(0.f, 0.f));
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int MT, int NT, bool SHIFT_A>
+__global__ void __launch_bounds__(kThreadsM, 2) wgrad_mma_kernel(const __grid_constant__ MParams P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0..3] full, [4..7] empty
+  uint8_t* stages = smem + kHdrM;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = cg_smem_u32(bars);
+  auto FULL = [&](int i) { return bar0 + 8u * i; };
+  auto EMPTY = [&](int i) { return bar0 + 8u * (kStagesM + i); };
+  constexpr int CO = MT * 16, CI = NT * 8;
+  const MChunk wc = P.chunk[blockIdx.y];
+  if (threadIdx.x == 0) CG_TL(P.tl, 1);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStagesM; ++i) {
+      mbar_init(FULL(i), 1);
+      mbar_init(EMPTY(i), kComputeWarps);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  float acc[3][MT][NT][4];
+  float bacc[MT][4];
+#pragma unroll
+  for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[kw][mt][nt][q] = 0.f;
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bacc[mt][q] = 0.f;
+
+  const int tg = warp % 3, pg = warp / 3;  // kernel row kh, pixel-row half (compute warps only)
+  const bool do_bias = P.a.dbias != nullptr && (SHIFT_A ? (blockIdx.y == 0 && tg == 1) : (tg == 0));
+
+  if (warp == kComputeWarps) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const CUtensorMap* wide_map = SHIFT_A ? &P.x_map[wc.src] : &P.dy_map;
+      const CUtensorMap* narrow_map = SHIFT_A ? &P.dy_map : &P.x_map[0];
+      const uint32_t tx = SHIFT_A ? (P.x_bytes[wc.src] + P.dy_bytes) : (P.x_bytes[0] + P.dy_bytes);
+      const int w_oct = wc.c0 >> 3;
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+        const int n = tile / P.tiles_per_img;
+        const int r = tile - n * P.tiles_per_img;
+        const int ty = r / P.tiles_x;
+        const int h0 = ty * 16, w0 = (r - ty * P.tiles_x) * 8;
+        mbar_wait(EMPTY(stage), phase ^ 1u);
+        mbar_expect_tx(FULL(stage), tx);
+        const uint32_t sb = cg_smem_u32(stages + stage * P.stage_bytes);
+        tma4m(sb, narrow_map, (w0 - 1) * 8, h0 - 1, 0, n, FULL(stage));
+        tma4m(sb + P.wide_off, wide_map, w0 * 8, h0, w_oct, n, FULL(stage));
+        if (++stage == kStagesM) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ compute warps
+    const int j = lane >> 3, i = lane & 7;  // ldmatrix: lane supplies row i of matrix j
+    const bool relu = P.a.act == CG_ACT_RELU;
+    const uint32_t ones = 0x3F803F80u;  // bf16 (1, 1)
+    // per-lane byte offsets inside a stage (tile-invariant)
+    //   A fragment x4: matrices (octet 0, rows lo) (octet 1, rows lo) (octet 0, rows hi) (octet 1, rows hi)
+    //   B fragment x4: matrices (octet 0, rows lo) (octet 0, rows hi) (octet 1, rows lo) (octet 1, rows hi)
+    uint32_t a_off, b_off;
+    if (SHIFT_A) {
+      a_off = (uint32_t)((j & 1) * kPlaneHalo + (((j >> 1) + 2 - tg) * 10 + (i + 2)) * 16);
+      b_off = (uint32_t)(P.wide_off + (j >> 1) * kPlaneFlat + ((j & 1) * 8 + i) * 16);
+    } else {
+      a_off = (uint32_t)(P.wide_off + (j & 1) * kPlaneFlat + ((j >> 1) * 8 + i) * 16);
+      b_off = (uint32_t)((j >> 1) * kPlaneHalo + (((j & 1) + tg) * 10 + i) * 16);
+    }
+    uint32_t stage = 0, phase = 0;
+    int tl_i = 0;
+    (void)tl_i;
+    if (threadIdx.x == 0) CG_TL(P.tl, 0);
+    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+      if (lane == 0) mbar_wait(FULL(stage), phase);
+      __syncwarp();
+      if (threadIdx.x == 0 && tl_i < 8) CG_TL(P.tl, 2 + 2 * tl_i);
+      const uint32_t sb = cg_smem_u32(stages + stage * P.stage_bytes);
+#pragma unroll 1
+      for (int ks = 0; ks < 4; ++ks) {
+        const int r0 = 2 * (pg * 4 + ks);  // first of the two tile rows of this k-step
+        if (SHIFT_A) {
+          // dY fragments of the three taps of kernel row tg: halo[(r + 2 - kh)][(c + 2 - kw)]
+          uint32_t a[3][MT][4];
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+              ldsm_x4_t(a[kw][mt], sb + a_off + (uint32_t)(mt * 2 * kPlaneHalo + (r0 * 10 - kw) * 16));
+          if (do_bias) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) mma_bf16(bacc[mt], a[1][mt], ones, ones);
+          }
+#pragma unroll
+          for (int n2 = 0; n2 < NT / 2; ++n2) {
+            uint32_t b[4];
+            ldsm_x4_t(b, sb + b_off + (uint32_t)(n2 * 2 * kPlaneFlat + r0 * 8 * 16));
+            if (relu) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) b[q] = relu2(b[q]);
+            }
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                mma_bf16(acc[kw][mt][2 * n2], a[kw][mt], b[0], b[1]);
+                mma_bf16(acc[kw][mt][2 * n2 + 1], a[kw][mt], b[2], b[3]);
+              }
+          }
+        } else {
+          uint32_t a[MT][4];
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            ldsm_x4_t(a[mt], sb + a_off + (uint32_t)(mt * 2 * kPlaneFlat + r0 * 8 * 16));
+          if (do_bias) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) mma_bf16(bacc[mt], a[mt], ones, ones);
+          }
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            // X fragments of tap (tg, kw): halo[(r + kh)][(c + kw)]
+#pragma unroll
+            for (int n2 = 0; n2 < NT / 2; ++n2) {
+              uint32_t b[4];
+              ldsm_x4_t(b, sb + b_off + (uint32_t)(n2 * 2 * kPlaneHalo + (r0 * 10 + kw) * 16));
+              if (relu) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) b[q] = relu2(b[q]);
+              }
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                mma_bf16(acc[kw][mt][2 * n2], a[mt], b[0], b[1]);
+                mma_bf16(acc[kw][mt][2 * n2 + 1], a[mt], b[2], b[3]);
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (threadIdx.x == 0 && tl_i < 8) CG_TL(P.tl, 3 + 2 * tl_i);
+      ++tl_i;
+      if (lane == 0) mbar_arrive(EMPTY(stage));
+      if (++stage == kStagesM) { stage = 0; phase ^= 1u; }
+    }
+  }
+
+  // ------------------------------------------------------------------ flush
+  __syncthreads();  // every stage has been consumed: the ring memory becomes the fp32 reduction tile
+  if (threadIdx.x == 0) CG_TL(P.tl, 20);
+  float* sacc = reinterpret_cast<float*>(stages);  // [CO][CI][9]  (OIHW order of this chunk)
+  float* sbias = sacc + CO * CI * 9;               // [CO]
+  for (int e = threadIdx.x; e < CO * CI * 9 + CO; e += kThreadsM) sacc[e] = 0.f;
+  __syncthreads();
+  if (warp < kComputeWarps) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int tap = tg * 3 + kw;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const int co = mt * 16 + g, ci = nt * 8 + 2 * t;
+          atomicAdd(&sacc[(co * CI + ci) * 9 + tap], acc[kw][mt][nt][0]);
+          atomicAdd(&sacc[(co * CI + ci + 1) * 9 + tap], acc[kw][mt][nt][1]);
+          atomicAdd(&sacc[((co + 8) * CI + ci) * 9 + tap], acc[kw][mt][nt][2]);
+          atomicAdd(&sacc[((co + 8) * CI + ci + 1) * 9 + tap], acc[kw][mt][nt][3]);
+        }
+    }
+    if (do_bias && t == 0) {
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        atomicAdd(&sbias[mt * 16 + g], bacc[mt][0]);
+        atomicAdd(&sbias[mt * 16 + g + 8], bacc[mt][2]);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) CG_TL(P.tl, 21);
+  {
+    const int co0 = SHIFT_A ? 0 : wc.c0;
+    const int xs = SHIFT_A ? wc.src : 0;
+    const int ci0 = SHIFT_A ? wc.c0 : 0;
+    const int co_n = SHIFT_A ? CO : wc.nc, ci_n = SHIFT_A ? wc.nc : CI;  // channels of the chunk actually loaded
+    const int cin_l = P.a.cin_l, cout_l = P.a.cout_l, xlog = P.a.src_log[xs], xoff = P.a.src_off[xs];
+    for (int e = threadIdx.x; e < CO * CI * 9; e += kThreadsM) {
+      const int co = e / (CI * 9), rem = e - co * (CI * 9);
+      const int ci = rem / 9;
+      if (co < co_n && ci < ci_n && co0 + co < cout_l && ci0 + ci < xlog)
+        atomicAdd(P.a.dw + ((long long)(co0 + co) * cin_l + (xoff + ci0)) * 9 + rem, sacc[e]);
+    }
+    if (P.a.dbias != nullptr && (SHIFT_A ? blockIdx.y == 0 : true)) {
+      for (int co = threadIdx.x; co < CO; co += kThreadsM)
+        if (co < co_n && co0 + co < cout_l) atomicAdd(P.a.dbias + co0 + co, sbias[co]);
+    }
+  }
+  if (threadIdx.x == 0) CG_TL(P.tl, 22);
+}
+
+template <int MT, int NT, bool SHIFT_A>
+int launch_mma(const MParams& kp, int gx, int smem_bytes, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_mma_kernel<MT, NT, SHIFT_A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem_bytes);
+    if (e != cudaSuccess) {
+      cg_set_error("cg_conv2d_wgrad(mma): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return CG_ERR_CUDA;
+    }
+    attr_done = true;
+  }
+  wgrad_mma_kernel<MT, NT, SHIFT_A><<<dim3(gx, kp.nchunks), kThreadsM, smem_bytes, st>>>(kp);
+  return CG_OK;
+}
+
+}  // namespace
+
+// Returns CG_OK with *handled = 1 when the problem was launched on the mma.sync kernel, *handled = 0 when the
+// caller must use the tcgen05 kernel (1x1 / centre-tap / 1-pixel problems, GELU, both operands wide).
+int cg_wgrad_mma_try(const cg_wgrad_args* a, void* stream, int* handled) {
+  *handled = 0;
+  if (a->ksize != 3 || a->taps != 9 || (a->H == 1 && a->W == 1)) return CG_OK;
+  if (a->act != CG_ACT_NONE && a->act != CG_ACT_RELU) return CG_OK;
+  int xtot = 0;
+  for (int s = 0; s < a->nsrc; ++s) xtot += a->src[s].C;
+  const int dyc = a->dy_c;
+  int MT, NT;
+  bool shift_a;
+  if (dyc <= 48 && dyc <= xtot) {  // dY is the narrow operand: it carries the halo
+    shift_a = true;
+    MT = dyc / 16;
+    const int nt_max = MT == 1 ? 8 : (MT == 2 ? 4 : 2);
+    int widest = 0;
+    for (int s = 0; s < a->nsrc; ++s) widest = a->src[s].C > widest ? a->src[s].C : widest;
+    NT = widest <= 16 ? 2 : (widest <= 32 ? 4 : 8);
+    if (NT > nt_max) NT = nt_max;
+  } else if (xtot <= 48 && a->nsrc == 1) {  // X is the narrow operand
+    shift_a = false;
+    NT = xtot / 8;
+    const int mt_max = NT == 2 ? 4 : (NT == 4 ? 2 : 1);
+    MT = dyc <= 16 ? 1 : (dyc <= 32 ? 2 : 4);
+    if (MT > mt_max) MT = mt_max;
+  } else {
+    return CG_OK;
+  }
+  MParams kp;
+  kp.a = *a;
+  kp.tl = cg_tl_ptr;
+  const int wide_planes = shift_a ? NT : MT * 2, narrow_planes = shift_a ? MT * 2 : NT;
+  const int wch = wide_planes * 8;
+  kp.nchunks = 0;
+  if (shift_a) {
+    for (int s = 0; s < a->nsrc; ++s)
+      for (int c0 = 0; c0 < a->src[s].C; c0 += wch) {
+        if (kp.nchunks >= kMaxChunksM) return CG_OK;
+        const int nc = a->src[s].C - c0 < wch ? a->src[s].C - c0 : wch;
+        kp.chunk[kp.nchunks++] = MChunk{(int16_t)s, (int16_t)c0, (int16_t)nc};
+      }
+  } else {
+    for (int c0 = 0; c0 < dyc; c0 += wch) {
+      if (kp.nchunks >= kMaxChunksM) return CG_OK;
+      const int nc = dyc - c0 < wch ? dyc - c0 : wch;
+      kp.chunk[kp.nchunks++] = MChunk{0, (int16_t)c0, (int16_t)nc};
+    }
+  }
+  // tensor maps: the narrow operand carries the halo
+  for (int s = 0; s < a->nsrc; ++s) {
+    const int c8 = a->src[s].C / 8;
+    int boct, rc;
+    if (shift_a) {
+      boct = c8 < wide_planes ? c8 : wide_planes;
+      rc = cg_make_planar_map(&kp.x_map[s], a->src[s].ptr, a->src[s].ns, a->N, a->H, a->W, c8, 0, 64, 16, boct);
+      kp.x_bytes[s] = (uint32_t)boct * kPlaneFlat;
+    } else {
+      boct = narrow_planes;  // == c8
+      rc = cg_make_planar_map(&kp.x_map[s], a->src[s].ptr, a->src[s].ns, a->N, a->H, a->W, c8, 0, 80, 18, boct);
+      kp.x_bytes[s] = (uint32_t)boct * kPlaneHalo;
+    }
+    if (rc != CG_OK) return rc;
+  }
+  {
+    const int c8 = dyc / 8;
+    int boct, rc;
+    if (shift_a) {
+      boct = narrow_planes;  // == c8
+      rc = cg_make_planar_map(&kp.dy_map, a->dy, a->dy_ns, a->N, a->H, a->W, c8, 0, 80, 18, boct);
+      kp.dy_bytes = (uint32_t)boct * kPlaneHalo;
+    } else {
+      boct = c8 < wide_planes ? c8 : wide_planes;
+      rc = cg_make_planar_map(&kp.dy_map, a->dy, a->dy_ns, a->N, a->H, a->W, c8, 0, 64, 16, boct);
+      kp.dy_bytes = (uint32_t)boct * kPlaneFlat;
+    }
+    if (rc != CG_OK) return rc;
+  }
+  kp.tiles_x = (a->W + 7) / 8;
+  kp.tiles_per_img = kp.tiles_x * ((a->H + 15) / 16);
+  kp.ntiles = a->N * kp.tiles_per_img;
+  kp.wide_off = narrow_planes * kPlaneHalo;  // multiple of 128 (even plane count)
+  kp.stage_bytes = (kp.wide_off + wide_planes * kPlaneFlat + 127) / 128 * 128;
+  const int smem_bytes = kHdrM + kStagesM * kp.stage_bytes;
+  // two CTAs per SM; CTAs along the pixel axis share the chunk's gradient through coalesced atomics
+  int gx = (2 * cg_device_sms()) / kp.nchunks;
+  if (gx < 1) gx = 1;
+  if (gx > kp.ntiles) gx = kp.ntiles;
+  cudaStream_t st = cg_stream(stream);
+  int rc = CG_ERR_UNSUPPORTED;
+#define CG_MMA_CASE(mt, nt, sa) \
+  if (MT == mt && NT == nt && shift_a == sa) rc = launch_mma<mt, nt, sa>(kp, gx, smem_bytes, st);
+  CG_MMA_CASE(1, 8, true) CG_MMA_CASE(1, 4, true) CG_MMA_CASE(1, 2, true)
+  CG_MMA_CASE(2, 4, true) CG_MMA_CASE(2, 2, true) CG_MMA_CASE(3, 2, true)
+  CG_MMA_CASE(4, 2, false) CG_MMA_CASE(2, 2, false) CG_MMA_CASE(1, 2, false)
+  CG_MMA_CASE(2, 4, false) CG_MMA_CASE(1, 4, false) CG_MMA_CASE(1, 6, false)
+#undef CG_MMA_CASE
+  if (rc == CG_ERR_UNSUPPORTED) {
+    cg_set_error("cg_conv2d_wgrad(mma): no kernel instance for MT=%d NT=%d shift_a=%d", MT, NT, (int)shift_a);
+    return rc;
+  }
+  if (rc != CG_OK) return rc;
+  CG_LAUNCH_CHECK("cg_conv2d_wgrad(mma)");
+  *handled = 1;
+  return CG_OK;
+}

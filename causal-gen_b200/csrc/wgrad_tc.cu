@@ -16,6 +16,7 @@
 #include <cuda.h>
 
 #include <cmath>
+#include <cstdlib>
 
 #include "cg_common.cuh"
 
@@ -279,6 +280,25 @@ extern "C" int cg_conv2d_wgrad(const cg_wgrad_args* a, void* stream) {
   CG_REQUIRE(a->dy != nullptr && ((uintptr_t)a->dy & 15) == 0 && a->dy_c % 16 == 0 && a->dy_ns % 8 == 0,
              "cg_conv2d_wgrad: dy (c=%d ns=%lld)", a->dy_c, (long long)a->dy_ns);
   CG_REQUIRE(a->taps == 1 || a->taps == a->ksize * a->ksize, "cg_conv2d_wgrad: taps %d", a->taps);
+  {
+    // small-channel 3x3 problems run on the warp-level mma.sync kernel (wgrad_mma.cu explains why);
+    // CG_WGRAD_TC_ONLY=1 forces the tcgen05 kernel (A/B measurements)
+    static int tc_only = -1;
+    if (tc_only < 0) {
+      const char* e = getenv("CG_WGRAD_TC_ONLY");
+      tc_only = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    if (!tc_only) {
+      for (int s = 0; s < a->nsrc; ++s)
+        CG_REQUIRE(a->src[s].ptr != nullptr && ((uintptr_t)a->src[s].ptr & 15) == 0 && a->src[s].C % 16 == 0 &&
+                       a->src[s].C > 0 && a->src[s].ns % 8 == 0,
+                   "cg_conv2d_wgrad: src %d", s);
+      int handled = 0;
+      int rc = cg_wgrad_mma_try(a, stream, &handled);
+      if (rc != CG_OK) return rc;
+      if (handled) return CG_OK;
+    }
+  }
   WParams kp;
   kp.a = *a;
   kp.tl = cg_tl_ptr;

@@ -77,7 +77,7 @@ typedef struct {
   int32_t nsrc, nseg;
   int32_t cout;        /* output channels incl. zero padding, multiple of 16 */
   cg_src src[CG_MAX_SRC];   /* K-concatenated inputs: torch.cat([...], dim=1) without the copy */
-  cg_seg seg[CG_MAX_SEG];   /* channel-split outputs (loc | logscale | features ...) */
+  cg_seg seg[CG_MAX_SEG];   /* channel-split outputs (loc | logscale | features ...), disjoint ranges */
   const void* wpack;   /* weights packed by cg_pack_weights for exactly this (src list, cout) */
   const float* bias;   /* fp32 [bias_n] or NULL */
   int32_t bias_n;      /* valid bias entries (logical output channels); the rest is 0 */

@@ -119,7 +119,9 @@ def test_conv_segments_add_and_fp32_split():
     feat = new_act(N, H, W, 48, DEV)
     hsum = new_act(N, H, W, 48, DEV)
     h = View(nhwc_bf16(rnd(N, 48, H, W, seed=77)), 48)
-    layer.forward(views, [SegSpec(stats, 0), SegSpec(feat, 32), SegSpec(hsum, 32, add=h)], N, H, W)(stream())
+    # segments are disjoint channel ranges of the conv output: [stats | feat], then [stats | feat + h]
+    layer.forward(views, [SegSpec(stats, 0), SegSpec(feat, 32)], N, H, W)(stream())
+    layer.forward(views, [SegSpec(stats, 0), SegSpec(hsum, 32, add=h)], N, H, W)(stream())
     torch.cuda.synchronize()
     assert_close(stats.t.permute(0, 3, 1, 2), ref[:, :32], 2e-3, "fp32 stats split")
     assert_close(to_nchw(feat.t, 48), ref[:, 32:], 1e-2, "feature split")
@@ -201,6 +203,46 @@ def test_conv_many_tiles_per_cta(case):
     layer.wgrad(views, dy, dw, None, N, H, W)(stream())
     torch.cuda.synchronize()
     assert_close(dw, wq.grad, 1e-2, f"wgrad {case}")
+
+
+WGRAD_MMA_CASES = [
+    # N, H, W, src channels, bcast ctx, cout, k, act -- one per template instance of wgrad_mma.cu
+    (3, 20, 12, [64], 0, 16, 3, 1),        # dY narrow (16) x X 64: ragged H and W
+    (2, 9, 9, [16], 0, 8, 3, 0),           # both 16, odd size, no activation
+    (2, 24, 24, [96, 96], 4, 24, 3, 1),    # posterior-style 3 sources, dY 32
+    (2, 8, 8, [16, 16], 0, 32, 3, 1),      # two narrow sources, dY 32
+    (2, 12, 12, [160], 0, 40, 3, 1),       # dY 48
+    (2, 10, 10, [16], 0, 64, 3, 1),        # X narrow (16), dY 64
+    (1, 48, 48, [8], 0, 32, 3, 1),         # X 8 (padded 16), dY 32
+    (2, 24, 24, [32], 0, 128, 3, 1),       # X 32, dY 128 -> two dY chunks
+    (3, 6, 6, [40], 0, 176, 3, 1),         # X 48, dY 176 -> eleven dY chunks
+    (40, 24, 24, [128], 0, 32, 3, 1),      # many tiles per CTA, ring wraps
+    (6, 96, 96, [16], 0, 64, 3, 1),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_MMA_CASES)
+def test_wgrad_mma_small_channel_3x3(case):
+    """weight + bias gradient of the warp-level mma.sync kernel vs autograd on the same bf16 operands"""
+    from causalgen_b200.ops import View, round16
+    N, H, W, chans, ctx, cout, k, act = case
+    layer, views, out, ref, w, b = run_conv(*case, seed=17)
+    dy = View(nhwc_bf16(rnd(N, cout, H, W, seed=61)), round16(cout), 0, cout)
+    logical = list(chans)
+    if ctx:
+        logical.insert(1, ctx)
+    parts = [to_nchw(v.t, c) for v, c in zip(views, logical)]
+    wq = w.to(torch.bfloat16).float().requires_grad_(True)
+    bq = b.clone().requires_grad_(True)
+    y = F.conv2d(act_fn(act)(torch.cat(parts, 1)), wq, bq, padding=1)
+    y.backward(to_nchw(dy.t, cout))
+    dw = torch.full_like(w, 0.5)
+    db = torch.full_like(b, -0.25)
+    for _ in range(2):  # accumulates: two launches = twice the gradient
+        layer.wgrad(views, dy, dw, db, N, H, W)(stream())
+    torch.cuda.synchronize()
+    assert_close(dw - 0.5, 2 * wq.grad, 1e-2, f"wgrad {case}")
+    assert_close(db + 0.25, 2 * bq.grad, 1e-2, f"bias grad {case}")
 
 
 def test_conv_centre_tap_on_1x1_image():
