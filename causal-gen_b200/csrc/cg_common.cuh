@@ -103,6 +103,18 @@ __device__ __forceinline__ float cg_warp_sum(float v) {
 __device__ __forceinline__ uint32_t cg_smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// one thread of a fully converged warp.  ptxas knows a region guarded by elect.sync has a single active
+// thread, so uniform-datapath instructions inside it (tcgen05.mma, TMA, commit) are emitted straight instead
+// of inside a per-active-thread ELECT/BRA.U.ANY loop (what `if (lane == 0)` costs: ~80 clk per tcgen05.mma).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }

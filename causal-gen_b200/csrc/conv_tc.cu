@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(P.a.wpack) + (size_t)nchunkN * P.slab_bytes;
       mbar_expect_tx(BAR(B_BFULL), P.slab_bytes);
       for (uint32_t off = 0; off < P.slab_bytes; off += 32768u) {
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
   } else if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       for (int s = 0; s < P.a.nsrc; ++s) tma_prefetch_desc(&P.src_map[s]);
       for (int k = 0; k < P.nE; ++k) tma_prefetch_desc(&P.e_map[k]);
       uint32_t stage = 0, phase = 0, es = 0, ephase = 0;

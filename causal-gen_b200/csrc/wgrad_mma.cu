@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kThreadsM, 2) wgrad_mma_kernel(const __grid_co
 
   if (warp == kComputeWarps) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       const CUtensorMap* wide_map = SHIFT_A ? &P.x_map[wc.src] : &P.dy_map;
       const CUtensorMap* narrow_map = SHIFT_A ? &P.dy_map : &P.x_map[0];
       const uint32_t tx = SHIFT_A ? (P.x_bytes[wc.src] + P.dy_bytes) : (P.x_bytes[0] + P.dy_bytes);
@@ -236,30 +236,45 @@ __global__ void __launch_bounds__(kThreadsM, 2) wgrad_mma_kernel(const __grid_co
   // ------------------------------------------------------------------ flush
   __syncthreads();  // every stage has been consumed: the ring memory becomes the fp32 reduction tile
   if (threadIdx.x == 0) CG_TL(P.tl, 20);
-  float* sacc = reinterpret_cast<float*>(stages);  // [CO][CI][9]  (OIHW order of this chunk)
-  float* sbias = sacc + CO * CI * 9;               // [CO]
-  for (int e = threadIdx.x; e < CO * CI * 9 + CO; e += kThreadsM) sacc[e] = 0.f;
-  __syncthreads();
-  if (warp < kComputeWarps) {
-    const int g = lane >> 2, t = lane & 3;
+  // [CO][CI*9 (+1 pad)]: OIHW order of this chunk; the three kernel-row groups own disjoint taps, so the only
+  // overlap is between the two pixel halves: half 0 stores, half 1 adds after a barrier -- no atomics.
+  constexpr int ROW = CI * 9 + 1;  // +1: fragment rows (co) land in different banks
+  float* sacc = reinterpret_cast<float*>(stages);
+  float* sbias = sacc + CO * ROW;  // [CO]
+  for (int e = threadIdx.x; e < CO; e += kThreadsM) sbias[e] = 0.f;
 #pragma unroll
-    for (int kw = 0; kw < 3; ++kw) {
-      const int tap = tg * 3 + kw;
+  for (int half = 0; half < 2; ++half) {
+    if (warp < kComputeWarps && pg == half) {
+      const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt)
+      for (int kw = 0; kw < 3; ++kw) {
+        const int tap = tg * 3 + kw;
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const int co = mt * 16 + g, ci = nt * 8 + 2 * t;
-          atomicAdd(&sacc[(co * CI + ci) * 9 + tap], acc[kw][mt][nt][0]);
-          atomicAdd(&sacc[(co * CI + ci + 1) * 9 + tap], acc[kw][mt][nt][1]);
-          atomicAdd(&sacc[((co + 8) * CI + ci) * 9 + tap], acc[kw][mt][nt][2]);
-          atomicAdd(&sacc[((co + 8) * CI + ci + 1) * 9 + tap], acc[kw][mt][nt][3]);
-        }
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            float* p0 = sacc + (mt * 16 + g) * ROW + (nt * 8 + 2 * t) * 9 + tap;
+            float* p1 = p0 + 8 * ROW;
+            if (half == 0) {
+              p0[0] = acc[kw][mt][nt][0];
+              p0[9] = acc[kw][mt][nt][1];
+              p1[0] = acc[kw][mt][nt][2];
+              p1[9] = acc[kw][mt][nt][3];
+            } else {
+              p0[0] += acc[kw][mt][nt][0];
+              p0[9] += acc[kw][mt][nt][1];
+              p1[0] += acc[kw][mt][nt][2];
+              p1[9] += acc[kw][mt][nt][3];
+            }
+          }
+      }
     }
-    if (do_bias && t == 0) {
+    __syncthreads();
+    if (half == 0 && warp < kComputeWarps && do_bias && (lane & 3) == 0) {
+      const int g = lane >> 2;
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        atomicAdd(&sbias[mt * 16 + g], bacc[mt][0]);
+        atomicAdd(&sbias[mt * 16 + g], bacc[mt][0]);  // two warps (pixel halves) per row: cheap
         atomicAdd(&sbias[mt * 16 + g + 8], bacc[mt][2]);
       }
     }
@@ -276,7 +291,7 @@ __global__ void __launch_bounds__(kThreadsM, 2) wgrad_mma_kernel(const __grid_co
       const int co = e / (CI * 9), rem = e - co * (CI * 9);
       const int ci = rem / 9;
       if (co < co_n && ci < ci_n && co0 + co < cout_l && ci0 + ci < xlog)
-        atomicAdd(P.a.dw + ((long long)(co0 + co) * cin_l + (xoff + ci0)) * 9 + rem, sacc[e]);
+        atomicAdd(P.a.dw + ((long long)(co0 + co) * cin_l + (xoff + ci0)) * 9 + rem, sacc[co * ROW + rem]);
     }
     if (P.a.dbias != nullptr && (SHIFT_A ? blockIdx.y == 0 : true)) {
       for (int co = threadIdx.x; co < CO; co += kThreadsM)
@@ -388,9 +403,10 @@ int cg_wgrad_mma_try(const cg_wgrad_args* a, void* stream, int* handled) {
   kp.stage_bytes = (kp.wide_off + wide_planes * kPlaneFlat + 127) / 128 * 128;
   const int smem_bytes = kHdrM + kStagesM * kp.stage_bytes;
   // two CTAs per SM; CTAs along the pixel axis share the chunk's gradient through coalesced atomics
+  // (each CTA ends with one flush of its whole accumulator tile: keep >= 4 pixel tiles of work per CTA)
   int gx = (2 * cg_device_sms()) / kp.nchunks;
+  if (gx > (kp.ntiles + 3) / 4) gx = (kp.ntiles + 3) / 4;
   if (gx < 1) gx = 1;
-  if (gx > kp.ntiles) gx = kp.ntiles;
   cudaStream_t st = cg_stream(stream);
   int rc = CG_ERR_UNSUPPORTED;
 #define CG_MMA_CASE(mt, nt, sa) \

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   if (threadIdx.x == 0) CG_TL(P.tl, 0);
 
   if (warp == kMmaWarp) {
-    if (lane == 0) {
+    if (elect_one()) {
       int tl_i = 0;
       (void)tl_i;
       const uint32_t idesc = umma_idesc_bf16(128, Nq, 1, 1);
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
       tc_commit(BAR(9));
     }
   } else if (warp == kTmaWarp) {
-    if (lane == 0) {
+    if (elect_one()) {
       const int xs_i = p_is_x ? pc.src : qc.src;
       const CUtensorMap* xmap = &P.x_map[xs_i];
       const uint32_t tx = P.x_bytes[xs_i] + P.dy_bytes;
