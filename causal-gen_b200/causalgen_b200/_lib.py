@@ -24,7 +24,8 @@ class Src(C.Structure):
 class Seg(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("add", C.c_void_p), ("add2", C.c_void_p), ("mul", C.c_void_p),
                 ("ns", C.c_int64), ("add_ns", C.c_int64), ("add2_ns", C.c_int64), ("mul_ns", C.c_int64),
-                ("c0", C.c_int32), ("cn", C.c_int32), ("dtype", C.c_int32), ("mul_act", C.c_int32)]
+                ("c0", C.c_int32), ("cn", C.c_int32), ("dtype", C.c_int32), ("mul_act", C.c_int32),
+                ("out_act", C.c_int32), ("_pad", C.c_int32)]
 
 
 class ConvArgs(C.Structure):

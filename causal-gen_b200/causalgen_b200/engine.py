@@ -99,12 +99,17 @@ class BlockLayers:
     def __init__(self, eng: "Engine", mod: Block, src_logical: Sequence[int], res: int, grad_srcs=None):
         self.mod = mod
         self.act = L.ACT_RELU if mod.light else L.ACT_GELU
+        # ReLU commutes with bf16 rounding and relu(x) > 0 <=> x > 0, so the intermediate of a "light" block
+        # is stored already activated by the producing conv: its consumers (next conv, weight gradient) skip
+        # the pre-activation pass and the data-gradient mask reads the same tensor.
+        self.mid_out_act = L.ACT_RELU if mod.light else L.ACT_NONE
         centre = (res == 1 and mod.ksize == 3)
         convs = mod.convs
         self.layers: List[ConvLayer] = []
         for i, c in enumerate(convs):
             srcs = list(src_logical) if i == 0 else [c.weight.shape[1]]
-            self.layers.append(ConvLayer(eng.table, c.weight, c.bias, srcs, self.act,
+            act_i = L.ACT_NONE if (i > 0 and self.mid_out_act != L.ACT_NONE) else self.act
+            self.layers.append(ConvLayer(eng.table, c.weight, c.bias, srcs, act_i,
                                          centre_only=centre and c.weight.shape[2] == 3,
                                          grad_srcs=(grad_srcs if i == 0 else None)))
         self.proj = None
@@ -196,7 +201,7 @@ class Engine:
         cur = srcs
         for layer in bl.layers[:-1]:
             mid = new_act(N, H, W, layer.cout_l, self.device)
-            prog.add(layer.forward(cur, [SegSpec(mid, 0)], N, H, W))
+            prog.add(layer.forward(cur, [SegSpec(mid, 0, out_act=bl.mid_out_act)], N, H, W))
             r.mids.append(mid)
             cur = [mid]
         last = bl.layers[-1]

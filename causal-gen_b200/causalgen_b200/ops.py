@@ -95,6 +95,7 @@ class SegSpec:
     mul: Optional[View] = None
     mul_act: int = L.ACT_NONE
     add2: Optional[View] = None
+    out_act: int = L.ACT_NONE   # activation applied to the stored value (consumer-side pre-activation hoisted)
 
 
 class PackTable:
@@ -196,6 +197,7 @@ class ConvLayer:
             s.mul = sg.mul.ptr if sg.mul is not None else None
             s.mul_ns = sg.mul.ns if sg.mul is not None else 0
             s.mul_act = sg.mul_act
+            s.out_act = sg.out_act
 
     def forward(self, srcs: Sequence[View], segs: Sequence[SegSpec], N, H, W) -> L.Launch:
         assert [s.C for s in srcs] == self.src_pad, ([s.C for s in srcs], self.src_pad)

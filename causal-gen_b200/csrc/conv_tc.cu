@@ -42,25 +42,27 @@ constexpr int kXfWarp0 = 10;
 constexpr int kXfWarps = 4;
 constexpr int kThreads = (kXfWarp0 + kXfWarps) * 32;  // 448
 constexpr int kXfThreads = kXfWarps * 32;
-constexpr int kStages = 6;
+constexpr int kMaxStages = 32;  // A-ring depth is chosen per launch from the shared memory left over
+constexpr int kMinStages = 4;   //   after the resident weight slab (pick_nc guarantees this many)
 constexpr int kPlane3 = 2880;  // 18 rows * 10 px * 16 B
 constexpr int kPlane1 = 2048;  // 16 rows *  8 px * 16 B
-constexpr int kStageBytes = 4 * kPlane3;  // 11520 (multiple of 128: TMA destination alignment)
-constexpr int kHdrBytes = 1408;   // barriers (<=256B) | tmem slot @256 | bias[256] @320
+constexpr int kStageBytes = 4 * kPlane3;  // 11520: largest A stage (32 channels with halo); multiple of 128
+constexpr int kHdrBytes = 2176;   // barriers (<=1024B) | tmem slot @1024 | bias[256] @1088
 constexpr int kSmemMax = 232448;  // 227 KB
 constexpr int kMaxChunks = 40;
 constexpr int kMaxNc = 64;        // GEMM-N per CTA
-constexpr int kEStages = 3;       // epilogue-operand ring depth
+constexpr int kMaxEStages = 8;    // epilogue-operand ring depth (chosen per launch, >= kMinEStages)
+constexpr int kMinEStages = 2;
 constexpr int kESlots = 2;        // staged operands per tile
 // a staged operand tile is [Nc/8 octets][16 rows][8 px][8 ch] bf16 = Nc/8 planes of 2048 B
 __host__ __device__ constexpr int e_slot_bytes(int nc) { return (nc / 8) * kPlane1; }
-__host__ __device__ constexpr int e_bytes(int nc) { return kEStages * kESlots * e_slot_bytes(nc); }
+__host__ __device__ constexpr int e_bytes_min(int nc) { return kMinEStages * kESlots * e_slot_bytes(nc); }
 
-// barrier indices
-constexpr int B_LANDED = 0, B_AFULL = kStages, B_AEMPTY = 2 * kStages, B_BFULL = 3 * kStages,
+// barrier indices (fixed slots sized for the maximum ring depths)
+constexpr int B_LANDED = 0, B_AFULL = kMaxStages, B_AEMPTY = 2 * kMaxStages, B_BFULL = 3 * kMaxStages,
               B_ACCFULL = B_BFULL + 1, B_ACCEMPTY = B_ACCFULL + 2, B_EFULL = B_ACCEMPTY + 2,
-              B_EEMPTY = B_EFULL + kEStages, B_COUNT = B_EEMPTY + kEStages;
-static_assert(B_COUNT * 8 <= 256, "barrier block overflows the header");
+              B_EEMPTY = B_EFULL + kMaxEStages, B_COUNT = B_EEMPTY + kMaxEStages;
+static_assert(B_COUNT * 8 <= 1024, "barrier block overflows the header");
 
 struct Chunk {
   uint16_t src, oct0, nc16, kbase;  // source index, first channel octet, K-blocks of 16 (1 or 2), first K-block
@@ -81,6 +83,8 @@ struct alignas(64) KParams {
   int nE, emode;
   int nchunks, ntaps, Nc, nN, ktot16;
   int flat;  // 1: H=W=1, samples are the GEMM rows (128 per tile)
+  int nst, nest;       // A-ring / E-ring depths of this launch
+  int stage_bytes;     // bytes of one A stage (largest source box)
   int tiles_x, tiles_per_img, ntiles;
   long long HW8;  // H*W*8: elements per channel-octet plane
   uint32_t idesc, tmem_cols, slab_bytes, e_tx_bytes;
@@ -150,12 +154,14 @@ __device__ __forceinline__ uint4 act8(uint4 u, int act) {
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
-  float* s_bias = reinterpret_cast<float*>(smem + 320);
-  uint8_t* sA = smem + kHdrBytes;
-  uint8_t* sE = sA + kStages * kStageBytes;
-  uint8_t* sB = sE + (P.emode ? e_bytes(P.Nc) : 0);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 1024);
+  float* s_bias = reinterpret_cast<float*>(smem + 1088);
   const int eslot = e_slot_bytes(P.Nc);
+  const int nst = P.nst, nest = P.nest, stage_bytes = P.stage_bytes;
+  const int estage = P.nE * eslot;  // bytes of one E stage (only the operands this launch stages)
+  uint8_t* sA = smem + kHdrBytes;
+  uint8_t* sE = sA + nst * stage_bytes;
+  uint8_t* sB = sE + nest * estage;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunkN = blockIdx.y;
@@ -166,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (threadIdx.x == 0) CG_TL(P.tl, 32);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < nst; ++i) {
       mbar_init(BAR(B_LANDED + i), 1);
       mbar_init(BAR(B_AFULL + i), kXfWarps);
       mbar_init(BAR(B_AEMPTY + i), 1);
@@ -176,7 +182,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(BAR(B_ACCFULL + i), 1);
       mbar_init(BAR(B_ACCEMPTY + i), kEpiWarps);
     }
-    for (int i = 0; i < kEStages; ++i) {
+    for (int i = 0; i < nest; ++i) {
       mbar_init(BAR(B_EFULL + i), 1);
       mbar_init(BAR(B_EEMPTY + i), kEpiWarps);
     }
@@ -219,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       auto D64 = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
       const uint32_t b_step16 = (uint32_t)Nc * 2u;  // (Nc*32 B per K-block) >> 4
       const uint32_t plane2_16 = (uint32_t)(2 * plane) >> 4;
-      const uint32_t stage16 = (uint32_t)kStageBytes >> 4;
+      const uint32_t stage16 = (uint32_t)stage_bytes >> 4;
       const uint32_t idesc = P.idesc;
       const int ready0 = (act == CG_ACT_NONE) ? B_LANDED : B_AFULL;  // no activation: consume TMA data directly
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
@@ -251,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             alo += plane2_16;
           }
           tc_commit(BAR(B_AEMPTY + stage));  // frees the A stage once these MMAs retire
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == nst) { stage = 0; phase ^= 1u; }
         }
         tc_commit(BAR(B_ACCFULL + as));  // accumulator ready for the epilogue
         if (tl_i < 6) CG_TL(P.tl, 36 + 2 * tl_i);
@@ -272,21 +278,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           mbar_wait(BAR(B_EEMPTY + es), ephase ^ 1u);
           mbar_expect_tx(BAR(B_EFULL + es), P.e_tx_bytes);
           for (int k = 0; k < P.nE; ++k) {
-            const uint32_t dst = cg_smem_u32(sE + (es * kESlots + k) * eslot);
+            const uint32_t dst = cg_smem_u32(sE + es * estage + k * eslot);
             const int oct = nchunkN * (Nc >> 3) - P.eop[k].oct_off;  // may be out of range: zero-filled
             if (P.flat) tma_load_3d(dst, &P.e_map[k], 0, g.n, oct, BAR(B_EFULL + es));
             else tma_load_4d(dst, &P.e_map[k], g.w0 * 8, g.h0, oct, g.n, BAR(B_EFULL + es));
           }
-          if (++es == kEStages) { es = 0; ephase ^= 1u; }
+          if (++es == nest) { es = 0; ephase ^= 1u; }
         }
         for (int c = 0; c < P.nchunks; ++c) {
           const Chunk ch = P.chunk[c];
           mbar_wait(BAR(B_AEMPTY + stage), phase ^ 1u);
           mbar_expect_tx(BAR(B_LANDED + stage), P.src_bytes[ch.src]);
-          const uint32_t dst = cg_smem_u32(sA + stage * kStageBytes);
+          const uint32_t dst = cg_smem_u32(sA + stage * stage_bytes);
           if (P.flat) tma_load_3d(dst, &P.src_map[ch.src], 0, g.n, ch.oct0, BAR(B_LANDED + stage));
           else tma_load_4d(dst, &P.src_map[ch.src], (g.w0 - halo) * 8, g.h0 - halo, ch.oct0, g.n, BAR(B_LANDED + stage));
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == nst) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -299,12 +305,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         for (int c = 0; c < P.nchunks; ++c) {
           const int n16 = (int)(P.src_bytes[P.chunk[c].src] >> 4);  // 16-byte slots the TMA box filled
           warp_wait(BAR(B_LANDED + stage), phase, lane);
-          uint4* base = reinterpret_cast<uint4*>(sA + stage * kStageBytes);
+          uint4* base = reinterpret_cast<uint4*>(sA + stage * stage_bytes);
           for (int i = xt; i < n16; i += kXfThreads) base[i] = act8(base[i], act);
           fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_AFULL + stage));
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == nst) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -324,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     struct ChunkPlan {
       int col, sgi, lc, cnt;        // sgi < 0: chunk has no destination (padding / beyond cout)
       int k_add, k_add2, k_mul;     // -2 absent, -1 read from global memory, >= 0 staged E slot
-      int dtype, mul_act;
+      int dtype, mul_act, out_act;
       uint8_t* out;                 // bf16: ptr + (lc/8) planes; fp32: ptr + lc floats
       long long ns;
     } plan[2];
@@ -337,6 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       pl.k_add = pl.k_add2 = pl.k_mul = -2;
       pl.dtype = CG_BF16;
       pl.mul_act = CG_ACT_NONE;
+      pl.out_act = CG_ACT_NONE;
       pl.out = nullptr;
       pl.ns = 0;
       const int cg0 = nchunkN * Nc + pl.col;
@@ -350,6 +357,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         pl.cnt = min(16, sg.cn - lc);
         pl.dtype = sg.dtype;
         pl.mul_act = sg.mul_act;
+        pl.out_act = sg.out_act;
         pl.ns = sg.ns;
         pl.out = reinterpret_cast<uint8_t*>(sg.ptr) +
                  (sg.dtype == CG_F32 ? (long long)lc * 4 : (long long)(lc >> 3) * P.HW8 * 2);
@@ -384,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       if (nE > 0) warp_wait(BAR(B_EFULL + es), ephase, lane);
       warp_wait(BAR(B_ACCFULL + as), aphase, lane);
       tc_fence_after();
-      const uint8_t* e_row = sE + (size_t)(es * kESlots) * eslot + (size_t)m * 16;
+      const uint8_t* e_row = sE + (size_t)es * estage + (size_t)m * 16;
       const uint32_t t_row = tmem_base + as * (uint32_t)Nc + ((uint32_t)(quarter * 32) << 16);
       float acc[2][16];
       __syncwarp();  // .aligned TMEM loads need the whole warp converged
@@ -443,6 +451,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[h8 + i] += x[i];
           }
+          if (pl.out_act == CG_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[h8 + i] = fmaxf(v[h8 + i], 0.f);
+          } else if (pl.out_act == CG_ACT_GELU) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[h8 + i] = cg_gelu(v[h8 + i]);
+          }
           if (pl.dtype == CG_F32) {  // fp32 statistics: row layout (pixel, channel), pitch ns
             float* op = reinterpret_cast<float*>(pl.out) + ((long long)n * H * W + hw) * pl.ns + h8;
             *reinterpret_cast<float4*>(op) = make_float4(v[h8], v[h8 + 1], v[h8 + 2], v[h8 + 3]);
@@ -456,7 +471,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       if (nE > 0) {
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(B_EEMPTY + es));
-        if (++es == kEStages) { es = 0; ephase ^= 1u; }
+        if (++es == nest) { es = 0; ephase ^= 1u; }
       }
       if (threadIdx.x == 0 && tl_i < 8) CG_TL(P.tl, 50 + tl_i);
       ++tl_i;
@@ -475,10 +490,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 // GEMM-N per CTA (<= 64, multiple of 16) such that the resident weight slab fits.  Prefer a size that also
 // leaves room for the epilogue-operand ring (*emode = 1); huge-K layers fall back to no ring.
 int pick_nc(int ktot16, int cout, int* emode) {
-  const int base = kSmemMax - kHdrBytes - kStages * kStageBytes;
+  const int base = kSmemMax - kHdrBytes - kMinStages * kStageBytes;
   for (int mode = 1; mode >= 0; --mode) {
     for (int nc_max = kMaxNc; nc_max >= 16; nc_max -= 16) {
-      if (ktot16 * nc_max * 32 + (mode ? e_bytes(nc_max) : 0) > base) continue;
+      if (ktot16 * nc_max * 32 + (mode ? e_bytes_min(nc_max) : 0) > base) continue;
       const int nN = (cout + nc_max - 1) / nc_max;
       const int nc = ((cout + nN - 1) / nN + 15) / 16 * 16;
       if (emode) *emode = mode;
@@ -633,7 +648,24 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
   uint32_t cols = 32;
   while (cols < 2u * kp.Nc) cols <<= 1;
   kp.tmem_cols = cols;
-  const int smem_bytes = kHdrBytes + kStages * kStageBytes + (kp.emode ? e_bytes(kp.Nc) : 0) + (int)kp.slab_bytes;
+  // ring depths: all shared memory left after the weight slab is prefetch distance.  E stages cover as many
+  // tiles ahead as the A ring does (bytes per tile: nchunks A stages + nE staged operands).
+  kp.stage_bytes = 0;
+  for (int s = 0; s < a->nsrc; ++s)
+    if ((int)kp.src_bytes[s] > kp.stage_bytes) kp.stage_bytes = (int)kp.src_bytes[s];
+  {
+    const int budget = kSmemMax - kHdrBytes - (int)kp.slab_bytes;
+    const int e_tile = kp.nE * e_slot_bytes(kp.Nc), a_tile = kp.nchunks * kp.stage_bytes;
+    kp.nest = 0;
+    if (e_tile > 0) {
+      int d = budget / (a_tile + e_tile);
+      kp.nest = d < kMinEStages ? kMinEStages : (d > kMaxEStages ? kMaxEStages : d);
+    }
+    kp.nst = (budget - kp.nest * e_tile) / kp.stage_bytes;
+    if (kp.nst > kMaxStages) kp.nst = kMaxStages;
+    CG_REQUIRE(kp.nst >= 2, "cg_conv2d: no shared memory left for the input ring (K=%d)", kp.ktot16 * 16);
+  }
+  const int smem_bytes = kHdrBytes + kp.nst * kp.stage_bytes + kp.nest * kp.nE * e_slot_bytes(kp.Nc) + (int)kp.slab_bytes;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);

@@ -68,6 +68,9 @@ typedef struct {
   int32_t c0, cn;   /* c0 multiple of 16, cn multiple of 8 */
   int32_t dtype;    /* CG_BF16 or CG_F32 */
   int32_t mul_act;  /* activation whose derivative is applied with `mul` */
+  int32_t out_act;  /* activation applied to the finished value before the store: lets a producer write
+                       act(y) when every consumer of y applies the same pre-activation (Block, src/vae.py:49-56) */
+  int32_t _pad;
 } cg_seg;
 
 typedef struct {

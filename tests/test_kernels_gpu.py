@@ -126,6 +126,12 @@ def test_conv_segments_add_and_fp32_split():
     assert_close(stats.t.permute(0, 3, 1, 2), ref[:, :32], 2e-3, "fp32 stats split")
     assert_close(to_nchw(feat.t, 48), ref[:, 32:], 1e-2, "feature split")
     assert_close(to_nchw(hsum.t, 48), ref[:, 32:] + to_nchw(h.t, 48), 1e-2, "residual add")
+    # stored activation: the producer writes relu(y) / gelu(y) for consumers that all pre-activate
+    for act_id in (1, 2):
+        ya = new_act(N, H, W, 48, DEV)
+        layer.forward(views, [SegSpec(stats, 0), SegSpec(ya, 32, add=h, out_act=act_id)], N, H, W)(stream())
+        torch.cuda.synchronize()
+        assert_close(to_nchw(ya.t, 48), act_fn(act_id)(ref[:, 32:] + to_nchw(h.t, 48)), 1e-2, f"out_act {act_id}")
 
 
 @pytest.mark.parametrize("case", [(2, 16, 16, [32], 0, 16, 3, 1), (2, 24, 24, [48, 48], 4, 8, 3, 2),
