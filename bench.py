@@ -278,7 +278,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--config", default="ukbb192")
-    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step (reference bs=32)")
+    ap.add_argument("--batch", type=int, default=128,
+                    help="images per GPU per step (throughput configuration; the reference's bs=32 is also measured)")
+    ap.add_argument("--no-ref-batch", action="store_true", help="skip the extra measurement at the reference bs=32")
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-graph", action="store_true")
@@ -340,7 +342,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{args.config} HVAE ELBO training step, {margs.input_channels}x{margs.input_res}x"
-                                   f"{margs.input_res} uint8 images, batch {B}/GPU (reference bs), fwd+bwd+"
+                                   f"{margs.input_res} uint8 images, batch {B}/GPU, fwd+bwd+"
                                    f"allreduce+clip+AdamW+EMA, reference init (seed 7)",
                        "params": int(sum(p.numel() for p in model.parameters())),
                        "l2": "per-step working set (saved activations + gradients) is several GB >> 126 MB L2; "
@@ -378,6 +380,25 @@ def main():
             line["cf_inference"] = {"metric": "counterfactual_images_per_sec", "value": cf_val, "unit": "images/s",
                                     "batch_per_gpu": Bc, "tensor_frac": CF_GFLOP.get(args.config, 0) * cf_val / 1e3 / tensor_tfs,
                                     "note": "abduct + forward_latents(cf_pa, pa) batched + combine, eager launches"}
+    # the same step at the reference's own batch size (src/hps.py ukbb192: bs=32): latency-bound regime
+    if B != 32 and not args.no_ref_batch:
+        del trainer
+        model.train()
+        model.engine().programs.clear()
+        torch.cuda.empty_cache()
+        tr32 = Trainer(model, 32, lr=margs.lr, wd=margs.wd, betas=margs.betas, lr_warmup_steps=margs.lr_warmup_steps,
+                       grad_clip=margs.grad_clip, grad_skip=margs.grad_skip, ema_rate=margs.ema_rate, beta=margs.beta,
+                       use_graph=not args.no_graph, noise_seed=7)
+        x32 = [x[:32].contiguous() for x in xs_d]
+        p32 = [p[:32].contiguous() for p in pas_d]
+        for i in range(4):
+            tr32.step_device(x32[i % nb], p32[i % nb])
+        n32 = min(args.steps, 10)
+        ms32, _, _ = timed(lambda i: tr32.step_device(x32[i % nb], p32[i % nb]), n32, world)
+        if rank == 0:
+            line["reference_batch32"] = {"value": 32 * world * n32 / (ms32 / 1e3), "unit": "images/s",
+                                         "ms_per_step": ms32 / n32, "batch_per_gpu": 32}
+        del tr32
     if rank == 0:
         if world == 1 and not args.no_cpu:
             sec, n = cpu_port_step_time(args.config, sd_cpu, args.cpu_batch, args.cpu_seconds, os.cpu_count() or 1)

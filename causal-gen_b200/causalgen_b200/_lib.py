@@ -94,6 +94,7 @@ _SIGNATURES = {
     "cg_packed_weight_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "cg_pack_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "cg_conv2d_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
+    "cg_conv2d_wgrad_launches": (C.c_int32, [C.POINTER(WgradArgs)]),
     "cg_stem_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                               C.c_int32, C.c_int64, C.c_void_p]),
     "cg_stem_wgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,

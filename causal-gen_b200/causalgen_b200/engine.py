@@ -55,8 +55,11 @@ class Program:
     def add(self, ln):
         self.launches.append(ln)
         if isinstance(ln, L.Launch):
-            self.n_kernels += 2 if (ln.name == "cg_conv2d_wgrad" and ln.keep[0].dbias) else 1
-            ln.side = ln.name == "cg_conv2d_wgrad"
+            if ln.name == "cg_conv2d_wgrad":
+                self.n_kernels += int(L.load().cg_conv2d_wgrad_launches(C.byref(ln.keep[0])))
+                ln.side = True
+            else:
+                self.n_kernels += 1
         return ln
 
     def call(self, name, *args):

@@ -24,6 +24,8 @@
 // GELU layers and 1x1 / 1-pixel problems stay on the tcgen05 kernel of wgrad_tc.cu.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "cg_common.cuh"
 
 namespace {
@@ -321,10 +323,27 @@ int launch_mma(const MParams& kp, int gx, int smem_bytes, cudaStream_t st) {
 
 // Returns CG_OK with *handled = 1 when the problem was launched on the mma.sync kernel, *handled = 0 when the
 // caller must use the tcgen05 kernel (1x1 / centre-tap / 1-pixel problems, GELU, both operands wide).
+static bool mma_eligible(const cg_wgrad_args* a) {
+  if (a->ksize != 3 || a->taps != 9 || (a->H == 1 && a->W == 1)) return false;
+  if (a->act != CG_ACT_NONE && a->act != CG_ACT_RELU) return false;
+  int xtot = 0;
+  for (int s = 0; s < a->nsrc; ++s) xtot += a->src[s].C;
+  return (a->dy_c <= 48 && a->dy_c <= xtot) || (xtot <= 48 && a->nsrc == 1);
+}
+
+// kernels one cg_conv2d_wgrad call launches: the mma.sync kernel folds the bias gradient in, the tcgen05
+// kernel is followed by a column-sum kernel when dbias is requested
+extern "C" int32_t cg_conv2d_wgrad_launches(const cg_wgrad_args* a) {
+  if (a == nullptr) return 0;
+  const char* e = getenv("CG_WGRAD_TC_ONLY");
+  const bool tc_only = e != nullptr && e[0] == '1';
+  if (!tc_only && mma_eligible(a)) return 1;
+  return a->dbias != nullptr ? 2 : 1;
+}
+
 int cg_wgrad_mma_try(const cg_wgrad_args* a, void* stream, int* handled) {
   *handled = 0;
-  if (a->ksize != 3 || a->taps != 9 || (a->H == 1 && a->W == 1)) return CG_OK;
-  if (a->act != CG_ACT_NONE && a->act != CG_ACT_RELU) return CG_OK;
+  if (!mma_eligible(a)) return CG_OK;
   int xtot = 0;
   for (int s = 0; s < a->nsrc; ++s) xtot += a->src[s].C;
   const int dyc = a->dy_c;

@@ -132,6 +132,8 @@ typedef struct {
 
 /* dW += sum_pixels dy (x) act(cat(src)) shifted per tap; dbias += sum_pixels dy */
 int cg_conv2d_wgrad(const cg_wgrad_args* a, void* stream);
+/* number of kernels the call above launches for these arguments (1 or 2): launch accounting only */
+int32_t cg_conv2d_wgrad_launches(const cg_wgrad_args* a);
 
 /* 7x7 stem, fp32 NCHW image in -> bf16 planar out (src/vae.py:104-110,126) and its weight grad */
 int cg_stem_fwd(const float* x, const float* w, const float* b, void* y, int32_t N, int32_t Cin,
