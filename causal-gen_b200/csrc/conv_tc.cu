@@ -151,6 +151,46 @@ __device__ __forceinline__ uint4 act8(uint4 u, int act) {
   return cg_pack8(f);
 }
 
+// Straight-line epilogue of one 16-column chunk for the common case (bf16 destination, all 16 columns live,
+// every fused operand staged in shared memory, ReLU-type activations): no data-dependent branches, invalid
+// (out-of-image) lanes compute on whatever their shared-memory slot holds and only the store is predicated.
+template <bool MUL, bool ADD, bool ADD2, bool ORELU>
+__device__ __forceinline__ void epi_chunk_fast(float (&v)[16], const uint8_t* e0, int eslot, int k_mul, int k_add,
+                                               int k_add2, const float* bias, bf16* op, long long HW8, bool valid) {
+  if (bias != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 16; q += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bias + q);
+      v[q] += b4.x; v[q + 1] += b4.y; v[q + 2] += b4.z; v[q + 3] += b4.w;
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float x[8];
+    if (MUL) {  // ReLU'(x): pass the gradient where the saved forward input is positive
+      cg_unpack8(*reinterpret_cast<const uint4*>(e0 + k_mul * eslot + h * kPlane1), x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[8 * h + i] = x[i] > 0.f ? v[8 * h + i] : 0.f;
+    }
+    if (ADD) {
+      cg_unpack8(*reinterpret_cast<const uint4*>(e0 + k_add * eslot + h * kPlane1), x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[8 * h + i] += x[i];
+    }
+    if (ADD2) {
+      cg_unpack8(*reinterpret_cast<const uint4*>(e0 + k_add2 * eslot + h * kPlane1), x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[8 * h + i] += x[i];
+    }
+    if (ORELU) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[8 * h + i] = fmaxf(v[8 * h + i], 0.f);
+    }
+    const uint4 o = cg_pack8(v + 8 * h);
+    if (valid) *reinterpret_cast<uint4*>(op + h * HW8) = o;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -163,7 +203,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   uint8_t* sE = sA + nst * stage_bytes;
   uint8_t* sB = sE + nest * estage;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle so the compiler knows it is warp-uniform (role branches, epilogue plans)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int nchunkN = blockIdx.y;
   const int Nc = P.Nc;
   const uint32_t bar0 = cg_smem_u32(bars);
@@ -331,6 +372,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       int col, sgi, lc, cnt;        // sgi < 0: chunk has no destination (padding / beyond cout)
       int k_add, k_add2, k_mul;     // -2 absent, -1 read from global memory, >= 0 staged E slot
       int dtype, mul_act, out_act;
+      int fast;                     // -1: generic path; else bit0 mul, bit1 add, bit2 add2, bit3 relu-on-store
       uint8_t* out;                 // bf16: ptr + (lc/8) planes; fp32: ptr + lc floats
       long long ns;
     } plan[2];
@@ -344,6 +386,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       pl.dtype = CG_BF16;
       pl.mul_act = CG_ACT_NONE;
       pl.out_act = CG_ACT_NONE;
+      pl.fast = -1;
       pl.out = nullptr;
       pl.ns = 0;
       const int cg0 = nchunkN * Nc + pl.col;
@@ -370,6 +413,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             else if (P.eop[k].kind == 1) pl.k_add2 = k;
             else pl.k_mul = k;
           }
+        if (sg.dtype == CG_BF16 && pl.cnt == 16 && pl.k_add != -1 && pl.k_add2 != -1 && pl.k_mul != -1 &&
+            (pl.k_mul == -2 || sg.mul_act == CG_ACT_RELU) && (sg.out_act == CG_ACT_NONE || sg.out_act == CG_ACT_RELU) &&
+            !(pl.k_mul >= 0 && pl.k_add2 >= 0))
+          pl.fast = (pl.k_mul >= 0 ? 1 : 0) | (pl.k_add >= 0 ? 2 : 0) | (pl.k_add2 >= 0 ? 4 : 0) |
+                    (sg.out_act == CG_ACT_RELU ? 8 : 0);
         break;
       }
     }
@@ -405,7 +453,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const ChunkPlan& pl = plan[j];
-        if (pl.sgi < 0 || !valid) continue;
+        if (pl.sgi < 0) continue;
+        if (pl.fast >= 0) {
+          const uint8_t* e0 = e_row + (pl.col >> 3) * kPlane1;
+          const float* bp = has_bias ? s_bias + pl.col : nullptr;
+          bf16* op = reinterpret_cast<bf16*>(pl.out) + n * pl.ns + hw * 8;
+#define CG_EPI(code, M, A, A2, R) \
+  case code: epi_chunk_fast<M, A, A2, R>(acc[j], e0, eslot, pl.k_mul, pl.k_add, pl.k_add2, bp, op, P.HW8, valid); break;
+          switch (pl.fast) {
+            CG_EPI(0, false, false, false, false) CG_EPI(8, false, false, false, true)
+            CG_EPI(2, false, true, false, false) CG_EPI(10, false, true, false, true)
+            CG_EPI(6, false, true, true, false) CG_EPI(14, false, true, true, true)
+            CG_EPI(1, true, false, false, false) CG_EPI(3, true, true, false, false)
+            default: break;
+          }
+#undef CG_EPI
+          continue;
+        }
+        if (!valid) continue;
         float* v = acc[j];
         if (has_bias) {
 #pragma unroll
