@@ -15,7 +15,7 @@
 //   roles       M = dY channels (A fragments), N = X channels (B fragments), K = 16 pixels (two tile rows).
 //               SHIFT_A: dY is narrow -> dY carries the halo, tile partitions X positions.
 //               else   : X is narrow  -> X carries the halo, tile partitions dY positions.
-//   warps       6 compute warps = 3 kernel rows (kh) x 2 halves of the tile's pixel rows, + 1 TMA producer warp;
+//   warps       12 compute warps = 3 kernel rows (kh) x 4 quarters of the tile's pixel rows, + 1 TMA producer warp;
 //               accumulators (3 taps x MT x NT fragments, <= 96 fp32 registers) persist over all tiles of the CTA.
 //   activation  ReLU of the forward pre-activation is applied to the X fragments in registers.
 //   dbias       one extra mma of the (unshifted) dY fragment against a ones fragment -- no second pass over dY.
@@ -30,13 +30,14 @@
 
 namespace {
 
-constexpr int kComputeWarps = 6;
-constexpr int kThreadsM = (kComputeWarps + 1) * 32;  // 224
-constexpr int kStagesM = 4;
+constexpr int kComputeWarps = 12;  // 3 kernel rows x 4 pixel-row quarters of the tile
+constexpr int kThreadsM = kComputeWarps * 32;  // 384: three warps per scheduler -> up to 168 registers/thread
+constexpr int kStagesM = 8;
 constexpr int kPlaneHalo = 2880;  // 18 rows * 10 px * 16 B
 constexpr int kPlaneFlat = 2048;  // 16 rows *  8 px * 16 B
 constexpr int kMaxChunksM = 32;
 constexpr int kHdrM = 128;
+constexpr int kPixGroups = kComputeWarps / 3;  // 4: each handles 2 of the tile's 8 k-steps
 
 struct MChunk {
   int16_t src, c0, nc;  // chunk of the wide operand: X source index (or 0 for dY), first channel, channels
@@ -82,11 +83,11 @@ __device__ __forceinline__ uint32_t relu2(uint32_t u) {
 }
 
 template <int MT, int NT, bool SHIFT_A>
-__global__ void __launch_bounds__(kThreadsM, 2) wgrad_mma_kernel(const __grid_constant__ MParams P) {
+__global__ void __launch_bounds__(kThreadsM, 1) wgrad_mma_kernel(const __grid_constant__ MParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0..3] full, [4..7] empty
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0..7] full, [8..15] empty
   uint8_t* stages = smem + kHdrM;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t bar0 = cg_smem_u32(bars);
   auto FULL = [&](int i) { return bar0 + 8u * i; };
   auto EMPTY = [&](int i) { return bar0 + 8u * (kStagesM + i); };
@@ -118,31 +119,36 @@ __global__ void __launch_bounds__(kThreadsM, 2) wgrad_mma_kernel(const __grid_co
 #pragma unroll
     for (int q = 0; q < 4; ++q) bacc[mt][q] = 0.f;
 
-  const int tg = warp % 3, pg = warp / 3;  // kernel row kh, pixel-row half (compute warps only)
+  const int tg = warp % 3, pg = warp / 3;  // kernel row kh, pixel-row quarter (compute warps only)
   const bool do_bias = P.a.dbias != nullptr && (SHIFT_A ? (blockIdx.y == 0 && tg == 1) : (tg == 0));
 
-  if (warp == kComputeWarps) {
-    // ------------------------------------------------------------------ TMA producer
-    if (elect_one()) {
-      const CUtensorMap* wide_map = SHIFT_A ? &P.x_map[wc.src] : &P.dy_map;
-      const CUtensorMap* narrow_map = SHIFT_A ? &P.dy_map : &P.x_map[0];
-      const uint32_t tx = SHIFT_A ? (P.x_bytes[wc.src] + P.dy_bytes) : (P.x_bytes[0] + P.dy_bytes);
-      const int w_oct = wc.c0 >> 3;
-      uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-        const int n = tile / P.tiles_per_img;
-        const int r = tile - n * P.tiles_per_img;
-        const int ty = r / P.tiles_x;
-        const int h0 = ty * 16, w0 = (r - ty * P.tiles_x) * 8;
-        mbar_wait(EMPTY(stage), phase ^ 1u);
-        mbar_expect_tx(FULL(stage), tx);
-        const uint32_t sb = cg_smem_u32(stages + stage * P.stage_bytes);
-        tma4m(sb, narrow_map, (w0 - 1) * 8, h0 - 1, 0, n, FULL(stage));
-        tma4m(sb + P.wide_off, wide_map, w0 * 8, h0, w_oct, n, FULL(stage));
-        if (++stage == kStagesM) { stage = 0; phase ^= 1u; }
-      }
-    }
-  } else {
+  // TMA issue is folded into warp 0 (one elected lane): before computing tile i it requests tile i + kStagesM - 1,
+  // i.e. the stage every warp released after tile i - 1.  No dedicated producer warp: 12 warps = 3 per scheduler.
+  const CUtensorMap* wide_map = SHIFT_A ? &P.x_map[wc.src] : &P.dy_map;
+  const CUtensorMap* narrow_map = SHIFT_A ? &P.dy_map : &P.x_map[0];
+  const uint32_t tx = SHIFT_A ? (P.x_bytes[wc.src] + P.dy_bytes) : (P.x_bytes[0] + P.dy_bytes);
+  const int w_oct = wc.c0 >> 3;
+  uint32_t p_stage = 0, p_phase = 0;
+  int p_tile = blockIdx.x;
+  auto produce = [&]() {  // called by one elected lane of warp 0
+    if (p_tile >= P.ntiles) return;
+    const int n = p_tile / P.tiles_per_img;
+    const int r = p_tile - n * P.tiles_per_img;
+    const int ty = r / P.tiles_x;
+    const int h0 = ty * 16, w0 = (r - ty * P.tiles_x) * 8;
+    mbar_wait(EMPTY(p_stage), p_phase ^ 1u);
+    mbar_expect_tx(FULL(p_stage), tx);
+    const uint32_t sb = cg_smem_u32(stages + p_stage * P.stage_bytes);
+    tma4m(sb, narrow_map, (w0 - 1) * 8, h0 - 1, 0, n, FULL(p_stage));
+    tma4m(sb + P.wide_off, wide_map, w0 * 8, h0, w_oct, n, FULL(p_stage));
+    if (++p_stage == kStagesM) { p_stage = 0; p_phase ^= 1u; }
+    p_tile += gridDim.x;
+  };
+  if (warp == 0 && elect_one()) {
+    for (int i = 0; i < kStagesM - 1; ++i) produce();
+  }
+  __syncwarp();
+  {
     // ------------------------------------------------------------------ compute warps
     const int j = lane >> 3, i = lane & 7;  // ldmatrix: lane supplies row i of matrix j
     const bool relu = P.a.act == CG_ACT_RELU;
@@ -163,40 +169,44 @@ __global__ void __launch_bounds__(kThreadsM, 2) wgrad_mma_kernel(const __grid_co
     (void)tl_i;
     if (threadIdx.x == 0) CG_TL(P.tl, 0);
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+      if (warp == 0) {
+        if (elect_one()) produce();
+        __syncwarp();
+      }
       if (lane == 0) mbar_wait(FULL(stage), phase);
       __syncwarp();
       if (threadIdx.x == 0 && tl_i < 8) CG_TL(P.tl, 2 + 2 * tl_i);
       const uint32_t sb = cg_smem_u32(stages + stage * P.stage_bytes);
 #pragma unroll 1
-      for (int ks = 0; ks < 4; ++ks) {
-        const int r0 = 2 * (pg * 4 + ks);  // first of the two tile rows of this k-step
+      for (int ks = 0; ks < 8 / kPixGroups; ++ks) {
+        const int r0 = 2 * (pg * (8 / kPixGroups) + ks);  // first of the two tile rows of this k-step
         if (SHIFT_A) {
-          // dY fragments of the three taps of kernel row tg: halo[(r + 2 - kh)][(c + 2 - kw)]
-          uint32_t a[3][MT][4];
-#pragma unroll
-          for (int kw = 0; kw < 3; ++kw)
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-              ldsm_x4_t(a[kw][mt], sb + a_off + (uint32_t)(mt * 2 * kPlaneHalo + (r0 * 10 - kw) * 16));
-          if (do_bias) {
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) mma_bf16(bacc[mt], a[1][mt], ones, ones);
-          }
+          // X fragments of this k-step stay in registers while the three taps of kernel row tg sweep over dY:
+          // dY position of tap (kh, kw) for tile pixel (r, c) is halo[(r + 2 - kh)][(c + 2 - kw)]
+          uint32_t b[NT][2];
 #pragma unroll
           for (int n2 = 0; n2 < NT / 2; ++n2) {
-            uint32_t b[4];
-            ldsm_x4_t(b, sb + b_off + (uint32_t)(n2 * 2 * kPlaneFlat + r0 * 8 * 16));
-            if (relu) {
+            uint32_t t4[4];
+            ldsm_x4_t(t4, sb + b_off + (uint32_t)(n2 * 2 * kPlaneFlat + r0 * 8 * 16));
+            b[2 * n2][0] = relu ? relu2(t4[0]) : t4[0];
+            b[2 * n2][1] = relu ? relu2(t4[1]) : t4[1];
+            b[2 * n2 + 1][0] = relu ? relu2(t4[2]) : t4[2];
+            b[2 * n2 + 1][1] = relu ? relu2(t4[3]) : t4[3];
+          }
 #pragma unroll
-              for (int q = 0; q < 4; ++q) b[q] = relu2(b[q]);
+          for (int kw = 0; kw < 3; ++kw) {
+            uint32_t a[MT][4];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+              ldsm_x4_t(a[mt], sb + a_off + (uint32_t)(mt * 2 * kPlaneHalo + (r0 * 10 - kw) * 16));
+            if (kw == 1 && do_bias) {
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) mma_bf16(bacc[mt], a[mt], ones, ones);
             }
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw)
+            for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
-                mma_bf16(acc[kw][mt][2 * n2], a[kw][mt], b[0], b[1]);
-                mma_bf16(acc[kw][mt][2 * n2 + 1], a[kw][mt], b[2], b[3]);
-              }
+              for (int nt = 0; nt < NT; ++nt) mma_bf16(acc[kw][mt][nt], a[mt], b[nt][0], b[nt][1]);
           }
         } else {
           uint32_t a[MT][4];
@@ -239,14 +249,14 @@ __global__ void __launch_bounds__(kThreadsM, 2) wgrad_mma_kernel(const __grid_co
   __syncthreads();  // every stage has been consumed: the ring memory becomes the fp32 reduction tile
   if (threadIdx.x == 0) CG_TL(P.tl, 20);
   // [CO][CI*9 (+1 pad)]: OIHW order of this chunk; the three kernel-row groups own disjoint taps, so the only
-  // overlap is between the two pixel halves: half 0 stores, half 1 adds after a barrier -- no atomics.
+  // overlap is between the pixel-row groups: group 0 stores, groups 1.. add in turn after a barrier -- no atomics.
   constexpr int ROW = CI * 9 + 1;  // +1: fragment rows (co) land in different banks
   float* sacc = reinterpret_cast<float*>(stages);
   float* sbias = sacc + CO * ROW;  // [CO]
   for (int e = threadIdx.x; e < CO; e += kThreadsM) sbias[e] = 0.f;
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    if (warp < kComputeWarps && pg == half) {
+  for (int half = 0; half < kPixGroups; ++half) {
+    if (pg == half) {
       const int g = lane >> 2, t = lane & 3;
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
@@ -272,11 +282,11 @@ __global__ void __launch_bounds__(kThreadsM, 2) wgrad_mma_kernel(const __grid_co
       }
     }
     __syncthreads();
-    if (half == 0 && warp < kComputeWarps && do_bias && (lane & 3) == 0) {
+    if (half == 0 && do_bias && (lane & 3) == 0) {
       const int g = lane >> 2;
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        atomicAdd(&sbias[mt * 16 + g], bacc[mt][0]);  // two warps (pixel halves) per row: cheap
+        atomicAdd(&sbias[mt * 16 + g], bacc[mt][0]);  // one warp per pixel group and row: cheap
         atomicAdd(&sbias[mt * 16 + g + 8], bacc[mt][2]);
       }
     }
@@ -421,9 +431,9 @@ int cg_wgrad_mma_try(const cg_wgrad_args* a, void* stream, int* handled) {
   kp.wide_off = narrow_planes * kPlaneHalo;  // multiple of 128 (even plane count)
   kp.stage_bytes = (kp.wide_off + wide_planes * kPlaneFlat + 127) / 128 * 128;
   const int smem_bytes = kHdrM + kStagesM * kp.stage_bytes;
-  // two CTAs per SM; CTAs along the pixel axis share the chunk's gradient through coalesced atomics
-  // (each CTA ends with one flush of its whole accumulator tile: keep >= 4 pixel tiles of work per CTA)
-  int gx = (2 * cg_device_sms()) / kp.nchunks;
+  // CTAs along the pixel axis share the chunk's gradient through coalesced atomics
+  // one CTA per SM; each CTA ends with one flush of its whole accumulator tile: keep >= 4 tiles of work per CTA
+  int gx = cg_device_sms() / kp.nchunks;
   if (gx > (kp.ntiles + 3) / 4) gx = (kp.ntiles + 3) / 4;
   if (gx < 1) gx = 1;
   cudaStream_t st = cg_stream(stream);
