@@ -15,7 +15,7 @@
 //   roles       M = dY channels (A fragments), N = X channels (B fragments), K = 16 pixels (two tile rows).
 //               SHIFT_A: dY is narrow -> dY carries the halo, tile partitions X positions.
 //               else   : X is narrow  -> X carries the halo, tile partitions dY positions.
-//   warps       12 compute warps = 3 kernel rows (kh) x 4 quarters of the tile's pixel rows, + 1 TMA producer warp;
+//   warps       12 warps = 3 kernel rows (kh) x 4 pixel groups; a group owns every 4th tile of the CTA and issues its own TMA;
 //               accumulators (3 taps x MT x NT fragments, <= 96 fp32 registers) persist over all tiles of the CTA.
 //   activation  ReLU of the forward pre-activation is applied to the X fragments in registers.
 //   dbias       one extra mma of the (unshifted) dY fragment against a ones fragment -- no second pass over dY.
@@ -30,14 +30,14 @@
 
 namespace {
 
-constexpr int kComputeWarps = 12;  // 3 kernel rows x 4 pixel-row quarters of the tile
+constexpr int kComputeWarps = 12;  // 3 kernel rows x 4 pixel groups (each group takes every 4th tile)
 constexpr int kThreadsM = kComputeWarps * 32;  // 384: three warps per scheduler -> up to 168 registers/thread
-constexpr int kStagesM = 8;
+constexpr int kMaxStagesM = 16;  // ring depth per launch: multiple of 4 (one slice per pixel group), from smem budget
 constexpr int kPlaneHalo = 2880;  // 18 rows * 10 px * 16 B
 constexpr int kPlaneFlat = 2048;  // 16 rows *  8 px * 16 B
 constexpr int kMaxChunksM = 32;
-constexpr int kHdrM = 128;
-constexpr int kPixGroups = kComputeWarps / 3;  // 4: each handles 2 of the tile's 8 k-steps
+constexpr int kHdrM = 256;
+constexpr int kPixGroups = kComputeWarps / 3;  // 4
 
 struct MChunk {
   int16_t src, c0, nc;  // chunk of the wide operand: X source index (or 0 for dY), first channel, channels
@@ -51,7 +51,7 @@ struct alignas(64) MParams {
   uint32_t x_bytes[CG_MAX_SRC], dy_bytes;  // TMA transaction bytes of one box
   int nchunks;
   int tiles_x, tiles_per_img, ntiles;
-  int stage_bytes, wide_off;
+  int stage_bytes, wide_off, nst;
   unsigned long long* tl;  // debug timeline (CG_TIMELINE builds)
 };
 
@@ -85,20 +85,20 @@ __device__ __forceinline__ uint32_t relu2(uint32_t u) {
 template <int MT, int NT, bool SHIFT_A>
 __global__ void __launch_bounds__(kThreadsM, 1) wgrad_mma_kernel(const __grid_constant__ MParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0..7] full, [8..15] empty
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0..15] full, [16..31] empty
   uint8_t* stages = smem + kHdrM;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t bar0 = cg_smem_u32(bars);
   auto FULL = [&](int i) { return bar0 + 8u * i; };
-  auto EMPTY = [&](int i) { return bar0 + 8u * (kStagesM + i); };
+  auto EMPTY = [&](int i) { return bar0 + 8u * (kMaxStagesM + i); };
   constexpr int CO = MT * 16, CI = NT * 8;
   const MChunk wc = P.chunk[blockIdx.y];
   if (threadIdx.x == 0) CG_TL(P.tl, 1);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStagesM; ++i) {
+    for (int i = 0; i < P.nst; ++i) {
       mbar_init(FULL(i), 1);
-      mbar_init(EMPTY(i), kComputeWarps);
+      mbar_init(EMPTY(i), 3);  // the three warps of the owning pixel group
     }
     mbar_fence_init();
   }
@@ -119,35 +119,41 @@ __global__ void __launch_bounds__(kThreadsM, 1) wgrad_mma_kernel(const __grid_co
 #pragma unroll
     for (int q = 0; q < 4; ++q) bacc[mt][q] = 0.f;
 
-  const int tg = warp % 3, pg = warp / 3;  // kernel row kh, pixel-row quarter (compute warps only)
+  const int tg = warp % 3, pg = warp / 3;  // kernel row kh, pixel group
   const bool do_bias = P.a.dbias != nullptr && (SHIFT_A ? (blockIdx.y == 0 && tg == 1) : (tg == 0));
 
-  // TMA issue is folded into warp 0 (one elected lane): before computing tile i it requests tile i + kStagesM - 1,
-  // i.e. the stage every warp released after tile i - 1.  No dedicated producer warp: 12 warps = 3 per scheduler.
+  // Each pixel group (3 warps = the three kernel rows) owns every 4th tile of the CTA and its own slice of the
+  // stage ring (stages pg, pg+4, ...): a warp meets one barrier pair per WHOLE tile (8 k-steps), and the four groups
+  // work on four different tiles at once.  TMA issue is folded into the group's first warp (one elected lane):
+  // before computing its j-th tile it requests its (j + depth - 1)-th, i.e. the stage the group released last.
   const CUtensorMap* wide_map = SHIFT_A ? &P.x_map[wc.src] : &P.dy_map;
   const CUtensorMap* narrow_map = SHIFT_A ? &P.dy_map : &P.x_map[0];
   const uint32_t tx = SHIFT_A ? (P.x_bytes[wc.src] + P.dy_bytes) : (P.x_bytes[0] + P.dy_bytes);
   const int w_oct = wc.c0 >> 3;
-  uint32_t p_stage = 0, p_phase = 0;
-  int p_tile = blockIdx.x;
-  auto produce = [&]() {  // called by one elected lane of warp 0
+  const int depth = P.nst / kPixGroups;  // stages per group (>= 2)
+  uint32_t p_slot = 0, p_phase = 0;
+  int p_tile = blockIdx.x + pg * gridDim.x;
+  auto produce = [&]() {  // called by one elected lane of the group's first warp
     if (p_tile >= P.ntiles) return;
     const int n = p_tile / P.tiles_per_img;
     const int r = p_tile - n * P.tiles_per_img;
     const int ty = r / P.tiles_x;
     const int h0 = ty * 16, w0 = (r - ty * P.tiles_x) * 8;
-    mbar_wait(EMPTY(p_stage), p_phase ^ 1u);
-    mbar_expect_tx(FULL(p_stage), tx);
-    const uint32_t sb = cg_smem_u32(stages + p_stage * P.stage_bytes);
-    tma4m(sb, narrow_map, (w0 - 1) * 8, h0 - 1, 0, n, FULL(p_stage));
-    tma4m(sb + P.wide_off, wide_map, w0 * 8, h0, w_oct, n, FULL(p_stage));
-    if (++p_stage == kStagesM) { p_stage = 0; p_phase ^= 1u; }
-    p_tile += gridDim.x;
+    const int st = pg + kPixGroups * (int)p_slot;
+    mbar_wait(EMPTY(st), p_phase ^ 1u);
+    mbar_expect_tx(FULL(st), tx);
+    const uint32_t sb = cg_smem_u32(stages + st * P.stage_bytes);
+    tma4m(sb, narrow_map, (w0 - 1) * 8, h0 - 1, 0, n, FULL(st));
+    tma4m(sb + P.wide_off, wide_map, w0 * 8, h0, w_oct, n, FULL(st));
+    if (++p_slot == (uint32_t)depth) { p_slot = 0; p_phase ^= 1u; }
+    p_tile += kPixGroups * gridDim.x;
   };
-  if (warp == 0 && elect_one()) {
-    for (int i = 0; i < kStagesM - 1; ++i) produce();
+  if (tg == 0) {
+    if (elect_one()) {
+      for (int i = 0; i < depth - 1; ++i) produce();
+    }
+    __syncwarp();
   }
-  __syncwarp();
   {
     // ------------------------------------------------------------------ compute warps
     const int j = lane >> 3, i = lane & 7;  // ldmatrix: lane supplies row i of matrix j
@@ -164,22 +170,23 @@ __global__ void __launch_bounds__(kThreadsM, 1) wgrad_mma_kernel(const __grid_co
       a_off = (uint32_t)(P.wide_off + (j & 1) * kPlaneFlat + ((j >> 1) * 8 + i) * 16);
       b_off = (uint32_t)((j >> 1) * kPlaneHalo + (((j & 1) + tg) * 10 + i) * 16);
     }
-    uint32_t stage = 0, phase = 0;
+    uint32_t slot = 0, phase = 0;
     int tl_i = 0;
     (void)tl_i;
     if (threadIdx.x == 0) CG_TL(P.tl, 0);
-    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-      if (warp == 0) {
+    for (int tile = blockIdx.x + pg * gridDim.x; tile < P.ntiles; tile += kPixGroups * gridDim.x) {
+      if (tg == 0) {
         if (elect_one()) produce();
         __syncwarp();
       }
+      const int stage = pg + kPixGroups * (int)slot;
       if (lane == 0) mbar_wait(FULL(stage), phase);
       __syncwarp();
       if (threadIdx.x == 0 && tl_i < 8) CG_TL(P.tl, 2 + 2 * tl_i);
       const uint32_t sb = cg_smem_u32(stages + stage * P.stage_bytes);
 #pragma unroll 1
-      for (int ks = 0; ks < 8 / kPixGroups; ++ks) {
-        const int r0 = 2 * (pg * (8 / kPixGroups) + ks);  // first of the two tile rows of this k-step
+      for (int ks = 0; ks < 8; ++ks) {
+        const int r0 = 2 * ks;  // first of the two tile rows of this k-step
         if (SHIFT_A) {
           // X fragments of this k-step stay in registers while the three taps of kernel row tg sweep over dY:
           // dY position of tap (kh, kw) for tile pixel (r, c) is halo[(r + 2 - kh)][(c + 2 - kw)]
@@ -241,7 +248,7 @@ __global__ void __launch_bounds__(kThreadsM, 1) wgrad_mma_kernel(const __grid_co
       if (threadIdx.x == 0 && tl_i < 8) CG_TL(P.tl, 3 + 2 * tl_i);
       ++tl_i;
       if (lane == 0) mbar_arrive(EMPTY(stage));
-      if (++stage == kStagesM) { stage = 0; phase ^= 1u; }
+      if (++slot == (uint32_t)depth) { slot = 0; phase ^= 1u; }
     }
   }
 
@@ -430,7 +437,9 @@ int cg_wgrad_mma_try(const cg_wgrad_args* a, void* stream, int* handled) {
   kp.ntiles = a->N * kp.tiles_per_img;
   kp.wide_off = narrow_planes * kPlaneHalo;  // multiple of 128 (even plane count)
   kp.stage_bytes = (kp.wide_off + wide_planes * kPlaneFlat + 127) / 128 * 128;
-  const int smem_bytes = kHdrM + kStagesM * kp.stage_bytes;
+  kp.nst = (232448 - kHdrM) / kp.stage_bytes / 4 * 4;
+  if (kp.nst > kMaxStagesM) kp.nst = kMaxStagesM;
+  const int smem_bytes = kHdrM + kp.nst * kp.stage_bytes;
   // CTAs along the pixel axis share the chunk's gradient through coalesced atomics
   // one CTA per SM; each CTA ends with one flush of its whole accumulator tile: keep >= 4 tiles of work per CTA
   int gx = cg_device_sms() / kp.nchunks;
