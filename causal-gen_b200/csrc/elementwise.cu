@@ -117,7 +117,10 @@ __global__ void upsample_dbias_kernel(const bf16* __restrict__ dy, float* __rest
 }
 
 // ------------------------------------------------------------------ Philox4x32-10 -> N(0,1)
-__device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t idx) {
+// One call = four standard normals (two Box-Muller pairs).  Noise element (n, c, pixel) of a latent block is
+// output (c & 3) of counter  offset + 2 * ((n*HW + pixel)*2 + c/8) + ((c & 7) >> 2)  -- the same in every
+// kernel below, so backward passes regenerate exactly the forward noise without storing it.
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t idx, float* out) {
   uint32_t c0 = (uint32_t)idx, c1 = (uint32_t)(idx >> 32), c2 = 0x243F6A88u, c3 = 0x85A308D3u;
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
@@ -127,9 +130,23 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t idx) {
     c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
-  float u1 = ((float)c0 + 0.5f) * 2.3283064365386963e-10f;
-  float u2 = ((float)c1 + 0.5f) * 2.3283064365386963e-10f;
-  return sqrtf(-2.0f * __logf(u1)) * __cosf(6.283185307179586f * u2);
+  const float s = 2.3283064365386963e-10f;
+  const float r0 = sqrtf(-2.0f * __logf(((float)c0 + 0.5f) * s)), r1 = sqrtf(-2.0f * __logf(((float)c2 + 0.5f) * s));
+  float sn0, cs0, sn1, cs1;
+  __sincosf(6.283185307179586f * ((float)c1 + 0.5f) * s, &sn0, &cs0);
+  __sincosf(6.283185307179586f * ((float)c3 + 0.5f) * s, &sn1, &cs1);
+  out[0] = r0 * cs0; out[1] = r0 * sn0; out[2] = r1 * cs1; out[3] = r1 * sn1;
+}
+// eight normals of work item (pixel, channel octet): channels [8*oc, 8*oc + 8)
+__device__ __forceinline__ void philox_normal8(uint64_t seed, uint64_t offset, long long item, float* out) {
+  philox_normal4(seed, offset + 2ull * (uint64_t)item, out);
+  philox_normal4(seed, offset + 2ull * (uint64_t)item + 1ull, out + 4);
+}
+// single element (slow path: explicit-layout kernels that need one channel at a time)
+__device__ __forceinline__ float philox_normal_at(uint64_t seed, uint64_t offset, long long pix, int c) {
+  float v[4];
+  philox_normal4(seed, offset + 2ull * (uint64_t)(pix * 2 + (c >> 3)) + (uint64_t)((c & 7) >> 2), v);
+  return v[c & 3];
 }
 
 // ------------------------------------------------------------------ latent block forward
@@ -152,7 +169,7 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const cg_latent_args a)
       float v = 0.f;
       if (px < npx) {
         long long gi = ((long long)n * zd + c) * a.HW + hw0 + px;
-        v = a.eps != nullptr ? a.eps[gi] : philox_normal(seed, a.offset + (uint64_t)gi);
+        v = a.eps != nullptr ? a.eps[gi] : philox_normal_at(seed, a.offset, (long long)n * a.HW + hw0 + px, c);
         if (a.eps_out != nullptr) a.eps_out[gi] = v;
       }
       s_eps[c][px] = v;
@@ -220,7 +237,7 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const cg_latent_bwd_arg
       float v = 0.f;
       if (px < npx) {
         long long gi = ((long long)n * zd + c) * a.HW + hw0 + px;
-        v = a.eps != nullptr ? a.eps[gi] : philox_normal(seed, a.offset + (uint64_t)gi);
+        v = a.eps != nullptr ? a.eps[gi] : philox_normal_at(seed, a.offset, (long long)n * a.HW + hw0 + px, c);
       }
       s_eps[c][px] = v;
     }
@@ -266,6 +283,111 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const cg_latent_bwd_arg
     *reinterpret_cast<uint4*>(p0 + (long long)oc * a.HW * 8) = cg_pack8(g_ploc);
     *reinterpret_cast<uint4*>(p0 + (long long)(2 + oc) * a.HW * 8) = cg_pack8(g_pls);
   }
+}
+
+// ------------------------------------------------------------------ streaming variants (in-kernel noise)
+// Training / sampling with Philox noise needs no NCHW staging: one thread = (pixel, channel octet), 128-bit loads of
+// the fp32 statistics rows, noise generated in registers, one 16-byte bf16 store, block-reduced KL.
+__global__ void __launch_bounds__(256) latent_fwd_stream_kernel(const cg_latent_args a) {
+  __shared__ float s_red[8];
+  const int n = blockIdx.y;
+  const long long item = (long long)blockIdx.x * 256 + threadIdx.x;  // (pixel, octet) inside the sample
+  const bool live = item < 2ll * a.HW;
+  float kl_acc = 0.f;
+  if (live) {
+    const long long hw = item >> 1;
+    const int oc = (int)(item & 1);
+    const long long pix = (long long)n * a.HW + hw;
+    const uint64_t seed = a.seed + (a.seed_dev != nullptr ? *a.seed_dev : 0ull);
+    float pl[8], ps[8], zv[8], e[8];
+    const float4* pp = reinterpret_cast<const float4*>(a.p + pix * a.p_ld + oc * 8);
+    const float4* pq = reinterpret_cast<const float4*>(a.p + pix * a.p_ld + 16 + oc * 8);
+    *reinterpret_cast<float4*>(pl) = pp[0]; *reinterpret_cast<float4*>(pl + 4) = pp[1];
+    *reinterpret_cast<float4*>(ps) = pq[0]; *reinterpret_cast<float4*>(ps + 4) = pq[1];
+    if (a.mode != 2) philox_normal8(seed, a.offset, pix * 2 + oc, e);
+    if (a.mode == 0) {
+      float ql[8], qs[8];
+      const float4* qp = reinterpret_cast<const float4*>(a.q + pix * a.q_ld + oc * 8);
+      const float4* qq = reinterpret_cast<const float4*>(a.q + pix * a.q_ld + 16 + oc * 8);
+      *reinterpret_cast<float4*>(ql) = qp[0]; *reinterpret_cast<float4*>(ql + 4) = qp[1];
+      *reinterpret_cast<float4*>(qs) = qq[0]; *reinterpret_cast<float4*>(qs + 4) = qq[1];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float q_ls = qs[k] + a.log_t, p_ls = ps[k] + a.log_t;
+        const float eq = __expf(q_ls), ep = __expf(p_ls), dm = ql[k] - pl[k];
+        zv[k] = ql[k] + eq * e[k];
+        kl_acc += -0.5f + p_ls - q_ls + 0.5f * (eq * eq + dm * dm) / (ep * ep);  // src/vae.py:14-25
+      }
+    } else if (a.mode == 1) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) zv[k] = pl[k] + __expf(ps[k] + a.log_t) * e[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) zv[k] = pl[k];
+    }
+    bf16* zb = reinterpret_cast<bf16*>(a.z_bf16);
+    *reinterpret_cast<uint4*>(zb + n * a.z_ns + ((long long)oc * a.HW + hw) * 8) = cg_pack8(zv);
+    if (a.eps_out != nullptr && a.mode != 2) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a.eps_out[((long long)n * 16 + oc * 8 + k) * a.HW + hw] = e[k];
+    }
+  }
+  if (a.kl_out != nullptr && a.mode == 0) {
+    kl_acc = cg_warp_sum(kl_acc);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = kl_acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int i = 0; i < 8; ++i) s += s_red[i];
+      atomicAdd(a.kl_out + n, s);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) latent_bwd_stream_kernel(const cg_latent_bwd_args a) {
+  const int n = blockIdx.y;
+  const long long item = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (item >= 2ll * a.HW) return;
+  const long long hw = item >> 1;
+  const int oc = (int)(item & 1);
+  const long long pix = (long long)n * a.HW + hw;
+  const uint64_t seed = a.seed + (a.seed_dev != nullptr ? *a.seed_dev : 0ull);
+  float pl[8], ps[8], e[8], dz[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const float4* pp = reinterpret_cast<const float4*>(a.p + pix * a.p_ld + oc * 8);
+  const float4* pq = reinterpret_cast<const float4*>(a.p + pix * a.p_ld + 16 + oc * 8);
+  *reinterpret_cast<float4*>(pl) = pp[0]; *reinterpret_cast<float4*>(pl + 4) = pp[1];
+  *reinterpret_cast<float4*>(ps) = pq[0]; *reinterpret_cast<float4*>(ps + 4) = pq[1];
+  if (a.dz != nullptr)
+    cg_unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.dz) + n * a.dz_ns + ((long long)oc * a.HW + hw) * 8), dz);
+  if (a.mode != 2) philox_normal8(seed, a.offset, pix * 2 + oc, e);
+  float g_ploc[8], g_pls[8];
+  if (a.mode == 0) {
+    float ql[8], qs[8], g_qloc[8], g_qls[8];
+    const float4* qp = reinterpret_cast<const float4*>(a.q + pix * a.q_ld + oc * 8);
+    const float4* qq = reinterpret_cast<const float4*>(a.q + pix * a.q_ld + 16 + oc * 8);
+    *reinterpret_cast<float4*>(ql) = qp[0]; *reinterpret_cast<float4*>(ql + 4) = qp[1];
+    *reinterpret_cast<float4*>(qs) = qq[0]; *reinterpret_cast<float4*>(qs + 4) = qq[1];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float eq = __expf(qs[k]), ivp = __expf(-2.0f * ps[k]), dm = ql[k] - pl[k];
+      g_qloc[k] = a.g_kl * dm * ivp + dz[k];
+      g_qls[k] = a.g_kl * (eq * eq * ivp - 1.0f) + dz[k] * eq * e[k];
+      g_ploc[k] = -a.g_kl * dm * ivp;
+      g_pls[k] = a.g_kl * (1.0f - (eq * eq + dm * dm) * ivp);
+    }
+    bf16* q0 = reinterpret_cast<bf16*>(a.dq) + n * a.dq_ns + hw * 8;
+    *reinterpret_cast<uint4*>(q0 + (long long)oc * a.HW * 8) = cg_pack8(g_qloc);
+    *reinterpret_cast<uint4*>(q0 + (long long)(2 + oc) * a.HW * 8) = cg_pack8(g_qls);
+  } else if (a.mode == 1) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { g_ploc[k] = dz[k]; g_pls[k] = dz[k] * __expf(ps[k]) * e[k]; }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { g_ploc[k] = dz[k]; g_pls[k] = 0.f; }
+  }
+  bf16* p0 = reinterpret_cast<bf16*>(a.dp) + n * a.dp_ns + hw * 8;
+  *reinterpret_cast<uint4*>(p0 + (long long)oc * a.HW * 8) = cg_pack8(g_ploc);
+  *reinterpret_cast<uint4*>(p0 + (long long)(2 + oc) * a.HW * 8) = cg_pack8(g_pls);
 }
 
 __global__ void latent_mix_kernel(const float* __restrict__ z, const float* __restrict__ q_loc,
@@ -364,6 +486,14 @@ extern "C" int cg_latent_fwd(const cg_latent_args* a, void* stream) {
   CG_ARCH_GUARD();
   CG_REQUIRE(a != nullptr && a->zdim == 16, "cg_latent_fwd: zdim must be 16");
   CG_REQUIRE(a->p != nullptr && a->z_bf16 != nullptr && (a->mode != 0 || a->q != nullptr), "cg_latent_fwd: null operand");
+  const bool rows16 = (((uintptr_t)a->p & 15) == 0) && a->p_ld % 4 == 0 &&
+                      (a->q == nullptr || ((((uintptr_t)a->q & 15) == 0) && a->q_ld % 4 == 0));
+  if (a->eps == nullptr && a->z_f32 == nullptr && rows16) {  // in-kernel noise: streaming kernel, no layout staging
+    dim3 g2(cg_ceil_div(2ll * a->HW, 256), a->N);
+    latent_fwd_stream_kernel<<<g2, 256, 0, cg_stream(stream)>>>(*a);
+    CG_LAUNCH_CHECK("cg_latent_fwd");
+    return CG_OK;
+  }
   dim3 grid(cg_ceil_div(a->HW, kLatPix), a->N);
   latent_fwd_kernel<<<grid, 256, 0, cg_stream(stream)>>>(*a);
   CG_LAUNCH_CHECK("cg_latent_fwd");
@@ -375,6 +505,14 @@ extern "C" int cg_latent_bwd(const cg_latent_bwd_args* a, void* stream) {
   CG_REQUIRE(a != nullptr && a->zdim == 16, "cg_latent_bwd: zdim must be 16");
   CG_REQUIRE(a->p != nullptr && a->dp != nullptr && (a->mode != 0 || (a->q != nullptr && a->dq != nullptr)),
              "cg_latent_bwd: null operand");
+  const bool rows16 = (((uintptr_t)a->p & 15) == 0) && a->p_ld % 4 == 0 &&
+                      (a->q == nullptr || ((((uintptr_t)a->q & 15) == 0) && a->q_ld % 4 == 0));
+  if (a->eps == nullptr && rows16) {
+    dim3 g2(cg_ceil_div(2ll * a->HW, 256), a->N);
+    latent_bwd_stream_kernel<<<g2, 256, 0, cg_stream(stream)>>>(*a);
+    CG_LAUNCH_CHECK("cg_latent_bwd");
+    return CG_OK;
+  }
   dim3 grid(cg_ceil_div(a->HW, kLatPix), a->N);
   latent_bwd_kernel<<<grid, 256, 0, cg_stream(stream)>>>(*a);
   CG_LAUNCH_CHECK("cg_latent_bwd");

@@ -48,30 +48,46 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__
   }
 }
 
-// dW[co][ci][tap] += sum_pixels dy[p][co] * x[p+tap][ci];  db[co] += sum dy.  Persistent blocks walk
-// tiles and keep their partial sums in registers, one atomicAdd per output per block at the end.
+// dW[co][ci][kh][kw] += sum_pixels dy[p][co] * x[p + (kh-3, kw-3)][ci];  db[co] += sum_pixels dy[p][co].
+// Persistent blocks walk 16x16 pixel tiles.  A thread owns a register block of 2 output channels x 4
+// consecutive kw taps of one (ci, kh) row and slides a 4-wide window of x along the pixel row, so every pixel
+// costs one 8-byte dy load + one x load for 8 FMAs.  Partial sums stay in registers over all tiles of the block;
+// one atomicAdd per output per block at the end.
+constexpr int kDyPitch = 36;  // floats per pixel row of the dy tile in shared memory (16-byte aligned, conflict-free)
+
 template <int CIN>
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dy,
                                                          float* __restrict__ dw, float* __restrict__ db, int N, int R,
                                                          int Cout, long long dy_ns) {
-  __shared__ float s_dy[kT * kT][kMaxCout + 1];
+  __shared__ __align__(16) float s_dy[kT * kT * kDyPitch];
   __shared__ float s_x[CIN * kHalo * kHalo];
-  const int nout = Cout * (CIN * 49 + 1);  // + bias column
-  constexpr int kPerThread = (kMaxCout * (CIN * 49 + 1) + 255) / 256;
-  float acc[kPerThread];
+  constexpr int kTapBlocks = CIN * 7 * 2;               // (ci, kh, kw half) blocks of 4 kw taps (kw = 7 is padding)
+  constexpr int kTasks = (16 * kTapBlocks + 255) / 256;  // (co pair, tap block) tasks per thread
+  const int ntask = (Cout / 2) * kTapBlocks;
+  float acc[kTasks][2][4];
 #pragma unroll
-  for (int j = 0; j < kPerThread; ++j) acc[j] = 0.f;
+  for (int t = 0; t < kTasks; ++t)
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[t][i][j] = 0.f;
+  float bsum = 0.f;  // warp 7: lane = output channel
   const int tiles_1d = (R + kT - 1) / kT;
   const int ntiles = N * tiles_1d * tiles_1d;
+  const int C8 = Cout / 8;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int n = tile / (tiles_1d * tiles_1d), tr = tile % (tiles_1d * tiles_1d);
     const int h0 = (tr / tiles_1d) * kT, w0 = (tr % tiles_1d) * kT;
     __syncthreads();
-    for (int i = threadIdx.x; i < kT * kT * Cout; i += 256) {
-      int co = i % Cout, p = i / Cout, hh = h0 + p / kT, ww = w0 + p % kT;
-      s_dy[p][co] = (hh < R && ww < R)
-                        ? __bfloat162float(dy[n * dy_ns + ((long long)(co >> 3) * R * R + (long long)hh * R + ww) * 8 + (co & 7)])
-                        : 0.f;
+    for (int i = threadIdx.x; i < kT * kT * C8; i += 256) {  // one 16-byte octet (8 channels of a pixel) per load
+      const int p = i % (kT * kT), c8 = i / (kT * kT);
+      const int hh = h0 + p / kT, ww = w0 + p % kT;
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (hh < R && ww < R)
+        cg_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + n * dy_ns + ((long long)c8 * R * R + (long long)hh * R + ww) * 8)), f);
+      float4* d = reinterpret_cast<float4*>(s_dy + p * kDyPitch + c8 * 8);
+      d[0] = make_float4(f[0], f[1], f[2], f[3]);
+      d[1] = make_float4(f[4], f[5], f[6], f[7]);
     }
     for (int i = threadIdx.x; i < CIN * kHalo * kHalo; i += 256) {
       int cc = i % kHalo, rr = (i / kHalo) % kHalo, ci = i / (kHalo * kHalo);
@@ -80,34 +96,47 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < kPerThread; ++j) {
-      const int o = threadIdx.x + 256 * j;
-      if (o >= nout) break;
-      const int co = o % Cout, r = o / Cout;  // r in [0, CIN*49] ; last = bias
-      float a = 0.f;
-      if (r == CIN * 49) {
-        for (int p = 0; p < kT * kT; ++p) a += s_dy[p][co];
-      } else {
-        const int ci = r / 49, tap = r % 49, kh = tap / 7, kw = tap % 7;
-        const float* xs = s_x + (ci * kHalo + kh) * kHalo + kw;
-        for (int py = 0; py < kT; ++py)
+    for (int t = 0; t < kTasks; ++t) {
+      const int task = threadIdx.x + 256 * t;
+      if (task >= ntask) break;
+      const int co = (task % (Cout / 2)) * 2, tb = task / (Cout / 2);
+      const int kw0 = (tb & 1) * 4, kh = (tb >> 1) % 7, ci = tb / 14;
+      // kw0 + 3 = 7 reads one column past the 7-tap window (still inside the 22-wide halo row); its sum is dropped
+      const float* xrow = s_x + (ci * kHalo + kh) * kHalo + kw0;
+      const float* dyp = s_dy + co;
+      for (int py = 0; py < kT; ++py) {
+        const float* xr = xrow + py * kHalo;
+        float w0v = xr[0], w1v = xr[1], w2v = xr[2], w3v = xr[3];
 #pragma unroll
-          for (int px = 0; px < kT; ++px) a += s_dy[py * kT + px][co] * xs[py * kHalo + px];
+        for (int px = 0; px < kT; ++px) {
+          const float2 d = *reinterpret_cast<const float2*>(dyp + (py * kT + px) * kDyPitch);
+          acc[t][0][0] += d.x * w0v; acc[t][0][1] += d.x * w1v; acc[t][0][2] += d.x * w2v; acc[t][0][3] += d.x * w3v;
+          acc[t][1][0] += d.y * w0v; acc[t][1][1] += d.y * w1v; acc[t][1][2] += d.y * w2v; acc[t][1][3] += d.y * w3v;
+          w0v = w1v; w1v = w2v; w2v = w3v;
+          if (px + 1 < kT) w3v = (kw0 + px + 4 < kHalo) ? xr[px + 4] : 0.f;
+        }
       }
-      acc[j] += a;
+    }
+    if (threadIdx.x >= 224 && (int)threadIdx.x - 224 < Cout) {
+      const int co = threadIdx.x - 224;
+      float a = 0.f;
+      for (int p = 0; p < kT * kT; ++p) a += s_dy[p * kDyPitch + co];
+      bsum += a;
     }
   }
 #pragma unroll
-  for (int j = 0; j < kPerThread; ++j) {
-    const int o = threadIdx.x + 256 * j;
-    if (o >= nout) break;
-    const int co = o % Cout, r = o / Cout;
-    if (r == CIN * 49) {
-      if (db != nullptr) atomicAdd(db + co, acc[j]);
-    } else {
-      atomicAdd(dw + (co * CIN + r / 49) * 49 + r % 49, acc[j]);
-    }
+  for (int t = 0; t < kTasks; ++t) {
+    const int task = threadIdx.x + 256 * t;
+    if (task >= ntask) break;
+    const int co = (task % (Cout / 2)) * 2, tb = task / (Cout / 2);
+    const int kw0 = (tb & 1) * 4, kh = (tb >> 1) % 7, ci = tb / 14;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (kw0 + j < 7) atomicAdd(dw + ((co + i) * CIN + ci) * 49 + kh * 7 + kw0 + j, acc[t][i][j]);
   }
+  if (db != nullptr && threadIdx.x >= 224 && (int)threadIdx.x - 224 < Cout) atomicAdd(db + threadIdx.x - 224, bsum);
 }
 
 }  // namespace
@@ -130,10 +159,10 @@ extern "C" int cg_stem_fwd(const float* x, const float* w, const float* b, void*
 extern "C" int cg_stem_wgrad(const float* x, const void* dy, float* dw, float* db, int32_t N, int32_t Cin, int32_t R,
                              int32_t Cout, int64_t dy_ld, void* stream) {
   CG_ARCH_GUARD();
-  CG_REQUIRE((Cin == 1 || Cin == 3) && Cout <= kMaxCout, "cg_stem_wgrad: Cin=%d Cout=%d", Cin, Cout);
+  CG_REQUIRE((Cin == 1 || Cin == 3) && Cout <= kMaxCout && Cout % 8 == 0, "cg_stem_wgrad: Cin=%d Cout=%d", Cin, Cout);
   const int t1 = cg_ceil_div(R, kT);
   int blocks = N * t1 * t1;
-  const int cap = 2 * cg_device_sms();
+  const int cap = 4 * cg_device_sms();
   if (blocks > cap) blocks = cap;
   if (Cin == 1)
     stem_wgrad_kernel<1><<<blocks, 256, 0, cg_stream(stream)>>>(x, reinterpret_cast<const bf16*>(dy), dw, db, N, R, Cout,

@@ -395,6 +395,63 @@ def test_latent_forward_backward():
     assert_close(to_nchw(dp, 32), pr.grad.view(N, H, H, 32).permute(0, 3, 1, 2), 1e-2, "dp")
 
 
+def test_latent_philox_stream_kernels_regenerate_forward_noise():
+    """in-kernel Philox mode: the streaming forward kernel, the layout-staging forward kernel and both backward
+    kernels must agree on the noise of every (sample, channel, pixel) -- backward never stores eps"""
+    import ctypes as C
+    from causalgen_b200 import _lib as L
+    lib = L.load()
+    N, H, zd = 3, 20, 16
+    HW = H * H
+    q = rnd(N, HW, 32, seed=11, scale=0.7).contiguous()
+    p = rnd(N, HW, 32, seed=12, scale=0.7).contiguous()
+
+    def fwd(with_f32):
+        z16 = torch.zeros(N, 2, H, H, 8, device=DEV, dtype=torch.bfloat16)
+        z32 = torch.zeros(N, zd, H, H, device=DEV)
+        eo = torch.zeros(N, zd, H, H, device=DEV)
+        kl = torch.zeros(N, device=DEV)
+        a = L.LatentArgs()
+        a.q, a.p, a.q_ld, a.p_ld = q.data_ptr(), p.data_ptr(), 32, 32
+        a.seed, a.offset = 0x1234567, 5 << 40
+        a.z_bf16, a.z_ns, a.kl_out, a.eps_out = z16.data_ptr(), ns_of(z16), kl.data_ptr(), eo.data_ptr()
+        if with_f32:
+            a.z_f32 = z32.data_ptr()
+        a.N, a.HW, a.zdim, a.mode = N, HW, zd, 0
+        L.check(lib.cg_latent_fwd(C.byref(a), stream()))
+        torch.cuda.synchronize()
+        return z16, eo, kl
+
+    z_s, e_s, kl_s = fwd(False)   # streaming kernel
+    z_l, e_l, kl_l = fwd(True)    # layout-staging kernel (abduct-style output)
+    assert_close(e_s, e_l, 1e-6, "the two forward kernels must draw identical noise")
+    assert abs(e_s.mean().item()) < 0.05 and abs(e_s.std().item() - 1.0) < 0.05
+    qn = q.view(N, H, H, 32).permute(0, 3, 1, 2)
+    assert_close(to_nchw(z_s, 16), qn[:, :16] + qn[:, 16:].exp() * e_s, 1e-2, "z from streamed noise")
+    assert_close(kl_s, kl_l, 1e-5, "kl")
+    dz = nhwc_bf16(rnd(N, 16, H, H, seed=14))
+
+    def bwd(eps):
+        dq = torch.zeros(N, 4, H, H, 8, device=DEV, dtype=torch.bfloat16)
+        dp = torch.zeros(N, 6, H, H, 8, device=DEV, dtype=torch.bfloat16)
+        b = L.LatentBwdArgs()
+        b.q, b.p, b.q_ld, b.p_ld = q.data_ptr(), p.data_ptr(), 32, 32
+        b.seed, b.offset = 0x1234567, 5 << 40
+        if eps is not None:
+            b.eps = eps.data_ptr()
+        b.dz, b.dz_ns, b.g_kl = dz.data_ptr(), ns_of(dz), 0.37
+        b.dq, b.dq_ns, b.dp, b.dp_ns = dq.data_ptr(), ns_of(dq), dp.data_ptr(), ns_of(dp)
+        b.N, b.HW, b.zdim, b.mode = N, HW, zd, 0
+        L.check(lib.cg_latent_bwd(C.byref(b), stream()))
+        torch.cuda.synchronize()
+        return dq, dp
+
+    dq_s, dp_s = bwd(None)     # regenerates the noise
+    dq_e, dp_e = bwd(e_s)      # explicit noise of the forward pass
+    assert_close(to_nchw(dq_s, 32), to_nchw(dq_e, 32), 1e-3, "dq with regenerated noise")
+    assert_close(to_nchw(dp_s, 32), to_nchw(dp_e, 32), 1e-3, "dp with regenerated noise")
+
+
 @pytest.mark.parametrize("Cc,Cw", [(1, 32), (3, 16)])
 def test_dgauss_forward_backward_sample(Cc, Cw):
     import ctypes as C
