@@ -6,114 +6,107 @@ namespace {
 // All bf16 tensors here are channel-octet planar (N, C/8, H, W, 8): one thread handles one 16-byte octet of one
 // pixel, consecutive threads walk consecutive pixels of a plane -> fully coalesced.
 // ------------------------------------------------------------------ avg-pool / nearest upsample
+// grid = (pixels of a plane / 256, channel octets, samples): no 64-bit index arithmetic per element
 __global__ void avgpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C8, int d,
                                    long long x_ns, long long y_ns, int Po) {
   const int Ho = H / d, Wo = W / d;
-  const long long total = (long long)N * C8 * Po * Po;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int wo = (int)(i % Po), ho = (int)((i / Po) % Po);
-    const int c8 = (int)((i / ((long long)Po * Po)) % C8), n = (int)(i / ((long long)Po * Po * C8));
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (ho < Ho && wo < Wo) {
-      const bf16* xp = x + n * x_ns + (long long)c8 * H * W * 8;
-      for (int a = 0; a < d; ++a)
-        for (int b = 0; b < d; ++b) {
-          float f[8];
-          cg_unpack8(__ldg(reinterpret_cast<const uint4*>(xp + ((long long)(ho * d + a) * W + wo * d + b) * 8)), f);
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Po * Po) return;
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  const int ho = p / Po, wo = p - ho * Po;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (ho < Ho && wo < Wo) {
+    const bf16* xp = x + n * x_ns + (long long)c8 * H * W * 8;
+    for (int a = 0; a < d; ++a)
+      for (int b = 0; b < d; ++b) {
+        float f[8];
+        cg_unpack8(__ldg(reinterpret_cast<const uint4*>(xp + ((ho * d + a) * W + wo * d + b) * 8)), f);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] += f[k];
-        }
-      const float inv = 1.0f / (d * d);
+        for (int k = 0; k < 8; ++k) acc[k] += f[k];
+      }
+    const float inv = 1.0f / (d * d);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] *= inv;
-    }
-    *reinterpret_cast<uint4*>(y + n * y_ns + ((long long)c8 * Po * Po + (long long)ho * Po + wo) * 8) = cg_pack8(acc);
+    for (int k = 0; k < 8; ++k) acc[k] *= inv;
   }
+  *reinterpret_cast<uint4*>(y + n * y_ns + ((long long)c8 * Po * Po + p) * 8) = cg_pack8(acc);
 }
 
 __global__ void avgpool_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int N, int H, int W, int C8,
                                    int d, long long dy_ns, long long dx_ns, int Po, int accumulate) {
-  const long long total = (long long)N * C8 * H * W;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= H * W) return;
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  const int h = p / W, w = p - h * W;
   const float inv = 1.0f / (d * d);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int w = (int)(i % W), h = (int)((i / W) % H);
-    const int c8 = (int)((i / ((long long)W * H)) % C8), n = (int)(i / ((long long)W * H * C8));
-    float f[8];
-    cg_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + n * dy_ns +
-                                                    ((long long)c8 * Po * Po + (long long)(h / d) * Po + w / d) * 8)), f);
-    bf16* o = dx + n * dx_ns + ((long long)c8 * H * W + (long long)h * W + w) * 8;
-    float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (accumulate) cg_unpack8(*reinterpret_cast<const uint4*>(o), g);
+  float f[8];
+  cg_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + n * dy_ns + ((long long)c8 * Po * Po + (h / d) * Po + w / d) * 8)), f);
+  bf16* o = dx + n * dx_ns + ((long long)c8 * H * W + p) * 8;
+  float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (accumulate) cg_unpack8(*reinterpret_cast<const uint4*>(o), g);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) g[k] += f[k] * inv;
-    *reinterpret_cast<uint4*>(o) = cg_pack8(g);
-  }
+  for (int k = 0; k < 8; ++k) g[k] += f[k] * inv;
+  *reinterpret_cast<uint4*>(o) = cg_pack8(g);
 }
 
 __global__ void upsample_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ bias, bf16* __restrict__ y,
                                     int N, int Hi, int Ho, int C, long long x_ns, long long y_ns) {
-  const int C8 = (C + 7) / 8;
-  const long long total = (long long)N * C8 * Ho * Ho;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int w = (int)(i % Ho), h = (int)((i / Ho) % Ho);
-    const int c8 = (int)((i / ((long long)Ho * Ho)) % C8), n = (int)(i / ((long long)Ho * Ho * C8));
-    const int hs = (h * Hi) / Ho, ws = (w * Hi) / Ho;
-    float f[8];
-    cg_unpack8(__ldg(reinterpret_cast<const uint4*>(x + n * x_ns + ((long long)c8 * Hi * Hi + (long long)hs * Hi + ws) * 8)), f);
-    if (bias != nullptr) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Ho * Ho) return;
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  const int h = p / Ho, w = p - h * Ho;
+  const int hs = (h * Hi) / Ho, ws = (w * Hi) / Ho;
+  float f[8];
+  cg_unpack8(__ldg(reinterpret_cast<const uint4*>(x + n * x_ns + ((long long)c8 * Hi * Hi + hs * Hi + ws) * 8)), f);
+  if (bias != nullptr) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int c = c8 * 8 + k;
-        if (c < C) f[k] += __ldg(bias + ((long long)c * Ho + h) * Ho + w);
-      }
+    for (int k = 0; k < 8; ++k) {
+      const int c = c8 * 8 + k;
+      if (c < C) f[k] += __ldg(bias + (long long)c * Ho * Ho + p);
     }
-    *reinterpret_cast<uint4*>(y + n * y_ns + ((long long)c8 * Ho * Ho + (long long)h * Ho + w) * 8) = cg_pack8(f);
   }
+  *reinterpret_cast<uint4*>(y + n * y_ns + ((long long)c8 * Ho * Ho + p) * 8) = cg_pack8(f);
 }
 
 __global__ void upsample_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int N, int Hi, int Ho, int C8,
                                     long long dy_ns, long long dx_ns, int accumulate) {
-  const long long total = (long long)N * C8 * Hi * Hi;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int w = (int)(i % Hi), h = (int)((i / Hi) % Hi);
-    const int c8 = (int)((i / ((long long)Hi * Hi)) % C8), n = (int)(i / ((long long)Hi * Hi * C8));
-    // destination rows/cols whose nearest source is (h, w): floor(ho*Hi/Ho) == h
-    const int h0 = (h * Ho + Hi - 1) / Hi, h1 = ((h + 1) * Ho + Hi - 1) / Hi;
-    const int w0 = (w * Ho + Hi - 1) / Hi, w1 = ((w + 1) * Ho + Hi - 1) / Hi;
-    float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    bf16* o = dx + n * dx_ns + ((long long)c8 * Hi * Hi + (long long)h * Hi + w) * 8;
-    if (accumulate) cg_unpack8(*reinterpret_cast<const uint4*>(o), g);
-    const bf16* dp = dy + n * dy_ns + (long long)c8 * Ho * Ho * 8;
-    for (int a = h0; a < h1; ++a)
-      for (int b = w0; b < w1; ++b) {
-        float f[8];
-        cg_unpack8(__ldg(reinterpret_cast<const uint4*>(dp + ((long long)a * Ho + b) * 8)), f);
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Hi * Hi) return;
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  const int h = p / Hi, w = p - h * Hi;
+  // destination rows/cols whose nearest source is (h, w): floor(ho*Hi/Ho) == h
+  const int h0 = (h * Ho + Hi - 1) / Hi, h1 = ((h + 1) * Ho + Hi - 1) / Hi;
+  const int w0 = (w * Ho + Hi - 1) / Hi, w1 = ((w + 1) * Ho + Hi - 1) / Hi;
+  float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bf16* o = dx + n * dx_ns + ((long long)c8 * Hi * Hi + p) * 8;
+  if (accumulate) cg_unpack8(*reinterpret_cast<const uint4*>(o), g);
+  const bf16* dp = dy + n * dy_ns + (long long)c8 * Ho * Ho * 8;
+  for (int a = h0; a < h1; ++a)
+    for (int b = w0; b < w1; ++b) {
+      float f[8];
+      cg_unpack8(__ldg(reinterpret_cast<const uint4*>(dp + (a * Ho + b) * 8)), f);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) g[k] += f[k];
-      }
-    *reinterpret_cast<uint4*>(o) = cg_pack8(g);
-  }
+      for (int k = 0; k < 8; ++k) g[k] += f[k];
+    }
+  *reinterpret_cast<uint4*>(o) = cg_pack8(g);
 }
 
-// dbias[c,h,w] += sum_n dy[n,c,h,w]
+// dbias[c,h,w] += sum_n dy[n,c,h,w]; blockIdx.z = chunk of 16 samples, partial sums meet through atomics
 __global__ void upsample_dbias_kernel(const bf16* __restrict__ dy, float* __restrict__ dbias, int N, int Ho, int C,
                                       long long dy_ns) {
-  const int C8 = (C + 7) / 8;
-  const long long total = (long long)C8 * Ho * Ho;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long p = i % ((long long)Ho * Ho);
-    const int c8 = (int)(i / ((long long)Ho * Ho));
-    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int n = 0; n < N; ++n) {
-      float f[8];
-      cg_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + n * dy_ns + ((long long)c8 * Ho * Ho + p) * 8)), f);
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Ho * Ho) return;
+  const int c8 = blockIdx.y;
+  const int n0 = blockIdx.z * 16, n1 = min(N, n0 + 16);
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int n = n0; n < n1; ++n) {
+    float f[8];
+    cg_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + n * dy_ns + ((long long)c8 * Ho * Ho + p) * 8)), f);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) s[k] += f[k];
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (c8 * 8 + k < C) dbias[(long long)(c8 * 8 + k) * Ho * Ho + p] += s[k];
+    for (int k = 0; k < 8; ++k) s[k] += f[k];
   }
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (c8 * 8 + k < C) atomicAdd(dbias + (long long)(c8 * 8 + k) * Ho * Ho + p, s[k]);
 }
 
 // ------------------------------------------------------------------ Philox4x32-10 -> N(0,1)
@@ -437,7 +430,7 @@ extern "C" int cg_avgpool_fwd(const void* x, void* y, int32_t N, int32_t H, int3
   CG_REQUIRE(C % 8 == 0 && x_ld % 8 == 0 && y_ld % 8 == 0, "cg_avgpool_fwd: C/ld multiples of 8");
   const int Po = pad_to > 0 ? pad_to : H / d;
   CG_REQUIRE(Po >= H / d, "cg_avgpool_fwd: pad_to %d < %d", Po, H / d);
-  avgpool_fwd_kernel<<<grid_for((long long)N * Po * Po * (C / 8), 256), 256, 0, cg_stream(stream)>>>(
+  avgpool_fwd_kernel<<<dim3(cg_ceil_div(Po * Po, 256), C / 8, N), 256, 0, cg_stream(stream)>>>(
       reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), N, H, W, C / 8, d, x_ld, y_ld, Po);
   CG_LAUNCH_CHECK("cg_avgpool_fwd");
   return CG_OK;
@@ -449,7 +442,7 @@ extern "C" int cg_avgpool_bwd(const void* dy, void* dx, int32_t N, int32_t H, in
   CG_REQUIRE(d >= 1 && H % d == 0 && W % d == 0 && H == W, "cg_avgpool_bwd: H=%d W=%d d=%d", H, W, d);
   CG_REQUIRE(C % 8 == 0 && dy_ld % 8 == 0 && dx_ld % 8 == 0, "cg_avgpool_bwd: C/ld multiples of 8");
   const int Po = pad_to > 0 ? pad_to : H / d;
-  avgpool_bwd_kernel<<<grid_for((long long)N * H * W * (C / 8), 256), 256, 0, cg_stream(stream)>>>(
+  avgpool_bwd_kernel<<<dim3(cg_ceil_div(H * W, 256), C / 8, N), 256, 0, cg_stream(stream)>>>(
       reinterpret_cast<const bf16*>(dy), reinterpret_cast<bf16*>(dx), N, H, W, C / 8, d, dy_ld, dx_ld, Po, accumulate);
   CG_LAUNCH_CHECK("cg_avgpool_bwd");
   return CG_OK;
@@ -459,7 +452,7 @@ extern "C" int cg_upsample_fwd(const void* x, const float* bias, void* y, int32_
                                int64_t x_ld, int64_t y_ld, void* stream) {
   CG_ARCH_GUARD();
   CG_REQUIRE(Ho >= Hi && x_ld % 8 == 0 && y_ld % 8 == 0, "cg_upsample_fwd: Hi=%d Ho=%d", Hi, Ho);
-  upsample_fwd_kernel<<<grid_for((long long)N * Ho * Ho * ((C + 7) / 8), 256), 256, 0, cg_stream(stream)>>>(
+  upsample_fwd_kernel<<<dim3(cg_ceil_div(Ho * Ho, 256), (C + 7) / 8, N), 256, 0, cg_stream(stream)>>>(
       reinterpret_cast<const bf16*>(x), bias, reinterpret_cast<bf16*>(y), N, Hi, Ho, C, x_ld, y_ld);
   CG_LAUNCH_CHECK("cg_upsample_fwd");
   return CG_OK;
@@ -470,12 +463,12 @@ extern "C" int cg_upsample_bwd(const void* dy, void* dx, float* dbias, int32_t N
   CG_ARCH_GUARD();
   CG_REQUIRE(Ho >= Hi && dy_ld % 8 == 0 && dx_ld % 8 == 0, "cg_upsample_bwd: Hi=%d Ho=%d", Hi, Ho);
   if (dx != nullptr) {
-    upsample_bwd_kernel<<<grid_for((long long)N * Hi * Hi * ((C + 7) / 8), 256), 256, 0, cg_stream(stream)>>>(
+    upsample_bwd_kernel<<<dim3(cg_ceil_div(Hi * Hi, 256), (C + 7) / 8, N), 256, 0, cg_stream(stream)>>>(
         reinterpret_cast<const bf16*>(dy), reinterpret_cast<bf16*>(dx), N, Hi, Ho, (C + 7) / 8, dy_ld, dx_ld, accumulate);
     CG_LAUNCH_CHECK("cg_upsample_bwd");
   }
   if (dbias != nullptr) {
-    upsample_dbias_kernel<<<grid_for((long long)Ho * Ho * ((C + 7) / 8), 256), 256, 0, cg_stream(stream)>>>(
+    upsample_dbias_kernel<<<dim3(cg_ceil_div(Ho * Ho, 256), (C + 7) / 8, cg_ceil_div(N, 16)), 256, 0, cg_stream(stream)>>>(
         reinterpret_cast<const bf16*>(dy), dbias, N, Ho, C, dy_ld);
     CG_LAUNCH_CHECK("cg_upsample_bwd(dbias)");
   }

@@ -9,10 +9,11 @@ constexpr int kT = 16;           // output tile edge
 constexpr int kHalo = kT + 6;    // input tile edge
 constexpr int kMaxCout = 32;
 
-template <int CIN>
+template <int CIN, int COUT>
 __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                        const float* __restrict__ b, bf16* __restrict__ y, int R,
-                                                       int Cout, long long y_ns) {
+                                                       long long y_ns) {
+  constexpr int Cout = COUT;  // compile-time: the accumulators must stay in registers
   extern __shared__ float sm[];
   float* s_w = sm;                              // [tap][ci][co]
   float* s_x = sm + 49 * CIN * Cout;            // [ci][kHalo][kHalo]
@@ -28,9 +29,9 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__
   }
   __syncthreads();
   const int ty = threadIdx.x / kT, tx = threadIdx.x % kT;
-  float acc[kMaxCout];
+  float acc[COUT];
 #pragma unroll
-  for (int co = 0; co < kMaxCout; ++co) acc[co] = co < Cout ? b[co] : 0.f;
+  for (int co = 0; co < COUT; ++co) acc[co] = b[co];
   for (int kh = 0; kh < 7; ++kh)
     for (int kw = 0; kw < 7; ++kw)
 #pragma unroll
@@ -38,13 +39,16 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__
         float v = s_x[(ci * kHalo + ty + kh) * kHalo + tx + kw];
         const float* wp = s_w + ((kh * 7 + kw) * CIN + ci) * Cout;
 #pragma unroll
-        for (int co = 0; co < kMaxCout; ++co)
-          if (co < Cout) acc[co] += v * wp[co];
+        for (int co = 0; co < COUT; co += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wp + co);
+          acc[co] += v * w4.x; acc[co + 1] += v * w4.y; acc[co + 2] += v * w4.z; acc[co + 3] += v * w4.w;
+        }
       }
   const int h = h0 + ty, wq = w0 + tx;
   if (h < R && wq < R) {
     bf16* o = y + n * y_ns + ((long long)h * R + wq) * 8;  // planar: one 16-byte octet per plane
-    for (int c8 = 0; c8 < Cout; c8 += 8) *reinterpret_cast<uint4*>(o + (long long)(c8 >> 3) * R * R * 8) = cg_pack8(acc + c8);
+#pragma unroll
+    for (int c8 = 0; c8 < COUT; c8 += 8) *reinterpret_cast<uint4*>(o + (long long)(c8 >> 3) * R * R * 8) = cg_pack8(acc + c8);
   }
 }
 
@@ -144,14 +148,16 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
 extern "C" int cg_stem_fwd(const float* x, const float* w, const float* b, void* y, int32_t N, int32_t Cin, int32_t R,
                            int32_t Cout, int64_t y_ld, void* stream) {
   CG_ARCH_GUARD();
-  CG_REQUIRE((Cin == 1 || Cin == 3) && Cout % 8 == 0 && Cout <= kMaxCout && y_ld % 8 == 0,
-             "cg_stem_fwd: Cin=%d Cout=%d", Cin, Cout);
+  CG_REQUIRE((Cin == 1 || Cin == 3) && (Cout == 16 || Cout == 32) && y_ld % 8 == 0,
+             "cg_stem_fwd: Cin=%d Cout=%d (supported: Cin 1|3, Cout 16|32 = widths[0] of every preset)", Cin, Cout);
   dim3 grid(cg_ceil_div(R, kT), cg_ceil_div(R, kT), N);
   size_t smem = (size_t)(49 * Cin * Cout + Cin * kHalo * kHalo) * sizeof(float);
-  if (Cin == 1)
-    stem_fwd_kernel<1><<<grid, 256, smem, cg_stream(stream)>>>(x, w, b, reinterpret_cast<bf16*>(y), R, Cout, y_ld);
-  else
-    stem_fwd_kernel<3><<<grid, 256, smem, cg_stream(stream)>>>(x, w, b, reinterpret_cast<bf16*>(y), R, Cout, y_ld);
+  bf16* yb = reinterpret_cast<bf16*>(y);
+  cudaStream_t st = cg_stream(stream);
+  if (Cin == 1 && Cout == 32) stem_fwd_kernel<1, 32><<<grid, 256, smem, st>>>(x, w, b, yb, R, y_ld);
+  else if (Cin == 1) stem_fwd_kernel<1, 16><<<grid, 256, smem, st>>>(x, w, b, yb, R, y_ld);
+  else if (Cout == 32) stem_fwd_kernel<3, 32><<<grid, 256, smem, st>>>(x, w, b, yb, R, y_ld);
+  else stem_fwd_kernel<3, 16><<<grid, 256, smem, st>>>(x, w, b, yb, R, y_ld);
   CG_LAUNCH_CHECK("cg_stem_fwd");
   return CG_OK;
 }
