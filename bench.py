@@ -28,6 +28,10 @@ HBM_FALLBACK_GBS = 6650.0
 TENSOR_FALLBACK_TFS = 1400.0
 # conv FLOPs per image of one ELBO forward pass (measured on the reference with hooks);
 # a training step executes 3x (forward + data-gradient + weight-gradient)
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per conv_tc_kernel launch, averaged over the 1815
+# conv launches of two training steps at the given per-GPU batch: profiles/r1f_ncu_launches_bench_b128.csv
+# (ncu pass of this very command).  Below the algorithmic bytes because producer->consumer tensors hit the L2.
+CONV_DRAM_TRAFFIC_PER_LAUNCH = {("ukbb192", 128): 84.37e6}
 FWD_GFLOP = {"ukbb192": 23.064, "mimic192": 9.127, "morphomnist": 0.0865, "cmnist": 0.0917, "mimic224": 12.460}
 CF_GFLOP = {"ukbb192": 47.670, "mimic192": 19.565, "morphomnist": 0.1845, "cmnist": 0.1924, "mimic224": 26.707}
 
@@ -357,11 +361,13 @@ def main():
             "loss": {"elbo": loss[0], "nll": loss[1], "kl": loss[2], "skipped_updates": trainer.skipped_updates()},
             "roofline": {"bound": "hbm", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv: forward + data-gradient)",
                          "achieved": conv_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": conv_gbs / hbm_gbs,
-                         "peak_source": peak_src, "traffic": None,
+                         "peak_source": peak_src, "traffic": CONV_DRAM_TRAFFIC_PER_LAUNCH.get((args.config, B)),
+                         "algorithmic_bytes_per_launch": prof["conv_bytes"] / max(prof["nconv"], 1),
                          "launches_per_step": prof["nconv"], "avg_launch_us": 1e3 * prof["conv_ms"] / max(prof["nconv"], 1),
                          "algorithmic_bytes_per_step": prof["conv_bytes"],
                          "share_of_step": prof["conv_ms"] / prof["total_ms"],
-                         "wgrad_kernel": {"achieved": wg_gbs, "frac": wg_gbs / hbm_gbs, "launches_per_step": prof["nwgrad"],
+                         "wgrad_kernel": {"kernel": "wgrad_mma_kernel (mma.sync, 3x3) + wgrad_tc_kernel (tcgen05, 1x1)",
+                                          "achieved": wg_gbs, "frac": wg_gbs / hbm_gbs, "launches_per_step": prof["nwgrad"],
                                           "share_of_step": prof["wgrad_ms"] / prof["total_ms"]},
                          "tensor": {"conv_tflops": gflop_step * value / 1e3, "peak": tensor_tfs,
                                     "frac": gflop_step * value / 1e3 / tensor_tfs,
