@@ -47,7 +47,9 @@ struct alignas(64) MParams {
   CUtensorMap x_map[CG_MAX_SRC];
   CUtensorMap dy_map;
   cg_wgrad_args a;
-  MChunk chunk[kMaxChunksM];
+  MChunk chunk[kMaxChunksM];   // 3x3: chunks of the wide operand; 1x1: chunks of X
+  MChunk ychunk[kMaxChunksM];  // 1x1 only: chunks of dY
+  int ny;
   uint32_t x_bytes[CG_MAX_SRC], dy_bytes;  // TMA transaction bytes of one box
   int nchunks;
   int tiles_x, tiles_per_img, ntiles;
@@ -320,6 +322,178 @@ __global__ void __launch_bounds__(kThreadsM, 1) wgrad_mma_kernel(const __grid_co
   if (threadIdx.x == 0) CG_TL(P.tl, 22);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// 1x1 convolutions (z_proj, z_feat_proj, width_proj: src/vae.py:70-78,165-170): dW[co][ci] += sum_p dY[p][co] X[p][ci].
+// Same machinery without taps: both operands are plain 16x8-pixel tiles.  12 warps = 4 pixel groups (every 4th
+// tile, own ring slice) x 3 output-channel groups; the CTA owns CO = 3*MT*16 dY channels x CI = NT*8 X channels.
+template <int MT, int NT>
+__global__ void __launch_bounds__(kThreadsM, 1) wgrad1_mma_kernel(const __grid_constant__ MParams P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint8_t* stages = smem + kHdrM;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t bar0 = cg_smem_u32(bars);
+  auto FULL = [&](int i) { return bar0 + 8u * i; };
+  auto EMPTY = [&](int i) { return bar0 + 8u * (kMaxStagesM + i); };
+  constexpr int CO = 3 * MT * 16, CI = NT * 8;
+  const int nx = P.nchunks;
+  const MChunk yc = P.ychunk[blockIdx.y / nx];
+  const MChunk xc = P.chunk[blockIdx.y % nx];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P.nst; ++i) {
+      mbar_init(FULL(i), 1);
+      mbar_init(EMPTY(i), 3);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  float acc[MT][NT][4];
+  float bacc[MT][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[mt][nt][q] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bacc[mt][q] = 0.f;
+  }
+  const int cg = warp % 3, pg = warp / 3;  // output-channel group, pixel group
+  const bool do_bias = P.a.dbias != nullptr && (blockIdx.y % nx) == 0;
+  const uint32_t tx = P.dy_bytes + P.x_bytes[xc.src];
+  const int depth = P.nst / kPixGroups;
+  uint32_t p_slot = 0, p_phase = 0;
+  int p_tile = blockIdx.x + pg * gridDim.x;
+  auto produce = [&]() {
+    if (p_tile >= P.ntiles) return;
+    const int n = p_tile / P.tiles_per_img;
+    const int r = p_tile - n * P.tiles_per_img;
+    const int ty = r / P.tiles_x;
+    const int h0 = ty * 16, w0 = (r - ty * P.tiles_x) * 8;
+    const int st = pg + kPixGroups * (int)p_slot;
+    mbar_wait(EMPTY(st), p_phase ^ 1u);
+    mbar_expect_tx(FULL(st), tx);
+    const uint32_t sb = cg_smem_u32(stages + st * P.stage_bytes);
+    tma4m(sb, &P.dy_map, w0 * 8, h0, yc.c0 >> 3, n, FULL(st));
+    tma4m(sb + P.wide_off, &P.x_map[xc.src], w0 * 8, h0, xc.c0 >> 3, n, FULL(st));
+    if (++p_slot == (uint32_t)depth) { p_slot = 0; p_phase ^= 1u; }
+    p_tile += kPixGroups * gridDim.x;
+  };
+  if (cg == 0) {
+    if (elect_one()) {
+      for (int i = 0; i < depth - 1; ++i) produce();
+    }
+    __syncwarp();
+  }
+  {
+    const int j = lane >> 3, i = lane & 7;
+    const bool relu = P.a.act == CG_ACT_RELU;
+    const uint32_t ones = 0x3F803F80u;
+    const uint32_t a_off = (uint32_t)((cg * MT * 2 + (j & 1)) * kPlaneFlat + ((j >> 1) * 8 + i) * 16);
+    const uint32_t b_off = (uint32_t)(P.wide_off + (j >> 1) * kPlaneFlat + ((j & 1) * 8 + i) * 16);
+    uint32_t slot = 0, phase = 0;
+    for (int tile = blockIdx.x + pg * gridDim.x; tile < P.ntiles; tile += kPixGroups * gridDim.x) {
+      if (cg == 0) {
+        if (elect_one()) produce();
+        __syncwarp();
+      }
+      const int stage = pg + kPixGroups * (int)slot;
+      if (lane == 0) mbar_wait(FULL(stage), phase);
+      __syncwarp();
+      const uint32_t sb = cg_smem_u32(stages + stage * P.stage_bytes);
+#pragma unroll 2
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint32_t roff = (uint32_t)(2 * ks * 8 * 16);
+        uint32_t a[MT][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) ldsm_x4_t(a[mt], sb + a_off + (uint32_t)(mt * 2 * kPlaneFlat) + roff);
+        if (do_bias) {
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) mma_bf16(bacc[mt], a[mt], ones, ones);
+        }
+#pragma unroll
+        for (int n2 = 0; n2 < NT / 2; ++n2) {
+          uint32_t b[4];
+          ldsm_x4_t(b, sb + b_off + (uint32_t)(n2 * 2 * kPlaneFlat) + roff);
+          if (relu) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) b[q] = relu2(b[q]);
+          }
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            mma_bf16(acc[mt][2 * n2], a[mt], b[0], b[1]);
+            mma_bf16(acc[mt][2 * n2 + 1], a[mt], b[2], b[3]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(EMPTY(stage));
+      if (++slot == (uint32_t)depth) { slot = 0; phase ^= 1u; }
+    }
+  }
+  // flush: [CO][CI (+1 pad)] fp32 tile; pixel group 0 stores, groups 1..3 add in turn
+  __syncthreads();
+  constexpr int ROW = CI + 1;
+  float* sacc = reinterpret_cast<float*>(stages);
+  float* sbias = sacc + CO * ROW;
+  for (int e = threadIdx.x; e < CO; e += kThreadsM) sbias[e] = 0.f;
+#pragma unroll
+  for (int half = 0; half < kPixGroups; ++half) {
+    if (pg == half) {
+      const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          float* p0 = sacc + ((cg * MT + mt) * 16 + g) * ROW + nt * 8 + 2 * t;
+          float* p1 = p0 + 8 * ROW;
+          if (half == 0) {
+            p0[0] = acc[mt][nt][0]; p0[1] = acc[mt][nt][1]; p1[0] = acc[mt][nt][2]; p1[1] = acc[mt][nt][3];
+          } else {
+            p0[0] += acc[mt][nt][0]; p0[1] += acc[mt][nt][1]; p1[0] += acc[mt][nt][2]; p1[1] += acc[mt][nt][3];
+          }
+        }
+    }
+    __syncthreads();
+    if (half == 0 && do_bias && (lane & 3) == 0) {
+      const int g = lane >> 2;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        atomicAdd(&sbias[(cg * MT + mt) * 16 + g], bacc[mt][0]);
+        atomicAdd(&sbias[(cg * MT + mt) * 16 + g + 8], bacc[mt][2]);
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int cin_l = P.a.cin_l, cout_l = P.a.cout_l, xlog = P.a.src_log[xc.src], xoff = P.a.src_off[xc.src];
+    for (int e = threadIdx.x; e < CO * CI; e += kThreadsM) {
+      const int co = e / CI, ci = e - co * CI;
+      if (co < yc.nc && ci < xc.nc && yc.c0 + co < cout_l && xc.c0 + ci < xlog)
+        atomicAdd(P.a.dw + (long long)(yc.c0 + co) * cin_l + xoff + xc.c0 + ci, sacc[co * ROW + ci]);
+    }
+    if (do_bias) {
+      for (int co = threadIdx.x; co < CO; co += kThreadsM)
+        if (co < yc.nc && yc.c0 + co < cout_l) atomicAdd(P.a.dbias + yc.c0 + co, sbias[co]);
+    }
+  }
+}
+
+template <int MT, int NT>
+int launch_mma1(const MParams& kp, int gx, int gy, int smem_bytes, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad1_mma_kernel<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) {
+      cg_set_error("cg_conv2d_wgrad(mma 1x1): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return CG_ERR_CUDA;
+    }
+    attr_done = true;
+  }
+  wgrad1_mma_kernel<MT, NT><<<dim3(gx, gy), kThreadsM, smem_bytes, st>>>(kp);
+  return CG_OK;
+}
+
 template <int MT, int NT, bool SHIFT_A>
 int launch_mma(const MParams& kp, int gx, int smem_bytes, cudaStream_t st) {
   static bool attr_done = false;
@@ -340,7 +514,13 @@ int launch_mma(const MParams& kp, int gx, int smem_bytes, cudaStream_t st) {
 
 // Returns CG_OK with *handled = 1 when the problem was launched on the mma.sync kernel, *handled = 0 when the
 // caller must use the tcgen05 kernel (1x1 / centre-tap / 1-pixel problems, GELU, both operands wide).
+static bool mma1_eligible(const cg_wgrad_args* a) {
+  return a->ksize == 1 && a->taps == 1 && !(a->H == 1 && a->W == 1) &&
+         (a->act == CG_ACT_NONE || a->act == CG_ACT_RELU);
+}
+
 static bool mma_eligible(const cg_wgrad_args* a) {
+  if (mma1_eligible(a)) return true;
   if (a->ksize != 3 || a->taps != 9 || (a->H == 1 && a->W == 1)) return false;
   if (a->act != CG_ACT_NONE && a->act != CG_ACT_RELU) return false;
   int xtot = 0;
@@ -358,9 +538,71 @@ extern "C" int32_t cg_conv2d_wgrad_launches(const cg_wgrad_args* a) {
   return a->dbias != nullptr ? 2 : 1;
 }
 
+static int wgrad_mma_1x1(const cg_wgrad_args* a, void* stream, int* handled) {
+  int widest = 0;
+  for (int s = 0; s < a->nsrc; ++s) widest = a->src[s].C > widest ? a->src[s].C : widest;
+  // X chunk width (NT*8) follows the widest source; the dY chunk (3*MT*16) takes what the stage budget leaves
+  const int NT = widest <= 16 ? 2 : (widest <= 32 ? 4 : 8);
+  const int MT = NT == 2 ? 2 : 1;
+  const int CO = 3 * MT * 16, CI = NT * 8;
+  MParams kp;
+  kp.a = *a;
+  kp.tl = cg_tl_ptr;
+  kp.nchunks = kp.ny = 0;
+  for (int s = 0; s < a->nsrc; ++s)
+    for (int c0 = 0; c0 < a->src[s].C; c0 += CI) {
+      if (kp.nchunks >= kMaxChunksM) return CG_OK;
+      const int nc = a->src[s].C - c0 < CI ? a->src[s].C - c0 : CI;
+      kp.chunk[kp.nchunks++] = MChunk{(int16_t)s, (int16_t)c0, (int16_t)nc};
+    }
+  for (int c0 = 0; c0 < a->dy_c; c0 += CO) {
+    if (kp.ny >= kMaxChunksM) return CG_OK;
+    const int nc = a->dy_c - c0 < CO ? a->dy_c - c0 : CO;
+    kp.ychunk[kp.ny++] = MChunk{0, (int16_t)c0, (int16_t)nc};
+  }
+  const int gy = kp.nchunks * kp.ny;
+  if (gy > cg_device_sms()) return CG_OK;  // more channel blocks than SMs: leave it to the tcgen05 kernel
+  for (int s = 0; s < a->nsrc; ++s) {
+    const int c8 = a->src[s].C / 8;
+    const int boct = c8 < NT ? c8 : NT;
+    int rc = cg_make_planar_map(&kp.x_map[s], a->src[s].ptr, a->src[s].ns, a->N, a->H, a->W, c8, 0, 64, 16, boct);
+    if (rc != CG_OK) return rc;
+    kp.x_bytes[s] = (uint32_t)boct * kPlaneFlat;
+  }
+  {
+    const int c8 = a->dy_c / 8;
+    const int boct = c8 < CO / 8 ? c8 : CO / 8;
+    int rc = cg_make_planar_map(&kp.dy_map, a->dy, a->dy_ns, a->N, a->H, a->W, c8, 0, 64, 16, boct);
+    if (rc != CG_OK) return rc;
+    kp.dy_bytes = (uint32_t)boct * kPlaneFlat;
+  }
+  kp.tiles_x = (a->W + 7) / 8;
+  kp.tiles_per_img = kp.tiles_x * ((a->H + 15) / 16);
+  kp.ntiles = a->N * kp.tiles_per_img;
+  kp.wide_off = (CO / 8) * kPlaneFlat;  // X tile sits after the dY planes
+  kp.stage_bytes = kp.wide_off + NT * kPlaneFlat;
+  kp.nst = (232448 - kHdrM) / kp.stage_bytes / 4 * 4;
+  if (kp.nst > kMaxStagesM) kp.nst = kMaxStagesM;
+  if (kp.nst < 8) return CG_OK;
+  const int smem_bytes = kHdrM + kp.nst * kp.stage_bytes;
+  int gx = cg_device_sms() / gy;
+  if (gx > (kp.ntiles + 3) / 4) gx = (kp.ntiles + 3) / 4;
+  if (gx < 1) gx = 1;
+  cudaStream_t st = cg_stream(stream);
+  int rc;
+  if (NT == 2) rc = launch_mma1<2, 2>(kp, gx, gy, smem_bytes, st);
+  else if (NT == 4) rc = launch_mma1<1, 4>(kp, gx, gy, smem_bytes, st);
+  else rc = launch_mma1<1, 8>(kp, gx, gy, smem_bytes, st);
+  if (rc != CG_OK) return rc;
+  CG_LAUNCH_CHECK("cg_conv2d_wgrad(mma 1x1)");
+  *handled = 1;
+  return CG_OK;
+}
+
 int cg_wgrad_mma_try(const cg_wgrad_args* a, void* stream, int* handled) {
   *handled = 0;
   if (!mma_eligible(a)) return CG_OK;
+  if (mma1_eligible(a)) return wgrad_mma_1x1(a, stream, handled);
   int xtot = 0;
   for (int s = 0; s < a->nsrc; ++s) xtot += a->src[s].C;
   const int dyc = a->dy_c;

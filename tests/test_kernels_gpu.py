@@ -224,6 +224,11 @@ WGRAD_MMA_CASES = [
     (3, 6, 6, [40], 0, 176, 3, 1),         # X 48, dY 176 -> eleven dY chunks
     (40, 24, 24, [128], 0, 32, 3, 1),      # many tiles per CTA, ring wraps
     (6, 96, 96, [16], 0, 64, 3, 1),
+    # 1x1 problems (z_proj / z_feat_proj / width_proj shapes) on the tap-less variant
+    (2, 24, 24, [16, 128], 0, 128, 1, 0),  # cat[z, p_feat] -> out: X chunks 16 | 64 | 64, dY chunks 48 | 48 | 32
+    (3, 12, 12, [160], 0, 192, 1, 0),      # width_proj
+    (2, 48, 48, [16], 4, 96, 1, 0),        # cat[z, pa] -> h: narrow X (NT=2), dY 96 in one chunk
+    (9, 20, 12, [32], 0, 40, 1, 1),        # ragged tile edges, ReLU, dY 48 padded
 ]
 
 
@@ -240,7 +245,7 @@ def test_wgrad_mma_small_channel_3x3(case):
     parts = [to_nchw(v.t, c) for v, c in zip(views, logical)]
     wq = w.to(torch.bfloat16).float().requires_grad_(True)
     bq = b.clone().requires_grad_(True)
-    y = F.conv2d(act_fn(act)(torch.cat(parts, 1)), wq, bq, padding=1)
+    y = F.conv2d(act_fn(act)(torch.cat(parts, 1)), wq, bq, padding=k // 2)
     y.backward(to_nchw(dy.t, cout))
     dw = torch.full_like(w, 0.5)
     db = torch.full_like(b, -0.25)
