@@ -382,12 +382,22 @@ def main():
         pa, cfp = pas_d[0], pas_d[1]
         for _ in range(2):
             counterfactual(model, xf, pa, cfp)
-        ms_cf, _, _ = timed(lambda i: counterfactual(model, xf, pa, cfp), max(3, args.steps // 2), world)
+        ncf = max(3, args.steps // 2)
+        ms_cf, _, _ = timed(lambda i: counterfactual(model, xf, pa, cfp), ncf, world)
+        from causalgen_b200 import CounterfactualGraph
+        cfg_run = CounterfactualGraph(model, Bc)
+        for _ in range(2):
+            cfg_run(xf, pa, cfp)
+        ms_cfg, _, _ = timed(lambda i: cfg_run(xf, pa, cfp), ncf, world)
         if rank == 0:
-            cf_val = Bc * world * max(3, args.steps // 2) / (ms_cf / 1e3)
+            cf_val = Bc * world * ncf / (ms_cfg / 1e3)
             line["cf_inference"] = {"metric": "counterfactual_images_per_sec", "value": cf_val, "unit": "images/s",
-                                    "batch_per_gpu": Bc, "tensor_frac": CF_GFLOP.get(args.config, 0) * cf_val / 1e3 / tensor_tfs,
-                                    "note": "abduct + forward_latents(cf_pa, pa) batched + combine, eager launches"}
+                                    "batch_per_gpu": Bc, "ms_per_batch": ms_cfg / ncf,
+                                    "eager_value": Bc * world * ncf / (ms_cf / 1e3),
+                                    "tensor_frac": CF_GFLOP.get(args.config, 0) * cf_val / 1e3 / tensor_tfs,
+                                    "note": "abduct + forward_latents(cf_pa, pa) batched + combine (src/pgm/dscm.py:47-72), "
+                                            "CUDA-graph replay; eager_value = same launches issued from Python"}
+        del cfg_run
     # the same step at the reference's own batch size (src/hps.py ukbb192: bs=32): latency-bound regime
     if B != 32 and not args.no_ref_batch:
         del trainer

@@ -312,3 +312,37 @@ def counterfactual(vae: HVAE, x: Tensor, pa: Tensor, cf_pa: Tensor, t_abduct: fl
         var = (acc2 - acc ** 2 / particles) / particles  # src/pgm/dscm.py:68
         return mean, var
     return cf_x, None
+
+
+class CounterfactualGraph:
+    """``counterfactual`` for a fixed batch size replayed from one CUDA graph (inference serving path).
+
+    The eager helper issues ~1500 small launches per call and is CPU-bound at small batches; the graph replays the
+    identical launch sequence (abduct program, two-parent-set decode program, combine) from static buffers.
+    Noise is drawn inside the graph by torch's graph-safe Philox generator (``randn_like``, as the reference does,
+    src/vae.py:30), so every replay sees fresh eps."""
+
+    def __init__(self, vae: HVAE, batch: int, t_abduct: float = 1.0, particles: int = 1):
+        eng = vae.engine()
+        dev = eng.device
+        self.vae, self.t, self.particles = vae, t_abduct, particles
+        self.x = torch.zeros(batch, eng.C, eng.R, eng.R, device=dev)
+        self.pa = torch.zeros(batch, eng.ctx, device=dev)
+        self.cf_pa = torch.zeros(batch, eng.ctx, device=dev)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # builds the programs and sets kernel attributes outside the capture
+            counterfactual(vae, self.x, self.pa, self.cf_pa, t_abduct, particles)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.cf_x, self.var = counterfactual(vae, self.x, self.pa, self.cf_pa, t_abduct, particles)
+
+    @torch.no_grad()
+    def __call__(self, x: Tensor, pa: Tensor, cf_pa: Tensor):
+        self.x.copy_(x, non_blocking=True)
+        self.pa.copy_(_pa_vector(pa), non_blocking=True)
+        self.cf_pa.copy_(_pa_vector(cf_pa), non_blocking=True)
+        self.graph.replay()
+        return self.cf_x, self.var
