@@ -168,7 +168,7 @@ def check(rc: int, what: str = ""):
 
 class Launch:
     """One recorded kernel launch: a bound C function plus its (mutable) argument tuple."""
-    __slots__ = ("fn", "args", "name", "keep", "side")
+    __slots__ = ("fn", "args", "name", "keep", "side", "lane")
 
     def __init__(self, name, *args):
         self.fn = getattr(load(), name)
@@ -176,6 +176,7 @@ class Launch:
         self.name = name
         self.keep = None
         self.side = False  # True: nothing later in the program reads its result -> may run on a side stream
+        self.lane = 0      # 0: main stream, 1: auxiliary lane of the program (engine.Program)
 
     def __call__(self, stream):
         rc = self.fn(*self.args, stream)

@@ -36,24 +36,68 @@ class PyOp:
     """a recorded torch-side glue op (layout copies only; never arithmetic on the path)"""
 
     side = False
+    lane = 0
 
     def __init__(self, fn, name="pyop"):
         self.fn, self.name = fn, name
 
     def __call__(self, stream):
-        self.fn()
+        if self.lane == 0:
+            self.fn()
+        else:  # torch op recorded on the auxiliary lane: run it on that stream
+            with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
+                self.fn()
+
+
+class Marker:
+    """fork / join point between the main stream (lane 0) and the auxiliary lane of a program"""
+    side = False
+    lane = 0
+
+    def __init__(self, kind):
+        self.kind, self.name = kind, "lane_" + kind
+
+    def __call__(self, stream):  # sequential execution: nothing to do
+        pass
 
 
 class Program:
+    """Recorded launch sequence.  Dependencies are expressed structurally: launches on lane 0 (main stream) and on
+    lane 1 (auxiliary stream) are each in order; ``fork()`` makes lane 1 wait for everything issued on lane 0 so far,
+    ``join()`` the reverse.  Weight-gradient launches (``side``) only feed the gradient bucket: each waits for the
+    lane it was recorded on and runs on a pool stream; everything meets again at the end of ``run``."""
+
     def __init__(self, name):
         self.name = name
         self.launches: List = []
         self.keep: List = []
         self.n_kernels = 0
         self.sides = None
+        self.aux = None
+        self.cur_lane = 0
+
+    def fork(self):
+        self.launches.append(Marker("fork"))
+
+    def join(self):
+        self.launches.append(Marker("join"))
+
+    class _Lane:
+        def __init__(self, prog, lane):
+            self.prog, self.lane = prog, lane
+
+        def __enter__(self):
+            self.prev, self.prog.cur_lane = self.prog.cur_lane, self.lane
+
+        def __exit__(self, *exc):
+            self.prog.cur_lane = self.prev
+
+    def on_lane(self, lane):
+        return Program._Lane(self, lane)
 
     def add(self, ln):
         self.launches.append(ln)
+        ln.lane = self.cur_lane
         if isinstance(ln, L.Launch):
             if ln.name == "cg_conv2d_wgrad":
                 self.n_kernels += int(L.load().cg_conv2d_wgrad_launches(C.byref(ln.keep[0])))
@@ -76,21 +120,42 @@ class Program:
             return
         if self.sides is None:
             self.sides = [torch.cuda.Stream() for _ in range(SIDE_STREAMS)]
-        ev, seen, k = None, [None] * len(self.sides), 0
+            self.aux = torch.cuda.Stream()
+        lanes = (main, self.aux)
+        raw = (s, self.aux.cuda_stream)
+        ev = [None, None]            # per lane: event covering everything issued on it so far (None = stale)
+        seen = [[None, None] for _ in self.sides]
+        k, aux_used = 0, False
+
+        def event_of(lane):
+            if ev[lane] is None:
+                ev[lane] = torch.cuda.Event()
+                ev[lane].record(lanes[lane])
+            return ev[lane]
+
         for ln in self.launches:
+            if isinstance(ln, Marker):
+                if ln.kind == "fork":
+                    self.aux.wait_event(event_of(0))
+                    ev[1] = None  # the lane now also covers main's work: a cached older event would miss it
+                    aux_used = True
+                else:
+                    main.wait_event(event_of(1))
+                    ev[0] = None
+                continue
             if ln.side:
-                if ev is None:  # main advanced since the last fork point
-                    ev = torch.cuda.Event()
-                    ev.record(main)
                 j = k % len(self.sides)
                 k += 1
-                if seen[j] is not ev:
-                    self.sides[j].wait_event(ev)
-                    seen[j] = ev
+                e = event_of(ln.lane)
+                if seen[j][ln.lane] is not e:
+                    self.sides[j].wait_event(e)
+                    seen[j][ln.lane] = e
                 ln(self.sides[j].cuda_stream)
             else:
-                ln(s)
-                ev = None
+                ln(raw[ln.lane])
+                ev[ln.lane] = None
+        if aux_used:
+            main.wait_stream(self.aux)
         if k:
             for st in self.sides:
                 main.wait_stream(st)
@@ -273,12 +338,16 @@ class Engine:
         zs = h  # h = z = bias[1].repeat (src/vae.py:232)
         cur_res = 1
         ksto = 0
+        zfp_pending = False  # z_feat_proj of the previous block still running on the auxiliary lane
         for d in self.dec_layers:
             st = d.st
             r = Rec()
             r.d, r.st = d, st
             res = st.res
             r.up = None
+            if zfp_pending:  # its output (the z stream) is consumed from here on
+                prog.join()
+                zfp_pending = False
             if cur_res < res:  # src/vae.py:251-262 (the z stream reuses the same bias b)
                 b = bias_of.get(res)
                 bptr = b.data_ptr() if b is not None else None
@@ -295,6 +364,16 @@ class Engine:
                 h = h_up
                 cur_res = res
             r.h_in, r.zs_in = h, zs
+            # ---- posterior net (src/vae.py:185-192): shares only READ operands with the prior net, so it is emitted
+            # first on the auxiliary lane and runs while the prior net occupies the main stream; they meet at the
+            # latent kernel
+            r.post, r.qstat = None, None
+            if st.stochastic and acts is not None:
+                r.qstat = View(torch.zeros(N, res, res, 2 * zd, device=self.device, dtype=torch.float32), 2 * zd)
+                prog.fork()
+                with prog.on_lane(1):
+                    r.post = self._block_fwd(prog, d.post, [h, pa[res], acts[res]], N, res, res,
+                                             final_segs=[SegSpec(r.qstat, 0)])
             # ---- prior (src/vae.py:172-183)
             p_src = [h if self.q_corr else zs] + ([pa_sto[res]] if self.cond_prior else [])
             r.pstat = View(torch.zeros(N, res, res, 2 * zd, device=self.device, dtype=torch.float32), 2 * zd)
@@ -303,17 +382,13 @@ class Engine:
                                       final_segs=[SegSpec(r.pstat, 0), SegSpec(r.pfeat, 2 * zd)])
             # ---- posterior + latent (src/vae.py:265-291)
             r.z = new_act(N, res, res, zd, self.device)
-            r.post = None
             r.mode = 2
             r.eps = None
-            r.qstat = None
             la = None
             if st.stochastic:
                 is_given = bool(given[ksto]) if given is not None and ksto < len(given) else False
                 if acts is not None:
-                    r.qstat = View(torch.zeros(N, res, res, 2 * zd, device=self.device, dtype=torch.float32), 2 * zd)
-                    r.post = self._block_fwd(prog, d.post, [h, pa[res], acts[res]], N, res, res,
-                                             final_segs=[SegSpec(r.qstat, 0)])
+                    prog.join()  # posterior statistics ready
                     r.mode = 0
                 elif is_given:
                     zin = torch.zeros(N, zd, res, res, device=self.device, dtype=torch.float32)
@@ -351,18 +426,26 @@ class Engine:
             if la is not None:
                 prog.add(L.Launch("cg_latent_fwd", C.byref(la))).keep = (la, r)
                 D.latent_args.append(la)
+            # z stream of the next block (src/vae.py:297-300) only needs z and p_feat: auxiliary lane, joined at the
+            # top of the next block
+            r.zs_out = None
+            if d.zfp is not None and st.idx + 1 < len(self.dec_layers):
+                r.zs_out = new_act(N, res, res, st.cout, self.device)
+                prog.fork()
+                with prog.on_lane(1):
+                    prog.add(d.zfp.forward([r.z, r.pfeat], [SegSpec(r.zs_out, 0)], N, res, res))
+                zfp_pending = True
             # ---- merge (src/vae.py:292-300)
             r.h3 = new_act(N, res, res, st.cin, self.device)
             # h3 = h + p_feat + z_proj(cat[z, pa]) in one epilogue (src/vae.py:292-294)
             prog.add(d.z_proj.forward([r.z, pa[res]], [SegSpec(r.h3, 0, add=h, add2=r.pfeat)], N, res, res))
             r.conv = self._block_fwd(prog, d.conv, [r.h3], N, res, res)
             h = r.conv.y
-            r.zs_out = None
-            if d.zfp is not None and st.idx + 1 < len(self.dec_layers):
-                r.zs_out = new_act(N, res, res, st.cout, self.device)
-                prog.add(d.zfp.forward([r.z, r.pfeat], [SegSpec(r.zs_out, 0)], N, res, res))
+            if r.zs_out is not None:
                 zs = r.zs_out
             D.blocks.append(r)
+        if zfp_pending:
+            prog.join()
         D.h = h
         D.nsto = ksto
         return D
@@ -468,8 +551,15 @@ class Engine:
                 else:
                     da = acts_grad[res] = new_act(N, res, res, st.cin, self.device)
                     seg_a = SegSpec(da, 0)
-                self._block_bwd(prog, r.post, dq, [SegSpec(dh_in, 0, add=dh3), None, seg_a])
+                # posterior and prior backward chains only meet again at the block input: the posterior chain runs on
+                # the auxiliary lane (with q_correction the prior chain accumulates into the same tensor: no fork)
+                forked = not self.q_corr
+                if forked:
+                    prog.fork()
+                with prog.on_lane(1 if forked else 0):
+                    self._block_bwd(prog, r.post, dq, [SegSpec(dh_in, 0, add=dh3), None, seg_a])
             else:
+                forked = False
                 dh_in = dh3
             # prior
             if self.q_corr:
@@ -483,6 +573,8 @@ class Engine:
             else:
                 dzs_in = new_act(N, res, res, st.cin, self.device)
                 self._block_bwd(prog, r.prior, DP, [SegSpec(dzs_in, 0)] + [None] * (len(r.prior.srcs) - 1))
+            if forked:
+                prog.join()
             # upsample
             if r.up is not None:
                 src_res, h_prev, zs_prev, b = r.up
