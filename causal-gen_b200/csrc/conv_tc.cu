@@ -228,6 +228,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(BAR(B_EEMPTY + i), kEpiWarps);
     }
     mbar_fence_init();
+    // resident weight slab of this CTA's Cout chunk.  Packed weights were written at the start of the step, not
+    // by the kernel right before this one, so the copy may start before the grid dependency is resolved (below).
+    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(P.a.wpack) + (size_t)nchunkN * P.slab_bytes;
+    mbar_expect_tx(BAR(B_BFULL), P.slab_bytes);
+    for (uint32_t off = 0; off < P.slab_bytes; off += 32768u) {
+      uint32_t n = min(32768u, P.slab_bytes - off);
+      bulk_g2s(cg_smem_u32(sB) + off, wsrc + off, n, BAR(B_BFULL));
+    }
   }
   if (warp == kMmaWarp) tmem_alloc(cg_smem_u32(tmem_slot), P.tmem_cols);
   for (int i = threadIdx.x; i < Nc; i += kThreads) {
@@ -237,6 +245,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // Programmatic dependent launch: everything above (barriers, TMEM, bias, weight slab request) overlapped the tail
+  // of the previous kernel in the stream.  From here on we touch its outputs: wait for it, then let OUR dependent
+  // start its own prologue (after our wait, so everything older than this kernel is complete for it).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) CG_TL(P.tl, 33);
   const bool k3 = P.a.ksize == 3;
@@ -246,13 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(P.a.wpack) + (size_t)nchunkN * P.slab_bytes;
-      mbar_expect_tx(BAR(B_BFULL), P.slab_bytes);
-      for (uint32_t off = 0; off < P.slab_bytes; off += 32768u) {
-        uint32_t n = min(32768u, P.slab_bytes - off);
-        bulk_g2s(cg_smem_u32(sB) + off, wsrc + off, n, BAR(B_BFULL));
-      }
-      mbar_wait(BAR(B_BFULL), 0);
+      mbar_wait(BAR(B_BFULL), 0);  // weight slab (requested by thread 0 in the prologue)
       CG_TL(P.tl, 34);
       int tl_i = 0;
       (void)tl_i;
@@ -751,7 +758,26 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
   int gx = sms / kp.nN;
   if (gx < 1) gx = 1;
   if (gx > kp.ntiles) gx = kp.ntiles;
-  conv_tc_kernel<<<dim3(gx, kp.nN), kThreads, smem_bytes, cg_stream(stream)>>>(kp);
+  static int pdl = -1;
+  if (pdl < 0) {
+    const char* e = getenv("CG_NO_PDL");
+    pdl = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(gx, kp.nN);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = cg_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel, kp);
+  if (le != cudaSuccess) {
+    cg_set_error("cg_conv2d: launch failed: %s", cudaGetErrorString(le));
+    return CG_ERR_CUDA;
+  }
   CG_LAUNCH_CHECK("cg_conv2d");
   return CG_OK;
 }
