@@ -38,8 +38,10 @@ __global__ void avgpool_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict
   const int c8 = blockIdx.y, n = blockIdx.z;
   const int h = p / W, w = p - h * W;
   const float inv = 1.0f / (d * d);
-  float f[8];
-  cg_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + n * dy_ns + ((long long)c8 * Po * Po + (h / d) * Po + w / d) * 8)), f);
+  float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // F.avg_pool2d floors: rows/columns beyond (H/d)*d belong to no window (8x8 map pooled by 7, src/vae.py:79-83)
+  if (h / d < H / d && w / d < W / d)
+    cg_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + n * dy_ns + ((long long)c8 * Po * Po + (h / d) * Po + w / d) * 8)), f);
   bf16* o = dx + n * dx_ns + ((long long)c8 * H * W + p) * 8;
   float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (accumulate) cg_unpack8(*reinterpret_cast<const uint4*>(o), g);
@@ -426,7 +428,7 @@ inline int grid_for(long long work, int threads) {
 extern "C" int cg_avgpool_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, int32_t d,
                               int64_t x_ld, int64_t y_ld, int32_t pad_to, void* stream) {
   CG_ARCH_GUARD();
-  CG_REQUIRE(d >= 1 && H % d == 0 && W % d == 0 && H == W, "cg_avgpool_fwd: H=%d W=%d d=%d", H, W, d);
+  CG_REQUIRE(d >= 1 && d <= H && H == W, "cg_avgpool_fwd: H=%d W=%d d=%d", H, W, d);
   CG_REQUIRE(C % 8 == 0 && x_ld % 8 == 0 && y_ld % 8 == 0, "cg_avgpool_fwd: C/ld multiples of 8");
   const int Po = pad_to > 0 ? pad_to : H / d;
   CG_REQUIRE(Po >= H / d, "cg_avgpool_fwd: pad_to %d < %d", Po, H / d);
@@ -439,7 +441,7 @@ extern "C" int cg_avgpool_fwd(const void* x, void* y, int32_t N, int32_t H, int3
 extern "C" int cg_avgpool_bwd(const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t C, int32_t d,
                               int64_t dy_ld, int64_t dx_ld, int32_t pad_to, int32_t accumulate, void* stream) {
   CG_ARCH_GUARD();
-  CG_REQUIRE(d >= 1 && H % d == 0 && W % d == 0 && H == W, "cg_avgpool_bwd: H=%d W=%d d=%d", H, W, d);
+  CG_REQUIRE(d >= 1 && d <= H && H == W, "cg_avgpool_bwd: H=%d W=%d d=%d", H, W, d);
   CG_REQUIRE(C % 8 == 0 && dy_ld % 8 == 0 && dx_ld % 8 == 0, "cg_avgpool_bwd: C/ld multiples of 8");
   const int Po = pad_to > 0 ? pad_to : H / d;
   avgpool_bwd_kernel<<<dim3(cg_ceil_div(H * W, 256), C / 8, N), 256, 0, cg_stream(stream)>>>(

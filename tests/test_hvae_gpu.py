@@ -169,6 +169,23 @@ def test_abduct_forward_latents_counterfactual(name):
     assert rel_l2(ss.cpu(), ref["sample_scale"]) <= max(5e-3, 2 * rel_l2(emu["sample_scale"], ref["sample_scale"]))
 
 
+def test_counterfactual_mimic224_custom_arch():
+    """config 5 of BASELINE.json: the 224x224 DSCM abduct -> predict pass.  The shipped mimic192 arch cannot run at 224
+    (SURVEY section 0); the custom arch has odd resolutions (7 -> zero-padded 8, src/vae.py:130-132) and the
+    4-conv GELU block."""
+    from causalgen_b200 import counterfactual
+    CASES["mimic224"] = 1
+    cfg, sd, model, x, pa, cf = build("mimic224")
+    R = cfg.input_res
+    pa_full, cf_full = O.expand_parents(pa, R), O.expand_parents(cf, R)
+    ref = oracle_cf(cfg, sd, x, pa_full, cf_full, False)
+    emu = oracle_cf(cfg, sd, x, pa_full, cf_full, True)
+    eps = [e.to(DEV) for e in ref["tape"].drawn]
+    cf_x, _ = counterfactual(model, x.to(DEV), pa.to(DEV), cf.to(DEV), t_abduct=0.9, eps=[eps])
+    assert cf_x.shape == (1, 1, 224, 224)
+    assert_pixels(cf_x.cpu(), ref["cf"], emu["cf"], "mimic224 cf_x")
+
+
 def test_counterfactual_particles():
     from causalgen_b200 import counterfactual
     cfg, sd, model, x, pa, cf = build("tiny_ukbb")

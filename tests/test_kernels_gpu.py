@@ -330,6 +330,18 @@ def test_pool_and_upsample():
     y8 = torch.ones(N, C // 8, 8, 8, 8, device=DEV, dtype=torch.bfloat16)
     L.check(lib.cg_avgpool_fwd(x14.data_ptr(), y8.data_ptr(), N, 14, 14, C, 2, ns_of(x14), ns_of(y8), 8, stream()))
     assert_close(to_nchw(y8, C), F.pad(F.avg_pool2d(to_nchw(x14, C), 2, 2), [0, 1, 0, 1]), 1e-2, "pool+pad")
+    # F.avg_pool2d floors: an 8x8 map (7 zero-padded to 8) pooled by 7 -> 1x1 over the top-left 7x7 window
+    x8 = nhwc_bf16(rnd(N, C, 8, 8, seed=7))
+    y1 = zeros(1)
+    L.check(lib.cg_avgpool_fwd(x8.data_ptr(), y1.data_ptr(), N, 8, 8, C, 7, ns_of(x8), ns_of(y1), 0, stream()))
+    xr = to_nchw(x8, C).requires_grad_(True)
+    pooled = F.avg_pool2d(xr, 7, 7)
+    assert_close(to_nchw(y1, C), pooled, 1e-2, "pool 8 by 7")
+    dy1 = nhwc_bf16(rnd(N, C, 1, 1, seed=8))
+    dx8 = torch.ones_like(x8)
+    L.check(lib.cg_avgpool_bwd(dy1.data_ptr(), dx8.data_ptr(), N, 8, 8, C, 7, ns_of(dy1), ns_of(dx8), 0, 0, stream()))
+    pooled.backward(to_nchw(dy1, C))
+    assert_close(to_nchw(dx8, C), xr.grad, 1e-2, "pool bwd 8 by 7")
     # nearest upsample + learned bias, integer and 7->8 style factors
     for hi, ho in ((6, 12), (1, 4), (7, 8), (8, 14)):
         xs = nhwc_bf16(rnd(N, C, hi, hi, seed=4))
