@@ -755,9 +755,17 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
   kp.dbg = dbg;
   kp.tl = cg_tl_ptr;
   const int sms = cg_device_sms();
+  // CTAs along the pixel axis.  Small problems keep >= min_tiles tiles per CTA: the prologue (barriers, TMEM, weight
+  // slab) is paid once per CTA, and the SMs left free run the kernels of the other lanes / weight-gradient streams.
+  static int min_tiles = -1;
+  if (min_tiles < 0) {
+    const char* e = getenv("CG_CONV_MIN_TILES");
+    min_tiles = e ? atoi(e) : 2;
+    if (min_tiles < 1) min_tiles = 1;
+  }
   int gx = sms / kp.nN;
   if (gx < 1) gx = 1;
-  if (gx > kp.ntiles) gx = kp.ntiles;
+  if (gx > (kp.ntiles + min_tiles - 1) / min_tiles) gx = (kp.ntiles + min_tiles - 1) / min_tiles;
   static int pdl = -1;
   if (pdl < 0) {
     const char* e = getenv("CG_NO_PDL");
