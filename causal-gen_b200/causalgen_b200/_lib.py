@@ -25,7 +25,7 @@ class Seg(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("add", C.c_void_p), ("add2", C.c_void_p), ("mul", C.c_void_p),
                 ("ns", C.c_int64), ("add_ns", C.c_int64), ("add2_ns", C.c_int64), ("mul_ns", C.c_int64),
                 ("c0", C.c_int32), ("cn", C.c_int32), ("dtype", C.c_int32), ("mul_act", C.c_int32),
-                ("out_act", C.c_int32), ("_pad", C.c_int32)]
+                ("out_act", C.c_int32), ("_pad", C.c_int32), ("act_copy", C.c_void_p), ("act_copy_ns", C.c_int64)]
 
 
 class ConvArgs(C.Structure):

@@ -171,12 +171,16 @@ class BlockLayers:
         # is stored already activated by the producing conv: its consumers (next conv, weight gradient) skip
         # the pre-activation pass and the data-gradient mask reads the same tensor.
         self.mid_out_act = L.ACT_RELU if mod.light else L.ACT_NONE
+        # GELU'(y) needs the raw y, so a GELU block stores BOTH: y (for the data-gradient factor) and gelu(y) (input of
+        # the next conv and of its weight gradient) -- the intermediates are 4x narrower than the block, the second
+        # store is cheap and removes every in-kernel GELU pass over them.
+        self.mid_dual = not mod.light
         centre = (res == 1 and mod.ksize == 3)
         convs = mod.convs
         self.layers: List[ConvLayer] = []
         for i, c in enumerate(convs):
             srcs = list(src_logical) if i == 0 else [c.weight.shape[1]]
-            act_i = L.ACT_NONE if (i > 0 and self.mid_out_act != L.ACT_NONE) else self.act
+            act_i = L.ACT_NONE if (i > 0 and (self.mid_out_act != L.ACT_NONE or self.mid_dual)) else self.act
             self.layers.append(ConvLayer(eng.table, c.weight, c.bias, srcs, act_i,
                                          centre_only=centre and c.weight.shape[2] == 3,
                                          grad_srcs=(grad_srcs if i == 0 else None)))
@@ -265,13 +269,20 @@ class Engine:
         """reference Block.forward (src/vae.py:73-84) without the pooling"""
         r = Rec()
         r.bl, r.srcs, r.N, r.H, r.W = bl, srcs, N, H, W
-        r.mids = []
+        r.mids = []       # what the data gradient multiplies by act'(.)
+        r.mids_in = []    # what the next conv / its weight gradient consume (already activated when possible)
         cur = srcs
         for layer in bl.layers[:-1]:
             mid = new_act(N, H, W, layer.cout_l, self.device)
-            prog.add(layer.forward(cur, [SegSpec(mid, 0, out_act=bl.mid_out_act)], N, H, W))
+            if bl.mid_dual:
+                mid_a = new_act(N, H, W, layer.cout_l, self.device)
+                prog.add(layer.forward(cur, [SegSpec(mid, 0, out_act=bl.act, act_copy=mid_a)], N, H, W))
+            else:
+                mid_a = mid
+                prog.add(layer.forward(cur, [SegSpec(mid, 0, out_act=bl.mid_out_act)], N, H, W))
             r.mids.append(mid)
-            cur = [mid]
+            r.mids_in.append(mid_a)
+            cur = [mid_a]
         last = bl.layers[-1]
         r.proj_out = None
         if final_segs is None:
@@ -457,7 +468,7 @@ class Engine:
         mul/mul_act are filled in here.  Weight/bias gradients accumulate into the flat bucket."""
         bl = r.bl
         N, H, W = r.N, r.H, r.W
-        ins = [r.srcs] + [[m] for m in r.mids]
+        ins = [r.srcs] + [[m] for m in r.mids_in]
         cur_dy = dy
         for li in range(len(bl.layers) - 1, -1, -1):
             layer = bl.layers[li]
@@ -465,7 +476,7 @@ class Engine:
             prog.add(layer.wgrad(srcs, cur_dy, self.g(layer.weight), self.g(layer.bias), N, H, W))
             if li > 0:
                 dmid = new_act(N, H, W, layer.src_logical[0], self.device)
-                prog.add(layer.dgrad(0, cur_dy, SegSpec(dmid, 0, mul=srcs[0], mul_act=bl.act), N, H, W))
+                prog.add(layer.dgrad(0, cur_dy, SegSpec(dmid, 0, mul=r.mids[li - 1], mul_act=bl.act), N, H, W))
                 cur_dy = dmid
             else:
                 for i, sg in enumerate(dsrc):

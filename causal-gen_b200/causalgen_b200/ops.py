@@ -96,6 +96,7 @@ class SegSpec:
     mul_act: int = L.ACT_NONE
     add2: Optional[View] = None
     out_act: int = L.ACT_NONE   # activation applied to the stored value (consumer-side pre-activation hoisted)
+    act_copy: Optional[View] = None  # when set: `out` gets the raw value, act_copy gets out_act(value)
 
 
 class PackTable:
@@ -198,6 +199,8 @@ class ConvLayer:
             s.mul_ns = sg.mul.ns if sg.mul is not None else 0
             s.mul_act = sg.mul_act
             s.out_act = sg.out_act
+            s.act_copy = sg.act_copy.ptr if sg.act_copy is not None else None
+            s.act_copy_ns = sg.act_copy.ns if sg.act_copy is not None else 0
 
     def forward(self, srcs: Sequence[View], segs: Sequence[SegSpec], N, H, W) -> L.Launch:
         assert [s.C for s in srcs] == self.src_pad, ([s.C for s in srcs], self.src_pad)

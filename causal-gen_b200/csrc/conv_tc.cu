@@ -154,9 +154,10 @@ __device__ __forceinline__ uint4 act8(uint4 u, int act) {
 // Straight-line epilogue of one 16-column chunk for the common case (bf16 destination, all 16 columns live,
 // every fused operand staged in shared memory, ReLU-type activations): no data-dependent branches, invalid
 // (out-of-image) lanes compute on whatever their shared-memory slot holds and only the store is predicated.
-template <bool MUL, bool ADD, bool ADD2, bool ORELU>
+template <bool MUL, bool ADD, bool ADD2, int OACT, bool COPY>
 __device__ __forceinline__ void epi_chunk_fast(float (&v)[16], const uint8_t* e0, int eslot, int k_mul, int k_add,
-                                               int k_add2, const float* bias, bf16* op, long long HW8, bool valid) {
+                                               int k_add2, const float* bias, bf16* op, bf16* op2, long long HW8,
+                                               bool valid) {
   if (bias != nullptr) {
 #pragma unroll
     for (int q = 0; q < 16; q += 4) {
@@ -182,12 +183,19 @@ __device__ __forceinline__ void epi_chunk_fast(float (&v)[16], const uint8_t* e0
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[8 * h + i] += x[i];
     }
-    if (ORELU) {
+    if (COPY) {  // raw value to the primary destination, activated value to the copy
+      const uint4 o = cg_pack8(v + 8 * h);
+      if (valid) *reinterpret_cast<uint4*>(op + h * HW8) = o;
+    }
+    if (OACT == CG_ACT_RELU) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[8 * h + i] = fmaxf(v[8 * h + i], 0.f);
+    } else if (OACT == CG_ACT_GELU) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[8 * h + i] = cg_gelu(v[8 * h + i]);
     }
     const uint4 o = cg_pack8(v + 8 * h);
-    if (valid) *reinterpret_cast<uint4*>(op + h * HW8) = o;
+    if (valid) *reinterpret_cast<uint4*>((COPY ? op2 : op) + h * HW8) = o;
   }
 }
 
@@ -379,7 +387,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       int col, sgi, lc, cnt;        // sgi < 0: chunk has no destination (padding / beyond cout)
       int k_add, k_add2, k_mul;     // -2 absent, -1 read from global memory, >= 0 staged E slot
       int dtype, mul_act, out_act;
-      int fast;                     // -1: generic path; else bit0 mul, bit1 add, bit2 add2, bit3 relu-on-store
+      int fast;                     // -1: generic path; else bit0 mul, bit1 add, bit2 add2, bit3 relu, bit4 gelu, bit5 copy
+      uint8_t* out2;                // act_copy destination (+ plane offset) or nullptr
+      long long ns2;                // its sample stride
       uint8_t* out;                 // bf16: ptr + (lc/8) planes; fp32: ptr + lc floats
       long long ns;
     } plan[2];
@@ -395,6 +405,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       pl.out_act = CG_ACT_NONE;
       pl.fast = -1;
       pl.out = nullptr;
+      pl.out2 = nullptr;
+      pl.ns2 = 0;
       pl.ns = 0;
       const int cg0 = nchunkN * Nc + pl.col;
       if (pl.col >= Nc || cg0 >= P.a.cout || (P.dbg & 8)) continue;
@@ -411,6 +423,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         pl.ns = sg.ns;
         pl.out = reinterpret_cast<uint8_t*>(sg.ptr) +
                  (sg.dtype == CG_F32 ? (long long)lc * 4 : (long long)(lc >> 3) * P.HW8 * 2);
+        if (sg.act_copy != nullptr) {
+          pl.out2 = reinterpret_cast<uint8_t*>(sg.act_copy) + (long long)(lc >> 3) * P.HW8 * 2;
+          pl.ns2 = sg.act_copy_ns;
+        }
         if (sg.add != nullptr) pl.k_add = -1;
         if (sg.add2 != nullptr) pl.k_add2 = -1;
         if (sg.mul != nullptr) pl.k_mul = -1;
@@ -421,10 +437,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             else pl.k_mul = k;
           }
         if (sg.dtype == CG_BF16 && pl.cnt == 16 && pl.k_add != -1 && pl.k_add2 != -1 && pl.k_mul != -1 &&
-            (pl.k_mul == -2 || sg.mul_act == CG_ACT_RELU) && (sg.out_act == CG_ACT_NONE || sg.out_act == CG_ACT_RELU) &&
-            !(pl.k_mul >= 0 && pl.k_add2 >= 0))
+            (pl.k_mul == -2 || sg.mul_act == CG_ACT_RELU) && !(pl.k_mul >= 0 && pl.k_add2 >= 0))
           pl.fast = (pl.k_mul >= 0 ? 1 : 0) | (pl.k_add >= 0 ? 2 : 0) | (pl.k_add2 >= 0 ? 4 : 0) |
-                    (sg.out_act == CG_ACT_RELU ? 8 : 0);
+                    (sg.out_act == CG_ACT_RELU ? 8 : 0) | (sg.out_act == CG_ACT_GELU ? 16 : 0) |
+                    (sg.act_copy != nullptr ? 32 : 0);
         break;
       }
     }
@@ -465,17 +481,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const uint8_t* e0 = e_row + (pl.col >> 3) * kPlane1;
           const float* bp = has_bias ? s_bias + pl.col : nullptr;
           bf16* op = reinterpret_cast<bf16*>(pl.out) + n * pl.ns + hw * 8;
-#define CG_EPI(code, M, A, A2, R) \
-  case code: epi_chunk_fast<M, A, A2, R>(acc[j], e0, eslot, pl.k_mul, pl.k_add, pl.k_add2, bp, op, P.HW8, valid); break;
+          bf16* op2 = reinterpret_cast<bf16*>(pl.out2) + n * pl.ns2 + hw * 8;  // only dereferenced by COPY variants
+          bool done = true;
+#define CG_EPI(code, M, A, A2, OA, CP)                                                                          \
+  case code:                                                                                                    \
+    epi_chunk_fast<M, A, A2, OA, CP>(acc[j], e0, eslot, pl.k_mul, pl.k_add, pl.k_add2, bp, op, op2, P.HW8, valid); \
+    break;
           switch (pl.fast) {
-            CG_EPI(0, false, false, false, false) CG_EPI(8, false, false, false, true)
-            CG_EPI(2, false, true, false, false) CG_EPI(10, false, true, false, true)
-            CG_EPI(6, false, true, true, false) CG_EPI(14, false, true, true, true)
-            CG_EPI(1, true, false, false, false) CG_EPI(3, true, true, false, false)
-            default: break;
+            CG_EPI(0, false, false, false, 0, false) CG_EPI(8, false, false, false, 1, false)
+            CG_EPI(16, false, false, false, 2, false) CG_EPI(48, false, false, false, 2, true)
+            CG_EPI(40, false, false, false, 1, true)
+            CG_EPI(2, false, true, false, 0, false) CG_EPI(10, false, true, false, 1, false)
+            CG_EPI(6, false, true, true, 0, false) CG_EPI(14, false, true, true, 1, false)
+            CG_EPI(1, true, false, false, 0, false) CG_EPI(3, true, true, false, 0, false)
+            default: done = false; break;
           }
 #undef CG_EPI
-          continue;
+          if (done) continue;
         }
         if (!valid) continue;
         float* v = acc[j];
@@ -523,6 +545,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[h8 + i] += x[i];
           }
+          if (pl.out2 != nullptr) {  // raw value first, the activated copy goes to act_copy
+            bf16* orw = reinterpret_cast<bf16*>(pl.out) + n * pl.ns + (long long)(h8 >> 3) * P.HW8 + hw * 8;
+            *reinterpret_cast<uint4*>(orw) = cg_pack8(v + h8);
+          }
           if (pl.out_act == CG_ACT_RELU) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[h8 + i] = fmaxf(v[h8 + i], 0.f);
@@ -530,7 +556,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[h8 + i] = cg_gelu(v[h8 + i]);
           }
-          if (pl.dtype == CG_F32) {  // fp32 statistics: row layout (pixel, channel), pitch ns
+          if (pl.out2 != nullptr) {
+            bf16* oc = reinterpret_cast<bf16*>(pl.out2) + n * pl.ns2 + (long long)(h8 >> 3) * P.HW8 + hw * 8;
+            *reinterpret_cast<uint4*>(oc) = cg_pack8(v + h8);
+          } else if (pl.dtype == CG_F32) {  // fp32 statistics: row layout (pixel, channel), pitch ns
             float* op = reinterpret_cast<float*>(pl.out) + ((long long)n * H * W + hw) * pl.ns + h8;
             *reinterpret_cast<float4*>(op) = make_float4(v[h8], v[h8 + 1], v[h8 + 2], v[h8 + 3]);
             *reinterpret_cast<float4*>(op + 4) = make_float4(v[h8 + 4], v[h8 + 5], v[h8 + 6], v[h8 + 7]);
@@ -687,6 +716,8 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
     CG_REQUIRE(sg.add == nullptr || (((uintptr_t)sg.add & 15) == 0 && sg.add_ns % 8 == 0), "cg_conv2d: seg %d add", s);
     CG_REQUIRE(sg.add2 == nullptr || (((uintptr_t)sg.add2 & 15) == 0 && sg.add2_ns % 8 == 0), "cg_conv2d: seg %d add2", s);
     CG_REQUIRE(sg.mul == nullptr || (((uintptr_t)sg.mul & 15) == 0 && sg.mul_ns % 8 == 0), "cg_conv2d: seg %d mul", s);
+    CG_REQUIRE(sg.act_copy == nullptr || (sg.dtype == CG_BF16 && ((uintptr_t)sg.act_copy & 15) == 0 && sg.act_copy_ns % 8 == 0),
+               "cg_conv2d: seg %d act_copy needs a bf16 segment and 16-byte alignment", s);
     for (int t = 0; t < s; ++t)
       CG_REQUIRE(sg.c0 >= a->seg[t].c0 + a->seg[t].cn || a->seg[t].c0 >= sg.c0 + sg.cn,
                  "cg_conv2d: segments %d and %d overlap (output channel ranges must be disjoint)", t, s);

@@ -71,6 +71,10 @@ typedef struct {
   int32_t out_act;  /* activation applied to the finished value before the store: lets a producer write
                        act(y) when every consumer of y applies the same pre-activation (Block, src/vae.py:49-56) */
   int32_t _pad;
+  void* act_copy;   /* optional second bf16 planar destination: when set, `ptr` receives the raw value and
+                       act_copy receives out_act(value) (GELU blocks need both: act(y) feeds the next conv and
+                       the weight gradient, y feeds act'(y) in the data gradient, src/vae.py:57-68) */
+  int64_t act_copy_ns;
 } cg_seg;
 
 typedef struct {

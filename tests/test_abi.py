@@ -34,8 +34,8 @@ def test_struct_layouts_match_the_header_sizes():
     """ctypes mirrors of the ABI structs: sizes that the C side static-asserts through its own layout"""
     from causalgen_b200 import _lib as L
     assert ctypes.sizeof(L.Src) == 24
-    assert ctypes.sizeof(L.Seg) == 88
-    assert ctypes.sizeof(L.ConvArgs) == 32 + 3 * 24 + 4 * 88 + 24
+    assert ctypes.sizeof(L.Seg) == 104
+    assert ctypes.sizeof(L.ConvArgs) == 32 + 3 * 24 + 4 * 104 + 24
     assert ctypes.sizeof(L.PackDesc) % 8 == 0
     # weight-slab planner is pure host arithmetic and must be callable without a GPU
     lib = L.load()

@@ -132,6 +132,14 @@ def test_conv_segments_add_and_fp32_split():
         layer.forward(views, [SegSpec(stats, 0), SegSpec(ya, 32, add=h, out_act=act_id)], N, H, W)(stream())
         torch.cuda.synchronize()
         assert_close(to_nchw(ya.t, 48), act_fn(act_id)(ref[:, 32:] + to_nchw(h.t, 48)), 1e-2, f"out_act {act_id}")
+        # dual store: raw value + activated copy (GELU blocks keep both), with and without a fused addend
+        for addend in (None, h):
+            raw, cp = new_act(N, H, W, 48, DEV), new_act(N, H, W, 48, DEV)
+            layer.forward(views, [SegSpec(stats, 0), SegSpec(raw, 32, add=addend, out_act=act_id, act_copy=cp)], N, H, W)(stream())
+            torch.cuda.synchronize()
+            want = ref[:, 32:] + (to_nchw(h.t, 48) if addend is not None else 0)
+            assert_close(to_nchw(raw.t, 48), want, 1e-2, f"act_copy raw {act_id}")
+            assert_close(to_nchw(cp.t, 48), act_fn(act_id)(want), 1e-2, f"act_copy copy {act_id}")
 
 
 @pytest.mark.parametrize("case", [(2, 16, 16, [32], 0, 16, 3, 1), (2, 24, 24, [48, 48], 4, 8, 3, 2),
