@@ -62,12 +62,39 @@ __device__ __forceinline__ void cg_tl_mark(unsigned long long* tl, int k) {
 #endif
 typedef __nv_bfloat16 bf16;
 
-__device__ __forceinline__ float cg_gelu(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// nn.GELU() (exact erf form, src/vae.py:58) for bf16 activations.  erf through Abramowitz-Stegun 7.1.25
+// (|error| <= 2.5e-5, one reciprocal + one exp2 + three FMAs): Phi is off by <= 1.3e-5, far below the 2^-9 relative
+// step of the bf16 value that is stored, at about a third of the instructions of erff/expf.  One shared
+// exp(-x^2/2) serves both Phi(x) and the density of the derivative.
+__device__ __forceinline__ float cg_ex2_approx(float v) {  // MUFU.EX2
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float cg_rcp_approx(float v) {  // MUFU.RCP
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void cg_phi_pdf(float x, float& cdf, float& pdf) {
+  const float ax = fabsf(x);
+  const float e = cg_ex2_approx(-0.72134752044448170f * x * x);          // exp(-x^2 / 2)
+  const float t = cg_rcp_approx(fmaf(0.33267074000000000f, ax, 1.0f));   // 1 / (1 + 0.47047 |x| / sqrt(2))
+  const float poly = t * fmaf(t, fmaf(t, 0.7478556f, -0.0958798f), 0.3480242f);
+  const float half_erfc = 0.5f * poly * e;                          // 0.5 * (1 - erf(|x| / sqrt(2)))
+  cdf = x >= 0.0f ? 1.0f - half_erfc : half_erfc;
+  pdf = 0.39894228040143268f * e;
+}
+__device__ __forceinline__ float cg_gelu(float x) {
+  float cdf, pdf;
+  cg_phi_pdf(x, cdf, pdf);
+  return x * cdf;
+}
 __device__ __forceinline__ float cg_dgelu(float x) {
   // d/dx [x Phi(x)] = Phi(x) + x phi(x)
-  float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float cdf, pdf;
+  cg_phi_pdf(x, cdf, pdf);
+  return fmaf(x, pdf, cdf);
 }
 __device__ __forceinline__ float cg_act(float x, int act) {
   return act == CG_ACT_RELU ? fmaxf(x, 0.0f) : (act == CG_ACT_GELU ? cg_gelu(x) : x);

@@ -199,6 +199,9 @@ __device__ __forceinline__ void epi_chunk_fast(float (&v)[16], const uint8_t* e0
   }
 }
 
+// DUAL: compiled with the act_copy (raw + activated) destinations of GELU blocks; the lean instance serves every
+// launch without them (all of UKBB) and keeps the epilogue code small.
+template <bool DUAL>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -423,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         pl.ns = sg.ns;
         pl.out = reinterpret_cast<uint8_t*>(sg.ptr) +
                  (sg.dtype == CG_F32 ? (long long)lc * 4 : (long long)(lc >> 3) * P.HW8 * 2);
-        if (sg.act_copy != nullptr) {
+        if (DUAL && sg.act_copy != nullptr) {
           pl.out2 = reinterpret_cast<uint8_t*>(sg.act_copy) + (long long)(lc >> 3) * P.HW8 * 2;
           pl.ns2 = sg.act_copy_ns;
         }
@@ -489,12 +492,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     break;
           switch (pl.fast) {
             CG_EPI(0, false, false, false, 0, false) CG_EPI(8, false, false, false, 1, false)
-            CG_EPI(16, false, false, false, 2, false) CG_EPI(48, false, false, false, 2, true)
-            CG_EPI(40, false, false, false, 1, true)
             CG_EPI(2, false, true, false, 0, false) CG_EPI(10, false, true, false, 1, false)
             CG_EPI(6, false, true, true, 0, false) CG_EPI(14, false, true, true, 1, false)
             CG_EPI(1, true, false, false, 0, false) CG_EPI(3, true, true, false, 0, false)
-            default: done = false; break;
+            default:
+              done = false;
+              if (DUAL) {
+                done = true;
+                switch (pl.fast) {
+                  CG_EPI(48, false, false, false, 2, true) CG_EPI(40, false, false, false, 1, true)
+                  CG_EPI(16, false, false, false, 2, false)
+                  default: done = false; break;
+                }
+              }
+              break;
           }
 #undef CG_EPI
           if (done) continue;
@@ -545,7 +556,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[h8 + i] += x[i];
           }
-          if (pl.out2 != nullptr) {  // raw value first, the activated copy goes to act_copy
+          if (DUAL && pl.out2 != nullptr) {  // raw value first, the activated copy goes to act_copy
             bf16* orw = reinterpret_cast<bf16*>(pl.out) + n * pl.ns + (long long)(h8 >> 3) * P.HW8 + hw * 8;
             *reinterpret_cast<uint4*>(orw) = cg_pack8(v + h8);
           }
@@ -556,7 +567,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[h8 + i] = cg_gelu(v[h8 + i]);
           }
-          if (pl.out2 != nullptr) {
+          if (DUAL && pl.out2 != nullptr) {
             bf16* oc = reinterpret_cast<bf16*>(pl.out2) + n * pl.ns2 + (long long)(h8 >> 3) * P.HW8 + hw * 8;
             *reinterpret_cast<uint4*>(oc) = cg_pack8(v + h8);
           } else if (pl.dtype == CG_F32) {  // fp32 statistics: row layout (pixel, channel), pitch ns
@@ -771,7 +782,9 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
   const int smem_bytes = kHdrBytes + kp.nst * kp.stage_bytes + kp.nest * kp.nE * e_slot_bytes(kp.Nc) + (int)kp.slab_bytes;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
     if (e != cudaSuccess) {
       cg_set_error("cg_conv2d: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return CG_ERR_CUDA;
@@ -812,7 +825,9 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel, kp);
+  bool dual = false;
+  for (int s = 0; s < a->nseg; ++s) dual = dual || a->seg[s].act_copy != nullptr;
+  cudaError_t le = dual ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, kp) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, kp);
   if (le != cudaSuccess) {
     cg_set_error("cg_conv2d: launch failed: %s", cudaGetErrorString(le));
     return CG_ERR_CUDA;
