@@ -10,7 +10,7 @@ from causalgen_b200.ops import ConvLayer, PackTable, SegSpec, View, new_act, pla
 DEV = "cuda"
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 only = sys.argv[2] if len(sys.argv) > 2 else None
-N = 32
+N = int(os.environ.get("MB_N", "32"))
 # name, H, cin list, cout, k, act, epilogue: none | add | mul | muladd
 CASES = [
     ("fwd 64->16 r96", 96, [64], 16, 3, 1, "none"),
@@ -31,6 +31,8 @@ CASES = [
     ("fwd 1x1 zfp 80->64 r96", 96, [16, 64], 64, 1, 0, "none"),
     ("fwd 48->160 r12 +res", 12, [48], 160, 3, 1, "add"),
     ("fwd 48->192 r6 +res", 6, [48], 192, 3, 1, "add"),
+    ("dgrad 1x1 192->192 r6 +add", 6, [192], 192, 1, 0, "add"),
+    ("dgrad 1x1 192->192 r12 +add", 12, [192], 192, 1, 0, "add"),
 ]
 def s(): return torch.cuda.current_stream().cuda_stream
 def timeit(fn):
