@@ -28,10 +28,10 @@ HBM_FALLBACK_GBS = 6650.0
 TENSOR_FALLBACK_TFS = 1400.0
 # conv FLOPs per image of one ELBO forward pass (measured on the reference with hooks);
 # a training step executes 3x (forward + data-gradient + weight-gradient)
-# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per conv_tc_kernel launch, averaged over the 1815
-# conv launches of two training steps at the given per-GPU batch: profiles/r1f_ncu_launches_bench_b128.csv
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per conv_tc_kernel launch, averaged over the 891
+# conv launches of one training step at the given per-GPU batch: profiles/r1h_ncu_launches_one_step_b128.csv
 # (ncu pass of this very command).  Below the algorithmic bytes because producer->consumer tensors hit the L2.
-CONV_DRAM_TRAFFIC_PER_LAUNCH = {("ukbb192", 128): 84.37e6}
+CONV_DRAM_TRAFFIC_PER_LAUNCH = {("ukbb192", 128): 85.92e6}
 FWD_GFLOP = {"ukbb192": 23.064, "mimic192": 9.127, "morphomnist": 0.0865, "cmnist": 0.0917, "mimic224": 12.460}
 CF_GFLOP = {"ukbb192": 47.670, "mimic192": 19.565, "morphomnist": 0.1845, "cmnist": 0.1924, "mimic224": 26.707}
 
