@@ -330,9 +330,12 @@ class Engine:
 
     def _decoder_fwd(self, prog: Program, N, pa: Dict[int, View], pa_sto: Dict[int, View], acts: Optional[Dict[int, View]],
                      given: Optional[Sequence[bool]] = None, want_z: bool = False, want_stats: bool = False,
-                     explicit_eps: bool = True, kl_rows: Optional[torch.Tensor] = None) -> Rec:
+                     explicit_eps: bool = True, kl_rows: Optional[torch.Tensor] = None,
+                     z_views: Optional[Sequence[View]] = None) -> Rec:
         """reference Decoder.forward (src/vae.py:222-301).  `given[i]` marks stochastic block i whose latent is
-        supplied by the caller (forward_latents); other stochastic blocks sample q (acts given) or p."""
+        supplied by the caller (forward_latents); other stochastic blocks sample q (acts given) or p.
+        `z_views[i]`: the given latent already lives on the device as a bf16 planar view (another decoder pass of
+        the same program produced it): used in place, no fp32 NCHW round trip."""
         dec = self.model.decoder
         zd = self.zd
         D = Rec()
@@ -392,7 +395,9 @@ class Engine:
             r.prior = self._block_fwd(prog, d.prior, p_src, N, res, res,
                                       final_segs=[SegSpec(r.pstat, 0), SegSpec(r.pfeat, 2 * zd)])
             # ---- posterior + latent (src/vae.py:265-291)
-            r.z = new_act(N, res, res, zd, self.device)
+            shared_z = (z_views is not None and st.stochastic and given is not None and ksto < len(given)
+                        and bool(given[ksto]))
+            r.z = z_views[ksto] if shared_z else new_act(N, res, res, zd, self.device)
             r.mode = 2
             r.eps = None
             la = None
@@ -402,9 +407,10 @@ class Engine:
                     prog.join()  # posterior statistics ready
                     r.mode = 0
                 elif is_given:
-                    zin = torch.zeros(N, zd, res, res, device=self.device, dtype=torch.float32)
-                    D.z_in[ksto] = zin
-                    prog.call("cg_nchw_f32_to_planar", zin.data_ptr(), r.z.ptr, N, zd, res * res, r.z.ns)
+                    if not shared_z:
+                        zin = torch.zeros(N, zd, res, res, device=self.device, dtype=torch.float32)
+                        D.z_in[ksto] = zin
+                        prog.call("cg_nchw_f32_to_planar", zin.data_ptr(), r.z.ptr, N, zd, res * res, r.z.ns)
                     r.mode = 3
                 else:
                     r.mode = 1
@@ -773,4 +779,41 @@ class Engine:
             prog.x_out.append(xo)
             prog.scale_out.append(so)
             prog.lik_args.append(la)
+        return prog
+
+    def build_counterfactual(self, N: int) -> Program:
+        """DSCM.forward hot lines (src/pgm/dscm.py:52-56) as ONE program: encoder + posterior decoder pass (abduction,
+        in-kernel Philox noise), two prior-only decoder passes on the abducted latents (counterfactual and observed
+        parents) reading the bf16 latents of the first pass in place, likelihood means, and the combine kernel."""
+        prog = Program(f"counterfactual(N={N})")
+        io = self._inputs(prog, N, with_x=True, n_pa=2)  # pa_in[0]: observed parents, pa_in[1]: counterfactual parents
+        prog.io = io
+        e = self._encoder_fwd(prog, io.x, N)
+        Da = self._decoder_fwd(prog, N, io.pa[0], io.pa_sto[0], e.acts, explicit_eps=False)
+        prog.D = Da
+        prog.seed_ctr = torch.zeros(1, dtype=torch.int64, device=self.device)
+        for la in Da.latent_args:
+            la.seed_dev = prog.seed_ctr.data_ptr()
+        zs = [r.z for r in Da.blocks if r.st.stochastic]
+        given = [True] * len(zs)
+        outs = []
+        for j in (1, 0):
+            D = self._decoder_fwd(prog, N, io.pa[j], io.pa_sto[j], None, given=given, z_views=zs)
+            xo = torch.zeros(N, self.C, self.R, self.R, device=self.device, dtype=torch.float32)
+            so = torch.zeros_like(xo)
+            la = self._lik_args(D.h, None, N)
+            if self.dmol:
+                prog.add(L.Launch("cg_dmol_predict", C.byref(la), 0, None, None, C.c_float(0.0), xo.data_ptr(),
+                                  so.data_ptr())).keep = (la, D)
+            else:
+                prog.add(L.Launch("cg_dgauss_sample", C.byref(la), xo.data_ptr(), so.data_ptr(), None,
+                                  C.c_float(0.0))).keep = (la, D)
+            outs.append((xo, so))
+        (cf_loc, cf_scale), (rec_loc, rec_scale) = outs
+        prog.cf_x = torch.zeros_like(cf_loc)
+        prog.acc = torch.zeros_like(cf_loc)
+        prog.acc2 = torch.zeros_like(cf_loc)
+        prog.call("cg_cf_combine", io.x.data_ptr(), rec_loc.data_ptr(), rec_scale.data_ptr(), cf_loc.data_ptr(),
+                  cf_scale.data_ptr(), prog.cf_x.data_ptr(), prog.acc.data_ptr(), prog.acc2.data_ptr(), io.x.numel())
+        prog.keep += [outs]
         return prog

@@ -293,6 +293,26 @@ def counterfactual(vae: HVAE, x: Tensor, pa: Tensor, cf_pa: Tensor, t_abduct: fl
                    eps: Optional[Sequence[Sequence[Tensor]]] = None):
     """abduct -> forward_latents(cf_pa) & forward_latents(pa) (one 2-parent-set pass) -> combine
     (src/pgm/dscm.py:47-72).  Returns (cf_x, var_cf_x or None)."""
+    if eps is None and not TRACE_ONLY:
+        # serving path: one fused program (abduction with in-kernel Philox noise, both decodes on the bf16 latents in
+        # place, combine); the explicit-eps path below keeps the reference's fp32 latent interface for parity tests
+        eng = vae.engine()
+        N = x.shape[0]
+        prog = vae._program(("cf", N), lambda: eng.build_counterfactual(N))
+        prog.io.x.copy_(x)
+        vae._load_parents(prog, prog.io, [pa, cf_pa])
+        vae._set_noise(prog.D, None, math.log(t_abduct) if t_abduct is not None else 0.0)
+        if particles > 1:
+            prog.acc.zero_()
+            prog.acc2.zero_()
+        eng.pack_weights()
+        for _ in range(particles):
+            prog.run()
+            prog.seed_ctr.add_(1)
+        if particles > 1:
+            mean = prog.acc / particles
+            return mean, (prog.acc2 - prog.acc ** 2 / particles) / particles  # src/pgm/dscm.py:68
+        return prog.cf_x.clone(), None
     lib = L.load()
     n = x.numel()
     acc = torch.zeros_like(x) if particles > 1 else None

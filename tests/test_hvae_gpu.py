@@ -201,6 +201,26 @@ def test_counterfactual_particles():
     assert float((v.cpu() - vref).abs().mean()) <= 1e-3 + 0.1 * float(vref.abs().mean())
 
 
+@pytest.mark.parametrize("name", ["tiny_ukbb", "tiny_morphomnist", "tiny_cmnist"])
+def test_counterfactual_fused_program_matches_reference_interface_path(name):
+    """serving path (one program, bf16 latents shared in place, in-kernel noise) against the path that goes through
+    the reference's fp32 latent interface (abduct -> forward_latents x2 -> combine), at a temperature where the
+    noise is negligible"""
+    from causalgen_b200 import counterfactual
+    cfg, sd, model, x, pa, cf = build(name)
+    xd, pad, cfd = x.to(DEV), pa.to(DEV), cf.to(DEV)
+    zero_eps = [torch.zeros_like(e).to(DEV) for e in draw_eps(cfg, sd, x, O.expand_parents(pa, cfg.input_res), 5)]
+    want, _ = counterfactual(model, xd, pad, cfd, t_abduct=1e-4, eps=[zero_eps])
+    got, var = counterfactual(model, xd, pad, cfd, t_abduct=1e-4)
+    torch.cuda.synchronize()
+    assert var is None and got.shape == x.shape
+    # the two paths round the abducted latents to bf16 at different points (1e-4-scaled noise flips last bits)
+    d = (got - want).abs()
+    assert float(d.mean()) <= 0.5 / 255 and float(d.max()) <= 6.0 / 255, (float(d.mean()), float(d.max()))
+    mean, var = counterfactual(model, xd, pad, cfd, t_abduct=1.0, particles=3)
+    assert bool(torch.isfinite(mean).all()) and bool((var >= -1e-6).all()) and float(var.mean()) > 0
+
+
 def test_counterfactual_graph_replay():
     """CUDA-graph replay of the abduct -> predict pass: null intervention returns the observation (both decodes
     share latents), a real intervention matches the eager helper up to the noise redrawn per call"""
