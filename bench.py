@@ -119,10 +119,21 @@ def dist_setup(n_gpus):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout is ONE JSON line: NCCL's banner / debug output (printed at NCCL_DEBUG >= VERSION) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # stdout is ONE JSON line: NCCL prints its version banner on stdout when the communicator is created, so fd 1
+        # points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            t = torch.zeros(1, device="cuda")
+            dist.all_reduce(t)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     else:
         torch.cuda.set_device(0)
     return world, rank, local
@@ -373,6 +384,7 @@ def main():
                                     "frac": gflop_step * value / 1e3 / tensor_tfs,
                                     "gflop_per_image_step": gflop_step}},
             "breakdown_ms": prof["families_ms"],
+            "hbm_gb_peak_train": round(torch.cuda.max_memory_allocated() / 1e9, 2),
         }
     # counterfactual inference throughput (abduct + 2x forward_latents + combine), replicas only
     if not args.no_cf:
@@ -418,6 +430,7 @@ def main():
                                          "ms_per_step": ms32 / n32, "batch_per_gpu": 32}
         del tr32
     if rank == 0:
+        line["hbm_gb_peak_total"] = round(torch.cuda.max_memory_allocated() / 1e9, 2)
         if world == 1 and not args.no_cpu:
             sec, n = cpu_port_step_time(args.config, sd_cpu, args.cpu_batch, args.cpu_seconds, os.cpu_count() or 1)
             line["cpu_baseline"] = {"value": args.cpu_batch / sec, "unit": "images/s", "cores": os.cpu_count() or 1,
