@@ -491,9 +491,11 @@ class Engine:
                     sg.mul, sg.mul_act = srcs[i], bl.act
                     prog.add(layer.dgrad(i, cur_dy, sg, N, H, W))
 
-    def _res_block_bwd(self, prog: Program, r: Rec, dout: View, extra: Optional[View] = None) -> View:
+    def _res_block_bwd(self, prog: Program, r: Rec, dout: View, extra: Optional[View] = None,
+                       dx_out: Optional[View] = None) -> View:
         """Backward of a residual Block (encoder block / decoder `conv`), incl. pooling.
-        Returns d(input).  `extra` is one more gradient contribution to the block input."""
+        Returns d(input) (written into `dx_out` when given).  `extra` is one more gradient contribution to the block
+        input."""
         bl = r.bl
         N, H, W = r.N, r.H, r.W
         st = getattr(r, "st", None)
@@ -502,7 +504,7 @@ class Engine:
             dy = new_act(N, H, W, r.y.logical, self.device)
             prog.call("cg_avgpool_bwd", dout.ptr, dy.ptr, N, H, W, dy.C, st.down, dout.ns, dy.ns, st.res_out, 0)
         x = r.srcs[0]
-        dx = new_act(N, H, W, x.logical, self.device)
+        dx = dx_out if dx_out is not None else new_act(N, H, W, x.logical, self.device)
         if bl.proj is not None:
             skip = new_act(N, H, W, x.logical, self.device)
             prog.add(bl.proj.wgrad(r.srcs, dy, self.g(bl.proj.weight), self.g(bl.proj.bias), N, H, W))
@@ -525,21 +527,19 @@ class Engine:
         for r in reversed(D.blocks):
             d, st = r.d, r.st
             res = st.res
-            # conv block
-            dh3 = self._res_block_bwd(prog, r.conv, dh_out)
             # gradient of the prior's last conv output: [dp stats (2*zd) | d p_feat (cin)]
             DP = new_act(N, res, res, 2 * zd + st.cin, self.device)
             dz = new_act(N, res, res, zd, self.device)
             dz_written = False
             dpf = DP.slice(2 * zd, round16(st.cin), st.cin)
+            # conv block.  Without a z_feat_proj consumer (last block) d p_feat IS d h3 (h3 = h + p_feat + ...): the block
+            # input gradient is written straight into that slice instead of being copied there
+            dh3 = self._res_block_bwd(prog, r.conv, dh_out, dx_out=dpf if r.zs_out is None else None)
             if r.zs_out is not None:
                 prog.add(d.zfp.wgrad([r.z, r.pfeat], dzs_out, self.g(d.zfp.weight), self.g(d.zfp.bias), N, res, res))
                 prog.add(d.zfp.dgrad(0, dzs_out, SegSpec(dz, 0), N, res, res))
                 dz_written = True
                 prog.add(d.zfp.dgrad(1, dzs_out, SegSpec(dpf, 0, add=dh3), N, res, res))
-            else:
-                w8, o8 = round16(st.cin) // 8, (2 * zd) // 8
-                prog.add(PyOp(lambda a=DP.t, b=dh3.t, w8=w8, o8=o8: a[:, o8:o8 + w8].copy_(b[:, :w8]), "copy_dpfeat"))
             # z_proj (no activation on its input)
             prog.add(d.z_proj.wgrad([r.z, r.pa], dh3, self.g(d.z_proj.weight), self.g(d.z_proj.bias), N, res, res))
             prog.add(d.z_proj.dgrad(0, dh3, SegSpec(dz, 0, add=dz if dz_written else None), N, res, res))
