@@ -628,6 +628,7 @@ int cg_wgrad_mma_try(const cg_wgrad_args* a, void* stream, int* handled) {
   MParams kp;
   kp.a = *a;
   kp.tl = cg_tl_ptr;
+  kp.ny = 0;
   const int wide_planes = shift_a ? NT : MT * 2, narrow_planes = shift_a ? MT * 2 : NT;
   const int wch = wide_planes * 8;
   kp.nchunks = 0;
