@@ -514,6 +514,19 @@ int launch_mma(const MParams& kp, int gx, int smem_bytes, cudaStream_t st) {
 
 // Returns CG_OK with *handled = 1 when the problem was launched on the mma.sync kernel, *handled = 0 when the
 // caller must use the tcgen05 kernel (1x1 / centre-tap / 1-pixel problems, GELU, both operands wide).
+// Pixel tiles per CTA (lower bound).  Weight gradients are off the critical path (side streams): a small grid costs
+// them little (one accumulator flush per CTA anyway) and leaves SMs to the latency-bound data-gradient chain running
+// next to them.  Measured on UKBB-192: 4 -> 24 tiles = 16.9 -> 15.9 ms per step at batch 32, 48.1 -> 47.8 at 128.
+static int wgrad_min_tiles() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CG_WGRAD_MIN_TILES");
+    v = e ? atoi(e) : 24;
+    if (v < 1) v = 1;
+  }
+  return v;
+}
+
 static bool mma1_eligible(const cg_wgrad_args* a) {
   return a->ksize == 1 && a->taps == 1 && !(a->H == 1 && a->W == 1) &&
          (a->act == CG_ACT_NONE || a->act == CG_ACT_RELU);
@@ -586,7 +599,7 @@ static int wgrad_mma_1x1(const cg_wgrad_args* a, void* stream, int* handled) {
   if (kp.nst < 8) return CG_OK;
   const int smem_bytes = kHdrM + kp.nst * kp.stage_bytes;
   int gx = cg_device_sms() / gy;
-  if (gx > (kp.ntiles + 3) / 4) gx = (kp.ntiles + 3) / 4;
+  if (gx > (kp.ntiles + wgrad_min_tiles() - 1) / wgrad_min_tiles()) gx = (kp.ntiles + wgrad_min_tiles() - 1) / wgrad_min_tiles();
   if (gx < 1) gx = 1;
   cudaStream_t st = cg_stream(stream);
   int rc;
@@ -684,9 +697,8 @@ int cg_wgrad_mma_try(const cg_wgrad_args* a, void* stream, int* handled) {
   if (kp.nst > kMaxStagesM) kp.nst = kMaxStagesM;
   const int smem_bytes = kHdrM + kp.nst * kp.stage_bytes;
   // CTAs along the pixel axis share the chunk's gradient through coalesced atomics
-  // one CTA per SM; each CTA ends with one flush of its whole accumulator tile: keep >= 4 tiles of work per CTA
   int gx = cg_device_sms() / kp.nchunks;
-  if (gx > (kp.ntiles + 3) / 4) gx = (kp.ntiles + 3) / 4;
+  if (gx > (kp.ntiles + wgrad_min_tiles() - 1) / wgrad_min_tiles()) gx = (kp.ntiles + wgrad_min_tiles() - 1) / wgrad_min_tiles();
   if (gx < 1) gx = 1;
   cudaStream_t st = cg_stream(stream);
   int rc = CG_ERR_UNSUPPORTED;
