@@ -75,6 +75,7 @@ class Program:
         self.sides = None
         self.aux = None
         self.cur_lane = 0
+        self._plan = None
 
     def fork(self):
         self.launches.append(Marker("fork"))
@@ -121,44 +122,66 @@ class Program:
         if self.sides is None:
             self.sides = [torch.cuda.Stream() for _ in range(SIDE_STREAMS)]
             self.aux = torch.cuda.Stream()
-        lanes = (main, self.aux)
-        raw = (s, self.aux.cuda_stream)
-        ev = [None, None]            # per lane: event covering everything issued on it so far (None = stale)
-        seen = [[None, None] for _ in self.sides]
-        k, aux_used = 0, False
-
-        def event_of(lane):
-            if ev[lane] is None:
-                ev[lane] = torch.cuda.Event()
-                ev[lane].record(lanes[lane])
-            return ev[lane]
-
-        for ln in self.launches:
-            if isinstance(ln, Marker):
-                if ln.kind == "fork":
-                    self.aux.wait_event(event_of(0))
-                    ev[1] = None  # the lane now also covers main's work: a cached older event would miss it
-                    aux_used = True
-                else:
-                    main.wait_event(event_of(1))
-                    ev[0] = None
-                continue
-            if ln.side:
-                j = k % len(self.sides)
-                k += 1
-                e = event_of(ln.lane)
-                if seen[j][ln.lane] is not e:
-                    self.sides[j].wait_event(e)
-                    seen[j][ln.lane] = e
-                ln(self.sides[j].cuda_stream)
+        streams = [main, self.aux] + self.sides          # stream ids of plan_streams(): 0 main, 1 aux, 2.. pool
+        raw = [s, self.aux.cuda_stream] + [st.cuda_stream for st in self.sides]
+        events = {}
+        if self._plan is None or self._plan[0] != len(self.launches):
+            self._plan = (len(self.launches), plan_streams(self.launches, len(self.sides)))
+        for act in self._plan[1]:
+            if act[0] == "record":
+                events[act[2]] = torch.cuda.Event()
+                events[act[2]].record(streams[act[1]])
+            elif act[0] == "wait":
+                streams[act[1]].wait_event(events[act[2]])
             else:
-                ln(raw[ln.lane])
-                ev[ln.lane] = None
-        if aux_used:
-            main.wait_stream(self.aux)
-        if k:
-            for st in self.sides:
-                main.wait_stream(st)
+                self.launches[act[2]](raw[act[1]])
+
+
+def plan_streams(launches, n_sides):
+    """Pure scheduling of a recorded program onto streams (0 = main, 1 = auxiliary lane, 2.. = weight-gradient pool).
+    Yields ("record", stream, event_id) / ("wait", stream, event_id) / ("launch", stream, launch_index) in issue
+    order; ends with every stream joined back into main.  Kept free of CUDA so the dependency logic is unit-tested
+    on the CPU (tests/test_host_logic.py)."""
+    ev = [None, None]        # per lane: id of an event covering everything issued on it so far (None = stale)
+    seen = [[None, None] for _ in range(n_sides)]
+    next_id = [0]
+    out = []
+
+    def event_of(lane):
+        if ev[lane] is None:
+            ev[lane] = next_id[0]
+            next_id[0] += 1
+            out.append(("record", lane, ev[lane]))
+        return ev[lane]
+
+    k, aux_used = 0, False
+    for idx, ln in enumerate(launches):
+        if isinstance(ln, Marker):
+            if ln.kind == "fork":
+                out.append(("wait", 1, event_of(0)))
+                ev[1] = None  # the lane now also covers main's work: a cached older event would miss it
+                aux_used = True
+            else:
+                out.append(("wait", 0, event_of(1)))
+                ev[0] = None
+            continue
+        if ln.side:
+            j = k % n_sides
+            k += 1
+            e = event_of(ln.lane)
+            if seen[j][ln.lane] != e:
+                out.append(("wait", 2 + j, e))
+                seen[j][ln.lane] = e
+            out.append(("launch", 2 + j, idx))
+        else:
+            out.append(("launch", ln.lane, idx))
+            ev[ln.lane] = None
+    tail = ([1] if aux_used else []) + ([2 + j for j in range(n_sides)] if k else [])
+    for st in tail:
+        out.append(("record", st, next_id[0]))
+        out.append(("wait", 0, next_id[0]))
+        next_id[0] += 1
+    return out
 
 
 class BlockLayers:

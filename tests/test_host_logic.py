@@ -148,3 +148,62 @@ def test_shard_batch_rejects_ragged_split():
     assert dp.shard_batch(32, 4, 3) == (24, 32)
     with pytest.raises(ValueError):
         dp.shard_batch(30, 4, 0)
+
+
+def _happens_before(plan, n_launches):
+    """replay a stream plan: for every launch, the set of launches guaranteed complete before it starts"""
+    done = {}      # stream -> launches complete before anything issued later on that stream
+    issued = {}    # stream -> launches issued on that stream so far
+    snap = {}      # event id -> launches covered by the event
+    before = {}
+    for act in plan:
+        kind, st, x = act
+        done.setdefault(st, set())
+        issued.setdefault(st, set())
+        if kind == "record":
+            snap[x] = done[st] | issued[st]
+        elif kind == "wait":
+            done[st] |= snap[x]
+        else:
+            before[x] = done[st] | issued[st]
+            issued[st] = issued[st] | {x}
+    assert sorted(before) == list(range(n_launches))
+    return before, done.get(0, set()) | issued.get(0, set())
+
+
+def test_stream_plan_respects_fork_join_and_side_dependencies():
+    """the pure scheduler behind Program.run: lane order, fork/join edges, pool launches waiting on their lane --
+    including the case of a pool launch recorded on the auxiliary lane right after a fork (it must inherit the
+    main-stream work the fork waited for)"""
+    from types import SimpleNamespace as NS
+    from causalgen_b200.engine import Marker, plan_streams
+
+    def L(lane=0, side=False):
+        return NS(lane=lane, side=side)
+
+    # index:      0        1             2                 3           4              5        6
+    prog = [L(0), L(0), Marker("fork"), L(1, side=True), L(1), Marker("join"), L(0), L(0, side=True), L(0)]
+    launches = [i for i, ln in enumerate(prog) if not isinstance(ln, Marker)]
+    for n_sides in (1, 2, 3):
+        plan = plan_streams(prog, n_sides)
+        done_sets, final = _happens_before([a if a[0] != "launch" else ("launch", a[1], launches.index(a[2])) for a in plan],
+                                          len(launches))
+        idx = {orig: launches.index(orig) for orig in launches}
+        assert {idx[0], idx[1]} <= done_sets[idx[3]], "pool launch on the aux lane must wait for pre-fork main work"
+        assert {idx[0], idx[1]} <= done_sets[idx[4]], "aux lane starts after the fork point"
+        assert idx[4] in done_sets[idx[6]], "main continues only after the join"
+        assert {idx[0], idx[1], idx[4], idx[6]} <= done_sets[idx[7]], "pool launch on main waits for main so far"
+        assert idx[6] in done_sets[idx[8]]
+        assert final == set(range(len(launches))), "everything is joined back into the main stream at the end"
+    # second block: the auxiliary lane's cached event predates the next fork -- a pool launch recorded right after
+    # that fork must still see the main-stream work issued in between (latent backward -> posterior weight gradient)
+    prog = [Marker("fork"), L(1), Marker("join"), L(0), Marker("fork"), L(1, side=True), L(1), Marker("join"), L(0)]
+    launches = [i for i, ln in enumerate(prog) if not isinstance(ln, Marker)]
+    for n_sides in (1, 2):
+        plan = plan_streams(prog, n_sides)
+        done_sets, final = _happens_before([a if a[0] != "launch" else ("launch", a[1], launches.index(a[2])) for a in plan],
+                                          len(launches))
+        a1, m, w, a2, tail = range(5)
+        assert {a1, m} <= done_sets[w], "pool launch after the second fork must wait for the main work before it"
+        assert {a1, m} <= done_sets[a2] and a2 in done_sets[tail]
+        assert final == set(range(5))
