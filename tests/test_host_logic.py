@@ -81,7 +81,20 @@ for name, nsto, nconv_min in (("tiny_ukbb", 5, 60), ("tiny_morphomnist", 4, 80))
     assert "cg_conv2d_wgrad" not in fwd and fwd[-1] == "cg_elbo_finalize"
     zs = m.abduct(x, pa, t=0.9)
     assert len(zs) == nsto
-    print(name, len(names), prog.n_kernels)
+    # lanes: every fork is joined again, pool (weight-gradient) launches never sit in the forward part
+    kinds = [getattr(l, "kind", None) for l in prog.launches]
+    assert kinds.count("fork") == kinds.count("join") and kinds.count("fork") >= nsto
+    assert not any(getattr(l, "side", False) for l in prog.launches[:prog.n_fwd])
+    assert all(l.side for l in prog.launches if getattr(l, "name", "") == "cg_conv2d_wgrad")
+    # fused counterfactual program: encoder + posterior pass + two prior-only passes sharing the latents + combine
+    from causalgen_b200 import counterfactual
+    cf_prog = m.engine().build_counterfactual(2)
+    cn = [getattr(l, "name", "py") for l in cf_prog.launches]
+    nblk = len(O.build_arch(cfg).dec)
+    assert cn.count("cg_stem_fwd") == 1 and cn[-1] == "cg_cf_combine" and "cg_nchw_f32_to_planar" not in cn
+    assert cn.count("cg_latent_fwd") == nblk + 2 * (nblk - nsto)   # given latents need no latent kernel
+    assert cn.count("cg_dgauss_sample") + cn.count("cg_dmol_predict") == 2
+    print(name, len(names), prog.n_kernels, len(cn))
 print("ok")
 ''' % (ROOT, ROOT)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
