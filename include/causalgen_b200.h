@@ -10,9 +10,10 @@
  *     never allocates, frees or synchronises device memory (CUDA-graph capturable);
  *   - every launch goes on the `stream` argument (a cudaStream_t passed as void*);
  *   - return 0 on success, a negative cg_status otherwise; cg_last_error() gives the text;
- *   - activations are NHWC bf16 with a channel pitch `ld` (elements) so channel slices of a
- *     wider buffer are valid operands; channel counts handed to the tensor-core kernels are
- *     multiples of 16 (zero padded); latent statistics / KL / likelihood math is fp32;
+ *   - activations are bf16 "channel-octet planar" (N, C/8, H, W, 8) with a sample stride `ns` (elements), so
+ *     channel slices that start at a multiple of 8 are valid operands of a wider buffer; channel counts handed
+ *     to the tensor-core kernels are multiples of 16 (zero padded); latent statistics / KL / likelihood math
+ *     is fp32 (layout notes at cg_src below);
  *   - sm_100a only: any other device returns CG_ERR_ARCH.  There is no CPU fallback.
  */
 #ifndef CAUSALGEN_B200_H
@@ -41,7 +42,8 @@ const char* cg_last_error(void);
 int cg_device_sms(void);
 
 /* ---------------------------------------------------------------------------------------
- * Convolution (implicit GEMM on tcgen05, fp32 accumulation in TMEM)
+ * Convolution (implicit GEMM on tcgen05, fp32 accumulation in TMEM; weight gradients of small-channel
+ * problems on warp-level mma.sync, see csrc/wgrad_mma.cu)
  *   replaces nn.Conv2d forward/backward in Block / DecoderBlock: src/vae.py:49-84,165-170
  * ------------------------------------------------------------------------------------- */
 #define CG_MAX_SRC 3
