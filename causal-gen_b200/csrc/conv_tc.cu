@@ -13,17 +13,24 @@
 //               and kept resident while the persistent CTA walks its pixel tiles.
 //   D           fp32 in TMEM, double buffered (2 x Nc columns, Nc <= 64; wider outputs are split over
 //               blockIdx.y) so the epilogue of tile i overlaps the MMAs of tile i+1.
-//   epilogue    bias, channel-split segments, act'(x) multiply (backward), residual / accumulate adds,
-//               bf16 (planar, 128-byte coalesced per octet) or fp32 (row) stores.  The tensors the epilogue
-//               READS (residual, pre-activation) are TMA-staged too ("E stages"), up to 3 tiles ahead.
+//   epilogue    bias, channel-split segments, act'(x) multiply (backward), residual / accumulate adds, stored
+//               activation (out_act) and raw + activated dual store (act_copy), bf16 (planar, 128-byte coalesced per
+//               octet) or fp32 (row) stores.  The tensors the epilogue READS (residual, pre-activation) are TMA-staged
+//               too ("E stages").  Which segment / operands a 16-column chunk maps to is resolved once per warp
+//               (ChunkPlan); the common cases run a straight-line templated path (epi_chunk_fast) with only the
+//               store predicated.
 //
-// Pipeline (every hand-off is one mbarrier arrival or a TMA transaction count -- measured on B200,
-// profiles/r1c: per-thread arrivals and per-slot address arithmetic, not memory, were the bottleneck):
-//   producer warp    one thread: wait stage free -> expect_tx -> cp.async.bulk.tensor (A chunk / E operands)
+// Pipeline (every hand-off is one mbarrier arrival or a TMA transaction count):
+//   producer warp    one elected thread: wait stage free -> expect_tx -> cp.async.bulk.tensor (A chunk / E operands)
 //   transform warps  wait "landed", apply the pre-activation (ReLU/GELU) in place, fence.proxy.async, publish
 //                    (skipped entirely when the conv has no input activation: the MMA waits on "landed")
-//   MMA warp         one thread issues tcgen05.mma; tcgen05.commit frees the stage / signals the epilogue
+//   MMA warp         one elected thread issues tcgen05.mma; tcgen05.commit frees the stage / signals the epilogue
 //   epilogue warps   TMEM -> registers -> global
+// Ring depths (A stages, E stages) are chosen per launch from the shared memory left after the weight slab.
+// Single-thread regions are guarded by elect.sync, NOT `lane == 0`: ptxas then emits tcgen05.mma / TMA straight
+// instead of inside a per-active-thread ELECT/BRA.U.ANY loop (measured: ~80 -> ~40 clk per MMA, profiles/r1e_*).
+// The kernel is launched with programmatic stream serialization: everything before griddepcontrol.wait (barriers,
+// TMEM allocation, bias, weight-slab request) overlaps the tail of the previous kernel in the stream.
 //
 // Warp roles: 0-7 epilogue (TMEM lane quarter = warp & 3, column half = warp >> 2), 8 MMA issuer + TMEM owner,
 //             9 TMA producer, 10-13 transform.
