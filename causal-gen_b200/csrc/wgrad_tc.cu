@@ -13,6 +13,11 @@
 //
 // Warp roles: 0-3 flush (TMEM lane quarters), 4 MMA issuer + TMEM owner, 5 TMA producer, 6-9 transform
 // (re-apply the forward pre-activation to the X tile in place).
+//
+// Scope: this kernel serves the problems the mma.sync kernels of wgrad_mma.cu decline -- GELU pre-activations on wide
+// inputs, centre-tap (3x3 on a 1x1 image) and 1-pixel problems, both operands wider than 48 channels.  ReLU / linear
+// 3x3 and 1x1 problems (all of UKBB) are dispatched to wgrad_mma.cu first (cg_conv2d_wgrad below), where the reasons
+// are written down: K = pixels gives tcgen05 16 pixels per instruction against a mandatory 128-row operand.
 #include <cuda.h>
 
 #include <cmath>
