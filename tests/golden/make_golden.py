@@ -46,6 +46,11 @@ CASES = {
     "cmnist": ("cmnist", "cmnist", ["--context_dim", "20"], 2),
     "ukbb192": ("ukbb192", "ukbb192", ["--context_dim", "4", "--z_max_res", "96", "--beta", "5"], 1),
     "mimic192": ("mimic192", "mimic192", ["--context_dim", "6", "--z_max_res", "96", "--beta", "9"], 1),
+    # BASELINE.json configs[4]: 224x224.  The shipped mimic192 arch cannot run at 224 (KeyError 6);
+    # this arch has odd resolutions (7 zero-padded to 8, src/vae.py:130-132, then pooled by 7 with floor semantics)
+    "mimic224": ("mimic224", "mimic192", ["--input_res", "224", "--enc_arch", "224b1d2,112b3d2,56b7d2,28b11d2,14b7d2,7b3d7,1b2",
+                                          "--dec_arch", "1b2,8b4,14b8,28b12,56b8,112b4,224b2", "--context_dim", "6",
+                                          "--z_max_res", "112", "--beta", "9"], 1),
 }
 
 

@@ -10,7 +10,7 @@ import hvae_oracle as O
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 CASES = {"tiny_ukbb": 3, "tiny_morphomnist": 3, "tiny_cmnist": 3, "morphomnist": 2, "cmnist": 2,
-         "ukbb192": 1, "mimic192": 1}
+         "ukbb192": 1, "mimic192": 1, "mimic224": 1}
 
 
 def sub(t, n=4096):
