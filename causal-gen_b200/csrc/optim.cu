@@ -53,13 +53,16 @@ __global__ void optim_advance_kernel(int* __restrict__ state, float* __restrict_
   dyn[0] = base_lr * ((it > warmup || warmup <= 0) ? 1.0f : (float)it / (float)warmup);
   dyn[1] = 1.0f - powf(beta1, (float)t);
   dyn[2] = 1.0f - powf(beta2, (float)t);
-  // EMA.update(): s = calls so far; s <= update_after_step -> copy (decay 0)
+  // EMA.update() (src/utils.py:169-193), s = calls so far: s <= update_after_step copies (decay 0), the first call
+  // after that copies once more (`initted`), then decay = 1 - 1/(1 + k) with k = s - update_after_step --
+  // get_current_decay() reads the step AFTER update() incremented it -- clamped to [0, beta].
+  // Pinned against the reference's own trajectory: tests/golden/ema_schedule.npz, oracle ema_decay().
   const int s = state[1];
   state[1] = s + 1;
   float decay = 0.f;
-  if (s > ema_after) {
-    const float epoch = fmaxf((float)(s - ema_after - 1), 0.f);
-    decay = epoch <= 0.f ? 0.f : fminf(fmaxf(1.0f - 1.0f / (1.0f + epoch), 0.f), ema_beta);
+  if (s > ema_after + 1) {
+    const float k = (float)(s - ema_after);
+    decay = fminf(fmaxf(1.0f - 1.0f / (1.0f + k), 0.f), ema_beta);
   }
   dyn[3] = decay;
 }

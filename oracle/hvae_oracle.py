@@ -679,6 +679,17 @@ def normalise_x(x8: Tensor) -> Tensor:  # src/trainer.py:17
     return (x8.float() - 127.5) / 127.5
 
 
+def ema_decay(call_index: int, beta: float = 0.999, update_after: int = 100) -> float:
+    """Decay the reference's EMA applies on its `call_index`-th update() (0-based), src/utils.py:169-193:
+    calls 0..update_after copy the weights, the first call after that copies once more (`initted`), then the decay
+    is 1 - 1/(1 + k) with k = call_index - update_after (get_current_decay reads the ALREADY incremented step),
+    clamped to [0, beta].  0.0 means "ema = online weights"."""
+    if call_index <= update_after + 1:
+        return 0.0
+    k = call_index - update_after
+    return min(max(1.0 - 1.0 / (1.0 + k), 0.0), beta)
+
+
 def train_step_cpu(sd, cfg, x, pa_full, noise, opt_state, lr=1e-3, wd=0.01, betas=(0.9, 0.9),
                    grad_clip=350.0, grad_skip=500.0, step=1, ema=None):
     """One reference training step on CPU: src/trainer.py:62-87 + AdamW (src/train_setup.py:42-53).

@@ -688,3 +688,22 @@ def test_optimizer_tail_matches_torch_adamw():
     assert_close(p, ref_p.detach(), 1e-5, "adamw params")
     assert state[2].item() == 1 and state[0].item() == 4  # the 30x gradient step was skipped
     assert_close(ema, p, 1e-6, "ema copies params during its first 100 calls")
+
+
+def test_ema_decay_schedule_on_device():
+    """cg_optim_advance's EMA decay (dyn[3]) against the rule pinned to the reference trajectory
+    (oracle ema_decay <- tests/golden/ema_schedule.npz): copy phase, one more copy, inverse-decay ramp"""
+    import hvae_oracle as O
+    from causalgen_b200 import _lib as L
+    lib = L.load()
+    state = torch.zeros(4, dtype=torch.int32, device=DEV)
+    dyn = torch.zeros(6, device=DEV)
+    ss = torch.full((1,), 1e-4, device=DEV)  # sum of squares of a tiny gradient: never skipped
+    got = []
+    for s in range(130):
+        L.check(lib.cg_optim_advance(state.data_ptr(), dyn.data_ptr(), ss.data_ptr(), None, 1e-3, 100, 0.9, 0.9, 350.0,
+                                     500.0, 1.0, 0.999, 100, stream()))
+        got.append(dyn[3].item())
+    want = [O.ema_decay(s, 0.999, 100) for s in range(130)]
+    assert max(abs(a - b) for a, b in zip(got, want)) <= 1e-6, list(zip(got, want))[98:106]
+    assert state[1].item() == 130 and state[2].item() == 0

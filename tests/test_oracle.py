@@ -152,3 +152,25 @@ def test_param_counts_match_survey():
     for n, c in counts.items():
         shapes = O.param_shapes(O.make_cfg(n))
         assert sum(int(np.prod(s)) for s in shapes.values()) == c
+
+
+def test_ema_decay_schedule_matches_reference_trajectory():
+    """src/utils.py EMA warm-up (copy phase, inverse-decay ramp, cap at beta) replayed on the reference's own
+    trajectory (tests/golden/make_golden_ema.py); the optimiser kernel implements the same rule"""
+    g = np.load(os.path.join(GOLD, "ema_schedule.npz"))
+    p, want = g["p"].astype(np.float64), g["ema"]
+    ema = 0.0
+    got = np.zeros_like(want)
+    for s in range(len(p)):
+        d = O.ema_decay(s, float(g["beta"]), int(g["update_after"]))
+        ema = p[s] if d == 0.0 else ema - (1.0 - d) * (ema - p[s])
+        got[s] = ema
+    np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-5)
+    assert O.ema_decay(101) == 0.0 and abs(O.ema_decay(102) - 2.0 / 3.0) < 1e-12 and O.ema_decay(5000) == 0.999
+    # the arithmetic of csrc/optim.cu (optim_advance_kernel), restated in float32
+    f = np.float32
+    for s in list(range(0, 140)) + [1098, 1099, 1100, 5000]:
+        dev = f(0.0)
+        if s > 100 + 1:
+            dev = min(max(f(1.0) - f(1.0) / (f(1.0) + f(s - 100)), f(0.0)), f(0.999))
+        assert abs(float(dev) - O.ema_decay(s)) <= 1e-6, s
