@@ -220,3 +220,23 @@ def test_stream_plan_respects_fork_join_and_side_dependencies():
         assert {a1, m} <= done_sets[w], "pool launch after the second fork must wait for the main work before it"
         assert {a1, m} <= done_sets[a2] and a2 in done_sets[tail]
         assert final == set(range(5))
+
+
+@pytest.mark.parametrize("name", ["tiny_ukbb", "tiny_morphomnist", "tiny_cmnist", "morphomnist", "cmnist", "ukbb192",
+                                  "mimic192", "mimic224"])
+def test_fresh_init_is_bit_identical_to_the_reference(name):
+    """same seed -> same weights as the reference's HVAE(args): module construction order, default Conv2d init and the
+    init scaling rules (src/vae.py:121-122,303-308), digests from tests/golden/make_golden_init.py"""
+    import hashlib
+    import json
+    from causalgen_b200 import HVAE
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "init_digests.json")))[name]
+    torch.manual_seed(7)
+    model = HVAE(O.make_cfg(name))
+    sd = model.state_dict()
+    h = hashlib.sha256()
+    for k, v in sd.items():
+        h.update(k.encode())
+        h.update(v.detach().cpu().contiguous().numpy().tobytes())
+    assert len(sd) == want["tensors"] and sum(p.numel() for p in model.parameters()) == want["params"]
+    assert h.hexdigest() == want["sha256"]
