@@ -712,6 +712,6 @@ def train_step_cpu(sd, cfg, x, pa_full, noise, opt_state, lr=1e-3, wd=0.01, beta
                 mh = m / (1 - betas[0] ** step)
                 vh = v / (1 - betas[1] ** step)
                 p.addcdiv_(mh, vh.sqrt().add_(1e-8), value=-lr)
-                if ema is not None:
-                    ema[k].lerp_(p, 1 - 0.999)
+                if ema is not None:  # ema.update() of the same (non-skipped) step, src/trainer.py:74-77
+                    ema[k].lerp_(p, 1.0 - ema_decay(step - 1))
     return out, gn
