@@ -2,12 +2,12 @@
 """Benchmark of the hot path: HVAE ELBO training step (images/s) on synthetic UKBB-shape images.
 
     python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
-    python bench.py --impl reference --gpus N ...            # the reference algorithm on the host CPUs
+    python bench.py --impl reference --gpus N ...            # the reference itself on the host CPUs
     torchrun --nproc-per-node N ... bench.py --gpus N ...    # one rank per GPU, weak scaling
 
 One step = preprocess + forward + backward + (all-reduce) + clip/AdamW/EMA over one batch of
-`--batch` images per GPU.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions
-of `value`, `e2e`, `roofline`, `cpu_baseline`.
+`--batch` images per GPU.  Prints ONE JSON line (rank 0).  DESIGN.md section 6 defines `value`, `e2e`, `roofline`,
+`cpu_baseline`, `configs` and `reference_gpu`.
 """
 import argparse
 import json
@@ -26,14 +26,12 @@ import torch  # noqa: E402
 METRIC = "hvae_elbo_train_images_per_sec"
 HBM_FALLBACK_GBS = 6650.0
 TENSOR_FALLBACK_TFS = 1400.0
-# conv FLOPs per image of one ELBO forward pass (measured on the reference with hooks);
-# a training step executes 3x (forward + data-gradient + weight-gradient)
-# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per conv_tc_kernel launch, averaged over the 891
-# conv launches of one training step at the given per-GPU batch: profiles/r1h_ncu_launches_one_step_b128.csv
-# (ncu pass of this very command).  Below the algorithmic bytes because producer->consumer tensors hit the L2.
-CONV_DRAM_TRAFFIC_PER_LAUNCH = {("ukbb192", 128): 85.92e6}
+# conv FLOPs per image (measured on the reference with hooks; tools/roofline.py regenerates them);
+# a training step executes 3x the forward FLOPs (forward + data-gradient + weight-gradient)
 FWD_GFLOP = {"ukbb192": 23.064, "mimic192": 9.127, "morphomnist": 0.0865, "cmnist": 0.0917, "mimic224": 12.460}
 CF_GFLOP = {"ukbb192": 47.670, "mimic192": 19.565, "morphomnist": 0.1845, "cmnist": 0.1924, "mimic224": 26.707}
+# SURVEY 8(d) "fwd layerwise bytes" per image (bf16 input + output activation bytes of every conv of one ELBO forward)
+FWD_LAYERWISE_MB = {"ukbb192": 226.1, "mimic192": 282.9, "morphomnist": 5.92, "cmnist": 6.01, "mimic224": 385.4}
 
 
 def peaks():
@@ -42,6 +40,17 @@ def peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured"
     return HBM_FALLBACK_GBS, TENSOR_FALLBACK_TFS, "fallback"
+
+
+def measured_traffic(config, batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per conv_tc_kernel launch from the committed ncu pass of one step of
+    this very workload (profiles/r2_traffic.json, written by tools/ncu_summary.py); None when no capture matches"""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p))
+    e = d.get(f"{config}:{batch}")
+    return (e["conv_dram_bytes_per_launch"], e) if e else (None, None)
 
 
 def synthetic_host_batches(args_m, batch, nbatch, seed):
@@ -169,7 +178,8 @@ def timed(fn, steps, world):
 
 
 def conv_bytes(a):
-    """algorithmic HBM bytes of one cg_conv2d launch: inputs + outputs + fused addends + packed weights"""
+    """ISSUED bytes of one cg_conv2d launch (padded channels, fused addends / masks, packed weights): what the
+    kernel asks the memory system for -- reported next to the algorithmic figure, never as the roofline numerator"""
     npix = a.N * a.H * a.W
     b = 0
     k = 0
@@ -195,18 +205,17 @@ def wgrad_bytes(a):
     return b + a.cout_l * a.cin_l * a.ksize * a.ksize * 4
 
 
-def profile_step(trainer):
-    """one eager (un-graphed) step with CUDA events around every launch: per-kernel-family device time and
-    the algorithmic bytes of the conv launches (for the roofline object)"""
-    from causalgen_b200 import _lib as L
-    prog = trainer.prog
+def profile_program(prog, pre=None):
+    """one eager (un-graphed) pass over a launch program with CUDA events around every launch, issued behind a spin
+    kernel so the host is ahead of the device and the events bracket device time only.  Returns per-family device
+    time, and for the conv launches the ALGORITHMIC bytes (bf16 input + output activation bytes, logical
+    channels) next to the issued bytes."""
     s = torch.cuda.current_stream().cuda_stream
-    evs = []
-    for t in prog.zero:
-        t.zero_()
-    trainer.eng.flat_grad.zero_()
-    trainer.eng.pack_weights(s)
+    if pre is not None:
+        pre()
     torch.cuda.synchronize()
+    torch.cuda._sleep(int(8e7))  # ~40 ms head start for the host
+    evs = []
     for ln in prog.launches:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -215,7 +224,7 @@ def profile_step(trainer):
         evs.append((ln, e0, e1))
     torch.cuda.synchronize()
     fam = {}
-    conv_t = conv_b = wg_t = wg_b = 0.0
+    conv_t = conv_algo = conv_issued = wg_t = wg_algo = 0.0
     nconv = nwg = 0
     for ln, e0, e1 in evs:
         ms = e0.elapsed_time(e1)
@@ -223,69 +232,261 @@ def profile_step(trainer):
         fam[name] = fam.get(name, 0.0) + ms
         if name == "cg_conv2d":
             conv_t += ms
-            conv_b += conv_bytes(ln.keep[0])
+            conv_algo += ln.algo_bytes
+            conv_issued += conv_bytes(ln.keep[0])
             nconv += 1
         elif name == "cg_conv2d_wgrad":
             wg_t += ms
-            wg_b += wgrad_bytes(ln.keep[0])
+            wg_algo += ln.algo_bytes
             nwg += 1
     total = sum(fam.values())
     return dict(families_ms={k: round(v, 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])},
-                total_ms=total, conv_ms=conv_t, conv_bytes=conv_b, nconv=nconv, wgrad_ms=wg_t, wgrad_bytes=wg_b,
-                nwgrad=nwg)
+                total_ms=total, conv_ms=conv_t, conv_algo_bytes=conv_algo, conv_issued_bytes=conv_issued, nconv=nconv,
+                wgrad_ms=wg_t, wgrad_algo_bytes=wg_algo, nwgrad=nwg)
 
 
-def cpu_port_step_time(name, sd_cpu, batch, budget_s, threads):
-    """the reference algorithm (oracle port) on the host cores: ELBO forward + backward + clip + AdamW + EMA"""
+def profile_step(trainer):
+    def pre():
+        for t in trainer.prog.zero:
+            t.zero_()
+        trainer.eng.flat_grad.zero_()
+        trainer.eng.pack_weights(torch.cuda.current_stream().cuda_stream)
+    out = profile_program(trainer.prog, pre)
+    trainer.eng.flat_grad.zero_()
+    return out
+
+
+def roofline_object(prof, hbm_gbs, peak_src, step_ms, config, batch, tensor=None):
+    conv_gbs = prof["conv_algo_bytes"] / (prof["conv_ms"] / 1e3) / 1e9
+    traffic, tr_meta = measured_traffic(config, batch)
+    r = {"bound": "hbm", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv: forward + data-gradient launches)",
+         "achieved": conv_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": conv_gbs / hbm_gbs, "peak_source": peak_src,
+         "traffic": traffic, "traffic_source": (tr_meta or {}).get("source"),
+         "algorithmic_bytes_per_launch": prof["conv_algo_bytes"] / max(prof["nconv"], 1),
+         "algorithmic_bytes_def": "SURVEY 8(d): sum over conv launches of 2 B x pixels x (logical Cin + logical Cout)",
+         "issued_bytes_per_launch": prof["conv_issued_bytes"] / max(prof["nconv"], 1),
+         "issued_over_algorithmic": prof["conv_issued_bytes"] / max(prof["conv_algo_bytes"], 1),
+         "launches_per_step": prof["nconv"], "avg_launch_us": 1e3 * prof["conv_ms"] / max(prof["nconv"], 1),
+         "algorithmic_bytes_per_step": prof["conv_algo_bytes"],
+         "timing": "CUDA events around each launch of one eager pass (launching stream, host ahead of device)",
+         "share_of_serialised_pass": prof["conv_ms"] / prof["total_ms"],
+         "serialised_pass_ms": prof["total_ms"], "graph_step_ms": step_ms}
+    if prof["nwgrad"]:
+        wg = prof["wgrad_algo_bytes"] / (prof["wgrad_ms"] / 1e3) / 1e9
+        r["wgrad_kernel"] = {"kernel": "wgrad_mma_kernel (mma.sync, 3x3) + wgrad_tc_kernel (tcgen05, 1x1)",
+                             "achieved": wg, "frac": wg / hbm_gbs, "launches_per_step": prof["nwgrad"],
+                             "share_of_serialised_pass": prof["wgrad_ms"] / prof["total_ms"]}
+    if tensor is not None:
+        r["tensor"] = tensor
+    return r
+
+
+# ---------------------------------------------------------------------------------------------- CPU / reference arms
+def _oracle():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import hvae_oracle as O
+    import ref_runner as R
+    return O, R
+
+
+def cpu_train_step_time(name, sd_cpu, batch, budget_s, threads):
+    """the reference's CPU implementation of the step on the host cores: the staged reference itself when
+    baseline/_ref exists (kind "reference"), else the oracle port (kind "port")"""
+    O, R = _oracle()
     torch.set_num_threads(threads)
     cfg = O.make_cfg(name)
+    x8, pa, _ = O.synthetic_batch(cfg, batch, seed=3)
+    if R.available() and name in R.FLAGS:
+        st = R.RefTrainStep(name, "cpu")
+        sec, n = R.time_steps(lambda: st(x8, pa), lambda: None, budget_s)
+        return sec, n, "reference"
     sd = {k: v.clone().float().requires_grad_(True) for k, v in sd_cpu.items()}
     ema = {k: v.detach().clone() for k, v in sd.items()}
+    x, pa_full = O.normalise_x(x8), O.expand_parents(pa, cfg.input_res)
+    state, step = {}, [0]
+
+    def fn():
+        step[0] += 1
+        O.train_step_cpu(sd, cfg, x, pa_full, O.NoiseTape(seed=step[0]), state, lr=1e-3, wd=0.05, step=step[0], ema=ema)
+    sec, n = R.time_steps(fn, lambda: None, budget_s)
+    return sec, n, "port"
+
+
+def cpu_cf_time(name, sd_cpu, batch, budget_s, threads):
+    """abduct + 2 x forward_latents + combine (src/pgm/dscm.py:52-56) on the host cores"""
+    O, R = _oracle()
+    torch.set_num_threads(threads)
+    cfg = O.make_cfg(name)
+    x8, pa, cf = O.synthetic_batch(cfg, batch, seed=3)
+    x, pa_full, cf_full = O.normalise_x(x8), O.expand_parents(pa, cfg.input_res), O.expand_parents(cf, cfg.input_res)
+    if R.available() and name in R.FLAGS:
+        _, model, _ = R.build(name, "cpu")
+        model.eval()
+        sec, n = R.time_steps(lambda: R.ref_counterfactual(model, x, pa_full, cf_full), lambda: None, budget_s)
+        return sec, n, "reference"
+    sd = {k: v.clone().float() for k, v in sd_cpu.items()}
+
+    def fn():
+        with torch.no_grad():
+            O.counterfactual(sd, cfg, x, pa_full, cf_full, O.NoiseTape(seed=1))
+    sec, n = R.time_steps(fn, lambda: None, budget_s)
+    return sec, n, "port"
+
+
+def reference_on_gpu(name, batch, steps):
+    """the real competitor: the unmodified reference module, eager PyTorch + cuDNN on this B200, default
+    TF32 and under autocast(bf16), same step (fwd + bwd + clip + AdamW + EMA), inputs resident"""
+    O, R = _oracle()
+    if not R.available() or name not in R.FLAGS:
+        return {"unavailable": "reference not staged under baseline/_ref"}
+    cfg = O.make_cfg(name)
     x8, pa, _ = O.synthetic_batch(cfg, batch, seed=3)
-    x = O.normalise_x(x8)
-    pa_full = O.expand_parents(pa, cfg.input_res)
-    state = {}
-    times = []
-    t_start = time.time()
-    step = 0
-    while True:
-        t0 = time.time()
-        O.train_step_cpu(sd, cfg, x, pa_full, O.NoiseTape(seed=step), state, lr=1e-3, wd=0.05, step=step + 1, ema=ema)
-        dt = time.time() - t0
-        step += 1
-        if step > 1:
-            times.append(dt)
-        if (time.time() - t_start > budget_s and len(times) >= 2) or len(times) >= 8:
-            break
-    return float(np.median(times)), len(times)
+    x8, pa = x8.cuda(), pa.cuda()
+    out = {"batch_per_gpu": batch, "what": "reference HVAE (src/vae.py) eager on cuda:0, src/trainer.py:62-87 step"}
+    for mode, kw in (("tf32", dict(autocast_bf16=False, tf32=True)), ("bf16_autocast", dict(autocast_bf16=True, tf32=True))):
+        try:
+            st = R.RefTrainStep(name, "cuda", **kw)
+            for _ in range(3):
+                st(x8, pa)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                o = st(x8, pa)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[mode] = {"value": batch / (ms / 1e3), "unit": "images/s", "ms_per_step": ms,
+                         "elbo": float(o["elbo"].detach())}
+            del st
+        except Exception as ex:  # e.g. out of memory at a large batch: report, do not hide
+            out[mode] = {"error": f"{type(ex).__name__}: {str(ex)[:160]}"}
+        torch.cuda.empty_cache()
+    return out
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port: the reference
-    package itself cannot travel to the GPU box) with all host threads, bounded sample per step"""
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    """--impl reference: the reference's own CPU implementation of the path with all host threads, bounded sample"""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    from causalgen_b200 import HVAE
-    from causalgen_b200.presets import init_like_reference_main, make_args
-    torch.manual_seed(7)
-    m = init_like_reference_main(HVAE(make_args(args.config)))
-    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    sd = None
+    _, R = _oracle()
+    if not (R.available() and args.config in R.FLAGS):
+        from causalgen_b200 import HVAE
+        from causalgen_b200.presets import init_like_reference_main, make_args
+        torch.manual_seed(7)
+        m = init_like_reference_main(HVAE(make_args(args.config)))
+        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
     threads = os.cpu_count() or 1
     bs = args.cpu_batch
-    sec, n = cpu_port_step_time(args.config, sd, bs, budget_s=max(10.0, 4.0 * args.steps), threads=threads)
+    sec, n, kind = cpu_train_step_time(args.config, sd, bs, budget_s=max(10.0, 4.0 * args.steps), threads=threads)
     val = bs / sec
+    what = ("unmodified reference (baseline/_ref/src: vae.py HVAE + trainer.py step body) on the host CPUs"
+            if kind == "reference" else "reference algorithm restated in oracle/ (torch CPU fp32)")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
             "steps": n, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.config} HVAE ELBO train step (fwd+bwd+clip+AdamW+EMA), CPU batch {bs}",
-                       "note": "reference algorithm restated in oracle/ (torch CPU fp32); /root/reference cannot travel"},
-            "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port",
+                       "note": what},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": kind,
                              "sample": f"{n} timed steps of batch {bs} after 1 warm-up"},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- GPU arms
+def make_trainer(name, B, use_graph=True, **over):
+    from causalgen_b200 import HVAE
+    from causalgen_b200.presets import init_like_reference_main, make_args
+    from causalgen_b200.trainer import Trainer
+    margs = make_args(name, **over)
+    torch.manual_seed(7)
+    model = init_like_reference_main(HVAE(margs)).cuda()
+    tr = Trainer(model, B, lr=margs.lr, wd=margs.wd, betas=margs.betas, lr_warmup_steps=margs.lr_warmup_steps,
+                 grad_clip=margs.grad_clip, grad_skip=margs.grad_skip, ema_rate=margs.ema_rate, beta=margs.beta,
+                 use_graph=use_graph, noise_seed=7)
+    return margs, model, tr
+
+
+def release(model):
+    model.engine().programs.clear()
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+def side_config_train(name, B, steps, world, rank, hbm_gbs, tensor_tfs, **over):
+    """train-step throughput of one more BASELINE config (device-resident inputs, graph replay, 4 rotating batches)"""
+    margs, model, tr = make_trainer(name, B, **over)
+    xs, pas = synthetic_host_batches(margs, B, 4, seed=200 + rank)
+    xs, pas = [x.cuda() for x in xs], [p.cuda() for p in pas]
+    for i in range(4):
+        tr.step_device(xs[i % 4], pas[i % 4])
+    ms, _, _ = timed(lambda i: tr.step_device(xs[i % 4], pas[i % 4]), steps, world)
+    val = B * world * steps / (ms / 1e3)
+    loss = [float(v) for v in tr.prog.out3]
+    out = {"metric": METRIC, "value": val, "unit": "images/s", "batch_per_gpu": B, "ms_per_step": ms / steps,
+           "cuda_graph": tr.g_fb is not None, "x_like": margs.x_like, "kernels_per_step": tr.kernels_per_step,
+           "tensor_frac": 3 * FWD_GFLOP[name] * val / 1e3 / tensor_tfs,
+           "hbm_layerwise_frac": 3 * FWD_LAYERWISE_MB[name] * 1e6 * val / 1e9 / hbm_gbs,
+           "loss": {"elbo": loss[0], "nll": loss[1], "kl": loss[2]}, "skipped_updates": tr.skipped_updates()}
+    del tr
+    release(model)
+    return out
+
+
+def cf_config(name, B, steps, world, rank, hbm_gbs, tensor_tfs, model=None, profile=False, peak_src="measured"):
+    """counterfactual inference (abduct + 2 x forward_latents + combine, src/pgm/dscm.py:47-72): replicas only"""
+    from causalgen_b200 import CounterfactualGraph, HVAE, counterfactual
+    from causalgen_b200.presets import init_like_reference_main, make_args
+    margs = make_args(name)
+    own = model is None
+    if own:
+        torch.manual_seed(7)
+        model = init_like_reference_main(HVAE(margs)).cuda()
+    model.eval()
+    xs, pas = synthetic_host_batches(margs, B, 2, seed=300 + rank)
+    x8h = xs[0].pin_memory()
+    pah, cfh = pas[0].pin_memory(), pas[1].pin_memory()
+    xf = (xs[0].cuda().float() - 127.5) / 127.5
+    pa, cfp = pas[0].cuda(), pas[1].cuda()
+    for _ in range(2):
+        counterfactual(model, xf, pa, cfp)
+    ms_eager, _, _ = timed(lambda i: counterfactual(model, xf, pa, cfp), max(2, steps // 2), world)
+    run = CounterfactualGraph(model, B)
+    for _ in range(2):
+        run(xf, pa, cfp)
+    ms, _, _ = timed(lambda i: run(xf, pa, cfp), steps, world)
+    # end to end through the public call: pinned host uint8 image + parents in, counterfactual image back on the host
+    out_h = torch.empty(B, margs.input_channels, margs.input_res, margs.input_res).pin_memory()
+
+    def e2e_step(i):
+        xd = (x8h.cuda(non_blocking=True).float() - 127.5) / 127.5
+        cf_x, _ = run(xd, pah.cuda(non_blocking=True), cfh.cuda(non_blocking=True))
+        out_h.copy_(cf_x, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e2e_step(0)
+    ms_e2e, _, _ = timed(e2e_step, steps, world)
+    val = B * world * steps / (ms / 1e3)
+    out = {"metric": "counterfactual_images_per_sec", "value": val, "unit": "images/s", "batch_per_gpu": B,
+           "ms_per_batch": ms / steps, "scaling": "replicas (no collective)",
+           "eager_value": B * world * max(2, steps // 2) / (ms_eager / 1e3),
+           "e2e": {"value": B * world * steps / (ms_e2e / 1e3), "unit": "images/s",
+                   "h2d_bytes_per_step": int(x8h.numel() + 2 * pah.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4)},
+           "tensor_frac": CF_GFLOP[name] * val / 1e3 / tensor_tfs,
+           "note": "abduct + forward_latents(cf_pa) + forward_latents(pa) + combine in ONE launch program, CUDA-graph "
+                   "replay; eager_value = same launches issued from Python"}
+    if profile and rank == 0:
+        prog = model.engine().programs[("cf", B)]
+        prof = profile_program(prog, lambda: model.engine().pack_weights())
+        out["roofline"] = roofline_object(prof, hbm_gbs, peak_src, ms / steps, name + ":cf", B,
+                                          tensor={"conv_tflops": CF_GFLOP[name] * val / 1e3, "peak": tensor_tfs,
+                                                  "frac": CF_GFLOP[name] * val / 1e3 / tensor_tfs})
+        out["breakdown_ms"] = prof["families_ms"]
+    del run
+    if own:
+        release(model)
+    return out
 
 
 def main():
@@ -299,10 +500,12 @@ def main():
                     help="images per GPU per step (throughput configuration; the reference's bs=32 is also measured)")
     ap.add_argument("--no-ref-batch", action="store_true", help="skip the extra measurement at the reference bs=32")
     ap.add_argument("--cpu-batch", type=int, default=2)
-    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cf", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs (morphomnist, cmnist, ...)")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-eager-on-B200 competitor arm")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -311,20 +514,11 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the product path has no CPU fallback (use --impl reference for the "
                          "CPU arm)")
-    from causalgen_b200 import HVAE, counterfactual
-    from causalgen_b200.presets import init_like_reference_main, make_args
-    from causalgen_b200.trainer import Trainer
-
     world, rank, local = dist_setup(args.gpus)
     hbm_gbs, tensor_tfs, peak_src = peaks()
-    margs = make_args(args.config)
-    torch.manual_seed(7)
-    model = init_like_reference_main(HVAE(margs)).cuda()
-    sd_cpu = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()} if rank == 0 else None
     B = args.batch
-    trainer = Trainer(model, B, lr=margs.lr, wd=margs.wd, betas=margs.betas, lr_warmup_steps=margs.lr_warmup_steps,
-                      grad_clip=margs.grad_clip, grad_skip=margs.grad_skip, ema_rate=margs.ema_rate, beta=margs.beta,
-                      use_graph=not args.no_graph, noise_seed=7)
+    margs, model, trainer = make_trainer(args.config, B, use_graph=not args.no_graph)
+    sd_cpu = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()} if rank == 0 else None
     nb = 4
     xs_h, pas_h = synthetic_host_batches(margs, B, nb, seed=100 + rank)
     xs_h = [x.pin_memory() for x in xs_h]
@@ -341,9 +535,13 @@ def main():
     ms_dev, w0, w1 = timed(lambda i: trainer.step_device(xs_d[i % nb], pas_d[i % nb]), args.steps, world)
     clocks = sampler.summary(w0, w1)
     # end-to-end arm: pinned host uint8 batch -> H2D -> step -> D2H loss, every step
-    ms_e2e, w2, w3 = timed(lambda i: trainer.step(xs_h[i % nb], pas_h[i % nb]), args.steps, world)
+    last = {}
+
+    def e2e_step(i):
+        last["loss"] = trainer.step(xs_h[i % nb], pas_h[i % nb])
+    ms_e2e, w2, w3 = timed(e2e_step, args.steps, world)
     sampler.stop()
-    loss = [float(v) for v in trainer.loss_host]
+    loss = [float(v) for v in last["loss"]]
     imgs = B * world * args.steps
     value = imgs / (ms_dev / 1e3)
     e2e = imgs / (ms_e2e / 1e3)
@@ -351,8 +549,6 @@ def main():
     line = None
     if rank == 0:
         prof = profile_step(trainer)
-        conv_gbs = prof["conv_bytes"] / (prof["conv_ms"] / 1e3) / 1e9
-        wg_gbs = prof["wgrad_bytes"] / (prof["wgrad_ms"] / 1e3) / 1e9
         gflop_step = 3.0 * FWD_GFLOP.get(args.config, 0.0)
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
@@ -370,52 +566,27 @@ def main():
                     "h2d_bytes_per_step": int(xs_h[0].numel() + pas_h[0].numel() * 4), "d2h_bytes_per_step": 12},
             "gpu_launches": int(trainer.kernels_per_step * args.steps),
             "loss": {"elbo": loss[0], "nll": loss[1], "kl": loss[2], "skipped_updates": trainer.skipped_updates()},
-            "roofline": {"bound": "hbm", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv: forward + data-gradient)",
-                         "achieved": conv_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": conv_gbs / hbm_gbs,
-                         "peak_source": peak_src, "traffic": CONV_DRAM_TRAFFIC_PER_LAUNCH.get((args.config, B)),
-                         "algorithmic_bytes_per_launch": prof["conv_bytes"] / max(prof["nconv"], 1),
-                         "launches_per_step": prof["nconv"], "avg_launch_us": 1e3 * prof["conv_ms"] / max(prof["nconv"], 1),
-                         "algorithmic_bytes_per_step": prof["conv_bytes"],
-                         "share_of_step": prof["conv_ms"] / prof["total_ms"],
-                         "wgrad_kernel": {"kernel": "wgrad_mma_kernel (mma.sync, 3x3) + wgrad_tc_kernel (tcgen05, 1x1)",
-                                          "achieved": wg_gbs, "frac": wg_gbs / hbm_gbs, "launches_per_step": prof["nwgrad"],
-                                          "share_of_step": prof["wgrad_ms"] / prof["total_ms"]},
-                         "tensor": {"conv_tflops": gflop_step * value / 1e3, "peak": tensor_tfs,
-                                    "frac": gflop_step * value / 1e3 / tensor_tfs,
-                                    "gflop_per_image_step": gflop_step}},
+            "roofline": roofline_object(
+                prof, hbm_gbs, peak_src, ms_dev / args.steps, args.config, B,
+                tensor={"conv_tflops": gflop_step * value / world / 1e3, "peak": tensor_tfs,
+                        "frac": gflop_step * value / world / 1e3 / tensor_tfs, "gflop_per_image_step": gflop_step}),
+            "hbm_layerwise_frac_step": 3 * FWD_LAYERWISE_MB.get(args.config, 0) * 1e6 * value / world / 1e9 / hbm_gbs,
             "breakdown_ms": prof["families_ms"],
             "hbm_gb_peak_train": round(torch.cuda.max_memory_allocated() / 1e9, 2),
         }
-    # counterfactual inference throughput (abduct + 2x forward_latents + combine), replicas only
+    # counterfactual inference throughput of the same config, replicas only
+    del trainer
+    release(model)
     if not args.no_cf:
-        model.eval()
-        Bc = B
-        xf = (xs_d[0].float() - 127.5) / 127.5
-        pa, cfp = pas_d[0], pas_d[1]
-        for _ in range(2):
-            counterfactual(model, xf, pa, cfp)
-        ncf = max(3, args.steps // 2)
-        ms_cf, _, _ = timed(lambda i: counterfactual(model, xf, pa, cfp), ncf, world)
-        from causalgen_b200 import CounterfactualGraph
-        cfg_run = CounterfactualGraph(model, Bc)
-        for _ in range(2):
-            cfg_run(xf, pa, cfp)
-        ms_cfg, _, _ = timed(lambda i: cfg_run(xf, pa, cfp), ncf, world)
+        cf = cf_config(args.config, B, max(3, args.steps // 2), world, rank, hbm_gbs, tensor_tfs, model=model, profile=True,
+                       peak_src=peak_src)
         if rank == 0:
-            cf_val = Bc * world * ncf / (ms_cfg / 1e3)
-            line["cf_inference"] = {"metric": "counterfactual_images_per_sec", "value": cf_val, "unit": "images/s",
-                                    "batch_per_gpu": Bc, "ms_per_batch": ms_cfg / ncf,
-                                    "eager_value": Bc * world * ncf / (ms_cf / 1e3),
-                                    "tensor_frac": CF_GFLOP.get(args.config, 0) * cf_val / 1e3 / tensor_tfs,
-                                    "note": "abduct + forward_latents(cf_pa, pa) batched + combine (src/pgm/dscm.py:47-72), "
-                                            "CUDA-graph replay; eager_value = same launches issued from Python"}
-        del cfg_run
+            line["cf_inference"] = cf
+        release(model)
     # the same step at the reference's own batch size (src/hps.py ukbb192: bs=32): latency-bound regime
     if B != 32 and not args.no_ref_batch:
-        del trainer
+        from causalgen_b200.trainer import Trainer
         model.train()
-        model.engine().programs.clear()
-        torch.cuda.empty_cache()
         tr32 = Trainer(model, 32, lr=margs.lr, wd=margs.wd, betas=margs.betas, lr_warmup_steps=margs.lr_warmup_steps,
                        grad_clip=margs.grad_clip, grad_skip=margs.grad_skip, ema_rate=margs.ema_rate, beta=margs.beta,
                        use_graph=not args.no_graph, noise_seed=7)
@@ -429,13 +600,41 @@ def main():
             line["reference_batch32"] = {"value": 32 * world * n32 / (ms32 / 1e3), "unit": "images/s",
                                          "ms_per_step": ms32 / n32, "batch_per_gpu": 32}
         del tr32
+        release(model)
+    del model
+    torch.cuda.empty_cache()
+    # the other BASELINE.json configs: driver-run numbers, same clocked run
+    if not args.no_configs:
+        n = min(args.steps, 10)
+        cfgs = {}
+        if world == 1:
+            cfgs["morphomnist"] = side_config_train("morphomnist", 1024, n, world, rank, hbm_gbs, tensor_tfs)
+            cfgs["morphomnist_bs32"] = side_config_train("morphomnist", 32, n, world, rank, hbm_gbs, tensor_tfs)
+            cfgs["cmnist"] = side_config_train("cmnist", 1024, n, world, rank, hbm_gbs, tensor_tfs)
+            cfgs["cmnist_dmol"] = side_config_train("cmnist", 1024, n, world, rank, hbm_gbs, tensor_tfs, x_like="diag_dmol")
+            cfgs["mimic192"] = side_config_train("mimic192", 64, n, world, rank, hbm_gbs, tensor_tfs)
+        cfgs["mimic224_cf"] = cf_config("mimic224", 32, max(3, n // 2), world, rank, hbm_gbs, tensor_tfs)
+        if rank == 0:
+            line["configs"] = cfgs
     if rank == 0:
         line["hbm_gb_peak_total"] = round(torch.cuda.max_memory_allocated() / 1e9, 2)
+        if world == 1 and not args.no_ref_gpu:
+            line["reference_gpu"] = reference_on_gpu(args.config, 32, 5)
+            if B != 32:
+                big = reference_on_gpu(args.config, B, 3)
+                line["reference_gpu"][f"batch{B}"] = {k: v for k, v in big.items() if k in ("tf32", "bf16_autocast")}
         if world == 1 and not args.no_cpu:
-            sec, n = cpu_port_step_time(args.config, sd_cpu, args.cpu_batch, args.cpu_seconds, os.cpu_count() or 1)
-            line["cpu_baseline"] = {"value": args.cpu_batch / sec, "unit": "images/s", "cores": os.cpu_count() or 1,
-                                    "kind": "port", "sample": f"{n} timed steps of batch {args.cpu_batch} "
-                                    f"(same model/weights, fwd+bwd+clip+AdamW+EMA) after 1 warm-up"}
+            cores = os.cpu_count() or 1
+            sec, n, kind = cpu_train_step_time(args.config, sd_cpu, args.cpu_batch, args.cpu_seconds, cores)
+            line["cpu_baseline"] = {"value": args.cpu_batch / sec, "unit": "images/s", "cores": cores,
+                                    "kind": kind, "sample": f"{n} timed steps of batch {args.cpu_batch} "
+                                    f"(fwd+bwd+clip+AdamW+EMA, src/trainer.py:62-87) after 1 warm-up"}
+            if "cf_inference" in line:
+                sec, n, kind = cpu_cf_time(args.config, sd_cpu, args.cpu_batch, args.cpu_seconds / 2, cores)
+                line["cf_inference"]["cpu_baseline"] = {
+                    "value": args.cpu_batch / sec, "unit": "images/s", "cores": cores, "kind": kind,
+                    "sample": f"{n} timed passes of batch {args.cpu_batch} (abduct + 2 x forward_latents + combine, "
+                              f"src/pgm/dscm.py:52-56, no_grad) after 1 warm-up"}
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

@@ -7,5 +7,6 @@ Public surface (mirrors reference src/vae.py, src/dmol.py, src/pgm/dscm.py):
     CounterfactualGraph   the same, fixed batch, replayed from one CUDA graph
     vae_preprocess(...)   parent concatenation
 """
-from .hvae import HVAE, CounterfactualGraph, counterfactual, vae_preprocess  # noqa: F401
+from .hvae import HVAE, CounterfactualGraph, counterfactual, ukbb_preprocess, vae_preprocess  # noqa: F401
+from . import dp  # noqa: F401
 from .model import DGaussNet, DmolNet  # noqa: F401

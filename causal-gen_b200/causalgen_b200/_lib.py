@@ -65,7 +65,8 @@ class LatentBwdArgs(C.Structure):
                 ("eps", C.c_void_p), ("seed", C.c_uint64), ("offset", C.c_uint64), ("seed_dev", C.c_void_p),
                 ("dz", C.c_void_p), ("dz_ns", C.c_int64), ("g_kl", C.c_float),
                 ("dq", C.c_void_p), ("dq_ns", C.c_int64), ("dp", C.c_void_p), ("dp_ns", C.c_int64),
-                ("N", C.c_int32), ("HW", C.c_int32), ("zdim", C.c_int32), ("mode", C.c_int32)]
+                ("N", C.c_int32), ("HW", C.c_int32), ("zdim", C.c_int32), ("mode", C.c_int32),
+                ("g_kl_dev", C.c_void_p)]
 
 
 class DGaussArgs(C.Structure):
@@ -118,7 +119,7 @@ _SIGNATURES = {
     "cg_cf_combine": (C.c_int, [C.c_void_p] * 8 + [C.c_int64, C.c_void_p]),
     "cg_normalise_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "cg_parents_plane": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
-                                   C.c_int32, C.c_int64, C.c_int32, C.c_float, C.c_void_p]),
+                                   C.c_int32, C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
     "cg_nchw_f32_to_planar": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 3 + [C.c_int64, C.c_void_p]),
     "cg_planar_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 3 + [C.c_int64, C.c_void_p]),
     "cg_stats_to_nchw": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_int32, C.c_int32,
@@ -127,8 +128,8 @@ _SIGNATURES = {
     "cg_colsum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]),
     "cg_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 3 + [C.c_int64] * 3 + [C.c_void_p]),
     "cg_elbo_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float,
-                                   C.c_void_p]),
-    "cg_sumsq": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+                                   C.c_void_p, C.c_void_p]),
+    "cg_sumsq": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "cg_optim_advance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32] +
                          [C.c_float] * 6 + [C.c_int32, C.c_void_p]),
     "cg_adamw_ema_step": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_float] * 4 +
@@ -168,7 +169,7 @@ def check(rc: int, what: str = ""):
 
 class Launch:
     """One recorded kernel launch: a bound C function plus its (mutable) argument tuple."""
-    __slots__ = ("fn", "args", "name", "keep", "side", "lane")
+    __slots__ = ("fn", "args", "name", "keep", "side", "lane", "algo_bytes")
 
     def __init__(self, name, *args):
         self.fn = getattr(load(), name)
@@ -177,6 +178,7 @@ class Launch:
         self.keep = None
         self.side = False  # True: nothing later in the program reads its result -> may run on a side stream
         self.lane = 0      # 0: main stream, 1: auxiliary lane of the program (engine.Program)
+        self.algo_bytes = 0  # algorithmic HBM bytes of the launch (logical channels), set by ops.ConvLayer
 
     def __call__(self, stream):
         rc = self.fn(*self.args, stream)

@@ -218,6 +218,13 @@ class Rec:
     pass
 
 
+def ordered_params(model) -> List[torch.nn.Parameter]:
+    """parameter order of the flat buffers: trainable first, frozen last (so optimiser kernels can stop before the
+    frozen tail: AdamW skips parameters without a gradient, src/train_setup.py:42-45 + src/vae.py:340-349)"""
+    ps = list(model.parameters())
+    return [p for p in ps if p.requires_grad] + [p for p in ps if not p.requires_grad]
+
+
 class Engine:
     def __init__(self, model, args):
         L.load()
@@ -263,7 +270,8 @@ class Engine:
             self.dec_layers.append(d)
         self.dmol = isinstance(model.likelihood, DmolNet)
         # flat gradient bucket with per-parameter views (the one buffer DDP all-reduces)
-        self.params = [p for p in model.parameters()]
+        self.params = ordered_params(model)
+        self.generation = 0  # bumped by every training forward: guards flat_grad against interleaved fwd/bwd pairs
         n = sum(p.numel() for p in self.params)
         self.flat_grad = torch.zeros(n, device=self.device, dtype=torch.float32)
         self.grad_of: Dict[int, torch.Tensor] = {}
@@ -276,7 +284,7 @@ class Engine:
 
     @staticmethod
     def param_signature(model):
-        return tuple(p.data_ptr() for p in model.parameters())
+        return tuple((p.data_ptr(), p.requires_grad) for p in model.parameters())
 
     def g(self, p: Optional[torch.Tensor]):
         return None if p is None else self.grad_of[id(p)]
@@ -693,7 +701,12 @@ class Engine:
         if with_x:
             io.x = torch.zeros(N, self.C, self.R, self.R, device=self.device, dtype=torch.float32)
         io.pa_in = [torch.zeros(N, self.ctx, device=self.device, dtype=torch.float32) for _ in range(n_pa)]
-        io.pa, io.pa_sto, io.drop_launch = [], [], []
+        io.pa, io.pa_sto = [], []
+        # live hyper-parameters as DEVICE scalars {beta, p_sto scale of the conditioning dropout}: the kernels read them
+        # at run time, so a captured CUDA graph follows beta annealing (src/trainer.py:52-57) and the per-step
+        # dropout draw (src/vae.py:234-249) without re-capture
+        io.hyp = torch.ones(4, device=self.device, dtype=torch.float32)
+        io.hyp_host = torch.ones(4, dtype=torch.float32)  # pageable on purpose: the H2D copy snapshots it at call time
         resolutions = sorted({d.st.res for d in self.dec_layers})
         drop = self.model.decoder.is_drop_cond and self.cond_prior
         for t in io.pa_in:
@@ -701,13 +714,12 @@ class Engine:
             for res in resolutions:
                 v = new_act(N, res, res, self.ctx, self.device)
                 prog.call("cg_parents_plane", t.data_ptr(), self.ctx, 1, v.ptr, N, self.ctx, v.C, res * res, v.ns,
-                          self.ctx, 1.0)
+                          self.ctx, 1.0, None)
                 planes[res] = v
                 if drop:  # src/vae.py:244-247: channels 2: scaled by p_sto on the stochastic (prior) path
                     vs = new_act(N, res, res, self.ctx, self.device)
-                    ln = prog.call("cg_parents_plane", t.data_ptr(), self.ctx, 1, vs.ptr, N, self.ctx, vs.C, res * res,
-                                   vs.ns, 2, 1.0)
-                    io.drop_launch.append(ln)
+                    prog.call("cg_parents_plane", t.data_ptr(), self.ctx, 1, vs.ptr, N, self.ctx, vs.C, res * res,
+                              vs.ns, 2, 1.0, io.hyp.data_ptr() + 4)
                     planes_sto[res] = vs
                 else:
                     planes_sto[res] = v
@@ -742,7 +754,7 @@ class Engine:
         prog.add(L.Launch("cg_dmol_loss_fwd" if self.dmol else "cg_dgauss_nll_fwd", C.byref(la)))
         npix = float(self.C * self.R * self.R)
         prog.fin = prog.call("cg_elbo_finalize", prog.nll.data_ptr(), prog.kl_rows.data_ptr(), prog.out3.data_ptr(),
-                             N, max(nsto, 1), 1.0 / npix, 1.0)
+                             N, max(nsto, 1), 1.0 / npix, 1.0, io.hyp.data_ptr())
         prog.n_fwd = len(prog.launches)
         if train:
             prog.beta_users = []
@@ -763,17 +775,25 @@ class Engine:
                 prog.add(L.Launch("cg_dgauss_nll_bwd", C.byref(lb))).keep = (lb, dh)
             acts_grad: Dict[int, View] = {}
             self._decoder_bwd(prog, D, dh, N, 1.0 / (N * npix), acts_grad, explicit_eps)
+            for lb in D.latent_bwd_args:  # g_kl = (1 / (N * npix)) * live beta
+                lb.g_kl_dev = io.hyp.data_ptr()
             self._encoder_bwd(prog, e, acts_grad, N)
             prog.npix = npix
         return prog
 
-    def set_beta(self, prog: Program, beta: float, N: int):
-        args = list(prog.fin.args)
-        args[-1] = C.c_float(beta)
-        prog.fin.args = tuple(args)
-        if hasattr(prog.D, "latent_bwd_args"):
-            for lb in prog.D.latent_bwd_args:
-                lb.g_kl = beta / (N * prog.npix)
+    @staticmethod
+    def set_hyper(prog: Program, beta: Optional[float] = None, drop_sto: Optional[float] = None):
+        """update the program's device scalars (stream-ordered 16-byte copy, issued only when a value changed; never
+        inside a graph capture -- captured programs read the scalars at replay time)"""
+        io = prog.io
+        new = io.hyp_host.clone()
+        if beta is not None:
+            new[0] = float(beta)
+        if drop_sto is not None:
+            new[1] = float(drop_sto)
+        if not torch.equal(new, io.hyp_host):
+            io.hyp_host.copy_(new)
+            io.hyp.copy_(io.hyp_host)
 
     def build_decode(self, N: int, kind: str, given: Optional[Sequence[bool]] = None, n_pa: int = 1,
                      want_stats: bool = False) -> Program:

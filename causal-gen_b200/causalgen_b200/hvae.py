@@ -42,18 +42,23 @@ class _ElboFn(torch.autograd.Function):
     def forward(ctx, model, x, parents, beta, eps, *params):
         out3 = model._run_elbo(x, parents, beta, eps, train=True)
         ctx.model = model
-        ctx.nparams = len(params)
+        ctx.generation = model._engine_or_none().generation
+        ctx.param_ids = [id(p) for p in params]
         return out3[0].clone()
 
     @staticmethod
     def backward(ctx, g):
         eng = ctx.model._engine_or_none()
+        if eng is None or eng.generation != ctx.generation:
+            raise RuntimeError("causalgen_b200: another training forward ran before this backward; the engine keeps ONE "
+                               "gradient bucket, so call backward() right after each forward() (gradient accumulation "
+                               "over micro-batches works that way)")
         flat = eng.flat_grad * g  # one op; views of the copy are safe for autograd to keep
-        grads, off = [], 0
+        by_id, off = {}, 0
         for p in eng.params:
-            grads.append(flat[off: off + p.numel()].view_as(p) if p.requires_grad else None)
+            by_id[id(p)] = flat[off: off + p.numel()].view_as(p) if p.requires_grad else None
             off += p.numel()
-        return (None, None, None, None, None) + tuple(grads)
+        return (None, None, None, None, None) + tuple(by_id[i] for i in ctx.param_ids)
 
 
 class HVAE(nn.Module):
@@ -111,11 +116,7 @@ class HVAE(nn.Module):
     def _load_parents(self, prog, io, plist: Sequence[Tensor], training_drop: Optional[Tuple[float, float]] = None):
         for buf, pa in zip(io.pa_in, plist):
             buf.copy_(_pa_vector(pa).to(torch.float32))
-        for ln in io.drop_launch:
-            scale = 1.0 if training_drop is None else float(training_drop[0])
-            a = list(ln.args)
-            a[-1] = C.c_float(scale)
-            ln.args = tuple(a)
+        Engine.set_hyper(prog, drop_sto=1.0 if training_drop is None else float(training_drop[0]))
 
     def _set_noise(self, D, eps: Optional[Sequence[Tensor]], log_t: float, bwd=None):
         seed = self._seed()
@@ -153,20 +154,15 @@ class HVAE(nn.Module):
             drop = self.drop_cond()
         self._load_parents(prog, prog.io, [parents], drop)
         self._set_noise(prog.D, eps, 0.0, getattr(prog.D, "latent_bwd_args", None))
-        eng.set_beta(prog, float(beta), N) if train else self._set_beta_fwd(prog, float(beta))
+        eng.set_hyper(prog, beta=float(beta))
         for t in prog.zero:
             t.zero_()
         if train:
             eng.flat_grad.zero_()
+            eng.generation += 1
         eng.pack_weights()
         prog.run()
         return prog.out3
-
-    @staticmethod
-    def _set_beta_fwd(prog, beta):
-        a = list(prog.fin.args)
-        a[-1] = C.c_float(beta)
-        prog.fin.args = tuple(a)
 
     def forward(self, x: Tensor, parents: Tensor, beta: float = 1, eps: Optional[Sequence[Tensor]] = None
                 ) -> Dict[str, Tensor]:
@@ -281,11 +277,45 @@ class HVAE(nn.Module):
 # ---------------------------------------------------------------------------------------------
 # DSCM hot lines (src/pgm/dscm.py)
 # ---------------------------------------------------------------------------------------------
-def vae_preprocess(args, pa: Dict[str, Tensor]) -> Tensor:
-    """src/pgm/dscm.py:121-132 without the (B,ctx,R,R) materialisation: returns (B, ctx) on the GPU;
-    every entry point of ``HVAE`` accepts either form."""
+# UKBB attribute ranges (max, min) of the PGM's [-1,1] normalisation (src/datasets.py:89-98) and the log-standardisation
+# constants the released UKBB HVAE was trained with (src/pgm/dscm.py:112-117)
+_UKBB_MAX_MIN = {"age": (73.0, 44.0), "brain_volume": (1629520.0, 841919.0),
+                 "ventricle_volume": (157075.0, 7613.27001953125)}
+_UKBB_LOG_STD = {"age": (4.112339973449707, 0.11769197136163712),
+                 "brain_volume": (13.965583801269531, 0.09537758678197861),
+                 "ventricle_volume": (10.345998764038086, 0.43127763271331787)}
+
+
+def ukbb_preprocess(pa: Dict[str, Tensor]) -> Dict[str, Tensor]:
+    """src/pgm/dscm.py:98-118: undo the PGM's [-1,1] normalisation of the continuous UKBB parents, then
+    log-standardise them the way the UKBB HVAE saw them in training.  Host-side control plane (B scalars per
+    attribute).  Like the reference, an attribute other than mri_seq / sex / the three known ones cannot be mapped
+    back (the reference fails on `_max, _min = None`); here that is a KeyError naming the attribute."""
+    out = dict(pa)
+    for k, v in pa.items():
+        if k in ("mri_seq", "sex"):
+            continue
+        if k not in _UKBB_MAX_MIN:
+            raise KeyError(f"ukbb_preprocess: no (max, min) statistics for parent '{k}' (src/datasets.py:89-98)")
+        mx, mn = _UKBB_MAX_MIN[k]
+        out[k] = ((v + 1) / 2) * (mx - mn) + mn
+    for k, v in out.items():
+        if k in _UKBB_LOG_STD:
+            mu, sd = _UKBB_LOG_STD[k]
+            out[k] = (torch.log(v.clamp(min=1e-12)) - mu) / sd
+    return out
+
+
+def vae_preprocess(args, pa: Dict[str, Tensor], expand: bool = False) -> Tensor:
+    """src/pgm/dscm.py:121-132.  Returns (B, ctx) on the GPU -- every entry point of ``HVAE`` accepts that or the
+    reference's materialised (B, ctx, R, R) form (``expand=True`` produces it)."""
+    if "ukbb" in getattr(args, "dataset", ""):
+        pa = ukbb_preprocess(pa)
     cols = [pa[k] if pa[k].dim() > 1 else pa[k][..., None] for k in args.parents_x]
-    return torch.cat(cols, dim=1).cuda().float()
+    out = torch.cat(cols, dim=1)
+    if expand:
+        out = out[..., None, None].repeat(1, 1, args.input_res, args.input_res)
+    return (out.cuda() if torch.cuda.is_available() else out).float()  # host glue; every HVAE entry needs the GPU
 
 
 @torch.no_grad()

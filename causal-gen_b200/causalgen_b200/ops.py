@@ -214,6 +214,8 @@ class ConvLayer:
             a.bias, a.bias_n = self.bias.data_ptr(), self.cout_l
         ln = L.Launch("cg_conv2d", C.byref(a))
         ln.keep = (a, srcs, segs)
+        # bf16 (input + output) activation bytes of the conv, LOGICAL channels (no padding, no fused operands)
+        ln.algo_bytes = 2 * N * H * W * (self.cin_l + self.cout_l)
         return ln
 
     def dgrad(self, i: int, dy: View, seg: SegSpec, N, H, W) -> L.Launch:
@@ -227,6 +229,7 @@ class ConvLayer:
         a.wpack = self.wpack_bwd[i].data_ptr()
         ln = L.Launch("cg_conv2d", C.byref(a))
         ln.keep = (a, dy, seg)
+        ln.algo_bytes = 2 * N * H * W * (self.cout_l + self.src_logical[i])
         return ln
 
     def wgrad(self, srcs: Sequence[View], dy: View, dw: torch.Tensor, db: Optional[torch.Tensor], N, H, W) -> L.Launch:
@@ -242,4 +245,5 @@ class ConvLayer:
             a.src_log[i], a.src_off[i] = self.src_logical[i], self.src_off[i]
         ln = L.Launch("cg_conv2d_wgrad", C.byref(a))
         ln.keep = (a, srcs, dy, dw, db)
+        ln.algo_bytes = 2 * N * H * W * (self.cin_l + self.cout_l) + 4 * self.weight.numel()
         return ln

@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const cg_latent_bwd_arg
   const int zd = a.zdim;
   const int tid = threadIdx.x;
   const uint64_t seed = a.seed + (a.seed_dev != nullptr ? *a.seed_dev : 0ull);
+  const float g_kl = a.g_kl * (a.g_kl_dev != nullptr ? __ldg(a.g_kl_dev) : 1.0f);
   if (a.mode != 2) {
     for (int e = tid; e < zd * kLatPix; e += 256) {
       int c = e / kLatPix, px = e - c * kLatPix;
@@ -256,10 +257,10 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const cg_latent_bwd_arg
       if (a.mode == 0) {
         const float q_loc = a.q[pix * a.q_ld + c], q_ls = a.q[pix * a.q_ld + zd + c];
         const float eq = __expf(q_ls), ivp = __expf(-2.0f * p_ls), dm = q_loc - p_loc;
-        g_qloc[k] = a.g_kl * dm * ivp + dz[k];
-        g_qls[k] = a.g_kl * (eq * eq * ivp - 1.0f) + dz[k] * eq * s_eps[c][px];
-        g_ploc[k] = -a.g_kl * dm * ivp;
-        g_pls[k] = a.g_kl * (1.0f - (eq * eq + dm * dm) * ivp);
+        g_qloc[k] = g_kl * dm * ivp + dz[k];
+        g_qls[k] = g_kl * (eq * eq * ivp - 1.0f) + dz[k] * eq * s_eps[c][px];
+        g_ploc[k] = -g_kl * dm * ivp;
+        g_pls[k] = g_kl * (1.0f - (eq * eq + dm * dm) * ivp);
       } else if (a.mode == 1) {
         g_ploc[k] = dz[k];
         g_pls[k] = dz[k] * __expf(p_ls) * s_eps[c][px];
@@ -347,6 +348,7 @@ __global__ void __launch_bounds__(256) latent_bwd_stream_kernel(const cg_latent_
   const int oc = (int)(item & 1);
   const long long pix = (long long)n * a.HW + hw;
   const uint64_t seed = a.seed + (a.seed_dev != nullptr ? *a.seed_dev : 0ull);
+  const float g_kl = a.g_kl * (a.g_kl_dev != nullptr ? __ldg(a.g_kl_dev) : 1.0f);
   float pl[8], ps[8], e[8], dz[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const float4* pp = reinterpret_cast<const float4*>(a.p + pix * a.p_ld + oc * 8);
   const float4* pq = reinterpret_cast<const float4*>(a.p + pix * a.p_ld + 16 + oc * 8);
@@ -365,10 +367,10 @@ __global__ void __launch_bounds__(256) latent_bwd_stream_kernel(const cg_latent_
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float eq = __expf(qs[k]), ivp = __expf(-2.0f * ps[k]), dm = ql[k] - pl[k];
-      g_qloc[k] = a.g_kl * dm * ivp + dz[k];
-      g_qls[k] = a.g_kl * (eq * eq * ivp - 1.0f) + dz[k] * eq * e[k];
-      g_ploc[k] = -a.g_kl * dm * ivp;
-      g_pls[k] = a.g_kl * (1.0f - (eq * eq + dm * dm) * ivp);
+      g_qloc[k] = g_kl * dm * ivp + dz[k];
+      g_qls[k] = g_kl * (eq * eq * ivp - 1.0f) + dz[k] * eq * e[k];
+      g_ploc[k] = -g_kl * dm * ivp;
+      g_pls[k] = g_kl * (1.0f - (eq * eq + dm * dm) * ivp);
     }
     bf16* q0 = reinterpret_cast<bf16*>(a.dq) + n * a.dq_ns + hw * 8;
     *reinterpret_cast<uint4*>(q0 + (long long)oc * a.HW * 8) = cg_pack8(g_qloc);

@@ -6,7 +6,10 @@
 
 namespace {
 
-__global__ void sumsq_kernel(const float* __restrict__ g, float* __restrict__ out, long long n) {
+// partials != nullptr: block b writes its partial sum to partials[b] (no atomics) and sumsq_final_kernel adds them in a
+// fixed order -> bit-identical result on every data-parallel replica (their clip coefficients must agree exactly)
+__global__ void sumsq_kernel(const float* __restrict__ g, float* __restrict__ out, long long n,
+                             float* __restrict__ partials) {
   float acc = 0.f;
   const long long n4 = n / 4;
   const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -25,7 +28,22 @@ __global__ void sumsq_kernel(const float* __restrict__ g, float* __restrict__ ou
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
-    atomicAdd(out, s);
+    if (partials != nullptr) partials[blockIdx.x] = s;
+    else atomicAdd(out, s);
+  }
+}
+
+__global__ void sumsq_final_kernel(const float* __restrict__ partials, int n, float* __restrict__ out) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partials[i];  // fixed assignment, fixed tree below
+  acc = cg_warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+    out[0] = s;
   }
 }
 
@@ -88,13 +106,19 @@ __global__ void adamw_ema_kernel(float* __restrict__ p, const float* __restrict_
 
 }  // namespace
 
-extern "C" int cg_sumsq(const float* g, float* out, int64_t n, void* stream) {
+extern "C" int cg_sumsq(const float* g, float* out, int64_t n, float* scratch, int32_t scratch_n, void* stream) {
   CG_ARCH_GUARD();
   CG_REQUIRE(((uintptr_t)g & 15) == 0, "cg_sumsq: unaligned");
   int blocks = (int)((n + 2047) / 2048);
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
-  sumsq_kernel<<<blocks, 256, 0, cg_stream(stream)>>>(g, out, n);
+  if (scratch != nullptr) {
+    CG_REQUIRE(scratch_n >= 148 * 4, "cg_sumsq: scratch needs %d floats", 148 * 4);
+    sumsq_kernel<<<blocks, 256, 0, cg_stream(stream)>>>(g, out, n, scratch);
+    sumsq_final_kernel<<<1, 256, 0, cg_stream(stream)>>>(scratch, blocks, out);
+  } else {
+    sumsq_kernel<<<blocks, 256, 0, cg_stream(stream)>>>(g, out, n, nullptr);
+  }
   CG_LAUNCH_CHECK("cg_sumsq");
   return CG_OK;
 }

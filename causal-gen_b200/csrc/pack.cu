@@ -62,7 +62,8 @@ __global__ void normalise_u8_kernel(const uint8_t* __restrict__ x8, float* __res
 // spatially constant parents -> bf16 planar (N, C/8, HW, 8)
 __global__ void parents_plane_kernel(const float* __restrict__ pa, long long sstride, long long cstride,
                                      bf16* __restrict__ out, int N, int ctx, int C8, int HW, long long ns, int drop_from,
-                                     float drop_scale) {
+                                     float drop_scale, const float* __restrict__ drop_scale_dev) {
+  if (drop_scale_dev != nullptr) drop_scale = __ldg(drop_scale_dev);  // device scalar: replayable from a CUDA graph
   const long long total = (long long)N * C8 * HW;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int hw = (int)(i % HW), c8 = (int)((i / HW) % C8), n = (int)(i / ((long long)HW * C8));
@@ -184,7 +185,8 @@ __global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ 
 }
 
 __global__ void elbo_finalize_kernel(const float* __restrict__ nll, const float* __restrict__ kl, float* __restrict__ out,
-                                     int N, int nblk, float kl_scale, float beta) {
+                                     int N, int nblk, float kl_scale, float beta, const float* __restrict__ beta_dev) {
+  if (beta_dev != nullptr) beta = __ldg(beta_dev);  // device scalar: beta annealing under graph replay
   float a = 0.f, b = 0.f;
   for (int i = threadIdx.x; i < N; i += 32) {
     a += nll[i];
@@ -228,11 +230,11 @@ static inline int glue_grid(long long work) {
 
 extern "C" int cg_parents_plane(const float* pa, int64_t sample_stride, int64_t chan_stride, void* out, int32_t N,
                                 int32_t ctx, int32_t C, int32_t HW, int64_t ns, int32_t drop_from, float drop_scale,
-                                void* stream) {
+                                const float* drop_scale_dev, void* stream) {
   CG_ARCH_GUARD();
   CG_REQUIRE(C % 8 == 0 && C >= ctx && ns % 8 == 0, "cg_parents_plane: C=%d ctx=%d", C, ctx);
   parents_plane_kernel<<<glue_grid((long long)N * (C / 8) * HW), 256, 0, cg_stream(stream)>>>(
-      pa, sample_stride, chan_stride, reinterpret_cast<bf16*>(out), N, ctx, C / 8, HW, ns, drop_from, drop_scale);
+      pa, sample_stride, chan_stride, reinterpret_cast<bf16*>(out), N, ctx, C / 8, HW, ns, drop_from, drop_scale, drop_scale_dev);
   CG_LAUNCH_CHECK("cg_parents_plane");
   return CG_OK;
 }
@@ -295,9 +297,9 @@ extern "C" int cg_add(const void* a, const void* b, void* y, int32_t N, int32_t 
 }
 
 extern "C" int cg_elbo_finalize(const float* nll, const float* kl, float* out, int32_t N, int32_t nblk, float kl_scale,
-                                float beta, void* stream) {
+                                float beta, const float* beta_dev, void* stream) {
   CG_ARCH_GUARD();
-  elbo_finalize_kernel<<<1, 32, 0, cg_stream(stream)>>>(nll, kl, out, N, nblk, kl_scale, beta);
+  elbo_finalize_kernel<<<1, 32, 0, cg_stream(stream)>>>(nll, kl, out, N, nblk, kl_scale, beta, beta_dev);
   CG_LAUNCH_CHECK("cg_elbo_finalize");
   return CG_OK;
 }

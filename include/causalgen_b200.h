@@ -195,6 +195,8 @@ typedef struct {
   float g_kl;                 /* d loss / d kl[n]  (= beta / (B * C*H*W)) */
   void* dq; int64_t dq_ns; void* dp; int64_t dp_ns;
   int32_t N, HW, zdim, mode;
+  const float* g_kl_dev;      /* optional device scalar multiplied into g_kl (beta annealing under CUDA-graph replay,
+                                 src/trainer.py:52-57): g_kl then carries 1 / (B * C*H*W) and *g_kl_dev the live beta */
 } cg_latent_bwd_args;
 int cg_latent_bwd(const cg_latent_bwd_args* a, void* stream);
 
@@ -261,6 +263,7 @@ int cg_normalise_u8(const uint8_t* x8, float* x, int64_t n, void* stream);
  * src/vae.py:244-247).  This is the materialised parents[..., :res, :res] of src/vae.py:241 at bf16. */
 int cg_parents_plane(const float* pa, int64_t sample_stride, int64_t chan_stride, void* out, int32_t N,
                      int32_t ctx, int32_t C, int32_t HW, int64_t ns, int32_t drop_from, float drop_scale,
+                     const float* drop_scale_dev /* optional device scalar overriding drop_scale (graph replay) */,
                      void* stream);
 /* fp32 NCHW (N,C,H,W) <-> bf16 planar (latents in / out) */
 int cg_nchw_f32_to_planar(const float* x, void* y, int32_t N, int32_t C, int32_t HW, int64_t ns,
@@ -281,13 +284,16 @@ int cg_add(const void* a, const void* b, void* y, int32_t N, int32_t HW, int32_t
 /* kl rows (nblk, N): per-block per-sample KL sums.  kl_pp[n] = kl_scale * sum_blk kl[blk][n];
  * elbo = mean(nll) + beta*mean(kl_pp)  (src/vae.py:451-458); out[3] = {elbo,nll,kl} */
 int cg_elbo_finalize(const float* nll, const float* kl, float* out, int32_t N, int32_t nblk,
-                     float kl_scale, float beta, void* stream);
+                     float kl_scale, float beta, const float* beta_dev /* optional device scalar overriding beta */,
+                     void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Optimiser tail on flat fp32 buffers (src/trainer.py:66-87, src/train_setup.py:42-53,
  * src/utils.py:169-220): global-norm clip, NaN/skip test, AdamW, EMA -- no host sync.
  * ------------------------------------------------------------------------------------- */
-int cg_sumsq(const float* g, float* out /* [1] accumulated */, int64_t n, void* stream);
+/* scratch == NULL: out[0] += sum g^2 (atomics).  scratch (>= 592 floats) given: out[0] = sum g^2 through per-block
+ * partials added in a fixed order -- bit-identical on every data-parallel replica, so their clip coefficients agree */
+int cg_sumsq(const float* g, float* out, int64_t n, float* scratch, int32_t scratch_n, void* stream);
 /* Device-side step bookkeeping so the whole training step is CUDA-graph replayable:
  *   state[4] (int32): {adam step t, ema update calls, skipped updates, skip flag of this step}
  *   dyn[6]   (fp32) : {lr, 1-b1^t, 1-b2^t, ema decay, grad scale*clip coefficient, grad norm}

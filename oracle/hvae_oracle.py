@@ -690,13 +690,21 @@ def ema_decay(call_index: int, beta: float = 0.999, update_after: int = 100) -> 
     return min(max(1.0 - 1.0 / (1.0 + k), 0.0), beta)
 
 
+def warmup_lr(base_lr: float, step: int, warmup: int) -> float:
+    """lr used by optimizer.step() number `step` (1-based) under LambdaLR(linear_warmup(warmup)):
+    src/train_setup.py:47-50, src/utils.py:32-36 -- the scheduler has been stepped step-1 times"""
+    it = step - 1
+    return base_lr * (1.0 if (it > warmup or warmup <= 0) else it / warmup)
+
+
 def train_step_cpu(sd, cfg, x, pa_full, noise, opt_state, lr=1e-3, wd=0.01, betas=(0.9, 0.9),
-                   grad_clip=350.0, grad_skip=500.0, step=1, ema=None):
+                   grad_clip=350.0, grad_skip=500.0, step=1, ema=None, ema_update_after=100, beta=None,
+                   drop=(1.0, 1.0)):
     """One reference training step on CPU: src/trainer.py:62-87 + AdamW (src/train_setup.py:42-53).
-    ``sd`` tensors must have requires_grad=True.  Returns (out, grad_norm)."""
+    ``sd`` tensors must have requires_grad=True (frozen ones False).  Returns (out, grad_norm)."""
     for p in sd.values():
         p.grad = None
-    out = hvae_forward(sd, cfg, x, pa_full, noise, beta=cfg.beta)
+    out = hvae_forward(sd, cfg, x, pa_full, noise, beta=cfg.beta if beta is None else beta, drop=drop)
     out["elbo"].backward()
     params = [p for p in sd.values() if p.grad is not None]
     gn = torch.nn.utils.clip_grad_norm_(params, grad_clip)
@@ -713,5 +721,5 @@ def train_step_cpu(sd, cfg, x, pa_full, noise, opt_state, lr=1e-3, wd=0.01, beta
                 vh = v / (1 - betas[1] ** step)
                 p.addcdiv_(mh, vh.sqrt().add_(1e-8), value=-lr)
                 if ema is not None:  # ema.update() of the same (non-skipped) step, src/trainer.py:74-77
-                    ema[k].lerp_(p, 1.0 - ema_decay(step - 1))
+                    ema[k].lerp_(p, 1.0 - ema_decay(step - 1, update_after=ema_update_after))
     return out, gn

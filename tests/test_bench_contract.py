@@ -25,6 +25,17 @@ def test_reference_arm_prints_one_json_line():
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
+def test_reference_arm_runs_the_staged_reference_itself():
+    """with baseline/_ref staged (build container / GPU box) the arm times the UNMODIFIED reference (kind = reference)"""
+    import pytest
+    if not os.path.exists(os.path.join(ROOT, "baseline", "_ref", "src", "vae.py")):
+        pytest.skip("reference not staged (run __graft_entry__.build() where /root/reference exists)")
+    r = _run(["--impl", "reference", "--config", "morphomnist", "--steps", "1", "--warmup", "1", "--cpu-batch", "4"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.strip()][-1])
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "reference" and d["value"] > 0
+
+
 def test_reference_arm_other_ranks_exit_quietly():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],

@@ -240,3 +240,28 @@ def test_fresh_init_is_bit_identical_to_the_reference(name):
         h.update(v.detach().cpu().contiguous().numpy().tobytes())
     assert len(sd) == want["tensors"] and sum(p.numel() for p in model.parameters()) == want["params"]
     assert h.hexdigest() == want["sha256"]
+
+
+def test_vae_preprocess_matches_reference_functions():
+    """src/pgm/dscm.py:98-132 incl. the UKBB log-standardisation branch, against vectors produced by executing the
+    reference's own function bodies (tests/golden/make_golden_preprocess.py)"""
+    from types import SimpleNamespace
+    from causalgen_b200 import vae_preprocess
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "preprocess.npz"))
+    pa = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("in_")}
+    a = SimpleNamespace(dataset="ukbb", input_res=8, parents_x=["mri_seq", "brain_volume", "ventricle_volume", "sex"])
+    src = {k: pa[k].clone() for k in a.parents_x}
+    got = vae_preprocess(a, src).cpu()
+    np.testing.assert_allclose(got.numpy(), g["ukbb_vae_pa"][:, :, 0, 0], rtol=1e-6, atol=1e-6)
+    assert all(torch.equal(src[k], pa[k]) for k in src), "caller's dict must not be modified"
+    full = vae_preprocess(a, {k: pa[k].clone() for k in a.parents_x}, expand=True).cpu()
+    np.testing.assert_allclose(full.numpy(), g["ukbb_vae_pa"], rtol=1e-6, atol=1e-6)
+    a2 = SimpleNamespace(dataset="ukbb", input_res=4, parents_x=["age", "sex"])
+    got = vae_preprocess(a2, {k: pa[k].clone() for k in a2.parents_x}).cpu()
+    np.testing.assert_allclose(got.numpy(), g["ukbb_age_vae_pa"][:, :, 0, 0], rtol=1e-6, atol=1e-6)
+    a3 = SimpleNamespace(dataset="morphomnist", input_res=4, parents_x=["brain_volume", "digit"])
+    got = vae_preprocess(a3, {"brain_volume": pa["brain_volume"][:, 0].clone(), "digit": pa["digit"]}).cpu()
+    np.testing.assert_allclose(got.numpy(), g["plain_vae_pa"][:, :, 0, 0], rtol=0, atol=0)
+    with pytest.raises(KeyError):
+        vae_preprocess(a, {"mri_seq": pa["mri_seq"], "brain_volume": pa["brain_volume"], "ventricle_volume": pa["sex"],
+                           "sex": pa["sex"], "thickness": pa["age"]})

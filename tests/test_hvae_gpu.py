@@ -22,6 +22,7 @@ import pytest
 import torch
 
 import hvae_oracle as O
+from conftest import parity_report
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -65,9 +66,13 @@ def oracle_elbo(cfg, sd, x, pa_full, emulate):
     return out, sdr, tape
 
 
-@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("name", list(CASES) + ["tiny_ukbb+q_correction"])
 def test_elbo_kl_and_gradients(name):
-    cfg, sd, model, x, pa, _ = build(name)
+    over = {}
+    if name.endswith("+q_correction"):  # src/vae.py:255-263,297: prior reads h, no z stream / z_feat_proj
+        name, over = name.split("+")[0], dict(q_correction=True)
+    cfg, sd, model, x, pa, _ = build(name, **over)
+    name = name + ("+qc" if over else "")
     pa_full = O.expand_parents(pa, cfg.input_res)
     ref, sd32, tape = oracle_elbo(cfg, sd, x, pa_full, False)
     emu, sd16, _ = oracle_elbo(cfg, sd, x, pa_full, True)
@@ -76,11 +81,21 @@ def test_elbo_kl_and_gradients(name):
     out = model(x.to(DEV), pa_full.to(DEV), beta=cfg.beta, eps=eps)
     out["elbo"].backward()
     torch.cuda.synchronize()
+    T = f"elbo[{name}]"
     for k in ("elbo", "nll", "kl"):
+        parity_report(T, f"{k} rel", abs(out[k].item() - ref[k].item()) / abs(ref[k].item()), 5e-3,
+                      f"bf16-emulated oracle: {abs(emu[k].item() - ref[k].item()) / abs(ref[k].item()):.2e}")
         np.testing.assert_allclose(out[k].item(), ref[k].item(), rtol=5e-3, err_msg=f"{name} {k}")
+    # per-block KL sums (rel <= 1e-2): every (sample, block) within 1e-2 of its reference value, plus an
+    # absolute floor of 1e-3 of the sample's total KL for blocks whose KL is ~0
     bk, rk = model.block_kl().cpu(), ref["block_kl"].detach()
-    tol = 3e-2 * rk.abs() + 2e-3 * rk.abs().sum(1, keepdim=True) + 1e-3
-    assert bool(((bk - rk).abs() <= tol).all()), f"{name} block KL: {(bk - rk).abs().max()} vs {rk.abs().max()}"
+    tol = 1e-2 * rk.abs() + 1e-3 * rk.abs().sum(1, keepdim=True)
+    worst = float(((bk - rk).abs() / tol).max())
+    big = rk.abs() >= 1e-2 * rk.abs().max()
+    parity_report(T, "block KL max rel (blocks>=1% max)", float(((bk - rk).abs() / rk.abs())[big].max()), 1e-2)
+    parity_report(T, "block KL worst |d|/tol", worst, 1.0, "tol = 1e-2*|ref| + 1e-3*sum|ref|")
+    parity_report(T, "block KL rel-L2", rel_l2(bk, rk), 5e-3)
+    assert worst <= 1.0, f"{name} block KL: {(bk - rk).abs().max()} vs {rk.abs().max()}"
     assert rel_l2(bk, rk) <= 5e-3, f"{name} block KL rel-L2 {rel_l2(bk, rk):.4g}"
     # gradients vs fp32, bounded by the measured bf16-storage drift of the algorithm itself
     named = dict(model.named_parameters())
@@ -99,6 +114,7 @@ def test_elbo_kl_and_gradients(name):
             if r > max(5e-2, 2 * drift + 2e-2):
                 bad.append((k, round(r, 4), round(drift, 4)))
     glob, gdrift = (num / den) ** 0.5, (dnum / den) ** 0.5
+    parity_report(T, "grad global rel-L2", glob, max(1.5e-2, 2 * gdrift), f"bf16-emulated oracle drift {gdrift:.2e}")
     assert glob <= max(1.5e-2, 2 * gdrift), f"{name} global grad rel-L2 {glob:.4f} (drift {gdrift:.4f})"
     assert not bad, f"{name} per-tensor grad outliers (name, rel, drift): {bad[:8]}"
 
@@ -111,6 +127,8 @@ def px_stats(a, b):
 def assert_pixels(ours, ref, emu, what):
     m, p99 = px_stats(ours, ref)
     dm, dp99 = px_stats(emu, ref)
+    parity_report("pixels", f"{what} mean|d| *255", m * 255, max(1.0, 1.5 * dm * 255), f"emulated drift {dm * 255:.3f}")
+    parity_report("pixels", f"{what} p99|d| *255", p99 * 255, max(2.0, 1.5 * dp99 * 255), f"emulated drift {dp99 * 255:.3f}")
     assert m <= max(1 / 255, 1.5 * dm), f"{what}: mean |d| {m:.5f} vs bf16 drift {dm:.5f}"
     assert p99 <= max(2 / 255, 1.5 * dp99), f"{what}: p99 |d| {p99:.5f} vs bf16 drift {dp99:.5f}"
 

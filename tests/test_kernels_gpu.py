@@ -642,7 +642,8 @@ def test_mix_cf_and_layout_glue():
     assert_close(back, t.to(torch.bfloat16).float(), 1e-6, "layout round trip")
     pa = rnd(3, 12, seed=31)
     pl = torch.zeros(3, 2, 5, 5, 8, device=DEV, dtype=torch.bfloat16)
-    L.check(lib.cg_parents_plane(pa.data_ptr(), 12, 1, pl.data_ptr(), 3, 12, 16, 25, ns_of(pl), 2, 0.0, stream()))
+    L.check(lib.cg_parents_plane(pa.data_ptr(), 12, 1, pl.data_ptr(), 3, 12, 16, 25, ns_of(pl), 2, 1.0,
+                                 torch.zeros(1, device=DEV).data_ptr(), stream()))  # device scalar overrides the 1.0
     want = pa.clone()
     want[:, 2:] = 0
     assert_close(to_nchw(pl, 12), want.to(torch.bfloat16).float()[:, :, None, None].expand(3, 12, 5, 5), 1e-6, "parents plane")
@@ -678,7 +679,7 @@ def test_optimizer_tail_matches_torch_adamw():
             opt.step()
             sched.step()
         ss.zero_()
-        L.check(lib.cg_sumsq(g.data_ptr(), ss.data_ptr(), n, stream()))
+        L.check(lib.cg_sumsq(g.data_ptr(), ss.data_ptr(), n, None, 0, stream()))
         L.check(lib.cg_optim_advance(state.data_ptr(), dyn.data_ptr(), ss.data_ptr(), None, 1e-3, 100, 0.9, 0.9, 350.0,
                                      500.0, 1.0, 0.999, 100, stream()))
         L.check(lib.cg_adamw_ema_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), ema.data_ptr(), n,
@@ -707,3 +708,31 @@ def test_ema_decay_schedule_on_device():
     want = [O.ema_decay(s, 0.999, 100) for s in range(130)]
     assert max(abs(a - b) for a, b in zip(got, want)) <= 1e-6, list(zip(got, want))[98:106]
     assert state[1].item() == 130 and state[2].item() == 0
+
+
+def test_normalise_u8_and_deterministic_sumsq():
+    """cg_normalise_u8 == trainer.preprocess_batch (src/trainer.py:17) bit for bit on every uint8 value (fixture produced by
+    the reference function, tests/golden/preprocess.npz); cg_sumsq with scratch is run-to-run bit-identical"""
+    import os
+    import numpy as np
+    from causalgen_b200 import _lib as L
+    lib = L.load()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "preprocess.npz"))
+    x8 = torch.from_numpy(g["x8"]).to(DEV)
+    out = torch.empty(x8.shape, device=DEV, dtype=torch.float32)
+    L.check(lib.cg_normalise_u8(x8.data_ptr(), out.data_ptr(), x8.numel(), stream()))
+    assert torch.equal(out.cpu(), torch.from_numpy(g["x_norm"]))
+    allv = torch.arange(256, dtype=torch.uint8, device=DEV).repeat(5)[:1279]  # ragged length, every value
+    out = torch.empty(allv.numel(), device=DEV, dtype=torch.float32)
+    L.check(lib.cg_normalise_u8(allv.data_ptr(), out.data_ptr(), allv.numel(), stream()))
+    assert torch.equal(out.cpu(), (allv.cpu().float() - 127.5) / 127.5)
+    n = 3_000_003
+    v = torch.randn(n, device=DEV)
+    scratch = torch.zeros(592, device=DEV)
+    res = []
+    for _ in range(3):
+        o = torch.zeros(1, device=DEV)
+        L.check(lib.cg_sumsq(v.data_ptr(), o.data_ptr(), n, scratch.data_ptr(), 592, stream()))
+        res.append(o.item())
+    assert res[0] == res[1] == res[2]
+    assert abs(res[0] - float((v.double() ** 2).sum())) <= 1e-5 * res[0]
