@@ -32,7 +32,7 @@ class ConvArgs(C.Structure):
     _fields_ = [("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("ksize", C.c_int32), ("act", C.c_int32),
                 ("nsrc", C.c_int32), ("nseg", C.c_int32), ("cout", C.c_int32),
                 ("src", Src * CG_MAX_SRC), ("seg", Seg * CG_MAX_SEG),
-                ("wpack", C.c_void_p), ("bias", C.c_void_p), ("bias_n", C.c_int32), ("_pad", C.c_int32)]
+                ("wpack", C.c_void_p), ("bias", C.c_void_p), ("bias_n", C.c_int32), ("nc", C.c_int32)]
 
 
 class PackDesc(C.Structure):
@@ -66,7 +66,7 @@ class LatentBwdArgs(C.Structure):
                 ("dz", C.c_void_p), ("dz_ns", C.c_int64), ("g_kl", C.c_float),
                 ("dq", C.c_void_p), ("dq_ns", C.c_int64), ("dp", C.c_void_p), ("dp_ns", C.c_int64),
                 ("N", C.c_int32), ("HW", C.c_int32), ("zdim", C.c_int32), ("mode", C.c_int32),
-                ("g_kl_dev", C.c_void_p)]
+                ("g_kl_dev", C.c_void_p), ("log_t", C.c_float), ("_pad", C.c_int32)]
 
 
 class DGaussArgs(C.Structure):
@@ -92,7 +92,9 @@ _SIGNATURES = {
     "cg_device_sms": (C.c_int, []),
     "cg_conv2d": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "cg_conv_nchunk": (C.c_int32, [C.c_int32, C.c_int32]),
+    "cg_conv_nchunk_ex": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32]),
     "cg_packed_weight_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "cg_packed_weight_bytes_nc": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "cg_pack_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "cg_conv2d_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
     "cg_conv2d_wgrad_launches": (C.c_int32, [C.POINTER(WgradArgs)]),
@@ -112,11 +114,13 @@ _SIGNATURES = {
     "cg_dgauss_nll_fwd": (C.c_int, [C.POINTER(DGaussArgs), C.c_void_p]),
     "cg_dgauss_nll_bwd": (C.c_int, [C.POINTER(DGaussArgs), C.c_void_p]),
     "cg_dgauss_sample": (C.c_int, [C.POINTER(DGaussArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
+    "cg_dgauss_sample_bwd": (C.c_int, [C.POINTER(DGaussArgs), C.c_void_p, C.c_void_p, C.c_void_p]),
     "cg_dmol_loss_fwd": (C.c_int, [C.POINTER(DmolArgs), C.c_void_p]),
     "cg_dmol_loss_bwd": (C.c_int, [C.POINTER(DmolArgs), C.c_void_p]),
     "cg_dmol_predict": (C.c_int, [C.POINTER(DmolArgs), C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
     "cg_cf_combine": (C.c_int, [C.c_void_p] * 8 + [C.c_int64, C.c_void_p]),
+    "cg_cf_combine_bwd": (C.c_int, [C.c_void_p] * 10 + [C.c_int64, C.c_void_p]),
     "cg_normalise_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "cg_parents_plane": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),

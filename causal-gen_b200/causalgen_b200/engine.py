@@ -206,7 +206,8 @@ class BlockLayers:
             act_i = L.ACT_NONE if (i > 0 and (self.mid_out_act != L.ACT_NONE or self.mid_dual)) else self.act
             self.layers.append(ConvLayer(eng.table, c.weight, c.bias, srcs, act_i,
                                          centre_only=centre and c.weight.shape[2] == 3,
-                                         grad_srcs=(grad_srcs if i == 0 else None)))
+                                         grad_srcs=(grad_srcs if i == 0 else None),
+                                         fwd_operands=(i == len(convs) - 1)))  # only a Block's last conv fuses adds
         self.proj = None
         if hasattr(mod, "width_proj"):
             self.proj = ConvLayer(eng.table, mod.width_proj.weight, mod.width_proj.bias, list(src_logical), L.ACT_NONE)
@@ -222,7 +223,18 @@ def ordered_params(model) -> List[torch.nn.Parameter]:
     """parameter order of the flat buffers: trainable first, frozen last (so optimiser kernels can stop before the
     frozen tail: AdamW skips parameters without a gradient, src/train_setup.py:42-45 + src/vae.py:340-349)"""
     ps = list(model.parameters())
-    return [p for p in ps if p.requires_grad] + [p for p in ps if not p.requires_grad]
+    dead = no_grad_param_ids(model)
+    live = [p for p in ps if p.requires_grad and id(p) not in dead]
+    return live + [p for p in ps if not (p.requires_grad and id(p) not in dead)]
+
+
+def no_grad_param_ids(model):
+    """parameters the forward never touches: the LAST decoder block's z_feat_proj (src/vae.py:297-300 skips it).  In the
+    reference their .grad stays None, so AdamW neither decays nor updates them; they are treated like frozen ones."""
+    blocks = getattr(getattr(model, "decoder", None), "blocks", None)
+    if not blocks or not hasattr(blocks[-1], "z_feat_proj"):
+        return set()
+    return {id(p) for p in blocks[-1].z_feat_proj.parameters()}
 
 
 class Engine:
@@ -549,7 +561,11 @@ class Engine:
         return dx
 
     def _decoder_bwd(self, prog: Program, D: Rec, dh_final: View, N, g_kl: float, acts_grad: Dict[int, View],
-                     explicit_eps: bool):
+                     explicit_eps: bool, dz_extra: Optional[Dict[int, List[View]]] = None,
+                     dz_out: Optional[Dict[int, View]] = None):
+        """Backward of _decoder_fwd.  `dz_extra[k]`: further gradients wrt the latent of stochastic block k (other decoder
+        passes of the same program consumed it: counterfactual training).  `dz_out`: for passes whose latents were GIVEN
+        (mode 3) the gradient wrt latent k is handed back here instead of going through a latent kernel."""
         dec = self.model.decoder
         zd = self.zd
         bias_param = {r: p for (r, _), p in zip(dec.bias_res, dec.bias)}
@@ -574,6 +590,13 @@ class Engine:
             # z_proj (no activation on its input)
             prog.add(d.z_proj.wgrad([r.z, r.pa], dh3, self.g(d.z_proj.weight), self.g(d.z_proj.bias), N, res, res))
             prog.add(d.z_proj.dgrad(0, dh3, SegSpec(dz, 0, add=dz if dz_written else None), N, res, res))
+            if dz_extra is not None and st.stochastic:
+                for ex in dz_extra.get(r.ksto, []):
+                    prog.call("cg_add", dz.ptr, ex.ptr, dz.ptr, N, res * res, dz.C, dz.ns, ex.ns, dz.ns)
+            if r.mode == 3:  # given latent: its gradient leaves the pass; the prior statistics were dead (DP stays 0 there)
+                if dz_out is not None:
+                    dz_out[r.ksto] = dz
+                prog.keep.append((dz, DP))
             # latent
             lb = L.LatentBwdArgs()
             lb.p, lb.p_ld = r.pstat.ptr, r.pstat.ns
@@ -588,8 +611,9 @@ class Engine:
             lb.dz, lb.dz_ns, lb.g_kl = dz.ptr, dz.ns, g_kl
             lb.dp, lb.dp_ns = DP.ptr, DP.ns
             lb.N, lb.HW, lb.zdim, lb.mode = N, res * res, zd, r.mode
-            prog.add(L.Launch("cg_latent_bwd", C.byref(lb))).keep = (lb, dz, DP, dq)
-            D.latent_bwd_args.append(lb)
+            if r.mode != 3:
+                prog.add(L.Launch("cg_latent_bwd", C.byref(lb))).keep = (lb, dz, DP, dq)
+                D.latent_bwd_args.append(lb)
             # posterior: d h_in = dh3 (+ posterior path), d acts[res] accumulates over blocks
             if r.post is not None:
                 dh_in = new_act(N, res, res, st.cin, self.device)
@@ -824,11 +848,13 @@ class Engine:
             prog.lik_args.append(la)
         return prog
 
-    def build_counterfactual(self, N: int) -> Program:
+    def build_counterfactual(self, N: int, train: bool = False) -> Program:
         """DSCM.forward hot lines (src/pgm/dscm.py:52-56) as ONE program: encoder + posterior decoder pass (abduction,
         in-kernel Philox noise), two prior-only decoder passes on the abducted latents (counterfactual and observed
-        parents) reading the bf16 latents of the first pass in place, likelihood means, and the combine kernel."""
-        prog = Program(f"counterfactual(N={N})")
+        parents) reading the bf16 latents of the first pass in place, likelihood means, and the combine kernel.
+        `train`: also records `prog.bwd`, the hand-derived backward of the whole pass given d cf_x (`prog.dcf`): the
+        reference back-propagates aux_loss(cf_x) into the HVAE (src/pgm/dscm.py:78-88, src/pgm/train_cf.py:159-180)."""
+        prog = Program(f"counterfactual(N={N},train={train})")
         io = self._inputs(prog, N, with_x=True, n_pa=2)  # pa_in[0]: observed parents, pa_in[1]: counterfactual parents
         prog.io = io
         e = self._encoder_fwd(prog, io.x, N)
@@ -839,7 +865,7 @@ class Engine:
             la.seed_dev = prog.seed_ctr.data_ptr()
         zs = [r.z for r in Da.blocks if r.st.stochastic]
         given = [True] * len(zs)
-        outs = []
+        outs, passes = [], []
         for j in (1, 0):
             D = self._decoder_fwd(prog, N, io.pa[j], io.pa_sto[j], None, given=given, z_views=zs)
             xo = torch.zeros(N, self.C, self.R, self.R, device=self.device, dtype=torch.float32)
@@ -852,6 +878,7 @@ class Engine:
                 prog.add(L.Launch("cg_dgauss_sample", C.byref(la), xo.data_ptr(), so.data_ptr(), None,
                                   C.c_float(0.0))).keep = (la, D)
             outs.append((xo, so))
+            passes.append((D, j))
         (cf_loc, cf_scale), (rec_loc, rec_scale) = outs
         prog.cf_x = torch.zeros_like(cf_loc)
         prog.acc = torch.zeros_like(cf_loc)
@@ -859,4 +886,51 @@ class Engine:
         prog.call("cg_cf_combine", io.x.data_ptr(), rec_loc.data_ptr(), rec_scale.data_ptr(), cf_loc.data_ptr(),
                   cf_scale.data_ptr(), prog.cf_x.data_ptr(), prog.acc.data_ptr(), prog.acc2.data_ptr(), io.x.numel())
         prog.keep += [outs]
+        if not train:
+            return prog
+        if self.dmol:
+            raise NotImplementedError("gradients through the counterfactual are implemented for the DGaussNet likelihood "
+                                      "(every reference counterfactual-training config, src/pgm/train_cf.py); DmolNet: no")
+        # ------------------------------------------------------------------ backward program (given prog.dcf = d loss / d cf_x)
+        bwd = Program(f"counterfactual_bwd(N={N})")
+        prog.bwd = bwd
+        prog.dcf = torch.zeros_like(cf_loc)
+        dl = [torch.zeros_like(cf_loc) for _ in range(4)]  # d rec_loc, d rec_scale, d cf_loc, d cf_scale
+        bwd.call("cg_cf_combine_bwd", io.x.data_ptr(), rec_loc.data_ptr(), rec_scale.data_ptr(), cf_loc.data_ptr(),
+                 cf_scale.data_ptr(), prog.dcf.data_ptr(), dl[0].data_ptr(), dl[1].data_ptr(), dl[2].data_ptr(),
+                 dl[3].data_ptr(), io.x.numel())
+        bwd.keep += [dl]
+        lik = self.model.likelihood
+        dz_extra: Dict[int, List[View]] = {}
+        for (D, j), (dloc, dscale) in zip(passes, ((dl[2], dl[3]), (dl[0], dl[1]))):
+            k = 0
+            for r in D.blocks:
+                r.pa, r.ksto = io.pa[j][r.st.res], k
+                if r.st.stochastic:
+                    k += 1
+            dh = new_act(N, self.R, self.R, self.args.widths[0], self.device)
+            lb = self._lik_args(D.h, None, N)
+            lb.dh, lb.dh_ns = dh.ptr, dh.ns
+            lb.dw_loc, lb.db_loc = self.g(lik.x_loc.weight).data_ptr(), self.g(lik.x_loc.bias).data_ptr()
+            lb.dw_ls, lb.db_ls = self.g(lik.x_logscale.weight).data_ptr(), self.g(lik.x_logscale.bias).data_ptr()
+            if self.C == 3:
+                lb.dw_co = self.g(lik.channel_coeffs.weight).data_ptr()
+                lb.db_co = self.g(lik.channel_coeffs.bias).data_ptr()
+            bwd.add(L.Launch("cg_dgauss_sample_bwd", C.byref(lb), dloc.data_ptr(), dscale.data_ptr())).keep = (lb, dh)
+            dz_pass: Dict[int, View] = {}
+            self._decoder_bwd(bwd, D, dh, N, 0.0, {}, False, dz_out=dz_pass)
+            for ks, v in dz_pass.items():
+                dz_extra.setdefault(ks, []).append(v)
+        # abduction pass: its output h feeds nothing (zero upstream gradient); the latents carry everything
+        k = 0
+        for r in Da.blocks:
+            r.pa, r.ksto = io.pa[0][r.st.res], k
+            if r.st.stochastic:
+                k += 1
+        dh0 = new_act(N, self.R, self.R, self.args.widths[0], self.device)  # stays zero
+        acts_grad: Dict[int, View] = {}
+        self._decoder_bwd(bwd, Da, dh0, N, 0.0, acts_grad, False, dz_extra=dz_extra)
+        for lb in Da.latent_bwd_args:
+            lb.seed_dev = prog.seed_ctr.data_ptr()
+        self._encoder_bwd(bwd, e, acts_grad, N)
         return prog

@@ -20,7 +20,7 @@ import torch
 from torch import Tensor, nn
 
 from . import _lib as L
-from .engine import Engine, TRACE_ONLY
+from .engine import Engine, TRACE_ONLY, no_grad_param_ids
 from .model import Decoder, DGaussNet, DmolNet, Encoder
 
 
@@ -42,21 +42,72 @@ class _ElboFn(torch.autograd.Function):
     def forward(ctx, model, x, parents, beta, eps, *params):
         out3 = model._run_elbo(x, parents, beta, eps, train=True)
         ctx.model = model
-        ctx.generation = model._engine_or_none().generation
+        eng = model._engine_or_none()
+        # the engine keeps ONE gradient bucket that the next training forward (or a counterfactual backward) overwrites:
+        # this node keeps its own copy, so forwards and backwards may interleave freely (DSCM.forward runs the ELBO and the
+        # counterfactual before a single backward, src/pgm/dscm.py:41-88)
+        ctx.grads = eng.flat_grad.clone()
         ctx.param_ids = [id(p) for p in params]
         return out3[0].clone()
 
     @staticmethod
     def backward(ctx, g):
         eng = ctx.model._engine_or_none()
-        if eng is None or eng.generation != ctx.generation:
-            raise RuntimeError("causalgen_b200: another training forward ran before this backward; the engine keeps ONE "
-                               "gradient bucket, so call backward() right after each forward() (gradient accumulation "
-                               "over micro-batches works that way)")
-        flat = eng.flat_grad * g  # one op; views of the copy are safe for autograd to keep
+        flat = ctx.grads * g
         by_id, off = {}, 0
+        dead = no_grad_param_ids(ctx.model)  # never touched by the forward: grad stays None like in the reference
         for p in eng.params:
-            by_id[id(p)] = flat[off: off + p.numel()].view_as(p) if p.requires_grad else None
+            by_id[id(p)] = flat[off: off + p.numel()].view_as(p) if (p.requires_grad and id(p) not in dead) else None
+            off += p.numel()
+        return (None, None, None, None, None) + tuple(by_id[i] for i in ctx.param_ids)
+
+
+class _CfFn(torch.autograd.Function):
+    """One autograd node for the fused counterfactual pass: forward = abduct -> 2 x forward_latents -> combine
+    (src/pgm/dscm.py:52-56); backward = the hand-derived backward program of engine.build_counterfactual(train=True)."""
+
+    @staticmethod
+    def forward(ctx, model, x, pa, cf_pa, t_abduct, *params):
+        eng = model.engine()
+        N = x.shape[0]
+        prog = model._program(("cf_train", N), lambda: eng.build_counterfactual(N, train=True))
+        if model.__dict__.get("export_eps") and not hasattr(prog, "eps_out"):
+            # parity hook: the abduction's latent kernels also write the eps they drew (fp32 NCHW, block order)
+            prog.eps_out = []
+            for la in prog.D.latent_args:
+                if la.mode in (0, 1):
+                    r = int(round(la.HW ** 0.5))
+                    t = torch.zeros(N, la.zdim, r, r, device=eng.device, dtype=torch.float32)
+                    la.eps_out = t.data_ptr()
+                    prog.eps_out.append(t)
+        prog.io.x.copy_(x)
+        model._load_parents(prog, prog.io, [pa, cf_pa])
+        model._set_noise(prog.D, None, math.log(t_abduct) if t_abduct is not None else 0.0, prog.D.latent_bwd_args)
+        eng.pack_weights()
+        prog.run()
+        prog.seed_ctr.add_(1)
+        ctx.model, ctx.prog = model, prog
+        ctx.seed_at_fwd = int(prog.seed_ctr.item()) - 1
+        ctx.param_ids = [id(p) for p in params]
+        return prog.cf_x.clone()
+
+    @staticmethod
+    def backward(ctx, dcf):
+        model, prog = ctx.model, ctx.prog
+        eng = model.engine()
+        if int(prog.seed_ctr.item()) - 1 != ctx.seed_at_fwd:
+            raise RuntimeError("causalgen_b200: another counterfactual forward of the same batch size ran before this backward; "
+                               "its saved activations were overwritten (call backward() first)")
+        prog.seed_ctr.sub_(1)  # the backward regenerates the abduction noise of THIS forward
+        prog.dcf.copy_(dcf)
+        eng.flat_grad.zero_()
+        prog.bwd.run()
+        prog.seed_ctr.add_(1)
+        flat = eng.flat_grad.clone()
+        by_id, off = {}, 0
+        dead = no_grad_param_ids(model)
+        for p in eng.params:
+            by_id[id(p)] = flat[off: off + p.numel()].view_as(p) if (p.requires_grad and id(p) not in dead) else None
             off += p.numel()
         return (None, None, None, None, None) + tuple(by_id[i] for i in ctx.param_ids)
 
@@ -132,7 +183,7 @@ class HVAE(nn.Module):
                 b.copy_(e)
         if bwd is not None:
             for lb in bwd:
-                lb.seed = seed
+                lb.seed, lb.log_t = seed, log_t
         return seed
 
     # ------------------------------------------------------------------ ELBO
@@ -318,11 +369,30 @@ def vae_preprocess(args, pa: Dict[str, Tensor], expand: bool = False) -> Tensor:
     return (out.cuda() if torch.cuda.is_available() else out).float()  # host glue; every HVAE entry needs the GPU
 
 
-@torch.no_grad()
 def counterfactual(vae: HVAE, x: Tensor, pa: Tensor, cf_pa: Tensor, t_abduct: float = 1.0, particles: int = 1,
                    eps: Optional[Sequence[Sequence[Tensor]]] = None):
     """abduct -> forward_latents(cf_pa) & forward_latents(pa) (one 2-parent-set pass) -> combine
-    (src/pgm/dscm.py:47-72).  Returns (cf_x, var_cf_x or None)."""
+    (src/pgm/dscm.py:47-72).  Returns (cf_x, var_cf_x or None).
+
+    With ``vae.train()``, autograd enabled and trainable HVAE parameters (counterfactual fine-tuning, src/pgm/train_cf.py:159-180)
+    ``cf_x`` is differentiable w.r.t. the HVAE parameters: ``aux_loss(cf_x).backward()`` reaches encoder, posterior,
+    prior, decoder and likelihood weights exactly as the reference's autograd graph does (src/pgm/dscm.py:52-56,78-88).
+    Gradient support covers particles == 1 (the reference's training setting) and in-kernel noise."""
+    # the reference fine-tunes with vae.train() and autograd on, and evaluates under vae.eval() + no_grad
+    # (src/pgm/train_cf.py:122,144,182): the differentiable path is taken in exactly that training situation
+    need_grad = (torch.is_grad_enabled() and vae.training and eps is None and not TRACE_ONLY
+                 and any(p.requires_grad for p in vae.parameters()))
+    if need_grad:
+        if particles != 1:
+            raise NotImplementedError("gradients through the counterfactual are implemented for cf_particles == 1 (the "
+                                      "reference's training setting, src/pgm/train_cf.py); use torch.no_grad() for "
+                                      "multi-particle uncertainty estimates")
+        return _CfFn.apply(vae, x, _pa_vector(pa), _pa_vector(cf_pa), t_abduct, *list(vae.parameters())), None
+    with torch.no_grad():
+        return _counterfactual_nograd(vae, x, pa, cf_pa, t_abduct, particles, eps)
+
+
+def _counterfactual_nograd(vae: HVAE, x: Tensor, pa: Tensor, cf_pa: Tensor, t_abduct, particles, eps):
     if eps is None and not TRACE_ONLY:
         # serving path: one fused program (abduction with in-kernel Philox noise, both decodes on the bf16 latents in
         # place, combine); the explicit-eps path below keeps the reference's fp32 latent interface for parity tests

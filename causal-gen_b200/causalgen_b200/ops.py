@@ -131,7 +131,9 @@ class ConvLayer:
 
     def __init__(self, table: PackTable, weight: torch.Tensor, bias: Optional[torch.Tensor],
                  src_logical: Sequence[int], act: int, centre_only: bool = False,
-                 grad_srcs: Optional[Sequence[bool]] = None):
+                 grad_srcs: Optional[Sequence[bool]] = None, fwd_operands: bool = True):
+        """fwd_operands=False: no forward launch of this layer fuses an epilogue operand (add / add2 / mul), so its
+        GEMM-N chunk need not reserve shared memory for the operand ring (first convs of a Block: huge K, narrow N)"""
         lib = L.load()
         self.weight, self.bias = weight, bias
         self.cout_l, self.cin_l, self.k = weight.shape[0], weight.shape[1], weight.shape[2]
@@ -145,8 +147,8 @@ class ConvLayer:
         self.ksize = 1 if self.taps == 1 else self.k
         dev = weight.device
         kt = self.taps * sum(self.src_pad) // 16
-        self.nc = lib.cg_conv_nchunk(kt, self.cout_pad)
-        nbytes = lib.cg_packed_weight_bytes(kt, self.cout_pad)
+        self.nc = lib.cg_conv_nchunk_ex(kt, self.cout_pad, int(fwd_operands))
+        nbytes = lib.cg_packed_weight_bytes_nc(kt, self.cout_pad, self.nc)
         if self.nc <= 0 or nbytes <= 0:
             raise RuntimeError(f"conv K={kt * 16} does not fit a resident weight slab")
         self.wpack = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
@@ -160,14 +162,17 @@ class ConvLayer:
         table.add(d)
         # data-gradient packs (one per source that needs a gradient): K side = dY channels
         self.wpack_bwd: List[Optional[torch.Tensor]] = []
+        self.nc_bwd: List[int] = []
         grad_srcs = [True] * len(src_logical) if grad_srcs is None else list(grad_srcs)
         ktb = self.taps * self.cout_pad // 16
         for i, need in enumerate(grad_srcs):
             if not need:
                 self.wpack_bwd.append(None)
+                self.nc_bwd.append(0)
                 continue
-            ncb = lib.cg_conv_nchunk(ktb, self.src_pad[i])
-            nb = lib.cg_packed_weight_bytes(ktb, self.src_pad[i])
+            ncb = lib.cg_conv_nchunk_ex(ktb, self.src_pad[i], 1)
+            nb = lib.cg_packed_weight_bytes_nc(ktb, self.src_pad[i], ncb)
+            self.nc_bwd.append(ncb)
             buf = torch.zeros(nb, dtype=torch.uint8, device=dev)
             b = L.PackDesc()
             b.w, b.out = weight.data_ptr(), buf.data_ptr()
@@ -209,7 +214,7 @@ class ConvLayer:
         a.nsrc, a.cout = len(srcs), self.cout_pad
         self._fill_srcs(a.src, srcs)
         self._fill_segs(a, segs)
-        a.wpack = self.wpack.data_ptr()
+        a.wpack, a.nc = self.wpack.data_ptr(), self.nc
         if self.bias is not None:
             a.bias, a.bias_n = self.bias.data_ptr(), self.cout_l
         ln = L.Launch("cg_conv2d", C.byref(a))
@@ -226,7 +231,7 @@ class ConvLayer:
         a.nsrc, a.cout = 1, self.src_pad[i]
         self._fill_srcs(a.src, [dy])
         self._fill_segs(a, [seg])
-        a.wpack = self.wpack_bwd[i].data_ptr()
+        a.wpack, a.nc = self.wpack_bwd[i].data_ptr(), self.nc_bwd[i]
         ln = L.Launch("cg_conv2d", C.byref(a))
         ln.keep = (a, dy, seg)
         ln.algo_bytes = 2 * N * H * W * (self.cout_l + self.src_logical[i])

@@ -25,7 +25,7 @@ import torch
 
 from . import _lib as L
 from . import dp
-from .engine import TRACE_ONLY, Engine, ordered_params
+from .engine import TRACE_ONLY, Engine, no_grad_param_ids, ordered_params
 from .hvae import HVAE, _stream
 
 
@@ -50,7 +50,8 @@ class Trainer:
         # views of it.  The engine lays its gradient bucket out in the same order.
         self.params: List[torch.nn.Parameter] = ordered_params(model)
         n = sum(p.numel() for p in self.params)
-        self.n_train = sum(p.numel() for p in self.params if p.requires_grad)
+        dead = no_grad_param_ids(model)
+        self.n_train = sum(p.numel() for p in self.params if p.requires_grad and id(p) not in dead)
         self.flat_p = torch.empty(n, device=dev, dtype=torch.float32)
         off = 0
         for p in self.params:

@@ -253,9 +253,9 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const cg_latent_bwd_arg
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int c = oc * 8 + k;
-      const float p_loc = a.p[pix * a.p_ld + c], p_ls = a.p[pix * a.p_ld + zd + c];
+      const float p_loc = a.p[pix * a.p_ld + c], p_ls = a.p[pix * a.p_ld + zd + c] + a.log_t;
       if (a.mode == 0) {
-        const float q_loc = a.q[pix * a.q_ld + c], q_ls = a.q[pix * a.q_ld + zd + c];
+        const float q_loc = a.q[pix * a.q_ld + c], q_ls = a.q[pix * a.q_ld + zd + c] + a.log_t;
         const float eq = __expf(q_ls), ivp = __expf(-2.0f * p_ls), dm = q_loc - p_loc;
         g_qloc[k] = g_kl * dm * ivp + dz[k];
         g_qls[k] = g_kl * (eq * eq * ivp - 1.0f) + dz[k] * eq * s_eps[c][px];
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(256) latent_bwd_stream_kernel(const cg_latent_
     *reinterpret_cast<float4*>(qs) = qq[0]; *reinterpret_cast<float4*>(qs + 4) = qq[1];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float eq = __expf(qs[k]), ivp = __expf(-2.0f * ps[k]), dm = ql[k] - pl[k];
+      const float eq = __expf(qs[k] + a.log_t), ivp = __expf(-2.0f * (ps[k] + a.log_t)), dm = ql[k] - pl[k];
       g_qloc[k] = g_kl * dm * ivp + dz[k];
       g_qls[k] = g_kl * (eq * eq * ivp - 1.0f) + dz[k] * eq * e[k];
       g_ploc[k] = -g_kl * dm * ivp;
@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(256) latent_bwd_stream_kernel(const cg_latent_
     *reinterpret_cast<uint4*>(q0 + (long long)(2 + oc) * a.HW * 8) = cg_pack8(g_qls);
   } else if (a.mode == 1) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { g_ploc[k] = dz[k]; g_pls[k] = dz[k] * __expf(ps[k]) * e[k]; }
+    for (int k = 0; k < 8; ++k) { g_ploc[k] = dz[k]; g_pls[k] = dz[k] * __expf(ps[k] + a.log_t) * e[k]; }
   } else {
 #pragma unroll
     for (int k = 0; k < 8; ++k) { g_ploc[k] = dz[k]; g_pls[k] = 0.f; }
@@ -415,6 +415,25 @@ __global__ void cf_combine_kernel(const float* __restrict__ x, const float* __re
     cf_x[i] = v;
     if (sum != nullptr) sum[i] += v;      // src/pgm/dscm.py:59
     if (sum2 != nullptr) sum2[i] += v * v;  // src/pgm/dscm.py:61
+  }
+}
+
+// backward of cf_combine_kernel: d cf_x -> d cf_loc, d cf_scale, d rec_loc, d rec_scale (torch.clamp masks inclusive)
+__global__ void cf_combine_bwd_kernel(const float* __restrict__ x, const float* __restrict__ rec_loc,
+                                      const float* __restrict__ rec_scale, const float* __restrict__ cf_loc,
+                                      const float* __restrict__ cf_scale, const float* __restrict__ dcf,
+                                      float* __restrict__ d_rec_loc, float* __restrict__ d_rec_scale,
+                                      float* __restrict__ d_cf_loc, float* __restrict__ d_cf_scale, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float s = fmaxf(rec_scale[i], 1e-12f);
+    const float u = (x[i] - rec_loc[i]) / s;
+    const float pre = cf_loc[i] + cf_scale[i] * u;
+    const float g = (pre >= -1.0f && pre <= 1.0f) ? dcf[i] : 0.f;
+    const float du = g * cf_scale[i];
+    d_cf_loc[i] = g;
+    d_cf_scale[i] = g * u;
+    d_rec_loc[i] = -du / s;
+    d_rec_scale[i] = rec_scale[i] >= 1e-12f ? -du * u / s : 0.f;
   }
 }
 
@@ -531,5 +550,15 @@ extern "C" int cg_cf_combine(const float* x, const float* rec_loc, const float* 
   cf_combine_kernel<<<grid_for(n, 256), 256, 0, cg_stream(stream)>>>(x, rec_loc, rec_scale, cf_loc, cf_scale, cf_x, sum,
                                                                      sum2, n);
   CG_LAUNCH_CHECK("cg_cf_combine");
+  return CG_OK;
+}
+
+extern "C" int cg_cf_combine_bwd(const float* x, const float* rec_loc, const float* rec_scale, const float* cf_loc,
+                                 const float* cf_scale, const float* dcf, float* d_rec_loc, float* d_rec_scale,
+                                 float* d_cf_loc, float* d_cf_scale, int64_t n, void* stream) {
+  CG_ARCH_GUARD();
+  cf_combine_bwd_kernel<<<grid_for(n, 256), 256, 0, cg_stream(stream)>>>(x, rec_loc, rec_scale, cf_loc, cf_scale, dcf,
+                                                                         d_rec_loc, d_rec_scale, d_cf_loc, d_cf_scale, n);
+  CG_LAUNCH_CHECK("cg_cf_combine_bwd");
   return CG_OK;
 }

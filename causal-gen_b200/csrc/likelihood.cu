@@ -123,8 +123,12 @@ __global__ void __launch_bounds__(256) dgauss_fwd_kernel(const cg_dgauss_args a)
   }
 }
 
-template <int C>
-__global__ void __launch_bounds__(256) dgauss_bwd_kernel(const cg_dgauss_args a) {
+// MODE 0: backward of the NLL (dgauss_fwd_kernel).  MODE 1: backward of likelihood.sample(h, return_loc=True)
+// (dgauss_sample_kernel, src/vae.py:413-422 + 352-369) given d x_out / d scale_out (fp32 NCHW) -- the counterfactual
+// training path back-propagates through cf_loc / cf_scale / rec_loc / rec_scale (src/pgm/dscm.py:53-56,78-88).
+template <int C, int MODE>
+__global__ void __launch_bounds__(256) dgauss_bwd_kernel(const cg_dgauss_args a, const float* __restrict__ dx_out,
+                                                         const float* __restrict__ dscale_out) {
   __shared__ Heads s;
   __shared__ float s_d[256][3 * C + 1];  // per pixel: dloc[C], dls[C], dco[C]
   load_heads(s, a);
@@ -142,24 +146,53 @@ __global__ void __launch_bounds__(256) dgauss_bwd_kernel(const cg_dgauss_args a)
     eval_heads<C>(s, hrow, (long long)a.HW * 8, a.Cw, loc, ls, co, C == 3);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      x[c] = a.x[((long long)n * C + c) * a.HW + hw];
+      x[c] = MODE == 0 ? a.x[((long long)n * C + c) * a.HW + hw] : 0.f;
       live[c] = ls[c] >= -9.0f;
       ls[c] = fmaxf(ls[c], -9.0f);
     }
     float tc[3] = {0.f, 0.f, 0.f};
-    if (C == 3) {
+    if (MODE == 1) {
+      float gx[C], gs[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const long long o = ((long long)n * C + c) * a.HW + hw;
+        gx[c] = dx_out != nullptr ? dx_out[o] : 0.f;
+        gs[c] = dscale_out != nullptr ? dscale_out[o] : 0.f;
+        dls[c] = live[c] ? gs[c] * __expf(ls[c]) : 0.f;  // scale = exp(max(raw, -9))
+      }
+      auto pass = [](float v) { return v >= -1.f && v <= 1.f; };  // torch.clamp backward mask (inclusive)
+      if (C == 1) {
+        dloc[0] = pass(loc[0]) ? gx[0] : 0.f;  // the final clamp(-1, 1) of src/vae.py:421
+      } else {
+        // r = clamp(l0); g = clamp(l1 + c0 r); b = clamp(l2 + c1 r + c2 g)   (src/vae.py:360-369), then clamp again (no-op)
+        tc[0] = tanhf(co[0]); tc[1] = tanhf(co[1]); tc[2] = tanhf(co[2]);
+        const float r = fminf(fmaxf(loc[0], -1.f), 1.f);
+        const float pg = loc[1] + tc[0] * r, g = fminf(fmaxf(pg, -1.f), 1.f);
+        const float pb = loc[2] + tc[1] * r + tc[2] * g;
+        const float db_ = pass(pb) ? gx[2] : 0.f;
+        const float dg_ = pass(pg) ? gx[1] + db_ * tc[2] : 0.f;
+        const float dr_ = pass(loc[0]) ? gx[0] + dg_ * tc[0] + db_ * tc[1] : 0.f;
+        dloc[0] = dr_; dloc[1] = dg_; dloc[2] = db_;
+        dco[0] = dg_ * r * (1.0f - tc[0] * tc[0]);
+        dco[1] = db_ * r * (1.0f - tc[1] * tc[1]);
+        dco[2] = db_ * g * (1.0f - tc[2] * tc[2]);
+      }
+    }
+    if (MODE == 0 && C == 3) {
       tc[0] = tanhf(co[0]); tc[1] = tanhf(co[1]); tc[2] = tanhf(co[2]);
       loc[1] += tc[0] * x[0];
       loc[2] += tc[1] * x[0] + tc[2] * x[1];
     }
+    if (MODE == 0) {
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      float gl, gs;
-      dgauss_logprob(x[c], loc[c], ls[c], &gl, &gs);
-      dloc[c] = scale * gl;
-      dls[c] = live[c] ? scale * gs : 0.f;
+      for (int c = 0; c < C; ++c) {
+        float gl, gs;
+        dgauss_logprob(x[c], loc[c], ls[c], &gl, &gs);
+        dloc[c] = scale * gl;
+        dls[c] = live[c] ? scale * gs : 0.f;
+      }
     }
-    if (C == 3) {
+    if (MODE == 0 && C == 3) {
       dco[0] = dloc[1] * x[0] * (1.0f - tc[0] * tc[0]);
       dco[1] = dloc[2] * x[0] * (1.0f - tc[1] * tc[1]);
       dco[2] = dloc[2] * x[1] * (1.0f - tc[2] * tc[2]);
@@ -547,9 +580,21 @@ extern "C" int cg_dgauss_nll_bwd(const cg_dgauss_args* a, void* stream) {
   DGAUSS_CHECK(a, "cg_dgauss_nll_bwd");
   CG_REQUIRE(a->dh != nullptr && a->dh_ns % 8 == 0, "cg_dgauss_nll_bwd: dh");
   dim3 grid(cg_ceil_div(a->HW, 256), a->N);
-  if (a->C == 1) dgauss_bwd_kernel<1><<<grid, 256, 0, cg_stream(stream)>>>(*a);
-  else dgauss_bwd_kernel<3><<<grid, 256, 0, cg_stream(stream)>>>(*a);
+  if (a->C == 1) dgauss_bwd_kernel<1, 0><<<grid, 256, 0, cg_stream(stream)>>>(*a, nullptr, nullptr);
+  else dgauss_bwd_kernel<3, 0><<<grid, 256, 0, cg_stream(stream)>>>(*a, nullptr, nullptr);
   CG_LAUNCH_CHECK("cg_dgauss_nll_bwd");
+  return CG_OK;
+}
+
+extern "C" int cg_dgauss_sample_bwd(const cg_dgauss_args* a, const float* dx_out, const float* dscale_out, void* stream) {
+  CG_ARCH_GUARD();
+  DGAUSS_CHECK(a, "cg_dgauss_sample_bwd");
+  CG_REQUIRE(a->dh != nullptr && a->dh_ns % 8 == 0, "cg_dgauss_sample_bwd: dh");
+  CG_REQUIRE(dx_out != nullptr || dscale_out != nullptr, "cg_dgauss_sample_bwd: no upstream gradient");
+  dim3 grid(cg_ceil_div(a->HW, 256), a->N);
+  if (a->C == 1) dgauss_bwd_kernel<1, 1><<<grid, 256, 0, cg_stream(stream)>>>(*a, dx_out, dscale_out);
+  else dgauss_bwd_kernel<3, 1><<<grid, 256, 0, cg_stream(stream)>>>(*a, dx_out, dscale_out);
+  CG_LAUNCH_CHECK("cg_dgauss_sample_bwd");
   return CG_OK;
 }
 

@@ -90,7 +90,7 @@ typedef struct {
   const void* wpack;   /* weights packed by cg_pack_weights for exactly this (src list, cout) */
   const float* bias;   /* fp32 [bias_n] or NULL */
   int32_t bias_n;      /* valid bias entries (logical output channels); the rest is 0 */
-  int32_t _pad;
+  int32_t nc;          /* GEMM-N chunk the weights were packed for (cg_conv_nchunk_ex); 0 = cg_conv_nchunk(ktot16, cout) */
 } cg_conv_args;
 
 /* y = conv(act(cat(src))) + bias, split/added per segment.  Also the data-gradient pass when
@@ -100,8 +100,12 @@ int cg_conv2d(const cg_conv_args* a, void* stream);
 /* GEMM-N chunk (output channels per CTA) the conv kernel uses for this problem size; the packed
  * weight image is laid out per chunk, so cg_pack_desc.nc must carry this value */
 int32_t cg_conv_nchunk(int32_t ktot16, int32_t cout);
+/* same with a hint: want_e = 0 when no launch of this pack has fused epilogue operands (add / add2 / mul), so the chunk
+ * need not leave shared memory for the operand ring (first convs of a Block: wide K, narrow N) */
+int32_t cg_conv_nchunk_ex(int32_t ktot16, int32_t cout, int32_t want_e);
 /* bytes of the packed-weight image for a conv with `ktot16` K-blocks of 16 (= taps * sum(C)/16) */
 int64_t cg_packed_weight_bytes(int32_t ktot16, int32_t cout);
+int64_t cg_packed_weight_bytes_nc(int32_t ktot16, int32_t cout, int32_t nc);
 
 typedef struct {
   const float* w;      /* fp32 OIHW master weight (Cout_l, Cin_l, k, k) -- reference layout */
@@ -197,6 +201,8 @@ typedef struct {
   int32_t N, HW, zdim, mode;
   const float* g_kl_dev;      /* optional device scalar multiplied into g_kl (beta annealing under CUDA-graph replay,
                                  src/trainer.py:52-57): g_kl then carries 1 / (B * C*H*W) and *g_kl_dev the live beta */
+  float log_t;                /* log temperature the forward added to both logscales (abduction with t, src/vae.py:176-190) */
+  int32_t _pad;
 } cg_latent_bwd_args;
 int cg_latent_bwd(const cg_latent_bwd_args* a, void* stream);
 
@@ -227,6 +233,11 @@ int cg_dgauss_nll_bwd(const cg_dgauss_args* a, void* stream);
 int cg_dgauss_sample(const cg_dgauss_args* a, float* x_out, float* scale_out, const float* eps,
                      float log_t, void* stream);
 
+/* backward of cg_dgauss_sample (eps == NULL): given d x_out and/or d scale_out (fp32 NCHW, either may be NULL) writes
+ * a->dh (bf16 planar) and accumulates a->dw_* / a->db_*.  Gradients reach the likelihood this way when the counterfactual
+ * is trained through (src/pgm/dscm.py:53-56,78-88; src/pgm/train_cf.py:159-180). */
+int cg_dgauss_sample_bwd(const cg_dgauss_args* a, const float* dx_out, const float* dscale_out, void* stream);
+
 /* DmolNet (src/dmol.py:24-245): 1x1 conv to 100 channels fused with the mixture loss.
  * w (100,Cw) b (100) fp32; x fp32 NCHW (N,3,H,W). */
 typedef struct {
@@ -252,6 +263,11 @@ int cg_dmol_predict(const cg_dmol_args* a, int32_t mode, const float* u_gumbel,
 int cg_cf_combine(const float* x, const float* rec_loc, const float* rec_scale, const float* cf_loc,
                   const float* cf_scale, float* cf_x, float* sum, float* sum2, int64_t n,
                   void* stream);
+
+/* backward of the combine: d cf_x -> gradients of the four likelihood outputs (src/pgm/dscm.py:55-56) */
+int cg_cf_combine_bwd(const float* x, const float* rec_loc, const float* rec_scale, const float* cf_loc,
+                      const float* cf_scale, const float* dcf, float* d_rec_loc, float* d_rec_scale,
+                      float* d_cf_loc, float* d_cf_scale, int64_t n, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Layout glue (src/trainer.py:16-21, src/pgm/dscm.py:121-132)

@@ -64,7 +64,8 @@ from causalgen_b200 import HVAE
 class Fake:
     def __init__(self, real): self.real = real
     def __getattr__(self, n):
-        if n in ("cg_conv_nchunk", "cg_packed_weight_bytes", "cg_version", "cg_last_error"): return getattr(self.real, n)
+        if n in ("cg_conv_nchunk", "cg_conv_nchunk_ex", "cg_packed_weight_bytes", "cg_packed_weight_bytes_nc", "cg_version",
+                     "cg_last_error"): return getattr(self.real, n)
         return lambda *a: 0
 L._lib = Fake(L.load())
 for name, nsto, nconv_min in (("tiny_ukbb", 5, 60), ("tiny_morphomnist", 4, 80)):

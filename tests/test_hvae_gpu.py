@@ -7,15 +7,20 @@ the oracle -- like the reference -- is fp32.  With the all-paths-active seeded w
 runs the oracle with the same bf16 storage points emulated (``hvae_oracle.EMULATE_BF16``) and states the
 tolerance against that measured, inherent drift:
 
-    elbo / nll / kl        rel <= 5e-3 vs the fp32 oracle
-    per-block KL sums      |d| <= 3e-2*|ref| + 2e-3*sum|ref| per block, rel-L2 over blocks <= 5e-3
-    gradients              global rel-L2 <= max(1.5e-2, 2 * drift); per tensor (norm > 1% of the largest)
-                           rel-L2 <= max(5e-2, 2 * drift_tensor + 2e-2)   (activation gradients are also
-                           stored in bf16, which the forward-only emulation does not include)
+    elbo / nll / kl        rel <= 5e-3 vs the fp32 oracle                      (measured <= 2.4e-3)
+    per-block KL sums      |d| <= 1e-2*|ref| + 1e-3*sum|ref| per (sample, block), rel-L2 over blocks <= 5e-3
+                           (rel 1e-2; measured max rel 4.6e-3 on blocks >= 1% of the largest)
+    gradients              global rel-L2 <= 3.5e-2 (fixed; measured 0.5e-2 ... 2.5e-2) AND <= max(1.5e-2, 2 * drift);
+                           per tensor (norm > 1% of the largest) rel-L2 <= max(5e-2, 2 * drift_tensor + 2e-2)
+                           (activation gradients are also stored in bf16, which the forward-only emulation omits)
     abducted z             rel-L2 <= max(5e-3, 2 * drift)
-    rec / cf / sampled px  mean |d| <= max(1/255, 1.5 * drift_mean), p99 |d| <= max(2/255, 1.5 * drift_p99)
+    rec / cf / sampled px  fixed caps: mean |d| <= 1.5/255 and p99 <= 6/255 at 16x16 / 32x32, mean <= 3/255 and
+                           p99 <= 13/255 at 192x192 / 224x224 (40 blocks; measured worst 2.6/255 and 11.3/255), AND
+                           mean <= max(1/255, 1.5 * drift_mean), p99 <= max(2/255, 1.5 * drift_p99)
 
-where drift = the same statistic of (bf16-storage oracle - fp32 oracle).
+where drift = the same statistic of (bf16-storage oracle - fp32 oracle): it tells "implementation differs" from "bf16
+storage differs" and is reported next to every measured deviation in the parity report (tests/conftest.py); the fixed
+numbers are what fails the test when the emulation itself would be wrong.
 """
 import numpy as np
 import pytest
@@ -114,7 +119,8 @@ def test_elbo_kl_and_gradients(name):
             if r > max(5e-2, 2 * drift + 2e-2):
                 bad.append((k, round(r, 4), round(drift, 4)))
     glob, gdrift = (num / den) ** 0.5, (dnum / den) ** 0.5
-    parity_report(T, "grad global rel-L2", glob, max(1.5e-2, 2 * gdrift), f"bf16-emulated oracle drift {gdrift:.2e}")
+    parity_report(T, "grad global rel-L2", glob, min(3.5e-2, max(1.5e-2, 2 * gdrift)), f"bf16-emulated oracle drift {gdrift:.2e}")
+    assert glob <= 3.5e-2, f"{name} global grad rel-L2 {glob:.4f}"
     assert glob <= max(1.5e-2, 2 * gdrift), f"{name} global grad rel-L2 {glob:.4f} (drift {gdrift:.4f})"
     assert not bad, f"{name} per-tensor grad outliers (name, rel, drift): {bad[:8]}"
 
@@ -127,8 +133,11 @@ def px_stats(a, b):
 def assert_pixels(ours, ref, emu, what):
     m, p99 = px_stats(ours, ref)
     dm, dp99 = px_stats(emu, ref)
-    parity_report("pixels", f"{what} mean|d| *255", m * 255, max(1.0, 1.5 * dm * 255), f"emulated drift {dm * 255:.3f}")
-    parity_report("pixels", f"{what} p99|d| *255", p99 * 255, max(2.0, 1.5 * dp99 * 255), f"emulated drift {dp99 * 255:.3f}")
+    big = ours.shape[-1] >= 192
+    cap_m, cap_p = (3.0, 13.0) if big else (1.5, 6.0)
+    parity_report("pixels", f"{what} mean|d| *255", m * 255, min(cap_m, max(1.0, 1.5 * dm * 255)), f"emulated drift {dm * 255:.3f}")
+    parity_report("pixels", f"{what} p99|d| *255", p99 * 255, min(cap_p, max(2.0, 1.5 * dp99 * 255)), f"emulated drift {dp99 * 255:.3f}")
+    assert m * 255 <= cap_m and p99 * 255 <= cap_p, f"{what}: mean {m * 255:.2f}/255 p99 {p99 * 255:.2f}/255 over the fixed caps"
     assert m <= max(1 / 255, 1.5 * dm), f"{what}: mean |d| {m:.5f} vs bf16 drift {dm:.5f}"
     assert p99 <= max(2 / 255, 1.5 * dp99), f"{what}: p99 |d| {p99:.5f} vs bf16 drift {dp99:.5f}"
 
@@ -237,6 +246,93 @@ def test_counterfactual_fused_program_matches_reference_interface_path(name):
     assert float(d.mean()) <= 0.5 / 255 and float(d.max()) <= 6.0 / 255, (float(d.mean()), float(d.max()))
     mean, var = counterfactual(model, xd, pad, cfd, t_abduct=1.0, particles=3)
     assert bool(torch.isfinite(mean).all()) and bool((var >= -1e-6).all()) and float(var.mean()) > 0
+
+
+@pytest.mark.parametrize("name,t_abduct", [("tiny_ukbb", 1.0), ("tiny_morphomnist", 0.8), ("tiny_cmnist", 1.0)])
+def test_counterfactual_gradients_reach_the_hvae(name, t_abduct):
+    """counterfactual fine-tuning (src/pgm/train_cf.py:159-180): aux_loss(cf_x).backward() must reach every HVAE weight
+    the reference's autograd graph reaches through abduct -> forward_latents x 2 -> combine (src/pgm/dscm.py:52-56).
+    Checked against the oracle's autograd on the eps the abduction kernels drew.
+
+    The counterfactual is a DIFFERENCE of two decodes of the same latents divided by a predicted scale, and its clamps /
+    ReLU masks are discontinuous, so its gradient is ill-conditioned under any storage rounding (the oracle with bf16
+    storage emulated deviates from the fp32 oracle by 6 ... 30 % on the benchmark inputs).  The test therefore uses a smooth
+    regime -- mid-range pixels, means scaled into (-1, 1), a full parent swap as intervention -- where that inherent
+    drift is 2 ... 6 % (reported next to the measurement).  Fixed tolerances: gradient global rel-L2 <= 0.12, cosine >= 0.985,
+    no gradient where the reference has none; the new kernels are checked tightly on their own
+    (test_kernels_gpu.py::test_cf_combine_and_sample_backward)."""
+    from causalgen_b200 import HVAE, counterfactual
+    cfg = O.make_cfg(name)
+    sd = O.seeded_state_dict(cfg, seed=7)
+    sd["likelihood.x_loc.weight"] = sd["likelihood.x_loc.weight"] * 0.25
+    sd["likelihood.x_loc.bias"] = sd["likelihood.x_loc.bias"] * 0.25
+    model = HVAE(cfg)
+    model.load_state_dict(sd, strict=True)
+    model.to(DEV).train()
+    model.__dict__["export_eps"] = True
+    if cfg.cond_prior:
+        model.drop_cond = lambda: (1, 1)
+    x8, pa, _ = O.synthetic_batch(cfg, CASES[name], seed=11)
+    x = O.normalise_x((x8.float() * 0.5 + 64).to(torch.uint8))
+    cf = O.synthetic_batch(cfg, CASES[name], seed=99)[1]
+    R = cfg.input_res
+    pa_full, cf_full = O.expand_parents(pa, R), O.expand_parents(cf, R)
+    w = torch.from_numpy(np.random.default_rng(5).standard_normal(tuple(x.shape)).astype(np.float32))
+    model.zero_grad()
+    cf_x, var = counterfactual(model, x.to(DEV), pa.to(DEV), cf.to(DEV), t_abduct=t_abduct)
+    assert var is None and cf_x.requires_grad
+    (cf_x * w.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    prog = model.engine().programs[("cf_train", x.shape[0])]
+    eps = [e.cpu().clone() for e in prog.eps_out]
+
+    def oracle(emulate):
+        O.EMULATE_BF16 = emulate
+        try:
+            sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+            zs = O.hvae_abduct(sdr, cfg, x, pa_full, O.NoiseTape(tensors=eps), t=t_abduct)
+            zs = [z["z"] for z in zs] if cfg.cond_prior else zs
+            cf_loc, cf_scale = O.hvae_forward_latents(sdr, cfg, zs, cf_full)
+            rec_loc, rec_scale = O.hvae_forward_latents(sdr, cfg, zs, pa_full)
+            u = (x - rec_loc) / rec_scale.clamp(min=1e-12)
+            out = torch.clamp(cf_loc + cf_scale * u, -1, 1)
+            (out * w).sum().backward()
+        finally:
+            O.EMULATE_BF16 = False
+        return out.detach(), sdr
+    ref, sd32 = oracle(False)
+    emu, sd16 = oracle(True)
+    assert_pixels(cf_x.detach().cpu(), ref, emu, f"{name} cf_x (grad path)")
+    named = dict(model.named_parameters())
+    num = den = dnum = 0.0
+    gmax = max(float(p.grad.norm()) for p in sd32.values() if p.grad is not None)
+    bad, reached = [], 0
+    for k, p in sd32.items():
+        if p.grad is None or float(p.grad.norm()) <= 1e-6 * gmax:  # untouched, or cancelling analytically (scale bias)
+            assert named[k].grad is None or float(named[k].grad.norm()) <= 1e-3 * gmax, f"{k}: gradient where the reference has none"
+            continue
+        reached += 1
+        g = named[k].grad.cpu()
+        num += float((g - p.grad).pow(2).sum())
+        dnum += float((sd16[k].grad - p.grad).pow(2).sum())
+        den += float(p.grad.pow(2).sum())
+        if float(p.grad.norm()) > 5e-2 * gmax and rel_l2(g, p.grad) > 0.3:
+            bad.append((k, round(rel_l2(g, p.grad), 4)))
+    glob, drift = (num / den) ** 0.5, (dnum / den) ** 0.5
+    ga = torch.cat([named[k].grad.cpu().flatten() for k, p in sd32.items() if p.grad is not None and float(p.grad.norm()) > 0])
+    gb = torch.cat([p.grad.flatten() for k, p in sd32.items() if p.grad is not None and float(p.grad.norm()) > 0])
+    cos = float((ga * gb).sum() / (ga.norm() * gb.norm()))
+    parity_report(f"cf-grad[{name}]", "grad global rel-L2", glob, 0.12, f"bf16-emulated oracle drift {drift:.2e}; {reached} tensors")
+    parity_report(f"cf-grad[{name}]", "grad 1 - cosine", 1 - cos, 0.015)
+    assert glob <= 0.12 and cos >= 0.985, f"{name} counterfactual grad rel-L2 {glob:.4f} cos {cos:.4f} (drift {drift:.4f})"
+    assert not bad, f"{name} per-tensor outliers: {bad[:8]}"
+    assert reached > 0.8 * len(sd32)
+    # the ELBO node and the counterfactual node may be evaluated before one backward (src/pgm/dscm.py:41-88)
+    model.zero_grad()
+    out = model(x.to(DEV), pa.to(DEV), beta=cfg.beta)
+    cf2, _ = counterfactual(model, x.to(DEV), pa.to(DEV), cf.to(DEV), t_abduct=t_abduct)
+    (out["elbo"] + 0.1 * (cf2 * w.to(DEV)).sum()).backward()
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
 
 
 def test_counterfactual_graph_replay():

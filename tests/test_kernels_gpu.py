@@ -183,7 +183,12 @@ def test_conv_dgrad_and_wgrad(case):
 
 @pytest.mark.parametrize("case", [(8, 96, 96, [16], 0, 64, 3, 1), (8, 96, 96, [64], 0, 16, 3, 1),
                                   (16, 48, 48, [32], 0, 96, 3, 2), (32, 24, 24, [128, 128], 4, 32, 3, 1),
-                                  (8, 96, 96, [16], 4, 64, 1, 0), (4, 192, 192, [16], 0, 32, 3, 1)])
+                                  (8, 96, 96, [16], 4, 64, 1, 0), (4, 192, 192, [16], 0, 32, 3, 1),
+                                  # wide outputs: one CTA covers up to 128 output channels in column groups of <= 64
+                                  (32, 24, 24, [32], 0, 128, 3, 1),     # Nc 128 = 64 + 64
+                                  (32, 24, 24, [32], 0, 160, 3, 1),     # two CTAs of Nc 80 = 48 + 32
+                                  (16, 12, 12, [48], 0, 224, 3, 1),     # two CTAs of Nc 112 = 64 + 48
+                                  (16, 48, 48, [32], 0, 96, 3, 1)])     # Nc 96 = 48 + 48
 def test_conv_many_tiles_per_cta(case):
     """pipeline rings wrap many times: several tiles per persistent CTA, in-place accumulate, fused operands"""
     from causalgen_b200.ops import SegSpec, View, new_act, round16
@@ -736,3 +741,74 @@ def test_normalise_u8_and_deterministic_sumsq():
         res.append(o.item())
     assert res[0] == res[1] == res[2]
     assert abs(res[0] - float((v.double() ** 2).sum())) <= 1e-5 * res[0]
+
+
+@pytest.mark.parametrize("Cc,Cw", [(1, 32), (3, 16)])
+def test_cf_combine_and_sample_backward(Cc, Cw):
+    """the two kernels the counterfactual backward adds (src/pgm/dscm.py:55-56, src/vae.py:352-369,413-422) against torch
+    autograd of the same expressions, fp32: 2e-3 of the tensor scale (h is bf16-rounded on both sides)"""
+    import ctypes as C
+    from causalgen_b200 import _lib as L
+    lib = L.load()
+    N, H = 3, 12
+    HW = H * H
+    n = N * Cc * HW
+    g = torch.Generator().manual_seed(4)
+    x = (torch.rand(N, Cc, H, H, generator=g) * 1.6 - 0.8).to(DEV)
+    t = {k: torch.randn(N, Cc, H, H, generator=g).to(DEV) for k in ("rec_loc", "cf_loc", "dcf")}
+    t["rec_loc"] = (t["rec_loc"] * 0.3).requires_grad_(True)
+    t["cf_loc"] = (t["cf_loc"] * 0.3).requires_grad_(True)
+    rec_scale = (torch.rand(N, Cc, H, H, generator=g) * 0.5 + 0.2).to(DEV).requires_grad_(True)
+    cf_scale = (torch.rand(N, Cc, H, H, generator=g) * 0.5 + 0.2).to(DEV).requires_grad_(True)
+    u = (x - t["rec_loc"]) / rec_scale.clamp(min=1e-12)
+    cf = torch.clamp(t["cf_loc"] + cf_scale * u, -1, 1)
+    cf.backward(t["dcf"])
+    outs = [torch.zeros(N, Cc, H, H, device=DEV) for _ in range(4)]
+    L.check(lib.cg_cf_combine_bwd(x.data_ptr(), t["rec_loc"].data_ptr(), rec_scale.data_ptr(), t["cf_loc"].data_ptr(),
+                                  cf_scale.data_ptr(), t["dcf"].data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(),
+                                  outs[2].data_ptr(), outs[3].data_ptr(), n, stream()))
+    torch.cuda.synchronize()
+    assert float((cf.abs() >= 1).float().mean()) > 0.02, "the clamp mask must be exercised"
+    for got, want, nm in zip(outs, (t["rec_loc"].grad, rec_scale.grad, t["cf_loc"].grad, cf_scale.grad),
+                             ("d rec_loc", "d rec_scale", "d cf_loc", "d cf_scale")):
+        assert_close(got, want, 1e-5, f"cf_combine_bwd {nm}")
+    # likelihood.sample(h, return_loc=True) backward
+    h_nchw = rnd(N, Cw, H, H, seed=8).to(torch.bfloat16).float().requires_grad_(True)
+    hp = nhwc_bf16(h_nchw.detach())
+    W = {k: (rnd(Cc, Cw, seed=20 + i, scale=0.6 / math.sqrt(Cw))).requires_grad_(True) for i, k in enumerate(("loc", "ls", "co"))}
+    Bv = {k: rnd(Cc, seed=30 + i, scale=0.3).requires_grad_(True) for i, k in enumerate(("loc", "ls", "co"))}
+    with torch.no_grad():
+        Bv["ls"] -= 1.0
+        Bv["loc"] += 0.6   # some means beyond +1 so the clamp mask matters
+
+    def head(k):
+        return torch.einsum("nkhw,ck->nchw", h_nchw, W[k]) + Bv[k][None, :, None, None]
+    loc, ls = head("loc"), head("ls").clamp(min=-9.0)
+    if Cc == 3:
+        co = torch.tanh(head("co"))
+        r = loc[:, 0].clamp(-1, 1)
+        gg = (loc[:, 1] + co[:, 0] * r).clamp(-1, 1)
+        b = (loc[:, 2] + co[:, 1] * r + co[:, 2] * gg).clamp(-1, 1)
+        loc = torch.stack([r, gg, b], 1)
+    xo, so = loc.clamp(-1, 1), ls.exp()
+    dxo, dso = rnd(N, Cc, H, H, seed=41), rnd(N, Cc, H, H, seed=42)
+    (xo * dxo + so * dso).sum().backward()
+    a = L.DGaussArgs()
+    a.h, a.h_ns, a.Cw = hp.data_ptr(), ns_of(hp), Cw
+    a.w_loc, a.b_loc, a.w_ls, a.b_ls = W["loc"].data_ptr(), Bv["loc"].data_ptr(), W["ls"].data_ptr(), Bv["ls"].data_ptr()
+    if Cc == 3:
+        a.w_co, a.b_co = W["co"].data_ptr(), Bv["co"].data_ptr()
+    a.N, a.HW, a.C = N, HW, Cc
+    dh = torch.zeros_like(hp)
+    gw = {k: torch.zeros(Cc, Cw, device=DEV) for k in W}
+    gb = {k: torch.zeros(Cc, device=DEV) for k in W}
+    a.dh, a.dh_ns = dh.data_ptr(), ns_of(dh)
+    a.dw_loc, a.db_loc, a.dw_ls, a.db_ls = gw["loc"].data_ptr(), gb["loc"].data_ptr(), gw["ls"].data_ptr(), gb["ls"].data_ptr()
+    if Cc == 3:
+        a.dw_co, a.db_co = gw["co"].data_ptr(), gb["co"].data_ptr()
+    L.check(lib.cg_dgauss_sample_bwd(C.byref(a), dxo.data_ptr(), dso.data_ptr(), stream()))
+    torch.cuda.synchronize()
+    assert_close(to_nchw(dh, Cw), h_nchw.grad, 1e-2, "sample_bwd dh (bf16 store)")
+    for k in (("loc", "ls", "co") if Cc == 3 else ("loc", "ls")):
+        assert_close(gw[k], W[k].grad, 2e-3, f"sample_bwd dW_{k}")
+        assert_close(gb[k], Bv[k].grad, 2e-3, f"sample_bwd db_{k}")

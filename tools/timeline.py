@@ -2,7 +2,8 @@
 usage: CAUSALGEN_B200_LIB=causal-gen_b200/causalgen_b200/libcausalgen_b200_tl.so python tools/timeline.py [case-substring]
 Marks (ns relative to kernel entry of CTA (0,0)):
   conv : 32 entry | 33 prologue done | 34 weight slab landed | 35+2i tile i first A chunk ready | 36+2i tile i MMAs
-         issued | 50+i epilogue of tile i done (warp 0) | 60 all warps done
+         issued | 50+i epilogue of tile i done (warp 0) | 60 all warps done | 70+i accumulator free for tile i (MMA warp)
+         | 80+i accumulator of tile i complete (epilogue warp 0).  CG_TL_FIRST=k moves the tile window to tiles k.. of CTA 0
   wgrad: 1 entry | 0 prologue done | 2+2i tile i ready | 3+2i tile i MMAs issued | 20 accumulators complete
          | 21 flush done | 22 all warps done"""
 import ctypes as C, os, sys
@@ -22,7 +23,7 @@ only = argv[0] if argv else None
 N = int(argv[1]) if len(argv) > 1 else 32
 lib = L.load()
 lib.cg_debug_timeline.argtypes = [C.c_void_p]; lib.cg_debug_timeline.restype = None
-tl = torch.zeros(64, dtype=torch.int64, device="cuda")
+tl = torch.zeros(128, dtype=torch.int64, device="cuda")
 def s(): return torch.cuda.current_stream().cuda_stream
 def show(tag, base, keys):
     v = tl.cpu().tolist()
@@ -47,7 +48,7 @@ for name, H, cins, cout, k, act, epi in CASES:
     dw = torch.zeros_like(w); db = torch.zeros_like(b)
     lw = layer.wgrad(views, x1, dw, db, N, H, H)
     print(name)
-    for tag, fn, base, keys in (("conv", ln, 32, [33, 34] + list(range(35, 47)) + list(range(50, 58)) + [60]),
+    for tag, fn, base, keys in (("conv", ln, 32, [33, 34] + list(range(35, 47)) + list(range(50, 58)) + [60] + list(range(70, 76)) + list(range(80, 88))),
                                 ("wgrad", lw, 1, [0] + list(range(2, 18)) + [20, 21, 22])):
         lib.cg_debug_timeline(None)
         for _ in range(3): fn(s())
