@@ -122,6 +122,7 @@ _SIGNATURES = {
     "cg_cf_combine": (C.c_int, [C.c_void_p] * 8 + [C.c_int64, C.c_void_p]),
     "cg_cf_combine_bwd": (C.c_int, [C.c_void_p] * 10 + [C.c_int64, C.c_void_p]),
     "cg_normalise_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "cg_augment_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p]),
     "cg_parents_plane": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
     "cg_nchw_f32_to_planar": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 3 + [C.c_int64, C.c_void_p]),

@@ -164,6 +164,10 @@ class Trainer:
     def start_epoch(self):
         self.iter_in_epoch = 0
 
+    def invalidate_graphs(self):
+        """drop the captured graphs (optimiser hyper-parameters are baked into them); the next step re-captures"""
+        self.g_fb = self.g_opt = None
+
     def step_device(self, x8_dev: torch.Tensor, pa_dev: torch.Tensor) -> torch.Tensor:
         """inputs already resident on the device; returns the device tensor {elbo, nll, kl} (overwritten by the next
         step)"""

@@ -32,8 +32,8 @@
 // The kernel is launched with programmatic stream serialization: everything before griddepcontrol.wait (barriers,
 // TMEM allocation, bias, weight-slab request) overlaps the tail of the previous kernel in the stream.
 //
-// Warp roles: 0-7 epilogue (TMEM lane quarter = warp & 3, column half = warp >> 2), 8 MMA issuer + TMEM owner,
-//             9 TMA producer, 10-13 transform.
+// Warp roles: 0-7 epilogue (TMEM lane quarter = warp & 3, column half = warp >> 2), 8 MMA issuer (even tiles) + TMEM owner,
+//             9 TMA producer, 10-13 transform, 14 MMA issuer (odd tiles).
 #include <cuda.h>
 
 #include <cstdlib>
@@ -47,28 +47,24 @@ constexpr int kMmaWarp = 8;
 constexpr int kTmaWarp = 9;
 constexpr int kXfWarp0 = 10;
 constexpr int kXfWarps = 4;
-constexpr int kThreads = (kXfWarp0 + kXfWarps) * 32;  // 448
+constexpr int kMmaWarp2 = kXfWarp0 + kXfWarps;        // second MMA issuer (tiles 1, 3, 5, ... of the CTA)
+constexpr int kThreads = (kMmaWarp2 + 1) * 32;        // 480
 constexpr int kXfThreads = kXfWarps * 32;
 constexpr int kMaxStages = 32;  // A-ring depth is chosen per launch from the shared memory left over
 constexpr int kMinStages = 4;   //   after the resident weight slab (pick_nc guarantees this many)
 constexpr int kPlane3 = 2880;  // 18 rows * 10 px * 16 B
 constexpr int kPlane1 = 2048;  // 16 rows *  8 px * 16 B
 constexpr int kStageBytes = 4 * kPlane3;  // 11520: largest A stage (32 channels with halo); multiple of 128
-constexpr int kHdrBytes = 4224;   // barriers (<=1024B) | tmem slot @1024 | bias[128] @1088 | epilogue plans @1664
-constexpr int kPlanOff = 1664;
+static_assert(kStageBytes / 16 <= 6 * 128, "transform warps cover a stage in six 16-byte slots per thread");
+constexpr int kHdrBytes = 2176;   // barriers (<=1024B) | tmem slot @1024 | bias[256] @1088
 constexpr int kSmemMax = 232448;  // 227 KB
 constexpr int kMaxChunks = 40;
-constexpr int kMaxNc = 128;       // GEMM-N per CTA: one A-tile read (TMA and tensor core) serves up to 128 output channels
-constexpr int kEGroup = 64;       // the epilogue walks the accumulator in column groups of <= 64 (2 x 16 columns per warp)
-constexpr int kMaxGroups = kMaxNc / kEGroup;
-constexpr int kMaxEStages = 8;    // epilogue-operand ring depth in groups (chosen per launch, >= kMinEStages)
+constexpr int kMaxNc = 64;        // GEMM-N per CTA
+constexpr int kMaxEStages = 8;    // epilogue-operand ring depth (chosen per launch, >= kMinEStages)
 constexpr int kMinEStages = 2;
-constexpr int kESlots = 2;        // staged operands per group
-// columns per epilogue group: Nc split evenly over ceil(Nc/64) groups, rounded up to whole 16-column chunks
-__host__ __device__ constexpr int e_groups(int nc) { return (nc + kEGroup - 1) / kEGroup; }
-__host__ __device__ constexpr int e_gcols(int nc) { return ((nc + e_groups(nc) - 1) / e_groups(nc) + 15) / 16 * 16; }
-// a staged operand group is [gcols/8 octets][16 rows][8 px][8 ch] bf16 = gcols/8 planes of 2048 B
-__host__ __device__ constexpr int e_slot_bytes(int nc) { return (e_gcols(nc) / 8) * kPlane1; }
+constexpr int kESlots = 2;        // staged operands per tile
+// a staged operand tile is [Nc/8 octets][16 rows][8 px][8 ch] bf16 = Nc/8 planes of 2048 B
+__host__ __device__ constexpr int e_slot_bytes(int nc) { return (nc / 8) * kPlane1; }
 __host__ __device__ constexpr int e_bytes_min(int nc) { return kMinEStages * kESlots * e_slot_bytes(nc); }
 
 // barrier indices (fixed slots sized for the maximum ring depths)
@@ -95,37 +91,20 @@ struct alignas(64) KParams {
   uint32_t src_bytes[CG_MAX_SRC];  // TMA transaction bytes of one A box per source
   int nE, emode;
   int nchunks, ntaps, Nc, nN, ktot16;
-  int ngroups, gcols;  // epilogue column groups of this launch (e_groups / e_gcols of Nc)
   int flat;  // 1: H=W=1, samples are the GEMM rows (128 per tile)
   int nst, nest;       // A-ring / E-ring depths of this launch
+  int nst0;            // stages of ring 0 (even local tiles); ring 1 (odd tiles) has nst - nst0; nst0 == nst: one ring
   int stage_bytes;     // bytes of one A stage (largest source box)
   int tiles_x, tiles_per_img, ntiles;
   long long HW8;  // H*W*8: elements per channel-octet plane
   uint32_t idesc, tmem_cols, slab_bytes, e_tx_bytes;
   unsigned long long* tl;  // debug timeline (CG_TIMELINE builds)
-  int tl_first;  // CG_TL_FIRST: first tile of the timeline window (debug builds)
-  int dbg;  // CG_DEBUG_SKIP bit mask (profiling experiments only): 2 no act, 4 no mma, 8 no epilogue stores, 16 no TMA refill
+  int dbg;  // CG_DEBUG_SKIP bit mask (profiling experiments only): 2 no act, 4 no mma, 8 no epilogue stores
 };
 
 struct TileGeom {
   int n, h0, w0;
 };
-
-// What one 16-column chunk of the accumulator maps to: resolved once per warp, kept in shared memory (warp-uniform
-// reads), because a warp now owns up to 2 chunks in each of up to kMaxGroups column groups.
-struct ChunkPlan {
-  int col, ecol;                // column inside the CTA's accumulator (-1: absent) / inside its group (staged operands)
-  int sgi, lc, cnt;             // sgi < 0: chunk has no destination (padding / beyond cout)
-  int k_add, k_add2, k_mul;     // -2 absent, -1 read from global memory, >= 0 staged E slot
-  int dtype, mul_act, out_act;
-  int fast;                     // -1: generic path; else bit0 mul, bit1 add, bit2 add2, bit3 relu, bit4 gelu, bit5 copy
-  uint8_t* out2;                // act_copy destination (+ plane offset) or nullptr
-  long long ns2;                // its sample stride
-  uint8_t* out;                 // bf16: ptr + (lc/8) planes; fp32: ptr + lc floats
-  long long ns;
-};
-static_assert(kPlanOff + kEpiWarps * 2 * kMaxGroups * sizeof(ChunkPlan) <= kHdrBytes, "plans overflow the header");
-static_assert(kPlanOff >= 1088 + kMaxNc * 4, "bias overlaps the plans");
 
 __device__ __forceinline__ TileGeom tile_geom(const KParams& P, int tile) {
   TileGeom g;
@@ -298,12 +277,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int plane = k3 ? kPlane3 : kPlane1;
   const int H = P.a.H, W = P.a.W, N = P.a.N;
 
-  if (warp == kMmaWarp) {
-    // ------------------------------------------------------------------ MMA issuer
+  if (warp == kMmaWarp || warp == kMmaWarp2) {
+    // ------------------------------------------------------------------ MMA issuers
+    // TWO issuing warps on alternate tiles (issuer w: local tiles w, w+2, ... into accumulator w).  The tensor pipe's
+    // instruction queue is shallow: with one issuer, the scalar work between two tiles (barrier polls, fences, descriptor
+    // set-up, commits: ~300 clk) drains it and every tile pays that bubble on top of its MMAs -- measured 1084 -> 711 clk
+    // per 18-MMA tile and 1854 -> 1409 clk per 36-MMA tile with the second issuer (tools/micro/umma_rate2.cu,
+    // profiles/r2i_umma_rate2.txt).  tcgen05.commit tracks the MMAs of the executing thread, so each issuer's commits
+    // cover exactly its own tile.
+    const uint32_t iw = warp == kMmaWarp ? 0u : 1u;
     if (elect_one()) {
       mbar_wait(BAR(B_BFULL), 0);  // weight slab (requested by thread 0 in the prologue)
-      CG_TL(P.tl, 34);
-      int tl_i = -P.tl_first;  // timeline window: tiles [tl_first, tl_first + 6) of this CTA (steady state when > 0)
+      if (iw == 0) CG_TL(P.tl, 34);
+      int tl_i = iw == 0 ? 0 : 1000;  // timeline marks: issuer 0 only (its tiles 0, 2, 4, ...)
       (void)tl_i;
       // Descriptors are built once; per MMA only the 14-bit start-address field (low word) advances
       // (all offsets are multiples of 16 B).
@@ -318,19 +304,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t stage16 = (uint32_t)stage_bytes >> 4;
       const uint32_t idesc = P.idesc;
       const int ready0 = (act == CG_ACT_NONE) ? B_LANDED : B_AFULL;  // no activation: consume TMA data directly
-      uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+      // Ring split: even local tiles live in ring 0 (stages [0, nst0)), odd tiles in ring 1 (stages [nst0, nst)), and issuer
+      // w only ever touches ring w.  Every waiter therefore observes EVERY fill of the stages it waits on, in order --
+      // an mbarrier parity wait is only valid for the phase right after the last one the waiter saw, so an issuer that
+      // skipped the other's fills of a shared stage could read a stale parity (that version deadlocked).
+      // One tile per CTA (nst0 == nst): a single ring, issuer 1 idles.
+      const bool two = P.nst0 < nst;
+      const uint32_t rbase = (two && iw) ? (uint32_t)P.nst0 : 0u, rn = two ? (iw ? (uint32_t)(nst - P.nst0) : (uint32_t)P.nst0) : (uint32_t)nst;
+      uint32_t stage = 0, phase = 0, aphase = 0, as = two ? iw : 0u;
+      const int tstep = two ? 2 * (int)gridDim.x : (int)gridDim.x;
+      for (int tile = blockIdx.x + (two ? (int)iw * (int)gridDim.x : 0); tile < P.ntiles && (two || iw == 0); tile += tstep) {
         mbar_wait(BAR(B_ACCEMPTY + as), aphase ^ 1u);
         tc_fence_after();
-        if (tl_i >= 0 && tl_i < 6) CG_TL(P.tl, 70 + tl_i);
         const uint32_t d_tmem = tmem_base + as * (uint32_t)Nc;
         uint32_t accum = 0;
         for (int c = 0; c < P.nchunks; ++c) {
           const Chunk ch = P.chunk[c];
-          mbar_wait(BAR(ready0 + stage), phase);
+          const uint32_t gs = rbase + stage;
+          mbar_wait(BAR(ready0 + gs), phase);
           tc_fence_after();
-          if (c == 0 && tl_i >= 0 && tl_i < 6) CG_TL(P.tl, 35 + 2 * tl_i);
-          uint32_t alo = a_lo0 + stage * stage16;
+          if (c == 0 && tl_i < 6) CG_TL(P.tl, 35 + 2 * tl_i);
+          uint32_t alo = a_lo0 + gs * stage16;
           uint32_t blo = b_lo0 + (uint32_t)ch.kbase * b_step16;
           for (int j = 0; j < ch.nc16 && !(P.dbg & 4); ++j) {
             if (k3) {
@@ -347,13 +341,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
             alo += plane2_16;
           }
-          tc_commit(BAR(B_AEMPTY + stage));  // frees the A stage once these MMAs retire
-          if (++stage == nst) { stage = 0; phase ^= 1u; }
+          tc_commit(BAR(B_AEMPTY + gs));  // frees the A stage once these MMAs retire
+          if (++stage == rn) { stage = 0; phase ^= 1u; }
         }
         tc_commit(BAR(B_ACCFULL + as));  // accumulator ready for the epilogue
-        if (tl_i >= 0 && tl_i < 6) CG_TL(P.tl, 36 + 2 * tl_i);
+        if (tl_i < 6) CG_TL(P.tl, 36 + 2 * tl_i);
         ++tl_i;
-        if (++as == 2) { as = 0; aphase ^= 1u; }
+        if (two) aphase ^= 1u;
+        else if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
   } else if (warp == kTmaWarp) {
@@ -361,54 +356,66 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (elect_one()) {
       for (int s = 0; s < P.a.nsrc; ++s) tma_prefetch_desc(&P.src_map[s]);
       for (int k = 0; k < P.nE; ++k) tma_prefetch_desc(&P.e_map[k]);
-      uint32_t stage = 0, phase = 0, es = 0, ephase = 0;
+      uint32_t es = 0, ephase = 0, lt = 0;
+      uint32_t st0 = 0, st1 = 0, ph0 = 0, ph1 = 0;  // stage / phase inside ring 0 (even local tiles) and ring 1 (odd)
+      const uint32_t len0 = (uint32_t)P.nst0, len1 = (uint32_t)(nst - P.nst0);
+      const bool two = P.nst0 < nst;
       const int halo = k3 ? 1 : 0;
-      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++lt) {
         const TileGeom g = tile_geom(P, tile);
+        const uint32_t r = two ? (lt & 1u) : 0u, rbase = r ? (uint32_t)P.nst0 : 0u;
         if (P.nE > 0) {
-          for (int gi = 0; gi < P.ngroups; ++gi) {  // one E stage per 64-column group of the tile
-            mbar_wait(BAR(B_EEMPTY + es), ephase ^ 1u);
-            mbar_expect_tx(BAR(B_EFULL + es), P.e_tx_bytes);
-            for (int k = 0; k < P.nE; ++k) {
-              const uint32_t dst = cg_smem_u32(sE + es * estage + k * eslot);
-              const int oct = nchunkN * (Nc >> 3) + gi * (P.gcols >> 3) - P.eop[k].oct_off;  // may be out of range: zero-filled
-              if (P.flat) tma_load_3d(dst, &P.e_map[k], 0, g.n, oct, BAR(B_EFULL + es));
-              else tma_load_4d(dst, &P.e_map[k], g.w0 * 8, g.h0, oct, g.n, BAR(B_EFULL + es));
-            }
-            if (++es == nest) { es = 0; ephase ^= 1u; }
+          mbar_wait(BAR(B_EEMPTY + es), ephase ^ 1u);
+          mbar_expect_tx(BAR(B_EFULL + es), P.e_tx_bytes);
+          for (int k = 0; k < P.nE; ++k) {
+            const uint32_t dst = cg_smem_u32(sE + es * estage + k * eslot);
+            const int oct = nchunkN * (Nc >> 3) - P.eop[k].oct_off;  // may be out of range: zero-filled
+            if (P.flat) tma_load_3d(dst, &P.e_map[k], 0, g.n, oct, BAR(B_EFULL + es));
+            else tma_load_4d(dst, &P.e_map[k], g.w0 * 8, g.h0, oct, g.n, BAR(B_EFULL + es));
           }
+          if (++es == nest) { es = 0; ephase ^= 1u; }
         }
         for (int c = 0; c < P.nchunks; ++c) {
           const Chunk ch = P.chunk[c];
-          mbar_wait(BAR(B_AEMPTY + stage), phase ^ 1u);
-          if ((P.dbg & 16) && phase != 0) {  // profiling experiment: after the first ring fill, consume stale tiles (no TMA)
-            mbar_arrive(BAR(B_LANDED + stage));
-            if (++stage == nst) { stage = 0; phase ^= 1u; }
-            continue;
-          }
+          const uint32_t stage = rbase + (r ? st1 : st0);
+          mbar_wait(BAR(B_AEMPTY + stage), (r ? ph1 : ph0) ^ 1u);
           mbar_expect_tx(BAR(B_LANDED + stage), P.src_bytes[ch.src]);
           const uint32_t dst = cg_smem_u32(sA + stage * stage_bytes);
           if (P.flat) tma_load_3d(dst, &P.src_map[ch.src], 0, g.n, ch.oct0, BAR(B_LANDED + stage));
           else tma_load_4d(dst, &P.src_map[ch.src], (g.w0 - halo) * 8, g.h0 - halo, ch.oct0, g.n, BAR(B_LANDED + stage));
-          if (++stage == nst) { stage = 0; phase ^= 1u; }
+          if (r) { if (++st1 == len1) { st1 = 0; ph1 ^= 1u; } }
+          else if (++st0 == len0) { st0 = 0; ph0 ^= 1u; }
         }
       }
     }
-  } else if (warp >= kXfWarp0) {
+  } else if (warp >= kXfWarp0 && warp < kMmaWarp2) {
     // ------------------------------------------------------------------ transform warps
     if (act != CG_ACT_NONE) {
       const int xt = threadIdx.x - kXfWarp0 * 32;
-      uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+      uint32_t st0 = 0, st1 = 0, ph0 = 0, ph1 = 0, lt = 0;
+      const uint32_t len0 = (uint32_t)P.nst0, len1 = (uint32_t)(nst - P.nst0);
+      const bool two = P.nst0 < nst;
+      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++lt) {
+        const uint32_t r = two ? (lt & 1u) : 0u, rbase = r ? (uint32_t)P.nst0 : 0u;
         for (int c = 0; c < P.nchunks; ++c) {
           const int n16 = (int)(P.src_bytes[P.chunk[c].src] >> 4);  // 16-byte slots the TMA box filled
+          const uint32_t stage = rbase + (r ? st1 : st0), phase = r ? ph1 : ph0;
           warp_wait(BAR(B_LANDED + stage), phase, lane);
           uint4* base = reinterpret_cast<uint4*>(sA + stage * stage_bytes);
-          for (int i = xt; i < n16; i += kXfThreads) base[i] = act8(base[i], act);
+          // a stage holds <= 720 16-byte slots = <= 6 per thread: all loads first, then activate + store (one round trip
+          // of shared-memory latency per stage instead of six)
+          uint4 v[6];
+#pragma unroll
+          for (int k = 0; k < 6; ++k)
+            if (xt + k * kXfThreads < n16) v[k] = base[xt + k * kXfThreads];
+#pragma unroll
+          for (int k = 0; k < 6; ++k)
+            if (xt + k * kXfThreads < n16) base[xt + k * kXfThreads] = act8(v[k], act);
           fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_AFULL + stage));
-          if (++stage == nst) { stage = 0; phase ^= 1u; }
+          if (r) { if (++st1 == len1) { st1 = 0; ph1 ^= 1u; } }
+          else if (++st0 == len0) { st0 = 0; ph0 ^= 1u; }
         }
       }
     }
@@ -419,72 +426,74 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // is the same for every tile, so it is resolved ONCE here (ChunkPlan); per tile the warp issues both TMEM
     // loads, waits once, releases the accumulator and then does bias / act' / residual / store from registers.
     uint32_t as = 0, aphase = 0, es = 0, ephase = 0;
-    int tl_i = -P.tl_first;
+    int tl_i = 0;
     (void)tl_i;
     const int quarter = warp & 3, half = warp >> 2;
     const int m = quarter * 32 + lane;
     const int nE = P.nE;
     const bool has_bias = P.a.bias != nullptr;
-    ChunkPlan* plan = reinterpret_cast<ChunkPlan*>(smem + kPlanOff) + warp * (2 * kMaxGroups);  // [group][j]
-    if (lane == 0) {
-      for (int pj = 0; pj < 2 * kMaxGroups; ++pj) {
-        ChunkPlan& pl = plan[pj];
-        const int gi = pj >> 1, j = pj & 1;
-        const int gbase = gi * P.gcols;
-        const int gend = min(Nc, gbase + P.gcols);
-        pl.ecol = half * 16 + 32 * j;
-        pl.col = gbase + pl.ecol;
-        pl.sgi = -1;
-        pl.lc = pl.cnt = 0;
-        pl.k_add = pl.k_add2 = pl.k_mul = -2;
-        pl.dtype = CG_BF16;
-        pl.mul_act = CG_ACT_NONE;
-        pl.out_act = CG_ACT_NONE;
-        pl.fast = -1;
-        pl.out = nullptr;
-        pl.out2 = nullptr;
-        pl.ns2 = 0;
-        pl.ns = 0;
-        if (gi >= P.ngroups || pl.col >= gend) { pl.col = -1; continue; }  // chunk does not exist in this launch
-        const int cg0 = nchunkN * Nc + pl.col;
-        if (cg0 >= P.a.cout || (P.dbg & 8)) continue;
-        for (int sgi = 0; sgi < P.a.nseg; ++sgi) {
-          const cg_seg& sg = P.a.seg[sgi];
-          const int lc = cg0 - sg.c0;
-          if (lc < 0 || lc >= sg.cn) continue;
-          pl.sgi = sgi;
-          pl.lc = lc;
-          pl.cnt = min(16, sg.cn - lc);
-          pl.dtype = sg.dtype;
-          pl.mul_act = sg.mul_act;
-          pl.out_act = sg.out_act;
-          pl.ns = sg.ns;
-          pl.out = reinterpret_cast<uint8_t*>(sg.ptr) +
-                   (sg.dtype == CG_F32 ? (long long)lc * 4 : (long long)(lc >> 3) * P.HW8 * 2);
-          if (DUAL && sg.act_copy != nullptr) {
-            pl.out2 = reinterpret_cast<uint8_t*>(sg.act_copy) + (long long)(lc >> 3) * P.HW8 * 2;
-            pl.ns2 = sg.act_copy_ns;
-          }
-          if (sg.add != nullptr) pl.k_add = -1;
-          if (sg.add2 != nullptr) pl.k_add2 = -1;
-          if (sg.mul != nullptr) pl.k_mul = -1;
-          for (int k = 0; k < nE; ++k)
-            if (P.eop[k].seg == sgi) {
-              if (P.eop[k].kind == 0) pl.k_add = k;
-              else if (P.eop[k].kind == 1) pl.k_add2 = k;
-              else pl.k_mul = k;
-            }
-          if (sg.dtype == CG_BF16 && pl.cnt == 16 && pl.k_add != -1 && pl.k_add2 != -1 && pl.k_mul != -1 &&
-              (pl.k_mul == -2 || sg.mul_act == CG_ACT_RELU) && !(pl.k_mul >= 0 && pl.k_add2 >= 0))
-            pl.fast = (pl.k_mul >= 0 ? 1 : 0) | (pl.k_add >= 0 ? 2 : 0) | (pl.k_add2 >= 0 ? 4 : 0) |
-                      (sg.out_act == CG_ACT_RELU ? 8 : 0) | (sg.out_act == CG_ACT_GELU ? 16 : 0) |
-                      (sg.act_copy != nullptr ? 32 : 0);
-          break;
+    struct ChunkPlan {
+      int col, sgi, lc, cnt;        // sgi < 0: chunk has no destination (padding / beyond cout)
+      int k_add, k_add2, k_mul;     // -2 absent, -1 read from global memory, >= 0 staged E slot
+      int dtype, mul_act, out_act;
+      int fast;                     // -1: generic path; else bit0 mul, bit1 add, bit2 add2, bit3 relu, bit4 gelu, bit5 copy
+      uint8_t* out2;                // act_copy destination (+ plane offset) or nullptr
+      long long ns2;                // its sample stride
+      uint8_t* out;                 // bf16: ptr + (lc/8) planes; fp32: ptr + lc floats
+      long long ns;
+    } plan[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      ChunkPlan& pl = plan[j];
+      pl.col = half * 16 + 32 * j;
+      pl.sgi = -1;
+      pl.lc = pl.cnt = 0;
+      pl.k_add = pl.k_add2 = pl.k_mul = -2;
+      pl.dtype = CG_BF16;
+      pl.mul_act = CG_ACT_NONE;
+      pl.out_act = CG_ACT_NONE;
+      pl.fast = -1;
+      pl.out = nullptr;
+      pl.out2 = nullptr;
+      pl.ns2 = 0;
+      pl.ns = 0;
+      const int cg0 = nchunkN * Nc + pl.col;
+      if (pl.col >= Nc || cg0 >= P.a.cout || (P.dbg & 8)) continue;
+      for (int sgi = 0; sgi < P.a.nseg; ++sgi) {
+        const cg_seg& sg = P.a.seg[sgi];
+        const int lc = cg0 - sg.c0;
+        if (lc < 0 || lc >= sg.cn) continue;
+        pl.sgi = sgi;
+        pl.lc = lc;
+        pl.cnt = min(16, sg.cn - lc);
+        pl.dtype = sg.dtype;
+        pl.mul_act = sg.mul_act;
+        pl.out_act = sg.out_act;
+        pl.ns = sg.ns;
+        pl.out = reinterpret_cast<uint8_t*>(sg.ptr) +
+                 (sg.dtype == CG_F32 ? (long long)lc * 4 : (long long)(lc >> 3) * P.HW8 * 2);
+        if (DUAL && sg.act_copy != nullptr) {
+          pl.out2 = reinterpret_cast<uint8_t*>(sg.act_copy) + (long long)(lc >> 3) * P.HW8 * 2;
+          pl.ns2 = sg.act_copy_ns;
         }
+        if (sg.add != nullptr) pl.k_add = -1;
+        if (sg.add2 != nullptr) pl.k_add2 = -1;
+        if (sg.mul != nullptr) pl.k_mul = -1;
+        for (int k = 0; k < nE; ++k)
+          if (P.eop[k].seg == sgi) {
+            if (P.eop[k].kind == 0) pl.k_add = k;
+            else if (P.eop[k].kind == 1) pl.k_add2 = k;
+            else pl.k_mul = k;
+          }
+        if (sg.dtype == CG_BF16 && pl.cnt == 16 && pl.k_add != -1 && pl.k_add2 != -1 && pl.k_mul != -1 &&
+            (pl.k_mul == -2 || sg.mul_act == CG_ACT_RELU) && !(pl.k_mul >= 0 && pl.k_add2 >= 0))
+          pl.fast = (pl.k_mul >= 0 ? 1 : 0) | (pl.k_add >= 0 ? 2 : 0) | (pl.k_add2 >= 0 ? 4 : 0) |
+                    (sg.out_act == CG_ACT_RELU ? 8 : 0) | (sg.out_act == CG_ACT_GELU ? 16 : 0) |
+                    (sg.act_copy != nullptr ? 32 : 0);
+        break;
       }
     }
-    __syncwarp();
-    const int ngroups = P.ngroups;
+    const bool two = plan[1].col < Nc;
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
       const TileGeom g = tile_geom(P, tile);
       bool valid;
@@ -500,33 +509,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         hw = (long long)h * W + w;
         valid = (h < H) && (w < W);
       }
-      const uint32_t t_row = tmem_base + as * (uint32_t)Nc + ((uint32_t)(quarter * 32) << 16);
-      for (int gi = 0; gi < ngroups; ++gi) {
-      const ChunkPlan* gplan = plan + 2 * gi;
       if (nE > 0) warp_wait(BAR(B_EFULL + es), ephase, lane);
-      if (gi == 0) {
-        warp_wait(BAR(B_ACCFULL + as), aphase, lane);
-        tc_fence_after();
-        if (threadIdx.x == 0 && tl_i >= 0 && tl_i < 8) CG_TL(P.tl, 80 + tl_i);
-      }
+      warp_wait(BAR(B_ACCFULL + as), aphase, lane);
+      tc_fence_after();
       const uint8_t* e_row = sE + (size_t)es * estage + (size_t)m * 16;
+      const uint32_t t_row = tmem_base + as * (uint32_t)Nc + ((uint32_t)(quarter * 32) << 16);
       float acc[2][16];
-      const int col0 = gplan[0].col, col1 = gplan[1].col;
       __syncwarp();  // .aligned TMEM loads need the whole warp converged
-      if (col0 >= 0) tmem_ld16_nowait(t_row + (uint32_t)col0, acc[0]);
-      if (col1 >= 0) tmem_ld16_nowait(t_row + (uint32_t)col1, acc[1]);
+      tmem_ld16_nowait(t_row + (uint32_t)plan[0].col, acc[0]);
+      if (two) tmem_ld16_nowait(t_row + (uint32_t)plan[1].col, acc[1]);
       tmem_ld_wait();
-      if (gi == ngroups - 1) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(B_ACCEMPTY + as));  // accumulator is in registers: MMA may reuse it
-      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_ACCEMPTY + as));  // accumulator is in registers: MMA may reuse it
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const ChunkPlan& pl = gplan[j];
-        if (pl.col < 0 || pl.sgi < 0) continue;
+        const ChunkPlan& pl = plan[j];
+        if (pl.sgi < 0) continue;
         if (pl.fast >= 0) {
-          const uint8_t* e0 = e_row + (pl.ecol >> 3) * kPlane1;
+          const uint8_t* e0 = e_row + (pl.col >> 3) * kPlane1;
           const float* bp = has_bias ? s_bias + pl.col : nullptr;
           bf16* op = reinterpret_cast<bf16*>(pl.out) + n * pl.ns + hw * 8;
           bf16* op2 = reinterpret_cast<bf16*>(pl.out2) + n * pl.ns2 + hw * 8;  // only dereferenced by COPY variants
@@ -567,7 +568,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         auto fetch = [&](int k, int kind, int h8, float* x) {
           uint4 u;
           if (k >= 0) {
-            u = *reinterpret_cast<const uint4*>(e_row + (size_t)k * eslot + ((pl.ecol + h8) >> 3) * kPlane1);
+            u = *reinterpret_cast<const uint4*>(e_row + (size_t)k * eslot + ((pl.col + h8) >> 3) * kPlane1);
           } else {
             const cg_seg& sg = P.a.seg[pl.sgi];
             const void* gp = kind == 0 ? sg.add : (kind == 1 ? sg.add2 : sg.mul);
@@ -630,8 +631,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (lane == 0) mbar_arrive(BAR(B_EEMPTY + es));
         if (++es == nest) { es = 0; ephase ^= 1u; }
       }
-      }  // column groups
-      if (threadIdx.x == 0 && tl_i >= 0 && tl_i < 8) CG_TL(P.tl, 50 + tl_i);
+      if (threadIdx.x == 0 && tl_i < 8) CG_TL(P.tl, 50 + tl_i);
       ++tl_i;
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
@@ -645,17 +645,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   }
 }
 
-// GEMM-N per CTA (<= kMaxNc, multiple of 16) such that the resident weight slab fits.  want_e: the launches of this
-// pack stage epilogue operands (residual / act' mask), so prefer a size that leaves room for the operand ring
-// (*emode = 1); packs whose launches never have such operands (first convs of a Block) take the largest chunk.
+// GEMM-N per CTA (<= 64, multiple of 16) such that the resident weight slab fits.  want_e: the launches of this pack
+// stage epilogue operands (residual / act' mask), so prefer a size that leaves room for the operand ring (*emode = 1);
+// packs whose launches never have such operands (first convs of a Block: huge K, narrow N) take the largest chunk.
 // Huge-K layers fall back to no ring (operands are then read straight from global memory by the epilogue).
+// Wider chunks (<= 128 columns per CTA) were built and measured in round 2 (profiles/r2c_microbench_b128.txt): with K
+// this small the epilogue, not the A-tile traffic, bounds wide outputs, and two CTAs beat one wide CTA.
 int pick_nc(int ktot16, int cout, int* emode, int want_e) {
   const int base = kSmemMax - kHdrBytes - kMinStages * kStageBytes;
   for (int mode = want_e ? 1 : 0; mode >= 0; --mode) {
     for (int nc_max = kMaxNc; nc_max >= 16; nc_max -= 16) {
+      if (ktot16 * nc_max * 32 + (mode ? e_bytes_min(nc_max) : 0) > base) continue;
       const int nN = (cout + nc_max - 1) / nc_max;
       const int nc = ((cout + nN - 1) / nN + 15) / 16 * 16;
-      if (ktot16 * nc * 32 + (mode ? e_bytes_min(nc) : 0) > base) continue;
       if (emode) *emode = mode;
       return nc;
     }
@@ -806,15 +808,13 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
       for (int kind = 0; kind < 3 && kp.nE < kESlots; ++kind) {
         if (ptrs[kind] == nullptr) continue;
         int rc = cg_make_planar_map(&kp.e_map[kp.nE], ptrs[kind], nss[kind], a->N, a->H, a->W, sg.cn / 8, kp.flat, 64, 16,
-                                    e_gcols(kp.Nc) / 8);
+                                    kp.Nc / 8);
         if (rc != CG_OK) return rc;
         kp.eop[kp.nE++] = EOp{s, kind, sg.c0 / 8};
       }
     }
   }
   kp.e_tx_bytes = (uint32_t)(kp.nE * e_slot_bytes(kp.Nc));
-  kp.ngroups = e_groups(kp.Nc);
-  kp.gcols = e_gcols(kp.Nc);
   if (flat) {
     kp.tiles_x = 1;
     kp.tiles_per_img = 1;
@@ -835,16 +835,17 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
     if ((int)kp.src_bytes[s] > kp.stage_bytes) kp.stage_bytes = (int)kp.src_bytes[s];
   {
     const int budget = kSmemMax - kHdrBytes - (int)kp.slab_bytes;
-    const int e_group = kp.nE * e_slot_bytes(kp.Nc), e_tile = e_group * kp.ngroups, a_tile = kp.nchunks * kp.stage_bytes;
-    kp.nest = 0;  // E stages are per column group
+    const int e_tile = kp.nE * e_slot_bytes(kp.Nc), a_tile = kp.nchunks * kp.stage_bytes;
+    kp.nest = 0;
     if (e_tile > 0) {
-      int d = budget / (a_tile + e_tile) * kp.ngroups;
+      int d = budget / (a_tile + e_tile);
       kp.nest = d < kMinEStages ? kMinEStages : (d > kMaxEStages ? kMaxEStages : d);
     }
-    kp.nst = (budget - kp.nest * e_group) / kp.stage_bytes;
+    kp.nst = (budget - kp.nest * e_tile) / kp.stage_bytes;
     if (kp.nst > kMaxStages) kp.nst = kMaxStages;
     CG_REQUIRE(kp.nst >= 2, "cg_conv2d: no shared memory left for the input ring (K=%d)", kp.ktot16 * 16);
   }
+  kp.nst0 = kp.nst;  // one ring unless the grid below gives a CTA more than one tile
   const int smem_bytes = kHdrBytes + kp.nst * kp.stage_bytes + kp.nest * kp.nE * e_slot_bytes(kp.Nc) + (int)kp.slab_bytes;
   static bool attr_done = false;
   if (!attr_done) {
@@ -864,10 +865,6 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
   }
   kp.dbg = dbg;
   kp.tl = cg_tl_ptr;
-  {
-    const char* e = getenv("CG_TL_FIRST");
-    kp.tl_first = e ? atoi(e) : 0;
-  }
   const int sms = cg_device_sms();
   // CTAs along the pixel axis.  Small problems keep >= min_tiles tiles per CTA: the prologue (barriers, TMEM, weight
   // slab) is paid once per CTA, and the SMs left free run the kernels of the other lanes / weight-gradient streams.
@@ -884,6 +881,15 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
   if (pdl < 0) {
     const char* e = getenv("CG_NO_PDL");
     pdl = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  // two MMA issuers (two A rings) as soon as a CTA walks more than one tile; each ring keeps at least 2 stages
+  {
+    static int one_issuer = -1;
+    if (one_issuer < 0) {
+      const char* e = getenv("CG_ONE_ISSUER");  // profiling experiment: the round-1 single-issuer pipeline
+      one_issuer = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    if (!one_issuer && kp.ntiles > gx && kp.nst >= 4) kp.nst0 = (kp.nst + 1) / 2;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(gx, kp.nN);

@@ -59,6 +59,22 @@ __global__ void normalise_u8_kernel(const uint8_t* __restrict__ x8, float* __res
     x[i] = ((float)x8[i] - 127.5f) / 127.5f;
 }
 
+// torchvision RandomCrop(size=R, padding=(pad_left, pad_top), fill=0) + RandomHorizontalFlip on uint8 NCHW batches, one
+// (top, left, flip) triple per sample (src/datasets.py:107-118 UKBB, :281-286 Morpho-MNIST): out[y, x] = in[y + top -
+// pad_top, x' + left - pad_left] with x' = R-1-x when flipped, 0 outside the source image.
+__global__ void augment_u8_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const int* __restrict__ prm,
+                                  int C, int Hi, int Wi, int R, int pad_top, int pad_left) {
+  const int n = blockIdx.z, c = blockIdx.y;
+  const int top = prm[n * 3 + 0], left = prm[n * 3 + 1], flip = prm[n * 3 + 2];
+  const uint8_t* src = in + ((long long)n * C + c) * Hi * Wi;
+  uint8_t* dst = out + ((long long)n * C + c) * R * R;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < R * R; p += gridDim.x * blockDim.x) {
+    const int y = p / R, x = p - y * R;
+    const int xs = (flip ? R - 1 - x : x) + left - pad_left, ys = y + top - pad_top;
+    dst[p] = (xs >= 0 && xs < Wi && ys >= 0 && ys < Hi) ? src[ys * Wi + xs] : (uint8_t)0;
+  }
+}
+
 // spatially constant parents -> bf16 planar (N, C/8, HW, 8)
 __global__ void parents_plane_kernel(const float* __restrict__ pa, long long sstride, long long cstride,
                                      bf16* __restrict__ out, int N, int ctx, int C8, int HW, long long ns, int drop_from,
@@ -226,6 +242,18 @@ static inline int glue_grid(long long work) {
   long long g = (work + 255) / 256;
   if (g > 148LL * 16) g = 148LL * 16;
   return g < 1 ? 1 : (int)g;
+}
+
+extern "C" int cg_augment_u8(const uint8_t* in, uint8_t* out, const int32_t* params, int32_t N, int32_t C, int32_t Hi,
+                             int32_t Wi, int32_t R, int32_t pad_top, int32_t pad_left, void* stream) {
+  CG_ARCH_GUARD();
+  CG_REQUIRE(in != nullptr && out != nullptr && params != nullptr && in != out, "cg_augment_u8: null / aliased buffers");
+  CG_REQUIRE(N > 0 && C > 0 && Hi > 0 && Wi > 0 && R > 0 && pad_top >= 0 && pad_left >= 0, "cg_augment_u8: bad shape");
+  CG_REQUIRE(Hi + 2 * pad_top >= R && Wi + 2 * pad_left >= R, "cg_augment_u8: padded image smaller than the crop");
+  dim3 grid(cg_ceil_div((int64_t)R * R, 256 * 4), C, N);
+  augment_u8_kernel<<<grid, 256, 0, cg_stream(stream)>>>(in, out, params, C, Hi, Wi, R, pad_top, pad_left);
+  CG_LAUNCH_CHECK("cg_augment_u8");
+  return CG_OK;
 }
 
 extern "C" int cg_parents_plane(const float* pa, int64_t sample_stride, int64_t chan_stride, void* out, int32_t N,

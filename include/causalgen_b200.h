@@ -274,6 +274,11 @@ int cg_cf_combine_bwd(const float* x, const float* rec_loc, const float* rec_sca
  * ------------------------------------------------------------------------------------- */
 /* uint8 (N,C,H,W) -> fp32 NCHW (x-127.5)/127.5 */
 int cg_normalise_u8(const uint8_t* x8, float* x, int64_t n, void* stream);
+/* on-device train-time augmentation of a uint8 NCHW batch (src/datasets.py:107-118,281-286): torchvision
+ * RandomCrop(size=R, padding=[pad_left, pad_top], fill=0) followed by RandomHorizontalFlip; params = int32 (N,3) device
+ * array of (top, left, flip) per sample, top in [0, Hi + 2*pad_top - R], left in [0, Wi + 2*pad_left - R] */
+int cg_augment_u8(const uint8_t* in, uint8_t* out, const int32_t* params, int32_t N, int32_t C, int32_t Hi, int32_t Wi,
+                  int32_t R, int32_t pad_top, int32_t pad_left, void* stream);
 /* parents (N,ctx,R,R) fp32 [sampled at pixel (0,0)] or (N,ctx) -> bf16 planar (N, ctx16/8, H, W, 8), spatially
  * constant, zero padded channels; channels >= drop_from multiplied by drop_scale (conditioning dropout,
  * src/vae.py:244-247).  This is the materialised parents[..., :res, :res] of src/vae.py:241 at bf16. */

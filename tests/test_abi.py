@@ -42,8 +42,8 @@ def test_struct_layouts_match_the_header_sizes():
     nc = lib.cg_conv_nchunk(9 * 4, 16)
     assert nc == 16
     assert lib.cg_packed_weight_bytes(9 * 4, 16) == 9 * 4 * 16 * 32
-    assert lib.cg_conv_nchunk(9 * 2, 224) == 112          # two chunks of 112 output channels (<= 128 per CTA)
-    assert lib.cg_conv_nchunk(9 * 2, 128) == 128
+    assert lib.cg_conv_nchunk(9 * 2, 224) == 64           # four chunks of <= 64 output channels per CTA
+    assert lib.cg_conv_nchunk(9 * 2, 128) == 64
     # a huge-K first conv of a Block (posterior, 272 -> 32 channels, 3x3): no operand ring needed -> one chunk of 32
     assert lib.cg_conv_nchunk_ex(9 * 17, 32, 0) == 32 and lib.cg_conv_nchunk_ex(9 * 17, 32, 1) == 16
     assert lib.cg_packed_weight_bytes_nc(9 * 17, 32, 32) == 9 * 17 * 32 * 32

@@ -266,3 +266,85 @@ def test_vae_preprocess_matches_reference_functions():
     with pytest.raises(KeyError):
         vae_preprocess(a, {"mri_seq": pa["mri_seq"], "brain_volume": pa["brain_volume"], "ventricle_volume": pa["sex"],
                            "sex": pa["sex"], "thickness": pa["age"]})
+
+
+def test_checkpoint_wire_format_round_trips_through_torch_and_the_reference():
+    """src/trainer.py:154-168 / src/main.py:74-90: our checkpoint loads into real torch AdamW / LambdaLR objects (what the
+    reference does on resume), a checkpoint written from the REFERENCE's own model + optimizer loads into a Trainer, and
+    the file survives torch.save / torch.load.  Runs trace-only (no kernels) in a subprocess."""
+    code = r'''
+import os, sys, tempfile
+os.environ["CAUSALGEN_B200_TRACE_ONLY"] = "1"
+sys.path.insert(0, os.path.join(%r, "causal-gen_b200")); sys.path.insert(0, os.path.join(%r, "oracle"))
+import torch, hvae_oracle as O
+import causalgen_b200._lib as L
+class Fake:
+    def __init__(self, real): self.real = real
+    def __getattr__(self, n):
+        if n in ("cg_conv_nchunk", "cg_conv_nchunk_ex", "cg_packed_weight_bytes", "cg_packed_weight_bytes_nc", "cg_version",
+                 "cg_last_error"): return getattr(self.real, n)
+        return lambda *a: 0
+L._lib = Fake(L.load())
+from causalgen_b200 import HVAE, checkpoint as CK
+from causalgen_b200.trainer import Trainer
+from causalgen_b200.presets import make_args
+cfg = make_args("morphomnist")
+tr = Trainer(HVAE(cfg), 2, lr=1e-3, wd=0.01, lr_warmup_steps=100, use_graph=False)
+g = torch.Generator().manual_seed(0)
+tr.m.copy_(torch.randn(tr.m.shape, generator=g)); tr.v.copy_(torch.rand(tr.v.shape, generator=g))
+tr.ema.copy_(torch.randn(tr.ema.shape, generator=g)); tr.state[0] = 37; tr.state[1] = 37; tr.steps_done = 37
+with tempfile.TemporaryDirectory() as d:
+    path = os.path.join(d, "checkpoint.pt")
+    CK.save(path, tr, hparams={"lr": 1e-3, "hps": "morphomnist"}, epoch=3, best_loss=1.25)
+    ck = torch.load(path, weights_only=False)
+assert set(ck) >= {"epoch", "step", "best_loss", "model_state_dict", "ema_model_state_dict", "optimizer_state_dict",
+                   "scheduler_state_dict", "hparams"}
+assert list(ck["model_state_dict"]) == list(ck["ema_model_state_dict"]) == [k for k, _ in tr.model.named_parameters()]
+# the reference's resume path: fresh model / AdamW / LambdaLR, load_state_dict of each (src/main.py:74-79)
+m2 = HVAE(cfg); m2.load_state_dict(ck["model_state_dict"])
+opt = torch.optim.AdamW(m2.parameters(), lr=1e-3, weight_decay=0.01, betas=(0.9, 0.9))
+opt.load_state_dict(ck["optimizer_state_dict"])
+assert abs(opt.param_groups[0]["lr"] - 0.37e-3) < 1e-12      # lr of optimizer.step() number 38 under the warm-up
+sch = torch.optim.lr_scheduler.LambdaLR(opt, lr_lambda=lambda it: 1.0 if it > 100 else it / 100)
+sch.load_state_dict(ck["scheduler_state_dict"])
+assert sch.last_epoch == 37 and abs(sch.get_last_lr()[0] - 0.37e-3) < 1e-12
+names = [k for k, _ in m2.named_parameters()]
+mv = tr._views(tr.m)
+for i, p in enumerate(m2.parameters()):
+    if names[i] in mv:
+        assert torch.equal(opt.state[p]["exp_avg"], mv[names[i]]) and float(opt.state[p]["step"]) == 37.0
+    else:
+        assert p not in opt.state          # last block's z_feat_proj: never used, no Adam state in the reference either
+# and back into a fresh trainer
+tr2 = Trainer(HVAE(cfg), 2, lr=1e-3, wd=0.01, lr_warmup_steps=100, use_graph=False)
+CK.from_checkpoint(tr2, ck)
+assert torch.equal(tr2.m, tr.m) and torch.equal(tr2.v, tr.v) and torch.equal(tr2.ema, tr.ema) and torch.equal(tr2.flat_p, tr.flat_p)
+assert tr2.state.tolist() == [37, 37, 0, 0] and tr2.steps_done == 37
+CK.from_checkpoint(tr2, ck, mode="reference")   # src/main.py:80-86: constant lr, fresh EMA counter
+assert tr2.state.tolist() == [37, 0, 0, 0] and tr2.hp["warmup"] == 0
+# a checkpoint produced by the reference's own objects (staged reference, when present)
+sys.path.insert(0, os.path.join(%r, "oracle"))
+import ref_runner as R
+if R.available():
+    st = R.RefTrainStep("morphomnist", "cpu")
+    x8, pa, _ = O.synthetic_batch(O.make_cfg("morphomnist"), 2, seed=1)
+    for _ in range(2): st(x8, pa)
+    ref_ck = {"epoch": 1, "step": 2, "best_loss": 3.0, "model_state_dict": st.model.state_dict(),
+              "ema_model_state_dict": st.ema.ema_model.state_dict(), "optimizer_state_dict": st.opt.state_dict(),
+              "scheduler_state_dict": st.sched.state_dict(), "hparams": {"lr": 1e-3}}
+    tr3 = Trainer(HVAE(cfg), 2, lr=1e-3, wd=0.01, lr_warmup_steps=100, use_graph=False)
+    CK.from_checkpoint(tr3, ref_ck)
+    m3 = tr3._views(tr3.m)
+    ref_named = dict(st.model.named_parameters())
+    n_checked = 0
+    for k, p in ref_named.items():
+        if p in st.opt.state:
+            assert torch.equal(m3[k], st.opt.state[p]["exp_avg"]), k
+            n_checked += 1
+    assert n_checked > 100 and tr3.state.tolist()[:2] == [2, 2]
+    assert all(torch.equal(dict(tr3.model.named_parameters())[k], v) for k, v in st.model.state_dict().items())
+    print("REF_CKPT_OK")
+print("CKPT_OK")
+''' % (ROOT, ROOT, ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "CKPT_OK" in r.stdout, r.stderr[-3000:]
