@@ -32,7 +32,8 @@ class ConvArgs(C.Structure):
     _fields_ = [("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("ksize", C.c_int32), ("act", C.c_int32),
                 ("nsrc", C.c_int32), ("nseg", C.c_int32), ("cout", C.c_int32),
                 ("src", Src * CG_MAX_SRC), ("seg", Seg * CG_MAX_SEG),
-                ("wpack", C.c_void_p), ("bias", C.c_void_p), ("bias_n", C.c_int32), ("nc", C.c_int32)]
+                ("wpack", C.c_void_p), ("bias", C.c_void_p), ("bias_n", C.c_int32), ("nc", C.c_int32),
+                ("fold", C.c_int32), ("_pad2", C.c_int32)]
 
 
 class PackDesc(C.Structure):
@@ -40,7 +41,7 @@ class PackDesc(C.Structure):
                 ("transpose", C.c_int32), ("taps", C.c_int32), ("n_pad", C.c_int32), ("nc", C.c_int32),
                 ("n_off", C.c_int32), ("n_log", C.c_int32), ("nsrc", C.c_int32),
                 ("src_c", C.c_int32 * CG_MAX_SRC), ("src_log", C.c_int32 * CG_MAX_SRC),
-                ("src_off", C.c_int32 * CG_MAX_SRC)]
+                ("src_off", C.c_int32 * CG_MAX_SRC), ("fold", C.c_int32)]
 
 
 class WgradArgs(C.Structure):
@@ -57,7 +58,7 @@ class LatentArgs(C.Structure):
                 ("log_t", C.c_float),
                 ("z_bf16", C.c_void_p), ("z_ns", C.c_int64), ("z_f32", C.c_void_p), ("eps_out", C.c_void_p),
                 ("kl_out", C.c_void_p), ("N", C.c_int32), ("HW", C.c_int32), ("zdim", C.c_int32),
-                ("mode", C.c_int32)]
+                ("mode", C.c_int32), ("kl_ch", C.c_void_p)]
 
 
 class LatentBwdArgs(C.Structure):
@@ -66,7 +67,8 @@ class LatentBwdArgs(C.Structure):
                 ("dz", C.c_void_p), ("dz_ns", C.c_int64), ("g_kl", C.c_float),
                 ("dq", C.c_void_p), ("dq_ns", C.c_int64), ("dp", C.c_void_p), ("dp_ns", C.c_int64),
                 ("N", C.c_int32), ("HW", C.c_int32), ("zdim", C.c_int32), ("mode", C.c_int32),
-                ("g_kl_dev", C.c_void_p), ("log_t", C.c_float), ("_pad", C.c_int32)]
+                ("g_kl_dev", C.c_void_p), ("log_t", C.c_float), ("_pad", C.c_int32),
+                ("kl_gate", C.c_void_p)]
 
 
 class DGaussArgs(C.Structure):
@@ -93,6 +95,7 @@ _SIGNATURES = {
     "cg_conv2d": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "cg_conv_nchunk": (C.c_int32, [C.c_int32, C.c_int32]),
     "cg_conv_nchunk_ex": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32]),
+    "cg_conv_fold_ok": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32]),
     "cg_packed_weight_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "cg_packed_weight_bytes_nc": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "cg_pack_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
@@ -110,6 +113,7 @@ _SIGNATURES = {
                         [C.c_int32, C.c_void_p]),
     "cg_latent_fwd": (C.c_int, [C.POINTER(LatentArgs), C.c_void_p]),
     "cg_latent_bwd": (C.c_int, [C.POINTER(LatentBwdArgs), C.c_void_p]),
+    "cg_free_bits": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "cg_latent_mix": (C.c_int, [C.c_void_p] * 6 + [C.c_int64, C.c_float, C.c_float, C.c_int32, C.c_void_p]),
     "cg_dgauss_nll_fwd": (C.c_int, [C.POINTER(DGaussArgs), C.c_void_p]),
     "cg_dgauss_nll_bwd": (C.c_int, [C.POINTER(DGaussArgs), C.c_void_p]),

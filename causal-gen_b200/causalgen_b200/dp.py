@@ -41,6 +41,14 @@ def reduce_gradients_(flat_grad: torch.Tensor) -> float:
     return 1.0 / world
 
 
+def all_reduce_sum_(t: torch.Tensor) -> torch.Tensor:
+    """in-place SUM all-reduce of a small statistics tensor (kl_free_bits per-channel KL sums)"""
+    world, _ = world_info()
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
 def rank_noise_seed(base_seed: int, rank: int) -> int:
     """rank-disjoint Philox key so shards draw independent eps (SURVEY 8e caveat 2)"""
     return (base_seed * 0x9E3779B97F4A7C15 + (rank << 48)) % (1 << 64)

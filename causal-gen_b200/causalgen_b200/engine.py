@@ -61,6 +61,19 @@ class Marker:
         pass
 
 
+class HostOp:
+    """A host-side step inside a program (a torch.distributed collective between two kernels): issued in order on the
+    main lane like a launch.  Programs that hold one are not captured into CUDA graphs."""
+    side = False
+    name = "host_op"
+
+    def __init__(self, what, fn):
+        self.what, self.fn, self.lane, self.algo_bytes = what, fn, 0, 0
+
+    def __call__(self, stream):
+        self.fn(stream)
+
+
 class Program:
     """Recorded launch sequence.  Dependencies are expressed structurally: launches on lane 0 (main stream) and on
     lane 1 (auxiliary stream) are each in order; ``fork()`` makes lane 1 wait for everything issued on lane 0 so far,
@@ -374,6 +387,7 @@ class Engine:
     def _decoder_fwd(self, prog: Program, N, pa: Dict[int, View], pa_sto: Dict[int, View], acts: Optional[Dict[int, View]],
                      given: Optional[Sequence[bool]] = None, want_z: bool = False, want_stats: bool = False,
                      explicit_eps: bool = True, kl_rows: Optional[torch.Tensor] = None,
+                     kl_ch: Optional[torch.Tensor] = None,
                      z_views: Optional[Sequence[View]] = None) -> Rec:
         """reference Decoder.forward (src/vae.py:222-301).  `given[i]` marks stochastic block i whose latent is
         supplied by the caller (forward_latents); other stochastic blocks sample q (acts given) or p.
@@ -474,6 +488,8 @@ class Engine:
                         la.z_f32 = zo.data_ptr()
                     if kl_rows is not None and r.mode == 0:
                         la.kl_out = kl_rows[ksto].data_ptr()
+                        if kl_ch is not None:  # kl_free_bits statistics (src/vae.py:443-449)
+                            la.kl_ch = kl_ch[ksto].data_ptr()
                     la.N, la.HW, la.zdim, la.mode = N, res * res, zd, r.mode
                     if want_stats:
                         D.stats_out[ksto] = (r.qstat, r.pstat)
@@ -562,7 +578,7 @@ class Engine:
 
     def _decoder_bwd(self, prog: Program, D: Rec, dh_final: View, N, g_kl: float, acts_grad: Dict[int, View],
                      explicit_eps: bool, dz_extra: Optional[Dict[int, List[View]]] = None,
-                     dz_out: Optional[Dict[int, View]] = None):
+                     dz_out: Optional[Dict[int, View]] = None, kl_gate: Optional[torch.Tensor] = None):
         """Backward of _decoder_fwd.  `dz_extra[k]`: further gradients wrt the latent of stochastic block k (other decoder
         passes of the same program consumed it: counterfactual training).  `dz_out`: for passes whose latents were GIVEN
         (mode 3) the gradient wrt latent k is handed back here instead of going through a latent kernel."""
@@ -611,6 +627,8 @@ class Engine:
             lb.dz, lb.dz_ns, lb.g_kl = dz.ptr, dz.ns, g_kl
             lb.dp, lb.dp_ns = DP.ptr, DP.ns
             lb.N, lb.HW, lb.zdim, lb.mode = N, res * res, zd, r.mode
+            if kl_gate is not None and r.mode == 0:
+                lb.kl_gate = kl_gate[r.ksto].data_ptr()
             if r.mode != 3:
                 prog.add(L.Launch("cg_latent_bwd", C.byref(lb))).keep = (lb, dz, DP, dq)
                 D.latent_bwd_args.append(lb)
@@ -761,9 +779,16 @@ class Engine:
         prog.nll = torch.zeros(N, device=self.device, dtype=torch.float32)
         prog.out3 = torch.zeros(3, device=self.device, dtype=torch.float32)
         prog.zero = [prog.kl_rows, prog.nll]
+        fb = float(self.model.free_bits)
+        prog.kl_ch = prog.kl_gate = None
+        if fb > 0:  # src/vae.py:443-449: the floor acts on per-channel batch means, so the forward also collects those
+            prog.kl_ch = torch.zeros(max(nsto, 1), 16, device=self.device, dtype=torch.float32)
+            prog.kl_gate = torch.zeros(max(nsto, 1), 16, device=self.device, dtype=torch.float32)
+            prog.kl_fb_row = torch.zeros(N, device=self.device, dtype=torch.float32)
+            prog.zero.append(prog.kl_ch)
         e = self._encoder_fwd(prog, io.x, N)
         D = self._decoder_fwd(prog, N, io.pa[0], io.pa_sto[0], e.acts, explicit_eps=explicit_eps,
-                              kl_rows=prog.kl_rows)
+                              kl_rows=prog.kl_rows, kl_ch=prog.kl_ch)
         k = 0
         for r in D.blocks:
             r.pa = io.pa[0][r.st.res]
@@ -777,8 +802,21 @@ class Engine:
         prog.lik = la
         prog.add(L.Launch("cg_dmol_loss_fwd" if self.dmol else "cg_dgauss_nll_fwd", C.byref(la)))
         npix = float(self.C * self.R * self.R)
-        prog.fin = prog.call("cg_elbo_finalize", prog.nll.data_ptr(), prog.kl_rows.data_ptr(), prog.out3.data_ptr(),
-                             N, max(nsto, 1), 1.0 / npix, 1.0, io.hyp.data_ptr())
+        if fb > 0:
+            # data parallel: the batch mean runs over the GLOBAL batch -- sum the 16 x nsto statistics over ranks before the
+            # max; a host-side collective, so such a program is not captured into a CUDA graph
+            from . import dp
+            world, _ = dp.world_info()
+            if world > 1:
+                prog.add(HostOp("allreduce_kl_ch", lambda s, t=prog.kl_ch: dp.all_reduce_sum_(t)))
+                prog.no_graph = True
+            prog.call("cg_free_bits", prog.kl_ch.data_ptr(), max(nsto, 1), fb, 1.0 / (N * world),
+                      prog.kl_gate.data_ptr(), prog.kl_fb_row.data_ptr(), N)
+            prog.fin = prog.call("cg_elbo_finalize", prog.nll.data_ptr(), prog.kl_fb_row.data_ptr(), prog.out3.data_ptr(),
+                                 N, 1, 1.0 / npix, 1.0, io.hyp.data_ptr())
+        else:
+            prog.fin = prog.call("cg_elbo_finalize", prog.nll.data_ptr(), prog.kl_rows.data_ptr(), prog.out3.data_ptr(),
+                                 N, max(nsto, 1), 1.0 / npix, 1.0, io.hyp.data_ptr())
         prog.n_fwd = len(prog.launches)
         if train:
             prog.beta_users = []
@@ -798,7 +836,9 @@ class Engine:
                     lb.db_co = self.g(lik.channel_coeffs.bias).data_ptr()
                 prog.add(L.Launch("cg_dgauss_nll_bwd", C.byref(lb))).keep = (lb, dh)
             acts_grad: Dict[int, View] = {}
-            self._decoder_bwd(prog, D, dh, N, 1.0 / (N * npix), acts_grad, explicit_eps)
+            # free bits: d kl / d KL[b,c,h,w] = gate[c] / (global batch) = gate[c] / N after the data-parallel 1/world that
+            # the optimiser applies to the summed bucket -- the same per-rank coefficient as without free bits
+            self._decoder_bwd(prog, D, dh, N, 1.0 / (N * npix), acts_grad, explicit_eps, kl_gate=prog.kl_gate)
             for lb in D.latent_bwd_args:  # g_kl = (1 / (N * npix)) * live beta
                 lb.g_kl_dev = io.hyp.data_ptr()
             self._encoder_bwd(prog, e, acts_grad, N)

@@ -193,8 +193,6 @@ class HVAE(nn.Module):
         return [(0, 1), (1, 0), (1, 1)][opt]
 
     def _run_elbo(self, x: Tensor, parents: Tensor, beta, eps, train: bool) -> Tensor:
-        if self.free_bits > 0:
-            raise NotImplementedError("kl_free_bits > 0 (src/vae.py:443-449) is not on the hot path (default 0)")
         eng = self.engine()
         N = x.shape[0]
         explicit = eps is not None

@@ -4,12 +4,21 @@ kernel of libcausalgen_b200.so."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
 import torch
 
 from . import _lib as L
+
+
+# Column-folded 3x3 convolutions (cg_conv_args.fold) are OFF by default: measured on B200 at batch 128 they are correct
+# (tests/test_kernels_gpu.py::test_conv_column_folded_matches_plain) and cut the tcgen05 operand reads to a third, but the
+# conv kernel is bound by its TMA box rate, not by the MMAs (profiles/r2o_conv_ablation.txt: loads-only skeleton 48.9 us,
+# nine-tap 83.8 us, folded 90.7 us for 64->16 @96^2): the folded tiling needs 1.17x more boxes.  CAUSALGEN_B200_FOLD=1
+# switches them on (A/B measurements, r <= 24 layers gain ~10 %).
+FOLD = os.environ.get("CAUSALGEN_B200_FOLD", "0") == "1"
 
 
 def round16(c: int) -> int:
@@ -147,7 +156,10 @@ class ConvLayer:
         self.ksize = 1 if self.taps == 1 else self.k
         dev = weight.device
         kt = self.taps * sum(self.src_pad) // 16
-        self.nc = lib.cg_conv_nchunk_ex(kt, self.cout_pad, int(fwd_operands))
+        # column-folded 3x3 (cg_conv_args.fold): wide input, narrow output -- the case bound by shared-memory operand reads
+        self.fold = int(FOLD and self.taps == 9 and sum(self.src_pad) >= 2 * self.cout_pad and
+                        lib.cg_conv_fold_ok(kt, self.cout_pad, int(fwd_operands)) == 1)
+        self.nc = self.cout_pad if self.fold else lib.cg_conv_nchunk_ex(kt, self.cout_pad, int(fwd_operands))
         nbytes = lib.cg_packed_weight_bytes_nc(kt, self.cout_pad, self.nc)
         if self.nc <= 0 or nbytes <= 0:
             raise RuntimeError(f"conv K={kt * 16} does not fit a resident weight slab")
@@ -156,6 +168,7 @@ class ConvLayer:
         d.w, d.out = weight.data_ptr(), self.wpack.data_ptr()
         d.cout_l, d.cin_l, d.k = self.cout_l, self.cin_l, self.k
         d.transpose, d.taps, d.n_pad, d.nc, d.n_off, d.n_log = 0, self.taps, self.cout_pad, self.nc, 0, self.cout_l
+        d.fold = self.fold
         d.nsrc = len(src_logical)
         for i in range(d.nsrc):
             d.src_c[i], d.src_log[i], d.src_off[i] = self.src_pad[i], self.src_logical[i], self.src_off[i]
@@ -163,14 +176,19 @@ class ConvLayer:
         # data-gradient packs (one per source that needs a gradient): K side = dY channels
         self.wpack_bwd: List[Optional[torch.Tensor]] = []
         self.nc_bwd: List[int] = []
+        self.fold_bwd: List[int] = []
         grad_srcs = [True] * len(src_logical) if grad_srcs is None else list(grad_srcs)
         ktb = self.taps * self.cout_pad // 16
         for i, need in enumerate(grad_srcs):
             if not need:
                 self.wpack_bwd.append(None)
                 self.nc_bwd.append(0)
+                self.fold_bwd.append(0)
                 continue
-            ncb = lib.cg_conv_nchunk_ex(ktb, self.src_pad[i], 1)
+            fb = int(FOLD and self.taps == 9 and self.cout_pad >= 2 * self.src_pad[i] and
+                     lib.cg_conv_fold_ok(ktb, self.src_pad[i], 1) == 1)
+            self.fold_bwd.append(fb)
+            ncb = self.src_pad[i] if fb else lib.cg_conv_nchunk_ex(ktb, self.src_pad[i], 1)
             nb = lib.cg_packed_weight_bytes_nc(ktb, self.src_pad[i], ncb)
             self.nc_bwd.append(ncb)
             buf = torch.zeros(nb, dtype=torch.uint8, device=dev)
@@ -180,6 +198,7 @@ class ConvLayer:
             b.transpose, b.taps, b.n_pad, b.nc = 1, self.taps, self.src_pad[i], ncb
             b.n_off, b.n_log, b.nsrc = self.src_off[i], self.src_logical[i], 1
             b.src_c[0], b.src_log[0], b.src_off[0] = self.cout_pad, self.cout_l, 0
+            b.fold = fb
             table.add(b)
             self.wpack_bwd.append(buf)
 
@@ -214,7 +233,7 @@ class ConvLayer:
         a.nsrc, a.cout = len(srcs), self.cout_pad
         self._fill_srcs(a.src, srcs)
         self._fill_segs(a, segs)
-        a.wpack, a.nc = self.wpack.data_ptr(), self.nc
+        a.wpack, a.nc, a.fold = self.wpack.data_ptr(), self.nc, self.fold
         if self.bias is not None:
             a.bias, a.bias_n = self.bias.data_ptr(), self.cout_l
         ln = L.Launch("cg_conv2d", C.byref(a))
@@ -231,7 +250,7 @@ class ConvLayer:
         a.nsrc, a.cout = 1, self.src_pad[i]
         self._fill_srcs(a.src, [dy])
         self._fill_segs(a, [seg])
-        a.wpack, a.nc = self.wpack_bwd[i].data_ptr(), self.nc_bwd[i]
+        a.wpack, a.nc, a.fold = self.wpack_bwd[i].data_ptr(), self.nc_bwd[i], self.fold_bwd[i]
         ln = L.Launch("cg_conv2d", C.byref(a))
         ln.keep = (a, dy, seg)
         ln.algo_bytes = 2 * N * H * W * (self.cout_l + self.src_logical[i])

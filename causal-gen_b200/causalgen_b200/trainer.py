@@ -92,7 +92,7 @@ class Trainer:
                     self.eps_out.append(t)
         self.x8 = torch.zeros(self.N, self.eng.C, self.eng.R, self.eng.R, dtype=torch.uint8, device=dev)
         self.loss_host = torch.zeros(3, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(3)
-        self.use_graph = use_graph and not TRACE_ONLY
+        self.use_graph = use_graph and not TRACE_ONLY and not getattr(self.prog, "no_graph", False)
         self.g_fb: Optional[torch.cuda.CUDAGraph] = None
         self.g_opt: Optional[torch.cuda.CUDAGraph] = None
         self.steps_done = 0        # micro-batches seen

@@ -152,6 +152,8 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const cg_latent_args a)
   __shared__ float s_eps[16][kLatPix + 1];
   __shared__ float s_z[16][kLatPix + 1];
   __shared__ float s_red[8];
+  __shared__ float s_ch[16];
+  if (threadIdx.x < 16) s_ch[threadIdx.x] = 0.f;
   const int n = blockIdx.y;
   const int hw0 = blockIdx.x * kLatPix;
   const int npx = min(kLatPix, a.HW - hw0);
@@ -188,7 +190,9 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const cg_latent_args a)
         z = q_loc + __expf(q_ls) * s_eps[c][px];
         // src/vae.py:14-25 (same term order)
         const float eq = __expf(q_ls), ep = __expf(p_ls), dm = q_loc - p_loc;
-        kl_acc += -0.5f + p_ls - q_ls + 0.5f * (eq * eq + dm * dm) / (ep * ep);
+        const float kl = -0.5f + p_ls - q_ls + 0.5f * (eq * eq + dm * dm) / (ep * ep);
+        kl_acc += kl;
+        if (a.kl_ch != nullptr) atomicAdd(&s_ch[c], kl);  // free-bits statistics (rare path): shared-memory atomics
       } else if (a.mode == 1) {
         z = p_loc + __expf(p_ls) * s_eps[c][px];
       } else {
@@ -209,6 +213,7 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const cg_latent_args a)
     for (int i = 0; i < 8; ++i) s += s_red[i];
     atomicAdd(a.kl_out + n, s);
   }
+  if (a.kl_ch != nullptr && a.mode == 0 && tid < 16) atomicAdd(a.kl_ch + tid, s_ch[tid]);
   if (a.z_f32 != nullptr) {
     for (int e = tid; e < zd * kLatPix; e += 256) {
       int c = e / kLatPix, px = e - c * kLatPix;
@@ -257,10 +262,11 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const cg_latent_bwd_arg
       if (a.mode == 0) {
         const float q_loc = a.q[pix * a.q_ld + c], q_ls = a.q[pix * a.q_ld + zd + c] + a.log_t;
         const float eq = __expf(q_ls), ivp = __expf(-2.0f * p_ls), dm = q_loc - p_loc;
-        g_qloc[k] = g_kl * dm * ivp + dz[k];
-        g_qls[k] = g_kl * (eq * eq * ivp - 1.0f) + dz[k] * eq * s_eps[c][px];
-        g_ploc[k] = -g_kl * dm * ivp;
-        g_pls[k] = g_kl * (1.0f - (eq * eq + dm * dm) * ivp);
+        const float gk = a.kl_gate != nullptr ? g_kl * __ldg(a.kl_gate + c) : g_kl;
+        g_qloc[k] = gk * dm * ivp + dz[k];
+        g_qls[k] = gk * (eq * eq * ivp - 1.0f) + dz[k] * eq * s_eps[c][px];
+        g_ploc[k] = -gk * dm * ivp;
+        g_pls[k] = gk * (1.0f - (eq * eq + dm * dm) * ivp);
       } else if (a.mode == 1) {
         g_ploc[k] = dz[k];
         g_pls[k] = dz[k] * __expf(p_ls) * s_eps[c][px];
@@ -286,6 +292,9 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const cg_latent_bwd_arg
 // the fp32 statistics rows, noise generated in registers, one 16-byte bf16 store, block-reduced KL.
 __global__ void __launch_bounds__(256) latent_fwd_stream_kernel(const cg_latent_args a) {
   __shared__ float s_red[8];
+  __shared__ float s_ch[16];
+  if (threadIdx.x < 16) s_ch[threadIdx.x] = 0.f;
+  float klc[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // this thread's KL per channel of its octet (free-bits statistics)
   const int n = blockIdx.y;
   const long long item = (long long)blockIdx.x * 256 + threadIdx.x;  // (pixel, octet) inside the sample
   const bool live = item < 2ll * a.HW;
@@ -312,7 +321,8 @@ __global__ void __launch_bounds__(256) latent_fwd_stream_kernel(const cg_latent_
         const float q_ls = qs[k] + a.log_t, p_ls = ps[k] + a.log_t;
         const float eq = __expf(q_ls), ep = __expf(p_ls), dm = ql[k] - pl[k];
         zv[k] = ql[k] + eq * e[k];
-        kl_acc += -0.5f + p_ls - q_ls + 0.5f * (eq * eq + dm * dm) / (ep * ep);  // src/vae.py:14-25
+        klc[k] = -0.5f + p_ls - q_ls + 0.5f * (eq * eq + dm * dm) / (ep * ep);  // src/vae.py:14-25
+        kl_acc += klc[k];
       }
     } else if (a.mode == 1) {
 #pragma unroll
@@ -337,6 +347,18 @@ __global__ void __launch_bounds__(256) latent_fwd_stream_kernel(const cg_latent_
       for (int i = 0; i < 8; ++i) s += s_red[i];
       atomicAdd(a.kl_out + n, s);
     }
+  }
+  if (a.kl_ch != nullptr && a.mode == 0) {  // kl_free_bits statistics: lanes of equal parity hold the same octet
+    __syncthreads();                         // s_ch zeroed
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float v = klc[k];
+#pragma unroll
+      for (int o = 16; o > 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) < 2) atomicAdd(&s_ch[(threadIdx.x & 1) * 8 + k], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) atomicAdd(a.kl_ch + threadIdx.x, s_ch[threadIdx.x]);
   }
 }
 
@@ -367,10 +389,11 @@ __global__ void __launch_bounds__(256) latent_bwd_stream_kernel(const cg_latent_
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float eq = __expf(qs[k] + a.log_t), ivp = __expf(-2.0f * (ps[k] + a.log_t)), dm = ql[k] - pl[k];
-      g_qloc[k] = g_kl * dm * ivp + dz[k];
-      g_qls[k] = g_kl * (eq * eq * ivp - 1.0f) + dz[k] * eq * e[k];
-      g_ploc[k] = -g_kl * dm * ivp;
-      g_pls[k] = g_kl * (1.0f - (eq * eq + dm * dm) * ivp);
+      const float gk = a.kl_gate != nullptr ? g_kl * __ldg(a.kl_gate + oc * 8 + k) : g_kl;
+      g_qloc[k] = gk * dm * ivp + dz[k];
+      g_qls[k] = gk * (eq * eq * ivp - 1.0f) + dz[k] * eq * e[k];
+      g_ploc[k] = -gk * dm * ivp;
+      g_pls[k] = gk * (1.0f - (eq * eq + dm * dm) * ivp);
     }
     bf16* q0 = reinterpret_cast<bf16*>(a.dq) + n * a.dq_ns + hw * 8;
     *reinterpret_cast<uint4*>(q0 + (long long)oc * a.HW * 8) = cg_pack8(g_qloc);
@@ -385,6 +408,29 @@ __global__ void __launch_bounds__(256) latent_bwd_stream_kernel(const cg_latent_
   bf16* p0 = reinterpret_cast<bf16*>(a.dp) + n * a.dp_ns + hw * 8;
   *reinterpret_cast<uint4*>(p0 + (long long)oc * a.HW * 8) = cg_pack8(g_ploc);
   *reinterpret_cast<uint4*>(p0 + (long long)(2 + oc) * a.HW * 8) = cg_pack8(g_pls);
+}
+
+// kl_free_bits (src/vae.py:443-449): one block; thread i = (stochastic block, latent channel)
+__global__ void free_bits_kernel(const float* __restrict__ kl_ch, int n, float fb, float inv_batch, float* __restrict__ gate,
+                                 float* __restrict__ kl_row, int N) {
+  __shared__ float s_part[32];
+  __shared__ float s_tot;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = kl_ch[i] * inv_batch;
+    gate[i] = v > fb ? 1.0f : 0.0f;
+    acc += fmaxf(fb, v);
+  }
+  acc = cg_warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += s_part[i];
+    s_tot = s;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) kl_row[i] = s_tot;
 }
 
 __global__ void latent_mix_kernel(const float* __restrict__ z, const float* __restrict__ q_loc,
@@ -532,6 +578,15 @@ extern "C" int cg_latent_bwd(const cg_latent_bwd_args* a, void* stream) {
   dim3 grid(cg_ceil_div(a->HW, kLatPix), a->N);
   latent_bwd_kernel<<<grid, 256, 0, cg_stream(stream)>>>(*a);
   CG_LAUNCH_CHECK("cg_latent_bwd");
+  return CG_OK;
+}
+
+extern "C" int cg_free_bits(const float* kl_ch, int32_t nblk, float free_bits, float inv_batch, float* gate, float* kl_row,
+                            int32_t N, void* stream) {
+  CG_ARCH_GUARD();
+  CG_REQUIRE(kl_ch != nullptr && gate != nullptr && kl_row != nullptr && nblk > 0 && N > 0, "cg_free_bits: null / empty");
+  free_bits_kernel<<<1, 256, 0, cg_stream(stream)>>>(kl_ch, nblk * 16, free_bits, inv_batch, gate, kl_row, N);
+  CG_LAUNCH_CHECK("cg_free_bits");
   return CG_OK;
 }
 

@@ -10,9 +10,13 @@ __global__ void pack_weights_kernel(const cg_pack_desc* __restrict__ descs) {
   const cg_pack_desc d = descs[blockIdx.y];
   int c16tot = 0;
   for (int s = 0; s < d.nsrc; ++s) c16tot += d.src_c[s] / 16;
-  const int ktot16 = c16tot * d.taps;
-  const int nc = d.nc;
-  const int nN = (d.n_pad + nc - 1) / nc;
+  // column-folded image (cg_pack_desc.fold): K-blocks are (channel block, kernel row), the GEMM-N axis carries the three
+  // kernel columns side by side: row kx*d.nc + n of chunk y = output channel y*d.nc + n, kernel column kx
+  const int fold = d.fold;
+  const int taps_k = fold ? 3 : d.taps;      // taps on the K axis
+  const int ktot16 = c16tot * taps_k;
+  const int nc = fold ? 3 * d.nc : d.nc;     // GEMM-N rows per chunk
+  const int nN = (d.n_pad + d.nc - 1) / d.nc;
   const long long total = (long long)nN * ktot16 * 2 * nc;  // 16-byte groups
   const int kk = d.k * d.k;
   uint4* out = reinterpret_cast<uint4*>(d.out);
@@ -23,9 +27,11 @@ __global__ void pack_weights_kernel(const cg_pack_desc* __restrict__ descs) {
     const int k8 = (int)((g / nc) & 1);
     const int kidx = (int)((g / (2 * nc)) % ktot16);
     const int y = (int)(g / ((long long)2 * nc * ktot16));
-    const int n = y * nc + n8 * 8 + ni;
-    int c16g = kidx / d.taps;
-    const int t = kidx - c16g * d.taps;
+    const int nrow = n8 * 8 + ni;
+    const int kx = fold ? nrow / d.nc : 0;
+    const int n = y * d.nc + (fold ? nrow - kx * d.nc : nrow);
+    int c16g = kidx / taps_k;
+    const int t = kidx - c16g * taps_k;
     int s = 0;
     while (s < d.nsrc - 1 && c16g >= d.src_c[s] / 16) {
       c16g -= d.src_c[s] / 16;
@@ -33,7 +39,8 @@ __global__ void pack_weights_kernel(const cg_pack_desc* __restrict__ descs) {
     }
     int kh = 0, kw = 0;
     if (d.k == 3) {
-      if (d.taps == 9) { kh = t / 3; kw = t % 3; } else { kh = 1; kw = 1; }
+      if (fold) { kh = t; kw = kx; }
+      else if (d.taps == 9) { kh = t / 3; kw = t % 3; } else { kh = 1; kw = 1; }
       if (d.transpose) { kh = 2 - kh; kw = 2 - kw; }
     }
     float f[8];

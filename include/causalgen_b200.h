@@ -91,6 +91,12 @@ typedef struct {
   const float* bias;   /* fp32 [bias_n] or NULL */
   int32_t bias_n;      /* valid bias entries (logical output channels); the rest is 0 */
   int32_t nc;          /* GEMM-N chunk the weights were packed for (cg_conv_nchunk_ex); 0 = cg_conv_nchunk(ktot16, cout) */
+  int32_t fold;        /* 1: the weights were packed with cg_pack_desc.fold = 1 ("column-folded" 3x3 conv, wide inputs and
+                          cout <= 32): the three kernel columns sit side by side on the GEMM-N axis (N = 3*cout), each input
+                          tile is multiplied once per kernel ROW (3 MMAs per K-block instead of 9) and the epilogue adds the
+                          three column partials of the left / same / right pixel.  Same result, a third of the shared-
+                          memory operand reads.  Requires ksize == 3 and nc == cout <= 32 */
+  int32_t _pad2;
 } cg_conv_args;
 
 /* y = conv(act(cat(src))) + bias, split/added per segment.  Also the data-gradient pass when
@@ -103,6 +109,9 @@ int32_t cg_conv_nchunk(int32_t ktot16, int32_t cout);
 /* same with a hint: want_e = 0 when no launch of this pack has fused epilogue operands (add / add2 / mul), so the chunk
  * need not leave shared memory for the operand ring (first convs of a Block: wide K, narrow N) */
 int32_t cg_conv_nchunk_ex(int32_t ktot16, int32_t cout, int32_t want_e);
+/* 1 when the 3x3 conv (ktot16 = 9 * sum(C)/16 K-blocks, cout padded output channels) can run column-folded
+ * (cg_conv_args.fold / cg_pack_desc.fold, nc = cout); want_e as above */
+int32_t cg_conv_fold_ok(int32_t ktot16, int32_t cout, int32_t want_e);
 /* bytes of the packed-weight image for a conv with `ktot16` K-blocks of 16 (= taps * sum(C)/16) */
 int64_t cg_packed_weight_bytes(int32_t ktot16, int32_t cout);
 int64_t cg_packed_weight_bytes_nc(int32_t ktot16, int32_t cout, int32_t nc);
@@ -121,6 +130,8 @@ typedef struct {
   int32_t src_c[CG_MAX_SRC];      /* padded channels per source (multiple of 16) */
   int32_t src_log[CG_MAX_SRC];    /* logical channels per source */
   int32_t src_off[CG_MAX_SRC];    /* first logical channel of the source on the K side */
+  int32_t fold;        /* 1: column-folded image for cg_conv_args.fold (k == 3, taps == 9, nc == n_pad <= 32):
+                          K-blocks are (channel block, kernel row), GEMM-N row kx*nc + n holds kernel column kx */
 } cg_pack_desc;
 
 /* pack `n` weight tensors in one launch; `descs_dev` is a device copy of the descriptors */
@@ -186,6 +197,8 @@ typedef struct {
   float* kl_out;          /* [N] accumulated, or NULL */
   int32_t N, HW, zdim;
   int32_t mode;           /* 0: z~q, KL(q||p)   1: z~p (prior sample)   2: z=p_loc (deterministic) */
+  float* kl_ch;           /* optional [zdim] accumulated: sum over (N,H,W) of the block's KL per latent CHANNEL -- the
+                             quantity kl_free_bits thresholds (src/vae.py:443-449), see cg_free_bits */
 } cg_latent_args;
 int cg_latent_fwd(const cg_latent_args* a, void* stream);
 
@@ -203,8 +216,18 @@ typedef struct {
                                  src/trainer.py:52-57): g_kl then carries 1 / (B * C*H*W) and *g_kl_dev the live beta */
   float log_t;                /* log temperature the forward added to both logscales (abduction with t, src/vae.py:176-190) */
   int32_t _pad;
+  const float* kl_gate;       /* optional [zdim] in {0,1}: kl_free_bits gate of this block's channels (cg_free_bits); the KL
+                                 gradient of a channel whose batch-mean KL sits below the free-bits floor is zero */
 } cg_latent_bwd_args;
 int cg_latent_bwd(const cg_latent_bwd_args* a, void* stream);
+
+/* kl_free_bits > 0 (src/vae.py:443-449): kl = sum_blocks sum_c max(free_bits, mean_batch sum_hw KL[b,c,h,w]).
+ *   kl_ch: [nblk*16] per-channel sums written by cg_latent_fwd (summed over the GLOBAL batch: all-reduce it first under
+ *   data parallelism); inv_batch = 1 / global batch.  Writes gate[nblk*16] (1 where the mean exceeds the
+ *   floor: those channels get a KL gradient) and fills kl_row[0..N) with the total, so that cg_elbo_finalize(kl = kl_row,
+ *   nblk = 1) yields the reference's kl / elbo. */
+int cg_free_bits(const float* kl_ch, int32_t nblk, float free_bits, float inv_batch, float* gate, float* kl_row, int32_t N,
+                 void* stream);
 
 /* mediator mixture r = alpha q + (1-alpha) p of HVAE.abduct (src/vae.py:485-513); all fp32 NCHW */
 int cg_latent_mix(const float* z, const float* q_loc, const float* q_ls, const float* p_loc,

@@ -35,7 +35,7 @@ def test_struct_layouts_match_the_header_sizes():
     from causalgen_b200 import _lib as L
     assert ctypes.sizeof(L.Src) == 24
     assert ctypes.sizeof(L.Seg) == 104
-    assert ctypes.sizeof(L.ConvArgs) == 32 + 3 * 24 + 4 * 104 + 24
+    assert ctypes.sizeof(L.ConvArgs) == 32 + 3 * 24 + 4 * 104 + 32
     assert ctypes.sizeof(L.PackDesc) % 8 == 0
     # weight-slab planner is pure host arithmetic and must be callable without a GPU
     lib = L.load()

@@ -82,6 +82,14 @@ for name, nsto, nconv_min in (("tiny_ukbb", 5, 60), ("tiny_morphomnist", 4, 80))
     assert "cg_conv2d_wgrad" not in fwd and fwd[-1] == "cg_elbo_finalize"
     zs = m.abduct(x, pa, t=0.9)
     assert len(zs) == nsto
+    # kl_free_bits > 0 (src/vae.py:443-449): statistics -> floor / gate kernel -> finalize over ONE row; gated backward
+    mf = HVAE(O.make_cfg(name, kl_free_bits=0.1))
+    out = mf(x, pa, beta=cfg.beta); out["elbo"].backward()
+    pf = mf.engine().programs[("elbo", 2, True, False)]
+    nf = [getattr(l, "name", "py") for l in pf.launches]
+    assert nf.count("cg_free_bits") == 1 and nf[pf.n_fwd - 1] == "cg_elbo_finalize" and nf[pf.n_fwd - 2] == "cg_free_bits"
+    assert pf.kl_ch.shape == (nsto, 16) and pf.kl_gate.shape == (nsto, 16)
+    assert sum(1 for lb in pf.D.latent_bwd_args if lb.kl_gate) == nsto and all(la.kl_ch for la in pf.D.latent_args if la.mode == 0)
     # lanes: every fork is joined again, pool (weight-gradient) launches never sit in the forward part
     kinds = [getattr(l, "kind", None) for l in prog.launches]
     assert kinds.count("fork") == kinds.count("join") and kinds.count("fork") >= nsto

@@ -125,6 +125,52 @@ def test_elbo_kl_and_gradients(name):
     assert not bad, f"{name} per-tensor grad outliers (name, rel, drift): {bad[:8]}"
 
 
+@pytest.mark.parametrize("name", ["tiny_ukbb", "tiny_morphomnist"])
+@pytest.mark.parametrize("explicit", [True, False])
+def test_free_bits_elbo_and_gradients(name, explicit):
+    """kl_free_bits > 0 (src/vae.py:443-449) against the oracle (pinned to the real reference by freebits_<name>.npz): the
+    per-channel batch-mean statistics (cg_latent_fwd kl_ch), the floor / gate (cg_free_bits) and the gated KL gradient
+    (cg_latent_bwd kl_gate).  explicit=False runs the Philox stream kernels (statistics only: the noise differs)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"freebits_{name}.npz"))
+    fb = float(g["free_bits"])
+    cfg, sd, model, x, pa, _ = build(name, kl_free_bits=fb)
+    pa_full = O.expand_parents(pa, cfg.input_res)
+    ref, sd32, tape = oracle_elbo(cfg, sd, x, pa_full, False)
+    np.testing.assert_allclose(ref["elbo"].item(), g["elbo"], rtol=2e-5)   # the oracle IS the reference here
+    T = f"freebits[{name},{'eps' if explicit else 'philox'}]"
+    model.zero_grad()
+    if explicit:
+        out = model(x.to(DEV), pa_full.to(DEV), beta=cfg.beta, eps=[e.to(DEV) for e in tape.drawn])
+    else:
+        out = model(x.to(DEV), pa_full.to(DEV), beta=cfg.beta)
+    out["elbo"].backward()
+    torch.cuda.synchronize()
+    prog = [p for k, p in model.engine().programs.items() if k[0] == "elbo"][-1]
+    ch = prog.kl_ch.flatten().cpu().numpy() / x.shape[0]
+    gate = prog.kl_gate.flatten().cpu().numpy()
+    if not explicit:
+        # different noise: the statistics must still be self-consistent (kl = sum max(fb, mean) / npix, gate = mean > fb)
+        npix = float(np.prod(x.shape[1:]))
+        np.testing.assert_allclose(out["kl"].item(), np.maximum(fb, ch).sum() / npix, rtol=1e-4)
+        assert ((ch > fb) == (gate > 0.5)).all()
+        return
+    parity_report(T, "per-channel mean KL max rel", float(np.max(np.abs(ch - g["kl_ch"]) / np.abs(g["kl_ch"]))), 1e-2)
+    np.testing.assert_allclose(ch, g["kl_ch"], rtol=1e-2)
+    assert ((g["kl_ch"] > fb) == (gate > 0.5)).all(), "free-bits gate differs from the reference"
+    for k in ("elbo", "nll", "kl"):
+        parity_report(T, f"{k} rel", abs(out[k].item() - ref[k].item()) / abs(ref[k].item()), 5e-3)
+        np.testing.assert_allclose(out[k].item(), ref[k].item(), rtol=5e-3, err_msg=f"{name} {k}")
+    named = dict(model.named_parameters())
+    num = den = 0.0
+    for k, p in sd32.items():
+        if p.grad is not None:
+            num += float((named[k].grad.cpu() - p.grad).pow(2).sum())
+            den += float(p.grad.pow(2).sum())
+    parity_report(T, "grad global rel-L2", (num / den) ** 0.5, 3.5e-2)
+    assert (num / den) ** 0.5 <= 3.5e-2
+
+
 def px_stats(a, b):
     d = (a - b).abs().flatten()
     return float(d.mean()), float(torch.quantile(d[:: max(1, d.numel() // 200000)], 0.99))

@@ -50,6 +50,27 @@ def test_elbo_and_grads_match_reference(name):
             np.testing.assert_allclose(sd[k[6:]].grad.reshape(-1)[:64].numpy(), g[k], rtol=2e-3, atol=1e-5)
 
 
+@pytest.mark.parametrize("name", ["tiny_ukbb", "tiny_morphomnist"])
+def test_free_bits_elbo_and_grads_match_reference(name):
+    """kl_free_bits > 0 (src/vae.py:443-449): floor = midpoint of the per-channel batch-mean KLs, so half of the channels are
+    gated (tests/golden/make_golden_freebits.py ran the real reference)."""
+    g = np.load(os.path.join(GOLD, f"freebits_{name}.npz"))
+    cfg, sd, x, pa, _ = setup(name)
+    cfg.kl_free_bits = float(g["free_bits"])
+    for p in sd.values():
+        p.requires_grad_(True)
+    out = O.hvae_forward(sd, cfg, x, pa, O.NoiseTape(seed=101), beta=cfg.beta)
+    for k in ("elbo", "nll", "kl"):
+        np.testing.assert_allclose(out[k].item(), g[k], rtol=2e-5)
+    out["elbo"].backward()
+    assert list(g["grad_names"]) == list(sd.keys())
+    mine = np.array([float(sd[n].grad.norm()) if sd[n].grad is not None else -1.0 for n in sd])
+    np.testing.assert_allclose(mine, g["grad_norm"], rtol=2e-3, atol=1e-6)
+    for k in g.files:
+        if k.startswith("grad::"):
+            np.testing.assert_allclose(sd[k[6:]].grad.reshape(-1)[:64].numpy(), g[k], rtol=2e-3, atol=1e-5)
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_counterfactual_path_matches_reference(name):
     g = np.load(os.path.join(GOLD, name + ".npz"))

@@ -3,7 +3,7 @@ usage: CAUSALGEN_B200_LIB=causal-gen_b200/causalgen_b200/libcausalgen_b200_tl.so
 Marks (ns relative to kernel entry of CTA (0,0)):
   conv : 32 entry | 33 prologue done | 34 weight slab landed | 35+2i tile i first A chunk ready | 36+2i tile i MMAs
          issued | 50+i epilogue of tile i done (warp 0) | 60 all warps done | 70+i accumulator free for tile i (MMA warp)
-         | 80+i accumulator of tile i complete (epilogue warp 0).  CG_TL_FIRST=k moves the tile window to tiles k.. of CTA 0
+         | 80+i accumulator of tile i complete (epilogue warp 0) | 90+4i producer starts tile i, 91+4i+c: its chunk c issued.  CG_TL_FIRST=k moves the tile window to tiles k.. of CTA 0
   wgrad: 1 entry | 0 prologue done | 2+2i tile i ready | 3+2i tile i MMAs issued | 20 accumulators complete
          | 21 flush done | 22 all warps done"""
 import ctypes as C, os, sys
@@ -48,7 +48,7 @@ for name, H, cins, cout, k, act, epi in CASES:
     dw = torch.zeros_like(w); db = torch.zeros_like(b)
     lw = layer.wgrad(views, x1, dw, db, N, H, H)
     print(name)
-    for tag, fn, base, keys in (("conv", ln, 32, [33, 34] + list(range(35, 47)) + list(range(50, 58)) + [60] + list(range(70, 76)) + list(range(80, 88))),
+    for tag, fn, base, keys in (("conv", ln, 32, [33, 34] + list(range(35, 47)) + list(range(50, 58)) + [60] + list(range(70, 76)) + list(range(80, 88)) + list(range(90, 114))),
                                 ("wgrad", lw, 1, [0] + list(range(2, 18)) + [20, 21, 22])):
         lib.cg_debug_timeline(None)
         for _ in range(3): fn(s())
