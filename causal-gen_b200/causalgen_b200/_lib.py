@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("CAUSALGEN_B200_LIB", os.path.join(_HERE, "libcausalge
 
 CG_MAX_SRC = 3
 CG_MAX_SEG = 4
-ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_LRELU = 0, 1, 2, 3
 BF16, F32 = 0, 1
 
 
@@ -41,7 +41,7 @@ class PackDesc(C.Structure):
                 ("transpose", C.c_int32), ("taps", C.c_int32), ("n_pad", C.c_int32), ("nc", C.c_int32),
                 ("n_off", C.c_int32), ("n_log", C.c_int32), ("nsrc", C.c_int32),
                 ("src_c", C.c_int32 * CG_MAX_SRC), ("src_log", C.c_int32 * CG_MAX_SRC),
-                ("src_off", C.c_int32 * CG_MAX_SRC), ("fold", C.c_int32)]
+                ("src_off", C.c_int32 * CG_MAX_SRC), ("fold", C.c_int32), ("n_scale", C.c_void_p)]
 
 
 class WgradArgs(C.Structure):
@@ -138,6 +138,14 @@ _SIGNATURES = {
     "cg_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 3 + [C.c_int64] * 3 + [C.c_void_p]),
     "cg_elbo_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float,
                                    C.c_void_p, C.c_void_p]),
+    "cg_bn_fold": (C.c_int, [C.c_void_p] * 4 + [C.c_float, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "cg_conv_direct_fwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 9 + [C.c_int64, C.c_void_p]),
+    "cg_pool_max_fwd": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 7 + [C.c_int64, C.c_int64, C.c_void_p]),
+    "cg_groupnorm_fwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int32, C.c_float, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p] +
+                         [C.c_int32] * 3 + [C.c_int64, C.c_int64, C.c_void_p]),
+    "cg_global_avgpool": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 3 + [C.c_int64, C.c_int32, C.c_void_p]),
+    "cg_linear": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p] + [C.c_int32] * 4 +
+                  [C.c_void_p]),
     "cg_sumsq": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "cg_optim_advance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32] +
                          [C.c_float] * 6 + [C.c_int32, C.c_void_p]),

@@ -140,7 +140,8 @@ class ConvLayer:
 
     def __init__(self, table: PackTable, weight: torch.Tensor, bias: Optional[torch.Tensor],
                  src_logical: Sequence[int], act: int, centre_only: bool = False,
-                 grad_srcs: Optional[Sequence[bool]] = None, fwd_operands: bool = True):
+                 grad_srcs: Optional[Sequence[bool]] = None, fwd_operands: bool = True,
+                 n_scale: Optional[torch.Tensor] = None):
         """fwd_operands=False: no forward launch of this layer fuses an epilogue operand (add / add2 / mul), so its
         GEMM-N chunk need not reserve shared memory for the operand ring (first convs of a Block: huge K, narrow N)"""
         lib = L.load()
@@ -169,6 +170,10 @@ class ConvLayer:
         d.cout_l, d.cin_l, d.k = self.cout_l, self.cin_l, self.k
         d.transpose, d.taps, d.n_pad, d.nc, d.n_off, d.n_log = 0, self.taps, self.cout_pad, self.nc, 0, self.cout_l
         d.fold = self.fold
+        self.n_scale = n_scale  # per-output-channel multiplier folded into the forward pack (eval-mode BatchNorm)
+        if n_scale is not None:
+            assert n_scale.dtype == torch.float32 and n_scale.numel() == self.cout_l
+            d.n_scale = n_scale.data_ptr()
         d.nsrc = len(src_logical)
         for i in range(d.nsrc):
             d.src_c[i], d.src_log[i], d.src_off[i] = self.src_pad[i], self.src_logical[i], self.src_off[i]

@@ -97,7 +97,7 @@ __device__ __forceinline__ float cg_dgelu(float x) {
   return fmaf(x, pdf, cdf);
 }
 __device__ __forceinline__ float cg_act(float x, int act) {
-  return act == CG_ACT_RELU ? fmaxf(x, 0.0f) : (act == CG_ACT_GELU ? cg_gelu(x) : x);
+  return act == CG_ACT_RELU ? fmaxf(x, 0.0f) : (act == CG_ACT_GELU ? cg_gelu(x) : (act == CG_ACT_LRELU ? (x > 0.0f ? x : 0.01f * x) : x));
 }
 __device__ __forceinline__ float cg_dact(float x, int act) {
   return act == CG_ACT_RELU ? (x > 0.0f ? 1.0f : 0.0f) : (act == CG_ACT_GELU ? cg_dgelu(x) : 1.0f);

@@ -33,7 +33,7 @@
 // TMEM allocation, bias, weight-slab request) overlaps the tail of the previous kernel in the stream.
 //
 // Warp roles: 0-7 epilogue (TMEM lane quarter = warp & 3, column half = warp >> 2), 8 MMA issuer (even tiles) + TMEM owner,
-//             9 TMA producer, 10-13 transform, 14 MMA issuer (odd tiles).
+//             9 TMA producer (even tiles), 10-13 transform, 14 MMA issuer (odd tiles), 15 TMA producer (odd tiles).
 #include <cuda.h>
 
 #include <cstdlib>
@@ -48,7 +48,8 @@ constexpr int kTmaWarp = 9;
 constexpr int kXfWarp0 = 10;
 constexpr int kXfWarps = 4;
 constexpr int kMmaWarp2 = kXfWarp0 + kXfWarps;        // second MMA issuer (tiles 1, 3, 5, ... of the CTA)
-constexpr int kThreads = (kMmaWarp2 + 1) * 32;        // 480
+constexpr int kTmaWarp2 = kMmaWarp2 + 1;              // second TMA producer (feeds ring 1 = the tiles of the second issuer)
+constexpr int kThreads = (kTmaWarp2 + 1) * 32;        // 512
 constexpr int kXfThreads = kXfWarps * 32;
 constexpr int kMaxStages = 32;  // A-ring depth is chosen per launch from the shared memory left over
 constexpr int kMinStages = 4;   //   after the resident weight slab (pick_nc guarantees this many)
@@ -391,21 +392,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         else if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
-  } else if (warp == kTmaWarp) {
-    // ------------------------------------------------------------------ TMA producer
-    if (elect_one()) {
-      for (int s = 0; s < P.a.nsrc; ++s) tma_prefetch_desc(&P.src_map[s]);
-      for (int k = 0; k < P.nE; ++k) tma_prefetch_desc(&P.e_map[k]);
-      uint32_t es = 0, ephase = 0, lt = 0;
-      uint32_t st0 = 0, st1 = 0, ph0 = 0, ph1 = 0;  // stage / phase inside ring 0 (even local tiles) and ring 1 (odd)
-      const uint32_t len0 = (uint32_t)P.nst0, len1 = (uint32_t)(nst - P.nst0);
-      const bool two = P.nst0 < nst;
+  } else if (warp == kTmaWarp || warp == kTmaWarp2) {
+    // ------------------------------------------------------------------ TMA producers
+    // TWO producer threads, one per A ring (producer w: local tiles w, w+2, ... -- the tiles issuer w consumes).  One thread
+    // issues a box every ~0.3 us (barrier poll + expect_tx + UTMALDG), which made the producer, not the TMA unit (0.22 us per
+    // box of this shape, tools/micro/tma_rate.cu) or HBM, the bound of the high-resolution layers (profiles/
+    // r2p_timeline_producer_marks.txt).  The epilogue-operand ring is walked in tile order by the epilogue, so with two
+    // producers its depth is even and producer w only ever owns the stages of parity w (it sees every phase of them).
+    const uint32_t pw = warp == kTmaWarp ? 0u : 1u;
+    const bool two = P.nst0 < nst;
+    if (elect_one() && (two || pw == 0)) {
+      if (pw == 0) {
+        for (int s = 0; s < P.a.nsrc; ++s) tma_prefetch_desc(&P.src_map[s]);
+        for (int k = 0; k < P.nE; ++k) tma_prefetch_desc(&P.e_map[k]);
+      }
+      const uint32_t rbase = (two && pw) ? (uint32_t)P.nst0 : 0u;
+      const uint32_t rlen = two ? (pw ? (uint32_t)(nst - P.nst0) : (uint32_t)P.nst0) : (uint32_t)nst;
+      const uint32_t lstep = two ? 2u : 1u;
+      uint32_t es = two ? pw : 0u, ephase = 0, lt = two ? pw : 0u, st = 0, ph = 0;
       const int halo_y = k3 ? 1 : 0, halo_x = (k3 && !fold) ? 1 : 0;
-      TileWalk walk(P, blockIdx.x, gridDim.x);
-      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++lt, walk.next()) {
+      const int first = blockIdx.x + (int)lt * (int)gridDim.x, tstep = (int)lstep * (int)gridDim.x;
+      TileWalk walk(P, first, tstep);
+      for (int tile = first; tile < P.ntiles; tile += tstep, lt += lstep, walk.next()) {
         const TileGeom g = walk.geom(P);
-        const uint32_t r = two ? (lt & 1u) : 0u, rbase = r ? (uint32_t)P.nst0 : 0u;
-        if (lt < 6) CG_TL(P.tl, 90 + 4 * lt);
+        if (pw == 0 && lt < 12) CG_TL(P.tl, 90 + 2 * lt);
         if (P.nE > 0) {
           mbar_wait(BAR(B_EEMPTY + es), ephase ^ 1u);
           mbar_expect_tx(BAR(B_EFULL + es), P.e_tx_bytes);
@@ -415,20 +425,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             if (P.flat) tma_load_3d(dst, &P.e_map[k], 0, g.n, oct, BAR(B_EFULL + es));
             else tma_load_4d(dst, &P.e_map[k], g.w0 * 8, g.h0, oct, g.n, BAR(B_EFULL + es));
           }
-          if (++es == nest) { es = 0; ephase ^= 1u; }
+          es += lstep;
+          if (es >= (uint32_t)nest) { es -= (uint32_t)nest; ephase ^= 1u; }
         }
         for (int c = 0; c < P.nchunks; ++c) {
           const Chunk ch = P.chunk[c];
-          const uint32_t stage = rbase + (r ? st1 : st0);
-          mbar_wait(BAR(B_AEMPTY + stage), (r ? ph1 : ph0) ^ 1u);
+          const uint32_t stage = rbase + st;
+          mbar_wait(BAR(B_AEMPTY + stage), ph ^ 1u);
           mbar_expect_tx(BAR(B_LANDED + stage), P.src_bytes[ch.src]);
           const uint32_t dst = cg_smem_u32(sA + stage * stage_bytes);
           if (P.flat) tma_load_3d(dst, &P.src_map[ch.src], 0, g.n, ch.oct0, BAR(B_LANDED + stage));
           else tma_load_4d(dst, &P.src_map[ch.src], (g.w0 - halo_x) * 8, g.h0 - halo_y, ch.oct0, g.n, BAR(B_LANDED + stage));
-          if (r) { if (++st1 == len1) { st1 = 0; ph1 ^= 1u; } }
-          else if (++st0 == len0) { st0 = 0; ph0 ^= 1u; }
-          if (lt < 6 && c < 3) CG_TL(P.tl, 91 + 4 * lt + c);
+          if (++st == rlen) { st = 0; ph ^= 1u; }
         }
+        if (pw == 0 && lt < 12) CG_TL(P.tl, 91 + 2 * lt);
       }
     }
   } else if (warp >= kXfWarp0 && warp < kMmaWarp2) {
@@ -529,6 +539,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             else pl.k_mul = k;
           }
         if (sg.dtype == CG_BF16 && pl.cnt == 16 && pl.k_add != -1 && pl.k_add2 != -1 && pl.k_mul != -1 &&
+            sg.out_act <= CG_ACT_GELU &&  // LeakyReLU (predictors) takes the generic path
             (pl.k_mul == -2 || sg.mul_act == CG_ACT_RELU) && !(pl.k_mul >= 0 && pl.k_add2 >= 0))
           pl.fast = (pl.k_mul >= 0 ? 1 : 0) | (pl.k_add >= 0 ? 2 : 0) | (pl.k_add2 >= 0 ? 4 : 0) |
                     (sg.out_act == CG_ACT_RELU ? 8 : 0) | (sg.out_act == CG_ACT_GELU ? 16 : 0) |
@@ -672,6 +683,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           } else if (pl.out_act == CG_ACT_GELU) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[h8 + i] = cg_gelu(v[h8 + i]);
+          } else if (pl.out_act == CG_ACT_LRELU) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[h8 + i] = v[h8 + i] > 0.f ? v[h8 + i] : 0.01f * v[h8 + i];
           }
           if (DUAL && pl.out2 != nullptr) {
             bf16* oc = reinterpret_cast<bf16*>(pl.out2) + n * pl.ns2 + (long long)(h8 >> 3) * P.HW8 + hw * 8;
@@ -963,6 +977,9 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
     }
     if (!one_issuer && kp.ntiles > gx && kp.nst >= 4) kp.nst0 = (kp.nst + 1) / 2;
   }
+  // two rings = two producers: each owns the operand-ring stages of its tile parity, so that ring's depth must be even
+  // (the launch keeps the shared-memory size computed above; an odd depth just leaves its last stage unused)
+  if (kp.nst0 < kp.nst && kp.nest > 0 && (kp.nest & 1)) kp.nest -= 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(gx, kp.nN);
   cfg.blockDim = dim3(kThreads);

@@ -54,6 +54,7 @@ __global__ void pack_weights_kernel(const cg_pack_desc* __restrict__ descs) {
         const int o = d.transpose ? kch : nch;
         const int i = d.transpose ? nch : kch;
         v = d.w[((long long)o * d.cin_l + i) * kk + kh * d.k + kw];
+        if (d.n_scale != nullptr && !d.transpose) v *= d.n_scale[o];  // folded eval-mode BatchNorm
       }
       f[ki] = v;
     }

@@ -33,7 +33,9 @@ typedef enum {
   CG_ERR_UNSUPPORTED = -4
 } cg_status;
 
-enum { CG_ACT_NONE = 0, CG_ACT_RELU = 1, CG_ACT_GELU = 2 };   /* nn.ReLU / nn.GELU(erf), src/vae.py:50,58 */
+enum { CG_ACT_NONE = 0, CG_ACT_RELU = 1, CG_ACT_GELU = 2,    /* nn.ReLU / nn.GELU(erf), src/vae.py:50,58 */
+       CG_ACT_LRELU = 3 };  /* nn.LeakyReLU(0.01) of the predictor CNN (src/pgm/layers.py:70): cg_seg.out_act and the predictor
+                               kernels only (no derivative / input pre-activation) */
 enum { CG_BF16 = 0, CG_F32 = 1 };
 
 int cg_version(void);
@@ -132,6 +134,8 @@ typedef struct {
   int32_t src_off[CG_MAX_SRC];    /* first logical channel of the source on the K side */
   int32_t fold;        /* 1: column-folded image for cg_conv_args.fold (k == 3, taps == 9, nc == n_pad <= 32):
                           K-blocks are (channel block, kernel row), GEMM-N row kx*nc + n holds kernel column kx */
+  const float* n_scale; /* optional fp32 [cout_l] multiplier per OUTPUT channel of w, applied while packing (forward packs
+                           only): eval-mode BatchNorm folded into the convolution, src/pgm/layers.py:72-92 */
 } cg_pack_desc;
 
 /* pack `n` weight tensors in one launch; `descs_dev` is a device copy of the descriptors */
@@ -350,6 +354,36 @@ int cg_optim_advance(int32_t* state, float* dyn, const float* gsumsq, const floa
 int cg_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, int64_t n,
                       const int32_t* state, const float* dyn, float beta1, float beta2, float eps,
                       float wd, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Anticausal predictors on counterfactual images (call site src/pgm/dscm.py:78-83), inference only:
+ * `CNN` (BatchNorm, src/pgm/layers.py:64-104) and GroupNorm ResNet-18 (src/pgm/resnet.py:9-239).  Their 3x3 / 1x1
+ * convolutions are cg_conv2d launches (BatchNorm folded through cg_pack_desc.n_scale + bias, LeakyReLU as out_act);
+ * stride-2 convolutions = stride-1 cg_conv2d + cg_pool_max_fwd(k = 1, stride = 2).
+ * ------------------------------------------------------------------------------------- */
+/* eval-mode nn.BatchNorm{1,2}d as an affine map: scale = gamma * rsqrt(var + eps), shift = beta - mean * scale */
+int cg_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale,
+               float* shift, int32_t C, void* stream);
+/* thin-input stem convolution (Cin <= 3, k <= 7, any stride / padding; src/pgm/layers.py:72, src/pgm/resnet.py:229-231):
+ * x fp32 NCHW, w fp32 OIHW, y bf16 planar (N, ceil(Cout/8), Ho, Wo, 8) = act(conv(x) * scale[c] + shift[c]); scale/shift
+ * optional (folded BatchNorm) */
+int cg_conv_direct_fwd(const float* x, const float* w, const float* scale, const float* shift, void* y, int32_t N,
+                       int32_t Cin, int32_t H, int32_t W, int32_t Cout, int32_t k, int32_t stride, int32_t pad, int32_t act,
+                       int64_t y_ns, void* stream);
+/* nn.MaxPool2d(k, stride, pad) on bf16 planar tensors (src/pgm/layers.py:75, src/pgm/resnet.py:98); k = 1: strided pick */
+int cg_pool_max_fwd(const void* x, void* y, int32_t N, int32_t C, int32_t H, int32_t W, int32_t k, int32_t stride, int32_t pad,
+                    int64_t x_ns, int64_t y_ns, void* stream);
+/* y = act(GroupNorm(groups, C)(x) [+ add]) on bf16 planar tensors (src/pgm/resnet.py:228, CustomBlock.forward :41-61);
+ * stats: fp32 scratch [N*C*2] (per-channel sum / sum of squares, written by the call) */
+int cg_groupnorm_fwd(const void* x, float* stats, const float* gamma, const float* beta, int32_t groups, float eps,
+                     const void* add, int64_t add_ns, int32_t act, void* y, int32_t N, int32_t C, int32_t HW, int64_t x_ns,
+                     int64_t y_ns, void* stream);
+/* x.mean(dim=(-2,-1)) of a bf16 planar tensor -> fp32 rows out[n*ld + c]  (src/pgm/layers.py:101, nn.AdaptiveAvgPool2d(1)) */
+int cg_global_avgpool(const void* x, float* out, int32_t N, int32_t C, int32_t HW, int64_t x_ns, int32_t ld, void* stream);
+/* out[n][m] = act((x[n] . w[m] + bias[m]) * scale[m] + shift[m]), fp32; bias / (scale, shift) optional
+ * (nn.Linear [+ BatchNorm1d + LeakyReLU], src/pgm/layers.py:94-99, src/pgm/resnet.py:233) */
+int cg_linear(const float* x, int32_t ldx, const float* w, const float* bias, const float* scale, const float* shift,
+              int32_t act, float* out, int32_t ldo, int32_t N, int32_t K, int32_t M, void* stream);
 
 #ifdef __cplusplus
 }
