@@ -447,10 +447,19 @@ class Engine:
                                              final_segs=[SegSpec(r.qstat, 0)])
             # ---- prior (src/vae.py:172-183)
             p_src = [h if self.q_corr else zs] + ([pa_sto[res]] if self.cond_prior else [])
-            r.pstat = View(torch.zeros(N, res, res, 2 * zd, device=self.device, dtype=torch.float32), 2 * zd)
+            # a block whose latent is GIVEN (forward_latents / the two decodes of a counterfactual) never reads p_loc /
+            # p_logscale (src/vae.py:274-279): the prior conv then stores its feature columns only -- the fp32
+            # statistics rows would be as many bytes again as the features at 96^2
+            dead_stats = (st.stochastic and acts is None and given is not None and ksto < len(given)
+                          and bool(given[ksto]) and not want_stats)
             r.pfeat = new_act(N, res, res, st.cin, self.device)
-            r.prior = self._block_fwd(prog, d.prior, p_src, N, res, res,
-                                      final_segs=[SegSpec(r.pstat, 0), SegSpec(r.pfeat, 2 * zd)])
+            if dead_stats:
+                r.pstat = View(torch.zeros(1, 1, 1, 2 * zd, device=self.device, dtype=torch.float32), 2 * zd)  # placeholder
+                segs = [SegSpec(r.pfeat, 2 * zd)]
+            else:
+                r.pstat = View(torch.zeros(N, res, res, 2 * zd, device=self.device, dtype=torch.float32), 2 * zd)
+                segs = [SegSpec(r.pstat, 0), SegSpec(r.pfeat, 2 * zd)]
+            r.prior = self._block_fwd(prog, d.prior, p_src, N, res, res, final_segs=segs)
             # ---- posterior + latent (src/vae.py:265-291)
             shared_z = (z_views is not None and st.stochastic and given is not None and ksto < len(given)
                         and bool(given[ksto]))
@@ -769,6 +778,28 @@ class Engine:
             io.pa_sto.append(planes_sto)
         return io
 
+    def dmol_mode(self) -> int:
+        """cg_dmol_predict mode of DmolNet.mask (src/dmol.py:164-190): soft 0 | hard 1 | 'top<k>' 10 + k"""
+        mask = getattr(self.model.likelihood, "mask", "soft")
+        if mask == "soft":
+            return 0
+        if mask == "hard":
+            return 1
+        if "top" in mask:
+            k = int(mask[-1])
+            if not 0 < k < 10:
+                raise ValueError("invalid top_k")  # src/dmol.py:180
+            return 10 + k
+        raise NotImplementedError(f"DmolNet.mask = {mask!r}")
+
+    def _dmol_mode_arg(self, prog: Program):
+        """mutable int32 launch argument, refreshed from DmolNet.mask whenever the program is fetched (HVAE._program)"""
+        m = C.c_int32(self.dmol_mode())
+        if not hasattr(prog, "dmol_modes"):
+            prog.dmol_modes = []
+        prog.dmol_modes.append(m)
+        return m
+
     def build_elbo(self, N: int, train: bool, explicit_eps: bool) -> Program:
         """HVAE.forward (src/vae.py:439-458) and, when `train`, its full backward"""
         prog = Program(f"elbo(N={N},train={train})")
@@ -878,7 +909,7 @@ class Engine:
             so = torch.zeros_like(xo)
             la = self._lik_args(D.h, None, N)
             if self.dmol:
-                prog.add(L.Launch("cg_dmol_predict", C.byref(la), 0, None, None, C.c_float(0.0), xo.data_ptr(),
+                prog.add(L.Launch("cg_dmol_predict", C.byref(la), self._dmol_mode_arg(prog), None, None, C.c_float(0.0), xo.data_ptr(),
                                   so.data_ptr()))
             else:
                 prog.add(L.Launch("cg_dgauss_sample", C.byref(la), xo.data_ptr(), so.data_ptr(), None, C.c_float(0.0)))
@@ -912,7 +943,7 @@ class Engine:
             so = torch.zeros_like(xo)
             la = self._lik_args(D.h, None, N)
             if self.dmol:
-                prog.add(L.Launch("cg_dmol_predict", C.byref(la), 0, None, None, C.c_float(0.0), xo.data_ptr(),
+                prog.add(L.Launch("cg_dmol_predict", C.byref(la), self._dmol_mode_arg(prog), None, None, C.c_float(0.0), xo.data_ptr(),
                                   so.data_ptr())).keep = (la, D)
             else:
                 prog.add(L.Launch("cg_dgauss_sample", C.byref(la), xo.data_ptr(), so.data_ptr(), None,

@@ -162,7 +162,10 @@ class HVAE(nn.Module):
                     eng.programs[key] = build()
             else:
                 eng.programs[key] = build()
-        return eng.programs[key]
+        prog = eng.programs[key]
+        for m in getattr(prog, "dmol_modes", ()):  # DmolNet.mask (src/dmol.py:226) is read at call time, like the reference
+            m.value = eng.dmol_mode()
+        return prog
 
     def _load_parents(self, prog, io, plist: Sequence[Tensor], training_drop: Optional[Tuple[float, float]] = None):
         for buf, pa in zip(io.pa_in, plist):

@@ -154,6 +154,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// (A try_wait with an explicit suspend-time hint -- ptxas lowers it to TRYWAIT + NANOSLEEP.SYNCS -- was measured neutral
+// for the conv pipeline, profiles/r2t_conv_microbench_trywait_hint.txt, so the plain polling form stays.)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   do {

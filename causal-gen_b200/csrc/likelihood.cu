@@ -564,6 +564,16 @@ __global__ void __launch_bounds__(256) dmol_predict_kernel(const cg_dmol_args a,
     float mx = hw_max(lg);
     float e = act ? __expf(lg - mx) : 0.f;
     sel = e / hw_sum(e);
+  } else if (mode > 10) {  // 'top<k>' (k = mode - 10): keep logits >= the k-th largest, renormalise  src/dmol.py:178-189
+    const float lg = act ? L.logit : -INFINITY;
+    int greater = 0;
+#pragma unroll
+    for (int j = 0; j < kMix; ++j) greater += __shfl_sync(0xffffffffu, lg, j, 16) > lg ? 1 : 0;
+    const bool keep = act && greater < mode - 10;   // "logit >= v[k-1]" of the descending sort, ties kept
+    const float lk = keep ? lg : -INFINITY;
+    const float mx = hw_max(lk);
+    const float e = keep ? __expf(lk - mx) : 0.f;
+    sel = e / hw_sum(e);
   } else {  // hard argmax (mode 1) or Gumbel argmax (mode 2)  src/dmol.py:128-131,175-177
     float score = L.logit;
     if (mode == 2) score -= __logf(-__logf(u_gumbel[pix * kMix + m]));
@@ -691,7 +701,8 @@ extern "C" int cg_dmol_predict(const cg_dmol_args* a, int32_t mode, const float*
                                float log_t, float* x_out, float* scale_out, void* stream) {
   CG_ARCH_GUARD();
   DMOL_CHECK(a, "cg_dmol_predict");
-  CG_REQUIRE(mode >= 0 && mode <= 2 && (mode != 2 || (u_gumbel && u_logistic)), "cg_dmol_predict: mode %d", mode);
+  CG_REQUIRE(((mode >= 0 && mode <= 2) || (mode > 10 && mode < 20)) && (mode != 2 || (u_gumbel && u_logistic)),
+             "cg_dmol_predict: mode %d", mode);
   DMOL_LAUNCH(dmol_predict_kernel, a, *a, mode, u_gumbel, u_logistic, log_t, x_out, scale_out);
   CG_LAUNCH_CHECK("cg_dmol_predict");
   return CG_OK;

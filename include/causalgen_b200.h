@@ -276,7 +276,8 @@ typedef struct {
 } cg_dmol_args;
 int cg_dmol_loss_fwd(const cg_dmol_args* a, void* stream);
 int cg_dmol_loss_bwd(const cg_dmol_args* a, void* stream);
-/* mode 0 soft mean, 1 hard (argmax) mean, 2 sample (u_gumbel (N,H,W,10), u_logistic (N,H,W,3)
+/* mode 0 soft mean, 1 hard (argmax) mean, 10+k 'top<k>' mean (the k most probable components, renormalised; src/dmol.py:
+ * 178-189), 2 sample (u_gumbel (N,H,W,10), u_logistic (N,H,W,3)
  * uniform(1e-5,1-1e-5) drawn by caller); outputs fp32 NCHW x (clamped) and scale */
 int cg_dmol_predict(const cg_dmol_args* a, int32_t mode, const float* u_gumbel,
                     const float* u_logistic, float log_t, float* x_out, float* scale_out,

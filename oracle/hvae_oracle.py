@@ -561,7 +561,7 @@ def likelihood_nll(sd, cfg, h, x):
 def likelihood_sample(sd, cfg, h, noise=None, return_loc=True, t=None):
     if cfg.x_like.endswith("dmol"):  # src/dmol.py:234-245
         l = dmolnet_params(sd, h)
-        x, s = dmol_mean(l) if return_loc else dmol_sample(l, noise, t=t)
+        x, s = dmol_mean(l, mask=getattr(cfg, "dmol_mask", "soft")) if return_loc else dmol_sample(l, noise, t=t)  # DmolNet.mask
         return x.clamp(-1, 1).permute(0, 3, 1, 2), s.permute(0, 3, 1, 2)
     return dgauss_sample(sd, cfg, h, noise, return_loc, t)
 

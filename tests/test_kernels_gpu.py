@@ -653,7 +653,7 @@ def test_dmol_against_oracle_functions():
     assert_close(db.cpu(), bc.grad, 2e-3, "dmol db")
     # predictions
     xo, so = torch.zeros_like(x), torch.zeros_like(x)
-    for mode, mask in ((0, "soft"), (1, "hard")):
+    for mode, mask in ((0, "soft"), (1, "hard"), (13, "top3"), (11, "top1"), (19, "top9")):
         L.check(lib.cg_dmol_predict(C.byref(a), mode, None, None, 0.0, xo.data_ptr(), so.data_ptr(), stream()))
         m, s = O.dmol_mean(l.detach(), mask=mask)
         torch.cuda.synchronize()
