@@ -41,12 +41,14 @@ __device__ void load_heads(Heads& s, const cg_dgauss_args& a) {
 // per-pixel head evaluation: raw loc / raw logscale / raw coeff for C channels
 template <int C>
 __device__ __forceinline__ void eval_heads(const Heads& s, const bf16* hrow, long long oct_stride, int Cw, float* loc,
-                                           float* ls, float* co, bool rgb) {
+                                           float* ls, float* co, bool rgb, uint4* stash = nullptr) {
 #pragma unroll
   for (int c = 0; c < C; ++c) { loc[c] = s.b_loc[c]; ls[c] = s.b_ls[c]; co[c] = s.b_co[c]; }
   for (int k8 = 0; k8 < Cw; k8 += 8) {
     float h[8];
-    cg_unpack8(*reinterpret_cast<const uint4*>(hrow + (k8 >> 3) * oct_stride), h);
+    const uint4 raw = *reinterpret_cast<const uint4*>(hrow + (k8 >> 3) * oct_stride);
+    if (stash != nullptr) stash[k8 >> 3] = raw;  // the backward kernel keeps the pixel's features for the weight gradient
+    cg_unpack8(raw, h);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
 #pragma unroll
@@ -131,6 +133,12 @@ __global__ void __launch_bounds__(256) dgauss_bwd_kernel(const cg_dgauss_args a,
                                                          const float* __restrict__ dscale_out) {
   __shared__ Heads s;
   __shared__ float s_d[256][3 * C + 1];  // per pixel: dloc[C], dls[C], dco[C]
+  // the block's features, bf16, one row per pixel with a 16-byte pad (pitch 2*Cw + 16 B: eight lanes of a 16-byte store hit
+  // eight different bank groups); dynamic, allocated when Cw <= 32 (every shipped config), else the weight gradient
+  // re-reads h from global memory
+  extern __shared__ __align__(16) uint8_t s_hraw[];
+  const int h_pitch = 2 * a.Cw + 16;
+  const bool h_smem = a.Cw <= 32;
   load_heads(s, a);
   const int n = blockIdx.y;
   const int hw = blockIdx.x * blockDim.x + threadIdx.x;
@@ -143,7 +151,8 @@ __global__ void __launch_bounds__(256) dgauss_bwd_kernel(const cg_dgauss_args a,
     const bf16* hrow = reinterpret_cast<const bf16*>(a.h) + n * a.h_ns + (long long)hw * 8;
     float loc[C], ls[C], co[C], x[C];
     bool live[C];
-    eval_heads<C>(s, hrow, (long long)a.HW * 8, a.Cw, loc, ls, co, C == 3);
+    eval_heads<C>(s, hrow, (long long)a.HW * 8, a.Cw, loc, ls, co, C == 3,
+                  h_smem ? reinterpret_cast<uint4*>(s_hraw + threadIdx.x * h_pitch) : nullptr);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       x[c] = MODE == 0 ? a.x[((long long)n * C + c) * a.HW + hw] : 0.f;
@@ -220,8 +229,10 @@ __global__ void __launch_bounds__(256) dgauss_bwd_kernel(const cg_dgauss_args a,
   }
   __syncthreads();
   // head weight gradients: dW[head][c][k] = sum_pixels d[head][c](p) * h[p][k].  The block's 256 pixels are split into
-  // kParts slices so that all 256 threads work (the first version left 3/4 of the block idle in a 256-step loop: 282 us,
-  // 0.32 of HBM, ncu profiles/r2m_ncu_full_summary.txt); slice partials meet in shared memory, one atomic per entry.
+  // kParts slices so that all 256 threads work, and h comes from the shared-memory copy made above: the first versions
+  // re-read it from global memory with one 2-byte load per (pixel, output) -- 60 % of the kernel's stall samples, 282 /
+  // 275 us = 0.32 of HBM (ncu profiles/r2m_ncu_full_summary.txt, r2w_*); slice partials meet in shared memory, one atomic
+  // per entry.
   const int nhead = (C == 3) ? 3 : 2;
   const int per = C * a.Cw;
   const int nout = nhead * per;                       // 64 (C=1, Cw=32) ... 144 (C=3, Cw=16)
@@ -237,7 +248,13 @@ __global__ void __launch_bounds__(256) dgauss_bwd_kernel(const cg_dgauss_args a,
                        ((long long)(k >> 3) * a.HW + blockIdx.x * blockDim.x) * 8 + (k & 7);
       float acc = 0.f;
       const int p1 = min(npx, (part + 1) * slice);
-      for (int p = part * slice; p < p1; ++p) acc += s_d[p][head * C + c] * __bfloat162float(hb[(long long)p * 8]);
+      if (h_smem) {
+        const uint8_t* hs = s_hraw + 2 * k;
+        for (int p = part * slice; p < p1; ++p)
+          acc += s_d[p][head * C + c] * __bfloat162float(*reinterpret_cast<const bf16*>(hs + p * h_pitch));
+      } else {
+        for (int p = part * slice; p < p1; ++p) acc += s_d[p][head * C + c] * __bfloat162float(hb[(long long)p * 8]);
+      }
       s_part[part][o] = acc;
     }
   }
@@ -637,8 +654,9 @@ extern "C" int cg_dgauss_nll_bwd(const cg_dgauss_args* a, void* stream) {
   DGAUSS_CHECK(a, "cg_dgauss_nll_bwd");
   CG_REQUIRE(a->dh != nullptr && a->dh_ns % 8 == 0, "cg_dgauss_nll_bwd: dh");
   dim3 grid(cg_ceil_div(a->HW, 256), a->N);
-  if (a->C == 1) dgauss_bwd_kernel<1, 0><<<grid, 256, 0, cg_stream(stream)>>>(*a, nullptr, nullptr);
-  else dgauss_bwd_kernel<3, 0><<<grid, 256, 0, cg_stream(stream)>>>(*a, nullptr, nullptr);
+  const int hs_bytes0 = a->Cw <= 32 ? 256 * (2 * a->Cw + 16) : 0;  // shared-memory copy of the block's features
+  if (a->C == 1) dgauss_bwd_kernel<1, 0><<<grid, 256, hs_bytes0, cg_stream(stream)>>>(*a, nullptr, nullptr);
+  else dgauss_bwd_kernel<3, 0><<<grid, 256, hs_bytes0, cg_stream(stream)>>>(*a, nullptr, nullptr);
   CG_LAUNCH_CHECK("cg_dgauss_nll_bwd");
   return CG_OK;
 }
@@ -649,8 +667,9 @@ extern "C" int cg_dgauss_sample_bwd(const cg_dgauss_args* a, const float* dx_out
   CG_REQUIRE(a->dh != nullptr && a->dh_ns % 8 == 0, "cg_dgauss_sample_bwd: dh");
   CG_REQUIRE(dx_out != nullptr || dscale_out != nullptr, "cg_dgauss_sample_bwd: no upstream gradient");
   dim3 grid(cg_ceil_div(a->HW, 256), a->N);
-  if (a->C == 1) dgauss_bwd_kernel<1, 1><<<grid, 256, 0, cg_stream(stream)>>>(*a, dx_out, dscale_out);
-  else dgauss_bwd_kernel<3, 1><<<grid, 256, 0, cg_stream(stream)>>>(*a, dx_out, dscale_out);
+  const int hs_bytes1 = a->Cw <= 32 ? 256 * (2 * a->Cw + 16) : 0;  // shared-memory copy of the block's features
+  if (a->C == 1) dgauss_bwd_kernel<1, 1><<<grid, 256, hs_bytes1, cg_stream(stream)>>>(*a, dx_out, dscale_out);
+  else dgauss_bwd_kernel<3, 1><<<grid, 256, hs_bytes1, cg_stream(stream)>>>(*a, dx_out, dscale_out);
   CG_LAUNCH_CHECK("cg_dgauss_sample_bwd");
   return CG_OK;
 }
