@@ -52,7 +52,11 @@ def main():
         out["elbo"].backward()
         named = dict(full.named_parameters())
         name_of = {id(p): k for k, p in model.named_parameters()}
-        want = torch.cat([named[name_of[id(p)]].grad.flatten() for p in tr.params if p.requires_grad])
+        # tr.grad covers the trainable parameters in flat-buffer order (engine.ordered_params): frozen ones and the last
+        # block's never-used z_feat_proj (grad None in the reference too) sit behind it
+        live = [p for p in tr.params if p.requires_grad and named[name_of[id(p)]].grad is not None]
+        assert sum(p.numel() for p in live) == tr.grad.numel()
+        want = torch.cat([named[name_of[id(p)]].grad.flatten() for p in live])
         got = tr.grad / world
         d = float((got - want).norm() / want.norm())
         print(f"PARITY reduced_bucket_vs_full_batch_relL2 {d:.3e} 2e-3")
