@@ -58,7 +58,7 @@ class LatentArgs(C.Structure):
                 ("log_t", C.c_float),
                 ("z_bf16", C.c_void_p), ("z_ns", C.c_int64), ("z_f32", C.c_void_p), ("eps_out", C.c_void_p),
                 ("kl_out", C.c_void_p), ("N", C.c_int32), ("HW", C.c_int32), ("zdim", C.c_int32),
-                ("mode", C.c_int32), ("kl_ch", C.c_void_p)]
+                ("mode", C.c_int32), ("kl_ch", C.c_void_p), ("kl_elem", C.c_void_p)]
 
 
 class LatentBwdArgs(C.Structure):

@@ -388,7 +388,7 @@ class Engine:
                      given: Optional[Sequence[bool]] = None, want_z: bool = False, want_stats: bool = False,
                      explicit_eps: bool = True, kl_rows: Optional[torch.Tensor] = None,
                      kl_ch: Optional[torch.Tensor] = None,
-                     z_views: Optional[Sequence[View]] = None) -> Rec:
+                     z_views: Optional[Sequence[View]] = None, want_kl_elem: bool = False) -> Rec:
         """reference Decoder.forward (src/vae.py:222-301).  `given[i]` marks stochastic block i whose latent is
         supplied by the caller (forward_latents); other stochastic blocks sample q (acts given) or p.
         `z_views[i]`: the given latent already lives on the device as a bf16 planar view (another decoder pass of
@@ -402,6 +402,7 @@ class Engine:
         D.z_in = {}
         D.z_out = {}
         D.stats_out = {}
+        D.kl_elem = {}
         bias_of = {r: p for (r, _), p in zip(dec.bias_res, dec.bias)}
         w1 = dec.plan[0].cin
         h = new_act(N, 1, 1, w1, self.device)
@@ -499,6 +500,10 @@ class Engine:
                         la.kl_out = kl_rows[ksto].data_ptr()
                         if kl_ch is not None:  # kl_free_bits statistics (src/vae.py:443-449)
                             la.kl_ch = kl_ch[ksto].data_ptr()
+                    if want_kl_elem and r.mode == 0:  # stats[i]["kl"] of the stand-alone Decoder call (src/vae.py:268)
+                        ke = torch.zeros(N, zd, res, res, device=self.device, dtype=torch.float32)
+                        D.kl_elem[ksto] = ke
+                        la.kl_elem = ke.data_ptr()
                     la.N, la.HW, la.zdim, la.mode = N, res * res, zd, r.mode
                     if want_stats:
                         D.stats_out[ksto] = (r.qstat, r.pstat)
@@ -917,6 +922,66 @@ class Engine:
             prog.x_out.append(xo)
             prog.scale_out.append(so)
             prog.lik_args.append(la)
+        return prog
+
+    # ---- stand-alone calls of the sub-modules (reference surface: model.encoder(x), model.decoder(...),
+    # model.likelihood.nll / .sample).  fp32 NCHW at the boundary like the reference; inference only.
+    def _nchw_out(self, prog: Program, v: View, N, C_, res) -> torch.Tensor:
+        out = torch.zeros(N, C_, res, res, device=self.device, dtype=torch.float32)
+        prog.call("cg_planar_to_nchw_f32", v.ptr, out.data_ptr(), N, C_, res * res, v.ns)
+        return out
+
+    def _nchw_in(self, prog: Program, N, C_, res):
+        buf = torch.zeros(N, C_, res, res, device=self.device, dtype=torch.float32)
+        v = new_act(N, res, res, C_, self.device)
+        prog.call("cg_nchw_f32_to_planar", buf.data_ptr(), v.ptr, N, C_, res * res, v.ns)
+        return buf, v
+
+    def build_encoder_call(self, N: int) -> Program:
+        """Encoder.forward (src/vae.py:124-134): {resolution: activations}"""
+        prog = Program(f"encoder(N={N})")
+        prog.x = torch.zeros(N, self.C, self.R, self.R, device=self.device, dtype=torch.float32)
+        e = self._encoder_fwd(prog, prog.x, N)
+        prog.acts_out = {res: self._nchw_out(prog, v, N, v.logical, res) for res, v in e.acts.items()}
+        prog.e = e
+        return prog
+
+    def build_decoder_call(self, N: int, has_acts: bool, given: Optional[Sequence[bool]]) -> Program:
+        """Decoder.forward (src/vae.py:222-301) on caller-supplied encoder activations / latents"""
+        prog = Program(f"decoder(N={N},acts={has_acts})")
+        io = self._inputs(prog, N, with_x=False, n_pa=1)
+        prog.io = io
+        prog.acts_in, acts = {}, None
+        if has_acts:
+            acts = {}
+            for res, st in {st.res_out: st for st in self.model.encoder.plan}.items():  # last block of each resolution
+                prog.acts_in[res], acts[res] = self._nchw_in(prog, N, st.cout, res)
+        prog.D = self._decoder_fwd(prog, N, io.pa[0], io.pa_sto[0], acts, given=given, want_z=has_acts, want_stats=True,
+                                   want_kl_elem=has_acts)
+        prog.h_out = self._nchw_out(prog, prog.D.h, N, self.args.widths[0], self.R)
+        return prog
+
+    def build_likelihood_call(self, N: int, kind: str) -> Program:
+        """DGaussNet / DmolNet .nll(h, x) and .sample(h) (src/vae.py:352-422, src/dmol.py:228-245) on caller-supplied h"""
+        prog = Program(f"likelihood.{kind}(N={N})")
+        prog.h_in, hv = self._nchw_in(prog, N, self.args.widths[0], self.R)
+        if kind == "nll":
+            prog.x = torch.zeros(N, self.C, self.R, self.R, device=self.device, dtype=torch.float32)
+            prog.nll = torch.zeros(N, device=self.device, dtype=torch.float32)
+            la = self._lik_args(hv, prog.x, N)
+            la.nll = prog.nll.data_ptr()
+            prog.add(L.Launch("cg_dmol_loss_fwd" if self.dmol else "cg_dgauss_nll_fwd", C.byref(la))).keep = (la, hv)
+            prog.zero = [prog.nll]
+        else:
+            prog.x_out = torch.zeros(N, self.C, self.R, self.R, device=self.device, dtype=torch.float32)
+            prog.scale_out = torch.zeros_like(prog.x_out)
+            la = self._lik_args(hv, None, N)
+            if self.dmol:
+                prog.add(L.Launch("cg_dmol_predict", C.byref(la), self._dmol_mode_arg(prog), None, None, C.c_float(0.0),
+                                  prog.x_out.data_ptr(), prog.scale_out.data_ptr())).keep = (la, hv)
+            else:
+                prog.add(L.Launch("cg_dgauss_sample", C.byref(la), prog.x_out.data_ptr(), prog.scale_out.data_ptr(), None,
+                                  C.c_float(0.0))).keep = (la, hv)
         return prog
 
     def build_counterfactual(self, N: int, train: bool = False) -> Program:

@@ -132,12 +132,24 @@ class HVAE(nn.Module):
         self._hp = {k: getattr(args, k) for k in keys}
         self.__dict__["_engine"] = None
         self.__dict__["_noise_calls"] = 0
+        self._bind_children()
 
     # ------------------------------------------------------------------ engine plumbing
     def __getstate__(self):  # copy.deepcopy (EMA, src/utils.py:125) must not drag device programs along
         st = self.__dict__.copy()
         st["_engine"] = None
         return st
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._bind_children()   # a deep copy (EMA, src/utils.py:125) binds its own sub-modules
+
+    def _bind_children(self):
+        """encoder / decoder / likelihood are callable like the reference's sub-modules (src/vae.py:440-442); they reach the
+        engine through a weak back-reference that is re-bound whenever an engine is (re)built, e.g. after copy.deepcopy"""
+        import weakref
+        for child in (self.encoder, self.decoder, self.likelihood):
+            child.__dict__["_owner"] = weakref.ref(self)
 
     def _engine_or_none(self) -> Optional[Engine]:
         return self.__dict__.get("_engine")
@@ -148,6 +160,7 @@ class HVAE(nn.Module):
             from types import SimpleNamespace
             eng = Engine(self, SimpleNamespace(**self._hp))
             self.__dict__["_engine"] = eng
+            self._bind_children()
         return eng
 
     def _seed(self) -> int:
@@ -276,6 +289,68 @@ class HVAE(nn.Module):
                                       float(t) if t is not None else 1.0, int(t is not None), s), "cg_latent_mix")
             out.append(z)
         return out
+
+    # ------------------------------------------------------------------ stand-alone sub-module calls (inference)
+    @torch.no_grad()
+    def _call_encoder(self, x: Tensor) -> Dict[int, Tensor]:
+        eng = self.engine()
+        N = x.shape[0]
+        prog = self._program(("encoder", N), lambda: eng.build_encoder_call(N))
+        prog.x.copy_(x)
+        eng.pack_weights()
+        prog.run()
+        return {res: t.clone() for res, t in prog.acts_out.items()}
+
+    @torch.no_grad()
+    def _call_decoder(self, parents: Tensor, x: Optional[Dict[int, Tensor]] = None, t: Optional[float] = None,
+                      abduct: bool = False, latents: Sequence[Optional[Tensor]] = (),
+                      eps: Optional[Sequence[Tensor]] = None):
+        """Decoder.forward (src/vae.py:222-301) -> (h, stats) with the reference's stats layout"""
+        eng = self.engine()
+        N = parents.shape[0]
+        nsto = sum(1 for d in eng.dec_layers if d.st.stochastic)
+        has_acts = x is not None
+        given = None if has_acts else tuple(i < len(latents) and latents[i] is not None for i in range(nsto))
+        prog = self._program(("decoder", N, has_acts, given), lambda: eng.build_decoder_call(N, has_acts, given))
+        drop = self.drop_cond() if (self.training and self.cond_prior and self.decoder.is_drop_cond) else None
+        self._load_parents(prog, prog.io, [parents], drop)
+        if has_acts:
+            for res, buf in prog.acts_in.items():
+                buf.copy_(x[res])
+        D = prog.D
+        for k, buf in D.z_in.items():
+            buf.copy_(latents[k])
+        log_t = math.log(t) if t is not None else 0.0
+        self._set_noise(D, eps if eps is not None else self._host_eps(D), log_t)
+        eng.pack_weights()
+        prog.run()
+        stats = []
+        for k in range(nsto):
+            if has_acts:  # src/vae.py:265-281
+                st = {"kl": D.kl_elem[k].clone()}
+                if abduct:
+                    z = D.z_out[k].clone()
+                    if self.cond_prior:
+                        qstat, _ = D.stats_out[k]
+                        z = {"z": z, "q_loc": self._stat_nchw(qstat, 0, 0.0), "q_logscale": self._stat_nchw(qstat, 16, log_t)}
+                    st["z"] = z
+                stats.append(st)
+            elif abduct and self.cond_prior and k >= len(latents):  # src/vae.py:284-290: only the out-of-range branch records
+                _, pstat = D.stats_out[k]
+                stats.append({"z": {"p_loc": self._stat_nchw(pstat, 0, 0.0), "p_logscale": self._stat_nchw(pstat, 16, log_t)}})
+        return prog.h_out.clone(), stats
+
+    @torch.no_grad()
+    def _call_likelihood(self, kind: str, h: Tensor, x: Optional[Tensor] = None):
+        eng = self.engine()
+        N = h.shape[0]
+        prog = self._program(("likelihood", kind, N), lambda: eng.build_likelihood_call(N, kind))
+        prog.h_in.copy_(h)
+        if kind == "nll":
+            prog.x.copy_(x)
+            prog.nll.zero_()
+        prog.run()
+        return prog.nll.clone() if kind == "nll" else (prog.x_out.clone(), prog.scale_out.clone())
 
     def _stat_nchw(self, stat, c0: int, add: float) -> Tensor:
         N, H, W, _ = stat.t.shape

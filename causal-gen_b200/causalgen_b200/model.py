@@ -28,6 +28,25 @@ class _Slot(nn.Module):
         raise RuntimeError("causalgen_b200 modules are parameter containers; call the HVAE surface instead")
 
 
+def _owner_of(child: nn.Module):
+    """the HVAE a sub-module belongs to (weak back-reference bound by HVAE._bind_children)"""
+    ref = child.__dict__.get("_owner")
+    owner = ref() if ref is not None else None
+    if owner is None or not any(c is child for c in (owner.encoder, owner.decoder, owner.likelihood)):
+        raise RuntimeError("this sub-module is not bound to a causalgen_b200.HVAE (stand-alone or copied container): call it "
+                           "through its HVAE, e.g. model.encoder(x) after model.engine()")
+    return owner
+
+
+class _Bound(nn.Module):
+    """sub-module with a weak back-reference to its HVAE; the reference is not part of its pickled / copied state"""
+
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st.pop("_owner", None)
+        return st
+
+
 class Block(nn.Module):
     def __init__(self, cin, cmid, cout, ksize=3, residual=True, down=None, light=False):
         super().__init__()
@@ -51,7 +70,7 @@ class Block(nn.Module):
         return [m for m in self.conv if isinstance(m, nn.Conv2d)]
 
 
-class Encoder(nn.Module):
+class Encoder(_Bound):
     def __init__(self, args):
         super().__init__()
         self.plan = encoder_plan(args)
@@ -61,6 +80,10 @@ class Encoder(nn.Module):
         for b in blocks:
             b.convs[-1].weight.data *= math.sqrt(1.0 / len(blocks))
         self.blocks = nn.ModuleList(blocks)
+
+    def forward(self, x):
+        """reference Encoder.forward (src/vae.py:124-134): {resolution: activations}, fp32 NCHW; inference only"""
+        return _owner_of(self)._call_encoder(x)
 
 
 class DecoderBlock(nn.Module):
@@ -81,7 +104,7 @@ class DecoderBlock(nn.Module):
         self.conv = Block(st.cin, st.cmid, st.cout, ksize=st.ksize, light=light)
 
 
-class Decoder(nn.Module):
+class Decoder(_Bound):
     def __init__(self, args):
         super().__init__()
         self.plan = decoder_plan(args)
@@ -97,8 +120,13 @@ class Decoder(nn.Module):
         self.cond_prior = args.cond_prior
         self.is_drop_cond = "morphomnist" in args.hps  # src/vae.py:220
 
+    def forward(self, parents, x=None, t=None, abduct=False, latents=(), eps=None):
+        """reference Decoder.forward (src/vae.py:222-301) -> (h, stats); fp32 NCHW; inference only.  `eps` (extension):
+        explicit N(0,1) draws, one per sampled block in block order, instead of torch's device RNG"""
+        return _owner_of(self)._call_decoder(parents, x=x, t=t, abduct=abduct, latents=latents, eps=eps)
 
-class DGaussNet(nn.Module):
+
+class DGaussNet(_Bound):
     """discretised-Gaussian likelihood head (reference src/vae.py:322-350)"""
 
     def __init__(self, args):
@@ -121,8 +149,18 @@ class DGaussNet(nn.Module):
             elif cov != "diag":
                 raise NotImplementedError(f"{args.x_like} not implemented.")
 
+    def nll(self, h, x):
+        """src/vae.py:371-411: per-sample negative log-likelihood (N,) of x under the heads applied to h; inference only"""
+        return _owner_of(self)._call_likelihood("nll", h, x)
 
-class DmolNet(nn.Module):
+    def sample(self, h, return_loc: bool = True, t=None):
+        """src/vae.py:413-422 with return_loc=True (every reference caller): (clamped loc, scale)"""
+        if not return_loc:
+            raise NotImplementedError("return_loc=False hits a reference bug (t passed as x, src/vae.py:419 vs :352)")
+        return _owner_of(self)._call_likelihood("sample", h)
+
+
+class DmolNet(_Bound):
     """mixture-of-logistics head (reference src/dmol.py:218-226): 1x1 conv to 10 * 10 channels"""
 
     def __init__(self, args):
@@ -131,3 +169,13 @@ class DmolNet(nn.Module):
         self.num_mixtures = 10
         self.conv = nn.Conv2d(self.width, 100, kernel_size=1, stride=1, padding=0)
         self.mask = "soft"
+
+    def nll(self, h, x):
+        """src/dmol.py:228-229: per-sample mixture-of-logistics loss (N,); inference only"""
+        return _owner_of(self)._call_likelihood("nll", h, x)
+
+    def sample(self, h, return_loc: bool = True, t=None):
+        """src/dmol.py:231-245 with return_loc=True: mean under `self.mask` (soft / hard / top-k) and scale"""
+        if not return_loc:
+            raise NotImplementedError("stochastic DMoL samples need caller-drawn uniforms: use cg_dmol_predict mode 2")
+        return _owner_of(self)._call_likelihood("sample", h)

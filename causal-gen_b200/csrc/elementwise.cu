@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const cg_latent_args a)
   __shared__ float s_z[16][kLatPix + 1];
   __shared__ float s_red[8];
   __shared__ float s_ch[16];
+  __shared__ float s_kl[16][kLatPix + 1];
   if (threadIdx.x < 16) s_ch[threadIdx.x] = 0.f;
   const int n = blockIdx.y;
   const int hw0 = blockIdx.x * kLatPix;
@@ -192,6 +193,7 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const cg_latent_args a)
         const float eq = __expf(q_ls), ep = __expf(p_ls), dm = q_loc - p_loc;
         const float kl = -0.5f + p_ls - q_ls + 0.5f * (eq * eq + dm * dm) / (ep * ep);
         kl_acc += kl;
+        s_kl[c][px] = kl;
         if (a.kl_ch != nullptr) atomicAdd(&s_ch[c], kl);  // free-bits statistics (rare path): shared-memory atomics
       } else if (a.mode == 1) {
         z = p_loc + __expf(p_ls) * s_eps[c][px];
@@ -214,6 +216,12 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const cg_latent_args a)
     atomicAdd(a.kl_out + n, s);
   }
   if (a.kl_ch != nullptr && a.mode == 0 && tid < 16) atomicAdd(a.kl_ch + tid, s_ch[tid]);
+  if (a.kl_elem != nullptr && a.mode == 0) {
+    for (int e = tid; e < zd * kLatPix; e += 256) {
+      int c = e / kLatPix, px = e - c * kLatPix;
+      if (px < npx) a.kl_elem[((long long)n * zd + c) * a.HW + hw0 + px] = s_kl[c][px];
+    }
+  }
   if (a.z_f32 != nullptr) {
     for (int e = tid; e < zd * kLatPix; e += 256) {
       int c = e / kLatPix, px = e - c * kLatPix;
@@ -550,7 +558,7 @@ extern "C" int cg_latent_fwd(const cg_latent_args* a, void* stream) {
   CG_REQUIRE(a->p != nullptr && a->z_bf16 != nullptr && (a->mode != 0 || a->q != nullptr), "cg_latent_fwd: null operand");
   const bool rows16 = (((uintptr_t)a->p & 15) == 0) && a->p_ld % 4 == 0 &&
                       (a->q == nullptr || ((((uintptr_t)a->q & 15) == 0) && a->q_ld % 4 == 0));
-  if (a->eps == nullptr && a->z_f32 == nullptr && rows16) {  // in-kernel noise: streaming kernel, no layout staging
+  if (a->eps == nullptr && a->z_f32 == nullptr && a->kl_elem == nullptr && rows16) {  // in-kernel noise: streaming kernel
     dim3 g2(cg_ceil_div(2ll * a->HW, 256), a->N);
     latent_fwd_stream_kernel<<<g2, 256, 0, cg_stream(stream)>>>(*a);
     CG_LAUNCH_CHECK("cg_latent_fwd");

@@ -203,6 +203,8 @@ typedef struct {
   int32_t mode;           /* 0: z~q, KL(q||p)   1: z~p (prior sample)   2: z=p_loc (deterministic) */
   float* kl_ch;           /* optional [zdim] accumulated: sum over (N,H,W) of the block's KL per latent CHANNEL -- the
                              quantity kl_free_bits thresholds (src/vae.py:443-449), see cg_free_bits */
+  float* kl_elem;         /* optional fp32 NCHW (N,zdim,H,W): the element-wise KL, i.e. stats[i]["kl"] of Decoder.forward
+                             (src/vae.py:268); only the stand-alone decoder call materialises it */
 } cg_latent_args;
 int cg_latent_fwd(const cg_latent_args* a, void* stream);
 

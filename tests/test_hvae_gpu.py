@@ -561,3 +561,71 @@ def test_write_images_grid(name, B, tmp_path):
         assert float(cf[0, 0]) == pytest.approx(1 - float(pa[0, 0]), rel=1e-6) and float(cf[1, 1]) == float(pa[1, 1])
         assert float(cf[3, 3]) == pytest.approx(1 - float(pa[0, 3]), rel=1e-6)
         assert (cf[0, 1:] == pa[0, 1:]).all()
+
+
+@pytest.mark.parametrize("name", ["tiny_ukbb", "tiny_morphomnist", "tiny_cmnist"])
+def test_submodule_calls_compose_like_the_reference(name):
+    """model.encoder(x), model.decoder(parents, x=acts, ...), model.likelihood.nll / .sample as stand-alone calls
+    (SURVEY 8b attrs row; src/vae.py:440-442 composes HVAE.forward from exactly these) against the oracle's functions on
+    the same eps; also the binding of a deep copy (EMA, src/utils.py:125)."""
+    import copy
+    cfg, sd, model, x, pa, _ = build(name)
+    pa_full = O.expand_parents(pa, cfg.input_res)
+    arch = O.build_arch(cfg)
+    T = f"submodules[{name}]"
+    with torch.no_grad():
+        acts_ref = O.encoder(sd, cfg, arch, x)
+        tape = O.NoiseTape(seed=303)
+        h_ref, stats_ref = O.decoder(sd, cfg, arch, pa_full, tape, acts=acts_ref, abduct=True, t=0.8)
+        nll_ref = O.likelihood_nll(sd, cfg, h_ref, x)
+        loc_ref, scale_ref = O.likelihood_sample(sd, cfg, h_ref)
+    # encoder
+    acts = model.encoder(x.to(DEV))
+    assert sorted(acts) == sorted(acts_ref)
+    worst = max(float((acts[r].cpu() - acts_ref[r]).abs().max() / (acts_ref[r].abs().max() + 1e-6)) for r in acts_ref)
+    parity_report(T, "encoder acts max err / scale (worst res)", worst, 1.5e-2)
+    assert worst <= 1.5e-2
+    # decoder on the ORACLE's activations (isolates the decoder), abduction mode with temperature
+    eps = [e.to(DEV) for e in tape.drawn]
+    h, stats = model.decoder(pa_full.to(DEV), x={r: a.to(DEV) for r, a in acts_ref.items()}, abduct=True, t=0.8, eps=eps)
+    eh = float((h.cpu() - h_ref).abs().max() / (h_ref.abs().max() + 1e-6))
+    parity_report(T, "decoder h max err / scale", eh, 1.5e-2)
+    assert eh <= 1.5e-2 and len(stats) == len(stats_ref)
+    kl_rel, z_err = 0.0, 0.0
+    for s, sr in zip(stats, stats_ref):
+        assert s["kl"].shape == sr["kl"].shape
+        kl_rel = max(kl_rel, abs(float(s["kl"].sum()) - float(sr["kl"].sum())) / (abs(float(sr["kl"].sum())) + 1e-3))
+        z, zr = (s["z"]["z"], sr["z"]["z"]) if cfg.cond_prior else (s["z"], sr["z"])
+        if cfg.cond_prior:
+            assert set(s["z"]) == {"z", "q_loc", "q_logscale"}
+            z_err = max(z_err, float((s["z"]["q_logscale"].cpu() - sr["z"]["q_logscale"]).abs().max()))
+        z_err = max(z_err, float((z.cpu() - zr).abs().max() / (zr.abs().max() + 1e-6)))
+    parity_report(T, "decoder stats: block KL sum rel (worst)", kl_rel, 1e-2)
+    parity_report(T, "decoder stats: z / q_logscale max err", z_err, 1.5e-2)
+    assert kl_rel <= 1e-2 and z_err <= 1.5e-2
+    # prior-only decode of given latents == forward_latents' features
+    zs = [(s["z"]["z"] if cfg.cond_prior else s["z"]) for s in stats_ref]
+    with torch.no_grad():
+        h2_ref, st2 = O.decoder(sd, cfg, arch, pa_full, O.NoiseTape(seed=1), latents=zs)
+    h2, st2o = model.decoder(pa_full.to(DEV), latents=[z.to(DEV) for z in zs])
+    e2 = float((h2.cpu() - h2_ref).abs().max() / (h2_ref.abs().max() + 1e-6))
+    parity_report(T, "decoder(latents) h max err / scale", e2, 1.5e-2)
+    assert e2 <= 1.5e-2 and st2o == [] and st2 == []
+    # likelihood on the ORACLE's features
+    nll = model.likelihood.nll(h_ref.to(DEV), x.to(DEV))
+    en = float((nll.cpu() - nll_ref).abs().max() / nll_ref.abs().max())
+    loc, scale = model.likelihood.sample(h_ref.to(DEV))
+    el = float((loc.cpu() - loc_ref).abs().max()) * 255
+    es = float(((scale.cpu() - scale_ref).abs() / scale_ref).max())
+    parity_report(T, "likelihood.nll rel", en, 5e-3)
+    parity_report(T, "likelihood.sample loc |d| *255", el, 2.0)
+    parity_report(T, "likelihood.sample scale rel", es, 3e-2)
+    assert en <= 5e-3 and el <= 2.0 and es <= 3e-2
+    # a deep copy binds its OWN sub-modules (and weights)
+    m2 = copy.deepcopy(model)
+    with torch.no_grad():
+        m2.encoder.stem.weight.mul_(0.5)
+    a2 = m2.encoder(x.to(DEV))
+    r0 = max(acts)
+    assert float((a2[r0] - acts[r0]).abs().max()) > 1e-3, "the copy must use its own parameters"
+    assert float((model.encoder(x.to(DEV))[r0] - acts[r0]).abs().max()) == 0.0
