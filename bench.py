@@ -185,7 +185,7 @@ def conv_bytes(a):
     k = 0
     for i in range(a.nsrc):
         s = a.src[i]
-        b += npix * s.C * 2
+        b += npix * (s.c8 * 8 if s.c8 else s.C) * 2   # octets physically stored (cg_src.c8), not the K-blocks
         k += s.C
     for i in range(a.nseg):
         sg = a.seg[i]
@@ -199,9 +199,9 @@ def conv_bytes(a):
 
 def wgrad_bytes(a):
     npix = a.N * a.H * a.W
-    b = npix * a.dy_c * 2
+    b = npix * (a.dy_c8 * 8 if a.dy_c8 else a.dy_c) * 2
     for i in range(a.nsrc):
-        b += npix * a.src[i].C * 2
+        b += npix * (a.src[i].c8 * 8 if a.src[i].c8 else a.src[i].C) * 2
     return b + a.cout_l * a.cin_l * a.ksize * a.ksize * 4
 
 

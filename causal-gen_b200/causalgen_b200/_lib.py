@@ -18,7 +18,7 @@ BF16, F32 = 0, 1
 
 
 class Src(C.Structure):
-    _fields_ = [("ptr", C.c_void_p), ("ns", C.c_int64), ("C", C.c_int32), ("_pad", C.c_int32)]
+    _fields_ = [("ptr", C.c_void_p), ("ns", C.c_int64), ("C", C.c_int32), ("c8", C.c_int32)]
 
 
 class Seg(C.Structure):
@@ -47,7 +47,7 @@ class PackDesc(C.Structure):
 class WgradArgs(C.Structure):
     _fields_ = [("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("ksize", C.c_int32), ("act", C.c_int32),
                 ("nsrc", C.c_int32), ("src", Src * CG_MAX_SRC), ("dy", C.c_void_p), ("dy_ns", C.c_int64),
-                ("dy_c", C.c_int32), ("_pad", C.c_int32), ("dw", C.c_void_p), ("dbias", C.c_void_p), ("cout_l", C.c_int32),
+                ("dy_c", C.c_int32), ("dy_c8", C.c_int32), ("dw", C.c_void_p), ("dbias", C.c_void_p), ("cout_l", C.c_int32),
                 ("cin_l", C.c_int32), ("src_log", C.c_int32 * CG_MAX_SRC), ("src_off", C.c_int32 * CG_MAX_SRC),
                 ("taps", C.c_int32)]
 

@@ -608,7 +608,7 @@ class Engine:
             DP = new_act(N, res, res, 2 * zd + st.cin, self.device)
             dz = new_act(N, res, res, zd, self.device)
             dz_written = False
-            dpf = DP.slice(2 * zd, round16(st.cin), st.cin)
+            dpf = DP.slice(2 * zd, DP.C - 2 * zd, st.cin)
             # conv block.  Without a z_feat_proj consumer (last block) d p_feat IS d h3 (h3 = h + p_feat + ...): the block
             # input gradient is written straight into that slice instead of being copied there
             dh3 = self._res_block_bwd(prog, r.conv, dh_out, dx_out=dpf if r.zs_out is None else None)

@@ -25,6 +25,21 @@ def round16(c: int) -> int:
     return (c + 15) // 16 * 16
 
 
+def round8(c: int) -> int:
+    return (c + 7) // 8 * 8
+
+
+# Channel octets stored per activation: PAD16=1 restores the round-1 layout (channels padded to a multiple of 16 in HBM;
+# A/B measurements).  Default: multiples of 8 -- a tensor with 8 / 24 / 40 channels keeps 1 / 3 / 5 octet planes and the
+# kernels let the TMA box of the last 16-channel K-block run past them (zero fill, cg_src.c8).
+PAD16 = os.environ.get("CAUSALGEN_B200_PAD16", "0") == "1"
+
+
+def phys(c: int) -> int:
+    """channels physically stored for a bf16 planar tensor with `c` logical channels"""
+    return round16(c) if PAD16 else round8(c)
+
+
 class View:
     """Channel slice [c0, c0+C) of an activation tensor.
 
@@ -79,7 +94,7 @@ class View:
 
 def new_act(N, H, W, C, device, dtype=torch.bfloat16, logical=None) -> View:
     """zero-initialised planar buffer; padded channels stay zero for the tensor-core K loop"""
-    Cp = round16(C)
+    Cp = phys(C) if dtype == torch.bfloat16 else round16(C)
     if dtype == torch.bfloat16:
         t = torch.zeros(N, Cp // 8, H, W, 8, device=device, dtype=dtype)
     else:
@@ -90,7 +105,7 @@ def new_act(N, H, W, C, device, dtype=torch.bfloat16, logical=None) -> View:
 def planar_from_nchw(x: torch.Tensor, pad_to: Optional[int] = None) -> torch.Tensor:
     """(N,C,H,W) float -> zero padded planar bf16 tensor (tests / debugging only)"""
     N, Cc, H, W = x.shape
-    Cp = pad_to or round16(Cc)
+    Cp = pad_to or phys(Cc)
     full = torch.zeros(N, Cp, H, W, device=x.device, dtype=torch.bfloat16)
     full[:, :Cc] = x.to(torch.bfloat16)
     return full.reshape(N, Cp // 8, 8, H, W).permute(0, 1, 3, 4, 2).contiguous()
@@ -211,7 +226,12 @@ class ConvLayer:
     @staticmethod
     def _fill_srcs(arr, srcs: Sequence[View]):
         for i, s in enumerate(srcs):
-            arr[i].ptr, arr[i].ns, arr[i].C = s.ptr, s.ns, s.C
+            # C: K-blocks of 16 channels; c8: octets the view physically holds (the last K-block may be half there)
+            arr[i].ptr, arr[i].ns, arr[i].C, arr[i].c8 = s.ptr, s.ns, round16(s.C), s.C // 8
+
+    @staticmethod
+    def _fits(v: View, logical: int) -> bool:
+        return round8(logical) <= v.C <= round16(logical)
 
     @staticmethod
     def _fill_segs(a, segs: Sequence[SegSpec]):
@@ -232,7 +252,7 @@ class ConvLayer:
             s.act_copy_ns = sg.act_copy.ns if sg.act_copy is not None else 0
 
     def forward(self, srcs: Sequence[View], segs: Sequence[SegSpec], N, H, W) -> L.Launch:
-        assert [s.C for s in srcs] == self.src_pad, ([s.C for s in srcs], self.src_pad)
+        assert all(self._fits(s, c) for s, c in zip(srcs, self.src_logical)), ([s.C for s in srcs], self.src_logical)
         a = L.ConvArgs()
         a.N, a.H, a.W, a.ksize, a.act = N, H, W, self.ksize, self.act
         a.nsrc, a.cout = len(srcs), self.cout_pad
@@ -249,7 +269,7 @@ class ConvLayer:
 
     def dgrad(self, i: int, dy: View, seg: SegSpec, N, H, W) -> L.Launch:
         """dX_i = conv^T(dY) [* act'(x_i)] [+ add]  for source i"""
-        assert dy.C == self.cout_pad and seg.out.C == self.src_pad[i]
+        assert self._fits(dy, self.cout_l) and self._fits(seg.out, self.src_logical[i]), (dy.C, seg.out.C)
         a = L.ConvArgs()
         a.N, a.H, a.W, a.ksize, a.act = N, H, W, self.ksize, L.ACT_NONE
         a.nsrc, a.cout = 1, self.src_pad[i]
@@ -266,7 +286,7 @@ class ConvLayer:
         a.N, a.H, a.W, a.ksize, a.act = N, H, W, self.k, self.act
         a.nsrc = len(srcs)
         self._fill_srcs(a.src, srcs)
-        a.dy, a.dy_c, a.dy_ns = dy.ptr, dy.C, dy.ns
+        a.dy, a.dy_c, a.dy_c8, a.dy_ns = dy.ptr, round16(dy.C), dy.C // 8, dy.ns
         a.dw = dw.data_ptr()
         a.dbias = db.data_ptr() if db is not None else None
         a.cout_l, a.cin_l, a.taps = self.cout_l, self.cin_l, self.taps

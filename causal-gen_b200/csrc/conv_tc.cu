@@ -199,7 +199,7 @@ __device__ __forceinline__ uint4 act8(uint4 u, int act) {
 template <bool MUL, bool ADD, bool ADD2, int OACT, bool COPY>
 __device__ __forceinline__ void epi_chunk_fast(float (&v)[16], const uint8_t* e0, int eslot, int k_mul, int k_add,
                                                int k_add2, const float* bias, bf16* op, bf16* op2, long long HW8,
-                                               bool valid) {
+                                               bool valid, int noct) {
   if (bias != nullptr) {
 #pragma unroll
     for (int q = 0; q < 16; q += 4) {
@@ -209,6 +209,7 @@ __device__ __forceinline__ void epi_chunk_fast(float (&v)[16], const uint8_t* e0
   }
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
+    if (h >= noct) break;  // a destination with 8 (mod 16) channels stores one octet of its last chunk
     float x[8];
     if (MUL) {  // ReLU'(x): pass the gradient where the saved forward input is positive
       cg_unpack8(*reinterpret_cast<const uint4*>(e0 + k_mul * eslot + h * kPlane1), x);
@@ -538,7 +539,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             else if (P.eop[k].kind == 1) pl.k_add2 = k;
             else pl.k_mul = k;
           }
-        if (sg.dtype == CG_BF16 && pl.cnt == 16 && pl.k_add != -1 && pl.k_add2 != -1 && pl.k_mul != -1 &&
+        if (sg.dtype == CG_BF16 && (pl.cnt == 16 || pl.cnt == 8) && pl.k_add != -1 && pl.k_add2 != -1 && pl.k_mul != -1 &&
             sg.out_act <= CG_ACT_GELU &&  // LeakyReLU (predictors) takes the generic path
             (pl.k_mul == -2 || sg.mul_act == CG_ACT_RELU) && !(pl.k_mul >= 0 && pl.k_add2 >= 0))
           pl.fast = (pl.k_mul >= 0 ? 1 : 0) | (pl.k_add >= 0 ? 2 : 0) | (pl.k_add2 >= 0 ? 4 : 0) |
@@ -605,7 +606,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           bool done = true;
 #define CG_EPI(code, M, A, A2, OA, CP)                                                                          \
   case code:                                                                                                    \
-    epi_chunk_fast<M, A, A2, OA, CP>(acc[j], e0, eslot, pl.k_mul, pl.k_add, pl.k_add2, bp, op, op2, P.HW8, valid); \
+    epi_chunk_fast<M, A, A2, OA, CP>(acc[j], e0, eslot, pl.k_mul, pl.k_add, pl.k_add2, bp, op, op2, P.HW8, valid, pl.cnt >> 3); \
     break;
           switch (pl.fast) {
             CG_EPI(0, false, false, false, 0, false) CG_EPI(8, false, false, false, 1, false)
@@ -843,8 +844,10 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
     CG_REQUIRE(src.C > 0 && src.C % 16 == 0 && src.ns % 8 == 0, "cg_conv2d: src %d C=%d ns=%lld", s, src.C,
                (long long)src.ns);
     const int box_c8 = src.C / 8 < 4 ? src.C / 8 : 4;
-    int rc = kp.fold ? cg_make_planar_map(&kp.src_map[s], src.ptr, src.ns, a->N, a->H, a->W, src.C / 8, 0, 16 * 8, 10, box_c8)
-                     : cg_make_planar_map(&kp.src_map[s], src.ptr, src.ns, a->N, a->H, a->W, src.C / 8, kp.flat,
+    const int c8_phys = src.c8 > 0 ? src.c8 : src.C / 8;  // octets stored; the box may run past them (zero fill)
+    CG_REQUIRE(c8_phys <= src.C / 8 && c8_phys * 8 + 8 > src.C - 8, "cg_conv2d: src %d c8=%d vs C=%d", s, c8_phys, src.C);
+    int rc = kp.fold ? cg_make_planar_map(&kp.src_map[s], src.ptr, src.ns, a->N, a->H, a->W, c8_phys, 0, 16 * 8, 10, box_c8)
+                     : cg_make_planar_map(&kp.src_map[s], src.ptr, src.ns, a->N, a->H, a->W, c8_phys, kp.flat,
                                           (8 + halo) * 8, 16 + halo, box_c8);
     if (rc != CG_OK) return rc;
     kp.src_bytes[s] = (uint32_t)box_c8 * (kp.fold ? kPlaneF : (flat ? kPlane1 : (a->ksize == 3 ? kPlane3 : kPlane1)));

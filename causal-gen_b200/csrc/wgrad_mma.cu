@@ -576,16 +576,16 @@ static int wgrad_mma_1x1(const cg_wgrad_args* a, void* stream, int* handled) {
   const int gy = kp.nchunks * kp.ny;
   if (gy > cg_device_sms()) return CG_OK;  // more channel blocks than SMs: leave it to the tcgen05 kernel
   for (int s = 0; s < a->nsrc; ++s) {
-    const int c8 = a->src[s].C / 8;
+    const int c8 = a->src[s].C / 8, c8p = a->src[s].c8 > 0 ? a->src[s].c8 : c8;  // K-blocks / octets stored
     const int boct = c8 < NT ? c8 : NT;
-    int rc = cg_make_planar_map(&kp.x_map[s], a->src[s].ptr, a->src[s].ns, a->N, a->H, a->W, c8, 0, 64, 16, boct);
+    int rc = cg_make_planar_map(&kp.x_map[s], a->src[s].ptr, a->src[s].ns, a->N, a->H, a->W, c8p, 0, 64, 16, boct);
     if (rc != CG_OK) return rc;
     kp.x_bytes[s] = (uint32_t)boct * kPlaneFlat;
   }
   {
-    const int c8 = a->dy_c / 8;
+    const int c8 = a->dy_c / 8, c8p = a->dy_c8 > 0 ? a->dy_c8 : c8;
     const int boct = c8 < CO / 8 ? c8 : CO / 8;
-    int rc = cg_make_planar_map(&kp.dy_map, a->dy, a->dy_ns, a->N, a->H, a->W, c8, 0, 64, 16, boct);
+    int rc = cg_make_planar_map(&kp.dy_map, a->dy, a->dy_ns, a->N, a->H, a->W, c8p, 0, 64, 16, boct);
     if (rc != CG_OK) return rc;
     kp.dy_bytes = (uint32_t)boct * kPlaneFlat;
   }
@@ -661,29 +661,29 @@ int cg_wgrad_mma_try(const cg_wgrad_args* a, void* stream, int* handled) {
   }
   // tensor maps: the narrow operand carries the halo
   for (int s = 0; s < a->nsrc; ++s) {
-    const int c8 = a->src[s].C / 8;
+    const int c8 = a->src[s].C / 8, c8p = a->src[s].c8 > 0 ? a->src[s].c8 : c8;  // K-blocks / octets stored
     int boct, rc;
     if (shift_a) {
       boct = c8 < wide_planes ? c8 : wide_planes;
-      rc = cg_make_planar_map(&kp.x_map[s], a->src[s].ptr, a->src[s].ns, a->N, a->H, a->W, c8, 0, 64, 16, boct);
+      rc = cg_make_planar_map(&kp.x_map[s], a->src[s].ptr, a->src[s].ns, a->N, a->H, a->W, c8p, 0, 64, 16, boct);
       kp.x_bytes[s] = (uint32_t)boct * kPlaneFlat;
     } else {
       boct = narrow_planes;  // == c8
-      rc = cg_make_planar_map(&kp.x_map[s], a->src[s].ptr, a->src[s].ns, a->N, a->H, a->W, c8, 0, 80, 18, boct);
+      rc = cg_make_planar_map(&kp.x_map[s], a->src[s].ptr, a->src[s].ns, a->N, a->H, a->W, c8p, 0, 80, 18, boct);
       kp.x_bytes[s] = (uint32_t)boct * kPlaneHalo;
     }
     if (rc != CG_OK) return rc;
   }
   {
-    const int c8 = dyc / 8;
+    const int c8 = dyc / 8, c8p = a->dy_c8 > 0 ? a->dy_c8 : c8;
     int boct, rc;
     if (shift_a) {
       boct = narrow_planes;  // == c8
-      rc = cg_make_planar_map(&kp.dy_map, a->dy, a->dy_ns, a->N, a->H, a->W, c8, 0, 80, 18, boct);
+      rc = cg_make_planar_map(&kp.dy_map, a->dy, a->dy_ns, a->N, a->H, a->W, c8p, 0, 80, 18, boct);
       kp.dy_bytes = (uint32_t)boct * kPlaneHalo;
     } else {
       boct = c8 < wide_planes ? c8 : wide_planes;
-      rc = cg_make_planar_map(&kp.dy_map, a->dy, a->dy_ns, a->N, a->H, a->W, c8, 0, 64, 16, boct);
+      rc = cg_make_planar_map(&kp.dy_map, a->dy, a->dy_ns, a->N, a->H, a->W, c8p, 0, 64, 16, boct);
       kp.dy_bytes = (uint32_t)boct * kPlaneFlat;
     }
     if (rc != CG_OK) return rc;

@@ -343,16 +343,16 @@ extern "C" int cg_conv2d_wgrad(const cg_wgrad_args* a, void* stream) {
   const int xw = kp.halo ? 80 : 64, xh = kp.halo ? 18 : 16;
   const int xplane = kp.halo ? kPlaneHalo : kPlaneFlat;
   for (int s = 0; s < a->nsrc; ++s) {
-    const int c8 = a->src[s].C / 8;
+    const int c8 = a->src[s].C / 8, c8p = a->src[s].c8 > 0 ? a->src[s].c8 : c8;  // K-blocks / octets stored
     const int boct = c8 < x_box_oct ? c8 : x_box_oct;
-    int rc = cg_make_planar_map(&kp.x_map[s], a->src[s].ptr, a->src[s].ns, a->N, a->H, a->W, c8, kp.flat, xw, xh, boct);
+    int rc = cg_make_planar_map(&kp.x_map[s], a->src[s].ptr, a->src[s].ns, a->N, a->H, a->W, c8p, kp.flat, xw, xh, boct);
     if (rc != CG_OK) return rc;
     kp.x_bytes[s] = (uint32_t)boct * xplane;
   }
   {
-    const int c8 = a->dy_c / 8;
+    const int c8 = a->dy_c / 8, c8p = a->dy_c8 > 0 ? a->dy_c8 : c8;
     const int boct = c8 < y_box_oct ? c8 : y_box_oct;
-    int rc = cg_make_planar_map(&kp.dy_map, a->dy, a->dy_ns, a->N, a->H, a->W, c8, kp.flat, 64, 16, boct);
+    int rc = cg_make_planar_map(&kp.dy_map, a->dy, a->dy_ns, a->N, a->H, a->W, c8p, kp.flat, 64, 16, boct);
     if (rc != CG_OK) return rc;
     kp.dy_bytes = (uint32_t)boct * kPlaneFlat;
   }

@@ -58,8 +58,10 @@ int cg_device_sms(void);
 typedef struct {
   const void* ptr;  /* first channel-octet plane of the view */
   int64_t ns;       /* sample stride in elements (multiple of 8) */
-  int32_t C;        /* channels taken from this source, multiple of 16 (zero padded) */
-  int32_t _pad;
+  int32_t C;        /* channels taken from this source, multiple of 16: the K-blocks of the GEMM */
+  int32_t c8;       /* channel octets PHYSICALLY stored (0 = C/8).  A tensor with 8, 24, 40 ... channels keeps 1, 3, 5 ... octet
+                       planes in HBM; the TMA box of the last 16-channel K-block runs past that extent and is zero-filled, so
+                       the zero half of the block costs no HBM bytes */
 } cg_src;
 
 typedef struct {
@@ -147,7 +149,7 @@ typedef struct {
   cg_src src[CG_MAX_SRC];  /* forward inputs (activation re-applied on load) */
   const void* dy;          /* bf16 planar gradient of the conv output */
   int64_t dy_ns;           /* its sample stride */
-  int32_t dy_c, _pad;      /* padded channels (multiple of 16) */
+  int32_t dy_c, dy_c8;     /* padded channels (multiple of 16); octets physically stored (0 = dy_c/8), see cg_src.c8 */
   float* dw;               /* fp32 OIHW gradient, ACCUMULATED into (atomics) */
   float* dbias;            /* fp32 [cout_l] accumulated, or NULL */
   int32_t cout_l, cin_l;   /* logical dims of dw */

@@ -74,15 +74,15 @@ CONV_CASES = [
 
 def run_conv(N, H, W, chans, ctx, cout, k, act, seed=0):
     from causalgen_b200 import _lib as L
-    from causalgen_b200.ops import ConvLayer, PackTable, SegSpec, View, new_act, round16
+    from causalgen_b200.ops import ConvLayer, PackTable, SegSpec, View, new_act, phys
     xs = [rnd(N, c, H, W, seed=seed + i) for i, c in enumerate(chans)]
-    views = [View(nhwc_bf16(x), round16(c), 0, c) for x, c in zip(xs, chans)]
+    views = [View(nhwc_bf16(x), phys(c), 0, c) for x, c in zip(xs, chans)]
     logical = list(chans)
     pa = None
     if ctx:  # spatially constant parents, materialised (src/vae.py:241)
         pa = rnd(N, ctx, seed=seed + 9)
         pat = nhwc_bf16(pa[:, :, None, None].expand(N, ctx, H, W))
-        views.insert(1, View(pat, round16(ctx), 0, ctx))
+        views.insert(1, View(pat, phys(ctx), 0, ctx))
         logical.insert(1, ctx)
         chans = list(chans)
     cin = sum(logical)
@@ -120,7 +120,7 @@ def test_conv_column_folded_matches_plain(case):
     """cg_conv_args.fold: kernel columns on the GEMM-N axis + shuffle-add epilogue == the nine-tap kernel == F.conv2d
     (src/vae.py:53-56 first conv of a Block), forward and the data gradient of the mirrored (narrow -> wide) conv."""
     from causalgen_b200 import ops
-    from causalgen_b200.ops import SegSpec, View, new_act, round16
+    from causalgen_b200.ops import SegSpec, View, new_act, phys
     N, H, W, chans, ctx, cout, k, act = case
     default = ops.FOLD
     try:
@@ -136,7 +136,7 @@ def test_conv_column_folded_matches_plain(case):
 
 def _folded_checks(case, layer, views, out, out0, ref):
     from causalgen_b200 import ops
-    from causalgen_b200.ops import SegSpec, View, new_act, round16
+    from causalgen_b200.ops import SegSpec, View, new_act, phys
     N, H, W, chans, ctx, cout, k, act = case
     got, plain = to_nchw(out.t, cout), to_nchw(out0.t, cout)
     assert_close(got, ref, 1e-2, f"folded fwd {case}")
@@ -144,8 +144,8 @@ def _folded_checks(case, layer, views, out, out0, ref):
     print(f"fold[{case}] folded vs nine-tap max rel diff {d:.3g} (bf16 rounding of the same fp32 sums)")
     assert d <= 8e-3  # one bf16 ulp of the largest output: the fp32 partial sums are only re-associated
     # fused epilogue operands on the folded path: ReLU' mask + accumulate (the data-gradient use), in place
-    res = View(nhwc_bf16(rnd(N, cout, H, W, seed=60)), round16(cout))
-    msk = View(nhwc_bf16(rnd(N, cout, H, W, seed=61)), round16(cout))
+    res = View(nhwc_bf16(rnd(N, cout, H, W, seed=60)), phys(cout))
+    msk = View(nhwc_bf16(rnd(N, cout, H, W, seed=61)), phys(cout))
     want = ref * (to_nchw(msk.t, cout) > 0) + to_nchw(res.t, cout)
     layer.forward(views, [SegSpec(res, 0, add=res, mul=msk, mul_act=1)], N, H, W)(stream())
     torch.cuda.synchronize()
@@ -158,9 +158,9 @@ def _folded_checks(case, layer, views, out, out0, ref):
         wm = rnd(chans[0], cout, 3, 3, scale=1.0 / math.sqrt(cout * 9), seed=70)   # conv cout -> chans[0]
         lm = ops.ConvLayer(table, wm, None, [cout], 0)
         table.launch(stream())
-        if chans[0] >= 2 * round16(cout):
+        if chans[0] >= 2 * phys(cout):
             assert lm.fold_bwd[0] == 1
-        dy = View(nhwc_bf16(rnd(N, chans[0], H, W, seed=71)), round16(chans[0]))
+        dy = View(nhwc_bf16(rnd(N, chans[0], H, W, seed=71)), phys(chans[0]))
         dx = new_act(N, H, W, cout, DEV)
         lm.dgrad(0, dy, SegSpec(dx, 0), N, H, W)(stream())
         torch.cuda.synchronize()
@@ -203,11 +203,11 @@ def test_conv_segments_add_and_fp32_split():
                                   (3, 6, 6, [40], 0, 176, 3, 2), (2, 8, 8, [16], 20, 64, 1, 0),
                                   (4, 1, 1, [128], 0, 64, 1, 2), (1, 48, 48, [24], 0, 128, 3, 1)])
 def test_conv_dgrad_and_wgrad(case):
-    from causalgen_b200.ops import SegSpec, View, new_act, round16
+    from causalgen_b200.ops import SegSpec, View, new_act, phys
     N, H, W, chans, ctx, cout, k, act = case
     layer, views, out, ref, w, b = run_conv(*case, seed=5)
     dy_nchw = rnd(N, cout, H, W, seed=31)
-    dy = View(nhwc_bf16(dy_nchw), round16(cout), 0, cout)
+    dy = View(nhwc_bf16(dy_nchw), phys(cout), 0, cout)
     # autograd reference on the bf16-rounded operands
     is_pa = [ctx and i == 1 for i in range(len(views))]
     data_views = [v for v, p in zip(views, is_pa) if not p]
@@ -225,7 +225,7 @@ def test_conv_dgrad_and_wgrad(case):
             continue
         j = data_views.index(v)
         dx = new_act(N, H, W, chans[j], DEV)
-        prev = View(nhwc_bf16(rnd(N, chans[j], H, W, seed=40 + j)), round16(chans[j]))
+        prev = View(nhwc_bf16(rnd(N, chans[j], H, W, seed=40 + j)), phys(chans[j]))
         layer.dgrad(i, dy, SegSpec(dx, 0, add=prev, mul=v, mul_act=act), N, H, W)(stream())
         torch.cuda.synchronize()
         assert_close(to_nchw(dx.t, chans[j]), xs[j].grad + to_nchw(prev.t, chans[j]), 1.5e-2, f"dgrad src{i} {case}")
@@ -248,19 +248,19 @@ def test_conv_dgrad_and_wgrad(case):
                                   (16, 48, 48, [32], 0, 96, 3, 1)])     # Nc 96 = 48 + 48
 def test_conv_many_tiles_per_cta(case):
     """pipeline rings wrap many times: several tiles per persistent CTA, in-place accumulate, fused operands"""
-    from causalgen_b200.ops import SegSpec, View, new_act, round16
+    from causalgen_b200.ops import SegSpec, View, new_act, phys
     N, H, W, chans, ctx, cout, k, act = case
     layer, views, out, ref, w, b = run_conv(*case, seed=11)
     assert_close(to_nchw(out.t, cout), ref, 1e-2, f"fwd {case}")
     # forward again with residual + second addend, accumulating IN PLACE into the first addend's buffer
-    acc = View(nhwc_bf16(rnd(N, cout, H, W, seed=50)), round16(cout))
+    acc = View(nhwc_bf16(rnd(N, cout, H, W, seed=50)), phys(cout))
     acc0 = to_nchw(acc.t, cout).clone()
-    other = View(nhwc_bf16(rnd(N, cout, H, W, seed=51)), round16(cout))
+    other = View(nhwc_bf16(rnd(N, cout, H, W, seed=51)), phys(cout))
     layer.forward(views, [SegSpec(acc, 0, add=acc, add2=other)], N, H, W)(stream())
     torch.cuda.synchronize()
     assert_close(to_nchw(acc.t, cout), ref + acc0 + to_nchw(other.t, cout), 1e-2, f"fwd in-place add {case}")
     # data gradient with act'(x) and in-place accumulate; weight gradient
-    dy = View(nhwc_bf16(rnd(N, cout, H, W, seed=52)), round16(cout), 0, cout)
+    dy = View(nhwc_bf16(rnd(N, cout, H, W, seed=52)), phys(cout), 0, cout)
     data_views = [v for i, v in enumerate(views) if not (ctx and i == 1)]
     xs = [to_nchw(v.t, c).requires_grad_(True) for v, c in zip(data_views, chans)]
     parts = list(xs)
@@ -270,7 +270,7 @@ def test_conv_many_tiles_per_cta(case):
     y = F.conv2d(act_fn(act)(torch.cat(parts, 1)), wq, None, padding=k // 2)
     y.backward(to_nchw(dy.t, cout))
     i0 = views.index(data_views[0])
-    dx = View(nhwc_bf16(rnd(N, chans[0], H, W, seed=53)), round16(chans[0]))
+    dx = View(nhwc_bf16(rnd(N, chans[0], H, W, seed=53)), phys(chans[0]))
     dx0 = to_nchw(dx.t, chans[0]).clone()
     layer.dgrad(i0, dy, SegSpec(dx, 0, add=dx, mul=data_views[0], mul_act=act), N, H, W)(stream())
     torch.cuda.synchronize()
@@ -305,10 +305,10 @@ WGRAD_MMA_CASES = [
 @pytest.mark.parametrize("case", WGRAD_MMA_CASES)
 def test_wgrad_mma_small_channel_3x3(case):
     """weight + bias gradient of the warp-level mma.sync kernel vs autograd on the same bf16 operands"""
-    from causalgen_b200.ops import View, round16
+    from causalgen_b200.ops import View, phys
     N, H, W, chans, ctx, cout, k, act = case
     layer, views, out, ref, w, b = run_conv(*case, seed=17)
-    dy = View(nhwc_bf16(rnd(N, cout, H, W, seed=61)), round16(cout), 0, cout)
+    dy = View(nhwc_bf16(rnd(N, cout, H, W, seed=61)), phys(cout), 0, cout)
     logical = list(chans)
     if ctx:
         logical.insert(1, ctx)

@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "causal-gen_b200
 import torch
 from bench import conv_bytes, wgrad_bytes
 from causalgen_b200 import _lib as L
-from causalgen_b200.ops import ConvLayer, PackTable, SegSpec, View, new_act, planar_from_nchw, round16
+from causalgen_b200.ops import ConvLayer, PackTable, SegSpec, View, new_act, planar_from_nchw, phys
 DEV = "cuda"
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 only = sys.argv[2] if len(sys.argv) > 2 else None
@@ -18,12 +18,12 @@ CASES = [
     ("dgrad 16->64 r96 mul", 96, [16], 64, 3, 0, "mul"),
     ("dgrad 16->64 r96 mul+add", 96, [16], 64, 3, 0, "muladd"),
     ("dgrad 64->16 r96 mul", 96, [64], 16, 3, 0, "mul"),
-    ("fwd 32->8 r192", 192, [32], 16, 3, 1, "none"),
-    ("fwd 8->32 r192 +res", 192, [16], 32, 3, 1, "add"),
-    ("fwd 96->24 r48", 48, [96], 32, 3, 1, "none"),
-    ("fwd 24->96 r48 +res", 48, [32], 96, 3, 1, "add"),
-    ("dgrad 24->96 r48 muladd", 48, [32], 96, 3, 0, "muladd"),
-    ("fwd post 208->24 r48", 48, [96, 16, 96], 32, 3, 1, "none"),
+    ("fwd 32->8 r192", 192, [32], 8, 3, 1, "none"),
+    ("fwd 8->32 r192 +res", 192, [8], 32, 3, 1, "add"),
+    ("fwd 96->24 r48", 48, [96], 24, 3, 1, "none"),
+    ("fwd 24->96 r48 +res", 48, [24], 96, 3, 1, "add"),
+    ("dgrad 24->96 r48 muladd", 48, [24], 96, 3, 0, "muladd"),
+    ("fwd post 208->24 r48", 48, [96, 4, 96], 24, 3, 1, "none"),
     ("fwd 128->32 r24", 24, [128], 32, 3, 1, "none"),
     ("fwd 32->128 r24 +res", 24, [32], 128, 3, 1, "add"),
     ("fwd 32->160 r24 prior", 24, [32], 160, 3, 1, "none"),
@@ -49,13 +49,13 @@ for name, H, cins, cout, k, act, epi in CASES:
     g = torch.Generator().manual_seed(0)
     views = []
     for i, c in enumerate(cins):
-        t = planar_from_nchw(torch.randn(N, round16(c), H, H, generator=g).to(DEV))
-        views.append(View(t, round16(c), 0, c))
+        t = planar_from_nchw(torch.randn(N, phys(c), H, H, generator=g).to(DEV))
+        views.append(View(t, phys(c), 0, c))
     w = (torch.randn(cout, sum(cins), k, k, generator=g) * 0.05).to(DEV); b = torch.zeros(cout, device=DEV)
     table = PackTable(DEV); layer = ConvLayer(table, w, b, cins, act); table.launch(s())
     out = new_act(N, H, H, cout, DEV)
-    x1 = View(planar_from_nchw(torch.randn(N, round16(cout), H, H, generator=g).to(DEV)), round16(cout))
-    x2 = View(planar_from_nchw(torch.randn(N, round16(cout), H, H, generator=g).to(DEV)), round16(cout))
+    x1 = View(planar_from_nchw(torch.randn(N, phys(cout), H, H, generator=g).to(DEV)), phys(cout))
+    x2 = View(planar_from_nchw(torch.randn(N, phys(cout), H, H, generator=g).to(DEV)), phys(cout))
     seg = SegSpec(out, 0)
     if epi == "add": seg.add = x1
     if epi in ("mul", "muladd"): seg.mul, seg.mul_act = x1, 1

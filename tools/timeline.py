@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "causal-gen_b200"))
 import torch
 from causalgen_b200 import _lib as L
-from causalgen_b200.ops import ConvLayer, PackTable, SegSpec, View, new_act, planar_from_nchw, round16
+from causalgen_b200.ops import ConvLayer, PackTable, SegSpec, View, new_act, planar_from_nchw, phys
 sys.argv, argv = sys.argv[:1], sys.argv[1:]
 import importlib.util
 spec = importlib.util.spec_from_file_location("mb", os.path.join(ROOT, "tools", "conv_microbench.py"))
@@ -34,12 +34,12 @@ for name, H, cins, cout, k, act, epi in CASES:
     g = torch.Generator().manual_seed(0)
     views = []
     for c in cins:
-        views.append(View(planar_from_nchw(torch.randn(N, round16(c), H, H, generator=g).cuda()), round16(c), 0, c))
+        views.append(View(planar_from_nchw(torch.randn(N, phys(c), H, H, generator=g).cuda()), phys(c), 0, c))
     w = (torch.randn(cout, sum(cins), k, k, generator=g) * 0.05).cuda(); b = torch.zeros(cout, device="cuda")
     table = PackTable("cuda"); layer = ConvLayer(table, w, b, cins, act); table.launch(s())
     out = new_act(N, H, H, cout, "cuda")
-    x1 = View(planar_from_nchw(torch.randn(N, round16(cout), H, H, generator=g).cuda()), round16(cout))
-    x2 = View(planar_from_nchw(torch.randn(N, round16(cout), H, H, generator=g).cuda()), round16(cout))
+    x1 = View(planar_from_nchw(torch.randn(N, phys(cout), H, H, generator=g).cuda()), phys(cout))
+    x2 = View(planar_from_nchw(torch.randn(N, phys(cout), H, H, generator=g).cuda()), phys(cout))
     seg = SegSpec(out, 0)
     if epi == "add": seg.add = x1
     if epi in ("mul", "muladd"): seg.mul, seg.mul_act = x1, 1
