@@ -13,12 +13,9 @@ import torch
 from . import _lib as L
 
 
-# Column-folded 3x3 convolutions (cg_conv_args.fold) are OFF by default: measured on B200 at batch 128 they are correct
-# (tests/test_kernels_gpu.py::test_conv_column_folded_matches_plain) and cut the tcgen05 operand reads to a third, but the
-# conv kernel is bound by its TMA box rate, not by the MMAs (profiles/r2o_conv_ablation.txt: loads-only skeleton 48.9 us,
-# nine-tap 83.8 us, folded 90.7 us for 64->16 @96^2): the folded tiling needs 1.17x more boxes.  CAUSALGEN_B200_FOLD=1
-# switches them on (A/B measurements, r <= 24 layers gain ~10 %).
-FOLD = os.environ.get("CAUSALGEN_B200_FOLD", "0") == "1"
+# The column-folded 3x3 convolution of round 2 (kernel columns on the GEMM-N axis) was parity-green but slower on every layer
+# (profiles/r2n_*, r2u_*) and has been retired from the kernel; cg_conv_fold_ok() answers 0, so `fold` stays 0 below.
+FOLD = False
 
 
 def round16(c: int) -> int:
