@@ -260,7 +260,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   // the four transform warps (the per-stage activation pass is the same kind of latency chain: with Nc = 16 sixteen warps
   // share a stage, two 16-byte slots per thread instead of six), or leave when the conv has no input activation.
   const int n_epi = 4 * ((Nc + 15) >> 4);              // epilogue warps with a chunk
-  const int n_xfw = kXfWarps + (kEpiWarps - n_epi);    // warps on the transform role
+  // warps on the transform role: about two 16-byte slots of the largest stage per thread, at least the four dedicated ones
+  // (more warps than that only add barrier polling: 8 -> 32 @192^2 lost 4 % with twelve warps on a 360-slot stage)
+  int n_xfw = (P.stage_bytes / 16 + 63) / 64;
+  n_xfw = n_xfw < kXfWarps ? kXfWarps : (n_xfw > kXfWarps + kEpiWarps - n_epi ? kXfWarps + kEpiWarps - n_epi : n_xfw);
   if (threadIdx.x == 0) CG_TL(P.tl, 32);
 
   if (threadIdx.x == 0) {
@@ -430,11 +433,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (pw == 0 && lt < 12) CG_TL(P.tl, 91 + 2 * lt);
       }
     }
-  } else if ((warp >= kXfWarp0 && warp < kMmaWarp2) || (warp < kEpiWarps && warp >= n_epi)) {
+  } else if ((warp >= kXfWarp0 && warp < kMmaWarp2) || (warp < kEpiWarps && warp >= n_epi && warp - n_epi < n_xfw - kXfWarps)) {
     // ------------------------------------------------------------------ transform warps (+ chunk-less epilogue warps)
     if (act != CG_ACT_NONE) {
       const int nthr = n_xfw * 32;
-      const int xt = (warp < kEpiWarps ? warp - n_epi : (kEpiWarps - n_epi) + warp - kXfWarp0) * 32 + lane;
+      const int xt = (warp < kEpiWarps ? warp - n_epi : (n_xfw - kXfWarps) + warp - kXfWarp0) * 32 + lane;
       uint32_t st0 = 0, st1 = 0, ph0 = 0, ph1 = 0, lt = 0;
       const uint32_t len0 = (uint32_t)P.nst0, len1 = (uint32_t)(nst - P.nst0);
       const bool two = P.nst0 < nst;
@@ -462,10 +465,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
       }
     }
-  } else {
+  } else if (warp < n_epi) {
     // ------------------------------------------------------------------ epilogue
     // warp = quarter + 4*chunk: TMEM lanes [32*quarter, +32) (one pixel per lane) and the 16-column chunk `chunk` of the
-    // CTA's GEMM-N range (Nc <= 64 -> <= 4 chunks; warps whose chunk lies beyond Nc only take part in the hand-offs).
+    // CTA's GEMM-N range (Nc <= 64 -> <= 4 chunks; warps whose chunk lies beyond Nc help the transform role or leave).
     // Which segment / staged operands the chunk maps to is the same for every tile, so it is resolved ONCE here
     // (ChunkPlan); per tile the warp issues its TMEM load, releases the accumulator and then does bias / act' / residual
     // / store from registers.
