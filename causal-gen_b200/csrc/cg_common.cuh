@@ -103,13 +103,15 @@ __device__ __forceinline__ float cg_dact(float x, int act) {
   return act == CG_ACT_RELU ? (x > 0.0f ? 1.0f : 0.0f) : (act == CG_ACT_GELU ? cg_dgelu(x) : 1.0f);
 }
 
+// two floats -> packed bf16x2 (a in the low half), round to nearest even: ONE cvt; bf16x2 -> two floats: a shift and a mask
+// (exact).  These sit on the conv epilogue's per-tile instruction chain, where every instruction counts.
 __device__ __forceinline__ uint32_t cg_pack2(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
 __device__ __forceinline__ float2 cg_unpack2(uint32_t u) {
-  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
-  return __bfloat1622float2(v);
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 // 8 bf16 <-> 8 floats
 __device__ __forceinline__ void cg_unpack8(const uint4& u, float* f) {

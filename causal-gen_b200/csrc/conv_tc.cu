@@ -472,9 +472,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // Which segment / staged operands the chunk maps to is the same for every tile, so it is resolved ONCE here
     // (ChunkPlan); per tile the warp issues its TMEM load, releases the accumulator and then does bias / act' / residual
     // / store from registers.
-    uint32_t as = 0, aphase = 0, es = 0, ephase = 0;
-    int tl_i = 0;
-    (void)tl_i;
     const int quarter = warp & 3, chunk = warp >> 2;
     const int m = quarter * 32 + lane;
     const int nE = P.nE;
@@ -541,70 +538,58 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         break;
       }
     }
-    TileWalk walk(P, blockIdx.x, gridDim.x);
-    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, walk.next()) {
-      const TileGeom g = walk.geom(P);
-      bool valid;
-      int n;
-      long long hw;  // pixel index inside the image
-      if (P.flat) {
-        n = g.n + m;
-        hw = 0;
-        valid = n < N;
-      } else {
-        const int h = g.h0 + (m >> 3), w = g.w0 + (m & 7);
-        n = g.n;
-        hw = (long long)h * W + w;
-        valid = (h < H) && (w < W);
-      }
-      if (nE > 0) warp_wait(BAR(B_EFULL + es), ephase, lane);
-      warp_wait(BAR(B_ACCFULL + as), aphase, lane);
-      tc_fence_after();
-      const uint8_t* e_row = sE + (size_t)es * estage + (size_t)m * 16;
-      const uint32_t t_row = tmem_base + as * (uint32_t)Nc + ((uint32_t)(quarter * 32) << 16);
-      float acc[1][16];
-      __syncwarp();  // .aligned TMEM loads need the whole warp converged
-      if (plan[0].col < Nc) tmem_ld16_nowait(t_row + (uint32_t)plan[0].col, acc[0]);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(B_ACCEMPTY + as));  // accumulator is in registers: MMA may reuse it
-#pragma unroll
-      for (int j = 0; j < 1; ++j) {
-        const ChunkPlan& pl = plan[j];
-        if (pl.sgi < 0) continue;
-        if (pl.fast >= 0) {
-          const uint8_t* e0 = e_row + (pl.col >> 3) * kPlane1;
-          const float* bp = has_bias ? s_bias + pl.col : nullptr;
-          bf16* op = reinterpret_cast<bf16*>(pl.out) + n * pl.ns + hw * 8;
-          bf16* op2 = reinterpret_cast<bf16*>(pl.out2) + n * pl.ns2 + hw * 8;  // only dereferenced by COPY variants
-          bool done = true;
-#define CG_EPI(code, M, A, A2, OA, CP)                                                                          \
-  case code:                                                                                                    \
-    epi_chunk_fast<M, A, A2, OA, CP>(acc[j], e0, eslot, pl.k_mul, pl.k_add, pl.k_add2, bp, op, op2, P.HW8, valid, pl.cnt >> 3); \
-    break;
-          switch (pl.fast) {
-            CG_EPI(0, false, false, false, 0, false) CG_EPI(8, false, false, false, 1, false)
-            CG_EPI(2, false, true, false, 0, false) CG_EPI(10, false, true, false, 1, false)
-            CG_EPI(6, false, true, true, 0, false) CG_EPI(14, false, true, true, 1, false)
-            CG_EPI(1, true, false, false, 0, false) CG_EPI(3, true, true, false, 0, false)
-            default:
-              done = false;
-              if (DUAL) {
-                done = true;
-                switch (pl.fast) {
-                  CG_EPI(48, false, false, false, 2, true) CG_EPI(40, false, false, false, 1, true)
-                  CG_EPI(16, false, false, false, 2, false)
-                  default: done = false; break;
-                }
-              }
-              break;
-          }
-#undef CG_EPI
-          if (done) continue;
+    const ChunkPlan& pl = plan[0];
+    // per-thread part of the pixel offset / validity: the per-tile part is warp-uniform
+    const int moff = P.flat ? 0 : (m >> 3) * W + (m & 7);
+    const bool all_valid = !P.flat && (H & 15) == 0 && (W & 7) == 0;
+    uint32_t as = 0, aphase = 0, es = 0, ephase = 0;
+    int tl_i = 0;
+    (void)tl_i;
+    // The tile loop, parameterised by what happens to the chunk once it is in registers: the dispatch on the chunk's
+    // epilogue variant is done ONCE per kernel (below), not per tile -- every instruction of this loop sits on the warp's
+    // serial per-tile chain, which is what bounds the kernel (ncu: ~210 instructions per warp and tile, 9 cycles each).
+    auto tile_loop = [&](auto&& chunk_fn) {
+      TileWalk walk(P, blockIdx.x, gridDim.x);
+      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, walk.next()) {
+        const TileGeom g = walk.geom(P);
+        bool valid;
+        int n;
+        long long hw;  // pixel index inside the image
+        if (P.flat) {
+          n = g.n + m;
+          hw = 0;
+          valid = n < N;
+        } else {
+          n = g.n;
+          hw = (long long)(g.h0 * W + g.w0 + moff);
+          valid = all_valid || ((g.h0 + (m >> 3) < H) && (g.w0 + (m & 7) < W));
         }
-        if (!valid) continue;
-        float* v = acc[j];
+        if (nE > 0) warp_wait(BAR(B_EFULL + es), ephase, lane);
+        warp_wait(BAR(B_ACCFULL + as), aphase, lane);
+        tc_fence_after();
+        const uint8_t* e_row = sE + (size_t)es * estage + (size_t)m * 16;
+        const uint32_t t_row = tmem_base + as * (uint32_t)Nc + ((uint32_t)(quarter * 32) << 16);
+        float acc[16];
+        __syncwarp();  // .aligned TMEM loads need the whole warp converged
+        tmem_ld16_nowait(t_row + (uint32_t)pl.col, acc);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(B_ACCEMPTY + as));  // accumulator is in registers: MMA may reuse it
+        chunk_fn(acc, n, hw, valid, e_row);
+        if (nE > 0) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_EEMPTY + es));
+          if (++es == nest) { es = 0; ephase ^= 1u; }
+        }
+        if (threadIdx.x == 0 && tl_i < 8) CG_TL(P.tl, 50 + tl_i);
+        ++tl_i;
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    };
+    auto generic_fn = [&](float (&acc)[16], int n, long long hw, bool valid, const uint8_t* e_row) {
+        if (!valid) return;
+        float* v = acc;
         if (has_bias) {
 #pragma unroll
           for (int q = 0; q < 16; q += 4) {
@@ -675,15 +660,54 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             *reinterpret_cast<uint4*>(op) = cg_pack8(v + h8);
           }
         }
+    };
+    if (pl.sgi < 0) {
+      tile_loop([](float (&)[16], int, long long, bool, const uint8_t*) {});  // padding chunk: hand-offs only
+    } else if (pl.fast < 0) {
+      tile_loop(generic_fn);
+    } else {
+      const float* bp = has_bias ? s_bias + pl.col : nullptr;
+#define CG_EPI(code, M, A, A2, OA, CP)                                                                                   \
+  case code:                                                                                                             \
+    tile_loop([&](float (&acc)[16], int n, long long hw, bool valid, const uint8_t* e_row) {                             \
+      epi_chunk_fast<M, A, A2, OA, CP>(acc, e_row + (pl.col >> 3) * kPlane1, eslot, pl.k_mul, pl.k_add, pl.k_add2, bp,   \
+                                       reinterpret_cast<bf16*>(pl.out) + n * pl.ns + hw * 8,                             \
+                                       reinterpret_cast<bf16*>(pl.out2) + n * pl.ns2 + hw * 8, P.HW8, valid, pl.cnt >> 3); \
+    });                                                                                                                  \
+    break;
+      switch (pl.fast) {
+        CG_EPI(0, false, false, false, 0, false) CG_EPI(8, false, false, false, 1, false)
+        CG_EPI(2, false, true, false, 0, false) CG_EPI(10, false, true, false, 1, false)
+        CG_EPI(6, false, true, true, 0, false) CG_EPI(14, false, true, true, 1, false)
+        CG_EPI(1, true, false, false, 0, false) CG_EPI(3, true, true, false, 0, false)
+        default:
+          if (DUAL && pl.fast == 48) {
+            tile_loop([&](float (&acc)[16], int n, long long hw, bool valid, const uint8_t* e_row) {
+              epi_chunk_fast<false, false, false, 2, true>(acc, e_row + (pl.col >> 3) * kPlane1, eslot, pl.k_mul, pl.k_add,
+                                                           pl.k_add2, bp, reinterpret_cast<bf16*>(pl.out) + n * pl.ns + hw * 8,
+                                                           reinterpret_cast<bf16*>(pl.out2) + n * pl.ns2 + hw * 8, P.HW8,
+                                                           valid, pl.cnt >> 3);
+            });
+          } else if (DUAL && pl.fast == 40) {
+            tile_loop([&](float (&acc)[16], int n, long long hw, bool valid, const uint8_t* e_row) {
+              epi_chunk_fast<false, false, false, 1, true>(acc, e_row + (pl.col >> 3) * kPlane1, eslot, pl.k_mul, pl.k_add,
+                                                           pl.k_add2, bp, reinterpret_cast<bf16*>(pl.out) + n * pl.ns + hw * 8,
+                                                           reinterpret_cast<bf16*>(pl.out2) + n * pl.ns2 + hw * 8, P.HW8,
+                                                           valid, pl.cnt >> 3);
+            });
+          } else if (DUAL && pl.fast == 16) {
+            tile_loop([&](float (&acc)[16], int n, long long hw, bool valid, const uint8_t* e_row) {
+              epi_chunk_fast<false, false, false, 2, false>(acc, e_row + (pl.col >> 3) * kPlane1, eslot, pl.k_mul, pl.k_add,
+                                                            pl.k_add2, bp, reinterpret_cast<bf16*>(pl.out) + n * pl.ns + hw * 8,
+                                                            reinterpret_cast<bf16*>(pl.out2) + n * pl.ns2 + hw * 8, P.HW8,
+                                                            valid, pl.cnt >> 3);
+            });
+          } else {
+            tile_loop(generic_fn);
+          }
+          break;
       }
-      if (nE > 0) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(B_EEMPTY + es));
-        if (++es == nest) { es = 0; ephase ^= 1u; }
-      }
-      if (threadIdx.x == 0 && tl_i < 8) CG_TL(P.tl, 50 + tl_i);
-      ++tl_i;
-      if (++as == 2) { as = 0; aphase ^= 1u; }
+#undef CG_EPI
     }
   }
   tc_fence_before();
