@@ -262,14 +262,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int n_epi = 4 * ((Nc + 15) >> 4);              // epilogue warps with a chunk
   // warps on the transform role: about two 16-byte slots of the largest stage per thread, at least the four dedicated ones
   // (more warps than that only add barrier polling: 8 -> 32 @192^2 lost 4 % with twelve warps on a 360-slot stage)
-  int n_xfw = (P.stage_bytes / 16 + 63) / 64;
+  int n_xfw = (P.stage_bytes / 16 + 31) / 32;
   n_xfw = n_xfw < kXfWarps ? kXfWarps : (n_xfw > kXfWarps + kEpiWarps - n_epi ? kXfWarps + kEpiWarps - n_epi : n_xfw);
+  // With two A rings the transform warps form two TEAMS, one per ring (= per tile parity): a stage's pass is a chain of
+  // wait -> loads -> stores -> fence -> arrive whose fixed part outweighs the per-slot part, so two chains in flight beat
+  // one chain with twice the threads.
+  const int n_xf0 = (P.nst0 < P.nst) ? (n_xfw + 1) / 2 : n_xfw;  // warps of team 0 (ring 0); team 1 has the rest
   if (threadIdx.x == 0) CG_TL(P.tl, 32);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < nst; ++i) {
       mbar_init(BAR(B_LANDED + i), 1);
-      mbar_init(BAR(B_AFULL + i), n_xfw);
+      mbar_init(BAR(B_AFULL + i), i < P.nst0 ? n_xf0 : n_xfw - n_xf0);
       mbar_init(BAR(B_AEMPTY + i), 1);
     }
     mbar_init(BAR(B_BFULL), 1);
@@ -436,32 +440,40 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   } else if ((warp >= kXfWarp0 && warp < kMmaWarp2) || (warp < kEpiWarps && warp >= n_epi && warp - n_epi < n_xfw - kXfWarps)) {
     // ------------------------------------------------------------------ transform warps (+ chunk-less epilogue warps)
     if (act != CG_ACT_NONE) {
-      const int nthr = n_xfw * 32;
-      const int xt = (warp < kEpiWarps ? warp - n_epi : (n_xfw - kXfWarps) + warp - kXfWarp0) * 32 + lane;
-      uint32_t st0 = 0, st1 = 0, ph0 = 0, ph1 = 0, lt = 0;
-      const uint32_t len0 = (uint32_t)P.nst0, len1 = (uint32_t)(nst - P.nst0);
+      const int xw = warp < kEpiWarps ? warp - n_epi : (n_xfw - kXfWarps) + warp - kXfWarp0;  // index among the transform warps
       const bool two = P.nst0 < nst;
-      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++lt) {
-        const uint32_t r = two ? (lt & 1u) : 0u, rbase = r ? (uint32_t)P.nst0 : 0u;
+      const int team = (two && xw >= n_xf0) ? 1 : 0;
+      const int nthr = (team ? n_xfw - n_xf0 : n_xf0) * 32;
+      const int xt = (xw - (team ? n_xf0 : 0)) * 32 + lane;
+      const uint32_t rbase = team ? (uint32_t)P.nst0 : 0u;
+      const uint32_t rlen = two ? (team ? (uint32_t)(nst - P.nst0) : (uint32_t)P.nst0) : (uint32_t)nst;
+      const int tstep = (two ? 2 : 1) * (int)gridDim.x;
+      uint32_t st = 0, ph = 0;
+      for (int tile = blockIdx.x + team * (int)gridDim.x; tile < P.ntiles; tile += tstep) {
         for (int c = 0; c < P.nchunks; ++c) {
           const int n16 = (int)(P.src_bytes[P.chunk[c].src] >> 4);  // 16-byte slots the TMA box filled
-          const uint32_t stage = rbase + (r ? st1 : st0), phase = r ? ph1 : ph0;
-          warp_wait(BAR(B_LANDED + stage), phase, lane);
-          uint4* base = reinterpret_cast<uint4*>(sA + stage * stage_bytes);
-          // a stage holds <= 720 16-byte slots = <= 6 per thread: all loads first, then activate + store (one round trip
-          // of shared-memory latency per stage instead of six)
-          uint4 v[6];
+          const uint32_t stage = rbase + st;
+          warp_wait(BAR(B_LANDED + stage), ph, lane);
+          uint4* base = reinterpret_cast<uint4*>(sA + stage * stage_bytes) + xt;
+          // rounds of <= six 16-byte slots per thread (a stage holds <= 720; a team has >= 64 threads): all loads of a round
+          // first, then activate + store -- one round trip of shared-memory latency per round
+          for (int k0 = 0; k0 * nthr < n16; k0 += 6) {
+            uint4 v[6];
 #pragma unroll
-          for (int k = 0; k < 6; ++k)
-            if (xt + k * nthr < n16) v[k] = base[xt + k * nthr];
+            for (int k = 0; k < 6; ++k) {
+              if ((k0 + k) * nthr >= n16) break;  // warp-uniform
+              if (xt + (k0 + k) * nthr < n16) v[k] = base[(k0 + k) * nthr];
+            }
 #pragma unroll
-          for (int k = 0; k < 6; ++k)
-            if (xt + k * nthr < n16) base[xt + k * nthr] = act8(v[k], act);
+            for (int k = 0; k < 6; ++k) {
+              if ((k0 + k) * nthr >= n16) break;
+              if (xt + (k0 + k) * nthr < n16) base[(k0 + k) * nthr] = act8(v[k], act);
+            }
+          }
           fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_AFULL + stage));
-          if (r) { if (++st1 == len1) { st1 = 0; ph1 ^= 1u; } }
-          else if (++st0 == len0) { st0 = 0; ph0 ^= 1u; }
+          if (++st == rlen) { st = 0; ph ^= 1u; }
         }
       }
     }
