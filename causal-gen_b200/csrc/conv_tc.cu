@@ -455,19 +455,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const uint32_t stage = rbase + st;
           warp_wait(BAR(B_LANDED + stage), ph, lane);
           uint4* base = reinterpret_cast<uint4*>(sA + stage * stage_bytes) + xt;
-          // rounds of <= six 16-byte slots per thread (a stage holds <= 720; a team has >= 64 threads): all loads of a round
-          // first, then activate + store -- one round trip of shared-memory latency per round
-          for (int k0 = 0; k0 * nthr < n16; k0 += 6) {
-            uint4 v[6];
+          // `per` 16-byte slots per thread (a stage holds <= 720, a team has >= 64 threads).  Usual case per <= 3: straight
+          // code, all loads first, then activate + store (one round trip of shared-memory latency); else rounds of six.
+          const int per = (n16 + nthr - 1) / nthr;  // warp-uniform
+          if (per <= 3) {
+            uint4 v[3];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) {
-              if ((k0 + k) * nthr >= n16) break;  // warp-uniform
-              if (xt + (k0 + k) * nthr < n16) v[k] = base[(k0 + k) * nthr];
-            }
+            for (int k = 0; k < 3; ++k)
+              if (k < per && xt + k * nthr < n16) v[k] = base[k * nthr];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) {
-              if ((k0 + k) * nthr >= n16) break;
-              if (xt + (k0 + k) * nthr < n16) base[(k0 + k) * nthr] = act8(v[k], act);
+            for (int k = 0; k < 3; ++k)
+              if (k < per && xt + k * nthr < n16) base[k * nthr] = act8(v[k], act);
+          } else {
+            for (int k0 = 0; k0 < per; k0 += 6) {
+              uint4 v[6];
+#pragma unroll
+              for (int k = 0; k < 6; ++k)
+                if (k0 + k < per && xt + (k0 + k) * nthr < n16) v[k] = base[(k0 + k) * nthr];
+#pragma unroll
+              for (int k = 0; k < 6; ++k)
+                if (k0 + k < per && xt + (k0 + k) * nthr < n16) base[(k0 + k) * nthr] = act8(v[k], act);
             }
           }
           fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
