@@ -220,7 +220,8 @@ class BlockLayers:
             self.layers.append(ConvLayer(eng.table, c.weight, c.bias, srcs, act_i,
                                          centre_only=centre and c.weight.shape[2] == 3,
                                          grad_srcs=(grad_srcs if i == 0 else None),
-                                         fwd_operands=(i == len(convs) - 1)))  # only a Block's last conv fuses adds
+                                         fwd_operands=(i == len(convs) - 1),  # only a Block's last conv fuses adds
+                                         res=res))
         self.proj = None
         if hasattr(mod, "width_proj"):
             self.proj = ConvLayer(eng.table, mod.width_proj.weight, mod.width_proj.bias, list(src_logical), L.ACT_NONE)

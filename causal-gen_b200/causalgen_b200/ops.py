@@ -13,9 +13,27 @@ import torch
 from . import _lib as L
 
 
-# The column-folded 3x3 convolution of round 2 (kernel columns on the GEMM-N axis) was parity-green but slower on every layer
-# (profiles/r2n_*, r2u_*) and has been retired from the kernel; cg_conv_fold_ok() answers 0, so `fold` stays 0 below.
-FOLD = False
+# Column-folded 3x3 convolutions (cg_conv_args.fold): wide input, cout <= 32.  Built in round 2, slower THEN because the
+# kernel was bound by its epilogue / transform instruction chains; once those were shortened the wide-input layers became
+# bound by the tensor cores' shared-memory operand reads (profiles/r3q_conv_ablation_final_kernel.txt), which folding cuts
+# to a third.  CAUSALGEN_B200_FOLD=0 switches it off (A/B measurements).
+# A folded tile is 8 rows x 14 valid pixels against 16 x 8 of the nine-tap walk: where that costs many more tiles (48^2: 24
+# against 18 per image) or the input is narrow (32 -> 8 @192^2: two K-blocks, nothing to save) the nine-tap kernel stays
+# (profiles/r3r_conv_ab_folded_final_kernel.txt).  CAUSALGEN_B200_FOLD=0 switches folding off, =2 folds wherever it fits
+# (A/B measurements).
+FOLD = int(os.environ.get("CAUSALGEN_B200_FOLD", "1"))
+
+
+def fold_pays(res: Optional[int], k_channels: int) -> bool:
+    """policy half of the fold decision (the kernel's half is cg_conv_fold_ok): `res` = image side, k_channels = padded
+    channels on the GEMM-K axis"""
+    if FOLD == 2:
+        return True
+    if not FOLD or res is None or k_channels < 64:
+        return False
+    plain = -(-res // 8) * -(-res // 16)
+    folded = -(-res // 14) * -(-res // 8)
+    return folded <= 1.2 * plain
 
 
 def round16(c: int) -> int:
@@ -153,8 +171,9 @@ class ConvLayer:
     def __init__(self, table: PackTable, weight: torch.Tensor, bias: Optional[torch.Tensor],
                  src_logical: Sequence[int], act: int, centre_only: bool = False,
                  grad_srcs: Optional[Sequence[bool]] = None, fwd_operands: bool = True,
-                 n_scale: Optional[torch.Tensor] = None):
-        """fwd_operands=False: no forward launch of this layer fuses an epilogue operand (add / add2 / mul), so its
+                 n_scale: Optional[torch.Tensor] = None, res: Optional[int] = None):
+        """res: side of the (square) image the layer runs on, when known at construction (fold policy, `fold_pays`).
+        fwd_operands=False: no forward launch of this layer fuses an epilogue operand (add / add2 / mul), so its
         GEMM-N chunk need not reserve shared memory for the operand ring (first convs of a Block: huge K, narrow N)"""
         lib = L.load()
         self.weight, self.bias = weight, bias
@@ -170,8 +189,8 @@ class ConvLayer:
         dev = weight.device
         kt = self.taps * sum(self.src_pad) // 16
         # column-folded 3x3 (cg_conv_args.fold): wide input, narrow output -- the case bound by shared-memory operand reads
-        self.fold = int(FOLD and self.taps == 9 and sum(self.src_pad) >= 2 * self.cout_pad and
-                        lib.cg_conv_fold_ok(kt, self.cout_pad, int(fwd_operands)) == 1)
+        self.fold = int(self.taps == 9 and sum(self.src_pad) >= 2 * self.cout_pad and
+                        fold_pays(res, sum(self.src_pad)) and lib.cg_conv_fold_ok(kt, self.cout_pad, int(fwd_operands)) == 1)
         self.nc = self.cout_pad if self.fold else lib.cg_conv_nchunk_ex(kt, self.cout_pad, int(fwd_operands))
         nbytes = lib.cg_packed_weight_bytes_nc(kt, self.cout_pad, self.nc)
         if self.nc <= 0 or nbytes <= 0:
@@ -202,7 +221,7 @@ class ConvLayer:
                 self.nc_bwd.append(0)
                 self.fold_bwd.append(0)
                 continue
-            fb = int(FOLD and self.taps == 9 and self.cout_pad >= 2 * self.src_pad[i] and
+            fb = int(self.taps == 9 and self.cout_pad >= 2 * self.src_pad[i] and fold_pays(res, self.cout_pad) and
                      lib.cg_conv_fold_ok(ktb, self.src_pad[i], 1) == 1)
             self.fold_bwd.append(fb)
             ncb = self.src_pad[i] if fb else lib.cg_conv_nchunk_ex(ktb, self.src_pad[i], 1)

@@ -59,6 +59,8 @@ constexpr int kMaxStages = 32;  // A-ring depth is chosen per launch from the sh
 constexpr int kMinStages = 4;   //   after the resident weight slab (pick_nc guarantees this many)
 constexpr int kPlane3 = 2880;  // 18 rows * 10 px * 16 B
 constexpr int kPlane1 = 2048;  // 16 rows *  8 px * 16 B
+constexpr int kPlaneF = 2560;  // column-folded 3x3: 10 rows * 16 px * 16 B (row halo only, see KParams::fold)
+constexpr int kFoldW = 14;     // valid output pixels per 16-pixel tile row in folded mode
 constexpr int kStageBytes = 4 * kPlane3;  // 11520: largest A stage (32 channels with halo); multiple of 128
 static_assert(kStageBytes / 16 <= 6 * 128, "transform warps cover a stage in six 16-byte slots per thread");
 constexpr int kHdrBytes = 2176;   // barriers (<=1024B) | tmem slot @1024 | bias[256] @1088
@@ -97,6 +99,16 @@ struct alignas(64) KParams {
   int nE, emode;
   int nchunks, ntaps, Nc, nN, ktot16;
   int flat;  // 1: H=W=1, samples are the GEMM rows (128 per tile)
+  // Column-folded 3x3 (wide input, cout <= 32).  A tcgen05.mma with small N is bound by its 4 KB A-operand read from shared
+  // memory (39 clk at N=16, 44 at N=48), and those reads take the shared-memory bandwidth the TMA writes and the activation
+  // pass need: on the final kernel a wide-input layer costs loads + MMAs, not max(loads, MMAs) (profiles/r3q_*: 32 -> 8
+  // @192^2 168 us, 87 us without the MMAs).  Folded, the GEMM-N axis carries the three kernel COLUMNS (N = 3*Nc):
+  // D[p][kx*Nc+co] = sum_{ky,ci} X[p + (ky-1) rows][ci] * W[co][ci][ky][kx], three MMAs (one per kernel row = +256 B start
+  // offset) per K-block instead of nine, and the epilogue forms out(x) = D_0(x-1) + D_1(x) + D_2(x+1) with two lane shuffles
+  // per channel.  Tile = 8 rows x 16 px (TMEM lane = row*16 + px; core matrix = 8 px of a row, SBO 128 B, no column halo in
+  // shared memory), pixels 1..14 of a row are valid outputs (tiles advance by 14 px).
+  int fold;
+  int Ng;    // GEMM-N per CTA: Nc, or 3*Nc when folded
   int nst, nest;       // A-ring / E-ring depths of this launch
   int nst0;            // stages of ring 0 (even local tiles); ring 1 (odd tiles) has nst - nst0; nst0 == nst: one ring
   int stage_bytes;     // bytes of one A stage (largest source box)
@@ -140,6 +152,7 @@ struct TileWalk {
   __device__ __forceinline__ TileGeom geom(const KParams& P) const {
     TileGeom g;
     if (P.flat) { g.n = n * 128; g.h0 = g.w0 = 0; }
+    else if (P.fold) { g.n = n; g.h0 = ty * 8; g.w0 = tx * kFoldW - 1; }
     else { g.n = n; g.h0 = ty * 16; g.w0 = tx * 8; }
     return g;
   }
@@ -311,7 +324,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) CG_TL(P.tl, 33);
   const bool k3 = P.a.ksize == 3;
-  const int plane = k3 ? kPlane3 : kPlane1;
+  const bool fold = P.fold != 0;
+  const int plane = fold ? kPlaneF : (k3 ? kPlane3 : kPlane1);
+  const int Ng = P.Ng;
   const int H = P.a.H, W = P.a.W, N = P.a.N;
 
   if (warp == kMmaWarp || warp == kMmaWarp2) {
@@ -330,13 +345,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       (void)tl_i;
       // Descriptors are built once; per MMA only the 14-bit start-address field (low word) advances
       // (all offsets are multiples of 16 B).
-      const uint32_t a_sbo = k3 ? 160u : 128u;
+      const uint32_t a_sbo = (k3 && !fold) ? 160u : 128u;
       const uint64_t a_d = umma_desc(cg_smem_u32(sA), (uint32_t)plane, a_sbo);
-      const uint64_t b_d = umma_desc(cg_smem_u32(sB), (uint32_t)Nc * 16u, 128u);
+      const uint64_t b_d = umma_desc(cg_smem_u32(sB), (uint32_t)Ng * 16u, 128u);
       const uint32_t a_hi = (uint32_t)(a_d >> 32), b_hi = (uint32_t)(b_d >> 32);
       const uint32_t a_lo0 = (uint32_t)a_d, b_lo0 = (uint32_t)b_d;
       auto D64 = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
-      const uint32_t b_step16 = (uint32_t)Nc * 2u;  // (Nc*32 B per K-block) >> 4
+      const uint32_t b_step16 = (uint32_t)Ng * 2u;  // (Ng*32 B per K-block) >> 4
       const uint32_t plane2_16 = (uint32_t)(2 * plane) >> 4;
       const uint32_t stage16 = (uint32_t)stage_bytes >> 4;
       const uint32_t idesc = P.idesc;
@@ -353,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       for (int tile = blockIdx.x + (two ? (int)iw * (int)gridDim.x : 0); tile < P.ntiles && (two || iw == 0); tile += tstep) {
         mbar_wait(BAR(B_ACCEMPTY + as), aphase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * (uint32_t)Nc;
+        const uint32_t d_tmem = tmem_base + as * (uint32_t)Ng;
         uint32_t accum = 0;
         for (int c = 0; c < P.nchunks; ++c) {
           const Chunk ch = P.chunk[c];
@@ -364,7 +379,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           uint32_t alo = a_lo0 + gs * stage16;
           uint32_t blo = b_lo0 + (uint32_t)ch.kbase * b_step16;
           for (int j = 0; j < ch.nc16 && !(P.dbg & 4); ++j) {
-            if (k3) {
+            if (fold) {
+#pragma unroll
+              for (int t = 0; t < 3; ++t) {  // kernel rows: +256 B (one 16-pixel row) per tap, columns live on GEMM-N
+                tc_mma_bf16(d_tmem, D64(a_hi, alo + (uint32_t)(t * 16)), D64(b_hi, blo), idesc, accum);
+                accum = 1;
+                blo += b_step16;
+              }
+            } else if (k3) {
 #pragma unroll
               for (int t = 0; t < 9; ++t) {
                 tc_mma_bf16(d_tmem, D64(a_hi, alo + (uint32_t)((t / 3) * 10 + (t % 3))), D64(b_hi, blo), idesc, accum);
@@ -406,7 +428,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t rlen = two ? (pw ? (uint32_t)(nst - P.nst0) : (uint32_t)P.nst0) : (uint32_t)nst;
       const uint32_t lstep = two ? 2u : 1u;
       uint32_t es = two ? pw : 0u, ephase = 0, lt = two ? pw : 0u, st = 0, ph = 0;
-      const int halo_y = k3 ? 1 : 0, halo_x = halo_y;
+      const int halo_y = k3 ? 1 : 0, halo_x = (k3 && !fold) ? 1 : 0;
       const int first = blockIdx.x + (int)lt * (int)gridDim.x, tstep = (int)lstep * (int)gridDim.x;
       TileWalk walk(P, first, tstep);
       for (int tile = first; tile < P.ntiles; tile += tstep, lt += lstep, walk.next()) {
@@ -559,8 +581,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     const ChunkPlan& pl = plan[0];
     // per-thread part of the pixel offset / validity: the per-tile part is warp-uniform
-    const int moff = P.flat ? 0 : (m >> 3) * W + (m & 7);
-    const bool all_valid = !P.flat && (H & 15) == 0 && (W & 7) == 0;
+    const int mrow = fold ? (m >> 4) : (m >> 3), mpx = fold ? (m & 15) : (m & 7);  // position of the lane inside the tile
+    const int moff = P.flat ? 0 : mrow * W + mpx;
+    const bool all_valid = !P.flat && !fold && (H & 15) == 0 && (W & 7) == 0;
+    const bool px_ok = !fold || (mpx >= 1 && mpx <= kFoldW);  // folded: pixels 0 and 15 of a tile row are halo
     uint32_t as = 0, aphase = 0, es = 0, ephase = 0;
     int tl_i = 0;
     (void)tl_i;
@@ -581,17 +605,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         } else {
           n = g.n;
           hw = (long long)(g.h0 * W + g.w0 + moff);
-          valid = all_valid || ((g.h0 + (m >> 3) < H) && (g.w0 + (m & 7) < W));
+          valid = all_valid || (px_ok && (g.h0 + mrow < H) && (g.w0 + mpx < W));
         }
         if (nE > 0) warp_wait(BAR(B_EFULL + es), ephase, lane);
         warp_wait(BAR(B_ACCFULL + as), aphase, lane);
         tc_fence_after();
         const uint8_t* e_row = sE + (size_t)es * estage + (size_t)m * 16;
-        const uint32_t t_row = tmem_base + as * (uint32_t)Nc + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t t_row = tmem_base + as * (uint32_t)Ng + ((uint32_t)(quarter * 32) << 16);
         float acc[16];
         __syncwarp();  // .aligned TMEM loads need the whole warp converged
-        tmem_ld16_nowait(t_row + (uint32_t)pl.col, acc);
-        tmem_ld_wait();
+        if (fold) {
+          // out(x) = D_0(x-1) + D_1(x) + D_2(x+1): the three column partials sit Nc columns apart, lanes of a 16-pixel row
+          // are neighbours (pixels 0 and 15 are halo).  One partial at a time keeps 32 values live, not 48.
+          float side[16];
+          tmem_ld16_nowait(t_row + (uint32_t)(Nc + pl.col), acc);
+          tmem_ld16_nowait(t_row + (uint32_t)pl.col, side);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[i] += __shfl_up_sync(0xffffffffu, side[i], 1);
+          tmem_ld16_nowait(t_row + (uint32_t)(2 * Nc + pl.col), side);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[i] += __shfl_down_sync(0xffffffffu, side[i], 1);
+        } else {
+          tmem_ld16_nowait(t_row + (uint32_t)pl.col, acc);
+          tmem_ld_wait();
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(B_ACCEMPTY + as));  // accumulator is in registers: MMA may reuse it
@@ -816,10 +855,14 @@ extern "C" int32_t cg_conv_nchunk_ex(int32_t ktot16, int32_t cout, int32_t want_
   return pick_nc(ktot16, cout, nullptr, want_e);
 }
 extern "C" int32_t cg_conv_nchunk(int32_t ktot16, int32_t cout) { return pick_nc(ktot16, cout, nullptr, 1); }
-// The column-folded 3x3 mode of round 2 (kernel columns on the GEMM-N axis, 3 MMAs per K-block, shuffle-add epilogue) was
-// parity-green but slower on every layer (profiles/r2n_*, r2u_*) and has been retired; the entry stays so that callers built
-// against the round-2 header keep linking, and always answers "no".
-extern "C" int32_t cg_conv_fold_ok(int32_t, int32_t, int32_t) { return 0; }
+// 1 when a 3x3 conv with `ktot16` K-blocks (9 taps * sum(C)/16) and `cout` padded output channels can run column-folded
+// (cg_conv_args.fold): one GEMM-N chunk (nc == cout <= 32) whose weight slab -- same bytes as the 9-tap image -- and, with
+// want_e, the epilogue-operand ring fit next to the minimum input ring.
+extern "C" int32_t cg_conv_fold_ok(int32_t ktot16, int32_t cout, int32_t want_e) {
+  if (cout <= 0 || cout > 32 || cout % 16 != 0 || ktot16 % 9 != 0) return 0;
+  const int room = kSmemMax - kHdrBytes - kMinStages * kStageBytes;
+  return ktot16 * cout * 32 + (want_e ? e_bytes_min(cout) : 0) <= room ? 1 : 0;
+}
 
 extern "C" int64_t cg_packed_weight_bytes_nc(int32_t ktot16, int32_t cout, int32_t nc) {
   if (nc <= 0 || nc % 16 != 0 || nc > kMaxNc) return -1;
@@ -844,8 +887,11 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
   KParams kp;
   kp.a = *a;
   kp.flat = flat ? 1 : 0;
-  CG_REQUIRE(a->fold == 0, "cg_conv2d: the column-folded mode was retired (cg_conv_fold_ok answers 0)");
-  kp.ntaps = a->ksize * a->ksize;
+  kp.fold = a->fold ? 1 : 0;
+  CG_REQUIRE(!kp.fold || (a->ksize == 3 && !flat && a->nc == a->cout && a->cout <= 32),
+             "cg_conv2d: fold needs ksize 3, a spatial image and nc == cout <= 32 (ksize %d, nc %d, cout %d)", a->ksize, a->nc,
+             a->cout);
+  kp.ntaps = kp.fold ? 3 : a->ksize * a->ksize;  // taps on the K axis
   kp.HW8 = (long long)a->H * a->W * 8;
   const int halo = a->ksize == 3 ? 2 : 0;
   int nchunks = 0, c16 = 0;
@@ -857,10 +903,11 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
     const int box_c8 = src.C / 8 < 4 ? src.C / 8 : 4;
     const int c8_phys = src.c8 > 0 ? src.c8 : src.C / 8;  // octets stored; the box may run past them (zero fill)
     CG_REQUIRE(c8_phys <= src.C / 8 && c8_phys * 8 + 8 > src.C - 8, "cg_conv2d: src %d c8=%d vs C=%d", s, c8_phys, src.C);
-    int rc = cg_make_planar_map(&kp.src_map[s], src.ptr, src.ns, a->N, a->H, a->W, c8_phys, kp.flat, (8 + halo) * 8, 16 + halo,
-                                box_c8);
+    int rc = kp.fold ? cg_make_planar_map(&kp.src_map[s], src.ptr, src.ns, a->N, a->H, a->W, c8_phys, 0, 16 * 8, 10, box_c8)
+                     : cg_make_planar_map(&kp.src_map[s], src.ptr, src.ns, a->N, a->H, a->W, c8_phys, kp.flat, (8 + halo) * 8,
+                                          16 + halo, box_c8);
     if (rc != CG_OK) return rc;
-    kp.src_bytes[s] = (uint32_t)box_c8 * (flat ? kPlane1 : (a->ksize == 3 ? kPlane3 : kPlane1));
+    kp.src_bytes[s] = (uint32_t)box_c8 * (kp.fold ? kPlaneF : (flat ? kPlane1 : (a->ksize == 3 ? kPlane3 : kPlane1)));
     for (int c0 = 0; c0 < src.C; c0 += 32) {
       CG_REQUIRE(nchunks < kMaxChunks, "cg_conv2d: too many K chunks");
       int n16 = (src.C - c0 >= 32) ? 2 : 1;
@@ -873,7 +920,7 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
   if (a->nc > 0) {  // chunk the caller packed the weights for (cg_conv_nchunk_ex)
     CG_REQUIRE(a->nc % 16 == 0 && a->nc <= kMaxNc, "cg_conv2d: nc=%d", a->nc);
     kp.Nc = a->nc;
-    const int ng = kp.Nc;
+    const int ng = kp.fold ? 3 * kp.Nc : kp.Nc;
     const int room = kSmemMax - kHdrBytes - kMinStages * kStageBytes;
     kp.emode = (kp.ktot16 * ng * 32 + e_bytes_min(kp.Nc) <= room) ? 1 : 0;
     CG_REQUIRE(kp.ktot16 * ng * 32 <= room, "cg_conv2d: weight slab of K=%d x N=%d does not fit", kp.ktot16 * 16, ng);
@@ -882,7 +929,8 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
   }
   CG_REQUIRE(kp.Nc >= 16, "cg_conv2d: K=%d too large for a resident weight slab", kp.ktot16 * 16);
   kp.nN = (a->cout + kp.Nc - 1) / kp.Nc;
-  kp.slab_bytes = (uint32_t)kp.ktot16 * kp.Nc * 32u;
+  kp.Ng = kp.fold ? 3 * kp.Nc : kp.Nc;
+  kp.slab_bytes = (uint32_t)kp.ktot16 * kp.Ng * 32u;
   for (int s = 0; s < a->nseg; ++s) {
     const cg_seg& sg = a->seg[s];
     CG_REQUIRE(sg.ptr != nullptr && ((uintptr_t)sg.ptr & 15) == 0, "cg_conv2d: seg %d null/unaligned", s);
@@ -906,7 +954,7 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
       for (int kind = 0; kind < 3 && kp.nE < kESlots; ++kind) {
         if (ptrs[kind] == nullptr) continue;
         int rc = cg_make_planar_map(&kp.e_map[kp.nE], ptrs[kind], nss[kind], a->N, a->H, a->W, sg.cn / 8, kp.flat,
-                                    64, 16, kp.Nc / 8);
+                                    kp.fold ? 128 : 64, kp.fold ? 8 : 16, kp.Nc / 8);
         if (rc != CG_OK) return rc;
         kp.eop[kp.nE++] = EOp{s, kind, sg.c0 / 8};
       }
@@ -918,13 +966,13 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
     kp.tiles_per_img = 1;
     kp.ntiles = (a->N + 127) / 128;
   } else {
-    kp.tiles_x = (a->W + 7) / 8;
-    kp.tiles_per_img = kp.tiles_x * ((a->H + 15) / 16);
+    kp.tiles_x = kp.fold ? (a->W + kFoldW - 1) / kFoldW : (a->W + 7) / 8;
+    kp.tiles_per_img = kp.tiles_x * (kp.fold ? (a->H + 7) / 8 : (a->H + 15) / 16);
     kp.ntiles = a->N * kp.tiles_per_img;
   }
-  kp.idesc = umma_idesc_bf16(128, kp.Nc, 0, 0);
+  kp.idesc = umma_idesc_bf16(128, kp.Ng, 0, 0);
   uint32_t cols = 32;
-  while (cols < 2u * kp.Nc) cols <<= 1;
+  while (cols < 2u * kp.Ng) cols <<= 1;
   kp.tmem_cols = cols;
   // ring depths: all shared memory left after the weight slab is prefetch distance.  E stages cover as many
   // tiles ahead as the A ring does (bytes per tile: nchunks A stages + nE staged operands).

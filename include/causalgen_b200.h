@@ -95,9 +95,11 @@ typedef struct {
   const float* bias;   /* fp32 [bias_n] or NULL */
   int32_t bias_n;      /* valid bias entries (logical output channels); the rest is 0 */
   int32_t nc;          /* GEMM-N chunk the weights were packed for (cg_conv_nchunk_ex); 0 = cg_conv_nchunk(ktot16, cout) */
-  int32_t fold;        /* must be 0.  (Round 2 carried a "column-folded" 3x3 mode here -- the three kernel columns side by side
-                          on the GEMM-N axis, 3 MMAs per K-block, shuffle-add epilogue.  It was parity-green but slower on every
-                          layer because the kernel is not bound by its MMAs, profiles/r2n_*, r2u_*, and has been retired.) */
+  int32_t fold;        /* 1: the weights were packed with cg_pack_desc.fold = 1 ("column-folded" 3x3 conv, wide inputs and
+                          cout <= 32): the three kernel columns sit side by side on the GEMM-N axis (N = 3*cout), each input
+                          tile is multiplied once per kernel ROW (3 MMAs per K-block instead of 9) and the epilogue adds the
+                          three column partials of the left / same / right pixel.  Same result, a third of the shared-
+                          memory operand reads.  Requires ksize == 3 and nc == cout <= 32 */
   int32_t _pad2;
 } cg_conv_args;
 
@@ -111,7 +113,8 @@ int32_t cg_conv_nchunk(int32_t ktot16, int32_t cout);
 /* same with a hint: want_e = 0 when no launch of this pack has fused epilogue operands (add / add2 / mul), so the chunk
  * need not leave shared memory for the operand ring (first convs of a Block: wide K, narrow N) */
 int32_t cg_conv_nchunk_ex(int32_t ktot16, int32_t cout, int32_t want_e);
-/* always 0: the column-folded mode (cg_conv_args.fold) was retired; kept so that round-2 callers keep linking */
+/* 1 when the 3x3 conv (ktot16 = 9 * sum(C)/16 K-blocks, cout padded output channels) can run column-folded
+ * (cg_conv_args.fold / cg_pack_desc.fold, nc = cout); want_e as above */
 int32_t cg_conv_fold_ok(int32_t ktot16, int32_t cout, int32_t want_e);
 /* bytes of the packed-weight image for a conv with `ktot16` K-blocks of 16 (= taps * sum(C)/16) */
 int64_t cg_packed_weight_bytes(int32_t ktot16, int32_t cout);

@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -47,6 +49,21 @@ def test_struct_layouts_match_the_header_sizes():
     # a huge-K first conv of a Block (posterior, 272 -> 32 channels, 3x3): no operand ring needed -> one chunk of 32
     assert lib.cg_conv_nchunk_ex(9 * 17, 32, 0) == 32 and lib.cg_conv_nchunk_ex(9 * 17, 32, 1) == 16
     assert lib.cg_packed_weight_bytes_nc(9 * 17, 32, 32) == 9 * 17 * 32 * 32
+    # column-folded 3x3 (cg_conv_args.fold): one GEMM-N chunk of <= 32 output channels, nine-tap K, slab must fit
+    assert lib.cg_conv_fold_ok(9 * 4, 16, 0) == 1 and lib.cg_conv_fold_ok(9 * 8, 32, 1) == 1
+    assert lib.cg_conv_fold_ok(9 * 4, 48, 0) == 0 and lib.cg_conv_fold_ok(4, 16, 0) == 0
+    assert lib.cg_conv_fold_ok(9 * 40, 32, 1) == 0          # 640 input channels: the slab leaves no room for the rings
+
+
+def test_fold_policy_follows_the_measured_layers():
+    """ops.fold_pays: the A/B of profiles/r3r_conv_ab_folded_final_kernel.txt as a rule (wide K, tile count within 20 %)"""
+    from causalgen_b200 import ops
+    if ops.FOLD != 1:
+        pytest.skip("CAUSALGEN_B200_FOLD overrides the policy")
+    assert ops.fold_pays(96, 64) and ops.fold_pays(24, 128) and ops.fold_pays(192, 64) and ops.fold_pays(12, 160)
+    assert not ops.fold_pays(48, 96) and not ops.fold_pays(48, 208)     # 24 folded tiles against 18 per image
+    assert not ops.fold_pays(192, 32)                                    # two K-blocks: nothing to save
+    assert not ops.fold_pays(None, 256)                                  # resolution unknown at construction
 
 
 def test_compute_entry_fails_loudly_without_b200():

@@ -111,6 +111,63 @@ def test_conv_forward(case):
         assert to_nchw(out.t, out.t.shape[1] * 8)[:, cout:].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("case", [(2, 30, 45, [64], 0, 32, 3, 1),          # H != W, W not a multiple of 14
+                                  (3, 13, 14, [32], 0, 16, 3, 2),          # exactly one 14-pixel tile per row, GELU input
+                                  (2, 17, 29, [96, 16], 4, 24, 3, 1),      # three K-concatenated sources, cout padded to 32
+                                  (8, 96, 96, [64], 0, 16, 3, 1),          # BASELINE shape, many tiles per CTA (two issuers)
+                                  (1, 192, 192, [32], 0, 8, 3, 1)])
+def test_conv_column_folded_matches_plain(case):
+    """cg_conv_args.fold: kernel columns on the GEMM-N axis + shuffle-add epilogue == the nine-tap kernel == F.conv2d
+    (src/vae.py:53-56 first conv of a Block), forward and the data gradient of the mirrored (narrow -> wide) conv."""
+    from causalgen_b200 import ops
+    from causalgen_b200.ops import SegSpec, View, new_act, phys
+    N, H, W, chans, ctx, cout, k, act = case
+    default = ops.FOLD
+    try:
+        ops.FOLD = 0
+        layer0, _, out0, _, _, _ = run_conv(*case, seed=13)
+        ops.FOLD = 2  # fold wherever the kernel can (the policy of ops.fold_pays is a speed matter, tested on the CPU)
+        layer, views, out, ref, w, b = run_conv(*case, seed=13)
+        assert layer.fold == 1 and layer0.fold == 0, "the case must exercise both paths"
+        _folded_checks(case, layer, views, out, out0, ref)
+    finally:
+        ops.FOLD = default
+
+
+def _folded_checks(case, layer, views, out, out0, ref):
+    from causalgen_b200 import ops
+    from causalgen_b200.ops import SegSpec, View, new_act, phys
+    N, H, W, chans, ctx, cout, k, act = case
+    got, plain = to_nchw(out.t, cout), to_nchw(out0.t, cout)
+    assert_close(got, ref, 1e-2, f"folded fwd {case}")
+    d = (got - plain).abs().max().item() / (ref.abs().max().item() + 1e-6)
+    print(f"fold[{case}] folded vs nine-tap max rel diff {d:.3g} (bf16 rounding of the same fp32 sums)")
+    assert d <= 8e-3  # one bf16 ulp of the largest output: the fp32 partial sums are only re-associated
+    # fused epilogue operands on the folded path: ReLU' mask + accumulate (the data-gradient use), in place
+    res = View(nhwc_bf16(rnd(N, cout, H, W, seed=60)), phys(cout))
+    msk = View(nhwc_bf16(rnd(N, cout, H, W, seed=61)), phys(cout))
+    want = ref * (to_nchw(msk.t, cout) > 0) + to_nchw(res.t, cout)
+    layer.forward(views, [SegSpec(res, 0, add=res, mul=msk, mul_act=1)], N, H, W)(stream())
+    torch.cuda.synchronize()
+    assert_close(to_nchw(res.t, cout), want, 1e-2, f"folded mul+add {case}")
+    if res.t.shape[1] * 8 > cout:
+        assert to_nchw(out.t, out.t.shape[1] * 8)[:, cout:].abs().max().item() == 0.0
+    # data gradient of the mirrored conv cout -> sum(chans) is a wide -> narrow conv when run backwards
+    if len(chans) == 1 and not ctx:
+        table = ops.PackTable(DEV)
+        wm = rnd(chans[0], cout, 3, 3, scale=1.0 / math.sqrt(cout * 9), seed=70)   # conv cout -> chans[0]
+        lm = ops.ConvLayer(table, wm, None, [cout], 0)
+        table.launch(stream())
+        if chans[0] >= 2 * phys(cout):
+            assert lm.fold_bwd[0] == 1
+        dy = View(nhwc_bf16(rnd(N, chans[0], H, W, seed=71)), phys(chans[0]))
+        dx = new_act(N, H, W, cout, DEV)
+        lm.dgrad(0, dy, SegSpec(dx, 0), N, H, W)(stream())
+        torch.cuda.synchronize()
+        refd = F.conv_transpose2d(to_nchw(dy.t, chans[0]), wm.to(torch.bfloat16).float(), padding=1)
+        assert_close(to_nchw(dx.t, cout), refd, 1e-2, f"folded dgrad {case}")
+
+
 def test_conv_segments_add_and_fp32_split():
     from causalgen_b200.ops import SegSpec, View, new_act
     N, H, W = 2, 12, 12

@@ -52,7 +52,7 @@ for name, H, cins, cout, k, act, epi in CASES:
         t = planar_from_nchw(torch.randn(N, phys(c), H, H, generator=g).to(DEV))
         views.append(View(t, phys(c), 0, c))
     w = (torch.randn(cout, sum(cins), k, k, generator=g) * 0.05).to(DEV); b = torch.zeros(cout, device=DEV)
-    table = PackTable(DEV); layer = ConvLayer(table, w, b, cins, act); table.launch(s())
+    table = PackTable(DEV); layer = ConvLayer(table, w, b, cins, act, res=H); table.launch(s())
     out = new_act(N, H, H, cout, DEV)
     x1 = View(planar_from_nchw(torch.randn(N, phys(cout), H, H, generator=g).to(DEV)), phys(cout))
     x2 = View(planar_from_nchw(torch.randn(N, phys(cout), H, H, generator=g).to(DEV)), phys(cout))
