@@ -29,7 +29,19 @@ from .ops import ConvLayer, PackTable, SegSpec, View, new_act, round16
 TRACE_ONLY = os.environ.get("CAUSALGEN_B200_TRACE_ONLY", "0") == "1"
 # Weight-gradient launches only feed the flat gradient bucket, so they are forked onto side streams (graph
 # branches under capture) and overlap the latency-bound data-gradient chain.  0 = everything on one stream.
-SIDE_STREAMS = int(os.environ.get("CAUSALGEN_B200_SIDE_STREAMS", "2"))
+SIDE_STREAMS = int(os.environ.get("CAUSALGEN_B200_SIDE_STREAMS", "6"))
+# The two lanes carry the dependent chain of the step (every conv waits for its predecessor); the weight gradients on
+# the pool streams are filler.  The lanes run at high stream priority (the capture stream of `Trainer` and the auxiliary
+# lane), so a lane kernel's CTAs are placed before queued weight-gradient CTAs; the deferred weight gradients then need a
+# wider pool to fill the gaps.  Measured together (profiles/r4b_streams_priority_ab.txt): priority with 2 pool streams
+# loses 1 % (batch 128) / 5 % (batch 32), with 6 it is neutral at batch 128 and +3 % at batch 32.
+# CAUSALGEN_B200_PRIO=0 restores equal priorities.
+LANE_PRIORITY = -1 if os.environ.get("CAUSALGEN_B200_PRIO", "1") == "1" else 0
+
+
+def lane_stream() -> "torch.cuda.Stream":
+    """a stream for one of the two lanes (capture stream of the Trainer graphs, auxiliary lane)"""
+    return torch.cuda.Stream(priority=LANE_PRIORITY)
 
 
 class PyOp:
@@ -134,7 +146,7 @@ class Program:
             return
         if self.sides is None:
             self.sides = [torch.cuda.Stream() for _ in range(SIDE_STREAMS)]
-            self.aux = torch.cuda.Stream()
+            self.aux = lane_stream()
         streams = [main, self.aux] + self.sides          # stream ids of plan_streams(): 0 main, 1 aux, 2.. pool
         raw = [s, self.aux.cuda_stream] + [st.cuda_stream for st in self.sides]
         events = {}

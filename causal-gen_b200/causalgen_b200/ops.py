@@ -21,14 +21,21 @@ from . import _lib as L
 # against 18 per image) or the input is narrow (32 -> 8 @192^2: two K-blocks, nothing to save) the nine-tap kernel stays
 # (profiles/r3r_conv_ab_folded_final_kernel.txt).  CAUSALGEN_B200_FOLD=0 switches folding off, =2 folds wherever it fits
 # (A/B measurements).
-FOLD = int(os.environ.get("CAUSALGEN_B200_FOLD", "1"))
+_FOLD_ENV = os.environ.get("CAUSALGEN_B200_FOLD", "1")
+FOLD = int(_FOLD_ENV) if _FOLD_ENV.isdigit() else 3
+# debugging aid: CAUSALGEN_B200_FOLD="res=24+96;kmin=64;dir=fb" folds exactly the layers at these resolutions with at least
+# kmin K channels, forward (f) and / or data-gradient (b) launches
+_FOLD_SPEC = dict(kv.split("=") for kv in _FOLD_ENV.split(";")) if FOLD == 3 else {}
 
 
-def fold_pays(res: Optional[int], k_channels: int) -> bool:
+def fold_pays(res: Optional[int], k_channels: int, bwd: bool = False) -> bool:
     """policy half of the fold decision (the kernel's half is cg_conv_fold_ok): `res` = image side, k_channels = padded
     channels on the GEMM-K axis"""
     if FOLD == 2:
         return True
+    if FOLD == 3:
+        return (("b" if bwd else "f") in _FOLD_SPEC.get("dir", "fb") and k_channels >= int(_FOLD_SPEC.get("kmin", "0")) and
+                ("res" not in _FOLD_SPEC or str(res) in _FOLD_SPEC["res"].split("+")))
     if not FOLD or res is None or k_channels < 64:
         return False
     plain = -(-res // 8) * -(-res // 16)
@@ -221,7 +228,7 @@ class ConvLayer:
                 self.nc_bwd.append(0)
                 self.fold_bwd.append(0)
                 continue
-            fb = int(self.taps == 9 and self.cout_pad >= 2 * self.src_pad[i] and fold_pays(res, self.cout_pad) and
+            fb = int(self.taps == 9 and self.cout_pad >= 2 * self.src_pad[i] and fold_pays(res, self.cout_pad, bwd=True) and
                      lib.cg_conv_fold_ok(ktb, self.src_pad[i], 1) == 1)
             self.fold_bwd.append(fb)
             ncb = self.src_pad[i] if fb else lib.cg_conv_nchunk_ex(ktb, self.src_pad[i], 1)

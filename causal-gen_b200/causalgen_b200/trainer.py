@@ -25,7 +25,7 @@ import torch
 
 from . import _lib as L
 from . import dp
-from .engine import TRACE_ONLY, Engine, no_grad_param_ids, ordered_params
+from .engine import TRACE_ONLY, Engine, lane_stream, no_grad_param_ids, ordered_params
 from .hvae import HVAE, _stream
 
 
@@ -146,7 +146,7 @@ class Trainer:
         torch.cuda.synchronize()
         saved = (self.seed_ctr.clone(), self.eng.flat_grad.clone())
         self.g_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_fb):
+        with torch.cuda.graph(self.g_fb, stream=lane_stream()):  # lane 0 of the program = the capture stream
             self._fwd_bwd()
         self.g_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_opt):

@@ -1,6 +1,11 @@
 // 7x7 stem convolution (reference src/vae.py:104-110,126): fp32 NCHW image (1 or 3 channels) ->
-// bf16 NHWC features, and its weight/bias gradient.  Cin is 1 or 3, far too thin for the tensor
-// cores (K = 49..147 with no reuse across Cin), so this is a direct shared-memory-tiled kernel.
+// bf16 planar features, and its weight/bias gradient.
+//   Cin = 1 (UKBB, MIMIC, Morpho-MNIST): warp-level mma.sync kernels with a split-bf16 (hi + lo) image and weights, fp32
+//            accurate (second half of this file; 0.5 ms -> HBM-bound at 128 x 192^2).
+//   Cin = 3 (Colour-MNIST, 32x32): direct shared-memory-tiled fp32 kernels (first half; also the A/B baseline of the
+//            mma kernels, CAUSALGEN_B200_STEM_MMA=0).
+#include <cstdlib>
+
 #include "cg_common.cuh"
 
 namespace {
@@ -143,6 +148,254 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
   if (db != nullptr && threadIdx.x >= 224 && (int)threadIdx.x - 224 < Cout) atomicAdd(db + threadIdx.x - 224, bsum);
 }
 
+
+// ------------------------------------------------------------------ tensor-core stem (Cin = 1)
+// The direct kernels above are FMA-bound (7*7*32 fp32 FMAs per pixel: 0.5 ms at 128 x 192^2 against 50 us of HBM time).
+// For the single-channel configs (UKBB / MIMIC / Morpho-MNIST) the same sums run on warp-level mma.sync m16n8k16:
+//   K axis   k = ky*8 + kx (kx = 7 and ky = 7 are zero padding): a K-block of 16 = two kernel rows, and the two K values a
+//            thread holds in one fragment register (kx = 2t, 2t+1) are NEIGHBOURING pixels of the image row -- one 32-bit
+//            shared-memory load.  Odd pixel positions would be misaligned, so the tile is stored twice, the second copy
+//            shifted by one pixel.
+//   fp32     the image and the weights are split x = hi + lo into two bf16 (2^-17 relative), products hi*hi + lo*hi +
+//            hi*lo accumulate in fp32: the result matches the fp32 direct kernel to ~1e-5, no bf16 rounding of the input.
+//   forward  M = 16 pixels of a tile row, N = output channels, A from the image tile, B (weights) in registers.
+//   wgrad    M = output channels (dY via ldmatrix.trans: an octet of a pixel is one 16-byte row), N = kx (one 8-wide
+//            block per ky), K = 16 pixels of a tile row; the bias gradient is one more n-block against a ones fragment.
+// tcgen05 does not fit: K = 49 taps from ONE channel cannot be expressed as a shared-memory operand descriptor (the
+// taps of neighbouring pixels overlap), it would need a materialised im2col tile.
+constexpr int kSxRows = 23, kSxPitch = 24;                    // image tile incl. halo: rows 0..21 / cols 0..21 real, rest 0
+constexpr int kSxElems = kSxRows * kSxPitch;                  // 552
+constexpr int kSxCopy = kSxElems;                             // elements of one copy
+constexpr int kSxPre = (kSxElems + 255) / 256;                // prefetch registers per thread (3)
+
+__device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack_bf16(bf16 a, bf16 b) {  // a = low half (lower K index)
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+// image tile of (n, h0, w0) -> registers (fp32, zero outside the image and in the padding row / column)
+__device__ __forceinline__ void stem_tile_fetch(const float* __restrict__ x, int R, int n, int h0, int w0, float (&pre)[kSxPre]) {
+#pragma unroll
+  for (int j = 0; j < kSxPre; ++j) {
+    const int i = threadIdx.x + 256 * j;
+    const int r = i / kSxPitch, c = i - r * kSxPitch;
+    const int hh = h0 - 3 + r, ww = w0 - 3 + c;
+    pre[j] = (i < kSxElems && r < 22 && c < 22 && hh >= 0 && hh < R && ww >= 0 && ww < R)
+                 ? __ldg(x + ((long long)n * R + hh) * R + ww) : 0.f;
+  }
+}
+// registers -> shared memory: s[(hl*2 + copy) * kSxCopy + r*kSxPitch + c], copy 1 shifted left by one pixel
+__device__ __forceinline__ void stem_tile_store(bf16* s, const float (&pre)[kSxPre]) {
+#pragma unroll
+  for (int j = 0; j < kSxPre; ++j) {
+    const int i = threadIdx.x + 256 * j;
+    if (i >= kSxElems) break;
+    bf16 hi, lo;
+    split_bf16(pre[j], hi, lo);
+    s[i] = hi;
+    s[2 * kSxCopy + i] = lo;
+    if (i % kSxPitch != 0) {
+      s[kSxCopy + i - 1] = hi;
+      s[3 * kSxCopy + i - 1] = lo;
+    }
+  }
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(256, 2) stem_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                              const float* __restrict__ b, bf16* __restrict__ y, int N, int R,
+                                                              long long y_ns) {
+  constexpr int NB = COUT / 8;
+  __shared__ __align__(16) bf16 s_x[4 * kSxCopy];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  // weight fragments: B[k = ky*8 + kx][n = co], hi and lo parts
+  uint32_t wh[4][NB][2], wl[4][NB][2];
+#pragma unroll
+  for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ky = 2 * kb + h, kx = 2 * t, co = nb * 8 + g;
+        float v0 = 0.f, v1 = 0.f;
+        if (ky < 7) {
+          v0 = __ldg(w + co * 49 + ky * 7 + kx);
+          if (kx + 1 < 7) v1 = __ldg(w + co * 49 + ky * 7 + kx + 1);
+        }
+        bf16 h0, l0, h1, l1;
+        split_bf16(v0, h0, l0);
+        split_bf16(v1, h1, l1);
+        wh[kb][nb][h] = pack_bf16(h0, h1);
+        wl[kb][nb][h] = pack_bf16(l0, l1);
+      }
+  const int tiles_1d = (R + kT - 1) / kT, tiles_img = tiles_1d * tiles_1d, ntiles = N * tiles_img;
+  // per-lane part of the fragment address: copy (g & 1), column g - (g & 1) + 2t  (+8 for the second pixel octet)
+  const int a_off = (g & 1) * kSxCopy + (g - (g & 1)) + 2 * t;
+  float pre[kSxPre];
+  int tile = blockIdx.x;
+  if (tile < ntiles) stem_tile_fetch(x, R, tile / tiles_img, ((tile % tiles_img) / tiles_1d) * kT, ((tile % tiles_img) % tiles_1d) * kT, pre);
+  for (; tile < ntiles; tile += gridDim.x) {
+    const int n = tile / tiles_img, tr = tile - n * tiles_img;
+    const int h0 = (tr / tiles_1d) * kT, w0 = (tr % tiles_1d) * kT;
+    __syncthreads();  // the previous tile's fragments have been read
+    stem_tile_store(s_x, pre);
+    __syncthreads();
+    const int nxt = tile + gridDim.x;
+    if (nxt < ntiles) stem_tile_fetch(x, R, nxt / tiles_img, ((nxt % tiles_img) / tiles_1d) * kT, ((nxt % tiles_img) % tiles_1d) * kT, pre);
+#pragma unroll 1
+    for (int rr = 0; rr < 2; ++rr) {
+      const int py = warp * 2 + rr;
+      float acc[NB][4];
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        acc[nb][0] = acc[nb][2] = __ldg(b + nb * 8 + 2 * t);  // L1-resident after the first tile
+        acc[nb][1] = acc[nb][3] = __ldg(b + nb * 8 + 2 * t + 1);
+      }
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        const bf16* p0 = s_x + (py + 2 * kb) * kSxPitch + a_off;  // ky = 2kb
+        const bf16* p1 = p0 + kSxPitch;                           // ky = 2kb + 1
+        const uint32_t ah0 = *reinterpret_cast<const uint32_t*>(p0), ah1 = *reinterpret_cast<const uint32_t*>(p0 + 8);
+        const uint32_t ah2 = *reinterpret_cast<const uint32_t*>(p1), ah3 = *reinterpret_cast<const uint32_t*>(p1 + 8);
+        const uint32_t al0 = *reinterpret_cast<const uint32_t*>(p0 + 2 * kSxCopy), al1 = *reinterpret_cast<const uint32_t*>(p0 + 2 * kSxCopy + 8);
+        const uint32_t al2 = *reinterpret_cast<const uint32_t*>(p1 + 2 * kSxCopy), al3 = *reinterpret_cast<const uint32_t*>(p1 + 2 * kSxCopy + 8);
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          mma16816(acc[nb], ah0, ah1, ah2, ah3, wh[kb][nb][0], wh[kb][nb][1]);
+          mma16816(acc[nb], al0, al1, al2, al3, wh[kb][nb][0], wh[kb][nb][1]);
+          mma16816(acc[nb], ah0, ah1, ah2, ah3, wl[kb][nb][0], wl[kb][nb][1]);
+        }
+      }
+      const int h = h0 + py;
+      if (h < R) {
+        bf16* o = y + n * y_ns + ((long long)h * R + w0 + g) * 8 + 2 * t;  // planar: octet nb of pixel (h, w0 + g)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          bf16* on = o + (long long)nb * R * R * 8;
+          if (w0 + g < R) *reinterpret_cast<__nv_bfloat162*>(on) = __floats2bfloat162_rn(acc[nb][0], acc[nb][1]);
+          if (w0 + g + 8 < R) *reinterpret_cast<__nv_bfloat162*>(on + 64) = __floats2bfloat162_rn(acc[nb][2], acc[nb][3]);
+        }
+      }
+    }
+  }
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(256, 2) stem_wgrad_mma_kernel(const float* __restrict__ x, const bf16* __restrict__ dy,
+                                                                float* __restrict__ dw, float* __restrict__ db, int N, int R,
+                                                                long long dy_ns) {
+  constexpr int C8 = COUT / 8, MB = COUT / 16;
+  constexpr int kDyPre = C8;  // 16-byte octets of the dY tile per thread (256 pixels x C8 octets / 256 threads)
+  __shared__ __align__(16) bf16 s_x[4 * kSxCopy];
+  __shared__ __align__(128) uint4 s_dy[C8 * 256];  // [octet][pixel of the 16x16 tile]; reused for the final reduction
+  static_assert(sizeof(uint4) * C8 * 256 >= sizeof(float) * (COUT * 49 + COUT), "reduction buffer fits the dY tile");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  float acc[MB][7][4], accb[MB][4];
+#pragma unroll
+  for (int mb = 0; mb < MB; ++mb) {
+#pragma unroll
+    for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[mb][ky][i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) accb[mb][i] = 0.f;
+  }
+  const int tiles_1d = (R + kT - 1) / kT, tiles_img = tiles_1d * tiles_1d, ntiles = N * tiles_img;
+  const int b_off = (g & 1) * kSxCopy + (g - (g & 1)) + 2 * t;
+  const uint32_t ones = (g == 0) ? 0x3F803F80u : 0u;  // bf16 (1, 1) in column n = 0
+  const uint32_t dy_base = (uint32_t)__cvta_generic_to_shared(s_dy);
+  // ldmatrix: lane supplies row i = lane & 7 of matrix j = lane >> 3: (octet 2mb + (j & 1), pixel half j >> 1)
+  const uint32_t lm_off = (uint32_t)((((lane >> 3) & 1) * 256 + (lane >> 4) * 8 + (lane & 7)) * 16);
+  float pre[kSxPre];
+  uint4 pdy[kDyPre];
+  auto fetch = [&](int tl) {
+    const int n = tl / tiles_img, tr = tl - n * tiles_img;
+    const int h0 = (tr / tiles_1d) * kT, w0 = (tr % tiles_1d) * kT;
+    stem_tile_fetch(x, R, n, h0, w0, pre);
+    const int p = threadIdx.x, hh = h0 + p / kT, ww = w0 + p % kT;
+#pragma unroll
+    for (int c8 = 0; c8 < C8; ++c8)
+      pdy[c8] = (hh < R && ww < R)
+                    ? __ldg(reinterpret_cast<const uint4*>(dy + n * dy_ns + ((long long)c8 * R * R + (long long)hh * R + ww) * 8))
+                    : make_uint4(0u, 0u, 0u, 0u);
+  };
+  int tile = blockIdx.x;
+  if (tile < ntiles) fetch(tile);
+  for (; tile < ntiles; tile += gridDim.x) {
+    __syncthreads();
+    stem_tile_store(s_x, pre);
+#pragma unroll
+    for (int c8 = 0; c8 < C8; ++c8) s_dy[c8 * 256 + threadIdx.x] = pdy[c8];
+    __syncthreads();
+    if (tile + (int)gridDim.x < ntiles) fetch(tile + gridDim.x);
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int py = warp * 2 + rr;
+      uint32_t a[MB][4];
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) {
+        const uint32_t addr = dy_base + (uint32_t)((2 * mb * 256 + py * 16) * 16) + lm_off;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(a[mb][0]), "=r"(a[mb][1]), "=r"(a[mb][2]), "=r"(a[mb][3])
+                     : "r"(addr));
+      }
+#pragma unroll
+      for (int ky = 0; ky < 7; ++ky) {
+        const bf16* p = s_x + (py + ky) * kSxPitch + b_off;
+        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(p), bh1 = *reinterpret_cast<const uint32_t*>(p + 8);
+        const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(p + 2 * kSxCopy), bl1 = *reinterpret_cast<const uint32_t*>(p + 2 * kSxCopy + 8);
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) {
+          mma16816(acc[mb][ky], a[mb][0], a[mb][1], a[mb][2], a[mb][3], bh0, bh1);
+          mma16816(acc[mb][ky], a[mb][0], a[mb][1], a[mb][2], a[mb][3], bl0, bl1);
+        }
+      }
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) mma16816(accb[mb], a[mb][0], a[mb][1], a[mb][2], a[mb][3], ones, ones);
+    }
+  }
+  // eight warps -> one shared-memory image [co][49] + [co] -> one atomic per entry and block
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(s_dy);
+  for (int i = threadIdx.x; i < COUT * 50; i += 256) red[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int mb = 0; mb < MB; ++mb) {
+#pragma unroll
+    for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int co = mb * 16 + g + (i >> 1) * 8, kx = 2 * t + (i & 1);
+        if (kx < 7) atomicAdd(red + co * 49 + ky * 7 + kx, acc[mb][ky][i]);
+      }
+    if (t == 0) {
+      atomicAdd(red + COUT * 49 + mb * 16 + g, accb[mb][0]);
+      atomicAdd(red + COUT * 49 + mb * 16 + g + 8, accb[mb][2]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < COUT * 49; i += 256) atomicAdd(dw + i, red[i]);
+  if (db != nullptr && threadIdx.x < COUT) atomicAdd(db + threadIdx.x, red[COUT * 49 + threadIdx.x]);
+}
+
+// CAUSALGEN_B200_STEM_MMA=0 keeps the direct kernels for the single-channel stems (A/B measurements)
+bool stem_mma_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("CAUSALGEN_B200_STEM_MMA");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+
 }  // namespace
 
 extern "C" int cg_stem_fwd(const float* x, const float* w, const float* b, void* y, int32_t N, int32_t Cin, int32_t R,
@@ -154,6 +407,15 @@ extern "C" int cg_stem_fwd(const float* x, const float* w, const float* b, void*
   size_t smem = (size_t)(49 * Cin * Cout + Cin * kHalo * kHalo) * sizeof(float);
   bf16* yb = reinterpret_cast<bf16*>(y);
   cudaStream_t st = cg_stream(stream);
+  if (Cin == 1 && stem_mma_enabled()) {
+    const int t1 = cg_ceil_div(R, kT);
+    int blocks = N * t1 * t1;
+    if (blocks > 2 * cg_device_sms()) blocks = 2 * cg_device_sms();
+    if (Cout == 32) stem_fwd_mma_kernel<32><<<blocks, 256, 0, st>>>(x, w, b, yb, N, R, y_ld);
+    else stem_fwd_mma_kernel<16><<<blocks, 256, 0, st>>>(x, w, b, yb, N, R, y_ld);
+    CG_LAUNCH_CHECK("cg_stem_fwd");
+    return CG_OK;
+  }
   if (Cin == 1 && Cout == 32) stem_fwd_kernel<1, 32><<<grid, 256, smem, st>>>(x, w, b, yb, R, y_ld);
   else if (Cin == 1) stem_fwd_kernel<1, 16><<<grid, 256, smem, st>>>(x, w, b, yb, R, y_ld);
   else if (Cout == 32) stem_fwd_kernel<3, 32><<<grid, 256, smem, st>>>(x, w, b, yb, R, y_ld);
@@ -168,6 +430,14 @@ extern "C" int cg_stem_wgrad(const float* x, const void* dy, float* dw, float* d
   CG_REQUIRE((Cin == 1 || Cin == 3) && Cout <= kMaxCout && Cout % 8 == 0, "cg_stem_wgrad: Cin=%d Cout=%d", Cin, Cout);
   const int t1 = cg_ceil_div(R, kT);
   int blocks = N * t1 * t1;
+  if (Cin == 1 && (Cout == 16 || Cout == 32) && stem_mma_enabled()) {
+    if (blocks > 2 * cg_device_sms()) blocks = 2 * cg_device_sms();
+    const bf16* dyb = reinterpret_cast<const bf16*>(dy);
+    if (Cout == 32) stem_wgrad_mma_kernel<32><<<blocks, 256, 0, cg_stream(stream)>>>(x, dyb, dw, db, N, R, dy_ld);
+    else stem_wgrad_mma_kernel<16><<<blocks, 256, 0, cg_stream(stream)>>>(x, dyb, dw, db, N, R, dy_ld);
+    CG_LAUNCH_CHECK("cg_stem_wgrad");
+    return CG_OK;
+  }
   const int cap = 4 * cg_device_sms();
   if (blocks > cap) blocks = cap;
   if (Cin == 1)

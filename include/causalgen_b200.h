@@ -162,7 +162,9 @@ int cg_conv2d_wgrad(const cg_wgrad_args* a, void* stream);
 /* number of kernels the call above launches for these arguments (1 or 2): launch accounting only */
 int32_t cg_conv2d_wgrad_launches(const cg_wgrad_args* a);
 
-/* 7x7 stem, fp32 NCHW image in -> bf16 planar out (src/vae.py:104-110,126) and its weight grad */
+/* 7x7 stem, fp32 NCHW image in -> bf16 planar out (src/vae.py:104-110,126) and its weight grad.  Cin 1 | 3, Cout 16 | 32.
+ * Single-channel images run on warp-level tensor-core instructions with the image and the weights split into two bf16
+ * halves (fp32-accurate); three-channel images on direct fp32 kernels */
 int cg_stem_fwd(const float* x, const float* w, const float* b, void* y, int32_t N, int32_t Cin,
                 int32_t R, int32_t Cout, int64_t y_ns, void* stream);
 int cg_stem_wgrad(const float* x, const void* dy, float* dw, float* db, int32_t N, int32_t Cin,
