@@ -514,9 +514,10 @@ class CounterfactualGraph:
     """``counterfactual`` for a fixed batch size replayed from one CUDA graph (inference serving path).
 
     The eager helper issues ~1500 small launches per call and is CPU-bound at small batches; the graph replays the
-    identical launch sequence (abduct program, two-parent-set decode program, combine) from static buffers.
-    Noise is drawn inside the graph by torch's graph-safe Philox generator (``randn_like``, as the reference does,
-    src/vae.py:30), so every replay sees fresh eps."""
+    identical launch sequence (the fused program of ``Engine.build_counterfactual``: abduction, two prior-only decodes on
+    the shared bf16 latents, combine) from static buffers.  Noise (the reference's ``randn_like``, src/vae.py:30) is drawn
+    inside the latent kernels from a Philox stream keyed by a host seed captured at build time plus the device-side
+    ``seed_ctr`` that the captured ``add_`` advances, so every replay sees fresh eps without host involvement."""
 
     def __init__(self, vae: HVAE, batch: int, t_abduct: float = 1.0, particles: int = 1):
         eng = vae.engine()
