@@ -50,23 +50,55 @@ __global__ void avgpool_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict
   *reinterpret_cast<uint4*>(o) = cg_pack8(g);
 }
 
+// the common case (H, W multiples of d, plain write): one thread per POOLED pixel octet scales its gradient once and
+// writes the d x d window -- a quarter of the threads, no per-output division, d consecutive 16-byte stores per row
+__global__ void avgpool_bwd_exact_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int H, int W, int d,
+                                         long long dy_ns, long long dx_ns, int Po) {
+  const int Ho = H / d, Wo = W / d;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Ho * Wo) return;
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  const int ho = p / Wo, wo = p - ho * Wo;
+  float f[8];
+  cg_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + n * dy_ns + ((long long)c8 * Po * Po + ho * Po + wo) * 8)), f);
+  const float inv = 1.0f / (d * d);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) f[k] *= inv;
+  const uint4 v = cg_pack8(f);
+  bf16* o = dx + n * dx_ns + ((long long)c8 * H * W + (long long)(ho * d) * W + wo * d) * 8;
+  for (int a = 0; a < d; ++a)
+    for (int b = 0; b < d; ++b) *reinterpret_cast<uint4*>(o + ((long long)a * W + b) * 8) = v;
+}
+
+// blockIdx.z = chunk of kUpN samples: the learned bias (fp32, 32 bytes per output octet -- twice the output itself) is
+// read once per chunk instead of once per sample
+constexpr int kUpN = 8;
 __global__ void upsample_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ bias, bf16* __restrict__ y,
                                     int N, int Hi, int Ho, int C, long long x_ns, long long y_ns) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= Ho * Ho) return;
-  const int c8 = blockIdx.y, n = blockIdx.z;
+  const int c8 = blockIdx.y;
+  const int n0 = blockIdx.z * kUpN, n1 = min(N, n0 + kUpN);
   const int h = p / Ho, w = p - h * Ho;
   const int hs = (h * Hi) / Ho, ws = (w * Hi) / Ho;
-  float f[8];
-  cg_unpack8(__ldg(reinterpret_cast<const uint4*>(x + n * x_ns + ((long long)c8 * Hi * Hi + hs * Hi + ws) * 8)), f);
+  float b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (bias != nullptr) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int c = c8 * 8 + k;
-      if (c < C) f[k] += __ldg(bias + (long long)c * Ho * Ho + p);
+      if (c < C) b[k] = __ldg(bias + (long long)c * Ho * Ho + p);
     }
   }
-  *reinterpret_cast<uint4*>(y + n * y_ns + ((long long)c8 * Ho * Ho + p) * 8) = cg_pack8(f);
+  const bf16* xp = x + ((long long)c8 * Hi * Hi + hs * Hi + ws) * 8;
+  bf16* yp = y + ((long long)c8 * Ho * Ho + p) * 8;
+#pragma unroll 4
+  for (int n = n0; n < n1; ++n) {
+    float f[8];
+    cg_unpack8(__ldg(reinterpret_cast<const uint4*>(xp + n * x_ns)), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] += b[k];
+    *reinterpret_cast<uint4*>(yp + n * y_ns) = cg_pack8(f);
+  }
 }
 
 __global__ void upsample_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int N, int Hi, int Ho, int C8,
@@ -519,6 +551,12 @@ extern "C" int cg_avgpool_bwd(const void* dy, void* dx, int32_t N, int32_t H, in
   CG_REQUIRE(d >= 1 && d <= H && H == W, "cg_avgpool_bwd: H=%d W=%d d=%d", H, W, d);
   CG_REQUIRE(C % 8 == 0 && dy_ld % 8 == 0 && dx_ld % 8 == 0, "cg_avgpool_bwd: C/ld multiples of 8");
   const int Po = pad_to > 0 ? pad_to : H / d;
+  if (!accumulate && H % d == 0 && W % d == 0) {
+    avgpool_bwd_exact_kernel<<<dim3(cg_ceil_div((H / d) * (W / d), 256), C / 8, N), 256, 0, cg_stream(stream)>>>(
+        reinterpret_cast<const bf16*>(dy), reinterpret_cast<bf16*>(dx), H, W, d, dy_ld, dx_ld, Po);
+    CG_LAUNCH_CHECK("cg_avgpool_bwd");
+    return CG_OK;
+  }
   avgpool_bwd_kernel<<<dim3(cg_ceil_div(H * W, 256), C / 8, N), 256, 0, cg_stream(stream)>>>(
       reinterpret_cast<const bf16*>(dy), reinterpret_cast<bf16*>(dx), N, H, W, C / 8, d, dy_ld, dx_ld, Po, accumulate);
   CG_LAUNCH_CHECK("cg_avgpool_bwd");
@@ -529,7 +567,7 @@ extern "C" int cg_upsample_fwd(const void* x, const float* bias, void* y, int32_
                                int64_t x_ld, int64_t y_ld, void* stream) {
   CG_ARCH_GUARD();
   CG_REQUIRE(Ho >= Hi && x_ld % 8 == 0 && y_ld % 8 == 0, "cg_upsample_fwd: Hi=%d Ho=%d", Hi, Ho);
-  upsample_fwd_kernel<<<dim3(cg_ceil_div(Ho * Ho, 256), (C + 7) / 8, N), 256, 0, cg_stream(stream)>>>(
+  upsample_fwd_kernel<<<dim3(cg_ceil_div(Ho * Ho, 256), (C + 7) / 8, cg_ceil_div(N, kUpN)), 256, 0, cg_stream(stream)>>>(
       reinterpret_cast<const bf16*>(x), bias, reinterpret_cast<bf16*>(y), N, Hi, Ho, C, x_ld, y_ld);
   CG_LAUNCH_CHECK("cg_upsample_fwd");
   return CG_OK;

@@ -412,11 +412,11 @@ def test_pool_and_upsample():
     L.check(lib.cg_avgpool_bwd(dy1.data_ptr(), dx8.data_ptr(), N, 8, 8, C, 7, ns_of(dy1), ns_of(dx8), 0, 0, stream()))
     pooled.backward(to_nchw(dy1, C))
     assert_close(to_nchw(dx8, C), xr.grad, 1e-2, "pool bwd 8 by 7")
-    # nearest upsample + learned bias, integer and 7->8 style factors
-    for hi, ho in ((6, 12), (1, 4), (7, 8), (8, 14)):
+    # nearest upsample + learned bias, integer and 7->8 style factors; 11 samples = one full chunk of 8 + a tail of 3
+    for hi, ho, N in ((6, 12, 2), (1, 4, 2), (7, 8, 2), (8, 14, 2), (6, 12, 11)):
         xs = nhwc_bf16(rnd(N, C, hi, hi, seed=4))
         bias = rnd(1, C, ho, ho, seed=5)
-        y = zeros(ho)
+        y = torch.zeros(N, C // 8, ho, ho, 8, device=DEV, dtype=torch.bfloat16)
         L.check(lib.cg_upsample_fwd(xs.data_ptr(), bias.data_ptr(), y.data_ptr(), N, hi, ho, C, ns_of(xs), ns_of(y), stream()))
         xr = to_nchw(xs, C).requires_grad_(True)
         br = bias.clone().requires_grad_(True)
