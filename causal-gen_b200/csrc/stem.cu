@@ -156,8 +156,14 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
 //            thread holds in one fragment register (kx = 2t, 2t+1) are NEIGHBOURING pixels of the image row -- one 32-bit
 //            shared-memory load.  Odd pixel positions would be misaligned, so the tile is stored twice, the second copy
 //            shifted by one pixel.
-//   fp32     the image and the weights are split x = hi + lo into two bf16 (2^-17 relative), products hi*hi + lo*hi +
-//            hi*lo accumulate in fp32: the result matches the fp32 direct kernel to ~1e-5, no bf16 rounding of the input.
+//   fp32     operands are split x = hi + lo into two 16-bit floats and the products hi*hi + lo*hi + hi*lo accumulate in
+//            fp32.  The forward pass splits into fp16 (11-bit significands: 2^-22 relative, the weights pre-scaled by 16 so
+//            their low halves stay normal; image values are O(1)): its output feeds forty residual blocks that amplify
+//            every flipped bf16 rounding, and with bf16 halves (2^-17) 0.36 % of the outputs rounded differently from the
+//            fp32 direct kernel -- enough to move the tiny-config losses by 2e-3 (profiles/r4e_stem_accuracy_bf16_halves.txt,
+//            r4e_trainer_step0_by_variant.txt); with
+//            fp16 halves the rate is that of the direct kernel (~1.5e-4, r4f_stem_accuracy_fp16_halves.txt).  The weight gradient keeps bf16 halves: dY is
+//            bf16 (fp16 would flush small gradients), and 2e-6 on 1568 weight gradients feeds nothing downstream.
 //   forward  M = 16 pixels of a tile row, N = output channels, A from the image tile, B (weights) in registers.
 //   wgrad    M = output channels (dY via ldmatrix.trans: an octet of a pixel is one 16-byte row), N = kx (one 8-wide
 //            block per ky), K = 16 pixels of a tile row; the bias gradient is one more n-block against a ones fragment.
@@ -175,13 +181,27 @@ __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
-  hi = __float2bfloat16_rn(v);
-  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+__device__ __forceinline__ void mma16816_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                             uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ uint32_t pack_bf16(bf16 a, bf16 b) {  // a = low half (lower K index)
-  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+// v = hi + lo (+ 2^-17 v for bf16 halves, 2^-22 v for fp16 halves), returned as raw 16-bit patterns
+template <bool F16>
+__device__ __forceinline__ void split16(float v, uint16_t& hi, uint16_t& lo) {
+  if (F16) {
+    const __half h = __float2half_rn(v);
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(__float2half_rn(v - __half2float(h)));
+  } else {
+    const bf16 h = __float2bfloat16_rn(v);
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+  }
 }
+__device__ __forceinline__ uint32_t pack16(uint16_t a, uint16_t b) { return (uint32_t)a | ((uint32_t)b << 16); }  // a = lower K
 // image tile of (n, h0, w0) -> registers (fp32, zero outside the image and in the padding row / column)
 __device__ __forceinline__ void stem_tile_fetch(const float* __restrict__ x, int R, int n, int h0, int w0, float (&pre)[kSxPre]) {
 #pragma unroll
@@ -194,13 +214,14 @@ __device__ __forceinline__ void stem_tile_fetch(const float* __restrict__ x, int
   }
 }
 // registers -> shared memory: s[(hl*2 + copy) * kSxCopy + r*kSxPitch + c], copy 1 shifted left by one pixel
-__device__ __forceinline__ void stem_tile_store(bf16* s, const float (&pre)[kSxPre]) {
+template <bool F16>
+__device__ __forceinline__ void stem_tile_store(uint16_t* s, const float (&pre)[kSxPre]) {
 #pragma unroll
   for (int j = 0; j < kSxPre; ++j) {
     const int i = threadIdx.x + 256 * j;
     if (i >= kSxElems) break;
-    bf16 hi, lo;
-    split_bf16(pre[j], hi, lo);
+    uint16_t hi, lo;
+    split16<F16>(pre[j], hi, lo);
     s[i] = hi;
     s[2 * kSxCopy + i] = lo;
     if (i % kSxPitch != 0) {
@@ -215,8 +236,9 @@ __global__ void __launch_bounds__(256, 2) stem_fwd_mma_kernel(const float* __res
                                                               const float* __restrict__ b, bf16* __restrict__ y, int N, int R,
                                                               long long y_ns) {
   constexpr int NB = COUT / 8;
-  __shared__ __align__(16) bf16 s_x[4 * kSxCopy];
+  __shared__ __align__(16) uint16_t s_x[4 * kSxCopy];  // fp16 halves of the image tile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  constexpr float kWScale = 16.f;  // keeps the low halves of |w| >= 2^-7 normal in fp16; undone (exactly) in the epilogue
   // weight fragments: B[k = ky*8 + kx][n = co], hi and lo parts
   uint32_t wh[4][NB][2], wl[4][NB][2];
 #pragma unroll
@@ -231,11 +253,11 @@ __global__ void __launch_bounds__(256, 2) stem_fwd_mma_kernel(const float* __res
           v0 = __ldg(w + co * 49 + ky * 7 + kx);
           if (kx + 1 < 7) v1 = __ldg(w + co * 49 + ky * 7 + kx + 1);
         }
-        bf16 h0, l0, h1, l1;
-        split_bf16(v0, h0, l0);
-        split_bf16(v1, h1, l1);
-        wh[kb][nb][h] = pack_bf16(h0, h1);
-        wl[kb][nb][h] = pack_bf16(l0, l1);
+        uint16_t h0, l0, h1, l1;
+        split16<true>(v0 * kWScale, h0, l0);
+        split16<true>(v1 * kWScale, h1, l1);
+        wh[kb][nb][h] = pack16(h0, h1);
+        wl[kb][nb][h] = pack16(l0, l1);
       }
   const int tiles_1d = (R + kT - 1) / kT, tiles_img = tiles_1d * tiles_1d, ntiles = N * tiles_img;
   // per-lane part of the fragment address: copy (g & 1), column g - (g & 1) + 2t  (+8 for the second pixel octet)
@@ -247,7 +269,7 @@ __global__ void __launch_bounds__(256, 2) stem_fwd_mma_kernel(const float* __res
     const int n = tile / tiles_img, tr = tile - n * tiles_img;
     const int h0 = (tr / tiles_1d) * kT, w0 = (tr % tiles_1d) * kT;
     __syncthreads();  // the previous tile's fragments have been read
-    stem_tile_store(s_x, pre);
+    stem_tile_store<true>(s_x, pre);
     __syncthreads();
     const int nxt = tile + gridDim.x;
     if (nxt < ntiles) stem_tile_fetch(x, R, nxt / tiles_img, ((nxt % tiles_img) / tiles_1d) * kT, ((nxt % tiles_img) % tiles_1d) * kT, pre);
@@ -257,22 +279,22 @@ __global__ void __launch_bounds__(256, 2) stem_fwd_mma_kernel(const float* __res
       float acc[NB][4];
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) {
-        acc[nb][0] = acc[nb][2] = __ldg(b + nb * 8 + 2 * t);  // L1-resident after the first tile
-        acc[nb][1] = acc[nb][3] = __ldg(b + nb * 8 + 2 * t + 1);
+        acc[nb][0] = acc[nb][2] = kWScale * __ldg(b + nb * 8 + 2 * t);  // L1-resident after the first tile
+        acc[nb][1] = acc[nb][3] = kWScale * __ldg(b + nb * 8 + 2 * t + 1);
       }
 #pragma unroll
       for (int kb = 0; kb < 4; ++kb) {
-        const bf16* p0 = s_x + (py + 2 * kb) * kSxPitch + a_off;  // ky = 2kb
-        const bf16* p1 = p0 + kSxPitch;                           // ky = 2kb + 1
+        const uint16_t* p0 = s_x + (py + 2 * kb) * kSxPitch + a_off;  // ky = 2kb
+        const uint16_t* p1 = p0 + kSxPitch;                           // ky = 2kb + 1
         const uint32_t ah0 = *reinterpret_cast<const uint32_t*>(p0), ah1 = *reinterpret_cast<const uint32_t*>(p0 + 8);
         const uint32_t ah2 = *reinterpret_cast<const uint32_t*>(p1), ah3 = *reinterpret_cast<const uint32_t*>(p1 + 8);
         const uint32_t al0 = *reinterpret_cast<const uint32_t*>(p0 + 2 * kSxCopy), al1 = *reinterpret_cast<const uint32_t*>(p0 + 2 * kSxCopy + 8);
         const uint32_t al2 = *reinterpret_cast<const uint32_t*>(p1 + 2 * kSxCopy), al3 = *reinterpret_cast<const uint32_t*>(p1 + 2 * kSxCopy + 8);
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
-          mma16816(acc[nb], ah0, ah1, ah2, ah3, wh[kb][nb][0], wh[kb][nb][1]);
-          mma16816(acc[nb], al0, al1, al2, al3, wh[kb][nb][0], wh[kb][nb][1]);
-          mma16816(acc[nb], ah0, ah1, ah2, ah3, wl[kb][nb][0], wl[kb][nb][1]);
+          mma16816_f16(acc[nb], ah0, ah1, ah2, ah3, wh[kb][nb][0], wh[kb][nb][1]);
+          mma16816_f16(acc[nb], al0, al1, al2, al3, wh[kb][nb][0], wh[kb][nb][1]);
+          mma16816_f16(acc[nb], ah0, ah1, ah2, ah3, wl[kb][nb][0], wl[kb][nb][1]);
         }
       }
       const int h = h0 + py;
@@ -281,8 +303,10 @@ __global__ void __launch_bounds__(256, 2) stem_fwd_mma_kernel(const float* __res
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
           bf16* on = o + (long long)nb * R * R * 8;
-          if (w0 + g < R) *reinterpret_cast<__nv_bfloat162*>(on) = __floats2bfloat162_rn(acc[nb][0], acc[nb][1]);
-          if (w0 + g + 8 < R) *reinterpret_cast<__nv_bfloat162*>(on + 64) = __floats2bfloat162_rn(acc[nb][2], acc[nb][3]);
+          constexpr float kInv = 1.f / kWScale;
+          if (w0 + g < R) *reinterpret_cast<__nv_bfloat162*>(on) = __floats2bfloat162_rn(acc[nb][0] * kInv, acc[nb][1] * kInv);
+          if (w0 + g + 8 < R)
+            *reinterpret_cast<__nv_bfloat162*>(on + 64) = __floats2bfloat162_rn(acc[nb][2] * kInv, acc[nb][3] * kInv);
         }
       }
     }
@@ -295,7 +319,7 @@ __global__ void __launch_bounds__(256, 2) stem_wgrad_mma_kernel(const float* __r
                                                                 long long dy_ns) {
   constexpr int C8 = COUT / 8, MB = COUT / 16;
   constexpr int kDyPre = C8;  // 16-byte octets of the dY tile per thread (256 pixels x C8 octets / 256 threads)
-  __shared__ __align__(16) bf16 s_x[4 * kSxCopy];
+  __shared__ __align__(16) uint16_t s_x[4 * kSxCopy];  // bf16 halves of the image tile
   __shared__ __align__(128) uint4 s_dy[C8 * 256];  // [octet][pixel of the 16x16 tile]; reused for the final reduction
   static_assert(sizeof(uint4) * C8 * 256 >= sizeof(float) * (COUT * 49 + COUT), "reduction buffer fits the dY tile");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -332,7 +356,7 @@ __global__ void __launch_bounds__(256, 2) stem_wgrad_mma_kernel(const float* __r
   if (tile < ntiles) fetch(tile);
   for (; tile < ntiles; tile += gridDim.x) {
     __syncthreads();
-    stem_tile_store(s_x, pre);
+    stem_tile_store<false>(s_x, pre);
 #pragma unroll
     for (int c8 = 0; c8 < C8; ++c8) s_dy[c8 * 256 + threadIdx.x] = pdy[c8];
     __syncthreads();
@@ -350,7 +374,7 @@ __global__ void __launch_bounds__(256, 2) stem_wgrad_mma_kernel(const float* __r
       }
 #pragma unroll
       for (int ky = 0; ky < 7; ++ky) {
-        const bf16* p = s_x + (py + ky) * kSxPitch + b_off;
+        const uint16_t* p = s_x + (py + ky) * kSxPitch + b_off;
         const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(p), bh1 = *reinterpret_cast<const uint32_t*>(p + 8);
         const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(p + 2 * kSxCopy), bl1 = *reinterpret_cast<const uint32_t*>(p + 2 * kSxCopy + 8);
 #pragma unroll
