@@ -49,7 +49,7 @@ class WgradArgs(C.Structure):
                 ("nsrc", C.c_int32), ("src", Src * CG_MAX_SRC), ("dy", C.c_void_p), ("dy_ns", C.c_int64),
                 ("dy_c", C.c_int32), ("dy_c8", C.c_int32), ("dw", C.c_void_p), ("dbias", C.c_void_p), ("cout_l", C.c_int32),
                 ("cin_l", C.c_int32), ("src_log", C.c_int32 * CG_MAX_SRC), ("src_off", C.c_int32 * CG_MAX_SRC),
-                ("taps", C.c_int32)]
+                ("taps", C.c_int32), ("min_tiles", C.c_int32)]
 
 
 class LatentArgs(C.Structure):

@@ -233,10 +233,11 @@ class BlockLayers:
                                          centre_only=centre and c.weight.shape[2] == 3,
                                          grad_srcs=(grad_srcs if i == 0 else None),
                                          fwd_operands=(i == len(convs) - 1),  # only a Block's last conv fuses adds
-                                         res=res))
+                                         res=res, light=mod.light))
         self.proj = None
         if hasattr(mod, "width_proj"):
-            self.proj = ConvLayer(eng.table, mod.width_proj.weight, mod.width_proj.bias, list(src_logical), L.ACT_NONE)
+            self.proj = ConvLayer(eng.table, mod.width_proj.weight, mod.width_proj.bias, list(src_logical), L.ACT_NONE,
+                                  light=mod.light)
         self.params = [(c.weight, c.bias) for c in convs]
 
 
@@ -299,11 +300,11 @@ class Engine:
                 d.post = BlockLayers(self, blk.posterior, [st.cin, self.ctx, st.cin], st.res,
                                      grad_srcs=[True, False, True])
             d.z_proj = ConvLayer(self.table, blk.z_proj.weight, blk.z_proj.bias, [self.zd, self.ctx], L.ACT_NONE,
-                                 grad_srcs=[True, False])
+                                 grad_srcs=[True, False], light=blk.conv.light)
             d.zfp = None
             if not self.q_corr:
                 d.zfp = ConvLayer(self.table, blk.z_feat_proj.weight, blk.z_feat_proj.bias, [self.zd, st.cin],
-                                  L.ACT_NONE)
+                                  L.ACT_NONE, light=blk.conv.light)
             d.conv = BlockLayers(self, blk.conv, [st.cin], st.res)
             self.dec_layers.append(d)
         self.dmol = isinstance(model.likelihood, DmolNet)

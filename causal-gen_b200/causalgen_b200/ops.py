@@ -43,6 +43,18 @@ def fold_pays(res: Optional[int], k_channels: int, bwd: bool = False) -> bool:
     return folded <= 1.2 * plain
 
 
+def wgrad_min_tiles(batch: int, light: bool) -> int:
+    """cg_wgrad_args.min_tiles: 128-pixel tiles per weight-gradient CTA (lower bound).  Measured on UKBB-192, whose "light"
+    two-conv ReLU blocks have cheap tiles (profiles/r4g_wgrad_grid_and_stem.txt: images/s at 128 | 32 images per GPU for
+    24 / 48 / 96 / 144 / 192 / 384 tiles = 3101 | 2260, 3141 | 2287, 3186 | 2306, 3201 | 2297, 3220 | 2141, 3121 | 2007):
+    best at 192 resp. 96 = 17 * sqrt(batch).  The same rule LOST 3-4 % on the four-conv GELU configs (Morpho-/colour-MNIST
+    at batch 1024, MIMIC-192 at 64: their expensive tiles make long launches that hold back the pool streams), which keep
+    the library default (0 -> 24)."""
+    if not light:
+        return 0
+    return max(24, min(256, int(17.0 * batch ** 0.5 + 0.5)))
+
+
 def round16(c: int) -> int:
     return (c + 15) // 16 * 16
 
@@ -178,12 +190,13 @@ class ConvLayer:
     def __init__(self, table: PackTable, weight: torch.Tensor, bias: Optional[torch.Tensor],
                  src_logical: Sequence[int], act: int, centre_only: bool = False,
                  grad_srcs: Optional[Sequence[bool]] = None, fwd_operands: bool = True,
-                 n_scale: Optional[torch.Tensor] = None, res: Optional[int] = None):
-        """res: side of the (square) image the layer runs on, when known at construction (fold policy, `fold_pays`).
+                 n_scale: Optional[torch.Tensor] = None, res: Optional[int] = None, light: bool = False):
+        """light: the layer belongs to a model built from "light" Blocks (weight-gradient grid policy, `wgrad_min_tiles`).
+        res: side of the (square) image the layer runs on, when known at construction (fold policy, `fold_pays`).
         fwd_operands=False: no forward launch of this layer fuses an epilogue operand (add / add2 / mul), so its
         GEMM-N chunk need not reserve shared memory for the operand ring (first convs of a Block: huge K, narrow N)"""
         lib = L.load()
-        self.weight, self.bias = weight, bias
+        self.weight, self.bias, self.light = weight, bias, light
         self.cout_l, self.cin_l, self.k = weight.shape[0], weight.shape[1], weight.shape[2]
         assert sum(src_logical) == self.cin_l, (src_logical, self.cin_l)
         self.src_logical = list(src_logical)
@@ -313,6 +326,7 @@ class ConvLayer:
         a.dw = dw.data_ptr()
         a.dbias = db.data_ptr() if db is not None else None
         a.cout_l, a.cin_l, a.taps = self.cout_l, self.cin_l, self.taps
+        a.min_tiles = wgrad_min_tiles(N, self.light)
         for i in range(len(srcs)):
             a.src_log[i], a.src_off[i] = self.src_logical[i], self.src_off[i]
         ln = L.Launch("cg_conv2d_wgrad", C.byref(a))

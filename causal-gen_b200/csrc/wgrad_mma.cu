@@ -24,7 +24,6 @@
 // GELU layers and 1x1 / 1-pixel problems stay on the tcgen05 kernel of wgrad_tc.cu.
 #include <cuda.h>
 
-#include <cmath>
 #include <cstdlib>
 
 #include "cg_common.cuh"
@@ -515,14 +514,12 @@ int launch_mma(const MParams& kp, int gx, int smem_bytes, cudaStream_t st) {
 
 // Returns CG_OK with *handled = 1 when the problem was launched on the mma.sync kernel, *handled = 0 when the
 // caller must use the tcgen05 kernel (1x1 / centre-tap / 1-pixel problems, GELU, both operands wide).
-// Pixel tiles per CTA (lower bound).  Weight gradients are off the critical path (low-priority pool streams) and the step
-// is throughput-bound: every CTA of a weight gradient flushes its whole accumulator tile through atomics and holds an SM
-// that a kernel of the dependent chain wants, so the low-resolution problems run on FEW CTAs with many tiles each -- as
-// many as the step can hide: a CTA needs ~0.75 us per tile, and the time to hide it in grows with the batch.  Measured on
-// UKBB-192 (profiles/r4g_wgrad_grid_and_stem.txt), images/s at 128 | 32 images per GPU for a minimum of 24 / 48 / 96 / 144 /
-// 192 / 384 tiles: 3101 | 2260, 3141 | 2287, 3186 | 2306, 3201 | 2297, 3220 | 2141, 3121 | 2007 -- best at 192 resp. 96,
-// i.e. ~17 * sqrt(batch).  CG_WGRAD_MIN_TILES overrides.
-static int wgrad_min_tiles(int batch) {
+// Pixel tiles per CTA (lower bound): cg_wgrad_args.min_tiles, 24 when the caller gives none.  Weight gradients are off the
+// critical path (low-priority pool streams) and the step is throughput-bound: every CTA of a weight gradient flushes its
+// whole accumulator tile through atomics and holds an SM that a kernel of the dependent chain wants, so the low-resolution
+// problems run on FEW CTAs with many tiles each -- as many as the step can hide (the policy lives with the caller:
+// ops.wgrad_min_tiles, measurements in profiles/r4g_wgrad_grid_and_stem.txt).  CG_WGRAD_MIN_TILES overrides both.
+static int wgrad_min_tiles(const cg_wgrad_args* a) {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("CG_WGRAD_MIN_TILES");
@@ -530,8 +527,7 @@ static int wgrad_min_tiles(int batch) {
     if (v < 0) v = 0;
   }
   if (v > 0) return v;
-  int t = (int)(17.0f * sqrtf((float)batch) + 0.5f);
-  return t < 24 ? 24 : (t > 256 ? 256 : t);
+  return a->min_tiles > 0 ? a->min_tiles : 24;
 }
 
 static bool mma1_eligible(const cg_wgrad_args* a) {
@@ -606,7 +602,7 @@ static int wgrad_mma_1x1(const cg_wgrad_args* a, void* stream, int* handled) {
   if (kp.nst < 8) return CG_OK;
   const int smem_bytes = kHdrM + kp.nst * kp.stage_bytes;
   int gx = cg_device_sms() / gy;
-  if (gx > (kp.ntiles + wgrad_min_tiles(a->N) - 1) / wgrad_min_tiles(a->N)) gx = (kp.ntiles + wgrad_min_tiles(a->N) - 1) / wgrad_min_tiles(a->N);
+  if (gx > (kp.ntiles + wgrad_min_tiles(a) - 1) / wgrad_min_tiles(a)) gx = (kp.ntiles + wgrad_min_tiles(a) - 1) / wgrad_min_tiles(a);
   if (gx < 1) gx = 1;
   cudaStream_t st = cg_stream(stream);
   int rc;
@@ -705,7 +701,7 @@ int cg_wgrad_mma_try(const cg_wgrad_args* a, void* stream, int* handled) {
   const int smem_bytes = kHdrM + kp.nst * kp.stage_bytes;
   // CTAs along the pixel axis share the chunk's gradient through coalesced atomics
   int gx = cg_device_sms() / kp.nchunks;
-  if (gx > (kp.ntiles + wgrad_min_tiles(a->N) - 1) / wgrad_min_tiles(a->N)) gx = (kp.ntiles + wgrad_min_tiles(a->N) - 1) / wgrad_min_tiles(a->N);
+  if (gx > (kp.ntiles + wgrad_min_tiles(a) - 1) / wgrad_min_tiles(a)) gx = (kp.ntiles + wgrad_min_tiles(a) - 1) / wgrad_min_tiles(a);
   if (gx < 1) gx = 1;
   cudaStream_t st = cg_stream(stream);
   int rc = CG_ERR_UNSUPPORTED;

@@ -155,6 +155,9 @@ typedef struct {
   int32_t cout_l, cin_l;   /* logical dims of dw */
   int32_t src_log[CG_MAX_SRC], src_off[CG_MAX_SRC];
   int32_t taps;            /* k*k or 1 (centre tap only) */
+  int32_t min_tiles;       /* scheduling hint: at least this many 128-pixel tiles per CTA (0 = 24).  Weight gradients are
+                              filler next to the dependent conv chain; few CTAs with many tiles leave the SMs to that chain
+                              and flush fewer accumulator tiles (the caller knows how much time the step has to hide them) */
 } cg_wgrad_args;
 
 /* dW += sum_pixels dy (x) act(cat(src)) shifted per tap; dbias += sum_pixels dy */

@@ -39,6 +39,7 @@ def test_struct_layouts_match_the_header_sizes():
     assert ctypes.sizeof(L.Seg) == 104
     assert ctypes.sizeof(L.ConvArgs) == 32 + 3 * 24 + 4 * 104 + 32
     assert ctypes.sizeof(L.PackDesc) % 8 == 0
+    assert ctypes.sizeof(L.WgradArgs) == 176 and L.WgradArgs.min_tiles.offset == 172   # include/causalgen_b200.h cg_wgrad_args
     # weight-slab planner is pure host arithmetic and must be callable without a GPU
     lib = L.load()
     nc = lib.cg_conv_nchunk(9 * 4, 16)
@@ -53,6 +54,15 @@ def test_struct_layouts_match_the_header_sizes():
     assert lib.cg_conv_fold_ok(9 * 4, 16, 0) == 1 and lib.cg_conv_fold_ok(9 * 8, 32, 1) == 1
     assert lib.cg_conv_fold_ok(9 * 4, 48, 0) == 0 and lib.cg_conv_fold_ok(4, 16, 0) == 0
     assert lib.cg_conv_fold_ok(9 * 40, 32, 1) == 0          # 640 input channels: the slab leaves no room for the rings
+
+
+def test_weight_gradient_grid_policy():
+    """ops.wgrad_min_tiles: the measured optimum of profiles/r4g_wgrad_grid_and_stem.txt (192 tiles at 128 images per GPU, 96
+    at 32) for models of light Blocks, the library default for the others"""
+    from causalgen_b200 import ops
+    assert ops.wgrad_min_tiles(128, True) == 192 and ops.wgrad_min_tiles(32, True) == 96
+    assert ops.wgrad_min_tiles(1, True) == 24 and ops.wgrad_min_tiles(4096, True) == 256
+    assert ops.wgrad_min_tiles(1024, False) == 0
 
 
 def test_fold_policy_follows_the_measured_layers():
