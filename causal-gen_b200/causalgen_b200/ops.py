@@ -47,11 +47,12 @@ def wgrad_min_tiles(batch: int, light: bool) -> int:
     """cg_wgrad_args.min_tiles: 128-pixel tiles per weight-gradient CTA (lower bound).  Measured on UKBB-192, whose "light"
     two-conv ReLU blocks have cheap tiles (profiles/r4g_wgrad_grid_and_stem.txt: images/s at 128 | 32 images per GPU for
     24 / 48 / 96 / 144 / 192 / 384 tiles = 3101 | 2260, 3141 | 2287, 3186 | 2306, 3201 | 2297, 3220 | 2141, 3121 | 2007):
-    best at 192 resp. 96 = 17 * sqrt(batch).  The same rule LOST 3-4 % on the four-conv GELU configs (Morpho-/colour-MNIST
-    at batch 1024, MIMIC-192 at 64: their expensive tiles make long launches that hold back the pool streams), which keep
-    the library default (0 -> 24)."""
+    best at 192 resp. 96 = 17 * sqrt(batch); flat around it at 64 images per GPU).  The same rule LOST 3-4 % on the four-conv
+    GELU configs (their expensive tiles make long launches that hold back the pool streams); forced through
+    CG_WGRAD_MIN_TILES they peak at 48 (Morpho-MNIST at batch 1024: 45.5 / 46.2 / 46.2 k images/s for 24 / 48 / 96 tiles,
+    MIMIC-192 at 64: 1742 / 1741 / 1717)."""
     if not light:
-        return 0
+        return 48
     return max(24, min(256, int(17.0 * batch ** 0.5 + 0.5)))
 
 

@@ -58,11 +58,11 @@ def test_struct_layouts_match_the_header_sizes():
 
 def test_weight_gradient_grid_policy():
     """ops.wgrad_min_tiles: the measured optimum of profiles/r4g_wgrad_grid_and_stem.txt (192 tiles at 128 images per GPU, 96
-    at 32) for models of light Blocks, the library default for the others"""
+    at 32) for models of light Blocks, 48 for the four-conv GELU configs"""
     from causalgen_b200 import ops
     assert ops.wgrad_min_tiles(128, True) == 192 and ops.wgrad_min_tiles(32, True) == 96
     assert ops.wgrad_min_tiles(1, True) == 24 and ops.wgrad_min_tiles(4096, True) == 256
-    assert ops.wgrad_min_tiles(1024, False) == 0
+    assert ops.wgrad_min_tiles(1024, False) == 48 and ops.wgrad_min_tiles(64, False) == 48
 
 
 def test_fold_policy_follows_the_measured_layers():
