@@ -149,10 +149,10 @@ struct TileWalk {
     if (ty >= tiles_y) { ty -= tiles_y; ++n; }
     n += dn;
   }
-  __device__ __forceinline__ TileGeom geom(const KParams& P) const {
+  __device__ __forceinline__ TileGeom geom(const KParams& P, bool fold) const {  // fold: compile-time at every call site
     TileGeom g;
     if (P.flat) { g.n = n * 128; g.h0 = g.w0 = 0; }
-    else if (P.fold) { g.n = n; g.h0 = ty * 8; g.w0 = tx * kFoldW - 1; }
+    else if (fold) { g.n = n; g.h0 = ty * 8; g.w0 = tx * kFoldW - 1; }
     else { g.n = n; g.h0 = ty * 16; g.w0 = tx * 8; }
     return g;
   }
@@ -249,7 +249,11 @@ __device__ __forceinline__ void epi_chunk_fast(float (&v)[16], const uint8_t* e0
 
 // DUAL: compiled with the act_copy (raw + activated) destinations of GELU blocks; the lean instance serves every
 // launch without them (all of UKBB) and keeps the epilogue code small.
-template <bool DUAL>
+// FOLD (column-folded 3x3, KParams::fold) is a template parameter, not a run-time flag: with the flag read from the
+// parameters the nine-tap instantiation carried the folded epilogue's registers and branches on its per-tile path and
+// lost 4 % of the whole step (2955 against 3070..3089 images/s over six sessions, profiles/r4n_*) -- more than folding
+// won back.  (The same lesson as the 16x16-step mode of round 2)
+template <bool DUAL, bool FOLD>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -324,9 +328,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) CG_TL(P.tl, 33);
   const bool k3 = P.a.ksize == 3;
-  const bool fold = P.fold != 0;
+  constexpr bool fold = FOLD;
   const int plane = fold ? kPlaneF : (k3 ? kPlane3 : kPlane1);
-  const int Ng = P.Ng;
+  const int Ng = fold ? P.Ng : Nc;
   const int H = P.a.H, W = P.a.W, N = P.a.N;
 
   if (warp == kMmaWarp || warp == kMmaWarp2) {
@@ -432,7 +436,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int first = blockIdx.x + (int)lt * (int)gridDim.x, tstep = (int)lstep * (int)gridDim.x;
       TileWalk walk(P, first, tstep);
       for (int tile = first; tile < P.ntiles; tile += tstep, lt += lstep, walk.next()) {
-        const TileGeom g = walk.geom(P);
+        const TileGeom g = walk.geom(P, fold);
         if (pw == 0 && lt < 12) CG_TL(P.tl, 90 + 2 * lt);
         if (P.nE > 0) {
           mbar_wait(BAR(B_EEMPTY + es), ephase ^ 1u);
@@ -594,7 +598,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     auto tile_loop = [&](auto&& chunk_fn) {
       TileWalk walk(P, blockIdx.x, gridDim.x);
       for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, walk.next()) {
-        const TileGeom g = walk.geom(P);
+        const TileGeom g = walk.geom(P, fold);
         bool valid;
         int n;
         long long hw;  // pixel index inside the image
@@ -995,9 +999,13 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
   const int smem_bytes = kHdrBytes + kp.nst * kp.stage_bytes + kp.nest * kp.nE * e_slot_bytes(kp.Nc) + (int)kp.slab_bytes;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+      e = cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
     if (e != cudaSuccess) {
       cg_set_error("cg_conv2d: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return CG_ERR_CUDA;
@@ -1052,7 +1060,9 @@ extern "C" int cg_conv2d(const cg_conv_args* a, void* stream) {
   cfg.numAttrs = pdl ? 1 : 0;
   bool dual = false;
   for (int s = 0; s < a->nseg; ++s) dual = dual || a->seg[s].act_copy != nullptr;
-  cudaError_t le = dual ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, kp) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, kp);
+  cudaError_t le;
+  if (kp.fold) le = dual ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, kp) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true>, kp);
+  else le = dual ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, kp) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false>, kp);
   if (le != cudaSuccess) {
     cg_set_error("cg_conv2d: launch failed: %s", cudaGetErrorString(le));
     return CG_ERR_CUDA;
