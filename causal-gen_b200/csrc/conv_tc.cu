@@ -32,8 +32,12 @@
 // The kernel is launched with programmatic stream serialization: everything before griddepcontrol.wait (barriers,
 // TMEM allocation, bias, weight-slab request) overlaps the tail of the previous kernel in the stream.
 //
-// Warp roles: 0-7 epilogue (TMEM lane quarter = warp & 3, column half = warp >> 2), 8 MMA issuer (even tiles) + TMEM owner,
-//             9 TMA producer (even tiles), 10-13 transform, 14 MMA issuer (odd tiles), 15 TMA producer (odd tiles).
+//   folded mode (template parameter FOLD, KParams::fold): wide-input 3x3 layers with <= 32 outputs put the three kernel
+//               COLUMNS on the GEMM-N axis (tile = 8 rows x 16 px, 3 MMAs per K-block, shuffle-add epilogue).
+//
+// Warp roles: 0-15 epilogue (TMEM lane quarter = warp & 3, 16-column chunk = warp >> 2; chunk-less ones join the transform
+//             role), 16 MMA issuer (even tiles) + TMEM owner, 17 TMA producer (even tiles), 18-21 transform, 22 MMA issuer
+//             (odd tiles), 23 TMA producer (odd tiles).
 #include <cuda.h>
 
 #include <cstdlib>
