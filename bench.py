@@ -289,16 +289,18 @@ def _oracle():
     return O, R
 
 
-def cpu_train_step_time(name, sd_cpu, batch, budget_s, threads):
+def cpu_train_step_time(name, sd_cpu, batch, budget_s, threads, steps=None, warmup=1):
     """the reference's CPU implementation of the step on the host cores: the staged reference itself when
-    baseline/_ref exists (kind "reference"), else the oracle port (kind "port")"""
+    baseline/_ref exists (kind "reference"), else the oracle port (kind "port").  steps / warmup: time exactly that many
+    steps (the --impl reference arm); budget_s then only stops a run that would take longer (at least 2 steps)"""
     O, R = _oracle()
+    tk = dict(warmup=warmup) if steps is None else dict(warmup=warmup, min_steps=min(2, steps), max_steps=steps)
     torch.set_num_threads(threads)
     cfg = O.make_cfg(name)
     x8, pa, _ = O.synthetic_batch(cfg, batch, seed=3)
     if R.available() and name in R.FLAGS:
         st = R.RefTrainStep(name, "cpu")
-        sec, n = R.time_steps(lambda: st(x8, pa), lambda: None, budget_s)
+        sec, n = R.time_steps(lambda: st(x8, pa), lambda: None, budget_s, **tk)
         return sec, n, "reference"
     sd = {k: v.clone().float().requires_grad_(True) for k, v in sd_cpu.items()}
     ema = {k: v.detach().clone() for k, v in sd.items()}
@@ -308,7 +310,7 @@ def cpu_train_step_time(name, sd_cpu, batch, budget_s, threads):
     def fn():
         step[0] += 1
         O.train_step_cpu(sd, cfg, x, pa_full, O.NoiseTape(seed=step[0]), state, lr=1e-3, wd=0.05, step=step[0], ema=ema)
-    sec, n = R.time_steps(fn, lambda: None, budget_s)
+    sec, n = R.time_steps(fn, lambda: None, budget_s, **tk)
     return sec, n, "port"
 
 
@@ -379,17 +381,20 @@ def run_reference(args):
         sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
     threads = os.cpu_count() or 1
     bs = args.cpu_batch
-    sec, n, kind = cpu_train_step_time(args.config, sd, bs, budget_s=max(10.0, 4.0 * args.steps), threads=threads)
+    # exactly --warmup untimed and --steps timed steps, each one batch of `bs` images (the bounded sample of the workload);
+    # a 150 s budget only cuts a run short that would not end within a few minutes (the line reports what was timed)
+    sec, n, kind = cpu_train_step_time(args.config, sd, bs, budget_s=150.0, threads=threads, steps=max(1, args.steps),
+                                       warmup=max(1, args.warmup))
     val = bs / sec
     what = ("unmodified reference (baseline/_ref/src: vae.py HVAE + trainer.py step body) on the host CPUs"
             if kind == "reference" else "reference algorithm restated in oracle/ (torch CPU fp32)")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
-            "steps": n, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "steps": n, "warmup": max(1, args.warmup), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.config} HVAE ELBO train step (fwd+bwd+clip+AdamW+EMA), CPU batch {bs}",
                        "note": what},
             "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": kind,
-                             "sample": f"{n} timed steps of batch {bs} after 1 warm-up"},
+                             "sample": f"{n} timed steps of batch {bs} after {max(1, args.warmup)} warm-up (median step time)"},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
