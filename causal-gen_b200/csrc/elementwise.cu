@@ -551,7 +551,7 @@ extern "C" int cg_avgpool_bwd(const void* dy, void* dx, int32_t N, int32_t H, in
   CG_REQUIRE(d >= 1 && d <= H && H == W, "cg_avgpool_bwd: H=%d W=%d d=%d", H, W, d);
   CG_REQUIRE(C % 8 == 0 && dy_ld % 8 == 0 && dx_ld % 8 == 0, "cg_avgpool_bwd: C/ld multiples of 8");
   const int Po = pad_to > 0 ? pad_to : H / d;
-  if (!accumulate && H % d == 0 && W % d == 0) {
+  if (!accumulate && H % d == 0 && W % d == 0 && Po == H / d) {  // (a padded gradient plane keeps the general kernel)
     avgpool_bwd_exact_kernel<<<dim3(cg_ceil_div((H / d) * (W / d), 256), C / 8, N), 256, 0, cg_stream(stream)>>>(
         reinterpret_cast<const bf16*>(dy), reinterpret_cast<bf16*>(dx), H, W, d, dy_ld, dx_ld, Po);
     CG_LAUNCH_CHECK("cg_avgpool_bwd");

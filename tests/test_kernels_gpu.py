@@ -351,7 +351,7 @@ def test_conv_centre_tap_on_1x1_image():
     assert dw[:, :, 0, 0].abs().max().item() == 0.0
 
 
-@pytest.mark.parametrize("cin,R,cout", [(1, 32, 16), (3, 32, 16), (1, 48, 32)])
+@pytest.mark.parametrize("cin,R,cout", [(1, 32, 16), (3, 32, 16), (1, 48, 32), (1, 28, 16)])  # 28: not a multiple of the tile
 def test_stem(cin, R, cout):
     from causalgen_b200 import _lib as L
     lib = L.load()
@@ -400,6 +400,13 @@ def test_pool_and_upsample():
     y8 = torch.ones(N, C // 8, 8, 8, 8, device=DEV, dtype=torch.bfloat16)
     L.check(lib.cg_avgpool_fwd(x14.data_ptr(), y8.data_ptr(), N, 14, 14, C, 2, ns_of(x14), ns_of(y8), 8, stream()))
     assert_close(to_nchw(y8, C), F.pad(F.avg_pool2d(to_nchw(x14, C), 2, 2), [0, 1, 0, 1]), 1e-2, "pool+pad")
+    # ... and its gradient: the 8x8 gradient plane's last row / column (the padding) reaches no input pixel
+    dy8 = nhwc_bf16(rnd(N, C, 8, 8, seed=9))
+    dx14 = torch.ones_like(x14)
+    L.check(lib.cg_avgpool_bwd(dy8.data_ptr(), dx14.data_ptr(), N, 14, 14, C, 2, ns_of(dy8), ns_of(dx14), 8, 0, stream()))
+    xr14 = to_nchw(x14, C).requires_grad_(True)
+    F.pad(F.avg_pool2d(xr14, 2, 2), [0, 1, 0, 1]).backward(to_nchw(dy8, C))
+    assert_close(to_nchw(dx14, C), xr14.grad, 1e-2, "pool+pad bwd")
     # F.avg_pool2d floors: an 8x8 map (7 zero-padded to 8) pooled by 7 -> 1x1 over the top-left 7x7 window
     x8 = nhwc_bf16(rnd(N, C, 8, 8, seed=7))
     y1 = zeros(1)
