@@ -206,7 +206,7 @@ def test_stream_plan_respects_fork_join_and_side_dependencies():
     # index:      0        1             2                 3           4              5        6
     prog = [L(0), L(0), Marker("fork"), L(1, side=True), L(1), Marker("join"), L(0), L(0, side=True), L(0)]
     launches = [i for i, ln in enumerate(prog) if not isinstance(ln, Marker)]
-    for n_sides in (1, 2, 3):
+    for n_sides in (1, 2, 3, 6):   # 6 = the default pool width (engine.SIDE_STREAMS)
         plan = plan_streams(prog, n_sides)
         done_sets, final = _happens_before([a if a[0] != "launch" else ("launch", a[1], launches.index(a[2])) for a in plan],
                                           len(launches))
@@ -221,7 +221,7 @@ def test_stream_plan_respects_fork_join_and_side_dependencies():
     # that fork must still see the main-stream work issued in between (latent backward -> posterior weight gradient)
     prog = [Marker("fork"), L(1), Marker("join"), L(0), Marker("fork"), L(1, side=True), L(1), Marker("join"), L(0)]
     launches = [i for i, ln in enumerate(prog) if not isinstance(ln, Marker)]
-    for n_sides in (1, 2):
+    for n_sides in (1, 2, 6):
         plan = plan_streams(prog, n_sides)
         done_sets, final = _happens_before([a if a[0] != "launch" else ("launch", a[1], launches.index(a[2])) for a in plan],
                                           len(launches))
@@ -229,6 +229,49 @@ def test_stream_plan_respects_fork_join_and_side_dependencies():
         assert {a1, m} <= done_sets[w], "pool launch after the second fork must wait for the main work before it"
         assert {a1, m} <= done_sets[a2] and a2 in done_sets[tail]
         assert final == set(range(5))
+
+
+def test_launch_policies_on_the_recorded_programs():
+    """the two scheduling policies as they land in the launch arguments of real programs (built on the CPU, nothing runs):
+    column-folded convs exactly on the layers ops.fold_pays names, cg_wgrad_args.min_tiles from ops.wgrad_min_tiles"""
+    code = r"""
+import os, sys
+os.environ["CAUSALGEN_B200_TRACE_ONLY"] = "1"
+sys.path.insert(0, os.path.join(%r, "causal-gen_b200")); sys.path.insert(0, os.path.join(%r, "oracle"))
+import torch, hvae_oracle as O
+import causalgen_b200._lib as L
+from causalgen_b200 import HVAE
+class Fake:
+    def __init__(self, real): self.real = real
+    def __getattr__(self, n):
+        if n in ("cg_conv_nchunk", "cg_conv_nchunk_ex", "cg_packed_weight_bytes", "cg_packed_weight_bytes_nc", "cg_version",
+                 "cg_last_error", "cg_conv_fold_ok", "cg_conv2d_wgrad_launches"): return getattr(self.real, n)
+        return lambda *a: 0
+L._lib = Fake(L.load())
+for name, light in (("ukbb192", True), ("morphomnist", False)):
+    cfg = O.make_cfg(name); m = HVAE(cfg)
+    prog = m.engine().build_elbo(1, True, False)
+    folded, plain = set(), set()
+    for ln in prog.launches:
+        nm = getattr(ln, "name", "")
+        if nm == "cg_conv2d":
+            a = ln.keep[0]
+            K = sum(a.src[s].C for s in range(a.nsrc))
+            if a.ksize == 3 and a.cout <= 32 and K >= 2 * a.cout:
+                (folded if a.fold else plain).add((a.H, K >= 64))
+            else:
+                assert a.fold == 0
+        elif nm == "cg_conv2d_wgrad":
+            assert ln.keep[0].min_tiles == (24 if light else 48), (name, ln.keep[0].min_tiles)   # 17*sqrt(1) clamps to 24
+    if light:
+        assert folded == {(192, True), (96, True), (24, True)}, folded      # wide K where the tile count stays within 20 %%
+        assert (48, True) in plain and (192, False) in plain, plain          # 48^2: 24 against 18 tiles; 32 -> 8: two K-blocks
+    else:
+        assert not folded or all(k for _, k in folded)
+print("ok")
+""" % (ROOT, ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
 
 
 @pytest.mark.parametrize("name", ["tiny_ukbb", "tiny_morphomnist", "tiny_cmnist", "morphomnist", "cmnist", "ukbb192",
